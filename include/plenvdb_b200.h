@@ -1,0 +1,256 @@
+/*
+ * plenvdb_b200.h — C-ABI of the B200-native PlenVDB hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns an int status
+ * (0 = ok; pvdb_last_error() holds the message otherwise) and never throws.  No torch types.
+ * All work is enqueued on the caller's CUDA stream (a `cudaStream_t` passed as void*); entry points
+ * whose name ends in `_host` take HOST pointers (the reference's numpy contract), stage through
+ * stream-ordered scratch and return after synchronising that stream.  Everything else takes DEVICE
+ * pointers, performs no allocation and no synchronisation, and is CUDA-graph capturable.
+ *
+ * Citations are to the reference tree (wolfball/PlenVDB), relative to its root:
+ *   B1  plenvdb/lib/vdb/plenvdb.cpp:3-172   (pybind11 module `plenvdb`)
+ *   B2  plenvdb/lib/cuda/render_utils.cpp:170-184 (torch ext `render_utils_cuda`)
+ * The Python mirror of both lives in plenvdb_b200/plenvdb.py and plenvdb_b200/render_utils_cuda.py.
+ */
+#ifndef PLENVDB_B200_H
+#define PLENVDB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVDB_OK 0
+#define PVDB_ERR_ARG 1
+#define PVDB_ERR_CUDA 2
+#define PVDB_ERR_STATE 3
+
+/* Thread-local message of the last failing call. */
+const char* pvdb_last_error(void);
+/* ABI version, bumped when a signature changes. */
+int pvdb_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * T1/T2 — sparse tree.  Same 5-4-3 hierarchy, same child/voxel offset functions and the same leaf
+ * order as the NanoVDB grid the reference builds (openvdb/nanovdb/nanovdb/NanoVDB.h:2185-2203,
+ * 3098-3127, 3426-3445, 3893-3900; util/OpenToNanoVDB.h:521-533), re-laid out for the GPU:
+ * one topology shared by value/grad/exp_avg/exp_avg_sq planes, int32 child tables, and payload
+ * planes that are plain leaf-major arrays  plane[leaf][512][C]  (C = 1 density, C = 12 colour).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pvdb_tree {
+    int32_t n_upper;             /* root tiles that have a child (32^3 x 16^3 x 8^3 = 4096^3 voxels each) */
+    int32_t n_lower;             /* 16^3-leaf internal nodes */
+    int32_t n_leaf;              /* 8^3-voxel leaves */
+    int32_t reserved;
+    uint64_t root_key0;          /* key of root tile 0 (NanoVDB.h:2702-2709), fast path for n_upper==1 */
+    const uint64_t* root_keys;   /* [n_upper]  device */
+    const int32_t* upper_child;  /* [n_upper][32768] -> lower index or -1   device */
+    const int32_t* lower_child;  /* [n_lower][4096]  -> leaf index or -1    device */
+    const int32_t* leaf_origin;  /* [n_leaf][3]                              device */
+    const uint64_t* leaf_mask;   /* [n_leaf][8] value mask, bit n = word n>>6, bit n&63 (NanoVDB.h:1902) */
+} pvdb_tree;
+
+/* Host-side topology builder (opaque).  Replaces OpenVDB denseFill + openToNanoVDB
+ * (plenvdb/lib/vdb/plenvdb.h:117-125, 197-210) and copyFromDense/pruned topologies. */
+typedef struct pvdb_topo pvdb_topo;
+/* denseFill(bbox [0,r-1]^3, 0, active=true): every 8^3 block touching the box is a leaf. */
+pvdb_topo* pvdb_topo_create_dense(int rx, int ry, int rz);
+/* Leaves where any voxel of `active` (host, uint8[rx*ry*rz], C order x-major) is set; value mask = active. */
+pvdb_topo* pvdb_topo_create_from_mask(const uint8_t* active, int rx, int ry, int rz);
+void pvdb_topo_destroy(pvdb_topo*);
+int pvdb_topo_counts(const pvdb_topo*, int32_t* n_upper, int32_t* n_lower, int32_t* n_leaf);
+/* Fill caller-provided HOST arrays (sizes as in pvdb_tree). */
+int pvdb_topo_export(const pvdb_topo*, uint64_t* root_keys, int32_t* upper_child, int32_t* lower_child,
+                     int32_t* leaf_origin, uint64_t* leaf_mask);
+
+/* ------------------------------------------------------------------------------------------------
+ * D1/D2/C1/C2 — trilinear sample forward / gradient scatter (densityvdb.cu:101-181, colorvdb.cu:81-175).
+ * Coordinates are index-space floats, SoA.  `channels` = 1 -> density arithmetic (densityvdb.cu:116-123),
+ * channels % 3 == 0 -> colour arithmetic (colorvdb.cu:16-26, 100-107).  corner_leaf/corner_off are
+ * optional [n][8] outputs (leaf index or -1, voxel offset) in the reference's corner order.
+ * ---------------------------------------------------------------------------------------------- */
+int pvdb_sample_forward(const pvdb_tree* tree, const float* plane, int channels,
+                        const float* xs, const float* ys, const float* zs, int64_t n,
+                        float* out, int32_t* corner_leaf, int32_t* corner_off, void* stream);
+int pvdb_sample_backward(const pvdb_tree* tree, float* grad_plane, int channels,
+                         const float* xs, const float* ys, const float* zs, const float* grad_out,
+                         int64_t n, void* stream);
+/* Host-pointer variants honouring B1's numpy contract (plenvdb.h:441-485, 535-573). */
+int pvdb_sample_forward_host(const pvdb_tree* tree, const float* plane, int channels,
+                             const float* xs, const float* ys, const float* zs, int64_t n,
+                             float* out, void* stream);
+int pvdb_sample_backward_host(const pvdb_tree* tree, float* grad_plane, int channels,
+                              const float* xs, const float* ys, const float* zs, const float* grad_out,
+                              int64_t n, void* stream);
+/* forward_single (densityvdb.cu:376-390, colorvdb.cu:380-399; colour starts from 0, not from
+ * uninitialised memory as the reference does). */
+int pvdb_sample_nearest(const pvdb_tree* tree, const float* plane, int channels,
+                        const int32_t* is, const int32_t* js, const int32_t* ks, int64_t n,
+                        float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * O1/O2/O3 — sparse Adam, zero_grad, dense <-> sparse (densityvdb.cu:31-97, 185-368; colorvdb.cu:42-77,
+ * 179-371; host scalars plenvdb.h:751-767).
+ * mode 0 = all active voxels, 1 = skip zero grad (colour: skip when all 3 comps of a Vec3 are 0),
+ * 2 = multiply by per-voxel lr (perlr plane [n_leaf][512]).
+ * ---------------------------------------------------------------------------------------------- */
+float pvdb_adam_stepsize(float lr, float beta0, float beta1, int step);   /* plenvdb.h:753 in float */
+int pvdb_adam_step(const pvdb_tree* tree, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   int channels, int mode, float stepsz, float eps, float beta0, float beta1,
+                   const float* perlr, void* stream);
+int pvdb_zero_grad(const pvdb_tree* tree, float* grad, int channels, void* stream);
+/* dense layout [rx][ry][rz][channels] C order (plenvdb.h:149-157, 241-250). */
+int pvdb_copy_from_dense(const pvdb_tree* tree, float* plane, int channels, const float* dense,
+                         int rx, int ry, int rz, void* stream);
+int pvdb_copy_to_dense(const pvdb_tree* tree, const float* plane, int channels, float* dense,
+                       int rx, int ry, int rz, void* stream);
+int pvdb_set_values_on_by_mask(const pvdb_tree* tree, float* plane, const uint8_t* mask, float val,
+                               int rx, int ry, int rz, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * B2 — render_utils ops on raw device pointers (plenvdb/lib/cuda/render_utils_kernel.cu).
+ * int64 outputs keep the reference's tensor dtypes.
+ * ---------------------------------------------------------------------------------------------- */
+int pvdb_infer_t_minmax(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max,
+                        float near, float far, int n_rays, float* t_min, float* t_max, void* stream);   /* :12-35 */
+int pvdb_infer_n_samples(const float* rays_d, const float* t_min, const float* t_max, float stepdist,
+                         int n_rays, int64_t* n_samples, void* stream);                                  /* :38-55 */
+int pvdb_infer_ray_start_dir(const float* rays_o, const float* rays_d, const float* t_min, int n_rays,
+                             float* rays_start, float* rays_dir, void* stream);                          /* :58-79 */
+/* sample_pts_on_rays (:196-242) in two phases because the output length is data dependent:
+ * count -> (caller reads n_steps_cumsum[n_rays-1], allocates) -> fill. */
+int pvdb_sample_pts_count(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max,
+                          float near, float far, float stepdist, int n_rays,
+                          float* t_min, float* t_max, int64_t* n_steps, int64_t* n_steps_cumsum,
+                          float* rays_start, float* rays_dir, void* stream);
+int pvdb_sample_pts_fill(const float* rays_start, const float* rays_dir, const float* xyz_min, const float* xyz_max,
+                         const int64_t* n_steps_cumsum, float stepdist, int n_rays, int64_t total_len,
+                         float* rays_pts, uint8_t* mask_outbbox, int64_t* ray_id, int64_t* step_id, void* stream);
+int pvdb_maskcache_lookup(const uint8_t* world, const float* xyz, uint8_t* out, const float* xyz2ijk_scale,
+                          const float* xyz2ijk_shift, int sz_i, int sz_j, int sz_k, int64_t n_pts, void* stream); /* :374-424 */
+int pvdb_raw2alpha(const float* density, float shift, float interval, int64_t n_pts, float* exp_d, float* alpha,
+                   void* stream);                                                                                  /* :431-481 */
+int pvdb_raw2alpha_backward(const float* exp_d, const float* grad_back, float interval, int64_t n_pts, float* grad,
+                            void* stream);                                                                         /* :507-552 */
+/* alpha2weight (:577-651): weight/T/alphainv_last/i_start/i_end must be pre-initialised by the caller to
+ * 0/1/1/0/0 exactly as the reference's host wrapper does (:625-629). */
+int pvdb_alpha2weight(const float* alpha, const int64_t* ray_id, int64_t n_pts, int n_rays, float* weight, float* T,
+                      float* alphainv_last, int64_t* i_start, int64_t* i_end, void* stream);
+int pvdb_alpha2weight_backward(const float* alpha, const float* weight, const float* T, const float* alphainv_last,
+                               const int64_t* i_start, const int64_t* i_end, int n_rays, const float* grad_weights,
+                               const float* grad_last, float* grad, void* stream);                                 /* :654-707 */
+/* adam_upd_cuda (plenvdb/lib/cuda/adam_upd_kernel.cu:9-132): mode 0 plain, 1 masked, 2 per-lr. */
+int pvdb_dense_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr,
+                    int64_t n, int mode, int step, float beta1, float beta2, float lr, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Occupancy bits for the fused paths: mask_cache.mask (plenvdb/lib/grid.py:207-246) as a two-level
+ * bit hierarchy.  fine[(bx*nby+by)*nbz+bz][8] holds the 512 voxel bits of an 8^3 block in the leaf's
+ * own bit order; coarse has one bit per block (block index / 64, % 64).
+ * ---------------------------------------------------------------------------------------------- */
+int pvdb_occ_build(const uint8_t* mask, int rx, int ry, int rz, uint64_t* fine, uint64_t* coarse, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused fine-stage training step (new entry point B1/B2 callers can opt into).  Restates
+ * DirectVoxGO.forward (plenvdb/lib/dvgo.py:296-388) + the losses and optimiser calls of
+ * plenvdb/run.py:541-588 as a fixed sequence of kernels on one stream, no host sync.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pvdb_train_cfg {
+    /* scene */
+    float xyz_min[3], xyz_max[3];
+    int32_t reso[3];                 /* world_size */
+    int32_t mask_reso[3];            /* mask_cache.mask shape */
+    float mask_scale[3], mask_shift[3]; /* xyz2ijk_scale / shift (grid.py:229-231), computed by the caller */
+    /* render kwargs */
+    float near, far, stepdist, act_shift, interval, fast_color_thres, bg;
+    /* loss weights (run.py:551-574) */
+    float weight_main, weight_entropy_last, weight_rgbper;
+    /* optimiser scalars; *_stepsz are the plenvdb.h:753 values for this step; rgbnet follows adam_upd_kernel.cu:72 */
+    float den_stepsz, k0_stepsz, eps, beta0, beta1;
+    int32_t den_mode, k0_mode;       /* the fused update implements stepmode 1 (fine stage, configs/default.py:77) */
+    float net_lr; int32_t net_step;  /* rgbnet MaskedAdam: lr and step (>=1) of this iteration */
+    int32_t k0_dim;                  /* 12 */
+    int32_t net_width;               /* 128 */
+    int32_t use_tensor_cores;        /* 1 = tcgen05 rgbnet, 0 = fp32 CUDA-core rgbnet */
+    int32_t n_rays_global;           /* N in the means of the losses (== n_rays on one GPU; world*n_rays when sharded) */
+    int32_t parity_counts;           /* 1: also produce the reference's untrimmed per-ray M2 counts (cnt_alpha_full) */
+} pvdb_train_cfg;
+
+typedef struct pvdb_train_bufs {
+    /* grids: one topology, congruent planes */
+    const pvdb_tree* tree;
+    float *den, *den_grad, *den_m, *den_v;     /* [n_leaf][512] */
+    float *k0, *k0_grad, *k0_m, *k0_v;         /* [n_leaf][512][12] */
+    const uint64_t *occ_fine, *occ_coarse;     /* pvdb_occ_build */
+    /* rgbnet params, PyTorch nn.Linear layout packed as w0[128][39] b0[128] w1[128][128] b1[128] w2[3][128] b2[3]
+     * (22019 floats); grad/m/v use the same packing. */
+    float *net, *net_grad, *net_m, *net_v;
+    /* per-ray scratch [n_rays] */
+    float *t_min, *t_max; int32_t* n_steps;
+    int32_t *cnt_mask, *cnt_alpha, *cnt_keep, *cnt_alpha_full;  /* M1 (up to the stop), trimmed M2, M3, full M2 */
+    int32_t *off_alpha, *off_keep;             /* exclusive scans = segment offsets, [n_rays+1] */
+    float *alphainv_last, *rgb_marched /*[n_rays][3]*/, *grad_last;
+    /* alpha list: one entry per sample with alpha > thres up to the early stop, ray order; capacity cap_alpha */
+    int64_t cap_alpha, cap_keep;
+    int32_t *s_ray, *s_step;
+    float *s_xyz /*[.][3] index-space coords*/, *s_density, *s_alpha, *s_T, *s_weight, *s_gden;
+    /* kept list: entries with weight > thres; capacity cap_keep */
+    int32_t *k_sample /* index into the alpha list */, *k_ray;
+    float *k_xyz /*[.][3]*/, *k_feat /*[.][12]*/, *k_rgb /*[.][3] rgb, then dL/dlogit*/, *k_gw /*[.] dL/dweight*/;
+    float *k_h0, *k_h1;                        /* [.][128] activations kept for the fp32 backward (NULL with tensor cores) */
+    /* touched-leaf bookkeeping, [n_leaf] each */
+    int32_t *den_touched, *k0_touched, *den_touched_list, *k0_touched_list;
+    int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0 */
+    float *loss;                               /* [4]: total, mse, entropy_last, rgbper */
+} pvdb_train_bufs;
+
+#define PVDB_PHASE_FORWARD 1    /* sample, interpolate, rgbnet, composite (+ losses when target != NULL) */
+#define PVDB_PHASE_BACKWARD 2   /* gradients into den_grad / k0_grad / net_grad (accumulating, like autograd) */
+#define PVDB_PHASE_UPDATE 4     /* sparse Adam on touched leaves + rgbnet Adam; clears the gradients it consumed */
+int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs,
+                    const float* rays_o, const float* rays_d, const float* viewdirs, const float* target,
+                    int n_rays, int phases, void* stream);
+/* Number of this library's kernel launches enqueued by the last pvdb_train_step / pvdb_render call on this thread. */
+int pvdb_last_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * R1/R2 — merged-VDB renderer (plenvdb/lib/vdb/renderer.cu:370-424, plenvdb.h:933-1068).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pvdb_render_cfg {
+    int32_t reso[3];
+    float K[9];
+    float xyz_min[3], xyz_max[3];
+    float near, far, stepdist, act_shift, interval, fast_color_thres, bg;
+    int32_t inverse_y, H, W;
+    int32_t dcol, dpe, dhid, dout;   /* 12, 27, 128, 3 */
+    int32_t use_tensor_cores;
+} pvdb_render_cfg;
+
+typedef struct pvdb_render_bufs {
+    const pvdb_tree* idx_tree;       /* merged index grid */
+    const float* idx_plane;          /* [n_leaf][512] 1-based row ids stored as float (vdb_compression.py:31-33) */
+    const float* dendata;            /* [N+1] */
+    const float* coldata;            /* [N+1][12] */
+    const float *w0, *b0, *w1, *b1, *w2, *b2;  /* transposed layout of run.py:98-104: w0[39][128], w1[128][128], w2[128][3] */
+    /* scratch sized for rows [row_begin,row_end) */
+    int32_t *n_samples, *i_starts;   /* [rows*W], [rows*W+1] */
+    float *tmins, *tmaxs;            /* [rows*W] */
+    int64_t cap_samples;
+    int32_t *s_ray; float *s_weight; float *s_feat; /* [cap][..] */
+    int32_t *counters;               /* [8] */
+} pvdb_render_bufs;
+
+int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bufs* bufs, const float* c2w /* device [16] */,
+                     int row_begin, int row_end, float* out_rgb /* device [(row_end-row_begin)*W*3] */,
+                     void* stream);
+/* Device-side merge (vdb_compression.py:19-59): see plenvdb_b200/merge.py for the host orchestration. */
+int pvdb_merge_gather(const pvdb_tree* tree, const float* den, const float* k0, int k0_dim,
+                      const uint8_t* mask, const int32_t* row_of_voxel /* [rx*ry*rz] 1-based or 0 */,
+                      int rx, int ry, int rz, float* dendata, float* coldata, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLENVDB_B200_H */

@@ -1,0 +1,117 @@
+// common.cuh — device-side tree lookup, exact-rounding math helpers and error plumbing shared by all
+// kernels of libplenvdb_b200.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/plenvdb_b200.h"
+
+#define PVDB_SMS 148          // B200 SM count; grids are sized in multiples of it
+#define PVDB_LEAF_VOX 512
+
+void pvdb_set_error(const char* fmt, ...);
+void pvdb_count_launch(int n = 1);
+void pvdb_reset_launch_count();
+
+#define PVDB_CHECK_ARG(cond, msg)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            pvdb_set_error("%s: %s", __func__, msg); \
+            return PVDB_ERR_ARG;                  \
+        }                                         \
+    } while (0)
+
+#define PVDB_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            pvdb_set_error("%s: %s (%s:%d)", __func__, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return PVDB_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+
+// After a launch: surface configuration errors without synchronising.
+#define PVDB_LAUNCH_CHECK()                                                              \
+    do {                                                                                 \
+        pvdb_count_launch();                                                             \
+        cudaError_t e__ = cudaPeekAtLastError();                                         \
+        if (e__ != cudaSuccess) {                                                        \
+            pvdb_set_error("%s: launch failed: %s (%s:%d)", __func__, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return PVDB_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+
+static inline int pvdb_grid_for(int64_t n, int block) {
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tree lookup.  Offsets follow NanoVDB.h: root key :2702-2709, upper CoordToOffset (LOG2DIM 5, child
+// TOTAL 7) :3377-3385, lower (LOG2DIM 4, child TOTAL 3), leaf :3893-3900.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pvdb_root_key(int x, int y, int z) {
+    return (uint64_t)((uint32_t)z >> 12) | ((uint64_t)((uint32_t)y >> 12) << 21) | ((uint64_t)((uint32_t)x >> 12) << 42);
+}
+__device__ __forceinline__ int pvdb_upper_off(int x, int y, int z) {
+    return (((x & 4095) >> 7) << 10) | (((y & 4095) >> 7) << 5) | ((z & 4095) >> 7);
+}
+__device__ __forceinline__ int pvdb_lower_off(int x, int y, int z) {
+    return (((x & 127) >> 3) << 8) | (((y & 127) >> 3) << 4) | ((z & 127) >> 3);
+}
+__device__ __forceinline__ int pvdb_leaf_off(int x, int y, int z) {
+    return ((x & 7) << 6) | ((y & 7) << 3) | (z & 7);
+}
+
+// Leaf index containing (x,y,z) or -1.  Top-down like ReadAccessor::getValue on a cold cache
+// (NanoVDB.h:2924-2948 findTile, :2998-3010, :3327-3335) but over int32 tables.
+__device__ __forceinline__ int pvdb_find_leaf(const pvdb_tree& t, int x, int y, int z) {
+    const uint64_t key = pvdb_root_key(x, y, z);
+    int u = 0;
+    if (key != t.root_key0) {
+        u = -1;
+        for (int i = 1; i < t.n_upper; ++i)
+            if (__ldg(t.root_keys + i) == key) { u = i; break; }
+        if (u < 0) return -1;
+    } else if (t.n_upper == 0) {
+        return -1;
+    }
+    const int l = __ldg(t.upper_child + (size_t)u * 32768 + pvdb_upper_off(x, y, z));
+    if (l < 0) return -1;
+    return __ldg(t.lower_child + (size_t)l * 4096 + pvdb_lower_off(x, y, z));
+}
+
+// One-entry leaf cache, the register-resident analogue of ReadAccessor's leaf-level key (NanoVDB.h:4514-4749).
+struct PvdbLeafCache {
+    int kx, ky, kz, leaf;
+    __device__ __forceinline__ PvdbLeafCache() : kx(INT32_MIN), ky(0), kz(0), leaf(-1) {}
+    __device__ __forceinline__ int find(const pvdb_tree& t, int x, int y, int z) {
+        if ((((x ^ kx) | (y ^ ky) | (z ^ kz)) & ~7) == 0) return leaf;
+        kx = x & ~7; ky = y & ~7; kz = z & ~7;
+        leaf = pvdb_find_leaf(t, x, y, z);
+        return leaf;
+    }
+};
+
+__device__ __forceinline__ bool pvdb_mask_bit(const uint64_t* leaf_mask, int leaf, int off) {
+    return (__ldg(leaf_mask + (size_t)leaf * 8 + (off >> 6)) >> (off & 63)) & 1ull;
+}
+
+// The reference's corner walk (densityvdb.cu:116-123): 000,001,011,010,110,111,101,100 as (dx,dy,dz).
+__device__ __constant__ const int8_t PVDB_CORNER[8][3] = {
+    {0, 0, 0}, {0, 0, 1}, {0, 1, 1}, {0, 1, 0}, {1, 1, 0}, {1, 1, 1}, {1, 0, 1}, {1, 0, 0}};
+
+// Per-corner weight factors in the reference's multiplication order: w = f0 * f1 * f2 with
+// f_axis = (d_axis ? u : 1-u).
+struct PvdbTri {
+    int i, j, k;
+    float u[3], m[3];   // u = frac, m = 1-u (sub.f32 as compiled from `1-uvw[a]`)
+    __device__ __forceinline__ void set(float x, float y, float z) {
+        const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+        i = (int)fx; j = (int)fy; k = (int)fz;                       // cvt.rmi then cvt.rzi.s32 (NanoVDB Floor)
+        u[0] = __fsub_rn(x, (float)i); u[1] = __fsub_rn(y, (float)j); u[2] = __fsub_rn(z, (float)k);
+        m[0] = __fsub_rn(1.0f, u[0]); m[1] = __fsub_rn(1.0f, u[1]); m[2] = __fsub_rn(1.0f, u[2]);
+    }
+    __device__ __forceinline__ float f(int axis, int d) const { return d ? u[axis] : m[axis]; }
+};

@@ -1,0 +1,20 @@
+// rgbnet.cuh — interface between the fused step and the rgbnet kernels (k0 gather + MLP forward/backward).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/plenvdb_b200.h"
+
+// Packed parameter layout (PyTorch nn.Linear, dvgo.py:99-107): w0[128][39] b0[128] w1[128][128] b1[128] w2[3][128] b2[3]
+#define PVDB_NET_DIN 39
+#define PVDB_NET_W 128
+#define PVDB_NET_OFF_W0 0
+#define PVDB_NET_OFF_B0 (PVDB_NET_OFF_W0 + PVDB_NET_W * PVDB_NET_DIN)
+#define PVDB_NET_OFF_W1 (PVDB_NET_OFF_B0 + PVDB_NET_W)
+#define PVDB_NET_OFF_B1 (PVDB_NET_OFF_W1 + PVDB_NET_W * PVDB_NET_W)
+#define PVDB_NET_OFF_W2 (PVDB_NET_OFF_B1 + PVDB_NET_W)
+#define PVDB_NET_OFF_B2 (PVDB_NET_OFF_W2 + 3 * PVDB_NET_W)
+#define PVDB_NET_N (PVDB_NET_OFF_B2 + 3)   // 22019
+
+// Forward over the kept-sample list: k_feat, k_h0, k_h1 (fp32 path), k_rgb.  Enqueues on `st`.
+int pvdb_rgbnet_forward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
+// Backward: consumes g_logit (in k_rgb), produces net_grad (zeroed first) and scatters the k0 gradient.
+int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);

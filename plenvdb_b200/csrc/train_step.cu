@@ -1,0 +1,562 @@
+// train_step.cu — fused fine-stage training step on one stream, no host synchronisation.
+//
+// Restates DirectVoxGO.forward (plenvdb/lib/dvgo.py:296-388), the losses of plenvdb/run.py:551-574,
+// autograd's backward through Alphas2Weights / Raw2Alpha / QueryVerticalInVDB (dvgo.py:408-466,
+// plenvdb/lib/grid.py:40-60) and the optimiser calls of run.py:585-588 as a fixed kernel sequence:
+//
+//   F1 k_march<COUNT>   warp per ray: t-range, N_steps, march, occupancy bits, density trilinear, alpha,
+//                       sequential transmittance with the reference's early stop  -> per-ray counts
+//   F2 k_scan_counts    exclusive scans -> segment offsets (ray order, deterministic)
+//   F3 k_march<EMIT>    same march, writes the compacted sample lists
+//   F4 k_rgbnet_fwd     k0 trilinear (12 ch) + view PE + MLP + sigmoid, 64-sample tiles
+//   F5 k_composite      per-ray compositing, losses, dL/d(rgb_marched), dL/d(alphainv_last), dL/d(rgb), dL/d(w)
+//   B1 k_rgbnet_bwd     MLP backward, weight-gradient partials in registers, k0 gradient scatter
+//   B2 k_ray_bwd        per-ray reverse cumprod backward + raw2alpha backward
+//   B3 k_density_scatter density gradient scatter
+//   U1 k_touched_compact / k_sparse_adam  Adam over touched leaves only, gradients cleared in the same pass
+//   U2 k_dense_adam     rgbnet parameters
+//
+// The per-sample arithmetic is shared with the drop-in ops through ray_math.cuh / common.cuh, so sample
+// counts, segment offsets and voxel indices are the reference's bit for bit.
+#include "common.cuh"
+#include "ray_math.cuh"
+#include "rgbnet.cuh"
+
+namespace {
+
+constexpr int CNT_M_ALPHA = 0, CNT_M_KEEP = 1, CNT_N_TOUCHED_DEN = 2, CNT_OVERFLOW = 3, CNT_N_TOUCHED_K0 = 4;
+
+struct MarchParams {
+    pvdb_tree tree;
+    const float* den;
+    const uint64_t* occ_fine;
+    const uint64_t* occ_coarse;
+    float xyz_min[3], xyz_max[3];
+    float rm1[3];                 // world_size - 1 as float
+    int mask_reso[3];
+    int nb[3];                    // blocks of the occupancy bit grid
+    float mask_scale[3], mask_shift[3];
+    float near, far, stepdist, act_shift, interval, thres;
+};
+
+__device__ __forceinline__ bool occ_test(const MarchParams& P, int i, int j, int k) {
+    if (i < 0 || i >= P.mask_reso[0] || j < 0 || j >= P.mask_reso[1] || k < 0 || k >= P.mask_reso[2]) return false;
+    const int b = ((i >> 3) * P.nb[1] + (j >> 3)) * P.nb[2] + (k >> 3);
+    if (!((__ldg(P.occ_coarse + (b >> 6)) >> (b & 63)) & 1ull)) return false;   // empty 8^3 block
+    const int n = pvdb_leaf_off(i, j, k);
+    return (__ldg(P.occ_fine + (size_t)b * 8 + (n >> 6)) >> (n & 63)) & 1ull;
+}
+
+// Trilinear density at index-space (x,y,z): densityvdb.cu:101-125 arithmetic.
+__device__ __forceinline__ float density_at(const MarchParams& P, PvdbLeafCache& cache, float x, float y, float z) {
+    PvdbTri tri;
+    tri.set(x, y, z);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+        const int cx = tri.i + dx, cy = tri.j + dy, cz = tri.k + dz;
+        const int leaf = cache.find(P.tree, cx, cy, cz);
+        const float v = leaf >= 0 ? __ldg(P.den + (size_t)leaf * 512 + pvdb_leaf_off(cx, cy, cz)) : 0.f;
+        acc = __fmaf_rn(tri.f(2, dz), __fmul_rn(tri.f(1, dy), __fmul_rn(tri.f(0, dx), v)), acc);
+    }
+    return acc;
+}
+
+struct MarchOut {
+    // per ray
+    float* t_min; float* t_max; int32_t* n_steps;
+    int32_t *cnt_mask, *cnt_alpha, *cnt_keep, *cnt_alpha_full;
+    const int32_t *off_alpha, *off_keep;
+    float* alphainv_last;
+    // per sample
+    int64_t cap_alpha, cap_keep;
+    int32_t *s_ray, *s_step; float *s_xyz, *s_density, *s_alpha, *s_T, *s_weight;
+    int32_t *k_sample, *k_ray; float* k_xyz;
+    int32_t* counters;
+};
+
+// One warp per ray.  MODE 0 = count, 1 = emit.  PARITY (count only): keep marching past the early stop so the
+// full M1 / M2 counts of the reference are produced too.
+template <int MODE, bool PARITY>
+__global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
+                                               const float* __restrict__ rays_d, int n_rays) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    float o[3] = {__ldg(rays_o + r * 3), __ldg(rays_o + r * 3 + 1), __ldg(rays_o + r * 3 + 2)};
+    float d[3] = {__ldg(rays_d + r * 3), __ldg(rays_d + r * 3 + 1), __ldg(rays_d + r * 3 + 2)};
+    float tmin, tmax, st[3], dir[3];
+    pvdb_ray_t_minmax(o, d, P.xyz_min, P.xyz_max, P.near, P.far, tmin, tmax);
+    const int nsteps = (int)pvdb_ray_n_samples(d, tmin, tmax, P.stepdist);
+    pvdb_ray_start_dir(o, d, tmin, st, dir);
+
+    PvdbLeafCache cache;
+    float T_cum = 1.f;
+    bool stopped = false;
+    int n_mask = 0, n_alpha = 0, n_keep = 0, n_alpha_full = 0;
+    int64_t oa = 0, ok = 0;
+    if (MODE == 1) { oa = O.off_alpha[r]; ok = O.off_keep[r]; }
+
+    for (int base = 0; base < nsteps; base += 32) {
+        const int step = base + lane;
+        bool in_mask = false;
+        float px = 0, py = 0, pz = 0;
+        if (step < nsteps) {
+            pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, step, px, py, pz);
+            const bool outb = (P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) | (P.xyz_max[0] < px) |
+                              (P.xyz_max[1] < py) | (P.xyz_max[2] < pz);
+            if (!outb)
+                in_mask = occ_test(P, pvdb_mask_ijk(px, P.mask_scale[0], P.mask_shift[0]),
+                                   pvdb_mask_ijk(py, P.mask_scale[1], P.mask_shift[1]),
+                                   pvdb_mask_ijk(pz, P.mask_scale[2], P.mask_shift[2]));
+        }
+        const unsigned mbits = __ballot_sync(0xffffffffu, in_mask);
+        if (mbits == 0) continue;
+        n_mask += __popc(mbits);
+        float x = 0, y = 0, z = 0, dens = 0, alpha = 0;
+        bool a_ok = false;
+        if (in_mask) {
+            x = pvdb_wld2idx(px, P.xyz_min[0], P.xyz_max[0], P.rm1[0]);
+            y = pvdb_wld2idx(py, P.xyz_min[1], P.xyz_max[1], P.rm1[1]);
+            z = pvdb_wld2idx(pz, P.xyz_min[2], P.xyz_max[2], P.rm1[2]);
+            dens = density_at(P, cache, x, y, z);
+            float e;
+            alpha = pvdb_raw2alpha(dens, P.act_shift, P.interval, e);
+            a_ok = alpha > P.thres;
+        }
+        unsigned abits = __ballot_sync(0xffffffffu, a_ok);
+        n_alpha_full += __popc(abits);
+        if (stopped) continue;   // PARITY only: counting beyond the stop
+        // sequential transmittance over the set bits, identical in every lane (alpha2weight :590-601)
+        float myT = 0, myW = 0;
+        int my_ai = -1, my_ki = -1;
+        while (abits) {
+            const int b = __ffs(abits) - 1;
+            abits &= abits - 1;
+            const float a = __shfl_sync(0xffffffffu, alpha, b);
+            const float w = __fmul_rn(T_cum, a);
+            const bool keep = w > P.thres;
+            if (lane == b) { myT = T_cum; myW = w; my_ai = n_alpha; my_ki = keep ? n_keep : -1; }
+            T_cum = pvdb_T_update(T_cum, a);
+            ++n_alpha;
+            n_keep += keep;
+            if ((double)T_cum < 1e-3) { stopped = true; break; }
+        }
+        if (MODE == 1 && my_ai >= 0) {
+            const int64_t ia = oa + my_ai;
+            if (ia < O.cap_alpha) {
+                O.s_ray[ia] = r; O.s_step[ia] = step;
+                O.s_xyz[ia * 3] = x; O.s_xyz[ia * 3 + 1] = y; O.s_xyz[ia * 3 + 2] = z;
+                O.s_density[ia] = dens; O.s_alpha[ia] = alpha; O.s_T[ia] = myT; O.s_weight[ia] = myW;
+            }
+            if (my_ki >= 0) {
+                const int64_t ik = ok + my_ki;
+                if (ik < O.cap_keep && ia < O.cap_alpha) {
+                    O.k_sample[ik] = (int32_t)ia; O.k_ray[ik] = r;
+                    O.k_xyz[ik * 3] = x; O.k_xyz[ik * 3 + 1] = y; O.k_xyz[ik * 3 + 2] = z;
+                }
+            }
+        }
+        if (stopped && !PARITY) break;
+    }
+    if (MODE == 0 && lane == 0) {
+        O.t_min[r] = tmin; O.t_max[r] = tmax; O.n_steps[r] = nsteps;
+        O.cnt_mask[r] = n_mask; O.cnt_alpha[r] = n_alpha; O.cnt_keep[r] = n_keep;
+        if (PARITY) O.cnt_alpha_full[r] = n_alpha_full;
+        O.alphainv_last[r] = T_cum;
+    }
+}
+
+// Exclusive scans of the two per-ray counts; single CTA (n_rays is 8192..65536).
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck,
+                                                      int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
+                                                      int32_t* __restrict__ counters, int64_t cap_alpha, int64_t cap_keep) {
+    __shared__ int2 wsum[32];
+    __shared__ int2 carry_s;
+    if (threadIdx.x == 0) carry_s = make_int2(0, 0);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        int2 v = i < n ? make_int2(ca[i], ck[i]) : make_int2(0, 0);
+        const int2 own = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ux = __shfl_up_sync(0xffffffffu, v.x, o), uy = __shfl_up_sync(0xffffffffu, v.y, o);
+            if (lane >= o) { v.x += ux; v.y += uy; }
+        }
+        if (lane == 31) wsum[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            int2 w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ux = __shfl_up_sync(0xffffffffu, w.x, o), uy = __shfl_up_sync(0xffffffffu, w.y, o);
+                if (lane >= o) { w.x += ux; w.y += uy; }
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const int2 c = carry_s;
+        const int2 pre = wid ? wsum[wid - 1] : make_int2(0, 0);
+        const int2 incl = make_int2(v.x + pre.x + c.x, v.y + pre.y + c.y);
+        if (i < n) { oa[i] = incl.x - own.x; ok[i] = incl.y - own.y; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int2 tot = carry_s;
+        oa[n] = tot.x; ok[n] = tot.y;
+        counters[CNT_M_ALPHA] = tot.x; counters[CNT_M_KEEP] = tot.y;
+        counters[CNT_OVERFLOW] = (tot.x > cap_alpha || tot.y > cap_keep) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F5 — compositing, losses, and the first backward step (per ray; one warp per ray).
+//   rgb_marched = sum_s w*rgb + alphainv_last*bg                          (dvgo.py:365-370)
+//   loss = w_main*mse + w_ent*entropy_last + w_per*rgbper                 (run.py:551-574)
+//   g_marched = w_main*2*(marched-target)/(3N);  g_last = sum_c g_marched*bg + w_ent*(-(log p - log(1-p)))/N
+//   g_rgb = w*g_marched + w_per*2*(rgb-target)*w/N;  g_logit = g_rgb*rgb*(1-rgb);  g_w = sum_c rgb*g_marched
+// ---------------------------------------------------------------------------------------------
+struct CompositeParams {
+    const int32_t* off_keep; const int32_t* k_sample; const float* s_weight;
+    float* k_rgb;            // in: rgb[M3][3]; out (backward enabled): g_logit[M3][3]
+    float* k_gw;             // out: dL/dw per kept sample
+    const float* alphainv_last; const float* target;
+    float* rgb_marched; float* grad_last; float* loss;
+    float bg, w_main, w_ent, w_per, inv_N;   // inv_N = 1/N_global
+    int64_t cap_keep;
+    int do_backward;
+};
+__global__ void __launch_bounds__(256) k_composite(CompositeParams C, int n_rays) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    float l_mse = 0, l_ent = 0, l_per = 0;
+    if (r < n_rays) {
+        const int64_t b = C.off_keep[r], e = min((int64_t)C.off_keep[r + 1], C.cap_keep);
+        float acc[3] = {0, 0, 0};
+        for (int64_t s = b + lane; s < e; s += 32) {
+            const float w = C.s_weight[C.k_sample[s]];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] += w * C.k_rgb[s * 3 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        const float ail = C.alphainv_last[r];
+        float tg[3], gm[3], gsum = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            tg[c] = C.target ? __ldg(C.target + r * 3 + c) : 0.f;
+            const float m = acc[c] + ail * C.bg;
+            if (lane == 0) C.rgb_marched[r * 3 + c] = m;
+            const float df = m - tg[c];
+            l_mse += df * df;
+            gm[c] = C.w_main * 2.0f * df * C.inv_N * (1.0f / 3.0f);
+            gsum += gm[c];
+        }
+        const float p = fminf(fmaxf(ail, 1e-6f), 1.0f - 1e-6f);
+        const float lp = logf(p), l1p = logf(1.0f - p);
+        l_ent = -(p * lp + (1.0f - p) * l1p);
+        if (C.do_backward) {
+            float ge = 0.f;
+            if (C.w_ent > 0.f && ail >= 1e-6f && ail <= 1.0f - 1e-6f) ge = C.w_ent * (-(logf(ail) - logf(1.0f - ail))) * C.inv_N;
+            if (lane == 0) C.grad_last[r] = gsum * C.bg + ge;
+        }
+        for (int64_t s = b + lane; C.target && s < e; s += 32) {
+            const float w = C.s_weight[C.k_sample[s]];
+            float gw = 0, per = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float col = C.k_rgb[s * 3 + c];
+                const float dc = col - tg[c];
+                per += dc * dc;
+                if (C.do_backward) {
+                    const float grgb = w * gm[c] + C.w_per * 2.0f * dc * w * C.inv_N;
+                    C.k_rgb[s * 3 + c] = grgb * col * (1.0f - col);
+                    gw += col * gm[c];
+                }
+            }
+            l_per += per * w;
+            if (C.do_backward) C.k_gw[s] = gw;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) l_per += __shfl_xor_sync(0xffffffffu, l_per, o);
+    }
+    // block reduction of the three loss sums -> one atomic per CTA
+    __shared__ float red[3][8];
+    const int wid = threadIdx.x >> 5;
+    if (lane == 0) { red[0][wid] = l_mse; red[1][wid] = l_ent; red[2][wid] = l_per; }
+    __syncthreads();
+    if (threadIdx.x < 3 && C.target) {
+        float s = 0;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        const float scale = threadIdx.x == 0 ? C.inv_N * (1.0f / 3.0f) : C.inv_N;
+        atomicAdd(C.loss + 1 + threadIdx.x, s * scale);
+    }
+}
+__global__ void k_finish_loss(float* loss, float w_main, float w_ent, float w_per) {
+    loss[0] = w_main * loss[1] + w_ent * loss[2] + w_per * loss[3];
+}
+
+// ---------------------------------------------------------------------------------------------
+// B2 — per-ray reverse pass (alpha2weight_backward :654-677 + raw2alpha_backward :507-517).  One thread per
+// ray: the recurrence is sequential; the scatter that follows (B3) is sample-parallel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ray_bwd(const int32_t* __restrict__ off_alpha, const int32_t* __restrict__ off_keep,
+                                                 const float* __restrict__ s_alpha, const float* __restrict__ s_T,
+                                                 const float* __restrict__ s_weight, const float* __restrict__ s_density,
+                                                 const float* __restrict__ k_gw, const float* __restrict__ alphainv_last,
+                                                 const float* __restrict__ grad_last, float* __restrict__ s_gden, int n_rays,
+                                                 float thres, float act_shift, float interval, int64_t cap_alpha, int64_t cap_keep) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const int64_t b = off_alpha[r], e = off_alpha[r + 1];
+    if (e > cap_alpha) return;
+    int64_t ks = off_keep[r + 1];
+    float back_cum = __fmul_rn(grad_last[r], alphainv_last[r]);
+    for (int64_t i = e - 1; i >= b; --i) {
+        const float w = s_weight[i], a = s_alpha[i];
+        float gw = 0.f;
+        if (w > thres) { --ks; gw = ks < cap_keep ? k_gw[ks] : 0.f; }
+        const float ga = pvdb_a2w_grad(gw, s_T[i], back_cum, a);
+        back_cum = __fmaf_rn(gw, w, back_cum);
+        const float ex = expf(__fadd_rn(s_density[i], act_shift));
+        s_gden[i] = pvdb_raw2alpha_bwd(ex, ga, interval);
+    }
+}
+
+__device__ __forceinline__ void red_add(float* addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// B3 — density gradient scatter (densityvdb.cu:143-167) over the compacted alpha list; marks touched leaves.
+__global__ void __launch_bounds__(256) k_density_scatter(pvdb_tree t, float* __restrict__ den_grad, const float* __restrict__ s_xyz,
+                                                         const float* __restrict__ s_gden, const int32_t* __restrict__ counters,
+                                                         int32_t* __restrict__ touched, int64_t cap_alpha) {
+    const int64_t n = min((int64_t)counters[CNT_M_ALPHA], cap_alpha);
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        const float g = s_gden[s];
+        if (g == 0.f) continue;   // adding an exact zero leaves the plane unchanged
+        PvdbTri tri;
+        tri.set(s_xyz[s * 3], s_xyz[s * 3 + 1], s_xyz[s * 3 + 2]);
+        PvdbLeafCache cache;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+            const int x = tri.i + dx, y = tri.j + dy, z = tri.k + dz;
+            const int leaf = cache.find(t, x, y, z);
+            if (leaf < 0) continue;
+            red_add(den_grad + (size_t)leaf * 512 + pvdb_leaf_off(x, y, z),
+                    __fmul_rn(__fmul_rn(__fmul_rn(g, tri.f(0, dx)), tri.f(1, dy)), tri.f(2, dz)));
+            touched[leaf] = 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// U1 — Adam over touched leaves (mode 1 semantics: a voxel whose gradient is zero is skipped, so leaves no
+// sample touched need no visit at all; densityvdb.cu:298-330, colorvdb.cu:297-331).  The same pass clears the
+// gradient of the active voxels it visits and the touched flag, which replaces the full-grid zero_grad sweep
+// (densityvdb.cu:353-368) of the next iteration.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_touched_compact(const int32_t* __restrict__ touched, int n_leaf, int32_t* __restrict__ list,
+                                                         int32_t* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool t = i < n_leaf && touched[i] != 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, t);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && bits) base = atomicAdd(count, __popc(bits));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (t) list[base + __popc(bits & ((1u << lane) - 1))] = i;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_sparse_adam(pvdb_tree t, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                     float* __restrict__ v, int C, float stepsz, float eps, float b0, float b1,
+                                                     const int32_t* __restrict__ list, const int32_t* __restrict__ count,
+                                                     int32_t* __restrict__ touched, int clear_grad) {
+    const int ngrp = C / G;
+    const int n = *count;
+    const float omb0 = __fsub_rn(1.0f, b0), omb1 = __fsub_rn(1.0f, b1);
+    for (int li = blockIdx.x; li < n; li += gridDim.x) {
+        const int leaf = list[li];
+        for (int e = threadIdx.x; e < 512 * ngrp; e += blockDim.x) {
+            const int off = e / ngrp, grp = e - off * ngrp;
+            if (!pvdb_mask_bit(t.leaf_mask, leaf, off)) continue;
+            const size_t base = ((size_t)leaf * 512 + off) * C + (size_t)grp * G;
+            float gg[G];
+            bool allzero = true;
+#pragma unroll
+            for (int c = 0; c < G; ++c) { gg[c] = g[base + c]; allzero = allzero && gg[c] == 0.0f; }
+            if (allzero) continue;
+#pragma unroll
+            for (int c = 0; c < G; ++c) {
+                const float nm = __fmaf_rn(omb0, gg[c], __fmul_rn(b0, m[base + c]));
+                const float nv = __fmaf_rn(gg[c], __fmul_rn(omb1, gg[c]), __fmul_rn(b1, v[base + c]));
+                m[base + c] = nm;
+                v[base + c] = nv;
+                p[base + c] = __fsub_rn(p[base + c], __fdiv_rn(__fmul_rn(stepsz, nm), __fadd_rn(eps, __fsqrt_rn(nv))));
+                if (clear_grad) g[base + c] = 0.f;
+            }
+        }
+        if (clear_grad && threadIdx.x == 0) touched[leaf] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_net_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                  float* __restrict__ v, int n, float step_size, float beta1, float beta2, float eps,
+                                                  int clear_grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pvdb_dense_adam_update(p[i], m[i], v[i], g[i], 1.f, false, step_size, beta1, beta2, eps);
+    if (clear_grad) g[i] = 0.f;
+}
+
+// Occupancy bits: fine[(bx*nby+by)*nbz+bz][8] + one coarse bit per block.  One warp per block.
+__global__ void __launch_bounds__(256) k_occ_build(const uint8_t* __restrict__ mask, int rx, int ry, int rz, int nbx, int nby, int nbz,
+                                                   uint64_t* __restrict__ fine, unsigned long long* __restrict__ coarse) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= nbx * nby * nbz) return;
+    const int bz = b % nbz, by = (b / nbz) % nby, bx = b / (nbz * nby);
+    bool any = false;
+    for (int w = 0; w < 8; ++w) {   // word w covers dx = w, (dy,dz) = 64 bits; each lane builds 2 bits
+        uint64_t bits = 0;
+        for (int h = 0; h < 2; ++h) {
+            const int n = lane * 2 + h;          // bit index inside the word: dy = n>>3, dz = n&7
+            const int x = bx * 8 + w, y = by * 8 + (n >> 3), z = bz * 8 + (n & 7);
+            if (x < rx && y < ry && z < rz && mask[((size_t)x * ry + y) * rz + z]) bits |= 1ull << n;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+        if (lane == 0) fine[(size_t)b * 8 + w] = bits;
+        any = any || bits != 0;
+    }
+    if (lane == 0 && any) atomicOr(coarse + (b >> 6), 1ull << (b & 63));
+}
+
+}  // namespace
+
+extern "C" int pvdb_occ_build(const uint8_t* mask, int rx, int ry, int rz, uint64_t* fine, uint64_t* coarse, void* stream) {
+    PVDB_CHECK_ARG(mask && fine && coarse && rx > 0 && ry > 0 && rz > 0, "bad arguments");
+    const int nbx = (rx + 7) / 8, nby = (ry + 7) / 8, nbz = (rz + 7) / 8;
+    const int nb = nbx * nby * nbz;
+    cudaStream_t st = (cudaStream_t)stream;
+    PVDB_CUDA(cudaMemsetAsync(coarse, 0, (size_t)((nb + 63) / 64) * 8, st));
+    k_occ_build<<<pvdb_grid_for((int64_t)nb * 32, 256), 256, 0, st>>>(mask, rx, ry, rz, nbx, nby, nbz, fine,
+                                                                      (unsigned long long*)coarse);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
+static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, MarchParams& P, MarchOut& O) {
+    P.tree = *b->tree;
+    P.den = b->den;
+    P.occ_fine = b->occ_fine;
+    P.occ_coarse = b->occ_coarse;
+    for (int a = 0; a < 3; ++a) {
+        P.xyz_min[a] = cfg->xyz_min[a]; P.xyz_max[a] = cfg->xyz_max[a];
+        P.rm1[a] = (float)(cfg->reso[a] - 1);
+        P.mask_reso[a] = cfg->mask_reso[a];
+        P.nb[a] = (cfg->mask_reso[a] + 7) / 8;
+        P.mask_scale[a] = cfg->mask_scale[a]; P.mask_shift[a] = cfg->mask_shift[a];
+    }
+    P.near = cfg->near; P.far = cfg->far; P.stepdist = cfg->stepdist; P.act_shift = cfg->act_shift;
+    P.interval = cfg->interval; P.thres = cfg->fast_color_thres;
+    O.t_min = b->t_min; O.t_max = b->t_max; O.n_steps = b->n_steps;
+    O.cnt_mask = b->cnt_mask; O.cnt_alpha = b->cnt_alpha; O.cnt_keep = b->cnt_keep; O.cnt_alpha_full = b->cnt_alpha_full;
+    O.off_alpha = b->off_alpha; O.off_keep = b->off_keep; O.alphainv_last = b->alphainv_last;
+    O.cap_alpha = b->cap_alpha; O.cap_keep = b->cap_keep;
+    O.s_ray = b->s_ray; O.s_step = b->s_step; O.s_xyz = b->s_xyz; O.s_density = b->s_density; O.s_alpha = b->s_alpha;
+    O.s_T = b->s_T; O.s_weight = b->s_weight;
+    O.k_sample = b->k_sample; O.k_ray = b->k_ray; O.k_xyz = b->k_xyz;
+    O.counters = b->counters;
+    return 0;
+}
+
+extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* rays_o, const float* rays_d,
+                               const float* viewdirs, const float* target, int n_rays, int phases, void* stream) {
+    PVDB_CHECK_ARG(cfg && b && b->tree, "null cfg/bufs");
+    PVDB_CHECK_ARG(cfg->k0_dim == 12 && cfg->net_width == 128, "the fused step is specialised for k0_dim=12, rgbnet_width=128");
+    PVDB_CHECK_ARG(n_rays > 0, "n_rays must be positive");
+    const bool do_fwd = phases & PVDB_PHASE_FORWARD, do_bwd = phases & PVDB_PHASE_BACKWARD, do_upd = phases & PVDB_PHASE_UPDATE;
+    PVDB_CHECK_ARG(!do_bwd || (do_fwd && target), "backward needs the forward phase and target colours");
+    PVDB_CHECK_ARG(!do_upd || (cfg->den_mode == 1 && cfg->k0_mode == 1),
+                   "the fused update implements stepmode 1 (skip zero grad); use pvdb_adam_step for modes 0/2");
+    cudaStream_t st = (cudaStream_t)stream;
+    pvdb_reset_launch_count();
+    MarchParams P;
+    MarchOut O;
+    fill_march(cfg, b, P, O);
+    const int n_glob = cfg->n_rays_global > 0 ? cfg->n_rays_global : n_rays;
+    const int warp_grid = pvdb_grid_for((int64_t)n_rays * 32, 256);
+
+    if (do_fwd) {
+        PVDB_CHECK_ARG(rays_o && rays_d && viewdirs, "null rays");
+        if (cfg->parity_counts) k_march<0, true><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
+        else k_march<0, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
+        PVDB_LAUNCH_CHECK();
+        k_scan_counts<<<1, 1024, 0, st>>>(b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays, b->counters, b->cap_alpha,
+                                          b->cap_keep);
+        PVDB_LAUNCH_CHECK();
+        k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
+        PVDB_LAUNCH_CHECK();
+        int rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
+        if (rc) return rc;
+        PVDB_CUDA(cudaMemsetAsync(b->loss, 0, 4 * sizeof(float), st));
+        CompositeParams C;
+        C.off_keep = b->off_keep; C.k_sample = b->k_sample; C.s_weight = b->s_weight; C.k_rgb = b->k_rgb; C.k_gw = b->k_gw;
+        C.alphainv_last = b->alphainv_last; C.target = target; C.rgb_marched = b->rgb_marched; C.grad_last = b->grad_last;
+        C.loss = b->loss; C.bg = cfg->bg; C.w_main = cfg->weight_main; C.w_ent = cfg->weight_entropy_last;
+        C.w_per = cfg->weight_rgbper; C.inv_N = 1.0f / (float)n_glob; C.cap_keep = b->cap_keep; C.do_backward = do_bwd ? 1 : 0;
+        k_composite<<<warp_grid, 256, 0, st>>>(C, n_rays);
+        PVDB_LAUNCH_CHECK();
+        if (target) {
+            k_finish_loss<<<1, 1, 0, st>>>(b->loss, cfg->weight_main, cfg->weight_entropy_last, cfg->weight_rgbper);
+            PVDB_LAUNCH_CHECK();
+        }
+    }
+    if (do_bwd) {
+        int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
+        if (rc) return rc;
+        k_ray_bwd<<<pvdb_grid_for(n_rays, 128), 128, 0, st>>>(b->off_alpha, b->off_keep, b->s_alpha, b->s_T, b->s_weight, b->s_density,
+                                                             b->k_gw, b->alphainv_last, b->grad_last, b->s_gden, n_rays,
+                                                             cfg->fast_color_thres, cfg->act_shift, cfg->interval, b->cap_alpha,
+                                                             b->cap_keep);
+        PVDB_LAUNCH_CHECK();
+        k_density_scatter<<<PVDB_SMS * 8, 256, 0, st>>>(*b->tree, b->den_grad, b->s_xyz, b->s_gden, b->counters, b->den_touched,
+                                                        b->cap_alpha);
+        PVDB_LAUNCH_CHECK();
+    }
+    if (do_upd) {
+        const int n_leaf = b->tree->n_leaf;
+        PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_DEN, 0, sizeof(int32_t), st));
+        PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_K0, 0, sizeof(int32_t), st));
+        k_touched_compact<<<pvdb_grid_for(n_leaf, 256), 256, 0, st>>>(b->den_touched, n_leaf, b->den_touched_list,
+                                                                      b->counters + CNT_N_TOUCHED_DEN);
+        PVDB_LAUNCH_CHECK();
+        k_touched_compact<<<pvdb_grid_for(n_leaf, 256), 256, 0, st>>>(b->k0_touched, n_leaf, b->k0_touched_list,
+                                                                      b->counters + CNT_N_TOUCHED_K0);
+        PVDB_LAUNCH_CHECK();
+        k_sparse_adam<1><<<PVDB_SMS * 4, 256, 0, st>>>(*b->tree, b->den, b->den_grad, b->den_m, b->den_v, 1, cfg->den_stepsz, cfg->eps,
+                                                       cfg->beta0, cfg->beta1, b->den_touched_list, b->counters + CNT_N_TOUCHED_DEN,
+                                                       b->den_touched, 1);
+        PVDB_LAUNCH_CHECK();
+        k_sparse_adam<3><<<PVDB_SMS * 4, 256, 0, st>>>(*b->tree, b->k0, b->k0_grad, b->k0_m, b->k0_v, 12, cfg->k0_stepsz, cfg->eps,
+                                                       cfg->beta0, cfg->beta1, b->k0_touched_list, b->counters + CNT_N_TOUCHED_K0,
+                                                       b->k0_touched, 1);
+        PVDB_LAUNCH_CHECK();
+        const float ss = pvdb_dense_adam_stepsize(cfg->net_lr, cfg->beta0, cfg->beta1, cfg->net_step);
+        k_net_adam<<<pvdb_grid_for(PVDB_NET_N, 256), 256, 0, st>>>(b->net, b->net_grad, b->net_m, b->net_v, PVDB_NET_N, ss, cfg->beta0,
+                                                                   cfg->beta1, cfg->eps, 1);
+        PVDB_LAUNCH_CHECK();
+    }
+    return PVDB_OK;
+}

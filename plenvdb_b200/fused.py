@@ -1,0 +1,189 @@
+"""Fused fine-stage trainer: the opt-in fast path behind the reference's call sequence
+``model(rays) -> zero_grad -> loss.backward() -> optimizer.step() / vdbopt.step()`` (plenvdb/run.py:541-588).
+
+``FusedTrainer`` owns (through torch) every device buffer the C-ABI entry point ``pvdb_train_step`` needs and
+enqueues one whole iteration on the current stream with no host synchronisation, so the step can be captured
+in a CUDA graph.  Grids are plain ``DensityVDB`` / ``ColorVDB`` objects from ``plenvdb_b200.plenvdb`` sharing
+one topology, i.e. the same objects the drop-in API exposes.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .plenvdb import ColorVDB, DensityVDB
+from .tree import Topology
+
+PHASE_FORWARD, PHASE_BACKWARD, PHASE_UPDATE = 1, 2, 4
+NET_N = 22019
+
+
+def mask_scale_shift(mask_shape, xyz_min, xyz_max):
+    """MaskGrid buffers (plenvdb/lib/grid.py:229-231) in float32, like torch computes them."""
+    xyz_min = np.asarray(xyz_min, np.float32)
+    xyz_max = np.asarray(xyz_max, np.float32)
+    scale = (np.asarray(mask_shape, np.float32) - np.float32(1)) / (xyz_max - xyz_min)
+    shift = -xyz_min * scale
+    return scale.astype(np.float32), shift.astype(np.float32)
+
+
+class FusedTrainer:
+    def __init__(self, params, density, k0, mask, net, n_rays, device="cuda", use_tensor_cores=False,
+                 cap_alpha_per_ray=96, cap_keep_per_ray=64, parity_counts=False, n_rays_global=None):
+        """params: dict from synth.scene_params (or the equivalent run.py scalars).
+        density: DensityVDB, k0: ColorVDB(12) on the SAME topology (k0.topo is density.topo).
+        mask: bool [reso] mask_cache.mask.  net: float32[22019] packed rgbnet parameters."""
+        assert k0.topo is density.topo, "density and k0 must share one topology"
+        self.P = dict(params)
+        self.dev = torch.device(device)
+        self.density, self.k0 = density, k0
+        topo = density.topo
+        self.topo = topo
+        self.n_rays = int(n_rays)
+        self.step_count = 0
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        # optimiser state (DensityOpt / ColorOpt / MaskedAdam equivalents)
+        self.den_m, self.den_v = topo.new_plane(1), topo.new_plane(1)
+        self.k0_m, self.k0_v = topo.new_plane(12), topo.new_plane(12)
+        self.net = torch.as_tensor(np.asarray(net, np.float32)).to(self.dev).contiguous()
+        assert self.net.numel() == NET_N
+        self.net_grad, self.net_m, self.net_v = (torch.zeros(NET_N, **f32) for _ in range(3))
+        self.lr_density, self.lr_k0, self.lr_net = float(params["lr_density"]), float(params["lr_k0"]), float(params["lr_net"])
+        # occupancy bits
+        self.set_mask(mask)
+        n = self.n_rays
+        ca, ck = int(cap_alpha_per_ray) * n, int(cap_keep_per_ray) * n
+        self.cap_alpha, self.cap_keep = ca, ck
+        z = lambda *shape, **kw: torch.zeros(*shape, **kw)
+        self.t = dict(
+            t_min=z(n, **f32), t_max=z(n, **f32), n_steps=z(n, **i32), cnt_mask=z(n, **i32), cnt_alpha=z(n, **i32),
+            cnt_keep=z(n, **i32), cnt_alpha_full=z(n, **i32), off_alpha=z(n + 1, **i32), off_keep=z(n + 1, **i32),
+            alphainv_last=z(n, **f32), rgb_marched=z(n, 3, **f32), grad_last=z(n, **f32),
+            s_ray=z(ca, **i32), s_step=z(ca, **i32), s_xyz=z(ca, 3, **f32), s_density=z(ca, **f32), s_alpha=z(ca, **f32),
+            s_T=z(ca, **f32), s_weight=z(ca, **f32), s_gden=z(ca, **f32),
+            k_sample=z(ck, **i32), k_ray=z(ck, **i32), k_xyz=z(ck, 3, **f32), k_feat=z(ck, 12, **f32), k_rgb=z(ck, 3, **f32),
+            k_gw=z(ck, **f32),
+            den_touched=z(max(topo.n_leaf, 1), **i32), k0_touched=z(max(topo.n_leaf, 1), **i32),
+            den_touched_list=z(max(topo.n_leaf, 1), **i32), k0_touched_list=z(max(topo.n_leaf, 1), **i32),
+            counters=z(16, **i32), loss=z(4, **f32),
+        )
+        self.use_tc = bool(use_tensor_cores)
+        if not self.use_tc:
+            self.t["k_h0"] = z(ck, 128, **f32)
+            self.t["k_h1"] = z(ck, 128, **f32)
+        self.parity_counts = bool(parity_counts)
+        self.n_rays_global = int(n_rays_global) if n_rays_global else self.n_rays
+        self._bufs = None
+        self._build_structs()
+
+    # ---- state
+    def set_mask(self, mask):
+        m = torch.as_tensor(np.ascontiguousarray(np.asarray(mask).astype(np.uint8))).to(self.dev)
+        self.mask_shape = tuple(m.shape)
+        nb = [(s + 7) // 8 for s in self.mask_shape]
+        nblk = nb[0] * nb[1] * nb[2]
+        self.occ_fine = torch.zeros(nblk * 8, dtype=torch.int64, device=self.dev)
+        self.occ_coarse = torch.zeros((nblk + 63) // 64, dtype=torch.int64, device=self.dev)
+        _lib.call("pvdb_occ_build", _lib.ptr(m), m.shape[0], m.shape[1], m.shape[2], _lib.ptr(self.occ_fine),
+                  _lib.ptr(self.occ_coarse), _lib.current_stream())
+        self.mask_dev = m
+        if getattr(self, "_bufs", None) is not None:
+            self._build_structs()
+
+    def _build_structs(self):
+        P = self.P
+        c = _lib.pvdb_train_cfg()
+        c.xyz_min = (C.c_float * 3)(*[float(v) for v in P["xyz_min"]])
+        c.xyz_max = (C.c_float * 3)(*[float(v) for v in P["xyz_max"]])
+        c.reso = (C.c_int32 * 3)(*[int(v) for v in P["reso"]])
+        c.mask_reso = (C.c_int32 * 3)(*self.mask_shape)
+        sc, sh = mask_scale_shift(self.mask_shape, P["xyz_min"], P["xyz_max"])
+        c.mask_scale = (C.c_float * 3)(*[float(v) for v in sc])
+        c.mask_shift = (C.c_float * 3)(*[float(v) for v in sh])
+        for k in ("near", "far", "stepdist", "act_shift", "interval", "fast_color_thres", "bg", "weight_main",
+                  "weight_entropy_last", "weight_rgbper", "eps", "beta0", "beta1", "den_mode", "k0_mode"):
+            setattr(c, k, P[k])
+        c.k0_dim, c.net_width = 12, 128
+        c.use_tensor_cores = int(self.use_tc)
+        c.n_rays_global = self.n_rays_global
+        c.parity_counts = int(self.parity_counts)
+        self.cfg = c
+        b = _lib.pvdb_train_bufs()
+        b.tree = C.pointer(self.topo.c)
+        p = lambda t: t.data_ptr()
+        b.den, b.den_grad, b.den_m, b.den_v = p(self.density.grid), p(self.density.grad), p(self.den_m), p(self.den_v)
+        b.k0, b.k0_grad, b.k0_m, b.k0_v = p(self.k0.grid), p(self.k0.grad), p(self.k0_m), p(self.k0_v)
+        b.occ_fine, b.occ_coarse = p(self.occ_fine), p(self.occ_coarse)
+        b.net, b.net_grad, b.net_m, b.net_v = p(self.net), p(self.net_grad), p(self.net_m), p(self.net_v)
+        b.cap_alpha, b.cap_keep = self.cap_alpha, self.cap_keep
+        for k, t in self.t.items():
+            setattr(b, k, p(t))
+        self._bufs = b
+
+    def _set_step_scalars(self):
+        s = self.step_count
+        self.cfg.den_stepsz = _lib.lib.pvdb_adam_stepsize(self.lr_density, self.P["beta0"], self.P["beta1"], s)
+        self.cfg.k0_stepsz = _lib.lib.pvdb_adam_stepsize(self.lr_k0, self.P["beta0"], self.P["beta1"], s)
+        self.cfg.net_lr = self.lr_net
+        self.cfg.net_step = s
+
+    def decay_lr(self, factor):
+        """run.py:592-598: multiply every lr by `factor` (float32 for the grids, like the C++ members)."""
+        self.lr_density = float(np.float32(self.lr_density) * np.float32(factor))
+        self.lr_k0 = float(np.float32(self.lr_k0) * np.float32(factor))
+        self.lr_net = self.lr_net * factor
+
+    # ---- execution
+    def run(self, rays_o, rays_d, viewdirs, target, phases):
+        n = rays_o.shape[0]
+        assert n <= self.n_rays
+        for t in (rays_o, rays_d, viewdirs) + ((target,) if target is not None else ()):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        if phases & PHASE_UPDATE:
+            self.step_count += 1
+            self._set_step_scalars()
+        _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(rays_o), _lib.ptr(rays_d),
+                  _lib.ptr(viewdirs), _lib.ptr(target), n, int(phases), _lib.current_stream())
+
+    def step(self, rays_o, rays_d, viewdirs, target):
+        """One full iteration: forward + backward + sparse Adam (grids) + Adam (rgbnet)."""
+        self.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE)
+
+    def forward_backward(self, rays_o, rays_d, viewdirs, target):
+        self.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD)
+
+    def update(self):
+        """Apply the optimisers to whatever gradients are accumulated (after a gradient all-reduce)."""
+        dummy = self.t["t_min"]
+        self.step_count += 1
+        self._set_step_scalars()
+        _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(dummy), _lib.ptr(dummy), _lib.ptr(dummy),
+                  None, self.n_rays, PHASE_UPDATE, _lib.current_stream())
+
+    def forward(self, rays_o, rays_d, viewdirs):
+        """Render rays through the training model (run.py:171-189); returns rgb_marched [n,3]."""
+        self.run(rays_o, rays_d, viewdirs, None, PHASE_FORWARD)
+        return self.t["rgb_marched"][: rays_o.shape[0]]
+
+    def launches_last_call(self):
+        return int(_lib.lib.pvdb_last_launch_count())
+
+    def counters(self):
+        c = self.t["counters"].cpu().numpy()
+        return dict(M_alpha=int(c[0]), M_keep=int(c[1]), n_touched_den=int(c[2]), overflow=int(c[3]), n_touched_k0=int(c[4]))
+
+
+def build_scene_grids(scene, device="cuda"):
+    """DensityVDB + ColorVDB(12) on one shared topology, filled from a synth.make_scene dict."""
+    reso = scene["reso"]
+    den = DensityVDB(list(reso), 1, device=device)
+    if scene["active"] is not None:
+        den._set_topology(Topology.from_mask(scene["active"], device=device))
+    k0 = ColorVDB.__new__(ColorVDB)
+    k0.num, k0.reso, k0.ndim, k0.device, k0.timer = 4, list(reso), 12, torch.device(device), 0.0
+    k0._set_topology(den.topo)
+    den.copyFromDense_torch(torch.from_numpy(scene["density"]))
+    k0.copyFromDense_torch(torch.from_numpy(scene["k0"]))
+    return den, k0

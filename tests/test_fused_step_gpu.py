@@ -1,0 +1,154 @@
+"""GPU parity of the fused fine-stage training step (SURVEY.md §8a rows S1..N3 composed as in dvgo.py:296-388 +
+run.py:541-588) against the CPU oracle on the same seeded scene, rays and rgbnet.
+Integers (sample counts, segment offsets, ray/step ids, voxel/leaf indices) bit-exact; values within 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _oracle_state(scene):
+    from oracle import oracle as orc
+    R, act = scene["reso"], scene["active"]
+    den, k0 = orc.Grid(R, 1, act), orc.Grid(R, 12, act)
+    den.copy_from_dense(scene["density"])
+    k0.copy_from_dense(scene["k0"])
+    aux = [orc.Grid(R, c, act) for c in (1, 1, 1, 12, 12, 12)]   # den_grad, den_m, den_v, k0_grad, k0_m, k0_v
+    return den, k0, aux
+
+
+def _oracle_cfg(P, step=1, do_update=1, n_rays_global=0, threads=8):
+    keys = ["xyz_min", "xyz_max", "reso", "near", "far", "stepdist", "act_shift", "interval", "fast_color_thres", "bg",
+            "weight_main", "weight_entropy_last", "weight_rgbper", "lr_density", "lr_k0", "lr_net", "eps", "beta0", "beta1",
+            "den_mode", "k0_mode"]
+    c = {k: P[k] for k in keys}
+    c.update(step=step, do_update=do_update, n_rays_global=n_rays_global, threads=threads)
+    return c
+
+
+def _run_oracle(scene, net, rays, step=1, do_update=1, cap_keep=0, n_rays_global=0):
+    from oracle import oracle as orc
+    den, k0, aux = _oracle_state(scene)
+    net = net.copy()
+    nm, nv = np.zeros_like(net), np.zeros_like(net)
+    out = orc.train_step(_oracle_cfg(scene, step, do_update, n_rays_global), den, aux[0], aux[1], aux[2], k0, aux[3], aux[4],
+                         aux[5], scene["mask"], net, nm, nv, *rays, cap_keep=cap_keep)
+    return out, den, k0, aux, net, nm, nv
+
+
+def _trainer(scene, net, n_rays, **kw):
+    from plenvdb_b200.fused import FusedTrainer, build_scene_grids
+    den, k0 = build_scene_grids(scene)
+    return FusedTrainer(scene, den, k0, scene["mask"], net, n_rays, **kw), den, k0
+
+
+@pytest.fixture(scope="module")
+def small():
+    from plenvdb_b200 import synth
+    scene = synth.make_scene(96, "dense")
+    net = synth.rgbnet_init()
+    rays = synth.ray_batch(2048, H=200, W=200, K=synth.intrinsics(200, 200), seed=777)
+    return scene, net, rays
+
+
+@pytest.mark.parametrize("variant", ["dense", "sparse"])
+def test_forward_counts_offsets_and_values(variant, small):
+    from plenvdb_b200 import synth
+    scene, net, rays = small
+    if variant == "sparse":
+        scene = synth.make_scene(96, "sparse")
+    n = rays[0].shape[0]
+    o, *_ = _run_oracle(scene, net, rays, do_update=0, cap_keep=200000)
+    assert o["M3"] > 1000, "degenerate test scene"
+    tr, den, k0 = _trainer(scene, net, n, parity_counts=True)
+    tr.forward_backward(*[_cu(a) for a in rays])
+    t = {k: v.cpu().numpy() for k, v in tr.t.items()}
+    c = tr.counters()
+    assert c["overflow"] == 0
+    # ---- integers: bit exact
+    assert np.array_equal(t["n_steps"], o["n_steps"].astype(np.int32))
+    assert np.array_equal(t["cnt_mask"], o["cnt_mask"])
+    assert np.array_equal(t["cnt_alpha_full"], o["cnt_alpha_full"])
+    assert np.array_equal(t["cnt_alpha"], o["cnt_alpha"])
+    assert np.array_equal(t["cnt_keep"], o["cnt_keep"])
+    assert c["M_alpha"] == o["M2_trim"] and c["M_keep"] == o["M3"]
+    assert np.array_equal(t["off_keep"], np.concatenate([[0], np.cumsum(o["cnt_keep"])]).astype(np.int32))
+    assert np.array_equal(t["off_alpha"], np.concatenate([[0], np.cumsum(o["cnt_alpha"])]).astype(np.int32))
+    M3 = o["M3"]
+    assert np.array_equal(t["k_ray"][:M3], o["keep_ray"])
+    assert np.array_equal(t["s_step"][t["k_sample"][:M3]], o["keep_step"])
+    # leaf / voxel indices of the 8 corners of every kept sample
+    cl = torch.zeros((M3, 8), dtype=torch.int32, device="cuda")
+    co = torch.zeros_like(cl)
+    k0.forward_torch(tr.t["k_xyz"][:M3].t().contiguous(), corner_out=(cl, co))
+    assert np.array_equal(cl.cpu().numpy(), o["keep_leaf"]) and np.array_equal(co.cpu().numpy(), o["keep_off"])
+    # ---- values
+    np.testing.assert_allclose(t["s_weight"][t["k_sample"][:M3]], o["keep_weight"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(t["k_feat"][:M3], o["keep_feat"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(t["alphainv_last"], o["alphainv_last"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(t["rgb_marched"], o["rgb_marched"], rtol=RTOL, atol=2e-6)
+    np.testing.assert_allclose(t["loss"], o["loss"], rtol=1e-4)
+
+
+def test_gradients_match_oracle(small):
+    scene, net, rays = small
+    n = rays[0].shape[0]
+    o, oden, ok0, aux, *_ = _run_oracle(scene, net, rays, do_update=0)
+    tr, den, k0 = _trainer(scene, net, n)
+    tr.forward_backward(*[_cu(a) for a in rays])
+    for got, want, name in ((den.get_dense_grid_torch(den.grad).cpu().numpy(), aux[0].to_dense(), "density"),
+                            (k0.get_dense_grid_torch(k0.grad).cpu().numpy(), aux[3].to_dense(), "k0")):
+        scale = np.abs(want).max()
+        assert scale > 0
+        assert np.abs(got - want).max() <= 2e-5 * scale, "%s grad: max err %g of scale %g" % (name, np.abs(got - want).max(), scale)
+        assert ((got != 0) == (want != 0)).mean() > 0.9999
+    gn, wn = tr.net_grad.cpu().numpy(), o["net_grad"]
+    assert np.abs(gn - wn).max() <= 2e-5 * np.abs(wn).max()
+
+
+def test_update_matches_oracle_over_steps(small):
+    scene, net, rays = small
+    from oracle import oracle as orc
+    n = rays[0].shape[0]
+    tr, den, k0 = _trainer(scene, net, n)
+    oden, ok0, aux = _oracle_state(scene)
+    onet, onm, onv = net.copy(), np.zeros_like(net), np.zeros_like(net)
+    cu = [_cu(a) for a in rays]
+    for step in (1, 2, 3):
+        tr.step(*cu)
+        orc.train_step(_oracle_cfg(scene, step, 1), oden, aux[0], aux[1], aux[2], ok0, aux[3], aux[4], aux[5], scene["mask"], onet,
+                       onm, onv, *rays)
+    assert tr.launches_last_call() > 0
+    # Adam divides by sqrt(v): relative differences of the gradients pass through ~unchanged; parameters moved by lr*O(1)
+    for got, want, name in ((den.get_dense_grid().reshape(-1), oden.to_dense().reshape(-1), "density"),
+                            (k0.get_dense_grid().reshape(-1), ok0.to_dense().reshape(-1), "k0"),
+                            (tr.net.cpu().numpy(), onet, "rgbnet")):
+        moved = got != (scene["density"].reshape(-1) if name == "density" else scene["k0"].reshape(-1) if name == "k0" else net)
+        assert moved.sum() > 0, name
+        np.testing.assert_allclose(got, want, rtol=1e-3, atol=2e-4, err_msg=name)
+    # gradients consumed by the update are cleared (replaces zero_grad); untouched leaves were never visited
+    assert float(den.grad.abs().max()) == 0.0 and float(k0.grad.abs().max()) == 0.0
+
+
+def test_data_parallel_shards_sum_to_full_batch(small):
+    """Two half-batches with n_rays_global = N reproduce the full-batch gradients."""
+    scene, net, rays = small
+    n = rays[0].shape[0]
+    full, dfull, kfull = _trainer(scene, net, n)
+    full.forward_backward(*[_cu(a) for a in rays])
+    acc_d, acc_k, acc_n = 0, 0, 0
+    for lo, hi in ((0, n // 2), (n // 2, n)):
+        tr, d, k = _trainer(scene, net, n // 2, n_rays_global=n)
+        tr.forward_backward(*[_cu(a[lo:hi]) for a in rays])
+        acc_d = acc_d + d.grad.clone()
+        acc_k = acc_k + k.grad.clone()
+        acc_n = acc_n + tr.net_grad.clone()
+    for a, b in ((acc_d, dfull.grad), (acc_k, kfull.grad), (acc_n, full.net_grad)):
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
