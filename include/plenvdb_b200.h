@@ -212,6 +212,13 @@ typedef struct pvdb_train_bufs {
 int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs,
                     const float* rays_o, const float* rays_d, const float* viewdirs, const float* target,
                     int n_rays, int phases, void* stream);
+/* hit_coarse_geo (plenvdb/lib/dvgo.py:253-270) for the 'in_maskcache' ray sampler: hit[r] = 1 iff some in-bbox sample
+ * of ray r lands in an occupied voxel.  Uses cfg's scene scalars and bufs->occ_*. */
+int pvdb_rays_hit_mask(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs, const float* rays_o, const float* rays_d,
+                       int n_rays, uint8_t* hit, void* stream);
+/* Per-kernel timing of the fused calls (CUDA events on the launching stream), for the benchmark's roofline line. */
+int pvdb_profile_enable(int on);
+int pvdb_profile_fetch(int max_segments, float* ms, char* names /* [max_segments][32] */);
 /* Number of this library's kernel launches enqueued by the last pvdb_train_step / pvdb_render call on this thread. */
 int pvdb_last_launch_count(void);
 
@@ -229,26 +236,32 @@ typedef struct pvdb_render_cfg {
 } pvdb_render_cfg;
 
 typedef struct pvdb_render_bufs {
-    const pvdb_tree* idx_tree;       /* merged index grid */
-    const float* idx_plane;          /* [n_leaf][512] 1-based row ids stored as float (vdb_compression.py:31-33) */
-    const float* dendata;            /* [N+1] */
-    const float* coldata;            /* [N+1][12] */
+    const pvdb_tree* idx_tree;       /* merged index grid: leaves where mask_cache.mask has a voxel, value mask = mask */
+    const int32_t* idx_plane;        /* [n_leaf][512] 1-based row ids (vdb_compression.py:31-33), 0 = none */
+    const float* dendata;            /* [N+1], row 0 = 0 */
+    const float* coldata;            /* [N+1][12], row 0 = 0 */
     const float *w0, *b0, *w1, *b1, *w2, *b2;  /* transposed layout of run.py:98-104: w0[39][128], w1[128][128], w2[128][3] */
-    /* scratch sized for rows [row_begin,row_end) */
-    int32_t *n_samples, *i_starts;   /* [rows*W], [rows*W+1] */
-    float *tmins, *tmaxs;            /* [rows*W] */
+    /* scratch for the rows of one call, npix = (row_end-row_begin)*W */
+    int32_t *n_samples;              /* [npix] */
+    int32_t *i_starts;               /* [npix+1] exclusive scan = segment offsets */
+    float *tmins, *tmaxs;            /* [npix] tightened range of pass 1 */
+    int32_t *scan_tmp;               /* [npix/4096 + 2] */
     int64_t cap_samples;
-    int32_t *s_ray; float *s_weight; float *s_feat; /* [cap][..] */
-    int32_t *counters;               /* [8] */
+    int32_t *s_ray;                  /* [cap] pixel index local to the band */
+    float *s_weight;                 /* [cap] */
+    float *s_feat;                   /* [cap][12] */
+    float *s_rgb;                    /* [cap][3] weight * sigmoid(rgbnet) */
+    int32_t *counters;               /* [8]: 0 total samples, 1 overflow flag, 2 rays whose two passes disagree */
 } pvdb_render_bufs;
 
-int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bufs* bufs, const float* c2w /* device [16] */,
-                     int row_begin, int row_end, float* out_rgb /* device [(row_end-row_begin)*W*3] */,
-                     void* stream);
-/* Device-side merge (vdb_compression.py:19-59): see plenvdb_b200/merge.py for the host orchestration. */
+/* Renders rows [row_begin,row_end) of the H x W image for camera `c2w` (device float[16], row-major 4x4) into
+ * out_rgb (device float[(row_end-row_begin)*W*3]).  No allocation, no synchronisation. */
+int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bufs* bufs, const float* c2w,
+                     int row_begin, int row_end, float* out_rgb, void* stream);
+/* Device-side half of the merge (vdb_compression.py:36-57): gathers density / colour rows of every masked voxel and
+ * rounds them through fp16.  row_of_voxel [rx*ry*rz]: 1-based row id or 0. */
 int pvdb_merge_gather(const pvdb_tree* tree, const float* den, const float* k0, int k0_dim,
-                      const uint8_t* mask, const int32_t* row_of_voxel /* [rx*ry*rz] 1-based or 0 */,
-                      int rx, int ry, int rz, float* dendata, float* coldata, void* stream);
+                      const int32_t* row_of_voxel, int rx, int ry, int rz, float* dendata, float* coldata, void* stream);
 
 #ifdef __cplusplus
 }

@@ -896,8 +896,9 @@ extern "C" void orc_render(const orc_render_cfg* cfg, const orc_grid* idx_grid, 
                     const float f0 = CORNER[q][0] ? u[0] : 1 - u[0], f1 = CORNER[q][1] ? u[1] : 1 - u[1], f2 = CORNER[q][2] ? u[2] : 1 - u[2];
                     sc[q] = (f0 * f1) * f2;
                 }
-                float vden = dendata[idx[0]] * sc[0];
-                for (int q = 1; q < 8; ++q) vden = fmaf(dendata[idx[q]], sc[q], vden);
+                // d0*s0 + d1*s1 + ... compiles to fma(d7,s7, ... fma(d2,s2, fma(d0,s0, d1*s1))) (:298-299)
+                float vden = fmaf(dendata[idx[0]], sc[0], dendata[idx[1]] * sc[1]);
+                for (int q = 2; q < 8; ++q) vden = fmaf(dendata[idx[q]], sc[q], vden);
                 const float alpha = 1 - powf(1 + expf(vden + cfg->act_shift), -cfg->interval);
                 if (alpha <= thres) continue;
                 const float weight = T_cum * alpha;
@@ -905,8 +906,8 @@ extern "C" void orc_render(const orc_render_cfg* cfg, const orc_grid* idx_grid, 
                 if (weight <= thres) continue;
                 if (r >= ns) { ++r; continue; }   // the reference would overrun its segment here
                 for (int i = 0; i < cdim; ++i) {
-                    float v = coldata[(size_t)idx[0] * cdim + i] * sc[0];
-                    for (int q = 1; q < 8; ++q) v = fmaf(coldata[(size_t)idx[q] * cdim + i], sc[q], v);
+                    float v = fmaf(coldata[(size_t)idx[0] * cdim + i], sc[0], coldata[(size_t)idx[1] * cdim + i] * sc[1]);   // :305-308
+                    for (int q = 2; q < 8; ++q) v = fmaf(coldata[(size_t)idx[q] * cdim + i], sc[q], v);
                     feats[(size_t)r * cdim + i] = v;
                 }
                 weights[r++] = weight;

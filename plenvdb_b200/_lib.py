@@ -88,9 +88,9 @@ class pvdb_render_bufs(C.Structure):
     _fields_ = [
         ("idx_tree", C.POINTER(pvdb_tree)), ("idx_plane", c_ptr), ("dendata", c_ptr), ("coldata", c_ptr),
         ("w0", c_ptr), ("b0", c_ptr), ("w1", c_ptr), ("b1", c_ptr), ("w2", c_ptr), ("b2", c_ptr),
-        ("n_samples", c_ptr), ("i_starts", c_ptr), ("tmins", c_ptr), ("tmaxs", c_ptr),
+        ("n_samples", c_ptr), ("i_starts", c_ptr), ("tmins", c_ptr), ("tmaxs", c_ptr), ("scan_tmp", c_ptr),
         ("cap_samples", C.c_int64),
-        ("s_ray", c_ptr), ("s_weight", c_ptr), ("s_feat", c_ptr), ("counters", c_ptr),
+        ("s_ray", c_ptr), ("s_weight", c_ptr), ("s_feat", c_ptr), ("s_rgb", c_ptr), ("counters", c_ptr),
     ]
 
 
@@ -131,6 +131,11 @@ _SIGS = {
     "pvdb_alpha2weight_backward": (None, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, _i, c_ptr, c_ptr, c_ptr, c_ptr]),
     "pvdb_dense_adam": (None, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, _i64, _i, _i, _f, _f, _f, _f, c_ptr]),
     "pvdb_occ_build": (None, [c_ptr, _i, _i, _i, c_ptr, c_ptr, c_ptr]),
+    "pvdb_profile_enable": (None, [_i]),
+    "pvdb_profile_fetch": (C.c_int, [_i, c_ptr, c_ptr]),
+    "pvdb_rays_hit_mask": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, _i, c_ptr, c_ptr]),
+    "pvdb_render_rows": (None, [C.POINTER(pvdb_render_cfg), C.POINTER(pvdb_render_bufs), c_ptr, _i, _i, c_ptr, c_ptr]),
+    "pvdb_merge_gather": (None, [_TP, c_ptr, c_ptr, _i, c_ptr, _i, _i, _i, c_ptr, c_ptr, c_ptr]),
     "pvdb_train_step": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, c_ptr, c_ptr, _i, _i,
                                c_ptr]),
 }
@@ -174,3 +179,15 @@ def ptr(t):
 def current_stream():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def profile_enable(on=True):
+    call("pvdb_profile_enable", int(bool(on)))
+
+
+def profile_fetch(max_segments=48):
+    """[(kernel name, ms)] of the last fused call issued with profiling enabled."""
+    ms = (C.c_float * max_segments)()
+    names = C.create_string_buffer(max_segments * 32)
+    n = lib.pvdb_profile_fetch(max_segments, ms, names)
+    return [(names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), float(ms[i])) for i in range(n)]

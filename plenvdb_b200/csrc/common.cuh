@@ -12,6 +12,10 @@
 void pvdb_set_error(const char* fmt, ...);
 void pvdb_count_launch(int n = 1);
 void pvdb_reset_launch_count();
+// Optional per-kernel timing for bench.py's roofline line: when enabled, pvdb_prof_mark() records a CUDA event on the
+// launching stream after each kernel of a fused call; pvdb_profile_fetch() returns the elapsed ms between marks.
+void pvdb_prof_begin(cudaStream_t st);
+void pvdb_prof_mark(const char* name, cudaStream_t st);
 
 #define PVDB_CHECK_ARG(cond, msg)                 \
     do {                                          \

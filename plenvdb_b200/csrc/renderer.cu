@@ -1,0 +1,501 @@
+// renderer.cu — merged-VDB renderer (R1/R2): MGRenderer::render_an_image of the reference
+// (plenvdb/lib/vdb/renderer.cu:370-424, plenvdb.h:933-1068) for a band of image rows.
+//
+//   P1 k_render_pass1     thread per pixel (8x4 pixel tile per warp): ray from (pixel, K, c2w), unit-box t range,
+//                         fixed-step march with the reference's `t += steplen` recurrence, active test on the index
+//                         grid, density trilinear through the index -> data indirection, alpha, thresholds;
+//                         counts kept samples and tightens [tmin, tmax]                       (renderer.cu:222-268)
+//   SC k_scan_*           exclusive scan of the per-pixel counts in pixel order -> i_starts    (renderer.cu:401-402)
+//   P2 k_render_pass2     second march from the tightened range, gathers the 12 colour features (renderer.cu:312-367)
+//   ML k_render_mlp       64-sample tiles: view PE + MLP(39->128->128->3), weight*sigmoid       (renderer.cu:83-119)
+//   CO k_render_composite per-pixel ordered sum (deterministic; the reference uses float atomics)
+//
+// Differences from the reference by design: no per-frame cudaMalloc/cudaFree or host sync, no race on rays_o
+// (renderer.cu:128-132), pass 2 cannot overrun its segment (such rays are counted), the
+// per-ray PE contribution is folded into the layer-0 tile GEMM instead of a separate HW x 128 GEMM.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "mlp_tile.cuh"
+
+namespace {
+
+constexpr int RC_TOTAL = 0, RC_OVERFLOW = 1, RC_INCONSISTENT = 2;
+
+struct RenderConst {
+    pvdb_tree tree;
+    const int32_t* idx_plane;
+    const float* dendata;
+    const float* coldata;
+    float K[9];
+    float xyz_min[3], ext[3];     // ext = xyz_max - xyz_min (float sub)
+    float wld[3];                 // reso - 1
+    float near, stepdist, act_shift, interval, thres, bg;
+    int inverse_y, H, W;
+};
+
+struct Ray {
+    float ro[3], rd[3], vd[3];
+    float steplen, tmin, tmax;
+};
+
+// get_rays (:122-167) + get_tminmax (:50-64), instruction order read from the reference PTX.
+__device__ __forceinline__ void ray_setup(const RenderConst& C, const float* __restrict__ c2w, int n, Ray& R) {
+    const float pixeli = (float)((double)(n % C.W) + 0.5), pixelj = (float)((double)(n / C.W) + 0.5);
+    float dir[3];
+    dir[0] = __fdiv_rn(__fsub_rn(pixeli, C.K[2]), C.K[0]);
+    if (C.inverse_y) { dir[1] = __fdiv_rn(__fsub_rn(pixelj, C.K[5]), C.K[4]); dir[2] = 1.f; }
+    else { dir[1] = __fdiv_rn(-__fsub_rn(pixelj, C.K[5]), C.K[4]); dir[2] = -1.f; }
+    float rdw[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // d0*c0 + d1*c1 + d2*c2  ->  fma(d2,c2, fma(d0,c0, d1*c1))
+        rdw[a] = __fmaf_rn(dir[2], __ldg(c2w + a * 4 + 2), __fmaf_rn(dir[0], __ldg(c2w + a * 4), __fmul_rn(dir[1], __ldg(c2w + a * 4 + 1))));
+        R.ro[a] = __fdiv_rn(__fsub_rn(__ldg(c2w + a * 4 + 3), C.xyz_min[a]), C.ext[a]);
+    }
+    const float len = __fsqrt_rn(__fmaf_rn(rdw[2], rdw[2], __fmaf_rn(rdw[0], rdw[0], __fmul_rn(rdw[1], rdw[1]))));
+    R.steplen = __fdiv_rn(C.stepdist, len);
+    const float inv = __frcp_rn(len);   // Vec3::normalize: *this *= 1/length
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        R.rd[a] = __fdiv_rn(rdw[a], C.ext[a]);
+        R.vd[a] = __fmul_rn(rdw[a], inv);
+    }
+    const float far = 1e9f;   // setKwargs overrides far (plenvdb.h:1008)
+    const float vx = R.rd[0] == 0.f ? 1e-6f : R.rd[0], vy = R.rd[1] == 0.f ? 1e-6f : R.rd[1], vz = R.rd[2] == 0.f ? 1e-6f : R.rd[2];
+    const float ax = __fdiv_rn(__fsub_rn(1.f, R.ro[0]), vx), ay = __fdiv_rn(__fsub_rn(1.f, R.ro[1]), vy), az = __fdiv_rn(__fsub_rn(1.f, R.ro[2]), vz);
+    const float bx = __fdiv_rn(-R.ro[0], vx), by = __fdiv_rn(-R.ro[1], vy), bz = __fdiv_rn(-R.ro[2], vz);
+    R.tmin = fmaxf(fminf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), far), C.near);
+    R.tmax = fmaxf(fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), far), C.near);
+}
+
+// alpha = 1 - pow(1 + exp(v + shift), -interval) exactly as nvcc compiles renderer.cu:256 / :350: the final scale
+// multiply of expf is contracted with the "+ 1" into one fma, so this expression is deliberately left to the
+// compiler (checked in the PTX of this file: fma.rn.f32 ..., 0f3F800000 after ex2.approx).
+__device__ __forceinline__ float render_alpha(float v_den, float act_shift, float interval) {
+    return 1 - powf(1 + expf(v_den + act_shift), -interval);
+}
+
+struct MarchState {
+    PvdbLeafCache cache;
+};
+
+// One march step: position, bbox test, active test.  Returns false when the step is skipped.
+__device__ __forceinline__ bool step_active(const RenderConst& C, const Ray& R, MarchState& S, float t, float* xyz, int& leaf_r) {
+    const float p0 = __fmaf_rn(R.rd[0], t, R.ro[0]), p1 = __fmaf_rn(R.rd[1], t, R.ro[1]), p2 = __fmaf_rn(R.rd[2], t, R.ro[2]);
+    if ((0.f > p0) | (0.f > p1) | (0.f > p2) | (1.f < p0) | (1.f < p1) | (1.f < p2)) return false;
+    xyz[0] = __fmul_rn(p0, C.wld[0]); xyz[1] = __fmul_rn(p1, C.wld[1]); xyz[2] = __fmul_rn(p2, C.wld[2]);
+    // acc.isActive(Round<Coord>(xyz)): rintf, leaf must exist and the voxel bit be set (NanoVDB.h:773-779, 3035-3045)
+    const int i = __float2int_rn(xyz[0]), j = __float2int_rn(xyz[1]), k = __float2int_rn(xyz[2]);
+    const int leaf = S.cache.find(C.tree, i, j, k);
+    leaf_r = leaf;
+    if (leaf < 0) return false;
+    return pvdb_mask_bit(C.tree.leaf_mask, leaf, pvdb_leaf_off(i, j, k));
+}
+
+__device__ __forceinline__ int idx_at(const RenderConst& C, PvdbLeafCache& cache, int x, int y, int z) {
+    const int leaf = cache.find(C.tree, x, y, z);
+    return leaf >= 0 ? __ldg(C.idx_plane + (size_t)leaf * 512 + pvdb_leaf_off(x, y, z)) : 0;
+}
+
+__device__ __forceinline__ int pixel_of_thread(int W, int rows, int& local) {
+    // 8x4 pixel tile per warp
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (W + 7) >> 3;
+    const int tx = warp % tiles_x, ty = warp / tiles_x;
+    const int col = tx * 8 + (lane & 7), row = ty * 4 + (lane >> 3);
+    if (col >= W || row >= rows) { local = -1; return -1; }
+    local = row * W + col;
+    return local;
+}
+
+__global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float* __restrict__ c2w, int row_begin, int rows,
+                                                      int32_t* __restrict__ n_samples, float* __restrict__ tmins,
+                                                      float* __restrict__ tmaxs) {
+    int local;
+    if (pixel_of_thread(C.W, rows, local) < 0) return;
+    const int n = row_begin * C.W + local;
+    Ray R;
+    ray_setup(C, c2w, n, R);
+    MarchState S;
+    PvdbLeafCache vcache;
+    float T_cum = 1.0f, t = R.tmin, tmin_out = R.tmin, tmax_out = R.tmax;
+    const float tmax0 = R.tmax;
+    bool update_tmin = false;
+    int ns = 0;
+    while (t < tmax0) {
+        t = __fadd_rn(t, R.steplen);
+        float xyz[3];
+        int leaf;
+        if (!step_active(C, R, S, t, xyz, leaf)) continue;
+        // trigetDensity (:191-220): int() truncation, res += d*f0*f1*f2 -> fma(f2, f1*(f0*d), res)
+        const int i = (int)xyz[0], j = (int)xyz[1], k = (int)xyz[2];
+        const float u = __fsub_rn(xyz[0], (float)i), v = __fsub_rn(xyz[1], (float)j), w = __fsub_rn(xyz[2], (float)k);
+        float res = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+            const float d = __ldg(C.dendata + idx_at(C, vcache, i + dx, j + dy, k + dz));
+            const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
+            res = __fmaf_rn(f2, __fmul_rn(f1, __fmul_rn(f0, d)), res);
+        }
+        const float alpha = render_alpha(res, C.act_shift, C.interval);
+        if (alpha <= C.thres) continue;
+        const float weight = __fmul_rn(T_cum, alpha);
+        T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, alpha));
+        if (weight <= C.thres) continue;
+        ++ns;
+        if (!update_tmin) { tmin_out = __fsub_rn(t, R.steplen); update_tmin = true; }
+        if ((double)T_cum < 1e-3) { tmax_out = t; break; }
+    }
+    n_samples[local] = ns;
+    tmins[local] = tmin_out;
+    tmaxs[local] = tmax_out;
+}
+
+// ---- exclusive scan over npix ints: 4096 items per CTA, then the block sums, then the offsets
+__global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n,
+                                                      int32_t* __restrict__ block_sums) {
+    __shared__ int wsum[32];
+    const int base = blockIdx.x * 4096 + threadIdx.x * 4;
+    int v[4], s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    int excl = incl - s + (wid ? wsum[wid - 1] : 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { if (base + i < n) out[base + i] = excl; excl += v[i]; }
+    if (threadIdx.x == 1023) block_sums[blockIdx.x] = excl;
+}
+__global__ void __launch_bounds__(1024) k_scan_tops(int32_t* __restrict__ block_sums, int nb) {
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int own = threadIdx.x < nb ? block_sums[threadIdx.x] : 0;
+    int incl = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    const int excl = incl - own + (wid ? wsum[wid - 1] : 0);
+    if (threadIdx.x < nb) block_sums[threadIdx.x] = excl;
+    if (threadIdx.x == nb - 1) block_sums[nb] = excl + own;   // grand total
+}
+__global__ void __launch_bounds__(1024) k_scan_add(int32_t* __restrict__ out, int n, const int32_t* __restrict__ block_sums, int nb,
+                                                   int32_t* __restrict__ counters, int64_t cap) {
+    const int base = blockIdx.x * 4096 + threadIdx.x * 4;
+    const int off = block_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (base + i < n) out[base + i] += off;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int total = block_sums[nb];
+        out[n] = total;
+        counters[RC_TOTAL] = total;
+        counters[RC_OVERFLOW] = total > cap ? 1 : 0;
+        counters[RC_INCONSISTENT] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float* __restrict__ c2w, int row_begin, int rows,
+                                                      const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
+                                                      const float* __restrict__ tmins, const float* __restrict__ tmaxs,
+                                                      int32_t* __restrict__ s_ray, float* __restrict__ s_weight,
+                                                      float* __restrict__ s_feat, int64_t cap, float* __restrict__ out_rgb,
+                                                      int32_t* __restrict__ counters) {
+    int local;
+    if (pixel_of_thread(C.W, rows, local) < 0) return;
+    const int ns = n_samples[local];
+    if (ns == 0) {   // :324-329
+        out_rgb[local * 3] = C.bg; out_rgb[local * 3 + 1] = C.bg; out_rgb[local * 3 + 2] = C.bg;
+        return;
+    }
+    const int n = row_begin * C.W + local;
+    Ray R;
+    ray_setup(C, c2w, n, R);
+    MarchState S;
+    PvdbLeafCache vcache;
+    float T_cum = 1.0f, t = tmins[local];
+    const float tmax = tmaxs[local];
+    const int64_t i0 = i_starts[local];
+    int r = 0;
+    while (t < tmax) {
+        t = __fadd_rn(t, R.steplen);
+        float xyz[3];
+        int leaf;
+        if (!step_active(C, R, S, t, xyz, leaf)) continue;
+        // trigetDensity2 (:271-300)
+        const int i = (int)xyz[0], j = (int)xyz[1], k = (int)xyz[2];
+        const float u = __fsub_rn(xyz[0], (float)i), v = __fsub_rn(xyz[1], (float)j), w = __fsub_rn(xyz[2], (float)k);
+        int idx[8];
+        float sc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+            idx[q] = idx_at(C, vcache, i + dx, j + dy, k + dz);
+            const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
+            sc[q] = __fmul_rn(__fmul_rn(f0, f1), f2);
+        }
+        // d0*s0 + d1*s1 + ... -> fma(d7,s7, ... fma(d2,s2, fma(d0,s0, d1*s1)))
+        float vden = __fmaf_rn(__ldg(C.dendata + idx[0]), sc[0], __fmul_rn(__ldg(C.dendata + idx[1]), sc[1]));
+#pragma unroll
+        for (int q = 2; q < 8; ++q) vden = __fmaf_rn(__ldg(C.dendata + idx[q]), sc[q], vden);
+        const float alpha = render_alpha(vden, C.act_shift, C.interval);
+        if (alpha <= C.thres) continue;
+        const float weight = __fmul_rn(T_cum, alpha);
+        T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, alpha));
+        if (weight <= C.thres) continue;
+        if (r < ns && i0 + r < cap) {
+            // trigetColor (:303-310), 12 channels as 3 float4 rows per corner
+            float4 f[3];
+#pragma unroll
+            for (int c4 = 0; c4 < 3; ++c4) {
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[0] * 12) + c4);
+                const float4 a1 = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[1] * 12) + c4);
+                f[c4].x = __fmaf_rn(a0.x, sc[0], __fmul_rn(a1.x, sc[1])); f[c4].y = __fmaf_rn(a0.y, sc[0], __fmul_rn(a1.y, sc[1]));
+                f[c4].z = __fmaf_rn(a0.z, sc[0], __fmul_rn(a1.z, sc[1])); f[c4].w = __fmaf_rn(a0.w, sc[0], __fmul_rn(a1.w, sc[1]));
+            }
+#pragma unroll
+            for (int q = 2; q < 8; ++q)
+#pragma unroll
+                for (int c4 = 0; c4 < 3; ++c4) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[q] * 12) + c4);
+                    f[c4].x = __fmaf_rn(a.x, sc[q], f[c4].x); f[c4].y = __fmaf_rn(a.y, sc[q], f[c4].y);
+                    f[c4].z = __fmaf_rn(a.z, sc[q], f[c4].z); f[c4].w = __fmaf_rn(a.w, sc[q], f[c4].w);
+                }
+            float4* dst = reinterpret_cast<float4*>(s_feat + (i0 + r) * 12);
+            dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];
+            s_weight[i0 + r] = weight;
+            s_ray[i0 + r] = local;
+        }
+        ++r;
+    }
+    if (r != ns) {
+        atomicAdd(counters + RC_INCONSISTENT, 1);
+        // keep the tail of the segment well defined: zero weight contributes nothing
+        for (int q = r; q < ns; ++q)
+            if (i0 + q < cap) {
+                s_weight[i0 + q] = 0.f; s_ray[i0 + q] = local;
+                float4* dst = reinterpret_cast<float4*>(s_feat + (i0 + q) * 12);
+                dst[0] = dst[1] = dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+    }
+    const float last = __fmul_rn(T_cum, C.bg);   // :364-365
+    out_rgb[local * 3] = last; out_rgb[local * 3 + 1] = last; out_rgb[local * 3 + 2] = last;
+}
+
+struct RenderMlpArgs {
+    RenderConst C;
+    const float* c2w;
+    const float *w0, *b0, *w1, *b1, *w2, *b2;
+    const int32_t* s_ray; const float* s_weight; const float* s_feat; float* s_rgb;
+    const int32_t* counters; int64_t cap; int row_begin;
+};
+
+__global__ void __launch_bounds__(NT, 1) k_render_mlp(RenderMlpArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW0t = smem;                    // [KX][128]  (w0 is already k-major: w0[i][j], run.py:98)
+    float* sW1t = sW0t + KX * W;           // [128][128]
+    float* sW2 = sW1t + W * W;             // [3][128]   sW2[j][i] = w2[i][j]
+    float* sb0 = sW2 + 3 * W;
+    float* sb1 = sb0 + W;
+    float* sb2 = sb1 + W;
+    float* sX = sb2 + 4;
+    float* sH0 = sX + TS * LDX;
+    float* sH1 = sH0 + TS * LDH;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int e = tid; e < KX * W; e += NT) sW0t[e] = e < DIN * W ? __ldg(A.w0 + e) : 0.f;
+    for (int e = tid; e < W * W; e += NT) sW1t[e] = __ldg(A.w1 + e);
+    for (int e = tid; e < 3 * W; e += NT) { const int j = e / W, i = e % W; sW2[e] = __ldg(A.w2 + i * 3 + j); }
+    if (tid < W) { sb0[tid] = __ldg(A.b0 + tid); sb1[tid] = __ldg(A.b1 + tid); }
+    if (tid < 3) sb2[tid] = __ldg(A.b2 + tid);
+    const int64_t M = min((int64_t)A.counters[RC_TOTAL], A.cap);
+    const int64_t n_tiles = (M + TS - 1) / TS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * TS;
+        __syncthreads();
+        if (tid < 192) {
+            const int s = tid / 3, c4 = tid % 3;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s0 + s < M) f = __ldg(reinterpret_cast<const float4*>(A.s_feat + (s0 + s) * 12) + c4);
+            *reinterpret_cast<float4*>(sX + s * LDX + c4 * 4) = f;
+        } else {
+            const int s = tid - 192;
+            float pe[27];
+#pragma unroll
+            for (int i = 0; i < 27; ++i) pe[i] = 0.f;
+            if (s0 + s < M) {
+                Ray R;
+                ray_setup(A.C, A.c2w, A.row_begin * A.C.W + A.s_ray[s0 + s], R);
+                pe[0] = R.vd[0]; pe[1] = R.vd[1]; pe[2] = R.vd[2];
+                // pefeat (:153-166): sin/cos(viewdir * pebase), pebase = 1,2,4,8 as int -> float
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float x = __fmul_rn(R.vd[a], (float)(1 << k));
+                        pe[3 + k + 4 * a] = sinf(x);
+                        pe[15 + k + 4 * a] = cosf(x);
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 27; ++i) sX[s * LDX + 12 + i] = pe[i];
+            sX[s * LDX + 39] = 0.f;
+        }
+        __syncthreads();
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = sb0[(c < 4 ? 0 : 64) + tx * 4 + (c & 3)];
+        gemm_4x8<KX, LDX, W>(sX, sW0t, ty, tx, acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<float4*>(sH0 + (ty * 4 + i) * LDH + tx * 4) =
+                make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
+            *reinterpret_cast<float4*>(sH0 + (ty * 4 + i) * LDH + 64 + tx * 4) =
+                make_float4(fmaxf(acc[i][4], 0.f), fmaxf(acc[i][5], 0.f), fmaxf(acc[i][6], 0.f), fmaxf(acc[i][7], 0.f));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = sb1[(c < 4 ? 0 : 64) + tx * 4 + (c & 3)];
+        gemm_4x8<W, LDH, W>(sH0, sW1t, ty, tx, acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<float4*>(sH1 + (ty * 4 + i) * LDH + tx * 4) =
+                make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
+            *reinterpret_cast<float4*>(sH1 + (ty * 4 + i) * LDH + 64 + tx * 4) =
+                make_float4(fmaxf(acc[i][4], 0.f), fmaxf(acc[i][5], 0.f), fmaxf(acc[i][6], 0.f), fmaxf(acc[i][7], 0.f));
+        }
+        __syncthreads();
+        if (tid < 192) {
+            const int s = tid / 3, j = tid % 3;
+            float a = sb2[j];
+#pragma unroll 8
+            for (int i = 0; i < W; ++i) a = fmaf(sH1[s * LDH + i], sW2[j * W + i], a);
+            // final_render (:115-117): weight / (1 + exp(-raw))
+            if (s0 + s < M) A.s_rgb[(s0 + s) * 3 + j] = A.s_weight[s0 + s] / (1 + expf(-a));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_render_composite(const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
+                                                          const float* __restrict__ s_rgb, int npix, int64_t cap,
+                                                          float* __restrict__ out_rgb) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const int ns = n_samples[p];
+    if (ns == 0) return;
+    const int64_t i0 = i_starts[p];
+    float r = out_rgb[p * 3], g = out_rgb[p * 3 + 1], b = out_rgb[p * 3 + 2];
+    for (int64_t s = i0; s < i0 + ns && s < cap; ++s) {
+        r = __fadd_rn(r, s_rgb[s * 3]); g = __fadd_rn(g, s_rgb[s * 3 + 1]); b = __fadd_rn(b, s_rgb[s * 3 + 2]);
+    }
+    out_rgb[p * 3] = r; out_rgb[p * 3 + 1] = g; out_rgb[p * 3 + 2] = b;
+}
+
+constexpr size_t RENDER_MLP_SMEM = (size_t)(KX * W + W * W + 3 * W + W + W + 4 + TS * LDX + 2 * TS * LDH) * sizeof(float);
+
+// vdb_compression.py:36-48: dendata[row], coldata[row][:] of every masked voxel, rounded through fp16 (:56-57)
+__global__ void __launch_bounds__(256) k_merge_gather(pvdb_tree t, const float* __restrict__ den, const float* __restrict__ k0, int cdim,
+                                                      const int32_t* __restrict__ row_of_voxel, int rx, int ry, int rz,
+                                                      float* __restrict__ dendata, float* __restrict__ coldata) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (int64_t)rx * ry * rz) return;
+    const int row = row_of_voxel[v];
+    if (row <= 0) return;
+    const int z = (int)(v % rz), y = (int)((v / rz) % ry), x = (int)(v / ((int64_t)rz * ry));
+    const int leaf = pvdb_find_leaf(t, x, y, z);
+    const int off = pvdb_leaf_off(x, y, z);
+    dendata[row] = __half2float(__float2half_rn(leaf >= 0 ? den[(size_t)leaf * 512 + off] : 0.f));
+    for (int c = 0; c < cdim; ++c)
+        coldata[(size_t)row * cdim + c] = __half2float(__float2half_rn(leaf >= 0 ? k0[((size_t)leaf * 512 + off) * cdim + c] : 0.f));
+}
+
+}  // namespace
+
+extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const float* c2w, int row_begin, int row_end,
+                                float* out_rgb, void* stream) {
+    PVDB_CHECK_ARG(cfg && b && b->idx_tree && c2w && out_rgb, "null pointer");
+    PVDB_CHECK_ARG(cfg->dcol == 12 && cfg->dpe == 27 && cfg->dhid == 128 && cfg->dout == 3,
+                   "the merged renderer is specialised for MGRenderer(12, 27, 128, 3) (run.py:77-82)");
+    PVDB_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= cfg->H, "bad row range");
+    PVDB_CHECK_ARG(!cfg->use_tensor_cores, "tensor-core renderer MLP not built");
+    cudaStream_t st = (cudaStream_t)stream;
+    pvdb_reset_launch_count();
+    pvdb_prof_begin(st);
+    RenderConst C;
+    C.tree = *b->idx_tree; C.idx_plane = b->idx_plane; C.dendata = b->dendata; C.coldata = b->coldata;
+    for (int i = 0; i < 9; ++i) C.K[i] = cfg->K[i];
+    for (int a = 0; a < 3; ++a) {
+        C.xyz_min[a] = cfg->xyz_min[a];
+        C.ext[a] = cfg->xyz_max[a] - cfg->xyz_min[a];
+        C.wld[a] = (float)(cfg->reso[a] - 1);
+    }
+    C.near = cfg->near; C.stepdist = cfg->stepdist; C.act_shift = cfg->act_shift; C.interval = cfg->interval;
+    C.thres = cfg->fast_color_thres; C.bg = cfg->bg; C.inverse_y = cfg->inverse_y; C.H = cfg->H; C.W = cfg->W;
+    const int rows = row_end - row_begin, npix = rows * cfg->W;
+    const int tiles = ((cfg->W + 7) / 8) * ((rows + 3) / 4);
+    const int pgrid = pvdb_grid_for((int64_t)tiles * 32, 256);
+    k_render_pass1<<<pgrid, 256, 0, st>>>(C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("render_pass1", st);
+    const int nb = (npix + 4095) / 4096;
+    PVDB_CHECK_ARG(nb <= 1023, "row band too large for the scan (max 4M pixels per call)");
+    k_scan_blocks<<<nb, 1024, 0, st>>>(b->n_samples, b->i_starts, npix, b->scan_tmp);
+    PVDB_LAUNCH_CHECK();
+    k_scan_tops<<<1, 1024, 0, st>>>(b->scan_tmp, nb);
+    PVDB_LAUNCH_CHECK();
+    k_scan_add<<<nb, 1024, 0, st>>>(b->i_starts, npix, b->scan_tmp, nb, b->counters, b->cap_samples);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("render_scan", st);
+    k_render_pass2<<<pgrid, 256, 0, st>>>(C, c2w, row_begin, rows, b->n_samples, b->i_starts, b->tmins, b->tmaxs, b->s_ray,
+                                          b->s_weight, b->s_feat, b->cap_samples, out_rgb, b->counters);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("render_pass2", st);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PVDB_CUDA(cudaFuncSetAttribute(k_render_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RENDER_MLP_SMEM));
+        attr_set = true;
+    }
+    RenderMlpArgs A;
+    A.C = C; A.c2w = c2w; A.w0 = b->w0; A.b0 = b->b0; A.w1 = b->w1; A.b1 = b->b1; A.w2 = b->w2; A.b2 = b->b2;
+    A.s_ray = b->s_ray; A.s_weight = b->s_weight; A.s_feat = b->s_feat; A.s_rgb = b->s_rgb; A.counters = b->counters;
+    A.cap = b->cap_samples; A.row_begin = row_begin;
+    k_render_mlp<<<PVDB_SMS, NT, RENDER_MLP_SMEM, st>>>(A);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("render_mlp", st);
+    k_render_composite<<<pvdb_grid_for(npix, 256), 256, 0, st>>>(b->n_samples, b->i_starts, b->s_rgb, npix, b->cap_samples, out_rgb);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("render_composite", st);
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_merge_gather(const pvdb_tree* tree, const float* den, const float* k0, int k0_dim, const int32_t* row_of_voxel,
+                                 int rx, int ry, int rz, float* dendata, float* coldata, void* stream) {
+    PVDB_CHECK_ARG(tree && den && k0 && row_of_voxel && dendata && coldata && k0_dim > 0, "bad arguments");
+    const int64_t n = (int64_t)rx * ry * rz;
+    k_merge_gather<<<pvdb_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*tree, den, k0, k0_dim, row_of_voxel, rx, ry, rz, dendata,
+                                                                             coldata);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}

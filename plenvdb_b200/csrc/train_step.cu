@@ -168,6 +168,38 @@ __global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const 
     }
 }
 
+// hit_coarse_geo (dvgo.py:253-270): does any in-bbox sample of the ray fall in an occupied voxel?  Feeds the
+// 'in_maskcache' ray sampler (dvgo.py:583-625).  One warp per ray, occupancy bits only.
+__global__ void __launch_bounds__(256) k_hit_mask(MarchParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                  int n_rays, uint8_t* __restrict__ hit) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    float o[3] = {__ldg(rays_o + r * 3), __ldg(rays_o + r * 3 + 1), __ldg(rays_o + r * 3 + 2)};
+    float d[3] = {__ldg(rays_d + r * 3), __ldg(rays_d + r * 3 + 1), __ldg(rays_d + r * 3 + 2)};
+    float tmin, tmax, st[3], dir[3];
+    pvdb_ray_t_minmax(o, d, P.xyz_min, P.xyz_max, P.near, P.far, tmin, tmax);
+    const int nsteps = (int)pvdb_ray_n_samples(d, tmin, tmax, P.stepdist);
+    pvdb_ray_start_dir(o, d, tmin, st, dir);
+    bool any = false;
+    for (int base = 0; base < nsteps && !any; base += 32) {
+        const int step = base + lane;
+        bool in_mask = false;
+        if (step < nsteps) {
+            float px, py, pz;
+            pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, step, px, py, pz);
+            const bool outb = (P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) | (P.xyz_max[0] < px) |
+                              (P.xyz_max[1] < py) | (P.xyz_max[2] < pz);
+            if (!outb)
+                in_mask = occ_test(P, pvdb_mask_ijk(px, P.mask_scale[0], P.mask_shift[0]),
+                                   pvdb_mask_ijk(py, P.mask_scale[1], P.mask_shift[1]),
+                                   pvdb_mask_ijk(pz, P.mask_scale[2], P.mask_shift[2]));
+        }
+        any = __ballot_sync(0xffffffffu, in_mask) != 0;
+    }
+    if (lane == 0) hit[r] = any ? 1 : 0;
+}
+
 // Exclusive scans of the two per-ray counts; single CTA (n_rays is 8192..65536).
 __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck,
                                                       int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
@@ -481,6 +513,18 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     return 0;
 }
 
+extern "C" int pvdb_rays_hit_mask(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* rays_o, const float* rays_d,
+                                  int n_rays, uint8_t* hit, void* stream) {
+    PVDB_CHECK_ARG(cfg && b && b->tree && rays_o && rays_d && hit, "null pointer");
+    if (n_rays <= 0) return PVDB_OK;
+    MarchParams P;
+    MarchOut O;
+    fill_march(cfg, b, P, O);
+    k_hit_mask<<<pvdb_grid_for((int64_t)n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(P, rays_o, rays_d, n_rays, hit);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
 extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* rays_o, const float* rays_d,
                                const float* viewdirs, const float* target, int n_rays, int phases, void* stream) {
     PVDB_CHECK_ARG(cfg && b && b->tree, "null cfg/bufs");
@@ -492,6 +536,7 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
                    "the fused update implements stepmode 1 (skip zero grad); use pvdb_adam_step for modes 0/2");
     cudaStream_t st = (cudaStream_t)stream;
     pvdb_reset_launch_count();
+    pvdb_prof_begin(st);
     MarchParams P;
     MarchOut O;
     fill_march(cfg, b, P, O);
@@ -503,13 +548,17 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         if (cfg->parity_counts) k_march<0, true><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
         else k_march<0, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("march_count", st);
         k_scan_counts<<<1, 1024, 0, st>>>(b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays, b->counters, b->cap_alpha,
                                           b->cap_keep);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("scan", st);
         k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("march_emit", st);
         int rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
         if (rc) return rc;
+        pvdb_prof_mark("rgbnet_fwd", st);
         PVDB_CUDA(cudaMemsetAsync(b->loss, 0, 4 * sizeof(float), st));
         CompositeParams C;
         C.off_keep = b->off_keep; C.k_sample = b->k_sample; C.s_weight = b->s_weight; C.k_rgb = b->k_rgb; C.k_gw = b->k_gw;
@@ -518,6 +567,7 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         C.w_per = cfg->weight_rgbper; C.inv_N = 1.0f / (float)n_glob; C.cap_keep = b->cap_keep; C.do_backward = do_bwd ? 1 : 0;
         k_composite<<<warp_grid, 256, 0, st>>>(C, n_rays);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("composite", st);
         if (target) {
             k_finish_loss<<<1, 1, 0, st>>>(b->loss, cfg->weight_main, cfg->weight_entropy_last, cfg->weight_rgbper);
             PVDB_LAUNCH_CHECK();
@@ -526,14 +576,17 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
     if (do_bwd) {
         int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
         if (rc) return rc;
+        pvdb_prof_mark("rgbnet_bwd", st);
         k_ray_bwd<<<pvdb_grid_for(n_rays, 128), 128, 0, st>>>(b->off_alpha, b->off_keep, b->s_alpha, b->s_T, b->s_weight, b->s_density,
                                                              b->k_gw, b->alphainv_last, b->grad_last, b->s_gden, n_rays,
                                                              cfg->fast_color_thres, cfg->act_shift, cfg->interval, b->cap_alpha,
                                                              b->cap_keep);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("ray_bwd", st);
         k_density_scatter<<<PVDB_SMS * 8, 256, 0, st>>>(*b->tree, b->den_grad, b->s_xyz, b->s_gden, b->counters, b->den_touched,
                                                         b->cap_alpha);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("density_scatter", st);
     }
     if (do_upd) {
         const int n_leaf = b->tree->n_leaf;
@@ -545,18 +598,22 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         k_touched_compact<<<pvdb_grid_for(n_leaf, 256), 256, 0, st>>>(b->k0_touched, n_leaf, b->k0_touched_list,
                                                                       b->counters + CNT_N_TOUCHED_K0);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("touched_compact", st);
         k_sparse_adam<1><<<PVDB_SMS * 4, 256, 0, st>>>(*b->tree, b->den, b->den_grad, b->den_m, b->den_v, 1, cfg->den_stepsz, cfg->eps,
                                                        cfg->beta0, cfg->beta1, b->den_touched_list, b->counters + CNT_N_TOUCHED_DEN,
                                                        b->den_touched, 1);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("adam_density", st);
         k_sparse_adam<3><<<PVDB_SMS * 4, 256, 0, st>>>(*b->tree, b->k0, b->k0_grad, b->k0_m, b->k0_v, 12, cfg->k0_stepsz, cfg->eps,
                                                        cfg->beta0, cfg->beta1, b->k0_touched_list, b->counters + CNT_N_TOUCHED_K0,
                                                        b->k0_touched, 1);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("adam_k0", st);
         const float ss = pvdb_dense_adam_stepsize(cfg->net_lr, cfg->beta0, cfg->beta1, cfg->net_step);
         k_net_adam<<<pvdb_grid_for(PVDB_NET_N, 256), 256, 0, st>>>(b->net, b->net_grad, b->net_m, b->net_v, PVDB_NET_N, ss, cfg->beta0,
                                                                    cfg->beta1, cfg->eps, 1);
         PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("adam_rgbnet", st);
     }
     return PVDB_OK;
 }

@@ -1,0 +1,106 @@
+"""Multi-GPU paths; the reference has none (single process, one GPU: run.py:31,696).
+
+Training: data parallel, one process per GPU, replicated grids and rgbnet, ray batch sharded.  One exchange per
+iteration between the backward and the update phases of the fused step:
+  1. all-reduce(MAX) of the per-leaf touched flags (density and k0)            -> union of touched leaves
+  2. gather the union leaves' gradient tiles into one contiguous buffer [n_union, 512, 13] + 22019 rgbnet grads
+  3. all-reduce(SUM) of that buffer (NCCL over NVLink), scatter back
+after which every rank runs the identical sparse Adam.  The losses are means over the GLOBAL batch
+(cfg.n_rays_global), so the summed shard gradients equal the single-GPU full-batch gradients.
+
+Rendering: replicas + contiguous row bands, no collective but the final gather.
+"""
+import torch
+import torch.distributed as dist
+
+from .fused import PHASE_BACKWARD, PHASE_FORWARD, FusedTrainer
+
+
+def init_from_env(backend=None):
+    """torchrun-style init: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, local, world
+
+
+def shard_range(n, rank, world):
+    """Contiguous shard [lo, hi) of n items; the union over ranks is exactly range(n)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def union_touched(den_touched, k0_touched, group=None):
+    """In-place MAX all-reduce of the two flag arrays (NCCL has no OR); returns the sorted union leaf ids."""
+    flags = torch.maximum(den_touched, k0_touched)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+    den_touched.copy_(flags)
+    k0_touched.copy_(flags)
+    return torch.nonzero(flags, as_tuple=False).reshape(-1)
+
+
+def allreduce_sparse_grads(den_grad, k0_grad, net_grad, leaves, group=None):
+    """SUM all-reduce of the gradient tiles of `leaves` (+ rgbnet grads) through one packed buffer."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return 0
+    n = leaves.numel()
+    nd, nk = n * 512, n * 512 * 12
+    buf = torch.empty(nd + nk + net_grad.numel(), dtype=torch.float32, device=den_grad.device)
+    buf[:nd] = den_grad[leaves].reshape(-1)
+    buf[nd:nd + nk] = k0_grad[leaves].reshape(-1)
+    buf[nd + nk:] = net_grad
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    den_grad[leaves] = buf[:nd].reshape(n, 512, 1)
+    k0_grad[leaves] = buf[nd:nd + nk].reshape(n, 512, 12)
+    net_grad.copy_(buf[nd + nk:])
+    return buf.numel() * 4
+
+
+class DataParallelTrainer:
+    """FusedTrainer + the gradient exchange.  `n_rays` is the PER-RANK shard size."""
+
+    def __init__(self, params, density, k0, mask, net, n_rays, world=None, group=None, **kw):
+        self.group = group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.tr = FusedTrainer(params, density, k0, mask, net, n_rays, n_rays_global=n_rays * self.world, **kw)
+        self.last_exchange_bytes = 0
+
+    def step(self, rays_o, rays_d, viewdirs, target):
+        tr = self.tr
+        if self.world == 1:
+            tr.step(rays_o, rays_d, viewdirs, target)
+            return
+        tr.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD)
+        leaves = union_touched(tr.t["den_touched"], tr.t["k0_touched"], self.group)
+        self.last_exchange_bytes = allreduce_sparse_grads(tr.density.grad, tr.k0.grad, tr.net_grad, leaves, self.group)
+        tr.update()
+
+
+def render_sharded(renderer, c2w_dev, rank, world, gather=True, group=None):
+    """Rank `rank` renders its contiguous row band; rank 0 gets the full [H, W, 3] frame when gather=True."""
+    H, W = renderer.cfg.H, renderer.cfg.W
+    lo, hi = shard_range(H, rank, world)
+    band = renderer.render_rows_torch(c2w_dev, lo, hi)
+    if world == 1 or not gather:
+        return band
+    sizes = [shard_range(H, r, world) for r in range(world)]
+    max_rows = max(b - a for a, b in sizes)
+    if band.shape[0] < max_rows:   # NCCL gather wants equal shapes: pad the short bands
+        band = torch.cat([band, band.new_zeros((max_rows - band.shape[0], W, 3))], 0)
+    if rank == 0:
+        parts = [torch.empty((max_rows, W, 3), dtype=torch.float32, device=band.device) for _ in sizes]
+        dist.gather(band, parts, dst=0, group=group)
+        return torch.cat([p[: b - a] for p, (a, b) in zip(parts, sizes)], 0)
+    dist.gather(band, None, dst=0, group=group)
+    return None

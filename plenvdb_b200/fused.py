@@ -167,6 +167,14 @@ class FusedTrainer:
         self.run(rays_o, rays_d, viewdirs, None, PHASE_FORWARD)
         return self.t["rgb_marched"][: rays_o.shape[0]]
 
+    def hit_mask(self, rays_o, rays_d):
+        """hit_coarse_geo (dvgo.py:253-270): bool [n] — does the ray touch the occupancy mask?"""
+        n = rays_o.shape[0]
+        hit = torch.zeros(n, dtype=torch.uint8, device=self.dev)
+        _lib.call("pvdb_rays_hit_mask", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(rays_o.contiguous()),
+                  _lib.ptr(rays_d.contiguous()), n, _lib.ptr(hit), _lib.current_stream())
+        return hit.bool()
+
     def launches_last_call(self):
         return int(_lib.lib.pvdb_last_launch_count())
 

@@ -262,3 +262,6 @@ class ColorOpt(_BaseOptimizer):
     """ColorOpt (plenvdb.h:770-790)."""
 
 
+
+
+from .renderer import MGRenderer  # noqa: E402,F401  (plenvdb.h:933-1068)
