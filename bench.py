@@ -34,7 +34,7 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def build_workload(n_batches, device, seed=777, pool_candidates=1 << 21, n_rays=N_RAYS):
+def build_workload(n_batches, device, seed=777, pool_candidates=1 << 21, n_rays=N_RAYS, use_tc=True):
     """Scene + grids + trainer + `n_batches` device-resident ray batches drawn like the fine stage does
     (ray_sampler='in_maskcache', configs/default.py:73; dvgo.py:583-625 keeps the rays that hit the mask)."""
     import torch
@@ -43,7 +43,7 @@ def build_workload(n_batches, device, seed=777, pool_candidates=1 << 21, n_rays=
     scene = synth.make_scene(RESO, "sparse")
     net = synth.rgbnet_init()
     den, k0 = build_scene_grids(scene, device=device)
-    tr = FusedTrainer(scene, den, k0, scene["mask"], net, n_rays, device=device)
+    tr = FusedTrainer(scene, den, k0, scene["mask"], net, n_rays, device=device, use_tensor_cores=use_tc)
     poses, K = synth.train_cameras(100), synth.intrinsics(800, 800)
     rng = np.random.default_rng(seed)
     need = n_batches * n_rays
@@ -147,7 +147,7 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
     nb = K + Wm
     t_setup = time.time()
-    scene, net, den, k0, tr, batches = build_workload(nb, dev, seed=777 + rank)
+    scene, net, den, k0, tr, batches = build_workload(nb, dev, seed=777 + rank, use_tc=not args.fp32_rgbnet)
     if world > 1:
         dp = pdist.DataParallelTrainer.__new__(pdist.DataParallelTrainer)
         dp.group, dp.world, dp.tr, dp.last_exchange_bytes = None, world, tr, 0
@@ -262,7 +262,7 @@ def run_ours(args):
             "config": {"workload": "F160-sparse fine-stage step: 8192 in_maskcache rays/GPU, 100 views 800x800, random-sparse 160^3 "
                                    "(p_drop 0.7), 12-ch k0 + rgbnet(39-128-128-3), stepmode 1",
                        "n_rays_per_gpu": N_RAYS, "l2": "flushed between timed steps (256 MiB write, outside the events)",
-                       "rgbnet": "fp32" if not tr.use_tc else "tcgen05", "parallelism": "dp%d" % world,
+                       "rgbnet": "fp32 cuda cores" if not tr.use_tc else "tcgen05 3xTF32 forward + fp32 backward", "parallelism": "dp%d" % world,
                        "samples": {"M_alpha": cnt["M_alpha"], "M_keep": M3, "touched_leaves_density": cnt["n_touched_den"],
                                    "touched_leaves_k0": cnt["n_touched_k0"]}},
             "warm_l2_ms_per_step": warm_ms,
@@ -299,7 +299,7 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
     H = W = 800
     dend, cold, idx, n = merge_grids(den, k0, scene["mask"])
     w0, b0, w1, b1, w2, b2 = synth.unpack_net(net)
-    r = MGRenderer(12, 27, 128, 3, device=dev)
+    r = MGRenderer(12, 27, 128, 3, device=dev, use_tensor_cores=not args.fp32_rgbnet)
     r.load_data_dense(dend, cold, idx)
     r.load_params(np.ascontiguousarray(w0.T).reshape(-1), b0, np.ascontiguousarray(w1.T).reshape(-1), b1,
                   np.ascontiguousarray(w2.T).reshape(-1), b2)
@@ -407,6 +407,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=20, help="frames timed for the render FPS sub-result")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--fp32-rgbnet", action="store_true", help="use the fp32 CUDA-core rgbnet instead of the tcgen05 one")
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per CPU-baseline step (bounded sample)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

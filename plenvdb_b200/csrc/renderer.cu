@@ -16,57 +16,11 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "mlp_tile.cuh"
+#include "render_ray.cuh"
 
 namespace {
 
 constexpr int RC_TOTAL = 0, RC_OVERFLOW = 1, RC_INCONSISTENT = 2;
-
-struct RenderConst {
-    pvdb_tree tree;
-    const int32_t* idx_plane;
-    const float* dendata;
-    const float* coldata;
-    float K[9];
-    float xyz_min[3], ext[3];     // ext = xyz_max - xyz_min (float sub)
-    float wld[3];                 // reso - 1
-    float near, stepdist, act_shift, interval, thres, bg;
-    int inverse_y, H, W;
-};
-
-struct Ray {
-    float ro[3], rd[3], vd[3];
-    float steplen, tmin, tmax;
-};
-
-// get_rays (:122-167) + get_tminmax (:50-64), instruction order read from the reference PTX.
-__device__ __forceinline__ void ray_setup(const RenderConst& C, const float* __restrict__ c2w, int n, Ray& R) {
-    const float pixeli = (float)((double)(n % C.W) + 0.5), pixelj = (float)((double)(n / C.W) + 0.5);
-    float dir[3];
-    dir[0] = __fdiv_rn(__fsub_rn(pixeli, C.K[2]), C.K[0]);
-    if (C.inverse_y) { dir[1] = __fdiv_rn(__fsub_rn(pixelj, C.K[5]), C.K[4]); dir[2] = 1.f; }
-    else { dir[1] = __fdiv_rn(-__fsub_rn(pixelj, C.K[5]), C.K[4]); dir[2] = -1.f; }
-    float rdw[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        // d0*c0 + d1*c1 + d2*c2  ->  fma(d2,c2, fma(d0,c0, d1*c1))
-        rdw[a] = __fmaf_rn(dir[2], __ldg(c2w + a * 4 + 2), __fmaf_rn(dir[0], __ldg(c2w + a * 4), __fmul_rn(dir[1], __ldg(c2w + a * 4 + 1))));
-        R.ro[a] = __fdiv_rn(__fsub_rn(__ldg(c2w + a * 4 + 3), C.xyz_min[a]), C.ext[a]);
-    }
-    const float len = __fsqrt_rn(__fmaf_rn(rdw[2], rdw[2], __fmaf_rn(rdw[0], rdw[0], __fmul_rn(rdw[1], rdw[1]))));
-    R.steplen = __fdiv_rn(C.stepdist, len);
-    const float inv = __frcp_rn(len);   // Vec3::normalize: *this *= 1/length
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        R.rd[a] = __fdiv_rn(rdw[a], C.ext[a]);
-        R.vd[a] = __fmul_rn(rdw[a], inv);
-    }
-    const float far = 1e9f;   // setKwargs overrides far (plenvdb.h:1008)
-    const float vx = R.rd[0] == 0.f ? 1e-6f : R.rd[0], vy = R.rd[1] == 0.f ? 1e-6f : R.rd[1], vz = R.rd[2] == 0.f ? 1e-6f : R.rd[2];
-    const float ax = __fdiv_rn(__fsub_rn(1.f, R.ro[0]), vx), ay = __fdiv_rn(__fsub_rn(1.f, R.ro[1]), vy), az = __fdiv_rn(__fsub_rn(1.f, R.ro[2]), vz);
-    const float bx = __fdiv_rn(-R.ro[0], vx), by = __fdiv_rn(-R.ro[1], vy), bz = __fdiv_rn(-R.ro[2], vz);
-    R.tmin = fmaxf(fminf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), far), C.near);
-    R.tmax = fmaxf(fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), far), C.near);
-}
 
 // alpha = 1 - pow(1 + exp(v + shift), -interval) exactly as nvcc compiles renderer.cu:256 / :350: the final scale
 // multiply of expf is contracted with the "+ 1" into one fma, so this expression is deliberately left to the
@@ -301,14 +255,6 @@ __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float
     out_rgb[local * 3] = last; out_rgb[local * 3 + 1] = last; out_rgb[local * 3 + 2] = last;
 }
 
-struct RenderMlpArgs {
-    RenderConst C;
-    const float* c2w;
-    const float *w0, *b0, *w1, *b1, *w2, *b2;
-    const int32_t* s_ray; const float* s_weight; const float* s_feat; float* s_rgb;
-    const int32_t* counters; int64_t cap; int row_begin;
-};
-
 __global__ void __launch_bounds__(NT, 1) k_render_mlp(RenderMlpArgs A) {
     extern __shared__ __align__(16) float smem[];
     float* sW0t = smem;                    // [KX][128]  (w0 is already k-major: w0[i][j], run.py:98)
@@ -433,13 +379,14 @@ __global__ void __launch_bounds__(256) k_merge_gather(pvdb_tree t, const float* 
 
 }  // namespace
 
+int pvdb_render_mlp_tc(const void* render_mlp_args, cudaStream_t st);   // rgbnet_tc.cu
+
 extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const float* c2w, int row_begin, int row_end,
                                 float* out_rgb, void* stream) {
     PVDB_CHECK_ARG(cfg && b && b->idx_tree && c2w && out_rgb, "null pointer");
     PVDB_CHECK_ARG(cfg->dcol == 12 && cfg->dpe == 27 && cfg->dhid == 128 && cfg->dout == 3,
                    "the merged renderer is specialised for MGRenderer(12, 27, 128, 3) (run.py:77-82)");
     PVDB_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= cfg->H, "bad row range");
-    PVDB_CHECK_ARG(!cfg->use_tensor_cores, "tensor-core renderer MLP not built");
     cudaStream_t st = (cudaStream_t)stream;
     pvdb_reset_launch_count();
     pvdb_prof_begin(st);
@@ -481,8 +428,13 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
     A.C = C; A.c2w = c2w; A.w0 = b->w0; A.b0 = b->b0; A.w1 = b->w1; A.b1 = b->b1; A.w2 = b->w2; A.b2 = b->b2;
     A.s_ray = b->s_ray; A.s_weight = b->s_weight; A.s_feat = b->s_feat; A.s_rgb = b->s_rgb; A.counters = b->counters;
     A.cap = b->cap_samples; A.row_begin = row_begin;
-    k_render_mlp<<<PVDB_SMS, NT, RENDER_MLP_SMEM, st>>>(A);
-    PVDB_LAUNCH_CHECK();
+    if (cfg->use_tensor_cores) {
+        int rc = pvdb_render_mlp_tc(&A, st);
+        if (rc) return rc;
+    } else {
+        k_render_mlp<<<PVDB_SMS, NT, RENDER_MLP_SMEM, st>>>(A);
+        PVDB_LAUNCH_CHECK();
+    }
     pvdb_prof_mark("render_mlp", st);
     k_render_composite<<<pvdb_grid_for(npix, 256), 256, 0, st>>>(b->n_samples, b->i_starts, b->s_rgb, npix, b->cap_samples, out_rgb);
     PVDB_LAUNCH_CHECK();

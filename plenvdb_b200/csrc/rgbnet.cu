@@ -386,9 +386,7 @@ int pvdb_rgbnet_forward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, con
     return PVDB_OK;
 }
 
-int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
-    PVDB_CUDA(cudaMemsetAsync(b->net_grad, 0, PVDB_NET_N * sizeof(float), st));
-    if (cfg->use_tensor_cores) return pvdb_rgbnet_backward_tc(cfg, b, viewdirs, st);
+int pvdb_rgbnet_backward_fp32(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
     PVDB_CHECK_ARG(b->k_h0 && b->k_h1, "the fp32 rgbnet backward needs the saved activations k_h0/k_h1");
     static bool attr_set = false;
     if (!attr_set) {
@@ -404,14 +402,8 @@ int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, co
     return PVDB_OK;
 }
 
-// Tensor-core path placeholders until rgbnet_tc.cu lands: fail loudly rather than fall back silently.
-#ifndef PVDB_HAVE_RGBNET_TC
-int pvdb_rgbnet_forward_tc(const pvdb_train_cfg*, const pvdb_train_bufs*, const float*, cudaStream_t) {
-    pvdb_set_error("rgbnet tcgen05 path is not built into this library");
-    return PVDB_ERR_STATE;
+int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
+    PVDB_CUDA(cudaMemsetAsync(b->net_grad, 0, PVDB_NET_N * sizeof(float), st));
+    if (cfg->use_tensor_cores) return pvdb_rgbnet_backward_tc(cfg, b, viewdirs, st);
+    return pvdb_rgbnet_backward_fp32(cfg, b, viewdirs, st);
 }
-int pvdb_rgbnet_backward_tc(const pvdb_train_cfg*, const pvdb_train_bufs*, const float*, cudaStream_t) {
-    pvdb_set_error("rgbnet tcgen05 path is not built into this library");
-    return PVDB_ERR_STATE;
-}
-#endif

@@ -29,7 +29,7 @@ def mask_scale_shift(mask_shape, xyz_min, xyz_max):
 
 
 class FusedTrainer:
-    def __init__(self, params, density, k0, mask, net, n_rays, device="cuda", use_tensor_cores=False,
+    def __init__(self, params, density, k0, mask, net, n_rays, device="cuda", use_tensor_cores=True,
                  cap_alpha_per_ray=96, cap_keep_per_ray=64, parity_counts=False, n_rays_global=None):
         """params: dict from synth.scene_params (or the equivalent run.py scalars).
         density: DensityVDB, k0: ColorVDB(12) on the SAME topology (k0.topo is density.topo).
@@ -70,9 +70,9 @@ class FusedTrainer:
             counters=z(16, **i32), loss=z(4, **f32),
         )
         self.use_tc = bool(use_tensor_cores)
-        if not self.use_tc:
-            self.t["k_h0"] = z(ck, 128, **f32)
-            self.t["k_h1"] = z(ck, 128, **f32)
+        # activations kept for the fp32 rgbnet backward (the tcgen05 forward still pairs with it)
+        self.t["k_h0"] = z(ck, 128, **f32)
+        self.t["k_h1"] = z(ck, 128, **f32)
         self.parity_counts = bool(parity_counts)
         self.n_rays_global = int(n_rays_global) if n_rays_global else self.n_rays
         self._bufs = None

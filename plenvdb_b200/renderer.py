@@ -44,14 +44,14 @@ def save_merged(basepath, den, col, idx_dense):
 class MGRenderer:
     """MGRenderer(dcol, dpe, dhid, dout) (plenvdb.h:936-945)."""
 
-    def __init__(self, dcol=12, dpe=27, dhid=128, dout=3, device="cuda"):
+    def __init__(self, dcol=12, dpe=27, dhid=128, dout=3, device="cuda", use_tensor_cores=True):
         self.dcol, self.dpe, self.dhid, self.dout = int(dcol), int(dpe), int(dhid), int(dout)
         self.dev = torch.device(device)
         self.flags = [False] * 5   # load_data, load_params, setScene, setKwargs, input_a_c2w (plenvdb.h:1056)
         self.timer = 0.0
         self.cfg = _lib.pvdb_render_cfg()
         self.cfg.dcol, self.cfg.dpe, self.cfg.dhid, self.cfg.dout = self.dcol, self.dpe, self.dhid, self.dout
-        self.cfg.use_tensor_cores = 0
+        self.cfg.use_tensor_cores = int(bool(use_tensor_cores))   # tcgen05 3xTF32 MLP (fp32 CUDA-core MLP when 0)
         self._scratch_rows = -1
         self.c2w = torch.zeros(16, dtype=torch.float32, device=self.dev)
         self.out = None

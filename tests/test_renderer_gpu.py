@@ -34,14 +34,14 @@ def test_merge_matches_oracle(merged):
     assert float(dend[0]) == 0.0 and float(cold[0].abs().sum()) == 0.0
 
 
-def _renderer(scene, dend, cold, idx, H, W, inverse_y=False):
+def _renderer(scene, dend, cold, idx, H, W, inverse_y=False, use_tc=True):
     from plenvdb_b200 import synth
     from plenvdb_b200.plenvdb import MGRenderer
     net = synth.rgbnet_init()
     w0, b0, w1, b1, w2, b2 = synth.unpack_net(net)
     mlp = (np.ascontiguousarray(w0.T), b0, np.ascontiguousarray(w1.T), b1, np.ascontiguousarray(w2.T), b2)   # run.py:98-104
     K = synth.intrinsics(H, W)
-    r = MGRenderer(12, 27, 128, 3)
+    r = MGRenderer(12, 27, 128, 3, use_tensor_cores=use_tc)
     r.load_data_dense(dend, cold, idx)
     r.load_params(mlp[0].reshape(-1), mlp[1], mlp[2].reshape(-1), mlp[3], mlp[4].reshape(-1), mlp[5])
     r.setScene(list(scene["reso"]), K.reshape(-1), scene["xyz_min"], scene["xyz_max"])
@@ -83,14 +83,15 @@ def test_render_matches_oracle(merged, inverse_y):
     assert np.array_equal(np.concatenate([top, bot]), img)
 
 
-def test_render_matches_reference_kernels(merged):
+@pytest.mark.parametrize("use_tc", [True, False])
+def test_render_matches_reference_kernels(merged, use_tc):
     from oracle import ref
     from plenvdb_b200 import synth
     if not ref.available("gpu"):
         pytest.skip("oracle/_ref/libref_gpu.so not present")
     scene, (dend, cold, idx, n), (wd, wc, widx) = merged
     H = W = 200
-    r, mlp, K = _renderer(scene, dend, cold, idx, H, W)
+    r, mlp, K = _renderer(scene, dend, cold, idx, H, W, use_tc=use_tc)
     rg = ref.RefGrid(scene["reso"], 1, widx != 0, kind="gpu")
     rg.gpu_copy_from_dense(widx)
     for cam in (0, 5):

@@ -1,0 +1,58 @@
+"""The tcgen05 (3xTF32, TMEM-resident activations) rgbnet against the fp32 CUDA-core rgbnet and the oracle:
+tensor-core products are error-compensated, so the fused step must stay inside the 1e-5 parity tolerance."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from plenvdb_b200 import synth
+    scene = synth.make_scene(96, "dense")
+    net = synth.rgbnet_init()
+    # scale the last layer up so the logits are not tiny (default init gives |logit| << 1)
+    rays = synth.ray_batch(2048, H=200, W=200, K=synth.intrinsics(200, 200), seed=777)
+    return scene, net, rays
+
+
+def _run(scene, net, rays, use_tc):
+    from plenvdb_b200.fused import FusedTrainer, build_scene_grids
+    den, k0 = build_scene_grids(scene)
+    tr = FusedTrainer(scene, den, k0, scene["mask"], net, rays[0].shape[0], use_tensor_cores=use_tc)
+    tr.forward_backward(*[_cu(a) for a in rays])
+    torch.cuda.synchronize()
+    return tr, den, k0
+
+
+def test_tc_forward_matches_fp32(setup):
+    scene, net, rays = setup
+    a, *_ = _run(scene, net, rays, False)
+    b, *_ = _run(scene, net, rays, True)
+    M = a.counters()["M_keep"]
+    assert M == b.counters()["M_keep"] and M > 1000
+    for k in ("k_feat", "k_h0", "k_h1"):
+        x, y = a.t[k][:M].cpu().numpy(), b.t[k][:M].cpu().numpy()
+        scale = np.abs(x).max()
+        assert np.abs(x - y).max() <= 2e-6 * max(scale, 1.0), "%s: max err %g (scale %g)" % (k, np.abs(x - y).max(), scale)
+    np.testing.assert_allclose(b.t["rgb_marched"].cpu().numpy(), a.t["rgb_marched"].cpu().numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(b.t["loss"].cpu().numpy(), a.t["loss"].cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(b.net_grad.cpu().numpy(), a.net_grad.cpu().numpy(), rtol=1e-3, atol=1e-6 * float(a.net_grad.abs().max()) * 50)
+
+
+def test_tc_forward_with_large_weights(setup):
+    """Random weights an order of magnitude above the default init: logits of O(10), exercises hi/lo cancellation."""
+    scene, net, rays = setup
+    rng = np.random.default_rng(0)
+    big = (net * 6 + rng.standard_normal(net.size).astype(np.float32) * 0.05).astype(np.float32)
+    a, *_ = _run(scene, big, rays, False)
+    b, *_ = _run(scene, big, rays, True)
+    M = a.counters()["M_keep"]
+    x, y = a.t["k_h1"][:M].cpu().numpy(), b.t["k_h1"][:M].cpu().numpy()
+    assert np.abs(x - y).max() <= 4e-6 * np.abs(x).max()
+    np.testing.assert_allclose(b.t["rgb_marched"].cpu().numpy(), a.t["rgb_marched"].cpu().numpy(), rtol=1e-5, atol=3e-6)
