@@ -42,6 +42,7 @@ class FusedTrainer:
         self.topo = topo
         self.n_rays = int(n_rays)
         self.step_count = 0
+        self.launches_total = 0      # kernels of this library launched through this trainer
         f32 = dict(dtype=torch.float32, device=self.dev)
         i32 = dict(dtype=torch.int32, device=self.dev)
         # optimiser state (DensityOpt / ColorOpt / MaskedAdam equivalents)
@@ -146,6 +147,7 @@ class FusedTrainer:
             self._set_step_scalars()
         _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(rays_o), _lib.ptr(rays_d),
                   _lib.ptr(viewdirs), _lib.ptr(target), n, int(phases), _lib.current_stream())
+        self.launches_total += int(_lib.lib.pvdb_last_launch_count())
 
     def step(self, rays_o, rays_d, viewdirs, target):
         """One full iteration: forward + backward + sparse Adam (grids) + Adam (rgbnet)."""
@@ -161,6 +163,7 @@ class FusedTrainer:
         self._set_step_scalars()
         _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(dummy), _lib.ptr(dummy), _lib.ptr(dummy),
                   None, self.n_rays, PHASE_UPDATE, _lib.current_stream())
+        self.launches_total += int(_lib.lib.pvdb_last_launch_count())
 
     def forward(self, rays_o, rays_d, viewdirs):
         """Render rays through the training model (run.py:171-189); returns rgb_marched [n,3]."""

@@ -1,0 +1,72 @@
+"""Two-GPU data-parallel training step (NCCL) equals the one-GPU step on the union batch, and the
+row-band sharded render equals the single-GPU frame.  Skipped on boxes with fewer than two GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from plenvdb_b200 import dist as pdist
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import FusedTrainer, build_scene_grids
+    pdist.init_from_env()
+    dev = torch.device("cuda", rank)
+    scene = synth.make_scene(96, "sparse")
+    net = synth.rgbnet_init()
+    rays = synth.ray_batch(2048, H=200, W=200, K=synth.intrinsics(200, 200), seed=777)
+    lo, hi = pdist.shard_range(2048, rank, world)
+    den, k0 = build_scene_grids(scene, device=dev)
+    dp = pdist.DataParallelTrainer(scene, den, k0, scene["mask"], net, hi - lo, device=dev)
+    shard = [torch.from_numpy(a[lo:hi].copy()).to(dev) for a in rays]
+    for _ in range(2):
+        dp.step(*shard)
+    torch.cuda.synchronize()
+    res = dict(den=den.get_dense_grid(), k0=k0.get_dense_grid(), net=dp.tr.net.cpu().numpy(), bytes=dp.last_exchange_bytes)
+    if rank == 0:   # single-GPU reference on the full batch
+        den1, k01 = build_scene_grids(scene, device=dev)
+        tr = FusedTrainer(scene, den1, k01, scene["mask"], net, 2048, device=dev)
+        full = [torch.from_numpy(a).to(dev) for a in rays]
+        for _ in range(2):
+            tr.step(*full)
+        torch.cuda.synchronize()
+        res.update(den1=den1.get_dense_grid(), k01=k01.get_dense_grid(), net1=tr.net.cpu().numpy())
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_dp_step_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    a, b = out[0], out[1]
+    # replicas stay identical (same reduced gradients, same Adam)
+    assert np.array_equal(a["den"], b["den"]) and np.array_equal(a["k0"], b["k0"]) and np.array_equal(a["net"], b["net"])
+    assert a["bytes"] > 0
+    for k, k1 in (("den", "den1"), ("k0", "k01"), ("net", "net1")):
+        np.testing.assert_allclose(a[k], a[k1], rtol=1e-3, atol=2e-4, err_msg=k)
