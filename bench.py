@@ -244,12 +244,16 @@ def run_ours(args):
         M3 = cnt["M_keep"]
         b_train = algorithmic_bytes({k: o[k] * scale for k in ("V_mask", "V_den", "V_k0", "V_den_grad")}, N_RAYS)
         mlp_flops_fwd = 2.0 * M3 * (39 * 128 + 128 * 128 + 128 * 3)
-        kern_flops = {"rgbnet_fwd": mlp_flops_fwd, "rgbnet_bwd": 2.0 * mlp_flops_fwd}
+        mlp_pass = 3.0 if tr.use_tc else 1.0      # 3xTF32 issues three tensor-core products per algorithmic product
+        kern_flops = {"rgbnet_fwd": mlp_flops_fwd, "rgbnet_bwd": 2.0 * mlp_flops_fwd,
+                      "rgbnet_bwd_act": 2.0 * M3 * (128 * 128 + 128 * 12), "rgbnet_bwd_wgrad": 2.0 * M3 * (128 * 128 + 128 * 40 + 3 * 128)}
         if top in kern_flops:
             ach = kern_flops[top] / (kern[top] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
                     "traffic": None, "peak_source": which,
-                    "note": "fp32 CUDA-core rgbnet tile kernel measured against the %s bf16 tensor peak" % which}
+                    "tensor_core_flops_issued": kern_flops[top] * mlp_pass,
+                    "note": ("algorithmic fp32 FLOPs of the kernel / its duration, against the %s dense bf16 cuBLAS peak; "
+                             "the tcgen05 path issues 3 TF32 products per algorithmic product (tf32 peak = bf16/2)" % which)}
         else:
             kb = {"march_count": 60 * N_RAYS / 2 + o["V_mask"] * scale + 4 * o["V_den"] * scale,
                   "march_emit": 60 * N_RAYS / 2 + o["V_mask"] * scale + 4 * o["V_den"] * scale + 36 * cnt["M_alpha"]}.get(top, b_train)
@@ -264,7 +268,7 @@ def run_ours(args):
             "config": {"workload": "F160-sparse fine-stage step: 8192 in_maskcache rays/GPU, 100 views 800x800, random-sparse 160^3 "
                                    "(p_drop 0.7), 12-ch k0 + rgbnet(39-128-128-3), stepmode 1",
                        "n_rays_per_gpu": N_RAYS, "l2": "flushed between timed steps (256 MiB write, outside the events)",
-                       "rgbnet": "fp32 cuda cores" if not tr.use_tc else "tcgen05 3xTF32 forward + fp32 backward", "parallelism": "dp%d" % world,
+                       "rgbnet": "fp32 cuda cores" if not tr.use_tc else "tcgen05 3xTF32 forward + backward", "parallelism": "dp%d" % world,
                        "samples": {"M_alpha": cnt["M_alpha"], "M_keep": M3, "touched_leaves_density": cnt["n_touched_den"],
                                    "touched_leaves_k0": cnt["n_touched_k0"]}},
             "warm_l2_ms_per_step": warm_ms,

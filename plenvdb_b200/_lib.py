@@ -67,7 +67,7 @@ class pvdb_train_bufs(C.Structure):
         ("s_xyz", c_ptr), ("s_density", c_ptr), ("s_alpha", c_ptr), ("s_T", c_ptr), ("s_weight", c_ptr), ("s_gden", c_ptr),
         ("k_sample", c_ptr), ("k_ray", c_ptr),
         ("k_xyz", c_ptr), ("k_feat", c_ptr), ("k_rgb", c_ptr), ("k_gw", c_ptr),
-        ("k_h0", c_ptr), ("k_h1", c_ptr),
+        ("k_h0", c_ptr), ("k_h1", c_ptr), ("k_x", c_ptr), ("k_dh0", c_ptr), ("k_dh1", c_ptr), ("k_mask", c_ptr),
         ("den_touched", c_ptr), ("k0_touched", c_ptr), ("den_touched_list", c_ptr), ("k0_touched_list", c_ptr),
         ("counters", c_ptr), ("loss", c_ptr),
     ]

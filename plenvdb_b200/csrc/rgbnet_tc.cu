@@ -17,10 +17,10 @@
 #include "ray_math.cuh"
 #include "rgbnet.cuh"
 #include "render_ray.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
-constexpr int TM = 128;            // samples per tile = UMMA M
 constexpr int WD = PVDB_NET_W;     // 128
 constexpr int K0P = 40;            // layer-0 K (39 padded to a multiple of 8)
 constexpr int N2P = 16;            // layer-2 N (3 padded to the UMMA minimum for M = 128)
@@ -40,110 +40,8 @@ constexpr int SM_B0 = SM_W2LO + N2P * WD * 4;               // [128] floats
 constexpr int SM_B1 = SM_B0 + WD * 4;
 constexpr int SM_B2 = SM_B1 + WD * 4;                       // [4]
 constexpr int SM_BAR = SM_B2 + 16;                          // mbarrier (8 B) + tmem base (4 B)
-constexpr int SM_TOTAL = SM_BAR + 16;
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
-}
-// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, issued by one thread
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-
-// ---- operand helpers ----------------------------------------------------------------------------------------
-// 3xTF32 split: hi keeps the 10 explicit tf32 mantissa bits, lo = x - hi is exact in fp32.
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & 0xffffe000u;
-    lo = __float_as_uint(x - __uint_as_float(hi));
-}
-// byte offset of element (n, k) of a K-major operand with K columns in the canonical no-swizzle UMMA layout:
-// 8-row x 16-byte core matrices, K-chunks of one 8-row group contiguous (LBO = 128 B), groups SBO = K/4*128 B apart.
-__device__ __forceinline__ int canon_off(int n, int k, int K) { return (n >> 3) * (K / 4) * 128 + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4; }
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46, no swizzle
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int K) {
-    const uint64_t lbo = 128 >> 4, sbo = (uint64_t)((K / 4) * 128) >> 4;
-    return (uint64_t)((saddr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc(int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24); }
-
-// Load W[n][k] (strides sn, sk in floats) for n < N_valid, k < K_valid into the canonical layout, split hi / lo.
-__device__ void load_weight(unsigned char* smem, int off_hi, int off_lo, const float* __restrict__ w, int sn, int sk, int N, int K,
-                            int N_valid, int K_valid) {
-    for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
-        const int n = e / K, k = e % K;
-        const float v = (n < N_valid && k < K_valid) ? __ldg(w + (size_t)n * sn + (size_t)k * sk) : 0.f;
-        uint32_t hi, lo;
-        split_tf32(v, hi, lo);
-        const int o = canon_off(n, k, K);
-        *reinterpret_cast<uint32_t*>(smem + off_hi + o) = hi;
-        *reinterpret_cast<uint32_t*>(smem + off_lo + o) = lo;
-    }
-}
+constexpr int SM_XBUF = SM_BAR + 16;                        // staging rows of the next tile: [128][44] floats
+constexpr int SM_TOTAL = SM_XBUF + 128 * 44 * 4;
 
 // Issue the 3xTF32 MMAs of one layer: D[128 x N] = A[128 x K] * W[N x K]^T.  Single thread.
 __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t smem_base, int off_hi, int off_lo, int K, int N, uint32_t bar) {
@@ -179,16 +77,25 @@ struct TcWeights {
     int w0_sn, w0_sk, w1_sn, w1_sk, w2_sn, w2_sk;   // strides (floats) of W[n][k]
 };
 
-// Common body.  FeatFn(s, x[40]) fills the input row of sample s; OutFn(s, raw[3], h0/h1 rows) consumes the result.
+// Common body, warp specialised.  Warps 0-3 ("lane warps", one thread per TMEM lane = sample) run the MLP; warps 4-7
+// ("producers") gather the NEXT tile's input rows (k0 trilinear / feature list + view PE, the memory- and SFU-latency
+// bound part) into a shared staging buffer while the lane warps are busy with the current tile.
+// FeatFn(s, x[40]) fills the input row of sample s; ActFn sees each post-ReLU chunk; OutFn(s, raw[3]) consumes the result.
+constexpr int FWD_THREADS = 256;
+constexpr int XLD = 44;   // staging row stride in floats: 16-byte row reads/writes by 8 consecutive threads hit distinct banks
+__device__ __forceinline__ void lane_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <class FeatFn, class OutFn, class ActFn>
 __device__ void mlp_tiles(unsigned char* smem, const TcWeights& Wt, int64_t M, FeatFn feat, OutFn out, ActFn act) {
     const int tid = threadIdx.x, warp = tid >> 5;
+    const bool lane_warp = tid < TM;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar = sbase + SM_BAR;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8);
     float* sb0 = reinterpret_cast<float*>(smem + SM_B0);
     float* sb1 = reinterpret_cast<float*>(smem + SM_B1);
     float* sb2 = reinterpret_cast<float*>(smem + SM_B2);
+    float* xbuf = reinterpret_cast<float*>(smem + SM_XBUF);
     load_weight(smem, SM_W0HI, SM_W0LO, Wt.w0, Wt.w0_sn, Wt.w0_sk, WD, K0P, WD, PVDB_NET_DIN);
     load_weight(smem, SM_W1HI, SM_W1LO, Wt.w1, Wt.w1_sn, Wt.w1_sk, WD, WD, WD, WD);
     load_weight(smem, SM_W2HI, SM_W2LO, Wt.w2, Wt.w2_sn, Wt.w2_sk, N2P, WD, 3, WD);
@@ -201,23 +108,41 @@ __device__ void mlp_tiles(unsigned char* smem, const TcWeights& Wt, int64_t M, F
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32-lane quarter
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32-lane quarter
     uint32_t parity = 0;
     const int64_t n_tiles = (M + TM - 1) / TM;
+    auto produce = [&](int64_t tile) {
+        const int p = tid - TM;
+        const int64_t s = tile * TM + p;
+        float x[K0P];
+#pragma unroll
+        for (int i = 0; i < K0P; ++i) x[i] = 0.f;
+        if (s < M) feat(s, x);
+        float4* row = reinterpret_cast<float4*>(xbuf + p * XLD);
+#pragma unroll
+        for (int q = 0; q < K0P / 4; ++q) row[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+    };
+    if (!lane_warp && (int64_t)blockIdx.x < n_tiles) produce(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();            // staging buffer holds this tile's rows
+        float x[K0P];
+        if (lane_warp) {
+            const float4* row = reinterpret_cast<const float4*>(xbuf + tid * XLD);
+#pragma unroll
+            for (int q = 0; q < K0P / 4; ++q) { const float4 v = row[q]; x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w; }
+        }
+        __syncthreads();            // staging buffer is free again
+        if (!lane_warp) {
+            if (tile + gridDim.x < n_tiles) produce(tile + gridDim.x);
+            continue;
+        }
         const int64_t s = tile * TM + tid;
         const bool valid = s < M;
         // ---- layer-0 input row -> TMEM
-        {
-            float x[K0P];
-#pragma unroll
-            for (int i = 0; i < K0P; ++i) x[i] = 0.f;
-            if (valid) feat(s, x);
-            store_a_row(lane_addr, 0, x, K0P);
-        }
+        store_a_row(lane_addr, 0, x, K0P);
         tmem_st_wait();
         tc_fence_before();
-        __syncthreads();
+        lane_bar();
         if (tid == 0) { tc_fence_after(); issue_layer(tmem, sbase, SM_W0HI, SM_W0LO, K0P, WD, bar); }
         mbar_wait(bar, parity); parity ^= 1;
         tc_fence_after();
@@ -238,7 +163,7 @@ __device__ void mlp_tiles(unsigned char* smem, const TcWeights& Wt, int64_t M, F
             }
             tmem_st_wait();
             tc_fence_before();
-            __syncthreads();
+            lane_bar();
             if (tid == 0) {
                 tc_fence_after();
                 if (layer == 0) issue_layer(tmem, sbase, SM_W1HI, SM_W1LO, WD, WD, bar);
@@ -258,7 +183,7 @@ __device__ void mlp_tiles(unsigned char* smem, const TcWeights& Wt, int64_t M, F
             }
         }
         tc_fence_before();
-        __syncthreads();     // every lane has drained D before the next tile's MMAs overwrite it
+        lane_bar();          // every lane has drained D before the next tile's MMAs overwrite it
         tc_fence_after();
     }
     __syncthreads();
@@ -282,12 +207,13 @@ __device__ __forceinline__ void view_embed_tc(const float* __restrict__ vd, floa
 struct TrainFwdArgs {
     pvdb_tree tree;
     const float* k0; const float* viewdirs; const int32_t* k_ray; const float* k_xyz;
-    float *k_feat, *k_h0, *k_h1, *k_rgb;
+    float *k_feat, *k_h0, *k_h1, *k_rgb, *k_x;
+    uint32_t* k_mask;
     const int32_t* counters; int64_t cap_keep;
     TcWeights W;
 };
 
-__global__ void __launch_bounds__(TM, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
     auto feat = [&](int64_t s, float* x) {
@@ -314,12 +240,23 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
         float4* kf = reinterpret_cast<float4*>(A.k_feat + s * 12);
         kf[0] = make_float4(x[0], x[1], x[2], x[3]); kf[1] = make_float4(x[4], x[5], x[6], x[7]); kf[2] = make_float4(x[8], x[9], x[10], x[11]);
         view_embed_tc(A.viewdirs + (size_t)A.k_ray[s] * 3, x + 12);
+        if (A.k_x) {   // full input row for the tensor-core weight-gradient pass
+            float4* kx = reinterpret_cast<float4*>(A.k_x + s * 40);
+#pragma unroll
+            for (int q = 0; q < 10; ++q) kx[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+        }
     };
     auto out = [&](int64_t s, const float* raw) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) A.k_rgb[s * 3 + j] = 1.0f / (1.0f + expf(-raw[j]));
     };
     auto act = [&](int64_t s, int layer, int c, const float* h) {
+        if (A.k_mask) {   // ReLU sign bits for the backward: bit i of word (layer*4 + c/32) = h[c+i] > 0
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m |= (h[i] > 0.f ? 1u : 0u) << i;
+            A.k_mask[s * 8 + layer * 4 + (c >> 5)] = m;
+        }
         float* dst = layer == 0 ? A.k_h0 : A.k_h1;
         if (!dst) return;
         float4* g = reinterpret_cast<float4*>(dst + s * WD + c);
@@ -330,7 +267,7 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
 }
 
 // ---- merged renderer MLP (renderer.cu:83-119): features from the gathered list, PE from the pixel's view direction
-__global__ void __launch_bounds__(TM, 1) k_render_mlp_tc(RenderMlpArgs A, TcWeights W) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs A, TcWeights W) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int64_t M = min((int64_t)A.counters[0], A.cap);
     auto feat = [&](int64_t s, float* x) {
@@ -371,21 +308,15 @@ int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     }
     TrainFwdArgs A;
     A.tree = *b->tree; A.k0 = b->k0; A.viewdirs = viewdirs; A.k_ray = b->k_ray; A.k_xyz = b->k_xyz; A.k_feat = b->k_feat;
-    A.k_h0 = b->k_h0; A.k_h1 = b->k_h1; A.k_rgb = b->k_rgb; A.counters = b->counters; A.cap_keep = b->cap_keep;
+    A.k_h0 = b->k_h0; A.k_h1 = b->k_h1; A.k_rgb = b->k_rgb; A.k_x = b->k_x; A.k_mask = b->k_mask; A.counters = b->counters; A.cap_keep = b->cap_keep;
     const float* net = b->net;   // PyTorch layout: W[n][k] row-major
     A.W.w0 = net + PVDB_NET_OFF_W0; A.W.w0_sn = PVDB_NET_DIN; A.W.w0_sk = 1;
     A.W.w1 = net + PVDB_NET_OFF_W1; A.W.w1_sn = WD; A.W.w1_sk = 1;
     A.W.w2 = net + PVDB_NET_OFF_W2; A.W.w2_sn = WD; A.W.w2_sk = 1;
     A.W.b0 = net + PVDB_NET_OFF_B0; A.W.b1 = net + PVDB_NET_OFF_B1; A.W.b2 = net + PVDB_NET_OFF_B2;
-    k_rgbnet_fwd_tc<<<PVDB_SMS, TM, SM_TOTAL, st>>>(A);
+    k_rgbnet_fwd_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
-}
-
-// The tensor-core backward is not written yet: the forward pairs with the fp32 backward (activations saved).
-int pvdb_rgbnet_backward_fp32(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
-int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
-    return pvdb_rgbnet_backward_fp32(cfg, b, viewdirs, st);
 }
 
 int pvdb_render_mlp_tc(const void* render_mlp_args, cudaStream_t st) {
@@ -400,7 +331,7 @@ int pvdb_render_mlp_tc(const void* render_mlp_args, cudaStream_t st) {
     W.w1 = A.w1; W.w1_sn = 1; W.w1_sk = WD;
     W.w2 = A.w2; W.w2_sn = 1; W.w2_sk = 3;
     W.b0 = A.b0; W.b1 = A.b1; W.b2 = A.b2;
-    k_render_mlp_tc<<<PVDB_SMS, TM, SM_TOTAL, st>>>(A, W);
+    k_render_mlp_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A, W);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

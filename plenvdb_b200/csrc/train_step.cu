@@ -576,7 +576,7 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
     if (do_bwd) {
         int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
         if (rc) return rc;
-        pvdb_prof_mark("rgbnet_bwd", st);
+        pvdb_prof_mark(cfg->use_tensor_cores ? "rgbnet_bwd_wgrad" : "rgbnet_bwd", st);
         k_ray_bwd<<<pvdb_grid_for(n_rays, 128), 128, 0, st>>>(b->off_alpha, b->off_keep, b->s_alpha, b->s_T, b->s_weight, b->s_density,
                                                              b->k_gw, b->alphainv_last, b->grad_last, b->s_gden, n_rays,
                                                              cfg->fast_color_thres, cfg->act_shift, cfg->interval, b->cap_alpha,

@@ -41,6 +41,7 @@ class FusedTrainer:
         topo = density.topo
         self.topo = topo
         self.n_rays = int(n_rays)
+        self.use_tc = bool(use_tensor_cores)
         self.step_count = 0
         self.launches_total = 0      # kernels of this library launched through this trainer
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -70,10 +71,14 @@ class FusedTrainer:
             den_touched_list=z(max(topo.n_leaf, 1), **i32), k0_touched_list=z(max(topo.n_leaf, 1), **i32),
             counters=z(16, **i32), loss=z(4, **f32),
         )
-        self.use_tc = bool(use_tensor_cores)
         # activations kept for the fp32 rgbnet backward (the tcgen05 forward still pairs with it)
         self.t["k_h0"] = z(ck, 128, **f32)
         self.t["k_h1"] = z(ck, 128, **f32)
+        if self.use_tc:   # tensor-core backward: input rows and masked activation gradients for the weight-gradient GEMM
+            self.t["k_x"] = z(ck, 40, **f32)
+            self.t["k_dh0"] = z(ck, 128, **f32)
+            self.t["k_dh1"] = z(ck, 128, **f32)
+            self.t["k_mask"] = z(ck, 8, **i32)
         self.parity_counts = bool(parity_counts)
         self.n_rays_global = int(n_rays_global) if n_rays_global else self.n_rays
         self._bufs = None
