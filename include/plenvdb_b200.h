@@ -199,10 +199,11 @@ typedef struct pvdb_train_bufs {
     /* kept list: entries with weight > thres; capacity cap_keep */
     int32_t *k_sample /* index into the alpha list */, *k_ray;
     float *k_xyz /*[.][3]*/, *k_feat /*[.][12]*/, *k_rgb /*[.][3] rgb, then dL/dlogit*/, *k_gw /*[.] dL/dweight*/;
-    float *k_h0, *k_h1;                        /* [.][128] post-ReLU activations kept for the backward */
-    float *k_x;                                /* [.][40] rgbnet input rows (12 k0 + 27 PE + pad), tensor-core path */
-    float *k_dh0, *k_dh1;                      /* [.][128] masked activation gradients, tensor-core backward */
-    uint32_t *k_mask;                          /* [.][8] ReLU sign bits of h0 (words 0-3) and h1 (words 4-7), tensor-core path */
+    float *k_h0, *k_h1;                        /* post-ReLU activations kept for the backward: [.][128] row-major (fp32 path) or
+                                                * tile-transposed [tile][128 features][128 samples] (tensor-core path) */
+    float *k_x;                                /* [tile][40][128] rgbnet inputs (12 k0 + 27 PE + pad), tensor-core path */
+    float *k_dh0, *k_dh1;                      /* [tile][128][128] masked activation gradients, tensor-core backward */
+    uint32_t *k_mask;                          /* [tile][8][128] ReLU sign bits of h0 (words 0-3) and h1 (words 4-7) */
     /* touched-leaf bookkeeping, [n_leaf] each */
     int32_t *den_touched, *k0_touched, *den_touched_list, *k0_touched_list;
     int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0 */

@@ -119,3 +119,9 @@ struct PvdbTri {
     }
     __device__ __forceinline__ float f(int axis, int d) const { return d ? u[axis] : m[axis]; }
 };
+
+// Flag a leaf as touched by a gradient scatter and append it once to the touched-leaf list.  The plain read filters
+// almost every call; the exchange elects the single appender.
+__device__ __forceinline__ void pvdb_touch_leaf(int32_t* __restrict__ flags, int32_t* __restrict__ list, int32_t* __restrict__ count, int leaf) {
+    if (flags[leaf] == 0 && atomicExch(flags + leaf, 1) == 0) list[atomicAdd(count, 1)] = leaf;
+}

@@ -159,7 +159,7 @@ struct NetBwdArgs {
     const float* net; const float* viewdirs;
     const int32_t* k_ray; const float* k_xyz; const float* k_feat; const float* k_h0; const float* k_h1;
     const float* k_glogit;     // [M3][3]
-    float* net_grad; float* k0_grad; int32_t* k0_touched;
+    float* net_grad; float* k0_grad; int32_t* k0_touched; int32_t* k0_touched_list; int32_t* counters_w;
     const int32_t* counters; int64_t cap_keep;
 };
 
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(NT, 1) k_rgbnet_bwd(NetBwdArgs A) {
                     const float sc = __fmul_rn(__fmul_rn(tri.f(0, dx), tri.f(1, dy)), tri.f(2, dz));
                     red_add4(A.k0_grad + ((size_t)leaf * 512 + pvdb_leaf_off(cx, cy, cz)) * 12 + c4 * 4, __fmul_rn(g.x, sc),
                              __fmul_rn(g.y, sc), __fmul_rn(g.z, sc), __fmul_rn(g.w, sc));
-                    if (c4 == 0) A.k0_touched[leaf] = 1;
+                    if (c4 == 0) pvdb_touch_leaf(A.k0_touched, A.k0_touched_list, A.counters_w + 4, leaf);
                 }
             }
         }
@@ -396,7 +396,8 @@ int pvdb_rgbnet_backward_fp32(const pvdb_train_cfg* cfg, const pvdb_train_bufs* 
     NetBwdArgs A;
     A.tree = *b->tree; A.net = b->net; A.viewdirs = viewdirs; A.k_ray = b->k_ray; A.k_xyz = b->k_xyz; A.k_feat = b->k_feat;
     A.k_h0 = b->k_h0; A.k_h1 = b->k_h1; A.k_glogit = b->k_rgb; A.net_grad = b->net_grad; A.k0_grad = b->k0_grad;
-    A.k0_touched = b->k0_touched; A.counters = b->counters; A.cap_keep = b->cap_keep;
+    A.k0_touched = b->k0_touched; A.k0_touched_list = b->k0_touched_list; A.counters_w = b->counters; A.counters = b->counters;
+    A.cap_keep = b->cap_keep;
     k_rgbnet_bwd<<<PVDB_SMS, NT, BWD_SMEM, st>>>(A);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;

@@ -240,10 +240,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
         float4* kf = reinterpret_cast<float4*>(A.k_feat + s * 12);
         kf[0] = make_float4(x[0], x[1], x[2], x[3]); kf[1] = make_float4(x[4], x[5], x[6], x[7]); kf[2] = make_float4(x[8], x[9], x[10], x[11]);
         view_embed_tc(A.viewdirs + (size_t)A.k_ray[s] * 3, x + 12);
-        if (A.k_x) {   // full input row for the tensor-core weight-gradient pass
-            float4* kx = reinterpret_cast<float4*>(A.k_x + s * 40);
+        if (A.k_x) {   // input row for the weight-gradient pass, tile-transposed [tile][40][128]: warp-coalesced stores
+            float* kx = A.k_x + (s >> 7) * (40 * 128) + (s & 127);
 #pragma unroll
-            for (int q = 0; q < 10; ++q) kx[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+            for (int i = 0; i < 40; ++i) kx[i * 128] = x[i];
         }
     };
     auto out = [&](int64_t s, const float* raw) {
@@ -255,13 +255,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
             uint32_t m = 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) m |= (h[i] > 0.f ? 1u : 0u) << i;
-            A.k_mask[s * 8 + layer * 4 + (c >> 5)] = m;
+            A.k_mask[(s >> 7) * (8 * 128) + (layer * 4 + (c >> 5)) * 128 + (s & 127)] = m;   // [tile][8][128]
         }
         float* dst = layer == 0 ? A.k_h0 : A.k_h1;
         if (!dst) return;
-        float4* g = reinterpret_cast<float4*>(dst + s * WD + c);
+        // tile-transposed [tile][128 features][128 samples]: lane l writes word l of a 128-byte line -> one wavefront per
+        // store instead of 32, and the weight-gradient pass reads 4 consecutive samples of a feature as one LDG.128
+        float* g = dst + (s >> 7) * (WD * 128) + (size_t)c * 128 + (s & 127);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = make_float4(h[i * 4], h[i * 4 + 1], h[i * 4 + 2], h[i * 4 + 3]);
+        for (int i = 0; i < 32; ++i) g[i * 128] = h[i];
     };
     mlp_tiles(smem, A.W, M, feat, out, act);
 }

@@ -70,7 +70,7 @@ struct BwdActArgs {
     const float *k_glogit, *k_xyz;
     const uint32_t* k_mask;
     float *k_dh1, *k_dh0;
-    float* k0_grad; int32_t* k0_touched;
+    float* k0_grad; int32_t* k0_touched; int32_t* k0_touched_list; int32_t* counters_w;
     const int32_t* counters; int64_t cap_keep;
 };
 
@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
         if (tile < n_tiles && s < M) {
             v.g0 = __ldg(A.k_glogit + s * 3); v.g1 = __ldg(A.k_glogit + s * 3 + 1); v.g2 = __ldg(A.k_glogit + s * 3 + 2);
             v.px = __ldg(A.k_xyz + s * 3); v.py = __ldg(A.k_xyz + s * 3 + 1); v.pz = __ldg(A.k_xyz + s * 3 + 2);
-            v.m0 = __ldg(reinterpret_cast<const uint4*>(A.k_mask + s * 8));
-            v.m1 = __ldg(reinterpret_cast<const uint4*>(A.k_mask + s * 8) + 1);
+            const uint32_t* mk = A.k_mask + (s >> 7) * (8 * 128) + (s & 127);   // [tile][8][128]
+            v.m0 = make_uint4(__ldg(mk), __ldg(mk + 128), __ldg(mk + 256), __ldg(mk + 384));
+            v.m1 = make_uint4(__ldg(mk + 512), __ldg(mk + 640), __ldg(mk + 768), __ldg(mk + 896));
         }
         return v;
     };
@@ -130,10 +131,10 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
                 const float v = fmaf(g2, sW2[2 * WD + j], fmaf(g1, sW2[WD + j], g0 * sW2[j]));
                 d[i] = (m1w[cc] >> i) & 1u ? v : 0.f;
             }
-            if (valid) {
-                float4* o = reinterpret_cast<float4*>(A.k_dh1 + s * WD + c);
+            if (valid) {   // tile-transposed [tile][128][128], warp-coalesced
+                float* o = A.k_dh1 + (s >> 7) * (WD * 128) + (size_t)c * 128 + (s & 127);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = make_float4(d[q * 4], d[q * 4 + 1], d[q * 4 + 2], d[q * 4 + 3]);
+                for (int i = 0; i < 32; ++i) o[i * 128] = d[i];
             }
             store_a_row32(lane_addr, c, d);
         }
@@ -154,9 +155,9 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) d[i] = (m0w[cc] >> i) & 1u ? __uint_as_float(r[i]) : 0.f;
             if (valid) {
-                float4* o = reinterpret_cast<float4*>(A.k_dh0 + s * WD + c);
+                float* o = A.k_dh0 + (s >> 7) * (WD * 128) + (size_t)c * 128 + (s & 127);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = make_float4(d[q * 4], d[q * 4 + 1], d[q * 4 + 2], d[q * 4 + 3]);
+                for (int i = 0; i < 32; ++i) o[i * 128] = d[i];
             }
             store_a_row32(lane_addr, c, d);
         }
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
                     for (int c4 = 0; c4 < 3; ++c4)
                         red_add4(dst + c4 * 4, __fmul_rn(__uint_as_float(r[c4 * 4]), sc), __fmul_rn(__uint_as_float(r[c4 * 4 + 1]), sc),
                                  __fmul_rn(__uint_as_float(r[c4 * 4 + 2]), sc), __fmul_rn(__uint_as_float(r[c4 * 4 + 3]), sc));
-                    A.k0_touched[leaf] = 1;
+                    pvdb_touch_leaf(A.k0_touched, A.k0_touched_list, A.counters_w + 4, leaf);
                 }
             }
         }
@@ -227,8 +228,18 @@ __device__ __forceinline__ void put_k4(unsigned char* base, int off_hi, int byte
     *reinterpret_cast<uint4*>(base + off_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(base + off_hi + bytes_tile + o) = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// feature column `f` of 4 consecutive rows of a row-major [.][ld] array (zero past M)
-__device__ __forceinline__ float4 col4(const float* __restrict__ a, int64_t s0, int64_t M, int ld, int f) {
+// feature `f` of 4 consecutive samples s0..s0+3 (s0 % 4 == 0) of a tile-transposed array [tile][nf][128]: one LDG.128.
+// Samples past M read as zero (their slots may hold stale data from an earlier, larger batch).
+__device__ __forceinline__ float4 col4(const float* __restrict__ a, int64_t s0, int64_t M, int nf, int f) {
+    if (s0 >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = __ldg(reinterpret_cast<const float4*>(a + (s0 >> 7) * (nf * 128) + (size_t)f * 128 + (s0 & 127)));
+    if (s0 + 1 >= M) v.y = 0.f;
+    if (s0 + 2 >= M) v.z = 0.f;
+    if (s0 + 3 >= M) v.w = 0.f;
+    return v;
+}
+// same for the row-major [.][3] logit gradients
+__device__ __forceinline__ float4 col4_rows(const float* __restrict__ a, int64_t s0, int64_t M, int ld, int f) {
     float4 v;
     v.x = s0 + 0 < M ? __ldg(a + (s0 + 0) * ld + f) : 0.f;
     v.y = s0 + 1 < M ? __ldg(a + (s0 + 1) * ld + f) : 0.f;
@@ -247,7 +258,9 @@ constexpr int B2_THREADS = 512;   // 16 warps stage (memory-latency bound); warp
 __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int f = tid & 127, k4 = tid >> 7;   // feature row and 4-sample group this thread stages
+    // feature row and 4-sample group this thread stages.  Per warp: 8 features x 4 groups; the 8 threads of a quarter warp
+    // take 8 different features (conflict-free 16-byte shared stores), the 4 groups of a feature read 64 contiguous bytes.
+    const int f = (tid >> 5) * 8 + (tid & 7), k4 = (tid >> 3) & 3;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + B2_BAR, bar1 = sbase + B2_BAR + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B2_BAR + 16);
@@ -265,29 +278,40 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
     int issued[2] = {0, 0};
     float gsum = 0.f;
     int it = 0;
+    struct Chunk { float4 a1, b1, a0, a2, xg; };
+    auto load_chunk = [&](int64_t ch) {
+        Chunk c;
+        const int64_t s0 = ch * KC + k4 * 4;
+        const bool live = ch < n_chunks;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        c.a1 = live ? col4(A.k_dh1, s0, M, WD, f) : z;
+        c.b1 = live ? col4(A.k_h0, s0, M, WD, f) : z;
+        c.a0 = live ? col4(A.k_dh0, s0, M, WD, f) : z;
+        c.a2 = live ? col4(A.k_h1, s0, M, WD, f) : z;
+        c.xg = z;
+        if (live && f < 39) c.xg = col4(A.k_x, s0, M, 40, f);
+        else if (live && f >= 64 && f < 67) c.xg = col4_rows(A.k_glogit, s0, M, 3, f - 64);
+        return c;
+    };
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++it) {
         const int st = it & 1;
         unsigned char* sb = smem + st * STAGE;
+        const Chunk cur = load_chunk(ch);
         if (issued[st]) { mbar_wait(st ? bar1 : bar0, par[st]); par[st] ^= 1; }   // MMAs that read this stage are done
-        // ---- stage the six operand tiles, transposed: thread = feature, 4 samples per 16-byte store
+        // ---- stage the six operand tiles, transposed: thread = (feature, 4 samples) -> one 16-byte K-major row
         {
             const int64_t s0 = ch * KC + k4 * 4;
-            const float4 a1 = col4(A.k_dh1, s0, M, WD, f), b1 = col4(A.k_h0, s0, M, WD, f);
-            const float4 a0 = col4(A.k_dh0, s0, M, WD, f), a2 = col4(A.k_h1, s0, M, WD, f);
-            float4 xg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (f < 39) xg = col4(A.k_x, s0, M, 40, f);
-            else if (f >= 64 && f < 67) xg = col4(A.k_glogit, s0, M, 3, f - 64);
-            put_k4(sb, S_A1, OPB(WD), f, k4, a1);
-            put_k4(sb, S_B1, OPB(N1), f, k4, b1);
-            put_k4(sb, S_A0, OPB(WD), f, k4, a0);
-            put_k4(sb, S_A2, OPB(WD), f, k4, a2);
+            put_k4(sb, S_A1, OPB(WD), f, k4, cur.a1);
+            put_k4(sb, S_B1, OPB(N1), f, k4, cur.b1);
+            put_k4(sb, S_A0, OPB(WD), f, k4, cur.a0);
+            put_k4(sb, S_A2, OPB(WD), f, k4, cur.a2);
             const float4 ones = make_float4(s0 < M ? 1.f : 0.f, s0 + 1 < M ? 1.f : 0.f, s0 + 2 < M ? 1.f : 0.f, s0 + 3 < M ? 1.f : 0.f);
-            if (f < 39) put_k4(sb, S_B0, OPB(N0), f, k4, xg);
+            if (f < 39) put_k4(sb, S_B0, OPB(N0), f, k4, cur.xg);
             else if (f == 39) put_k4(sb, S_B0, OPB(N0), 39, k4, ones);             // bias row of dW0
             else if (f == 40) put_k4(sb, S_B1, OPB(N1), 128, k4, ones);            // bias row of dW1
             else if (f >= 64 && f < 67) {                                           // G^T rows; db2 on the side
-                gsum += (xg.x + xg.y) + (xg.z + xg.w);
-                put_k4(sb, S_B2, OPB(N2), f - 64, k4, xg);
+                gsum += (cur.xg.x + cur.xg.y) + (cur.xg.z + cur.xg.w);
+                put_k4(sb, S_B2, OPB(N2), f - 64, k4, cur.xg);
             }
         }
         fence_async_smem();
@@ -321,7 +345,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
     for (int st = 0; st < 2; ++st)
         if (issued[st]) { mbar_wait(st ? bar1 : bar0, par[st]); par[st] ^= 1; }
     tc_fence_after();
-    if (it > 0 && tid >= 64 && (tid & 127) >= 64 && (tid & 127) < 67) red_add(A.net_grad + PVDB_NET_OFF_B2 + ((tid & 127) - 64), gsum);
+    if (it > 0 && f >= 64 && f < 67) red_add(A.net_grad + PVDB_NET_OFF_B2 + (f - 64), gsum);
     if (it > 0 && tid < TM) {
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
         float* G = A.net_grad;
@@ -384,7 +408,8 @@ int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b,
     }
     BwdActArgs A;
     A.tree = *b->tree; A.net = b->net; A.k_glogit = b->k_rgb; A.k_mask = b->k_mask; A.k_xyz = b->k_xyz;
-    A.k_dh1 = b->k_dh1; A.k_dh0 = b->k_dh0; A.k0_grad = b->k0_grad; A.k0_touched = b->k0_touched; A.counters = b->counters;
+    A.k_dh1 = b->k_dh1; A.k_dh0 = b->k_dh0; A.k0_grad = b->k0_grad; A.k0_touched = b->k0_touched; A.k0_touched_list = b->k0_touched_list; A.counters_w = b->counters;
+    A.counters = b->counters;
     A.cap_keep = b->cap_keep;
     k_rgbnet_bwd_act_tc<<<PVDB_SMS, TM, B1_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();

@@ -11,10 +11,9 @@
 //   F4 k_rgbnet_fwd     k0 trilinear (12 ch) + view PE + MLP + sigmoid, 64-sample tiles
 //   F5 k_composite      per-ray compositing, losses, dL/d(rgb_marched), dL/d(alphainv_last), dL/d(rgb), dL/d(w)
 //   B1 k_rgbnet_bwd     MLP backward, weight-gradient partials in registers, k0 gradient scatter
-//   B2 k_ray_bwd        per-ray reverse cumprod backward + raw2alpha backward
+//   B2 k_ray_bwd        warp per ray: reverse cumprod backward (shuffle suffix scan) + raw2alpha backward
 //   B3 k_density_scatter density gradient scatter
-//   U1 k_touched_compact / k_sparse_adam  Adam over touched leaves only, gradients cleared in the same pass
-//   U2 k_dense_adam     rgbnet parameters
+//   U1 k_update_fused   one launch: Adam over touched leaves only (gradients cleared in the same pass) + rgbnet Adam
 //
 // The per-sample arithmetic is shared with the drop-in ops through ray_math.cuh / common.cuh, so sample
 // counts, segment offsets and voxel indices are the reference's bit for bit.
@@ -200,50 +199,52 @@ __global__ void __launch_bounds__(256) k_hit_mask(MarchParams P, const float* __
     if (lane == 0) hit[r] = any ? 1 : 0;
 }
 
-// Exclusive scans of the two per-ray counts; single CTA (n_rays is 8192..65536).
+// Exclusive scans of the two per-ray counts -> segment offsets in ray order.  One CTA of 32 warps: warp w owns the
+// contiguous run [w*n/32, (w+1)*n/32) and walks it 32 rays at a time (coalesced loads, shuffle scan, running carry);
+// the 32 run totals are scanned by warp 0 and added in a second sweep.
 __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck,
                                                       int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
                                                       int32_t* __restrict__ counters, int64_t cap_alpha, int64_t cap_keep) {
-    __shared__ int2 wsum[32];
-    __shared__ int2 carry_s;
-    if (threadIdx.x == 0) carry_s = make_int2(0, 0);
-    __syncthreads();
+    __shared__ int2 wtot[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        int2 v = i < n ? make_int2(ca[i], ck[i]) : make_int2(0, 0);
-        const int2 own = v;
+    const int per = ((n + 31) / 32 + 31) & ~31;          // rays per warp, multiple of 32
+    const int lo = min(n, wid * per), hi = min(n, lo + per);
+    int2 carry = make_int2(0, 0);
+    for (int base = lo; base < hi; base += 32) {
+        const int i = base + lane;
+        const int2 own = i < hi ? make_int2(ca[i], ck[i]) : make_int2(0, 0);
+        int2 v = own;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int ux = __shfl_up_sync(0xffffffffu, v.x, o), uy = __shfl_up_sync(0xffffffffu, v.y, o);
             if (lane >= o) { v.x += ux; v.y += uy; }
         }
-        if (lane == 31) wsum[wid] = v;
-        __syncthreads();
-        if (wid == 0) {
-            int2 w = wsum[lane];
+        if (i < hi) { oa[i] = carry.x + v.x - own.x; ok[i] = carry.y + v.y - own.y; }   // exclusive within the warp's run
+        carry.x += __shfl_sync(0xffffffffu, v.x, 31);
+        carry.y += __shfl_sync(0xffffffffu, v.y, 31);
+    }
+    if (lane == 0) wtot[wid] = carry;
+    __syncthreads();
+    if (wid == 0) {
+        const int2 own = wtot[lane];
+        int2 w = own;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int ux = __shfl_up_sync(0xffffffffu, w.x, o), uy = __shfl_up_sync(0xffffffffu, w.y, o);
-                if (lane >= o) { w.x += ux; w.y += uy; }
-            }
-            wsum[lane] = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ux = __shfl_up_sync(0xffffffffu, w.x, o), uy = __shfl_up_sync(0xffffffffu, w.y, o);
+            if (lane >= o) { w.x += ux; w.y += uy; }
         }
-        __syncthreads();
-        const int2 c = carry_s;
-        const int2 pre = wid ? wsum[wid - 1] : make_int2(0, 0);
-        const int2 incl = make_int2(v.x + pre.x + c.x, v.y + pre.y + c.y);
-        if (i < n) { oa[i] = incl.x - own.x; ok[i] = incl.y - own.y; }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = incl;
-        __syncthreads();
+        wtot[lane] = make_int2(w.x - own.x, w.y - own.y);   // exclusive prefix of each warp's run
+        if (lane == 31) {
+            oa[n] = w.x; ok[n] = w.y;
+            counters[CNT_M_ALPHA] = w.x; counters[CNT_M_KEEP] = w.y;
+            counters[CNT_OVERFLOW] = (w.x > cap_alpha || w.y > cap_keep) ? 1 : 0;
+            counters[CNT_N_TOUCHED_DEN] = 0; counters[CNT_N_TOUCHED_K0] = 0;
+        }
     }
-    if (threadIdx.x == 0) {
-        const int2 tot = carry_s;
-        oa[n] = tot.x; ok[n] = tot.y;
-        counters[CNT_M_ALPHA] = tot.x; counters[CNT_M_KEEP] = tot.y;
-        counters[CNT_OVERFLOW] = (tot.x > cap_alpha || tot.y > cap_keep) ? 1 : 0;
-    }
+    __syncthreads();
+    const int2 pre = wtot[wid];
+    if (pre.x | pre.y)
+        for (int i = lo + lane; i < hi; i += 32) { oa[i] += pre.x; ok[i] += pre.y; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -336,29 +337,52 @@ __global__ void k_finish_loss(float* loss, float w_main, float w_ent, float w_pe
 }
 
 // ---------------------------------------------------------------------------------------------
-// B2 — per-ray reverse pass (alpha2weight_backward :654-677 + raw2alpha_backward :507-517).  One thread per
-// ray: the recurrence is sequential; the scatter that follows (B3) is sample-parallel.
+// B2 — per-ray reverse pass (alpha2weight_backward :654-677 + raw2alpha_backward :507-517).  One warp per ray: the
+// reference's sequential recurrence  back_cum += gw*w  is a suffix sum, evaluated here 32 samples at a time from the far
+// end of the segment with a shuffle scan (summation order differs from the reference's serial loop at the 1e-7 level).
+// The gradient wrt the weight of a kept sample is fetched through its position among the ray's kept samples.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_ray_bwd(const int32_t* __restrict__ off_alpha, const int32_t* __restrict__ off_keep,
+__global__ void __launch_bounds__(256) k_ray_bwd(const int32_t* __restrict__ off_alpha, const int32_t* __restrict__ off_keep,
                                                  const float* __restrict__ s_alpha, const float* __restrict__ s_T,
                                                  const float* __restrict__ s_weight, const float* __restrict__ s_density,
                                                  const float* __restrict__ k_gw, const float* __restrict__ alphainv_last,
                                                  const float* __restrict__ grad_last, float* __restrict__ s_gden, int n_rays,
                                                  float thres, float act_shift, float interval, int64_t cap_alpha, int64_t cap_keep) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= n_rays) return;
     const int64_t b = off_alpha[r], e = off_alpha[r + 1];
     if (e > cap_alpha) return;
-    int64_t ks = off_keep[r + 1];
-    float back_cum = __fmul_rn(grad_last[r], alphainv_last[r]);
-    for (int64_t i = e - 1; i >= b; --i) {
-        const float w = s_weight[i], a = s_alpha[i];
+    int64_t ks_end = off_keep[r + 1];                       // kept samples are consumed from the end of the ray
+    float carry = __fmul_rn(grad_last[r], alphainv_last[r]);   // back_cum before the last sample
+    for (int64_t top = e; top > b; top -= 32) {
+        const int64_t i = top - 1 - lane;                   // lane 0 = farthest sample of this chunk
+        const bool live = i >= b;
+        float w = 0.f, a = 0.f, T = 0.f, dens = 0.f;
+        if (live) { w = s_weight[i]; a = s_alpha[i]; T = s_T[i]; dens = s_density[i]; }
+        const bool kept = live && w > thres;
+        const unsigned kb = __ballot_sync(0xffffffffu, kept);
         float gw = 0.f;
-        if (w > thres) { --ks; gw = ks < cap_keep ? k_gw[ks] : 0.f; }
-        const float ga = pvdb_a2w_grad(gw, s_T[i], back_cum, a);
-        back_cum = __fmaf_rn(gw, w, back_cum);
-        const float ex = expf(__fadd_rn(s_density[i], act_shift));
-        s_gden[i] = pvdb_raw2alpha_bwd(ex, ga, interval);
+        if (kept) {
+            const int64_t ks = ks_end - 1 - __popc(kb & ((1u << lane) - 1u));
+            gw = ks < cap_keep ? k_gw[ks] : 0.f;
+        }
+        ks_end -= __popc(kb);
+        // back_cum seen by sample i = carry + sum of gw*w over the samples behind it (lanes < lane)
+        const float c = __fmul_rn(gw, w);
+        float incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const float back_cum = carry + (incl - c);
+        if (live) {
+            const float ga = pvdb_a2w_grad(gw, T, back_cum, a);
+            const float ex = expf(__fadd_rn(dens, act_shift));
+            s_gden[i] = pvdb_raw2alpha_bwd(ex, ga, interval);
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -370,7 +394,8 @@ __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c,
 // B3 — density gradient scatter (densityvdb.cu:143-167) over the compacted alpha list; marks touched leaves.
 __global__ void __launch_bounds__(256) k_density_scatter(pvdb_tree t, float* __restrict__ den_grad, const float* __restrict__ s_xyz,
                                                          const float* __restrict__ s_gden, const int32_t* __restrict__ counters,
-                                                         int32_t* __restrict__ touched, int64_t cap_alpha) {
+                                                         int32_t* __restrict__ touched, int32_t* __restrict__ touched_list,
+                                                         int32_t* __restrict__ counters_w, int64_t cap_alpha) {
     const int64_t n = min((int64_t)counters[CNT_M_ALPHA], cap_alpha);
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
         const float g = s_gden[s];
@@ -386,7 +411,7 @@ __global__ void __launch_bounds__(256) k_density_scatter(pvdb_tree t, float* __r
             if (leaf < 0) continue;
             red_add(den_grad + (size_t)leaf * 512 + pvdb_leaf_off(x, y, z),
                     __fmul_rn(__fmul_rn(__fmul_rn(g, tri.f(0, dx)), tri.f(1, dy)), tri.f(2, dz)));
-            touched[leaf] = 1;
+            pvdb_touch_leaf(touched, touched_list, counters_w + CNT_N_TOUCHED_DEN, leaf);
         }
     }
 }
@@ -397,6 +422,9 @@ __global__ void __launch_bounds__(256) k_density_scatter(pvdb_tree t, float* __r
 // gradient of the active voxels it visits and the touched flag, which replaces the full-grid zero_grad sweep
 // (densityvdb.cu:353-368) of the next iteration.
 // ---------------------------------------------------------------------------------------------
+// One launch for the whole update: Adam over the touched leaves (lists built by the scatter kernels) + the dense Adam
+// of the 22019 rgbnet parameters (adam_upd_kernel.cu:9-23) in the trailing blocks.
+// Rebuild a touched-leaf list from the flags (update-only calls after a data-parallel flag all-reduce).
 __global__ void __launch_bounds__(256) k_touched_compact(const int32_t* __restrict__ touched, int n_leaf, int32_t* __restrict__ list,
                                                          int32_t* __restrict__ count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -409,46 +437,53 @@ __global__ void __launch_bounds__(256) k_touched_compact(const int32_t* __restri
     if (t) list[base + __popc(bits & ((1u << lane) - 1))] = i;
 }
 
-template <int G>
-__global__ void __launch_bounds__(256) k_sparse_adam(pvdb_tree t, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                     float* __restrict__ v, int C, float stepsz, float eps, float b0, float b1,
-                                                     const int32_t* __restrict__ list, const int32_t* __restrict__ count,
-                                                     int32_t* __restrict__ touched, int clear_grad) {
-    const int ngrp = C / G;
-    const int n = *count;
-    const float omb0 = __fsub_rn(1.0f, b0), omb1 = __fsub_rn(1.0f, b1);
-    for (int li = blockIdx.x; li < n; li += gridDim.x) {
-        const int leaf = list[li];
-        for (int e = threadIdx.x; e < 512 * ngrp; e += blockDim.x) {
-            const int off = e / ngrp, grp = e - off * ngrp;
-            if (!pvdb_mask_bit(t.leaf_mask, leaf, off)) continue;
+struct UpdateArgs {
+    pvdb_tree tree;
+    float *den, *den_g, *den_m, *den_v, *k0, *k0_g, *k0_m, *k0_v, *net, *net_g, *net_m, *net_v;
+    int32_t *den_touched, *k0_touched, *den_list, *k0_list, *counters;
+    float den_stepsz, k0_stepsz, net_stepsize, eps, b0, b1;
+    int leaf_blocks;
+};
+// Work items: (touched density leaf) and (touched k0 leaf, quarter); a persistent grid strides over them.
+__global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
+    if ((int)blockIdx.x >= U.leaf_blocks) {
+        const int i = ((int)blockIdx.x - U.leaf_blocks) * blockDim.x + threadIdx.x;
+        if (i < PVDB_NET_N) {
+            pvdb_dense_adam_update(U.net[i], U.net_m[i], U.net_v[i], U.net_g[i], 1.f, false, U.net_stepsize, U.b0, U.b1, U.eps);
+            U.net_g[i] = 0.f;
+        }
+        return;
+    }
+    const int nd = U.counters[CNT_N_TOUCHED_DEN], nk = U.counters[CNT_N_TOUCHED_K0];
+    const float omb0 = __fsub_rn(1.0f, U.b0), omb1 = __fsub_rn(1.0f, U.b1);
+    for (int w = blockIdx.x; w < nd + nk * 4; w += U.leaf_blocks) {
+        const bool is_den = w < nd;
+        const int leaf = is_den ? U.den_list[w] : U.k0_list[(w - nd) >> 2];
+        const int part = is_den ? 0 : (w - nd) & 3;
+        float *p = is_den ? U.den : U.k0, *g = is_den ? U.den_g : U.k0_g, *m = is_den ? U.den_m : U.k0_m, *v = is_den ? U.den_v : U.k0_v;
+        const float stepsz = is_den ? U.den_stepsz : U.k0_stepsz;
+        const int C = is_den ? 1 : 12, G = is_den ? 1 : 3, ngrp = C / G;
+        // density: 512 voxels by 256 threads (2 each); k0 quarter: 128 voxels x 4 groups = 512 items (2 each)
+        for (int e = threadIdx.x; e < 512; e += blockDim.x) {
+            const int off = is_den ? e : part * 128 + (e >> 2), grp = is_den ? 0 : (e & 3);
+            if (!pvdb_mask_bit(U.tree.leaf_mask, leaf, off)) continue;
             const size_t base = ((size_t)leaf * 512 + off) * C + (size_t)grp * G;
-            float gg[G];
+            float gg[3];
             bool allzero = true;
-#pragma unroll
             for (int c = 0; c < G; ++c) { gg[c] = g[base + c]; allzero = allzero && gg[c] == 0.0f; }
             if (allzero) continue;
-#pragma unroll
             for (int c = 0; c < G; ++c) {
-                const float nm = __fmaf_rn(omb0, gg[c], __fmul_rn(b0, m[base + c]));
-                const float nv = __fmaf_rn(gg[c], __fmul_rn(omb1, gg[c]), __fmul_rn(b1, v[base + c]));
+                const float nm = __fmaf_rn(omb0, gg[c], __fmul_rn(U.b0, m[base + c]));
+                const float nv = __fmaf_rn(gg[c], __fmul_rn(omb1, gg[c]), __fmul_rn(U.b1, v[base + c]));
                 m[base + c] = nm;
                 v[base + c] = nv;
-                p[base + c] = __fsub_rn(p[base + c], __fdiv_rn(__fmul_rn(stepsz, nm), __fadd_rn(eps, __fsqrt_rn(nv))));
-                if (clear_grad) g[base + c] = 0.f;
+                p[base + c] = __fsub_rn(p[base + c], __fdiv_rn(__fmul_rn(stepsz, nm), __fadd_rn(U.eps, __fsqrt_rn(nv))));
+                g[base + c] = 0.f;
             }
         }
-        if (clear_grad && threadIdx.x == 0) touched[leaf] = 0;
+        if (threadIdx.x == 0 && part == 0) (is_den ? U.den_touched : U.k0_touched)[leaf] = 0;
+        (void)ngrp;
     }
-}
-
-__global__ void __launch_bounds__(256) k_net_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                  float* __restrict__ v, int n, float step_size, float beta1, float beta2, float eps,
-                                                  int clear_grad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    pvdb_dense_adam_update(p[i], m[i], v[i], g[i], 1.f, false, step_size, beta1, beta2, eps);
-    if (clear_grad) g[i] = 0.f;
 }
 
 // Occupancy bits: fine[(bx*nby+by)*nbz+bz][8] + one coarse bit per block.  One warp per block.
@@ -577,43 +612,44 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
         if (rc) return rc;
         pvdb_prof_mark(cfg->use_tensor_cores ? "rgbnet_bwd_wgrad" : "rgbnet_bwd", st);
-        k_ray_bwd<<<pvdb_grid_for(n_rays, 128), 128, 0, st>>>(b->off_alpha, b->off_keep, b->s_alpha, b->s_T, b->s_weight, b->s_density,
+        k_ray_bwd<<<warp_grid, 256, 0, st>>>(b->off_alpha, b->off_keep, b->s_alpha, b->s_T, b->s_weight, b->s_density,
                                                              b->k_gw, b->alphainv_last, b->grad_last, b->s_gden, n_rays,
                                                              cfg->fast_color_thres, cfg->act_shift, cfg->interval, b->cap_alpha,
                                                              b->cap_keep);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("ray_bwd", st);
         k_density_scatter<<<PVDB_SMS * 8, 256, 0, st>>>(*b->tree, b->den_grad, b->s_xyz, b->s_gden, b->counters, b->den_touched,
-                                                        b->cap_alpha);
+                                                        b->den_touched_list, b->counters, b->cap_alpha);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("density_scatter", st);
     }
     if (do_upd) {
-        const int n_leaf = b->tree->n_leaf;
-        PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_DEN, 0, sizeof(int32_t), st));
-        PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_K0, 0, sizeof(int32_t), st));
-        k_touched_compact<<<pvdb_grid_for(n_leaf, 256), 256, 0, st>>>(b->den_touched, n_leaf, b->den_touched_list,
-                                                                      b->counters + CNT_N_TOUCHED_DEN);
+        UpdateArgs U;
+        U.tree = *b->tree;
+        U.den = b->den; U.den_g = b->den_grad; U.den_m = b->den_m; U.den_v = b->den_v;
+        U.k0 = b->k0; U.k0_g = b->k0_grad; U.k0_m = b->k0_m; U.k0_v = b->k0_v;
+        U.net = b->net; U.net_g = b->net_grad; U.net_m = b->net_m; U.net_v = b->net_v;
+        U.den_touched = b->den_touched; U.k0_touched = b->k0_touched; U.counters = b->counters;
+        U.den_list = b->den_touched_list; U.k0_list = b->k0_touched_list;
+        if (!do_bwd) {   // gradients (and flags) came from elsewhere, e.g. a data-parallel all-reduce: rebuild the lists
+            const int n_leaf = b->tree->n_leaf;
+            PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_DEN, 0, sizeof(int32_t), st));
+            PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_K0, 0, sizeof(int32_t), st));
+            k_touched_compact<<<pvdb_grid_for(n_leaf, 256), 256, 0, st>>>(b->den_touched, n_leaf, b->den_touched_list,
+                                                                          b->counters + CNT_N_TOUCHED_DEN);
+            PVDB_LAUNCH_CHECK();
+            k_touched_compact<<<pvdb_grid_for(n_leaf, 256), 256, 0, st>>>(b->k0_touched, n_leaf, b->k0_touched_list,
+                                                                          b->counters + CNT_N_TOUCHED_K0);
+            PVDB_LAUNCH_CHECK();
+        }
+        U.den_stepsz = cfg->den_stepsz; U.k0_stepsz = cfg->k0_stepsz;
+        U.net_stepsize = pvdb_dense_adam_stepsize(cfg->net_lr, cfg->beta0, cfg->beta1, cfg->net_step);
+        U.eps = cfg->eps; U.b0 = cfg->beta0; U.b1 = cfg->beta1;
+        U.leaf_blocks = PVDB_SMS * 4;
+        const int net_blocks = (PVDB_NET_N + 255) / 256;
+        k_update_fused<<<U.leaf_blocks + net_blocks, 256, 0, st>>>(U);
         PVDB_LAUNCH_CHECK();
-        k_touched_compact<<<pvdb_grid_for(n_leaf, 256), 256, 0, st>>>(b->k0_touched, n_leaf, b->k0_touched_list,
-                                                                      b->counters + CNT_N_TOUCHED_K0);
-        PVDB_LAUNCH_CHECK();
-        pvdb_prof_mark("touched_compact", st);
-        k_sparse_adam<1><<<PVDB_SMS * 4, 256, 0, st>>>(*b->tree, b->den, b->den_grad, b->den_m, b->den_v, 1, cfg->den_stepsz, cfg->eps,
-                                                       cfg->beta0, cfg->beta1, b->den_touched_list, b->counters + CNT_N_TOUCHED_DEN,
-                                                       b->den_touched, 1);
-        PVDB_LAUNCH_CHECK();
-        pvdb_prof_mark("adam_density", st);
-        k_sparse_adam<3><<<PVDB_SMS * 4, 256, 0, st>>>(*b->tree, b->k0, b->k0_grad, b->k0_m, b->k0_v, 12, cfg->k0_stepsz, cfg->eps,
-                                                       cfg->beta0, cfg->beta1, b->k0_touched_list, b->counters + CNT_N_TOUCHED_K0,
-                                                       b->k0_touched, 1);
-        PVDB_LAUNCH_CHECK();
-        pvdb_prof_mark("adam_k0", st);
-        const float ss = pvdb_dense_adam_stepsize(cfg->net_lr, cfg->beta0, cfg->beta1, cfg->net_step);
-        k_net_adam<<<pvdb_grid_for(PVDB_NET_N, 256), 256, 0, st>>>(b->net, b->net_grad, b->net_m, b->net_v, PVDB_NET_N, ss, cfg->beta0,
-                                                                   cfg->beta1, cfg->eps, 1);
-        PVDB_LAUNCH_CHECK();
-        pvdb_prof_mark("adam_rgbnet", st);
+        pvdb_prof_mark("update_fused", st);
     }
     return PVDB_OK;
 }
