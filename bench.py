@@ -149,10 +149,7 @@ def run_ours(args):
     t_setup = time.time()
     scene, net, den, k0, tr, batches = build_workload(nb, dev, seed=777 + rank, use_tc=not args.fp32_rgbnet)
     if world > 1:
-        dp = pdist.DataParallelTrainer.__new__(pdist.DataParallelTrainer)
-        dp.group, dp.world, dp.tr, dp.last_exchange_bytes = None, world, tr, 0
-        tr.n_rays_global = N_RAYS * world
-        tr._build_structs()
+        dp = pdist.DataParallelTrainer.wrap(tr, world)
         stepper = dp.step
     else:
         stepper = tr.step

@@ -216,6 +216,15 @@ typedef struct pvdb_train_bufs {
 int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs,
                     const float* rays_o, const float* rays_d, const float* viewdirs, const float* target,
                     int n_rays, int phases, void* stream);
+/* Data-parallel gradient exchange (no counterpart in the reference, which is single-GPU).  Call after the ranks' touched
+ * flags (bufs->den_touched / k0_touched) were MAX-all-reduced: builds the union leaf list on the device, copies its
+ * length to *union_count_host (pinned; valid after the stream is synchronised) and packs the union leaves' gradient
+ * tiles [n][512*13] followed by the 22019 rgbnet gradients into `buf` for ONE sum all-reduce of
+ * (n*6656 + 22019) floats.  pvdb_dp_unpack writes the reduced values back. */
+int pvdb_dp_pack(const pvdb_train_bufs* bufs, int32_t* union_list, int32_t* union_count_dev, int32_t* union_count_host,
+                 float* buf, int64_t buf_capacity_floats, void* stream);
+int pvdb_dp_unpack(const pvdb_train_bufs* bufs, const int32_t* union_list, const int32_t* union_count_dev, float* buf,
+                   void* stream);
 /* hit_coarse_geo (plenvdb/lib/dvgo.py:253-270) for the 'in_maskcache' ray sampler: hit[r] = 1 iff some in-bbox sample
  * of ray r lands in an occupied voxel.  Uses cfg's scene scalars and bufs->occ_*. */
 int pvdb_rays_hit_mask(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs, const float* rays_o, const float* rays_d,

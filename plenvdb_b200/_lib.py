@@ -131,6 +131,8 @@ _SIGS = {
     "pvdb_alpha2weight_backward": (None, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, _i, c_ptr, c_ptr, c_ptr, c_ptr]),
     "pvdb_dense_adam": (None, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, _i64, _i, _i, _f, _f, _f, _f, c_ptr]),
     "pvdb_occ_build": (None, [c_ptr, _i, _i, _i, c_ptr, c_ptr, c_ptr]),
+    "pvdb_dp_pack": (None, [C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, c_ptr, c_ptr, _i64, c_ptr]),
+    "pvdb_dp_unpack": (None, [C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, c_ptr, c_ptr]),
     "pvdb_profile_enable": (None, [_i]),
     "pvdb_profile_fetch": (C.c_int, [_i, c_ptr, c_ptr]),
     "pvdb_rays_hit_mask": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, _i, c_ptr, c_ptr]),

@@ -548,6 +548,86 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Data-parallel exchange helpers.  After the ranks' touched flags were MAX-all-reduced, pack the
+// gradient tiles of the union leaves (density [512] + k0 [512][12] per leaf) and the rgbnet gradients into one
+// contiguous buffer for a single SUM all-reduce; unpack writes the reduced tiles back.  The union list is built on
+// the device; its length goes to a pinned host word so the caller can size the collective.
+// ---------------------------------------------------------------------------------------------
+// One CTA; the list is in ascending leaf order so that every rank packs the same leaf into the same slot.
+__global__ void __launch_bounds__(1024) k_dp_union_list(int32_t* __restrict__ den_touched, int32_t* __restrict__ k0_touched, int n_leaf,
+                                                        int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    __shared__ int warp_cnt[32];
+    __shared__ int running;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n_leaf; base += 1024) {
+        const int i = base + threadIdx.x;
+        const bool t = i < n_leaf && (den_touched[i] | k0_touched[i]) != 0;
+        if (t) { den_touched[i] = 1; k0_touched[i] = 1; }
+        const unsigned bits = __ballot_sync(0xffffffffu, t);
+        if (lane == 0) warp_cnt[warp] = __popc(bits);
+        __syncthreads();
+        int c = warp_cnt[lane], incl = c;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        const int warp_off = __shfl_sync(0xffffffffu, incl - c, warp);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int start = running;
+        if (t) list[start + warp_off + __popc(bits & ((1u << lane) - 1))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) running = start + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = running;
+}
+// grid: one CTA per union slot (grid-stride), 256 threads move 512*13 floats as float4
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_dp_move(float* __restrict__ den_grad, float* __restrict__ k0_grad, float* __restrict__ net_grad,
+                                                 const int32_t* __restrict__ list, const int32_t* __restrict__ count,
+                                                 float* __restrict__ buf) {
+    const int n = *count;
+    float* net_slot = buf + (size_t)n * (512 * 13);
+    for (int slot = blockIdx.x; slot <= n; slot += gridDim.x) {
+        if (slot == n) {   // trailing slot: rgbnet gradients
+            for (int i = threadIdx.x; i < PVDB_NET_N; i += blockDim.x) {
+                if (PACK) net_slot[i] = net_grad[i]; else net_grad[i] = net_slot[i];
+            }
+            continue;
+        }
+        const int leaf = list[slot];
+        float4* b4 = reinterpret_cast<float4*>(buf + (size_t)slot * (512 * 13));
+        float4* d4 = reinterpret_cast<float4*>(den_grad + (size_t)leaf * 512);
+        float4* k4 = reinterpret_cast<float4*>(k0_grad + (size_t)leaf * 512 * 12);
+        for (int i = threadIdx.x; i < 128 + 1536; i += blockDim.x) {
+            float4* g = i < 128 ? d4 + i : k4 + (i - 128);
+            if (PACK) b4[i] = *g; else *g = b4[i];
+        }
+    }
+}
+
+extern "C" int pvdb_dp_pack(const pvdb_train_bufs* b, int32_t* union_list, int32_t* union_count_dev, int32_t* union_count_host,
+                            float* buf, int64_t buf_capacity_floats, void* stream) {
+    PVDB_CHECK_ARG(b && b->tree && union_list && union_count_dev && union_count_host && buf, "null pointer");
+    PVDB_CHECK_ARG(buf_capacity_floats >= (int64_t)b->tree->n_leaf * 512 * 13 + PVDB_NET_N, "pack buffer smaller than the worst case");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_leaf = b->tree->n_leaf;
+    k_dp_union_list<<<1, 1024, 0, st>>>(b->den_touched, b->k0_touched, n_leaf, union_list, union_count_dev);
+    PVDB_LAUNCH_CHECK();
+    PVDB_CUDA(cudaMemcpyAsync(union_count_host, union_count_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    k_dp_move<true><<<PVDB_SMS * 2, 256, 0, st>>>(b->den_grad, b->k0_grad, b->net_grad, union_list, union_count_dev, buf);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+extern "C" int pvdb_dp_unpack(const pvdb_train_bufs* b, const int32_t* union_list, const int32_t* union_count_dev, float* buf,
+                              void* stream) {
+    PVDB_CHECK_ARG(b && b->tree && union_list && union_count_dev && buf, "null pointer");
+    k_dp_move<false><<<PVDB_SMS * 2, 256, 0, (cudaStream_t)stream>>>(b->den_grad, b->k0_grad, b->net_grad, union_list, union_count_dev, buf);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
 extern "C" int pvdb_rays_hit_mask(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* rays_o, const float* rays_d,
                                   int n_rays, uint8_t* hit, void* stream) {
     PVDB_CHECK_ARG(cfg && b && b->tree && rays_o && rays_d && hit, "null pointer");

@@ -68,23 +68,72 @@ def allreduce_sparse_grads(den_grad, k0_grad, net_grad, leaves, group=None):
 
 
 class DataParallelTrainer:
-    """FusedTrainer + the gradient exchange.  `n_rays` is the PER-RANK shard size."""
+    """FusedTrainer + the gradient exchange.  `n_rays` is the PER-RANK shard size.
+
+    Per iteration: forward+backward (local shard, losses normalised by the global batch) -> MAX all-reduce of the two
+    touched-flag arrays -> device-side union list + pack (pvdb_dp_pack) -> one host read of the union size -> ONE SUM
+    all-reduce of the packed tiles + rgbnet gradients -> unpack + the fused sparse Adam (identical on every rank)."""
 
     def __init__(self, params, density, k0, mask, net, n_rays, world=None, group=None, **kw):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
         self.group = group
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.tr = FusedTrainer(params, density, k0, mask, net, n_rays, n_rays_global=n_rays * self.world, **kw)
+        self._init_exchange()
+
+    def _init_exchange(self):
+        tr = self.tr
+        n_leaf = max(tr.topo.n_leaf, 1)
+        dev = tr.dev
+        self.flags = torch.zeros(2 * n_leaf, dtype=torch.int32, device=dev)
+        self.union_list = torch.zeros(n_leaf, dtype=torch.int32, device=dev)
+        self.union_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.union_count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.cap = n_leaf * 512 * 13 + 22019
+        self.buf = torch.empty(self.cap, dtype=torch.float32, device=dev)
         self.last_exchange_bytes = 0
 
+    @classmethod
+    def wrap(cls, trainer, world, group=None):
+        """Turn an existing single-GPU FusedTrainer into the data-parallel one (its loss means become global)."""
+        import ctypes as C
+        from . import _lib
+        self = cls.__new__(cls)
+        self._C, self._lib = C, _lib
+        self.group, self.world, self.tr = group, world, trainer
+        trainer.n_rays_global = trainer.n_rays * world
+        trainer._build_structs()
+        self._init_exchange()
+        return self
+
     def step(self, rays_o, rays_d, viewdirs, target):
-        tr = self.tr
+        tr, C, _lib = self.tr, self._C, self._lib
         if self.world == 1:
             tr.step(rays_o, rays_d, viewdirs, target)
             return
         tr.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD)
-        leaves = union_touched(tr.t["den_touched"], tr.t["k0_touched"], self.group)
-        self.last_exchange_bytes = allreduce_sparse_grads(tr.density.grad, tr.k0.grad, tr.net_grad, leaves, self.group)
+        n_leaf = tr.topo.n_leaf
+        # 1. union of touched leaves: both flag arrays in one MAX all-reduce
+        self.flags[:n_leaf].copy_(tr.t["den_touched"][:n_leaf])
+        self.flags[n_leaf:2 * n_leaf].copy_(tr.t["k0_touched"][:n_leaf])
+        dist.all_reduce(self.flags, op=dist.ReduceOp.MAX, group=self.group)
+        tr.t["den_touched"][:n_leaf].copy_(self.flags[:n_leaf])
+        tr.t["k0_touched"][:n_leaf].copy_(self.flags[n_leaf:2 * n_leaf])
+        # 2. pack on the device, read the union size (the only host sync of the step)
+        st = _lib.current_stream()
+        _lib.call("pvdb_dp_pack", C.byref(tr._bufs), _lib.ptr(self.union_list), _lib.ptr(self.union_count),
+                  C.c_void_p(self.union_count_host.data_ptr()), _lib.ptr(self.buf), self.cap, st)
+        torch.cuda.current_stream().synchronize()
+        n = int(self.union_count_host[0])
+        numel = n * 512 * 13 + 22019
+        # 3. one SUM all-reduce over NVLink, then unpack + identical update everywhere
+        dist.all_reduce(self.buf[:numel], op=dist.ReduceOp.SUM, group=self.group)
+        _lib.call("pvdb_dp_unpack", C.byref(tr._bufs), _lib.ptr(self.union_list), _lib.ptr(self.union_count), _lib.ptr(self.buf), st)
+        tr.launches_total += 4
         tr.update()
+        self.last_exchange_bytes = numel * 4 + self.flags.numel() * 4
 
 
 def render_sharded(renderer, c2w_dev, rank, world, gather=True, group=None):

@@ -70,3 +70,42 @@ def test_two_gpu_dp_step_matches_single_gpu():
     assert a["bytes"] > 0
     for k, k1 in (("den", "den1"), ("k0", "k01"), ("net", "net1")):
         np.testing.assert_allclose(a[k], a[k1], rtol=1e-3, atol=2e-4, err_msg=k)
+
+
+def test_dp_pack_unpack_roundtrip_single_gpu():
+    """pvdb_dp_pack / pvdb_dp_unpack on one GPU: union list = sorted set of touched leaves, packed tiles equal the gradient
+    planes, and unpack writes back exactly what the buffer holds (here 2x, as a 2-rank sum of equal shards would)."""
+    import ctypes as C
+    from plenvdb_b200 import _lib, synth
+    from plenvdb_b200 import dist as pdist
+    from plenvdb_b200.fused import FusedTrainer, build_scene_grids, PHASE_FORWARD, PHASE_BACKWARD
+    dev = torch.device("cuda", 0)
+    scene = synth.make_scene(96, "sparse")
+    net = synth.rgbnet_init()
+    rays = [torch.from_numpy(a).to(dev) for a in synth.ray_batch(1024, H=200, W=200, K=synth.intrinsics(200, 200), seed=5)]
+    den, k0 = build_scene_grids(scene, device=dev)
+    tr = FusedTrainer(scene, den, k0, scene["mask"], net, 1024, device=dev)
+    dp = pdist.DataParallelTrainer.wrap(tr, 1)
+    tr.run(*rays, PHASE_FORWARD | PHASE_BACKWARD)
+    n_leaf = tr.topo.n_leaf
+    flags = ((tr.t["den_touched"][:n_leaf] | tr.t["k0_touched"][:n_leaf]) != 0)
+    want = torch.nonzero(flags).flatten().cpu().numpy()
+    dg, kg, ng = tr.density.grad.clone(), tr.k0.grad.clone(), tr.net_grad.clone()
+    st = _lib.current_stream()
+    _lib.call("pvdb_dp_pack", C.byref(tr._bufs), _lib.ptr(dp.union_list), _lib.ptr(dp.union_count),
+              C.c_void_p(dp.union_count_host.data_ptr()), _lib.ptr(dp.buf), dp.cap, st)
+    torch.cuda.synchronize()
+    n = int(dp.union_count_host[0])
+    assert n == len(want) and n > 0
+    got = dp.union_list[:n].cpu().numpy()
+    assert np.array_equal(got, want)   # ascending: identical slot order on every rank
+    tiles = dp.buf[:n * 6656].reshape(n, 6656)
+    gl = torch.from_numpy(got.astype(np.int64)).to(dev)
+    assert torch.equal(tiles[:, :512], dg.reshape(-1, 512)[gl])
+    assert torch.equal(tiles[:, 512:], kg.reshape(-1, 512 * 12)[gl])
+    assert torch.equal(dp.buf[n * 6656:n * 6656 + 22019], ng)
+    dp.buf[:n * 6656 + 22019] *= 2
+    _lib.call("pvdb_dp_unpack", C.byref(tr._bufs), _lib.ptr(dp.union_list), _lib.ptr(dp.union_count), _lib.ptr(dp.buf), st)
+    torch.cuda.synchronize()
+    assert torch.equal(tr.density.grad, dg * 2) and torch.equal(tr.k0.grad, kg * 2)
+    assert torch.equal(tr.net_grad, ng * 2)
