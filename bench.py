@@ -149,7 +149,7 @@ def run_ours(args):
     t_setup = time.time()
     scene, net, den, k0, tr, batches = build_workload(nb, dev, seed=777 + rank, use_tc=not args.fp32_rgbnet)
     if world > 1:
-        dp = pdist.DataParallelTrainer.wrap(tr, world)
+        dp = pdist.DataParallelTrainer.wrap(tr, world, exchange=args.exchange)
         stepper = dp.step
     else:
         stepper = tr.step
@@ -218,6 +218,21 @@ def run_ours(args):
     h2d = 4 * N_RAYS * 3 * 4
     clk.__exit__()
 
+    # ---- exchange kernels (all ranks step together; rank 0 reports)
+    xchg = {}
+    if world > 1 and dp.peer is not None:
+        _lib.profile_enable(True)
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            tr.run(ro[Wm + i], rd[Wm + i], vd[Wm + i], tg[Wm + i], 3)
+            dp.peer.exchange(tr._bufs)
+            torch.cuda.synchronize()
+            for name, t_ms in _lib.profile_fetch():
+                xchg.setdefault(name, []).append(t_ms)
+            tr.update(lists_ready=True)
+        _lib.profile_enable(False)
+        xchg = {k: float(np.mean(v)) for k, v in xchg.items()}
+
     result = None
     if rank == 0:
         hbm, tf, which = measured_peaks()
@@ -280,7 +295,13 @@ def run_ours(args):
             "clocks": clk.summary(),
         }
         if world > 1:
-            result["config"]["exchange_bytes_per_step"] = dp.last_exchange_bytes
+            result["config"]["exchange_bytes_per_step"] = dp.exchange_bytes()
+            if xchg:
+                result["exchange_kernel_ms"] = xchg
+            result["config"]["exchange"] = ("own kernels over NVLink peer memory (CUDA IPC), no NCCL call in the step"
+                                            if dp.peer is not None else "NCCL all-reduce of packed touched-leaf tiles")
+            if dp.peer is not None and dp.peer.error():
+                result["config"]["exchange_error"] = dp.peer.error()
     # ---- merged-VDB render FPS (config[2]); tile-sharded across ranks
     if not args.no_render:
         r = run_render(args, scene, net, den, k0, dev, rank, world)
@@ -410,6 +431,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=20, help="frames timed for the render FPS sub-result")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl"],
+                    help="N>1 gradient exchange: own kernels over NVLink peer memory, or NCCL all-reduce of the packed tiles")
     ap.add_argument("--fp32-rgbnet", action="store_true", help="use the fp32 CUDA-core rgbnet instead of the tcgen05 one")
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per CPU-baseline step (bounded sample)")
     args = ap.parse_args()

@@ -213,6 +213,7 @@ typedef struct pvdb_train_bufs {
 #define PVDB_PHASE_FORWARD 1    /* sample, interpolate, rgbnet, composite (+ losses when target != NULL) */
 #define PVDB_PHASE_BACKWARD 2   /* gradients into den_grad / k0_grad / net_grad (accumulating, like autograd) */
 #define PVDB_PHASE_UPDATE 4     /* sparse Adam on touched leaves + rgbnet Adam; clears the gradients it consumed */
+#define PVDB_PHASE_LISTS_READY 8 /* with UPDATE alone: den/k0_touched_list + counters[2],[4] are already valid (pvdb_dp_exchange) */
 int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs,
                     const float* rays_o, const float* rays_d, const float* viewdirs, const float* target,
                     int n_rays, int phases, void* stream);
@@ -225,6 +226,26 @@ int pvdb_dp_pack(const pvdb_train_bufs* bufs, int32_t* union_list, int32_t* unio
                  float* buf, int64_t buf_capacity_floats, void* stream);
 int pvdb_dp_unpack(const pvdb_train_bufs* bufs, const int32_t* union_list, const int32_t* union_count_dev, float* buf,
                    void* stream);
+/* The same exchange over NVLink peer memory, without NCCL and without a host synchronisation (dp_exchange.cu).  Every
+ * rank allocates one symmetric block (pvdb_dp_symm_bytes / _alloc: cudaMalloc + a 64-byte CUDA IPC handle), the handles
+ * are exchanged by the caller's own transport (torch.distributed all_gather_object here) and opened with
+ * pvdb_dp_symm_open; base[r] is rank r's block as mapped in THIS process (base[rank] = the own allocation).
+ * pvdb_dp_exchange(step) runs after the backward phase on every rank with the same monotone `step` (0,1,2,...):
+ * cross-GPU barrier, union of touched leaves, pack, barrier, peer-read sum in rank order into den_grad/k0_grad/net_grad,
+ * and leaves den/k0_touched_list + counters[2],[4] ready for pvdb_train_step(PVDB_PHASE_UPDATE|PVDB_PHASE_LISTS_READY).
+ * A peer that does not arrive within 2 s sets the block's error word (pvdb_dp_symm_error: 1 timeout, 2 union > cap). */
+typedef struct {
+    int32_t world, rank;      /* world <= 8 (one NVSwitch domain) */
+    int32_t n_leaf, cap_leaves;
+    void* base[8];
+} pvdb_dp_peers;
+size_t pvdb_dp_symm_bytes(int n_leaf, int cap_leaves);
+int pvdb_dp_symm_alloc(size_t bytes, void** ptr, void* handle64);
+int pvdb_dp_symm_open(const void* handle64, void** ptr);
+int pvdb_dp_symm_close(void* ptr);
+int pvdb_dp_symm_free(void* ptr);
+int pvdb_dp_symm_error(const pvdb_dp_peers* peers, int32_t* err_out);
+int pvdb_dp_exchange(const pvdb_dp_peers* peers, const pvdb_train_bufs* bufs, uint32_t step, void* stream);
 /* hit_coarse_geo (plenvdb/lib/dvgo.py:253-270) for the 'in_maskcache' ray sampler: hit[r] = 1 iff some in-bbox sample
  * of ray r lands in an occupied voxel.  Uses cfg's scene scalars and bufs->occ_*. */
 int pvdb_rays_hit_mask(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs, const float* rays_o, const float* rays_d,

@@ -94,6 +94,11 @@ class pvdb_render_bufs(C.Structure):
     ]
 
 
+class pvdb_dp_peers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_leaf", C.c_int32), ("cap_leaves", C.c_int32),
+                ("base", C.c_void_p * 8)]
+
+
 _TP = C.POINTER(pvdb_tree)
 _i, _i64, _f = C.c_int, C.c_int64, C.c_float
 
@@ -133,6 +138,13 @@ _SIGS = {
     "pvdb_occ_build": (None, [c_ptr, _i, _i, _i, c_ptr, c_ptr, c_ptr]),
     "pvdb_dp_pack": (None, [C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, c_ptr, c_ptr, _i64, c_ptr]),
     "pvdb_dp_unpack": (None, [C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, c_ptr, c_ptr]),
+    "pvdb_dp_symm_bytes": (C.c_size_t, [_i, _i]),
+    "pvdb_dp_symm_alloc": (None, [C.c_size_t, C.POINTER(C.c_void_p), c_ptr]),
+    "pvdb_dp_symm_open": (None, [c_ptr, C.POINTER(C.c_void_p)]),
+    "pvdb_dp_symm_close": (None, [c_ptr]),
+    "pvdb_dp_symm_free": (None, [c_ptr]),
+    "pvdb_dp_symm_error": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(C.c_int32)]),
+    "pvdb_dp_exchange": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(pvdb_train_bufs), C.c_uint32, c_ptr]),
     "pvdb_profile_enable": (None, [_i]),
     "pvdb_profile_fetch": (C.c_int, [_i, c_ptr, c_ptr]),
     "pvdb_rays_hit_mask": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, _i, c_ptr, c_ptr]),

@@ -1,0 +1,246 @@
+// dp_exchange.cu — data-parallel gradient exchange over NVLink peer memory (the reference is single-GPU,
+// so this has no counterpart there).  Each rank owns one "symmetric block" (cudaMalloc + CUDA IPC, mapped by every peer):
+//
+//   [0,256)      signal[src]      u32, monotone epoch written by rank `src` (st.release.sys), polled by the owner
+//   [256,512)    err, done_ctas
+//   [1024,..)    flags[2][n_leaf] i32   touched flags published by the owner (double-buffered by step parity)
+//   [grad_off,.) grad[2][cap]     f32   packed gradient tiles of the union leaves + rgbnet gradients (double-buffered)
+//
+// One exchange = three kernels on the training stream, no host synchronisation and no NCCL call:
+//   k_dp_union    1 CTA : publish own flags -> cross-GPU barrier -> OR of all peers' flags -> ascending union list
+//   k_dp_pack     grid  : own gradient tiles of the union leaves -> own grad[parity]; the last CTA signals the peers
+//   k_dp_reduce   grid  : wait for the peers' signals, then every rank sums the peers' tiles in rank order (identical
+//                         bits everywhere) straight into its gradient planes, ready for the fused sparse Adam.
+// Double buffering makes a third barrier unnecessary: a rank can only overwrite parity p two steps later, after every
+// peer passed the barrier of the step in between, which is stream-ordered after its reads of parity p.
+#include "common.cuh"
+#include "rgbnet.cuh"
+
+namespace {
+
+constexpr int TILE_F = PVDB_LEAF_VOX * 13;                 // density [512] + k0 [512][12]
+constexpr int NET_PAD = (PVDB_NET_N + 3) & ~3;
+constexpr unsigned long long SPIN_TIMEOUT_NS = 2000000000ull;   // 2 s: a dead peer must not hang the GPU
+
+struct Blk {
+    uint32_t* signal;
+    int32_t* err;
+    uint32_t* done;
+    int32_t* flags[2];
+    float* grad[2];
+};
+__host__ __device__ inline size_t grad_off(int n_leaf) { return (1024 + (size_t)8 * n_leaf + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t cap_floats(int cap_leaves) { return (size_t)cap_leaves * TILE_F + NET_PAD; }
+__host__ __device__ inline Blk view(void* base, int n_leaf, int cap_leaves) {
+    char* p = static_cast<char*>(base);
+    Blk b;
+    b.signal = reinterpret_cast<uint32_t*>(p);
+    b.err = reinterpret_cast<int32_t*>(p + 256);
+    b.done = reinterpret_cast<uint32_t*>(p + 260);
+    b.flags[0] = reinterpret_cast<int32_t*>(p + 1024);
+    b.flags[1] = b.flags[0] + n_leaf;
+    b.grad[0] = reinterpret_cast<float*>(p + grad_off(n_leaf));
+    b.grad[1] = b.grad[0] + cap_floats(cap_leaves);
+    return b;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// thread `peer` of a CTA: tell rank `peer` that this rank reached `epoch`
+__device__ __forceinline__ void signal_peer(const pvdb_dp_peers& P, int peer, uint32_t epoch) {
+    st_release_sys(view(P.base[peer], P.n_leaf, P.cap_leaves).signal + P.rank, epoch);
+}
+// thread `peer` of a CTA: wait until rank `peer` reached `epoch`
+__device__ __forceinline__ void wait_peer(const pvdb_dp_peers& P, int peer, uint32_t epoch) {
+    const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
+    const unsigned long long t0 = globaltimer();
+    while ((int32_t)(ld_acquire_sys(me.signal + peer) - epoch) < 0) {
+        if (globaltimer() - t0 > SPIN_TIMEOUT_NS) { atomicExch(me.err, 1); break; }
+        __nanosleep(64);
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epoch, int parity, int32_t* __restrict__ den_touched,
+                                                   int32_t* __restrict__ k0_touched, int32_t* __restrict__ den_list,
+                                                   int32_t* __restrict__ k0_list, int32_t* __restrict__ counters, int cnt_den, int cnt_k0) {
+    __shared__ int warp_cnt[32];
+    __shared__ int running;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
+    for (int i = threadIdx.x; i < P.n_leaf; i += 1024) me.flags[parity][i] = (den_touched[i] | k0_touched[i]) != 0;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();   // the st.release.sys below is cumulative over the CTA's flag writes ordered by this barrier
+    if (threadIdx.x < P.world) {
+        signal_peer(P, threadIdx.x, epoch);
+        wait_peer(P, threadIdx.x, epoch);
+    }
+    __syncthreads();
+    const int32_t* pf[8];
+    for (int r = 0; r < 8; ++r) pf[r] = view(P.base[r < P.world ? r : 0], P.n_leaf, P.cap_leaves).flags[parity];
+    for (int base = 0; base < P.n_leaf; base += 1024) {
+        const int i = base + threadIdx.x;
+        int f = 0;
+        if (i < P.n_leaf)
+            for (int r = 0; r < P.world; ++r) f |= __ldcv(pf[r] + i);
+        const bool t = f != 0;
+        if (i < P.n_leaf) { den_touched[i] = t; k0_touched[i] = t; }
+        const unsigned bits = __ballot_sync(0xffffffffu, t);
+        if (lane == 0) warp_cnt[warp] = __popc(bits);
+        __syncthreads();
+        const int c = warp_cnt[lane];
+        int incl = c;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        const int warp_off = __shfl_sync(0xffffffffu, incl - c, warp);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int start = running;
+        if (t) {
+            const int slot = start + warp_off + __popc(bits & ((1u << lane) - 1));
+            den_list[slot] = i;
+            k0_list[slot] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running = start + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int n = running;
+        if (n > P.cap_leaves) { atomicExch(me.err, 2); n = P.cap_leaves; }
+        counters[cnt_den] = n;
+        counters[cnt_k0] = n;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch, int parity, const float* __restrict__ den_grad,
+                                                 const float* __restrict__ k0_grad, const float* __restrict__ net_grad,
+                                                 const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
+    const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
+    const int n = counters[cnt_den];
+    float* buf = me.grad[parity];
+    constexpr int T4 = TILE_F / 4;
+    const int total = n * T4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int slot = idx / T4, i = idx - slot * T4;
+        const int leaf = list[slot];
+        const float4 v = i < 128 ? reinterpret_cast<const float4*>(den_grad + (size_t)leaf * 512)[i]
+                                 : reinterpret_cast<const float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128];
+        reinterpret_cast<float4*>(buf)[idx] = v;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < PVDB_NET_N; i += gridDim.x * blockDim.x)
+        buf[(size_t)n * TILE_F + i] = net_grad[i];
+    // last CTA out tells every peer that this rank's tiles are in place (threadFenceReduction pattern; the final
+    // st.release.sys is cumulative over everything the counter made visible)
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(me.done, 1u) == gridDim.x - 1;
+        if (last) { *me.done = 0; __threadfence(); }
+    }
+    __syncthreads();
+    if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, epoch);
+}
+
+__global__ void __launch_bounds__(256) k_dp_reduce(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ den_grad,
+                                                   float* __restrict__ k0_grad, float* __restrict__ net_grad,
+                                                   const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
+    if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, epoch);
+    __syncthreads();
+    const int n = counters[cnt_den];
+    const float* pb[8];
+    for (int r = 0; r < 8; ++r) pb[r] = view(P.base[r < P.world ? r : 0], P.n_leaf, P.cap_leaves).grad[parity];
+    constexpr int T4 = TILE_F / 4;
+    const int total = n * T4;
+    // plain loads: these peer addresses were last read two steps ago in another launch, and the acquire + barrier above
+    // orders them after the peers' packs
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        float4 v[8];
+        #pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < P.world) v[r] = reinterpret_cast<const float4*>(pb[r])[idx];
+        float4 s = v[0];
+        #pragma unroll
+        for (int r = 1; r < 8; ++r)
+            if (r < P.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+        const int slot = idx / T4, i = idx - slot * T4;
+        const int leaf = list[slot];
+        if (i < 128) reinterpret_cast<float4*>(den_grad + (size_t)leaf * 512)[i] = s;
+        else reinterpret_cast<float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128] = s;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < PVDB_NET_N; i += gridDim.x * blockDim.x) {
+        const size_t off = (size_t)n * TILE_F + i;
+        float s = pb[0][off];
+        for (int r = 1; r < P.world; ++r) s += pb[r][off];
+        net_grad[i] = s;
+    }
+}
+
+}  // namespace
+
+extern "C" size_t pvdb_dp_symm_bytes(int n_leaf, int cap_leaves) {
+    if (n_leaf < 0 || cap_leaves < 0) return 0;
+    return grad_off(n_leaf) + 2 * cap_floats(cap_leaves) * sizeof(float);
+}
+extern "C" int pvdb_dp_symm_alloc(size_t bytes, void** ptr, void* handle64) {
+    PVDB_CHECK_ARG(ptr && handle64 && bytes > 0, "null pointer / zero size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    PVDB_CUDA(cudaMalloc(ptr, bytes));
+    PVDB_CUDA(cudaMemset(*ptr, 0, bytes));
+    PVDB_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), *ptr));
+    PVDB_CUDA(cudaDeviceSynchronize());
+    return PVDB_OK;
+}
+extern "C" int pvdb_dp_symm_open(const void* handle64, void** ptr) {
+    PVDB_CHECK_ARG(ptr && handle64, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    PVDB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PVDB_OK;
+}
+extern "C" int pvdb_dp_symm_close(void* ptr) {
+    if (ptr) PVDB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return PVDB_OK;
+}
+extern "C" int pvdb_dp_symm_free(void* ptr) {
+    if (ptr) PVDB_CUDA(cudaFree(ptr));
+    return PVDB_OK;
+}
+extern "C" int pvdb_dp_symm_error(const pvdb_dp_peers* P, int32_t* err_out) {
+    PVDB_CHECK_ARG(P && err_out && P->rank >= 0 && P->rank < 8 && P->base[P->rank], "bad peers");
+    PVDB_CUDA(cudaMemcpy(err_out, view(P->base[P->rank], P->n_leaf, P->cap_leaves).err, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_dp_exchange(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
+    PVDB_CHECK_ARG(P && b && b->tree, "null pointer");
+    PVDB_CHECK_ARG(P->world >= 1 && P->world <= 8 && P->rank >= 0 && P->rank < P->world, "world must be 1..8");
+    PVDB_CHECK_ARG(P->n_leaf == b->tree->n_leaf && P->cap_leaves >= 1, "peers block was sized for another tree");
+    for (int r = 0; r < P->world; ++r) PVDB_CHECK_ARG(P->base[r], "peer block not mapped");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int parity = step & 1;
+    const uint32_t e1 = 2 * step + 1, e2 = 2 * step + 2;   // monotone epochs; the pads start at 0
+    const int CNT_DEN = 2, CNT_K0 = 4;                      // counters[] slots of pvdb_train_bufs (include/plenvdb_b200.h)
+    pvdb_reset_launch_count();
+    pvdb_prof_begin(st);
+    k_dp_union<<<1, 1024, 0, st>>>(*P, e1, parity, b->den_touched, b->k0_touched, b->den_touched_list, b->k0_touched_list, b->counters,
+                                   CNT_DEN, CNT_K0);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("dp_union", st);
+    k_dp_pack<<<PVDB_SMS, 256, 0, st>>>(*P, e2, parity, b->den_grad, b->k0_grad, b->net_grad, b->den_touched_list, b->counters, CNT_DEN);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("dp_pack", st);
+    k_dp_reduce<<<PVDB_SMS * 2, 256, 0, st>>>(*P, e2, parity, b->den_grad, b->k0_grad, b->net_grad, b->den_touched_list, b->counters,
+                                              CNT_DEN);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("dp_reduce", st);
+    return PVDB_OK;
+}

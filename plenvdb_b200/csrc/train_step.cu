@@ -711,7 +711,7 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         U.net = b->net; U.net_g = b->net_grad; U.net_m = b->net_m; U.net_v = b->net_v;
         U.den_touched = b->den_touched; U.k0_touched = b->k0_touched; U.counters = b->counters;
         U.den_list = b->den_touched_list; U.k0_list = b->k0_touched_list;
-        if (!do_bwd) {   // gradients (and flags) came from elsewhere, e.g. a data-parallel all-reduce: rebuild the lists
+        if (!do_bwd && !(phases & PVDB_PHASE_LISTS_READY)) {   // gradients (and flags) came from elsewhere, e.g. a data-parallel all-reduce: rebuild the lists
             const int n_leaf = b->tree->n_leaf;
             PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_DEN, 0, sizeof(int32_t), st));
             PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_K0, 0, sizeof(int32_t), st));

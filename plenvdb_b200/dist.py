@@ -67,45 +67,98 @@ def allreduce_sparse_grads(den_grad, k0_grad, net_grad, leaves, group=None):
     return buf.numel() * 4
 
 
-class DataParallelTrainer:
-    """FusedTrainer + the gradient exchange.  `n_rays` is the PER-RANK shard size.
+class PeerExchange:
+    """The NVLink peer-memory exchange (csrc/dp_exchange.cu): one symmetric block per rank, mapped by every peer through
+    CUDA IPC; the handles travel over torch.distributed (plumbing), the gradients never touch NCCL."""
 
-    Per iteration: forward+backward (local shard, losses normalised by the global batch) -> MAX all-reduce of the two
-    touched-flag arrays -> device-side union list + pack (pvdb_dp_pack) -> one host read of the union size -> ONE SUM
-    all-reduce of the packed tiles + rgbnet gradients -> unpack + the fused sparse Adam (identical on every rank)."""
-
-    def __init__(self, params, density, k0, mask, net, n_rays, world=None, group=None, **kw):
+    def __init__(self, n_leaf, cap_leaves=None, group=None):
         import ctypes as C
         from . import _lib
         self._C, self._lib = C, _lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        assert self.world <= 8, "one NVSwitch domain (<= 8 GPUs)"
+        cap = int(cap_leaves) if cap_leaves else max(int(n_leaf), 1)
+        nbytes = _lib.lib.pvdb_dp_symm_bytes(int(n_leaf), cap)
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.call("pvdb_dp_symm_alloc", nbytes, C.byref(own), handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peers = _lib.pvdb_dp_peers()
+        self.peers.world, self.peers.rank, self.peers.n_leaf, self.peers.cap_leaves = self.world, self.rank, int(n_leaf), cap
+        self._own, self._opened = own, []
+        for r in range(self.world):
+            if r == self.rank:
+                self.peers.base[r] = own.value
+            else:
+                p = C.c_void_p()
+                _lib.call("pvdb_dp_symm_open", C.create_string_buffer(handles[r], 64), C.byref(p))
+                self.peers.base[r] = p.value
+                self._opened.append(p)
+        dist.barrier(group=group)   # every block is zeroed and mapped before the first signal is written
+        self.step = 0
+        self.nbytes = nbytes
+
+    def exchange(self, bufs):
+        self._lib.call("pvdb_dp_exchange", self._C.byref(self.peers), self._C.byref(bufs), self.step, self._lib.current_stream())
+        self.step += 1
+
+    def error(self):
+        e = self._C.c_int32(0)
+        self._lib.call("pvdb_dp_symm_error", self._C.byref(self.peers), self._C.byref(e))
+        return int(e.value)
+
+    def close(self):
+        for p in self._opened:
+            self._lib.call("pvdb_dp_symm_close", p)
+        self._opened = []
+        if self._own is not None:
+            self._lib.call("pvdb_dp_symm_free", self._own)
+            self._own = None
+
+
+class DataParallelTrainer:
+    """FusedTrainer + the gradient exchange.  `n_rays` is the PER-RANK shard size.
+
+    exchange="nvlink" (default on CUDA): forward+backward -> pvdb_dp_exchange (device-side barrier, union of touched
+    leaves, pack, peer-read sum over NVLink; no NCCL, no host sync) -> the fused sparse Adam, identical on every rank.
+    exchange="nccl": MAX all-reduce of the touched flags -> pvdb_dp_pack -> one host read of the union size -> ONE SUM
+    all-reduce of the packed tiles + rgbnet gradients -> pvdb_dp_unpack -> update."""
+
+    def __init__(self, params, density, k0, mask, net, n_rays, world=None, group=None, exchange="nvlink", **kw):
         self.group = group
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.tr = FusedTrainer(params, density, k0, mask, net, n_rays, n_rays_global=n_rays * self.world, **kw)
-        self._init_exchange()
+        self._init_exchange(exchange)
 
-    def _init_exchange(self):
+    def _init_exchange(self, exchange):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
         tr = self.tr
         n_leaf = max(tr.topo.n_leaf, 1)
         dev = tr.dev
+        self.exchange = exchange
+        self.peer = None
+        self.last_exchange_bytes = 0
+        if self.world > 1 and exchange == "nvlink":
+            self.peer = PeerExchange(tr.topo.n_leaf, group=self.group)
+            return
         self.flags = torch.zeros(2 * n_leaf, dtype=torch.int32, device=dev)
         self.union_list = torch.zeros(n_leaf, dtype=torch.int32, device=dev)
         self.union_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.union_count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.cap = n_leaf * 512 * 13 + 22019
         self.buf = torch.empty(self.cap, dtype=torch.float32, device=dev)
-        self.last_exchange_bytes = 0
 
     @classmethod
-    def wrap(cls, trainer, world, group=None):
+    def wrap(cls, trainer, world, group=None, exchange="nvlink"):
         """Turn an existing single-GPU FusedTrainer into the data-parallel one (its loss means become global)."""
-        import ctypes as C
-        from . import _lib
         self = cls.__new__(cls)
-        self._C, self._lib = C, _lib
         self.group, self.world, self.tr = group, world, trainer
         trainer.n_rays_global = trainer.n_rays * world
         trainer._build_structs()
-        self._init_exchange()
+        self._init_exchange(exchange)
         return self
 
     def step(self, rays_o, rays_d, viewdirs, target):
@@ -114,6 +167,11 @@ class DataParallelTrainer:
             tr.step(rays_o, rays_d, viewdirs, target)
             return
         tr.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD)
+        if self.peer is not None:
+            self.peer.exchange(tr._bufs)
+            tr.launches_total += 3
+            tr.update(lists_ready=True)
+            return
         n_leaf = tr.topo.n_leaf
         # 1. union of touched leaves: both flag arrays in one MAX all-reduce
         self.flags[:n_leaf].copy_(tr.t["den_touched"][:n_leaf])
@@ -134,6 +192,13 @@ class DataParallelTrainer:
         tr.launches_total += 4
         tr.update()
         self.last_exchange_bytes = numel * 4 + self.flags.numel() * 4
+
+    def exchange_bytes(self):
+        """Bytes this rank moved over NVLink in the last exchange (peer reads, or the all-reduce payload)."""
+        if self.peer is not None:
+            n = int(self.tr.t["counters"][2].item())
+            return (self.world - 1) * (n * 512 * 13 + 22019) * 4 + (self.world - 1) * self.tr.topo.n_leaf * 4
+        return self.last_exchange_bytes
 
 
 def render_sharded(renderer, c2w_dev, rank, world, gather=True, group=None):

@@ -15,7 +15,7 @@ from . import _lib
 from .plenvdb import ColorVDB, DensityVDB
 from .tree import Topology
 
-PHASE_FORWARD, PHASE_BACKWARD, PHASE_UPDATE = 1, 2, 4
+PHASE_FORWARD, PHASE_BACKWARD, PHASE_UPDATE, PHASE_LISTS_READY = 1, 2, 4, 8
 NET_N = 22019
 
 
@@ -161,13 +161,14 @@ class FusedTrainer:
     def forward_backward(self, rays_o, rays_d, viewdirs, target):
         self.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD)
 
-    def update(self):
-        """Apply the optimisers to whatever gradients are accumulated (after a gradient all-reduce)."""
+    def update(self, lists_ready=False):
+        """Apply the optimisers to whatever gradients are accumulated (after a gradient all-reduce).  lists_ready: the
+        touched-leaf lists were already rebuilt by pvdb_dp_exchange."""
         dummy = self.t["t_min"]
         self.step_count += 1
         self._set_step_scalars()
         _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(dummy), _lib.ptr(dummy), _lib.ptr(dummy),
-                  None, self.n_rays, PHASE_UPDATE, _lib.current_stream())
+                  None, self.n_rays, PHASE_UPDATE | (PHASE_LISTS_READY if lists_ready else 0), _lib.current_stream())
         self.launches_total += int(_lib.lib.pvdb_last_launch_count())
 
     def forward(self, rays_o, rays_d, viewdirs):

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, exchange="nvlink"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as dist
     from plenvdb_b200 import dist as pdist
@@ -32,12 +32,13 @@ def _worker(rank, world, port, q):
     rays = synth.ray_batch(2048, H=200, W=200, K=synth.intrinsics(200, 200), seed=777)
     lo, hi = pdist.shard_range(2048, rank, world)
     den, k0 = build_scene_grids(scene, device=dev)
-    dp = pdist.DataParallelTrainer(scene, den, k0, scene["mask"], net, hi - lo, device=dev)
+    dp = pdist.DataParallelTrainer(scene, den, k0, scene["mask"], net, hi - lo, device=dev, exchange=exchange)
     shard = [torch.from_numpy(a[lo:hi].copy()).to(dev) for a in rays]
     for _ in range(2):
         dp.step(*shard)
     torch.cuda.synchronize()
-    res = dict(den=den.get_dense_grid(), k0=k0.get_dense_grid(), net=dp.tr.net.cpu().numpy(), bytes=dp.last_exchange_bytes)
+    res = dict(den=den.get_dense_grid(), k0=k0.get_dense_grid(), net=dp.tr.net.cpu().numpy(), bytes=dp.exchange_bytes(),
+               err=dp.peer.error() if dp.peer is not None else 0)
     if rank == 0:   # single-GPU reference on the full batch
         den1, k01 = build_scene_grids(scene, device=dev)
         tr = FusedTrainer(scene, den1, k01, scene["mask"], net, 2048, device=dev)
@@ -51,13 +52,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_gpu_dp_step_matches_single_gpu():
+@pytest.mark.parametrize("exchange", ["nvlink", "nccl"])
+def test_two_gpu_dp_step_matches_single_gpu(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, exchange)) for r in range(2)]
     for p in procs:
         p.start()
     out = dict(q.get(timeout=300) for _ in range(2))
@@ -65,6 +67,7 @@ def test_two_gpu_dp_step_matches_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     a, b = out[0], out[1]
+    assert a["err"] == 0 and b["err"] == 0
     # replicas stay identical (same reduced gradients, same Adam)
     assert np.array_equal(a["den"], b["den"]) and np.array_equal(a["k0"], b["k0"]) and np.array_equal(a["net"], b["net"])
     assert a["bytes"] > 0
