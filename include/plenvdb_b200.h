@@ -204,6 +204,8 @@ typedef struct pvdb_train_bufs {
     float *k_x;                                /* [tile][40][128] rgbnet inputs (12 k0 + 27 PE + pad), tensor-core path */
     float *k_dh0, *k_dh1;                      /* [tile][128][128] masked activation gradients, tensor-core backward */
     uint32_t *k_mask;                          /* [tile][8][128] ReLU sign bits of h0 (words 0-3) and h1 (words 4-7) */
+    int32_t *k_corner;                         /* [cap_keep][8] record id (leaf*512+voxel) of the 8 trilinear corners, -1 = none */
+    void *net_img;                             /* >= 512 KiB scratch: tf32 hi/lo weight images of the tensor-core kernels */
     /* touched-leaf bookkeeping, [n_leaf] each */
     int32_t *den_touched, *k0_touched, *den_touched_list, *k0_touched_list;
     int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0 */
@@ -286,6 +288,7 @@ typedef struct pvdb_render_bufs {
     float *s_feat;                   /* [cap][12] */
     float *s_rgb;                    /* [cap][3] weight * sigmoid(rgbnet) */
     int32_t *counters;               /* [8]: 0 total samples, 1 overflow flag, 2 rays whose two passes disagree */
+    void *w_img;                     /* >= 256 KiB scratch: tf32 hi/lo weight image (use_tensor_cores) */
 } pvdb_render_bufs;
 
 /* Renders rows [row_begin,row_end) of the H x W image for camera `c2w` (device float[16], row-major 4x4) into

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libplenvdb_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
-          "--expt-relaxed-constexpr"]
+          "--expt-relaxed-constexpr"] + os.environ.get("PVDB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

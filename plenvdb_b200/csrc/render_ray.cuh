@@ -59,6 +59,7 @@ struct RenderMlpArgs {
     const float *w0, *b0, *w1, *b1, *w2, *b2;
     const int32_t* s_ray; const float* s_weight; const float* s_feat; float* s_rgb;
     const int32_t* counters; int64_t cap; int row_begin;
+    unsigned char* img;   // tcgen05 weight image scratch (pvdb_render_bufs.w_img)
 };
 
 }  // namespace

@@ -427,7 +427,7 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
     RenderMlpArgs A;
     A.C = C; A.c2w = c2w; A.w0 = b->w0; A.b0 = b->b0; A.w1 = b->w1; A.b1 = b->b1; A.w2 = b->w2; A.b2 = b->b2;
     A.s_ray = b->s_ray; A.s_weight = b->s_weight; A.s_feat = b->s_feat; A.s_rgb = b->s_rgb; A.counters = b->counters;
-    A.cap = b->cap_samples; A.row_begin = row_begin;
+    A.cap = b->cap_samples; A.row_begin = row_begin; A.img = static_cast<unsigned char*>(b->w_img);
     if (cfg->use_tensor_cores) {
         int rc = pvdb_render_mlp_tc(&A, st);
         if (rc) return rc;

@@ -23,41 +23,48 @@ namespace {
 
 constexpr int WD = PVDB_NET_W;     // 128
 constexpr int K0P = 40;            // layer-0 K (39 padded to a multiple of 8)
-constexpr int N2P = 16;            // layer-2 N (3 padded to the UMMA minimum for M = 128)
 constexpr int CNT_M_KEEP = 1;
 
-// TMEM column map (512 columns allocated): A_hi [0,128) A_lo [128,256) D [256,384)
-constexpr uint32_t COL_AHI = 0, COL_ALO = 128, COL_D = 256;
+// TMEM column map (512 columns allocated): A_hi [0,128) A_lo [128,256) D0 [256,384) D1 [384,512).
+// Two accumulators let the tensor core run one layer while the lane warps drain the other.
+constexpr uint32_t COL_AHI = 0, COL_ALO = 128, COL_D0 = 256, COL_D1 = 384;
 
-// shared memory map (bytes)
-constexpr int SM_W0HI = 0;                                  // [128][40] tf32 hi, canonical K-major
+// Shared memory map (bytes).  [0, IMG_BYTES) is the "weight image": hi/lo tf32 splits of W0, W1 in the canonical K-major
+// UMMA layout, then W2 and the biases as plain fp32.  k_prep_fwd_image builds it once per launch in global memory and
+// every CTA pulls it in with one bulk async copy (TMA 1-D) instead of re-splitting 22 k weights itself.
+constexpr int SM_W0HI = 0;                                  // [128][40]
 constexpr int SM_W0LO = SM_W0HI + WD * K0P * 4;
 constexpr int SM_W1HI = SM_W0LO + WD * K0P * 4;             // [128][128]
 constexpr int SM_W1LO = SM_W1HI + WD * WD * 4;
-constexpr int SM_W2HI = SM_W1LO + WD * WD * 4;              // [16][128]
-constexpr int SM_W2LO = SM_W2HI + N2P * WD * 4;
-constexpr int SM_B0 = SM_W2LO + N2P * WD * 4;               // [128] floats
+constexpr int SM_W2F = SM_W1LO + WD * WD * 4;               // [3][128] fp32 (layer 2 runs on the CUDA cores)
+constexpr int SM_B0 = SM_W2F + 3 * WD * 4;
 constexpr int SM_B1 = SM_B0 + WD * 4;
 constexpr int SM_B2 = SM_B1 + WD * 4;                       // [4]
-constexpr int SM_BAR = SM_B2 + 16;                          // mbarrier (8 B) + tmem base (4 B)
-constexpr int SM_XBUF = SM_BAR + 16;                        // staging rows of the next tile: [128][44] floats
-constexpr int SM_TOTAL = SM_XBUF + 128 * 44 * 4;
+constexpr int IMG_BYTES = SM_B2 + 16;
+constexpr int SM_BAR = IMG_BYTES;   // mbarriers: W, L0, L1, FULL[2], EMPTY[2], X_RDY, A_RDY[4]; tmem base at +96
+constexpr int BAR_W = 0, BAR_L0 = 8, BAR_L1 = 16, BAR_FULL = 24, BAR_EMPTY = 40, BAR_XRDY = 56, BAR_ARDY = 64, TMEM_SLOT = 96;
+constexpr int XLD = 44;   // staging row stride in floats: 16-byte row reads/writes by 8 consecutive threads hit distinct banks
+constexpr int SM_RED = SM_BAR + 112;                        // [3][128] partial outputs of the second lane-warp group
+constexpr int SM_XBUF = SM_RED + 3 * 128 * 4;               // two staging buffers [128][44] floats
+constexpr int XBUF_BYTES = 128 * XLD * 4;
+constexpr int SM_TOTAL = SM_XBUF + 2 * XBUF_BYTES;
+static_assert(IMG_BYTES % 16 == 0 && SM_XBUF % 16 == 0 && SM_TOTAL <= 227 * 1024, "smem map");
 
-// Issue the 3xTF32 MMAs of one layer: D[128 x N] = A[128 x K] * W[N x K]^T.  Single thread.
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t smem_base, int off_hi, int off_lo, int K, int N, uint32_t bar) {
+// Issue the 3xTF32 MMAs of k-steps [ks0, ks1) of one layer: D[128 x N] (+)= A[128 x K] * W[N x K]^T.  Single thread.
+__device__ __forceinline__ void issue_ksteps(uint32_t tmem, uint32_t d_col, uint32_t smem_base, int off_hi, int off_lo, int K, int N,
+                                             int ks0, int ks1, bool zero_first) {
     const uint32_t idesc = make_idesc(N);
     const uint64_t bhi = make_desc(smem_base + off_hi, K), blo = make_desc(smem_base + off_lo, K);
-    uint32_t acc = 0;
-    for (int ks = 0; ks < K / 8; ++ks) {
+    uint32_t acc = zero_first ? 0u : 1u;
+    for (int ks = ks0; ks < ks1; ++ks) {
         // one k-step = 8 tf32 = two 16-byte chunks = 256 B further along the group: start address field is in 16-B units
         const uint64_t adv = (uint64_t)(ks * 256) >> 4;
         const uint32_t ahi = tmem + COL_AHI + ks * 8, alo = tmem + COL_ALO + ks * 8;
-        umma_tf32_ts(tmem + COL_D, ahi, bhi + adv, idesc, acc);
+        umma_tf32_ts(tmem + d_col, ahi, bhi + adv, idesc, acc);
         acc = 1;
-        umma_tf32_ts(tmem + COL_D, alo, bhi + adv, idesc, 1);
-        umma_tf32_ts(tmem + COL_D, ahi, blo + adv, idesc, 1);
+        umma_tf32_ts(tmem + d_col, alo, bhi + adv, idesc, 1);
+        umma_tf32_ts(tmem + d_col, ahi, blo + adv, idesc, 1);
     }
-    umma_commit(bar);
 }
 
 // Write a row of activations (n values, multiple of 8, starting at column c0) as the next A operand.
@@ -72,120 +79,236 @@ __device__ __forceinline__ void store_a_row(uint32_t tmem_lane, int c0, const fl
     }
 }
 
+// Optional phase timing (build with PVDB_EXTRA_NVCC_FLAGS=-DPVDB_TC_TIMING): clock64 stamps of thread 0, first 8 tiles per CTA.
+#ifdef PVDB_TC_TIMING
+__device__ long long g_tc_t[PVDB_SMS][8][16];
+#define TC_T(i) do { if (tid == 0 && tile_no < 8) g_tc_t[blockIdx.x][tile_no][i] = clock64(); } while (0)
+#else
+#define TC_T(i) do { } while (0)
+#endif
+
 struct TcWeights {
     const float *w0, *b0, *w1, *b1, *w2, *b2;
     int w0_sn, w0_sk, w1_sn, w1_sk, w2_sn, w2_sk;   // strides (floats) of W[n][k]
 };
 
-// Common body, warp specialised.  Warps 0-3 ("lane warps", one thread per TMEM lane = sample) run the MLP; warps 4-7
-// ("producers") gather the NEXT tile's input rows (k0 trilinear / feature list + view PE, the memory- and SFU-latency
-// bound part) into a shared staging buffer while the lane warps are busy with the current tile.
+// Build the weight image (see the smem map) in global memory.  Any grid; ~22 k elements.
+__global__ void __launch_bounds__(256) k_prep_fwd_image(TcWeights Wt, unsigned char* __restrict__ img) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int e = gtid; e < WD * K0P; e += gsz) {
+        const int n = e / K0P, k = e % K0P;
+        const float v = k < PVDB_NET_DIN ? __ldg(Wt.w0 + (size_t)n * Wt.w0_sn + (size_t)k * Wt.w0_sk) : 0.f;
+        uint32_t hi, lo;
+        split_tf32(v, hi, lo);
+        const int o = canon_off(n, k, K0P);
+        *reinterpret_cast<uint32_t*>(img + SM_W0HI + o) = hi;
+        *reinterpret_cast<uint32_t*>(img + SM_W0LO + o) = lo;
+    }
+    for (int e = gtid; e < WD * WD; e += gsz) {
+        const int n = e / WD, k = e % WD;
+        const float v = __ldg(Wt.w1 + (size_t)n * Wt.w1_sn + (size_t)k * Wt.w1_sk);
+        uint32_t hi, lo;
+        split_tf32(v, hi, lo);
+        const int o = canon_off(n, k, WD);
+        *reinterpret_cast<uint32_t*>(img + SM_W1HI + o) = hi;
+        *reinterpret_cast<uint32_t*>(img + SM_W1LO + o) = lo;
+    }
+    float* w2f = reinterpret_cast<float*>(img + SM_W2F);
+    for (int e = gtid; e < 3 * WD; e += gsz) w2f[e] = __ldg(Wt.w2 + (size_t)(e / WD) * Wt.w2_sn + (size_t)(e % WD) * Wt.w2_sk);
+    for (int e = gtid; e < WD; e += gsz) {
+        reinterpret_cast<float*>(img + SM_B0)[e] = __ldg(Wt.b0 + e);
+        reinterpret_cast<float*>(img + SM_B1)[e] = __ldg(Wt.b1 + e);
+    }
+    if (gtid < 4) reinterpret_cast<float*>(img + SM_B2)[gtid] = gtid < 3 ? __ldg(Wt.b2 + gtid) : 0.f;
+}
+
+// Common body, warp specialised (13 warps):
+//   warps 0-7   "lane warps": thread = (TMEM lane = sample, column half).  Warp w and w+4 share the 32 lanes of quarter
+//               w%4 (the TMEM access rule) and split every 128-column row in two.  They run the epilogues (bias, ReLU, tf32
+//               split back into TMEM as the next A operand, activation stores) and the 128 -> 3 output layer on the CUDA cores;
+//   warps 8-11  "producers": gather the input rows of the tiles ahead (k0 trilinear / feature list + view PE, the memory-
+//               and SFU-latency bound part) into two shared staging buffers (full/empty mbarriers);
+//   warp 12     "issuer": one thread feeds the tensor core.  It never touches TMEM data itself, so the lane warps are never
+//               held up behind a queue of MMAs: they signal "chunk c of A is in TMEM" through mbarriers and move on.
+// Per tile: epilogue 0 drains D0 in four 32-column chunks and the issuer starts layer 1's k-steps of each chunk (into D1)
+// as soon as it lands; while the lane warps run epilogue 1 from D1, the next tile's layer 0 already runs into D0.
 // FeatFn(s, x[40]) fills the input row of sample s; ActFn sees each post-ReLU chunk; OutFn(s, raw[3]) consumes the result.
-constexpr int FWD_THREADS = 256;
-constexpr int XLD = 44;   // staging row stride in floats: 16-byte row reads/writes by 8 consecutive threads hit distinct banks
-__device__ __forceinline__ void lane_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+constexpr int FWD_THREADS = 416;
+constexpr int N_LANE_THREADS = 256;
 
 template <class FeatFn, class OutFn, class ActFn>
-__device__ void mlp_tiles(unsigned char* smem, const TcWeights& Wt, int64_t M, FeatFn feat, OutFn out, ActFn act) {
+__device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__ img, int64_t M, FeatFn feat, OutFn out, ActFn act) {
     const int tid = threadIdx.x, warp = tid >> 5;
-    const bool lane_warp = tid < TM;
+    int tile_no = 0;
+    TC_T(0);
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar = sbase + SM_BAR;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8);
-    float* sb0 = reinterpret_cast<float*>(smem + SM_B0);
-    float* sb1 = reinterpret_cast<float*>(smem + SM_B1);
-    float* sb2 = reinterpret_cast<float*>(smem + SM_B2);
-    float* xbuf = reinterpret_cast<float*>(smem + SM_XBUF);
-    load_weight(smem, SM_W0HI, SM_W0LO, Wt.w0, Wt.w0_sn, Wt.w0_sk, WD, K0P, WD, PVDB_NET_DIN);
-    load_weight(smem, SM_W1HI, SM_W1LO, Wt.w1, Wt.w1_sn, Wt.w1_sk, WD, WD, WD, WD);
-    load_weight(smem, SM_W2HI, SM_W2LO, Wt.w2, Wt.w2_sn, Wt.w2_sk, N2P, WD, 3, WD);
-    if (tid < WD) { sb0[tid] = __ldg(Wt.b0 + tid); sb1[tid] = __ldg(Wt.b1 + tid); }
-    if (tid < 3) sb2[tid] = __ldg(Wt.b2 + tid);
-    if (tid == 0) mbar_init(bar, 1);
-    if (warp == 0) tmem_alloc(sbase + SM_BAR + 8, 512);
-    fence_async_smem();           // weights written through the generic proxy, read by the tensor core (async proxy)
+    const uint32_t bars = sbase + SM_BAR;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + TMEM_SLOT);
+    const float* sb0 = reinterpret_cast<const float*>(smem + SM_B0);
+    const float* sb1 = reinterpret_cast<const float*>(smem + SM_B1);
+    const float* sb2 = reinterpret_cast<const float*>(smem + SM_B2);
+    const float* sw2 = reinterpret_cast<const float*>(smem + SM_W2F);
+    float* red = reinterpret_cast<float*>(smem + SM_RED);
+    if (tid == 0) {
+        mbar_init(bars + BAR_W, 1);
+        mbar_init(bars + BAR_L0, 1);
+        mbar_init(bars + BAR_L1, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(bars + BAR_FULL + 8 * b, 128); mbar_init(bars + BAR_EMPTY + 8 * b, N_LANE_THREADS); }
+        mbar_init(bars + BAR_XRDY, N_LANE_THREADS);
+        for (int c = 0; c < 4; ++c) mbar_init(bars + BAR_ARDY + 8 * c, 128);
+        fence_async_smem();
+        mbar_expect_tx(bars + BAR_W, IMG_BYTES);
+        constexpr int CH = 32768;
+        for (int o = 0; o < IMG_BYTES; o += CH) bulk_g2s(sbase + o, img + o, min(CH, IMG_BYTES - o), bars + BAR_W);
+    }
+    if (warp == 0) tmem_alloc(sbase + SM_BAR + TMEM_SLOT, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32-lane quarter
-    uint32_t parity = 0;
     const int64_t n_tiles = (M + TM - 1) / TM;
-    auto produce = [&](int64_t tile) {
-        const int p = tid - TM;
-        const int64_t s = tile * TM + p;
-        float x[K0P];
-#pragma unroll
-        for (int i = 0; i < K0P; ++i) x[i] = 0.f;
-        if (s < M) feat(s, x);
-        float4* row = reinterpret_cast<float4*>(xbuf + p * XLD);
-#pragma unroll
-        for (int q = 0; q < K0P / 4; ++q) row[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
-    };
-    if (!lane_warp && (int64_t)blockIdx.x < n_tiles) produce(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        __syncthreads();            // staging buffer holds this tile's rows
-        float x[K0P];
-        if (lane_warp) {
-            const float4* row = reinterpret_cast<const float4*>(xbuf + tid * XLD);
-#pragma unroll
-            for (int q = 0; q < K0P / 4; ++q) { const float4 v = row[q]; x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w; }
-        }
-        __syncthreads();            // staging buffer is free again
-        if (!lane_warp) {
-            if (tile + gridDim.x < n_tiles) produce(tile + gridDim.x);
-            continue;
-        }
-        const int64_t s = tile * TM + tid;
-        const bool valid = s < M;
-        // ---- layer-0 input row -> TMEM
-        store_a_row(lane_addr, 0, x, K0P);
-        tmem_st_wait();
-        tc_fence_before();
-        lane_bar();
-        if (tid == 0) { tc_fence_after(); issue_layer(tmem, sbase, SM_W0HI, SM_W0LO, K0P, WD, bar); }
-        mbar_wait(bar, parity); parity ^= 1;
-        tc_fence_after();
-        // ---- hidden layers: D -> bias + ReLU -> next A
-#pragma unroll 1
-        for (int layer = 0; layer < 2; ++layer) {
-            const float* sb = layer == 0 ? sb0 : sb1;
-#pragma unroll 1
-            for (int c = 0; c < WD; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + COL_D + c, r);
-                tmem_ld_wait();
-                float h[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) h[i] = fmaxf(__uint_as_float(r[i]) + sb[c + i], 0.f);
-                if (valid) act(s, layer, c, h);
-                store_a_row(lane_addr, c, h, 32);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            lane_bar();
-            if (tid == 0) {
-                tc_fence_after();
-                if (layer == 0) issue_layer(tmem, sbase, SM_W1HI, SM_W1LO, WD, WD, bar);
-                else issue_layer(tmem, sbase, SM_W2HI, SM_W2LO, WD, N2P, bar);
-            }
-            mbar_wait(bar, parity); parity ^= 1;
+    TC_T(1);
+
+    if (warp == 12) {
+        // ---------------- issuer
+        if (tid == 384 && (int64_t)blockIdx.x < n_tiles) {
+            mbar_wait(bars + BAR_W, 0);          // weight image landed
+            int i = 0;
+            mbar_wait(bars + BAR_XRDY, 0);
             tc_fence_after();
+            issue_ksteps(tmem, COL_D0, sbase, SM_W0HI, SM_W0LO, K0P, WD, 0, K0P / 8, true);
+            umma_commit(bars + BAR_L0);
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+                for (int c = 0; c < 4; ++c) {
+                    mbar_wait(bars + BAR_ARDY + 8 * c, i & 1);
+                    tc_fence_after();
+                    issue_ksteps(tmem, COL_D1, sbase, SM_W1HI, SM_W1LO, WD, WD, c * 4, c * 4 + 4, c == 0);
+                }
+                umma_commit(bars + BAR_L1);
+                if (tile + gridDim.x < n_tiles) {
+                    mbar_wait(bars + BAR_XRDY, (i + 1) & 1);
+                    tc_fence_after();
+                    issue_ksteps(tmem, COL_D0, sbase, SM_W0HI, SM_W0LO, K0P, WD, 0, K0P / 8, true);
+                    umma_commit(bars + BAR_L0);
+                }
+            }
         }
-        // ---- output layer
-        {
-            uint32_t r[16];
-            tmem_ld16(lane_addr + COL_D, r);
-            tmem_ld_wait();
-            if (valid) {
-                const float raw[3] = {__uint_as_float(r[0]) + sb2[0], __uint_as_float(r[1]) + sb2[1], __uint_as_float(r[2]) + sb2[2]};
+    } else if (warp >= 8) {
+        // ---------------- producers
+        const int p = tid - N_LANE_THREADS;
+        int i = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+            const int b = i & 1;
+            if (i >= 2) mbar_wait(bars + BAR_EMPTY + 8 * b, ((i >> 1) - 1) & 1);
+            const int64_t s = tile * TM + p;
+            float x[K0P];
+#pragma unroll
+            for (int q = 0; q < K0P; ++q) x[q] = 0.f;
+            if (s < M) feat(s, x);
+            float4* row = reinterpret_cast<float4*>(smem + SM_XBUF + b * XBUF_BYTES) + p * (XLD / 4);
+#pragma unroll
+            for (int q = 0; q < K0P / 4; ++q) row[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+            mbar_arrive(bars + BAR_FULL + 8 * b);
+        }
+    } else if ((int64_t)blockIdx.x < n_tiles) {
+        // ---------------- lane warps
+        const int grp = warp >> 2;                               // column half
+        const int lane_s = (warp & 3) * 32 + (tid & 31);         // sample within the tile = TMEM lane
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32-lane quarter
+        uint32_t par0 = 0, par1 = 0;
+        int i = 0;
+        // take this thread's part of tile `it`'s staged row (group 0: columns 0-23, group 1: 24-39), hand the buffer back,
+        // write it as the layer-0 A operand and tell the issuer
+        auto start_tile = [&](int it) {
+            const int b = it & 1;
+            mbar_wait(bars + BAR_FULL + 8 * b, (it >> 1) & 1);
+            const float4* row = reinterpret_cast<const float4*>(smem + SM_XBUF + b * XBUF_BYTES) + lane_s * (XLD / 4);
+            float x[24];
+            if (grp == 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { const float4 v = row[q]; x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w; }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const float4 v = row[6 + q]; x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w; }
+            }
+            mbar_arrive(bars + BAR_EMPTY + 8 * b);
+            if (grp == 0) store_a_row(lane_addr, 0, x, 24); else store_a_row(lane_addr, 24, x, 16);
+            tmem_st_wait();
+            tc_fence_before();     // also orders this thread's earlier D0 reads before the issuer's next layer-0 MMAs
+            mbar_arrive(bars + BAR_XRDY);
+        };
+        start_tile(0);
+        mbar_wait(bars + BAR_W, 0);      // biases / W2 of the image are read below
+        const int cb = grp * 64;         // this thread's 64 columns of every 128-column row
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i, ++tile_no) {
+            const int64_t s = tile * TM + lane_s;
+            const bool valid = s < M;
+            TC_T(2);
+            mbar_wait(bars + BAR_L0, par0); par0 ^= 1;
+            tc_fence_after();
+            TC_T(3);
+            // ---- epilogue 0: D0 -> bias + ReLU -> A; layer 1 follows chunk by chunk on the tensor core
+            {
+                uint32_t r[2][32];
+                tmem_ld32(lane_addr + COL_D0 + cb, r[0]);
+                tmem_ld32(lane_addr + COL_D0 + cb + 32, r[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = cb + j * 32;
+                    float h[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]) + sb0[c + q], 0.f);
+                    store_a_row(lane_addr, c, h, 32);
+                    tmem_st_wait();
+                    tc_fence_before();   // (first chunk: also orders the previous tile's D1 reads before the new layer-1 MMAs)
+                    mbar_arrive(bars + BAR_ARDY + 8 * (c >> 5));
+                    if (valid) act(s, 0, c, h);
+                }
+            }
+            TC_T(4);
+            mbar_wait(bars + BAR_L1, par1); par1 ^= 1;
+            tc_fence_after();
+            TC_T(5);
+            // ---- the next tile's layer 0 runs under this tile's second epilogue
+            if (tile + gridDim.x < n_tiles) start_tile(i + 1);
+            TC_T(6);
+            // ---- epilogue 1: D1 -> bias + ReLU -> 128 -> 3 output layer on the CUDA cores
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+            {
+                uint32_t r[2][32];
+                tmem_ld32(lane_addr + COL_D1 + cb, r[0]);
+                tmem_ld32(lane_addr + COL_D1 + cb + 32, r[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = cb + j * 32;
+                    float h[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]) + sb1[c + q], 0.f);
+                    if (valid) act(s, 1, c, h);
+#pragma unroll
+                    for (int q = 0; q < 32; q += 4) {
+                        const float4 a = *reinterpret_cast<const float4*>(sw2 + c + q);
+                        const float4 bq = *reinterpret_cast<const float4*>(sw2 + WD + c + q);
+                        const float4 cq = *reinterpret_cast<const float4*>(sw2 + 2 * WD + c + q);
+                        o0 = fmaf(h[q], a.x, o0); o0 = fmaf(h[q + 1], a.y, o0); o0 = fmaf(h[q + 2], a.z, o0); o0 = fmaf(h[q + 3], a.w, o0);
+                        o1 = fmaf(h[q], bq.x, o1); o1 = fmaf(h[q + 1], bq.y, o1); o1 = fmaf(h[q + 2], bq.z, o1); o1 = fmaf(h[q + 3], bq.w, o1);
+                        o2 = fmaf(h[q], cq.x, o2); o2 = fmaf(h[q + 1], cq.y, o2); o2 = fmaf(h[q + 2], cq.z, o2); o2 = fmaf(h[q + 3], cq.w, o2);
+                    }
+                }
+            }
+            // the two column halves meet in shared memory: group 1 hands its partial sums to group 0
+            if (grp == 1) { red[lane_s] = o0; red[128 + lane_s] = o1; red[256 + lane_s] = o2; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (grp == 0 && valid) {
+                const float raw[3] = {o0 + red[lane_s] + sb2[0], o1 + red[128 + lane_s] + sb2[1], o2 + red[256 + lane_s] + sb2[2]};
                 out(s, raw);
             }
+            TC_T(7);
         }
-        tc_fence_before();
-        lane_bar();          // every lane has drained D before the next tile's MMAs overwrite it
-        tc_fence_after();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
@@ -209,30 +332,38 @@ struct TrainFwdArgs {
     const float* k0; const float* viewdirs; const int32_t* k_ray; const float* k_xyz;
     float *k_feat, *k_h0, *k_h1, *k_rgb, *k_x;
     uint32_t* k_mask;
+    const int32_t* k_corner;
     const int32_t* counters; int64_t cap_keep;
-    TcWeights W;
+    const unsigned char* img;
 };
 
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
     auto feat = [&](int64_t s, float* x) {
-        // 12-channel trilinear sample, colorvdb.cu:81-111 arithmetic and corner order
+        // 12-channel trilinear sample, colorvdb.cu:81-111 arithmetic and corner order.  The eight record ids were found
+        // by the march (same topology as the density grid), so all 24 16-byte loads are independent and in flight at
+        // once; a missing corner contributes fma(sc, 0, x) = x, bit-identical to skipping it.
         const float* p = A.k_xyz + s * 3;
         PvdbTri tri;
         tri.set(p[0], p[1], p[2]);
-        PvdbLeafCache cache;
+        const int4 ca = __ldg(reinterpret_cast<const int4*>(A.k_corner + s * 8));
+        const int4 cb = __ldg(reinterpret_cast<const int4*>(A.k_corner + s * 8) + 1);
+        const int rec[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        float4 v[8][3];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4* src = reinterpret_cast<const float4*>(A.k0 + (size_t)max(rec[q], 0) * 12);
+#pragma unroll
+            for (int c4 = 0; c4 < 3; ++c4) v[q][c4] = rec[q] >= 0 ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
-            const int cx = tri.i + dx, cy = tri.j + dy, cz = tri.k + dz;
-            const int leaf = cache.find(A.tree, cx, cy, cz);
-            if (leaf < 0) continue;
             const float sc = __fmul_rn(__fmul_rn(tri.f(0, dx), tri.f(1, dy)), tri.f(2, dz));
-            const float4* v = reinterpret_cast<const float4*>(A.k0 + ((size_t)leaf * 512 + pvdb_leaf_off(cx, cy, cz)) * 12);
 #pragma unroll
             for (int c4 = 0; c4 < 3; ++c4) {
-                const float4 a = __ldg(v + c4);
+                const float4 a = v[q][c4];
                 x[c4 * 4 + 0] = __fmaf_rn(sc, a.x, x[c4 * 4 + 0]); x[c4 * 4 + 1] = __fmaf_rn(sc, a.y, x[c4 * 4 + 1]);
                 x[c4 * 4 + 2] = __fmaf_rn(sc, a.z, x[c4 * 4 + 2]); x[c4 * 4 + 3] = __fmaf_rn(sc, a.w, x[c4 * 4 + 3]);
             }
@@ -265,11 +396,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
 #pragma unroll
         for (int i = 0; i < 32; ++i) g[i * 128] = h[i];
     };
-    mlp_tiles(smem, A.W, M, feat, out, act);
+    mlp_tiles(smem, A.img, M, feat, out, act);
 }
 
 // ---- merged renderer MLP (renderer.cu:83-119): features from the gathered list, PE from the pixel's view direction
-__global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs A, TcWeights W) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int64_t M = min((int64_t)A.counters[0], A.cap);
     auto feat = [&](int64_t s, float* x) {
@@ -297,10 +428,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs 
         for (int j = 0; j < 3; ++j) A.s_rgb[s * 3 + j] = w / (1 + expf(-raw[j]));   // final_render (:115-117)
     };
     auto act = [&](int64_t, int, int, const float*) {};
-    mlp_tiles(smem, W, M, feat, out, act);
+    mlp_tiles(smem, A.img, M, feat, out, act);
 }
 
 }  // namespace
+
+#ifdef PVDB_TC_TIMING
+extern "C" int pvdb_debug_tc_timing(long long* out) {
+    PVDB_CUDA(cudaMemcpyFromSymbol(out, g_tc_t, sizeof(long long) * PVDB_SMS * 8 * 16));
+    return PVDB_OK;
+}
+#endif
 
 int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
     static bool attr_set = false;
@@ -308,14 +446,20 @@ int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         PVDB_CUDA(cudaFuncSetAttribute(k_rgbnet_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         attr_set = true;
     }
+    PVDB_CHECK_ARG(b->net_img && b->k_corner, "net_img / k_corner scratch missing (tensor-core rgbnet)");
     TrainFwdArgs A;
     A.tree = *b->tree; A.k0 = b->k0; A.viewdirs = viewdirs; A.k_ray = b->k_ray; A.k_xyz = b->k_xyz; A.k_feat = b->k_feat;
     A.k_h0 = b->k_h0; A.k_h1 = b->k_h1; A.k_rgb = b->k_rgb; A.k_x = b->k_x; A.k_mask = b->k_mask; A.counters = b->counters; A.cap_keep = b->cap_keep;
+    A.k_corner = b->k_corner;
+    A.img = static_cast<const unsigned char*>(b->net_img);
     const float* net = b->net;   // PyTorch layout: W[n][k] row-major
-    A.W.w0 = net + PVDB_NET_OFF_W0; A.W.w0_sn = PVDB_NET_DIN; A.W.w0_sk = 1;
-    A.W.w1 = net + PVDB_NET_OFF_W1; A.W.w1_sn = WD; A.W.w1_sk = 1;
-    A.W.w2 = net + PVDB_NET_OFF_W2; A.W.w2_sn = WD; A.W.w2_sk = 1;
-    A.W.b0 = net + PVDB_NET_OFF_B0; A.W.b1 = net + PVDB_NET_OFF_B1; A.W.b2 = net + PVDB_NET_OFF_B2;
+    TcWeights W;
+    W.w0 = net + PVDB_NET_OFF_W0; W.w0_sn = PVDB_NET_DIN; W.w0_sk = 1;
+    W.w1 = net + PVDB_NET_OFF_W1; W.w1_sn = WD; W.w1_sk = 1;
+    W.w2 = net + PVDB_NET_OFF_W2; W.w2_sn = WD; W.w2_sk = 1;
+    W.b0 = net + PVDB_NET_OFF_B0; W.b1 = net + PVDB_NET_OFF_B1; W.b2 = net + PVDB_NET_OFF_B2;
+    k_prep_fwd_image<<<32, 256, 0, st>>>(W, static_cast<unsigned char*>(b->net_img));
+    PVDB_LAUNCH_CHECK();
     k_rgbnet_fwd_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
@@ -333,7 +477,10 @@ int pvdb_render_mlp_tc(const void* render_mlp_args, cudaStream_t st) {
     W.w1 = A.w1; W.w1_sn = 1; W.w1_sk = WD;
     W.w2 = A.w2; W.w2_sn = 1; W.w2_sk = 3;
     W.b0 = A.b0; W.b1 = A.b1; W.b2 = A.b2;
-    k_render_mlp_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A, W);
+    PVDB_CHECK_ARG(A.img, "w_img scratch missing (tensor-core rgbnet)");
+    k_prep_fwd_image<<<32, 256, 0, st>>>(W, A.img);
+    PVDB_LAUNCH_CHECK();
+    k_render_mlp_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

@@ -47,7 +47,10 @@ __device__ __forceinline__ bool occ_test(const MarchParams& P, int i, int j, int
 }
 
 // Trilinear density at index-space (x,y,z): densityvdb.cu:101-125 arithmetic.
-__device__ __forceinline__ float density_at(const MarchParams& P, PvdbLeafCache& cache, float x, float y, float z) {
+// rec[q] (EMIT only) receives the record id leaf*512+voxel of corner q, -1 when the corner has no leaf: the k0 grid
+// shares the topology, so the rgbnet kernels reuse them instead of walking the tree again.
+template <bool WITH_REC>
+__device__ __forceinline__ float density_at(const MarchParams& P, PvdbLeafCache& cache, float x, float y, float z, int* rec) {
     PvdbTri tri;
     tri.set(x, y, z);
     float acc = 0.f;
@@ -56,6 +59,7 @@ __device__ __forceinline__ float density_at(const MarchParams& P, PvdbLeafCache&
         const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
         const int cx = tri.i + dx, cy = tri.j + dy, cz = tri.k + dz;
         const int leaf = cache.find(P.tree, cx, cy, cz);
+        if (WITH_REC) rec[q] = leaf >= 0 ? leaf * 512 + pvdb_leaf_off(cx, cy, cz) : -1;
         const float v = leaf >= 0 ? __ldg(P.den + (size_t)leaf * 512 + pvdb_leaf_off(cx, cy, cz)) : 0.f;
         acc = __fmaf_rn(tri.f(2, dz), __fmul_rn(tri.f(1, dy), __fmul_rn(tri.f(0, dx), v)), acc);
     }
@@ -72,6 +76,7 @@ struct MarchOut {
     int64_t cap_alpha, cap_keep;
     int32_t *s_ray, *s_step; float *s_xyz, *s_density, *s_alpha, *s_T, *s_weight;
     int32_t *k_sample, *k_ray; float* k_xyz;
+    int32_t* k_corner;   // [cap_keep][8] or null
     int32_t* counters;
 };
 
@@ -114,12 +119,13 @@ __global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const 
         if (mbits == 0) continue;
         n_mask += __popc(mbits);
         float x = 0, y = 0, z = 0, dens = 0, alpha = 0;
+        int rec[8];
         bool a_ok = false;
         if (in_mask) {
             x = pvdb_wld2idx(px, P.xyz_min[0], P.xyz_max[0], P.rm1[0]);
             y = pvdb_wld2idx(py, P.xyz_min[1], P.xyz_max[1], P.rm1[1]);
             z = pvdb_wld2idx(pz, P.xyz_min[2], P.xyz_max[2], P.rm1[2]);
-            dens = density_at(P, cache, x, y, z);
+            dens = density_at<MODE == 1>(P, cache, x, y, z, rec);
             float e;
             alpha = pvdb_raw2alpha(dens, P.act_shift, P.interval, e);
             a_ok = alpha > P.thres;
@@ -154,6 +160,11 @@ __global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const 
                 if (ik < O.cap_keep && ia < O.cap_alpha) {
                     O.k_sample[ik] = (int32_t)ia; O.k_ray[ik] = r;
                     O.k_xyz[ik * 3] = x; O.k_xyz[ik * 3 + 1] = y; O.k_xyz[ik * 3 + 2] = z;
+                    if (O.k_corner) {
+                        int4* kc = reinterpret_cast<int4*>(O.k_corner + ik * 8);
+                        kc[0] = make_int4(rec[0], rec[1], rec[2], rec[3]);
+                        kc[1] = make_int4(rec[4], rec[5], rec[6], rec[7]);
+                    }
                 }
             }
         }
@@ -543,7 +554,7 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     O.cap_alpha = b->cap_alpha; O.cap_keep = b->cap_keep;
     O.s_ray = b->s_ray; O.s_step = b->s_step; O.s_xyz = b->s_xyz; O.s_density = b->s_density; O.s_alpha = b->s_alpha;
     O.s_T = b->s_T; O.s_weight = b->s_weight;
-    O.k_sample = b->k_sample; O.k_ray = b->k_ray; O.k_xyz = b->k_xyz;
+    O.k_sample = b->k_sample; O.k_ray = b->k_ray; O.k_xyz = b->k_xyz; O.k_corner = b->k_corner;
     O.counters = b->counters;
     return 0;
 }
