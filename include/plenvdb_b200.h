@@ -200,12 +200,13 @@ typedef struct pvdb_train_bufs {
     int32_t *k_sample /* index into the alpha list */, *k_ray;
     float *k_xyz /*[.][3]*/, *k_feat /*[.][12]*/, *k_rgb /*[.][3] rgb, then dL/dlogit*/, *k_gw /*[.] dL/dweight*/;
     float *k_h0, *k_h1;                        /* post-ReLU activations kept for the backward: [.][128] row-major (fp32 path) or
-                                                * tile-transposed [tile][128 features][128 samples] (tensor-core path) */
-    float *k_x;                                /* [tile][40][128] rgbnet inputs (12 k0 + 27 PE + pad), tensor-core path */
-    float *k_dh0, *k_dh1;                      /* [tile][128][128] masked activation gradients, tensor-core backward */
+                                                * chunk-major [tile][8 chunks][128 features][16 samples] (tensor-core path) */
+    float *k_x;                                /* chunk-major [tile][8][40][16] rgbnet inputs (12 k0 + 27 PE + a ones row), tensor-core path */
+    float *k_dh0, *k_dh1;                      /* chunk-major [tile][8][128][16] masked activation gradients, tensor-core backward */
     uint32_t *k_mask;                          /* [tile][8][128] ReLU sign bits of h0 (words 0-3) and h1 (words 4-7) */
     int32_t *k_corner;                         /* [cap_keep][8] record id (leaf*512+voxel) of the 8 trilinear corners, -1 = none */
     void *net_img;                             /* >= 512 KiB scratch: tf32 hi/lo weight images of the tensor-core kernels */
+    float *net_partial;                        /* [148][22048] per-CTA weight-gradient partial sums (tensor-core backward) */
     /* touched-leaf bookkeeping, [n_leaf] each */
     int32_t *den_touched, *k0_touched, *den_touched_list, *k0_touched_list;
     int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0 */

@@ -404,7 +404,7 @@ int pvdb_rgbnet_backward_fp32(const pvdb_train_cfg* cfg, const pvdb_train_bufs* 
 }
 
 int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
+    if (cfg->use_tensor_cores) return pvdb_rgbnet_backward_tc(cfg, b, viewdirs, st);   // overwrites net_grad (partials + reduce)
     PVDB_CUDA(cudaMemsetAsync(b->net_grad, 0, PVDB_NET_N * sizeof(float), st));
-    if (cfg->use_tensor_cores) return pvdb_rgbnet_backward_tc(cfg, b, viewdirs, st);
     return pvdb_rgbnet_backward_fp32(cfg, b, viewdirs, st);
 }

@@ -204,7 +204,7 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
             float x[K0P];
 #pragma unroll
             for (int q = 0; q < K0P; ++q) x[q] = 0.f;
-            if (s < M) feat(s, x);
+            feat(s, s < M, x);
             float4* row = reinterpret_cast<float4*>(smem + SM_XBUF + b * XBUF_BYTES) + p * (XLD / 4);
 #pragma unroll
             for (int q = 0; q < K0P / 4; ++q) row[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
@@ -263,7 +263,7 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
                     tmem_st_wait();
                     tc_fence_before();   // (first chunk: also orders the previous tile's D1 reads before the new layer-1 MMAs)
                     mbar_arrive(bars + BAR_ARDY + 8 * (c >> 5));
-                    if (valid) act(s, 0, c, h);
+                    act(s, valid, 0, c, h);
                 }
             }
             TC_T(4);
@@ -286,7 +286,7 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
                     float h[32];
 #pragma unroll
                     for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]) + sb1[c + q], 0.f);
-                    if (valid) act(s, 1, c, h);
+                    act(s, valid, 1, c, h);
 #pragma unroll
                     for (int q = 0; q < 32; q += 4) {
                         const float4 a = *reinterpret_cast<const float4*>(sw2 + c + q);
@@ -340,7 +340,15 @@ struct TrainFwdArgs {
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
-    auto feat = [&](int64_t s, float* x) {
+    auto feat = [&](int64_t s, bool valid, float* x) {
+        if (!valid) {   // lanes past M in the last tile: zero input row in HBM (the weight-gradient pass reads whole tiles)
+            if (A.k_x) {
+                float* kx = A.k_x + act_off(s, 0, 40);
+#pragma unroll
+                for (int i = 0; i < 40; ++i) kx[i * 16] = 0.f;
+            }
+            return;
+        }
         // 12-channel trilinear sample, colorvdb.cu:81-111 arithmetic and corner order.  The eight record ids were found
         // by the march (same topology as the density grid), so all 24 16-byte loads are independent and in flight at
         // once; a missing corner contributes fma(sc, 0, x) = x, bit-identical to skipping it.
@@ -371,30 +379,32 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
         float4* kf = reinterpret_cast<float4*>(A.k_feat + s * 12);
         kf[0] = make_float4(x[0], x[1], x[2], x[3]); kf[1] = make_float4(x[4], x[5], x[6], x[7]); kf[2] = make_float4(x[8], x[9], x[10], x[11]);
         view_embed_tc(A.viewdirs + (size_t)A.k_ray[s] * 3, x + 12);
-        if (A.k_x) {   // input row for the weight-gradient pass, tile-transposed [tile][40][128]: warp-coalesced stores
-            float* kx = A.k_x + (s >> 7) * (40 * 128) + (s & 127);
+        if (A.k_x) {   // input row for the weight-gradient pass, chunk-major (act_off);
+                       // row 39 (the K padding) carries the constant 1 that turns the bias gradient into a GEMM column
+            float* kx = A.k_x + act_off(s, 0, 40);
 #pragma unroll
-            for (int i = 0; i < 40; ++i) kx[i * 128] = x[i];
+            for (int i = 0; i < 39; ++i) kx[i * 16] = x[i];
+            kx[39 * 16] = 1.0f;
         }
     };
     auto out = [&](int64_t s, const float* raw) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) A.k_rgb[s * 3 + j] = 1.0f / (1.0f + expf(-raw[j]));
     };
-    auto act = [&](int64_t s, int layer, int c, const float* h) {
+    auto act = [&](int64_t s, bool valid, int layer, int c, const float* h) {
         if (A.k_mask) {   // ReLU sign bits for the backward: bit i of word (layer*4 + c/32) = h[c+i] > 0
             uint32_t m = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m |= (h[i] > 0.f ? 1u : 0u) << i;
+            for (int i = 0; i < 32; ++i) m |= (valid && h[i] > 0.f ? 1u : 0u) << i;
             A.k_mask[(s >> 7) * (8 * 128) + (layer * 4 + (c >> 5)) * 128 + (s & 127)] = m;   // [tile][8][128]
         }
         float* dst = layer == 0 ? A.k_h0 : A.k_h1;
         if (!dst) return;
-        // tile-transposed [tile][128 features][128 samples]: lane l writes word l of a 128-byte line -> one wavefront per
-        // store instead of 32, and the weight-gradient pass reads 4 consecutive samples of a feature as one LDG.128
-        float* g = dst + (s >> 7) * (WD * 128) + (size_t)c * 128 + (s & 127);
+        // chunk-major (act_off): a warp's store covers two full 64-byte runs, and the weight-gradient pass streams each
+        // 16-sample chunk as one contiguous block
+        float* g = dst + act_off(s, c, WD);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) g[i * 128] = h[i];
+        for (int i = 0; i < 32; ++i) g[i * 16] = valid ? h[i] : 0.f;   // zero rows past M: the weight-gradient pass reads whole tiles
     };
     mlp_tiles(smem, A.img, M, feat, out, act);
 }
@@ -403,7 +413,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int64_t M = min((int64_t)A.counters[0], A.cap);
-    auto feat = [&](int64_t s, float* x) {
+    auto feat = [&](int64_t s, bool valid, float* x) {
+        if (!valid) return;
         const float4* f = reinterpret_cast<const float4*>(A.s_feat + s * 12);
 #pragma unroll
         for (int c4 = 0; c4 < 3; ++c4) {
@@ -427,7 +438,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs 
 #pragma unroll
         for (int j = 0; j < 3; ++j) A.s_rgb[s * 3 + j] = w / (1 + expf(-raw[j]));   // final_render (:115-117)
     };
-    auto act = [&](int64_t, int, int, const float*) {};
+    auto act = [&](int64_t, bool, int, int, const float*) {};
     mlp_tiles(smem, A.img, M, feat, out, act);
 }
 

@@ -14,6 +14,9 @@
 //                           flushed once with red.global.add.
 // Reference semantics: autograd through nn.Sequential(Linear, ReLU, Linear, ReLU, Linear) (dvgo.py:99-107) and
 // QueryVerticalInVDB.backward -> color_backward (grid.py:53-60, colorvdb.cu:130-175).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "rgbnet.cuh"
 #include "tc_ptx.cuh"
@@ -131,10 +134,10 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
                 const float v = fmaf(g2, sW2[2 * WD + j], fmaf(g1, sW2[WD + j], g0 * sW2[j]));
                 d[i] = (m1w[cc] >> i) & 1u ? v : 0.f;
             }
-            if (valid) {   // tile-transposed [tile][128][128], warp-coalesced
-                float* o = A.k_dh1 + (s >> 7) * (WD * 128) + (size_t)c * 128 + (s & 127);
+            {   // tile-transposed [tile][128][128], warp-coalesced; lanes past M write the zeros the weight-gradient pass relies on
+                float* o = A.k_dh1 + act_off(s, c, WD);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i * 128] = d[i];
+                for (int i = 0; i < 32; ++i) o[i * 16] = d[i];
             }
             store_a_row32(lane_addr, c, d);
         }
@@ -154,10 +157,10 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
             float d[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) d[i] = (m0w[cc] >> i) & 1u ? __uint_as_float(r[i]) : 0.f;
-            if (valid) {
-                float* o = A.k_dh0 + (s >> 7) * (WD * 128) + (size_t)c * 128 + (s & 127);
+            {
+                float* o = A.k_dh0 + act_off(s, c, WD);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i * 128] = d[i];
+                for (int i = 0; i < 32; ++i) o[i * 16] = d[i];
             }
             store_a_row32(lane_addr, c, d);
         }
@@ -201,199 +204,380 @@ __global__ void __launch_bounds__(TM, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------- B2
-// Both operands are transposed activations (contraction over samples).  MN-major tf32 operands only exist in the
-// 128B_BASE32B swizzled layout (CUTLASS sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available
-// smem layout"), so the tiles are transposed while they are staged instead: thread t owns FEATURE t, reads it for 4
-// consecutive samples (each read is a coalesced 128-byte row segment across the warp) and writes one 16-byte
-// K-major core-matrix row -> the same canonical no-swizzle K-major layout the forward uses, conflict free.
+// Weight gradients: contraction over SAMPLES, so both operands of every GEMM are activations transposed.
+//   dW1[j][i] = sum_s dH1[s][j] H0[s][i]   (M = 128, N = 128 + bias column, tcgen05)
+//   dW0[j][k] = sum_s dH0[s][j] X[s][k]    (M = 128, N = 39 + bias column, tcgen05)
+//   dW2[c][i] = sum_s G[s][c]  H1[s][i]    (3 x 128: CUDA cores, an N = 16 MMA costs as much tensor time as N = 128)
+// MN-major tf32 operands only exist in the 128B_BASE32B swizzled layout (CUTLASS sm100_common.inl), so the operands are
+// K-major instead: the activations live in HBM chunk-major [chunk of 16 samples][feature][16 samples] (act_off), i.e. a
+// chunk of one tensor is a row-major [features][64 bytes] block — exactly the K-major SWIZZLE_64B UMMA layout (8-row x
+// 64-byte atoms) up to the XOR of the 16-byte column with row bits, which TMA applies on the way in.
+// One elected thread issues five TMA tensor loads + one bulk copy per chunk; nothing else touches the load path.
+// Measured on B200 (scratch/tf32_probe.cu): kind::tf32 TRUNCATES the low 13 mantissa bits, so the raw fp32 tile is its own
+// "hi" operand and only lo = x - trunc(x) has to be computed (elementwise, layout-agnostic).
+//
+// Warp-specialised streaming pipeline, 3 stages of 16 samples:
+//   warps 0-7   converters: wait full[st]; lo tiles; warps 4-7 also dW2 / db2 partial sums on the CUDA cores; arrive conv[st]
+//   warp 8      loader: wait free[st]; expect_tx + TMA loads onto full[st]   (cp.async fallback: all 32 lanes copy)
+//   warp 9      issuer: wait conv[st]; 12 MMAs (2 k-steps x 3 passes x 2 GEMMs); tcgen05.commit -> free[st]
+// Accumulators stay in TMEM for the CTA's lifetime and are flushed once with red.global.add.
 constexpr int KC = 16;                                   // samples per chunk = 2 k-steps of 8
-constexpr int N1 = 144, N0 = 48, N2 = 16;                // padded N of the three GEMMs (128+1 bias, 39+1 bias, 3)
-constexpr int OPB(int mn) { return mn * KC * 4; }        // bytes of one operand tile [mn][KC]
-constexpr int S_A1 = 0;                                  // dH1^T [128][KC] hi, lo
-constexpr int S_B1 = S_A1 + 2 * OPB(WD);                 // [H0^T ; 1 ; 0..] [144][KC] hi, lo
-constexpr int S_A0 = S_B1 + 2 * OPB(N1);                 // dH0^T [128][KC]
-constexpr int S_B0 = S_A0 + 2 * OPB(WD);                 // [X^T(39) ; 1 ; 0..] [48][KC]
-constexpr int S_A2 = S_B0 + 2 * OPB(N0);                 // H1^T [128][KC]
-constexpr int S_B2 = S_A2 + 2 * OPB(WD);                 // G^T [16][KC]
-constexpr int STAGE = S_B2 + 2 * OPB(N2);
-constexpr int B2_BAR = 2 * STAGE;                        // two mbarriers + tmem slot
-constexpr int B2_TOTAL = B2_BAR + 32;
-constexpr uint32_t ACC1 = 0, ACC0 = 144, ACC2 = 192;     // TMEM columns of the three accumulators (256 allocated)
+constexpr int N1 = 144, N0 = 48;                         // padded N (128 + bias row, 39 + bias row)
+constexpr int ROWB = KC * 4;                             // 64-byte rows
+constexpr int S_A1 = 0;                                  // dH1^T [128][KC] raw (= hi)
+constexpr int S_B1 = S_A1 + WD * ROWB;                   // [H0^T ; 1 ; 0..] [144][KC]
+constexpr int S_A0 = S_B1 + N1 * ROWB;                   // dH0^T [128][KC]
+constexpr int S_B0 = S_A0 + WD * ROWB;                   // [X^T(39) ; 1 ; 0..] [48][KC]  (k_x row 39 holds the ones)
+constexpr int S_H1 = S_B0 + N0 * ROWB;                   // H1^T [128][KC] raw, CUDA-core dW2
+constexpr int S_G = S_H1 + WD * ROWB;                    // logit gradients [KC][3]
+constexpr int STAGE = S_G + 512;                         // one raw stage (what TMA fills)
+constexpr int NSTAGE = 4;
+// lo tiles (same order / offsets as the first four raw tiles) only live between the converters and the MMAs of one chunk:
+// two sets, alternating by chunk parity, instead of one per stage -> a fourth stage of loads in flight fits
+constexpr int LO_A1 = 0, LO_B1 = LO_A1 + WD * ROWB, LO_A0 = LO_B1 + N1 * ROWB, LO_B0 = LO_A0 + WD * ROWB;
+constexpr int LOSET = LO_B0 + N0 * ROWB;
+constexpr int S_LOSETS = NSTAGE * STAGE;
+constexpr int B2_BAR = S_LOSETS + 2 * LOSET;             // full[4], conv[4], free[4] mbarriers + tmem slot
+constexpr int BAR_FULL2 = 0, BAR_CONV2 = 32, BAR_FREE2 = 64, TMEM_SLOT2 = 96;
+constexpr int B2_TOTAL = B2_BAR + 112;
+constexpr uint32_t ACC1 = 0, ACC0 = 144;                 // TMEM columns of the two accumulators (256 allocated)
+constexpr uint32_t TX_BYTES = 4 * WD * ROWB + 40 * ROWB + KC * 3 * 4;   // bytes landing per stage
+static_assert(S_B1 % 512 == 0 && S_A0 % 512 == 0 && S_B0 % 512 == 0 && S_H1 % 512 == 0 && LO_B1 % 512 == 0 &&
+              LO_A0 % 512 == 0 && LO_B0 % 512 == 0 && STAGE % 512 == 0 && LOSET % 512 == 0, "SW64 tiles must start on the 512-byte swizzle period");
+static_assert(B2_TOTAL <= 227 * 1024, "wgrad smem");
 
-// 4 consecutive samples (k4*4 .. +3) of feature `mn` -> one 16-byte row of a K-major core matrix, hi and lo tiles
-__device__ __forceinline__ void put_k4(unsigned char* base, int off_hi, int bytes_tile, int mn, int k4, float4 v) {
-    uint32_t h[4], l[4];
-    split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]); split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
-    const int o = canon_off(mn, k4 * 4, KC);
-    *reinterpret_cast<uint4*>(base + off_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(base + off_hi + bytes_tile + o) = make_uint4(l[0], l[1], l[2], l[3]);
+// byte offset of (row f, 16-byte column k4) inside a K-major SWIZZLE_64B tile with 64-byte rows
+__device__ __forceinline__ uint32_t sw64_off(int f, int k4) { return (uint32_t)(f * ROWB + ((k4 ^ ((f >> 1) & 3)) << 4)); }
+// UMMA shared-memory descriptor, K-major SWIZZLE_64B: LBO = 1 (unused), SBO = 512 B between 8-row groups, layout type 4
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
-// feature `f` of 4 consecutive samples s0..s0+3 (s0 % 4 == 0) of a tile-transposed array [tile][nf][128]: one LDG.128.
-// Samples past M read as zero (their slots may hold stale data from an earlier, larger batch).
-__device__ __forceinline__ float4 col4(const float* __restrict__ a, int64_t s0, int64_t M, int nf, int f) {
-    if (s0 >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 v = __ldg(reinterpret_cast<const float4*>(a + (s0 >> 7) * (nf * 128) + (size_t)f * 128 + (s0 & 127)));
-    if (s0 + 1 >= M) v.y = 0.f;
-    if (s0 + 2 >= M) v.z = 0.f;
-    if (s0 + 3 >= M) v.w = 0.f;
-    return v;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-// same for the row-major [.][3] logit gradients
-__device__ __forceinline__ float4 col4_rows(const float* __restrict__ a, int64_t s0, int64_t M, int ld, int f) {
-    float4 v;
-    v.x = s0 + 0 < M ? __ldg(a + (s0 + 0) * ld + f) : 0.f;
-    v.y = s0 + 1 < M ? __ldg(a + (s0 + 1) * ld + f) : 0.f;
-    v.z = s0 + 2 < M ? __ldg(a + (s0 + 2) * ld + f) : 0.f;
-    v.w = s0 + 3 < M ? __ldg(a + (s0 + 3) * ld + f) : 0.f;
-    return v;
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// TMA tensor tile load (3-D map: sample-in-chunk, feature, chunk), completion in bytes on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 
 struct BwdWgradArgs {
     const float *k_dh1, *k_h0, *k_dh0, *k_x, *k_h1, *k_glogit;
-    float* net_grad;
+    float* partial;   // [gridDim.x][PART_LD] per-CTA weight-gradient partial sums (net_grad layout)
     const int32_t* counters; int64_t cap_keep;
+    int use_tma;
 };
+constexpr int PART_LD = (PVDB_NET_N + 31) & ~31;
+struct WgradMaps { CUtensorMap dh1, h0, dh0, h1, x; };
 
-constexpr int B2_THREADS = 512;   // 16 warps stage (memory-latency bound); warps 0-3 own the TMEM lanes for the flush
-__global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradArgs A) {
-    extern __shared__ __align__(128) unsigned char smem[];
+#ifdef PVDB_TC_TIMING
+__device__ long long g_wg_t[PVDB_SMS][16];
+#define WG_T(i, v) g_wg_t[blockIdx.x][i] = (v)
+#else
+#define WG_T(i, v) do { } while (0)
+#endif
+
+constexpr int B2_THREADS = 320;
+constexpr int B2_CONV = 256;
+__global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradArgs A, const __grid_constant__ WgradMaps maps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    // feature row and 4-sample group this thread stages.  Per warp: 8 features x 4 groups; the 8 threads of a quarter warp
-    // take 8 different features (conflict-free 16-byte shared stores), the 4 groups of a feature read 64 contiguous bytes.
-    const int f = (tid >> 5) * 8 + (tid & 7), k4 = (tid >> 3) & 3;
+    const long long t_start = clock64();
+    long long t_wait = 0, t_mma = 0, t_lo = 0;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar0 = sbase + B2_BAR, bar1 = sbase + B2_BAR + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B2_BAR + 16);
+    const uint32_t bars = sbase + B2_BAR;
+    const uint32_t bar_full = bars + BAR_FULL2, bar_conv = bars + BAR_CONV2, bar_free = bars + BAR_FREE2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B2_BAR + TMEM_SLOT2);
     const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
     const int64_t n_chunks = (M + KC - 1) / KC;
-    // zero both stages once: padding rows (bias/pad columns of B, unused n) must stay zero
-    for (int e = tid; e < 2 * STAGE / 16; e += B2_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
-    if (warp == 0) tmem_alloc(sbase + B2_BAR + 16, 256);
+    // contiguous chunk range of this CTA (sequential HBM addresses per array)
+    const int64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const int64_t ch_lo = min(n_chunks, (int64_t)blockIdx.x * per), ch_hi = min(n_chunks, ch_lo + per);
+    const int n_it = (int)(ch_hi - ch_lo);
+    // constant parts of every stage: zero everything once, then the bias "ones" row of B1 (k = all samples; rows of A are
+    // zero for samples past M, so the padding contributes nothing)
+    for (int e = tid; e < B2_BAR / 16; e += B2_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (tid < NSTAGE * KC) {
+        const int st = tid / KC, k = tid % KC;
+        *reinterpret_cast<float*>(smem + st * STAGE + S_B1 + 128 * ROWB + k * 4) = 1.0f;
+    }
+    if (tid == 0)
+        for (int st = 0; st < NSTAGE; ++st) {
+            mbar_init(bar_full + 8 * st, A.use_tma ? 1 : 32);
+            mbar_init(bar_conv + 8 * st, B2_CONV);
+            mbar_init(bar_free + 8 * st, 1);
+        }
+    if (warp == 0) tmem_alloc(sbase + B2_BAR + TMEM_SLOT2, 256);
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    uint32_t par[2] = {0, 0};
-    int issued[2] = {0, 0};
-    float gsum = 0.f;
-    int it = 0;
-    struct Chunk { float4 a1, b1, a0, a2, xg; };
-    auto load_chunk = [&](int64_t ch) {
-        Chunk c;
-        const int64_t s0 = ch * KC + k4 * 4;
-        const bool live = ch < n_chunks;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        c.a1 = live ? col4(A.k_dh1, s0, M, WD, f) : z;
-        c.b1 = live ? col4(A.k_h0, s0, M, WD, f) : z;
-        c.a0 = live ? col4(A.k_dh0, s0, M, WD, f) : z;
-        c.a2 = live ? col4(A.k_h1, s0, M, WD, f) : z;
-        c.xg = z;
-        if (live && f < 39) c.xg = col4(A.k_x, s0, M, 40, f);
-        else if (live && f >= 64 && f < 67) c.xg = col4_rows(A.k_glogit, s0, M, 3, f - 64);
-        return c;
-    };
-    for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++it) {
-        const int st = it & 1;
-        unsigned char* sb = smem + st * STAGE;
-        const Chunk cur = load_chunk(ch);
-        if (issued[st]) { mbar_wait(st ? bar1 : bar0, par[st]); par[st] ^= 1; }   // MMAs that read this stage are done
-        // ---- stage the six operand tiles, transposed: thread = (feature, 4 samples) -> one 16-byte K-major row
-        {
-            const int64_t s0 = ch * KC + k4 * 4;
-            put_k4(sb, S_A1, OPB(WD), f, k4, cur.a1);
-            put_k4(sb, S_B1, OPB(N1), f, k4, cur.b1);
-            put_k4(sb, S_A0, OPB(WD), f, k4, cur.a0);
-            put_k4(sb, S_A2, OPB(WD), f, k4, cur.a2);
-            const float4 ones = make_float4(s0 < M ? 1.f : 0.f, s0 + 1 < M ? 1.f : 0.f, s0 + 2 < M ? 1.f : 0.f, s0 + 3 < M ? 1.f : 0.f);
-            if (f < 39) put_k4(sb, S_B0, OPB(N0), f, k4, cur.xg);
-            else if (f == 39) put_k4(sb, S_B0, OPB(N0), 39, k4, ones);             // bias row of dW0
-            else if (f == 40) put_k4(sb, S_B1, OPB(N1), 128, k4, ones);            // bias row of dW1
-            else if (f >= 64 && f < 67) {                                           // G^T rows; db2 on the side
-                gsum += (cur.xg.x + cur.xg.y) + (cur.xg.z + cur.xg.w);
-                put_k4(sb, S_B2, OPB(N2), f - 64, k4, cur.xg);
-            }
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t base = sbase + st * STAGE;
-            const uint32_t acc0 = it > 0 ? 1u : 0u;
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                const int offA = g == 0 ? S_A1 : g == 1 ? S_A0 : S_A2, offB = g == 0 ? S_B1 : g == 1 ? S_B0 : S_B2;
-                const int nB = g == 0 ? N1 : g == 1 ? N0 : N2;
-                const uint32_t dcol = tmem + (g == 0 ? ACC1 : g == 1 ? ACC0 : ACC2);
-                const uint32_t idesc = make_idesc(nB);
-                const uint64_t ahi = make_desc(base + offA, KC), alo = make_desc(base + offA + OPB(WD), KC);
-                const uint64_t bhi = make_desc(base + offB, KC), blo = make_desc(base + offB + OPB(nB), KC);
+    float w2acc[3] = {0.f, 0.f, 0.f};
+    float gs[3] = {0.f, 0.f, 0.f};
+    if (tid == 0) { WG_T(0, t_start); WG_T(1, clock64()); WG_T(2, (long long)n_it); }
+
+    if (warp == 9) {
+        // ---------------- issuer
+        if (tid == 288) {
+            const uint32_t id1 = make_idesc(N1), id0 = make_idesc(N0);
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it % NSTAGE;
+                { const long long t0 = clock64(); mbar_wait(bar_conv + 8 * st, (it / NSTAGE) & 1); t_wait += clock64() - t0; }
+                tc_fence_after();
+                const uint32_t base = sbase + st * STAGE, lob = sbase + S_LOSETS + (it & 1) * LOSET;
+                const uint32_t acc = it > 0 ? 1u : 0u;
+                const uint64_t a1h = make_desc_sw64(base + S_A1), a1l = make_desc_sw64(lob + LO_A1);
+                const uint64_t b1h = make_desc_sw64(base + S_B1), b1l = make_desc_sw64(lob + LO_B1);
+                const uint64_t a0h = make_desc_sw64(base + S_A0), a0l = make_desc_sw64(lob + LO_A0);
+                const uint64_t b0h = make_desc_sw64(base + S_B0), b0l = make_desc_sw64(lob + LO_B0);
 #pragma unroll
                 for (int ks = 0; ks < KC / 8; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 256) >> 4;
-                    umma_tf32_ss(dcol, ahi + adv, bhi + adv, idesc, (ks == 0) ? acc0 : 1u);
-                    umma_tf32_ss(dcol, alo + adv, bhi + adv, idesc, 1u);
-                    umma_tf32_ss(dcol, ahi + adv, blo + adv, idesc, 1u);
+                    const uint64_t adv = (uint64_t)(ks * 32) >> 4;   // 8 tf32 = 32 bytes along the swizzled row
+                    umma_tf32_ss(tmem + ACC1, a1h + adv, b1h + adv, id1, ks == 0 ? acc : 1u);
+                    umma_tf32_ss(tmem + ACC1, a1l + adv, b1h + adv, id1, 1u);
+                    umma_tf32_ss(tmem + ACC1, a1h + adv, b1l + adv, id1, 1u);
+                    umma_tf32_ss(tmem + ACC0, a0h + adv, b0h + adv, id0, ks == 0 ? acc : 1u);
+                    umma_tf32_ss(tmem + ACC0, a0l + adv, b0h + adv, id0, 1u);
+                    umma_tf32_ss(tmem + ACC0, a0h + adv, b0l + adv, id0, 1u);
+                }
+                umma_commit(bar_free + 8 * st);
+            }
+            WG_T(3, t_wait); WG_T(4, clock64()); WG_T(11, t_mma);
+        }
+    } else if (warp == 8) {
+        // ---------------- loader
+        const int t = tid - B2_CONV;
+        for (int it = 0; it < n_it; ++it) {
+            const int st = it % NSTAGE;
+            if (it >= NSTAGE) { const long long t0 = clock64(); mbar_wait(bar_free + 8 * st, ((it / NSTAGE) - 1) & 1); t_wait += clock64() - t0; }
+            const int64_t ch = ch_lo + it;
+            const uint32_t base = sbase + st * STAGE;
+            const uint32_t full = bar_full + 8 * st;
+            if (A.use_tma) {
+                if (t == 0) {
+                    mbar_expect_tx(full, TX_BYTES);
+                    tma_load_3d(base + S_A1, &maps.dh1, 0, 0, (int)ch, full);
+                    tma_load_3d(base + S_B1, &maps.h0, 0, 0, (int)ch, full);
+                    tma_load_3d(base + S_A0, &maps.dh0, 0, 0, (int)ch, full);
+                    tma_load_3d(base + S_H1, &maps.h1, 0, 0, (int)ch, full);
+                    tma_load_3d(base + S_B0, &maps.x, 0, 0, (int)ch, full);
+                    bulk_g2s(base + S_G, A.k_glogit + ch * (KC * 3), KC * 3 * 4, full);
+                }
+            } else {
+                // fallback: 16-byte async copies straight into the swizzled positions (chunk `ch` of each tensor is contiguous)
+                const float* g_dh1 = A.k_dh1 + ch * (WD * KC);
+                const float* g_h0 = A.k_h0 + ch * (WD * KC);
+                const float* g_dh0 = A.k_dh0 + ch * (WD * KC);
+                const float* g_h1 = A.k_h1 + ch * (WD * KC);
+                const float* g_x = A.k_x + ch * (40 * KC);
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int idx = t + 32 * i, f = idx >> 2, k4 = idx & 3;
+                    const uint32_t o = sw64_off(f, k4);
+                    const int go = f * KC + k4 * 4;
+                    cp_async16(base + S_A1 + o, g_dh1 + go);
+                    cp_async16(base + S_B1 + o, g_h0 + go);
+                    cp_async16(base + S_A0 + o, g_dh0 + go);
+                    cp_async16(base + S_H1 + o, g_h1 + go);
+                }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const int idx = t + 32 * i, f = idx >> 2, k4 = idx & 3;
+                    cp_async16(base + S_B0 + sw64_off(f, k4), g_x + f * KC + k4 * 4);
+                }
+                if (t < 12) cp_async16(base + S_G + t * 16, A.k_glogit + ch * (KC * 3) + t * 4);
+                cp_async_arrive(full);
+            }
+        }
+        if (t == 0) { WG_T(5, t_wait); WG_T(6, clock64()); }
+    } else {
+        // ---------------- converters: lo = x - trunc(x) for the four MMA operand tiles; dW2 / db2 on the CUDA cores
+        const int f2 = tid - 128;                                  // warps 4-7: the dW2 feature of this thread
+        for (int it = 0; it < n_it; ++it) {
+            const int st = it % NSTAGE;
+            { const long long t0 = clock64(); mbar_wait(bar_full + 8 * st, (it / NSTAGE) & 1); t_wait += clock64() - t0; }
+            unsigned char* sb = smem + st * STAGE;
+            unsigned char* lo = smem + S_LOSETS + (it & 1) * LOSET;
+            // this lo set was last read by the MMAs of chunk it-2
+            if (it >= 2) { const long long t0 = clock64(); mbar_wait(bar_free + 8 * ((it - 2) % NSTAGE), ((it - 2) / NSTAGE) & 1); t_lo += clock64() - t0; }
+            // 1696 16-byte items: A1 512, B1 512 (rows 0..127), A0 512, B0 160 (rows 0..39).  All loads first (the two converter
+            // warps of a scheduler cannot hide shared-memory latency by themselves), then lo = x - trunc(x), then the stores.
+            // The raw tiles are the hi operands as they are: async-copied data tracked by the mbarrier needs no proxy fence.
+            float4 v[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const int e = tid + q * B2_CONV;
+                if (e < 1696) v[q] = *reinterpret_cast<const float4*>(sb + e * 16 + (e >= 1024 ? 1024 : 0));
+            }
+            float4 h[4], g4[12];
+            if (tid >= 128) {   // H1 row of feature f2 (h[k4] = samples 4*k4 .. 4*k4+3) and the whole G tile (broadcast reads)
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) h[k4] = *reinterpret_cast<const float4*>(sb + S_H1 + sw64_off(f2, k4));
+#pragma unroll
+                for (int q = 0; q < 12; ++q) g4[q] = *reinterpret_cast<const float4*>(sb + S_G + q * 16);
+            }
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const int e = tid + q * B2_CONV;
+                if (e < 1696) {
+                    float4 l;
+                    l.x = v[q].x - __uint_as_float(__float_as_uint(v[q].x) & 0xffffe000u);
+                    l.y = v[q].y - __uint_as_float(__float_as_uint(v[q].y) & 0xffffe000u);
+                    l.z = v[q].z - __uint_as_float(__float_as_uint(v[q].z) & 0xffffe000u);
+                    l.w = v[q].w - __uint_as_float(__float_as_uint(v[q].w) & 0xffffe000u);
+                    *reinterpret_cast<float4*>(lo + e * 16 + (e >= 1024 ? 1024 : 0)) = l;
                 }
             }
-            umma_commit(st ? bar1 : bar0);
+            if (tid >= 128) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    // samples 4*k4 .. 4*k4+3 occupy floats 12*k4 .. 12*k4+11 of the [16][3] gradient tile = g4[3*k4 .. 3*k4+2]
+                    const float4 ga = g4[3 * k4], gb = g4[3 * k4 + 1], gc = g4[3 * k4 + 2];
+                    const float4 hv = h[k4];
+                    w2acc[0] = fmaf(ga.x, hv.x, w2acc[0]); w2acc[1] = fmaf(ga.y, hv.x, w2acc[1]); w2acc[2] = fmaf(ga.z, hv.x, w2acc[2]);
+                    w2acc[0] = fmaf(ga.w, hv.y, w2acc[0]); w2acc[1] = fmaf(gb.x, hv.y, w2acc[1]); w2acc[2] = fmaf(gb.y, hv.y, w2acc[2]);
+                    w2acc[0] = fmaf(gb.z, hv.z, w2acc[0]); w2acc[1] = fmaf(gb.w, hv.z, w2acc[1]); w2acc[2] = fmaf(gc.x, hv.z, w2acc[2]);
+                    w2acc[0] = fmaf(gc.y, hv.w, w2acc[0]); w2acc[1] = fmaf(gc.z, hv.w, w2acc[1]); w2acc[2] = fmaf(gc.w, hv.w, w2acc[2]);
+                }
+                if (tid == 128) {   // db2: sum of the logit gradients of the valid samples
+                    const int64_t s0 = (ch_lo + it) * KC;
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) {
+                        const float gq[4] = {g4[q].x, g4[q].y, g4[q].z, g4[q].w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = q * 4 + u;          // float e of the tile = (sample e / 3, channel e % 3)
+                            if (s0 + e / 3 < M) gs[e % 3] += gq[u];
+                        }
+                    }
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(bar_conv + 8 * st);
         }
-        issued[st] = 1;
+        if (tid == 0) { WG_T(7, t_wait); WG_T(8, clock64()); WG_T(12, t_lo); }
     }
-    // ---- drain and flush the accumulators
-    for (int st = 0; st < 2; ++st)
-        if (issued[st]) { mbar_wait(st ? bar1 : bar0, par[st]); par[st] ^= 1; }
-    tc_fence_after();
-    if (it > 0 && f >= 64 && f < 67) red_add(A.net_grad + PVDB_NET_OFF_B2 + (f - 64), gsum);
-    if (it > 0 && tid < TM) {
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        float* G = A.net_grad;
-        const int j = tid;   // accumulator row
-        // dW1[j][0..128) and db1[j] (column 128)
+    // ---- drain and flush: each CTA stores its partial sums (plain stores, net_grad layout); k_wgrad_reduce adds the
+    // gridDim.x partials.  148 CTAs x 22 k red.global.add on the same addresses cost ~16 us; this costs ~1 + 3.
+    __syncthreads();
+    if (tid == 0) WG_T(9, clock64());
+    float* P = A.partial + (size_t)blockIdx.x * PART_LD;
+    if (n_it == 0) {
+        for (int e = tid; e < PART_LD; e += B2_THREADS) P[e] = 0.f;
+    } else {
+        if (tid < B2_CONV) {
+            // all MMAs are complete once the last commit of every stage in use has fired
+            for (int st = 0; st < NSTAGE && st < n_it; ++st) {
+                const int last_it = ((n_it - 1 - st) / NSTAGE) * NSTAGE + st;
+                mbar_wait(bar_free + 8 * st, (last_it / NSTAGE) & 1);
+            }
+            tc_fence_after();
+            if (tid >= 128) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) P[PVDB_NET_OFF_W2 + c * WD + (tid - 128)] = w2acc[c];
+            }
+            if (tid == 128) { P[PVDB_NET_OFF_B2] = gs[0]; P[PVDB_NET_OFF_B2 + 1] = gs[1]; P[PVDB_NET_OFF_B2 + 2] = gs[2]; }
+        }
+        if (tid < TM) {
+            const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+            const int j = tid;   // accumulator row
+            // dW1[j][0..128) and db1[j] (column 128)
 #pragma unroll 1
-        for (int c = 0; c < WD; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(lane_addr + ACC1 + c, r);
-            tmem_ld_wait();
+            for (int c = 0; c < WD; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + ACC1 + c, r);
+                tmem_ld_wait();
+                float4* dst = reinterpret_cast<float4*>(P + PVDB_NET_OFF_W1 + j * WD + c);   // OFF_W1 = 5120: 16-byte aligned rows
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-                red_add4(G + PVDB_NET_OFF_W1 + j * WD + c + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                         __uint_as_float(r[i + 3]));
-        }
-        {
-            uint32_t r[8];
-            tmem_ld8(lane_addr + ACC1 + 128, r);
-            tmem_ld_wait();
-            red_add(G + PVDB_NET_OFF_B1 + j, __uint_as_float(r[0]));
-        }
-        // dW0[j][0..39) and db0[j] (column 39)
-        {
-            uint32_t r[32];
-            tmem_ld32(lane_addr + ACC0, r);
-            tmem_ld_wait();
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            }
+            {
+                uint32_t r[8];
+                tmem_ld8(lane_addr + ACC1 + 128, r);
+                tmem_ld_wait();
+                P[PVDB_NET_OFF_B1 + j] = __uint_as_float(r[0]);
+            }
+            // dW0[j][0..39) and db0[j] (column 39)
+            {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + ACC0, r);
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) red_add(G + PVDB_NET_OFF_W0 + j * PVDB_NET_DIN + i, __uint_as_float(r[i]));
-            uint32_t q[8];
-            tmem_ld8(lane_addr + ACC0 + 32, q);
-            tmem_ld_wait();
+                for (int i = 0; i < 32; ++i) P[PVDB_NET_OFF_W0 + j * PVDB_NET_DIN + i] = __uint_as_float(r[i]);
+                uint32_t q[8];
+                tmem_ld8(lane_addr + ACC0 + 32, q);
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 7; ++i) red_add(G + PVDB_NET_OFF_W0 + j * PVDB_NET_DIN + 32 + i, __uint_as_float(q[i]));
-            red_add(G + PVDB_NET_OFF_B0 + j, __uint_as_float(q[7]));
+                for (int i = 0; i < 7; ++i) P[PVDB_NET_OFF_W0 + j * PVDB_NET_DIN + 32 + i] = __uint_as_float(q[i]);
+                P[PVDB_NET_OFF_B0 + j] = __uint_as_float(q[7]);
+            }
         }
-        // dW2[c][i = j] (accumulator rows are i, columns c)
-        {
-            uint32_t r[8];
-            tmem_ld8(lane_addr + ACC2, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 3; ++c) red_add(G + PVDB_NET_OFF_W2 + c * WD + j, __uint_as_float(r[c]));
-        }
-
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) WG_T(10, clock64());
     if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// net_grad[e] = sum over the CTAs' partials.  64 elements x 4 partial groups per CTA; coalesced across elements.
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad) {
+    __shared__ float red[4][64];
+    const int e = blockIdx.x * 64 + (threadIdx.x & 63), g = threadIdx.x >> 6;
+    float s = 0.f;
+    if (e < PVDB_NET_N) {
+        float a[8];
+        int c = g;
+        for (; c + 28 < n_part; c += 32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = __ldcg(partial + (size_t)(c + 4 * u) * PART_LD + e);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += a[u];
+        }
+        for (; c < n_part; c += 4) s += __ldcg(partial + (size_t)c * PART_LD + e);
+    }
+    red[g][threadIdx.x & 63] = s;
+    __syncthreads();
+    if (g == 0 && e < PVDB_NET_N) net_grad[e] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+#ifdef PVDB_TC_TIMING
+}  // namespace
+extern "C" int pvdb_debug_wgrad_timing(long long* out) {
+    PVDB_CUDA(cudaMemcpyFromSymbol(out, g_wg_t, sizeof(long long) * PVDB_SMS * 16));
+    return PVDB_OK;
+}
+namespace {
+#endif
+
+// Tensor map of one chunk-major activation tensor: dims (16 samples, nf features, chunks), 64-byte inner box, SWIZZLE_64B.
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_act_map(CUtensorMap* map, const float* base, int nf, int64_t cap_keep) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return 1;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t n_chunks = (cuuint64_t)(cap_keep / KC);
+    const cuuint64_t dims[3] = {(cuuint64_t)KC, (cuuint64_t)nf, n_chunks};
+    const cuuint64_t strides[2] = {(cuuint64_t)ROWB, (cuuint64_t)nf * ROWB};
+    const cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)nf, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+               ? 0
+               : 2;
 }
 
 }  // namespace
@@ -416,8 +600,25 @@ int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b,
     pvdb_prof_mark("rgbnet_bwd_act", st);
     BwdWgradArgs W;
     W.k_dh1 = b->k_dh1; W.k_h0 = b->k_h0; W.k_dh0 = b->k_dh0; W.k_x = b->k_x; W.k_h1 = b->k_h1; W.k_glogit = b->k_rgb;
-    W.net_grad = b->net_grad; W.counters = b->counters; W.cap_keep = b->cap_keep;
-    k_rgbnet_bwd_wgrad_tc<<<PVDB_SMS, B2_THREADS, B2_TOTAL, st>>>(W);
+    PVDB_CHECK_ARG(b->net_partial, "net_partial scratch missing (tensor-core backward)");
+    W.partial = b->net_partial; W.counters = b->counters; W.cap_keep = b->cap_keep;
+    // tensor maps are pure host-side encodings of (pointer, shape): rebuilt when a buffer changes
+    static thread_local WgradMaps maps;
+    static thread_local const void* maps_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    static thread_local int maps_ok = 0;
+    const void* key[6] = {b->k_dh1, b->k_h0, b->k_dh0, b->k_h1, b->k_x, (const void*)(intptr_t)b->cap_keep};
+    if (memcmp(key, maps_key, sizeof(key)) != 0) {
+        const int rc = make_act_map(&maps.dh1, b->k_dh1, WD, b->cap_keep) | make_act_map(&maps.h0, b->k_h0, WD, b->cap_keep) |
+                       make_act_map(&maps.dh0, b->k_dh0, WD, b->cap_keep) | make_act_map(&maps.h1, b->k_h1, WD, b->cap_keep) |
+                       make_act_map(&maps.x, b->k_x, 40, b->cap_keep);
+        maps_ok = rc == 0;
+        memcpy(maps_key, key, sizeof(key));
+    }
+    static const bool no_tma = getenv("PVDB_NO_TMA") != nullptr;   // bring-up switch: cp.async loader instead of TMA
+    W.use_tma = maps_ok && !no_tma;
+    k_rgbnet_bwd_wgrad_tc<<<PVDB_SMS, B2_THREADS, B2_TOTAL, st>>>(W, maps);
+    PVDB_LAUNCH_CHECK();
+    k_wgrad_reduce<<<(PVDB_NET_N + 63) / 64, 256, 0, st>>>(b->net_partial, PVDB_SMS, b->net_grad);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

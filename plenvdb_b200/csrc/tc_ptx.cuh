@@ -92,6 +92,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 
+// Activation tensors exchanged between the rgbnet kernels through HBM are "chunk-major": [tile of 128 samples][chunk of 16
+// samples][feature][16 samples].  A lane (= sample) writing feature f of its row lands in one of two 64-byte runs per warp
+// (full 32-byte sectors), consecutive features are adjacent, and the weight-gradient pass streams a whole 16-sample chunk of
+// one tensor as ONE contiguous nf*64-byte block.  act_off: float offset of (sample s, feature f) in a tensor with nf features.
+__device__ __forceinline__ size_t act_off(int64_t s, int f, int nf) {
+    return (size_t)(s >> 7) * (size_t)(nf * 128) + (size_t)((s >> 4) & 7) * (size_t)(nf * 16) + (size_t)f * 16 + (size_t)(s & 15);
+}
+
 // ---- operand helpers ----------------------------------------------------------------------------------------
 // 3xTF32 split: hi keeps the 10 explicit tf32 mantissa bits, lo = x - hi is exact in fp32.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {

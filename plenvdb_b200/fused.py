@@ -81,6 +81,7 @@ class FusedTrainer:
             self.t["k_mask"] = z(ck, 8, **i32)
             self.t["k_corner"] = z(ck, 8, **i32)
             self.t["net_img"] = z(512 * 1024 // 4, **i32)
+            self.t["net_partial"] = z(148, 22048, **f32)
         self.parity_counts = bool(parity_counts)
         self.n_rays_global = int(n_rays_global) if n_rays_global else self.n_rays
         self._bufs = None

@@ -36,10 +36,10 @@ def test_tc_forward_matches_fp32(setup):
     b, *_ = _run(scene, net, rays, True)
     M = a.counters()["M_keep"]
     assert M == b.counters()["M_keep"] and M > 1000
-    def rows(tr, k):   # the tensor-core path keeps activations tile-transposed [tile][feature][128 samples]
+    def rows(tr, k):   # the tensor-core path keeps activations chunk-major [tile][8 chunks][feature][16 samples]
         t = tr.t[k]
         if tr.use_tc and k in ("k_h0", "k_h1"):
-            t = t.reshape(-1, 128, 128).transpose(1, 2).reshape(-1, 128)
+            t = t.reshape(-1, 8, 128, 16).permute(0, 1, 3, 2).reshape(-1, 128)
         return t[:M].cpu().numpy()
     for k in ("k_feat", "k_h0", "k_h1"):
         x, y = rows(a, k), rows(b, k)
@@ -64,7 +64,7 @@ def test_tc_forward_with_large_weights(setup):
     b, *_ = _run(scene, big, rays, True)
     M = a.counters()["M_keep"]
     x = a.t["k_h1"][:M].cpu().numpy()
-    y = b.t["k_h1"].reshape(-1, 128, 128).transpose(1, 2).reshape(-1, 128)[:M].cpu().numpy()
+    y = b.t["k_h1"].reshape(-1, 8, 128, 16).permute(0, 1, 3, 2).reshape(-1, 128)[:M].cpu().numpy()
     assert np.abs(x - y).max() <= 4e-6 * np.abs(x).max()
     np.testing.assert_allclose(b.t["rgb_marched"].cpu().numpy(), a.t["rgb_marched"].cpu().numpy(), rtol=1e-5, atol=3e-6)
     ga, gb = a.net_grad.cpu().numpy(), b.net_grad.cpu().numpy()
