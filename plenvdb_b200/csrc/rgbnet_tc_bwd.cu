@@ -59,146 +59,231 @@ __device__ __forceinline__ void issue_ts(uint32_t tmem, uint32_t smem_hi, uint32
 }
 
 // ---------------------------------------------------------------------------------------------- B1
+// Same warp-specialised structure as the forward (rgbnet_tc.cu): 8 lane warps (thread = sample lane x column half), one
+// issuer warp; the weight image (W1^T, W0[:, :12]^T as tf32 hi/lo in the canonical K-major layout + W2 as fp32) is built
+// once per step by k_prep_bwd_image and pulled into shared memory with one bulk async copy per CTA.
+//   step 1  dH1 = (g . W2) * [h1 > 0] on the CUDA cores, 32 columns at a time: to HBM (chunk-major, for B2) and into
+//           TMEM as the A operand; the issuer starts the matching k-steps of dH0 = dH1 . W1 (into D0) chunk by chunk
+//   step 2  dH0 = D0 * [h0 > 0]: to HBM and back into TMEM as A; the issuer follows with dX = dH0 . W0[:, :12] (into D1)
+//   step 3  dX -> k0 gradient scatter (colorvdb.cu:130-160) with the corner record ids the march saved; it is deferred
+//           until the NEXT tile's step 1 has been issued, so the scatter atomics run under that tile's MMAs
 constexpr int B1_W1HI = 0;                              // B[N=i][K=j] = w1[j][i], canonical K-major, [128][128]
 constexpr int B1_W1LO = B1_W1HI + WD * WD * 4;
 constexpr int B1_W0HI = B1_W1LO + WD * WD * 4;          // B[N=i<16][K=j] = w0[j][i], [16][128]
 constexpr int B1_W0LO = B1_W0HI + 16 * WD * 4;
 constexpr int B1_W2 = B1_W0LO + 16 * WD * 4;            // plain floats [3][128]
-constexpr int B1_BAR = B1_W2 + 3 * WD * 4;
-constexpr int B1_TOTAL = B1_BAR + 16;
+constexpr int B1_IMG = B1_W2 + 3 * WD * 4;
+constexpr int B1_BAR = B1_IMG;                          // W, D0, D1, A1_RDY[4], A0_RDY[4]; tmem slot at +88
+constexpr int B1B_W = 0, B1B_D0 = 8, B1B_D1 = 16, B1B_A1 = 24, B1B_A0 = 56, B1_TMEM_SLOT = 88;
+constexpr int B1_TOTAL = B1_BAR + 96;
+constexpr uint32_t COL_D0 = 256, COL_D1 = 384;
+constexpr int B1_THREADS = 288, B1_LANES = 256;
+static_assert(B1_IMG % 16 == 0, "bulk copy granularity");
+
+__global__ void __launch_bounds__(256) k_prep_bwd_image(const float* __restrict__ net, unsigned char* __restrict__ img) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int e = gtid; e < WD * WD; e += gsz) {           // B[n = i][k = j] = w1[j][i]
+        const int n = e % WD, k = e / WD;                 // coalesced read of w1[k][n]
+        uint32_t hi, lo;
+        split_tf32(__ldg(net + PVDB_NET_OFF_W1 + k * WD + n), hi, lo);
+        const int o = canon_off(n, k, WD);
+        *reinterpret_cast<uint32_t*>(img + B1_W1HI + o) = hi;
+        *reinterpret_cast<uint32_t*>(img + B1_W1LO + o) = lo;
+    }
+    for (int e = gtid; e < 16 * WD; e += gsz) {           // B[n = c < 16][k = j] = w0[j][c] (c < 12), zero padding rows
+        const int n = e / WD, k = e % WD;
+        uint32_t hi, lo;
+        split_tf32(n < 12 ? __ldg(net + PVDB_NET_OFF_W0 + k * PVDB_NET_DIN + n) : 0.f, hi, lo);
+        const int o = canon_off(n, k, WD);
+        *reinterpret_cast<uint32_t*>(img + B1_W0HI + o) = hi;
+        *reinterpret_cast<uint32_t*>(img + B1_W0LO + o) = lo;
+    }
+    for (int e = gtid; e < 3 * WD; e += gsz) reinterpret_cast<float*>(img + B1_W2)[e] = __ldg(net + PVDB_NET_OFF_W2 + e);
+}
 
 struct BwdActArgs {
-    pvdb_tree tree;
-    const float* net;
+    const unsigned char* img;
     const float *k_glogit, *k_xyz;
     const uint32_t* k_mask;
+    const int32_t* k_corner;
     float *k_dh1, *k_dh0;
     float* k0_grad; int32_t* k0_touched; int32_t* k0_touched_list; int32_t* counters_w;
     const int32_t* counters; int64_t cap_keep;
 };
 
-__global__ void __launch_bounds__(TM, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
+// k-steps [ks0, ks1) of D[128 x N] (+)= A(TMEM)[128 x 128] * B(smem, K-major)[N x 128]^T, 3xTF32
+__device__ __forceinline__ void issue_b1(uint32_t tmem, uint32_t d_col, uint32_t smem_hi, uint32_t smem_lo, int N, int ks0, int ks1, bool zero_first) {
+    const uint32_t idesc = make_idesc(N);
+    const uint64_t bhi = make_desc(smem_hi, WD), blo = make_desc(smem_lo, WD);
+    uint32_t acc = zero_first ? 0u : 1u;
+    for (int ks = ks0; ks < ks1; ++ks) {
+        const uint64_t adv = (uint64_t)(ks * 256) >> 4;
+        const uint32_t ahi = tmem + COL_AHI + ks * 8, alo = tmem + COL_ALO + ks * 8;
+        umma_tf32_ts(tmem + d_col, ahi, bhi + adv, idesc, acc);
+        acc = 1;
+        umma_tf32_ts(tmem + d_col, alo, bhi + adv, idesc, 1);
+        umma_tf32_ts(tmem + d_col, ahi, blo + adv, idesc, 1);
+    }
+}
+
+__global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar = sbase + B1_BAR;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B1_BAR + 8);
-    float* sW2 = reinterpret_cast<float*>(smem + B1_W2);
-    const float* net = A.net;
-    load_weight(smem, B1_W1HI, B1_W1LO, net + PVDB_NET_OFF_W1, /*sn(i)*/ 1, /*sk(j)*/ WD, WD, WD, WD, WD);
-    load_weight(smem, B1_W0HI, B1_W0LO, net + PVDB_NET_OFF_W0, /*sn(i)*/ 1, /*sk(j)*/ PVDB_NET_DIN, 16, WD, 12, WD);
-    for (int e = tid; e < 3 * WD; e += TM) sW2[e] = __ldg(net + PVDB_NET_OFF_W2 + e);
-    if (tid == 0) mbar_init(bar, 1);
-    if (warp == 0) tmem_alloc(sbase + B1_BAR + 8, 512);
-    fence_async_smem();
+    const uint32_t bars = sbase + B1_BAR;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B1_BAR + B1_TMEM_SLOT);
+    const float* sW2 = reinterpret_cast<const float*>(smem + B1_W2);
+    if (tid == 0) {
+        mbar_init(bars + B1B_W, 1);
+        mbar_init(bars + B1B_D0, 1);
+        mbar_init(bars + B1B_D1, 1);
+        for (int c = 0; c < 4; ++c) { mbar_init(bars + B1B_A1 + 8 * c, 128); mbar_init(bars + B1B_A0 + 8 * c, 128); }
+        fence_async_smem();
+        mbar_expect_tx(bars + B1B_W, B1_IMG);
+        constexpr int CH = 32768;
+        for (int o = 0; o < B1_IMG; o += CH) bulk_g2s(sbase + o, A.img + o, min(CH, B1_IMG - o), bars + B1B_W);
+    }
+    if (warp == 0) tmem_alloc(sbase + B1_BAR + B1_TMEM_SLOT, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    uint32_t parity = 0;
     const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
     const int64_t n_tiles = (M + TM - 1) / TM;
-    // per-sample inputs are tiny (3 + 8 + 3 words): fetched one tile ahead so their latency hides behind the MMAs
-    struct In { float g0, g1, g2, px, py, pz; uint4 m0, m1; };
-    auto fetch = [&](int64_t tile) {
-        In v;
-        v.g0 = v.g1 = v.g2 = v.px = v.py = v.pz = 0.f;
-        v.m0 = v.m1 = make_uint4(0, 0, 0, 0);
-        const int64_t s = tile * TM + tid;
-        if (tile < n_tiles && s < M) {
-            v.g0 = __ldg(A.k_glogit + s * 3); v.g1 = __ldg(A.k_glogit + s * 3 + 1); v.g2 = __ldg(A.k_glogit + s * 3 + 2);
-            v.px = __ldg(A.k_xyz + s * 3); v.py = __ldg(A.k_xyz + s * 3 + 1); v.pz = __ldg(A.k_xyz + s * 3 + 2);
-            const uint32_t* mk = A.k_mask + (s >> 7) * (8 * 128) + (s & 127);   // [tile][8][128]
-            v.m0 = make_uint4(__ldg(mk), __ldg(mk + 128), __ldg(mk + 256), __ldg(mk + 384));
-            v.m1 = make_uint4(__ldg(mk + 512), __ldg(mk + 640), __ldg(mk + 768), __ldg(mk + 896));
-        }
-        return v;
-    };
-    In nxt = fetch(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t s = tile * TM + tid;
-        const bool valid = s < M;
-        const In cur = nxt;
-        nxt = fetch(tile + gridDim.x);
-        const float g0 = cur.g0, g1 = cur.g1, g2 = cur.g2;
-        const uint32_t m0w[4] = {cur.m0.x, cur.m0.y, cur.m0.z, cur.m0.w}, m1w[4] = {cur.m1.x, cur.m1.y, cur.m1.z, cur.m1.w};
-        // ---- dH1 = (g . W2) masked by h1 > 0
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c = cc * 32;
-            float d[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int j = c + i;
-                const float v = fmaf(g2, sW2[2 * WD + j], fmaf(g1, sW2[WD + j], g0 * sW2[j]));
-                d[i] = (m1w[cc] >> i) & 1u ? v : 0.f;
+
+    if (warp == 8) {
+        // ---------------- issuer
+        if (tid == 256 && (int64_t)blockIdx.x < n_tiles) {
+            mbar_wait(bars + B1B_W, 0);
+            int i = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+                for (int c = 0; c < 4; ++c) {
+                    mbar_wait(bars + B1B_A1 + 8 * c, i & 1);
+                    tc_fence_after();
+                    issue_b1(tmem, COL_D0, sbase + B1_W1HI, sbase + B1_W1LO, WD, c * 4, c * 4 + 4, c == 0);
+                }
+                umma_commit(bars + B1B_D0);
+                for (int c = 0; c < 4; ++c) {
+                    mbar_wait(bars + B1B_A0 + 8 * c, i & 1);
+                    tc_fence_after();
+                    issue_b1(tmem, COL_D1, sbase + B1_W0HI, sbase + B1_W0LO, 16, c * 4, c * 4 + 4, c == 0);
+                }
+                umma_commit(bars + B1B_D1);
             }
-            {   // tile-transposed [tile][128][128], warp-coalesced; lanes past M write the zeros the weight-gradient pass relies on
+        }
+    } else if ((int64_t)blockIdx.x < n_tiles) {
+        // ---------------- lane warps
+        const int grp = warp >> 2;                               // column half (and corner half for the scatter)
+        const int lane_s = (warp & 3) * 32 + (tid & 31);         // sample within the tile = TMEM lane
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int cb = grp * 64;
+        // per-sample inputs of this thread's half: logit gradient, 2 + 2 mask words, 4 corner ids, position
+        struct In { float g0, g1, g2, px, py, pz; uint32_t m1a, m1b, m0a, m0b; int4 rec; };
+        auto fetch = [&](int64_t tile) {
+            In v;
+            v.g0 = v.g1 = v.g2 = v.px = v.py = v.pz = 0.f;
+            v.m1a = v.m1b = v.m0a = v.m0b = 0u;
+            v.rec = make_int4(-1, -1, -1, -1);
+            const int64_t s = tile * TM + lane_s;
+            if (tile < n_tiles && s < M) {
+                v.g0 = __ldg(A.k_glogit + s * 3); v.g1 = __ldg(A.k_glogit + s * 3 + 1); v.g2 = __ldg(A.k_glogit + s * 3 + 2);
+                v.px = __ldg(A.k_xyz + s * 3); v.py = __ldg(A.k_xyz + s * 3 + 1); v.pz = __ldg(A.k_xyz + s * 3 + 2);
+                const uint32_t* mk = A.k_mask + (s >> 7) * (8 * 128) + (s & 127);   // [tile][8][128]: words 0-3 h0, 4-7 h1
+                v.m0a = __ldg(mk + (grp * 2) * 128); v.m0b = __ldg(mk + (grp * 2 + 1) * 128);
+                v.m1a = __ldg(mk + (4 + grp * 2) * 128); v.m1b = __ldg(mk + (5 + grp * 2) * 128);
+                v.rec = __ldg(reinterpret_cast<const int4*>(A.k_corner + s * 8) + grp);
+            }
+            return v;
+        };
+        // step 1 of a tile: dH1 for this thread's 64 columns -> HBM + A operand, chunk by chunk
+        auto step1 = [&](int64_t tile, const In& in) {
+            const int64_t s = tile * TM + lane_s;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int c = cb + jj * 32;
+                const uint32_t mw = jj == 0 ? in.m1a : in.m1b;
+                float d[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int j = c + q;
+                    const float v = fmaf(in.g2, sW2[2 * WD + j], fmaf(in.g1, sW2[WD + j], in.g0 * sW2[j]));
+                    d[q] = (mw >> q) & 1u ? v : 0.f;
+                }
+                store_a_row32(lane_addr, c, d);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(bars + B1B_A1 + 8 * (c >> 5));
+                // chunk-major for B2; lanes past M write the zeros the weight-gradient pass relies on
                 float* o = A.k_dh1 + act_off(s, c, WD);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i * 16] = d[i];
+                for (int q = 0; q < 32; ++q) o[q * 16] = d[q];
             }
-            store_a_row32(lane_addr, c, d);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) { tc_fence_after(); issue_ts(tmem, sbase + B1_W1HI, sbase + B1_W1LO, WD, WD, bar); }
-        mbar_wait(bar, parity); parity ^= 1;
-        tc_fence_after();
-        // ---- dH0 = D masked by h0 > 0
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c = cc * 32;
-            uint32_t r[32];
-            tmem_ld32(lane_addr + COL_D + c, r);
-            tmem_ld_wait();
-            float d[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) d[i] = (m0w[cc] >> i) & 1u ? __uint_as_float(r[i]) : 0.f;
+        };
+        uint32_t par0 = 0, par1 = 0;
+        In cur = fetch(blockIdx.x);
+        mbar_wait(bars + B1B_W, 0);
+        step1(blockIdx.x, cur);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t s = tile * TM + lane_s;
+            const bool valid = s < M;
+            const In nxt = fetch(tile + gridDim.x);
+            // ---- step 2: dH0 = D0 masked by h0 > 0
+            mbar_wait(bars + B1B_D0, par0); par0 ^= 1;
+            tc_fence_after();
             {
-                float* o = A.k_dh0 + act_off(s, c, WD);
+                uint32_t r[2][32];
+                tmem_ld32(lane_addr + COL_D0 + cb, r[0]);
+                tmem_ld32(lane_addr + COL_D0 + cb + 32, r[1]);
+                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i * 16] = d[i];
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int c = cb + jj * 32;
+                    const uint32_t mw = jj == 0 ? cur.m0a : cur.m0b;
+                    float d[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) d[q] = (mw >> q) & 1u ? __uint_as_float(r[jj][q]) : 0.f;
+                    store_a_row32(lane_addr, c, d);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(bars + B1B_A0 + 8 * (c >> 5));
+                    float* o = A.k_dh0 + act_off(s, c, WD);
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) o[q * 16] = d[q];
+                }
             }
-            store_a_row32(lane_addr, c, d);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) { tc_fence_after(); issue_ts(tmem, sbase + B1_W0HI, sbase + B1_W0LO, WD, 16, bar); }
-        mbar_wait(bar, parity); parity ^= 1;
-        tc_fence_after();
-        // ---- dX[0..12) -> k0 gradient scatter (colorvdb.cu:130-160), 3 x red.v4 per corner
-        {
+            // every lane has drained D0 before any lane lets the issuer start the next tile's dH0 MMAs
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // ---- step 3a: dX row of this sample out of D1
+            mbar_wait(bars + B1B_D1, par1); par1 ^= 1;
+            tc_fence_after();
             uint32_t r[16];
-            tmem_ld16(lane_addr + COL_D, r);
+            tmem_ld16(lane_addr + COL_D1, r);
             tmem_ld_wait();
+            // ---- next tile's step 1 goes first: its MMAs run under the scatter below (A is free: both MMAs of this tile are done)
+            if (tile + gridDim.x < n_tiles) step1(tile + gridDim.x, nxt);
+            // ---- step 3b: k0 gradient scatter, 4 corners per thread (group 0: corners 0-3, group 1: 4-7), 3 x red.v4 per corner
             if (valid) {
                 PvdbTri tri;
                 tri.set(cur.px, cur.py, cur.pz);
-                PvdbLeafCache cache;
+                const int rec[4] = {cur.rec.x, cur.rec.y, cur.rec.z, cur.rec.w};
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int qq = 0; qq < 4; ++qq) {
+                    if (rec[qq] < 0) continue;
+                    const int q = grp * 4 + qq;
                     const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
-                    const int cx = tri.i + dx, cy = tri.j + dy, cz = tri.k + dz;
-                    const int leaf = cache.find(A.tree, cx, cy, cz);
-                    if (leaf < 0) continue;
                     const float sc = __fmul_rn(__fmul_rn(tri.f(0, dx), tri.f(1, dy)), tri.f(2, dz));
-                    float* dst = A.k0_grad + ((size_t)leaf * 512 + pvdb_leaf_off(cx, cy, cz)) * 12;
+                    float* dst = A.k0_grad + (size_t)rec[qq] * 12;
 #pragma unroll
                     for (int c4 = 0; c4 < 3; ++c4)
                         red_add4(dst + c4 * 4, __fmul_rn(__uint_as_float(r[c4 * 4]), sc), __fmul_rn(__uint_as_float(r[c4 * 4 + 1]), sc),
                                  __fmul_rn(__uint_as_float(r[c4 * 4 + 2]), sc), __fmul_rn(__uint_as_float(r[c4 * 4 + 3]), sc));
-                    pvdb_touch_leaf(A.k0_touched, A.k0_touched_list, A.counters_w + 4, leaf);
+                    pvdb_touch_leaf(A.k0_touched, A.k0_touched_list, A.counters_w + 4, rec[qq] >> 9);
                 }
             }
+            cur = nxt;
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
@@ -590,12 +675,16 @@ int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b,
         PVDB_CUDA(cudaFuncSetAttribute(k_rgbnet_bwd_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_TOTAL));
         attr_set = true;
     }
+    PVDB_CHECK_ARG(b->net_img && b->k_corner, "net_img / k_corner scratch missing (tensor-core backward)");
+    unsigned char* img = static_cast<unsigned char*>(b->net_img) + 256 * 1024;   // second half of the scratch: backward image
+    k_prep_bwd_image<<<32, 256, 0, st>>>(b->net, img);
+    PVDB_LAUNCH_CHECK();
     BwdActArgs A;
-    A.tree = *b->tree; A.net = b->net; A.k_glogit = b->k_rgb; A.k_mask = b->k_mask; A.k_xyz = b->k_xyz;
+    A.img = img; A.k_glogit = b->k_rgb; A.k_mask = b->k_mask; A.k_xyz = b->k_xyz; A.k_corner = b->k_corner;
     A.k_dh1 = b->k_dh1; A.k_dh0 = b->k_dh0; A.k0_grad = b->k0_grad; A.k0_touched = b->k0_touched; A.k0_touched_list = b->k0_touched_list; A.counters_w = b->counters;
     A.counters = b->counters;
     A.cap_keep = b->cap_keep;
-    k_rgbnet_bwd_act_tc<<<PVDB_SMS, TM, B1_TOTAL, st>>>(A);
+    k_rgbnet_bwd_act_tc<<<PVDB_SMS, B1_THREADS, B1_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("rgbnet_bwd_act", st);
     BwdWgradArgs W;
