@@ -207,6 +207,9 @@ typedef struct pvdb_train_bufs {
     int32_t *k_corner;                         /* [cap_keep][8] record id (leaf*512+voxel) of the 8 trilinear corners, -1 = none */
     void *net_img;                             /* >= 512 KiB scratch: tf32 hi/lo weight images of the tensor-core kernels */
     float *net_partial;                        /* [148][22048] per-CTA weight-gradient partial sums (tensor-core backward) */
+    void *march_scratch;                       /* optional: 20 * scratch_rays * scratch_per_ray words; the count pass parks its
+                                                * per-sample results here and the emit pass becomes a compaction (NULL: march twice) */
+    int32_t scratch_rays, scratch_per_ray;
     /* touched-leaf bookkeeping, [n_leaf] each */
     int32_t *den_touched, *k0_touched, *den_touched_list, *k0_touched_list;
     int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0 */

@@ -69,6 +69,7 @@ class pvdb_train_bufs(C.Structure):
         ("k_xyz", c_ptr), ("k_feat", c_ptr), ("k_rgb", c_ptr), ("k_gw", c_ptr),
         ("k_h0", c_ptr), ("k_h1", c_ptr), ("k_x", c_ptr), ("k_dh0", c_ptr), ("k_dh1", c_ptr), ("k_mask", c_ptr),
         ("k_corner", c_ptr), ("net_img", c_ptr), ("net_partial", c_ptr),
+        ("march_scratch", c_ptr), ("scratch_rays", C.c_int32), ("scratch_per_ray", C.c_int32),
         ("den_touched", c_ptr), ("k0_touched", c_ptr), ("den_touched_list", c_ptr), ("k0_touched_list", c_ptr),
         ("counters", c_ptr), ("loss", c_ptr),
     ]

@@ -50,18 +50,27 @@ __device__ __forceinline__ bool occ_test(const MarchParams& P, int i, int j, int
 // rec[q] (EMIT only) receives the record id leaf*512+voxel of corner q, -1 when the corner has no leaf: the k0 grid
 // shares the topology, so the rgbnet kernels reuse them instead of walking the tree again.
 template <bool WITH_REC>
-__device__ __forceinline__ float density_at(const MarchParams& P, PvdbLeafCache& cache, float x, float y, float z, int* rec) {
+__device__ __forceinline__ float density_at(const MarchParams& P, float x, float y, float z, int* rec) {
     PvdbTri tri;
     tri.set(x, y, z);
+    // The eight corner lookups are independent (no accessor cache threading them together), so their table and value
+    // loads overlap: the march is latency bound, one dependent chain per sample instead of up to eight.
+    int id[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int cx = tri.i + PVDB_CORNER[q][0], cy = tri.j + PVDB_CORNER[q][1], cz = tri.k + PVDB_CORNER[q][2];
+        const int leaf = pvdb_find_leaf(P.tree, cx, cy, cz);
+        id[q] = leaf >= 0 ? leaf * 512 + pvdb_leaf_off(cx, cy, cz) : -1;
+    }
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = id[q] >= 0 ? __ldg(P.den + id[q]) : 0.f;
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
-        const int cx = tri.i + dx, cy = tri.j + dy, cz = tri.k + dz;
-        const int leaf = cache.find(P.tree, cx, cy, cz);
-        if (WITH_REC) rec[q] = leaf >= 0 ? leaf * 512 + pvdb_leaf_off(cx, cy, cz) : -1;
-        const float v = leaf >= 0 ? __ldg(P.den + (size_t)leaf * 512 + pvdb_leaf_off(cx, cy, cz)) : 0.f;
-        acc = __fmaf_rn(tri.f(2, dz), __fmul_rn(tri.f(1, dy), __fmul_rn(tri.f(0, dx), v)), acc);
+        if (WITH_REC) rec[q] = id[q];
+        acc = __fmaf_rn(tri.f(2, dz), __fmul_rn(tri.f(1, dy), __fmul_rn(tri.f(0, dx), v[q])), acc);
     }
     return acc;
 }
@@ -78,16 +87,17 @@ struct MarchOut {
     int32_t *k_sample, *k_ray; float* k_xyz;
     int32_t* k_corner;   // [cap_keep][8] or null
     int32_t* counters;
+    // per-ray scratch of the count pass: what it computed for each alpha-passing sample, so that the emit pass is a
+    // compaction instead of a second march.  Entry (ray, i) = 5 x 16 bytes at ((ray * scr_cap + i) * 5):
+    // {step, x, y, z} {density, alpha, T, weight} {keep index, -, -, -} {corner ids 0-3} {corner ids 4-7}
+    uint4* scratch; int scr_cap;
 };
 
 // One warp per ray.  MODE 0 = count, 1 = emit.  PARITY (count only): keep marching past the early stop so the
 // full M1 / M2 counts of the reference are produced too.
 template <int MODE, bool PARITY>
-__global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
-                                               const float* __restrict__ rays_d, int n_rays) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (r >= n_rays) return;
+__device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& O, const float* __restrict__ rays_o,
+                                          const float* __restrict__ rays_d, const int r, const int lane) {
     float o[3] = {__ldg(rays_o + r * 3), __ldg(rays_o + r * 3 + 1), __ldg(rays_o + r * 3 + 2)};
     float d[3] = {__ldg(rays_d + r * 3), __ldg(rays_d + r * 3 + 1), __ldg(rays_d + r * 3 + 2)};
     float tmin, tmax, st[3], dir[3];
@@ -95,7 +105,6 @@ __global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const 
     const int nsteps = (int)pvdb_ray_n_samples(d, tmin, tmax, P.stepdist);
     pvdb_ray_start_dir(o, d, tmin, st, dir);
 
-    PvdbLeafCache cache;
     float T_cum = 1.f;
     bool stopped = false;
     int n_mask = 0, n_alpha = 0, n_keep = 0, n_alpha_full = 0;
@@ -125,7 +134,7 @@ __global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const 
             x = pvdb_wld2idx(px, P.xyz_min[0], P.xyz_max[0], P.rm1[0]);
             y = pvdb_wld2idx(py, P.xyz_min[1], P.xyz_max[1], P.rm1[1]);
             z = pvdb_wld2idx(pz, P.xyz_min[2], P.xyz_max[2], P.rm1[2]);
-            dens = density_at<MODE == 1>(P, cache, x, y, z, rec);
+            dens = density_at<true>(P, x, y, z, rec);
             float e;
             alpha = pvdb_raw2alpha(dens, P.act_shift, P.interval, e);
             a_ok = alpha > P.thres;
@@ -147,6 +156,16 @@ __global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const 
             ++n_alpha;
             n_keep += keep;
             if ((double)T_cum < 1e-3) { stopped = true; break; }
+        }
+        if (MODE == 0 && O.scratch && my_ai >= 0 && my_ai < O.scr_cap) {
+            uint4* e = O.scratch + ((int64_t)r * O.scr_cap + my_ai) * 5;
+            e[0] = make_uint4((uint32_t)step, __float_as_uint(x), __float_as_uint(y), __float_as_uint(z));
+            e[1] = make_uint4(__float_as_uint(dens), __float_as_uint(alpha), __float_as_uint(myT), __float_as_uint(myW));
+            e[2] = make_uint4((uint32_t)my_ki, 0u, 0u, 0u);
+            if (my_ki >= 0) {
+                e[3] = make_uint4((uint32_t)rec[0], (uint32_t)rec[1], (uint32_t)rec[2], (uint32_t)rec[3]);
+                e[4] = make_uint4((uint32_t)rec[4], (uint32_t)rec[5], (uint32_t)rec[6], (uint32_t)rec[7]);
+            }
         }
         if (MODE == 1 && my_ai >= 0) {
             const int64_t ia = oa + my_ai;
@@ -175,6 +194,51 @@ __global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const 
         O.cnt_mask[r] = n_mask; O.cnt_alpha[r] = n_alpha; O.cnt_keep[r] = n_keep;
         if (PARITY) O.cnt_alpha_full[r] = n_alpha_full;
         O.alphainv_last[r] = T_cum;
+    }
+}
+
+template <int MODE, bool PARITY>
+__global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
+                                               const float* __restrict__ rays_d, int n_rays) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rays) return;
+    march_ray<MODE, PARITY>(P, O, rays_o, rays_d, r, threadIdx.x & 31);
+}
+
+// Emit pass as a compaction: one warp per ray copies the count pass's scratch entries to their final, scanned positions.
+// A ray with more alpha-passing samples than the scratch holds is simply marched again.
+__global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
+                                                      const float* __restrict__ rays_d, int n_rays) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    const int na = O.cnt_alpha[r];
+    if (na > O.scr_cap) { march_ray<1, false>(P, O, rays_o, rays_d, r, lane); return; }
+    const int64_t oa = O.off_alpha[r], ok = O.off_keep[r];
+    for (int i = lane; i < na; i += 32) {
+        const uint4* e = O.scratch + ((int64_t)r * O.scr_cap + i) * 5;
+        const uint4 e0 = e[0], e1 = e[1], e2 = e[2];
+        const int64_t ia = oa + i;
+        const float x = __uint_as_float(e0.y), y = __uint_as_float(e0.z), z = __uint_as_float(e0.w);
+        if (ia < O.cap_alpha) {
+            O.s_ray[ia] = r; O.s_step[ia] = (int32_t)e0.x;
+            O.s_xyz[ia * 3] = x; O.s_xyz[ia * 3 + 1] = y; O.s_xyz[ia * 3 + 2] = z;
+            O.s_density[ia] = __uint_as_float(e1.x); O.s_alpha[ia] = __uint_as_float(e1.y);
+            O.s_T[ia] = __uint_as_float(e1.z); O.s_weight[ia] = __uint_as_float(e1.w);
+        }
+        const int ki = (int32_t)e2.x;
+        if (ki >= 0) {
+            const int64_t ik = ok + ki;
+            if (ik < O.cap_keep && ia < O.cap_alpha) {
+                O.k_sample[ik] = (int32_t)ia; O.k_ray[ik] = r;
+                O.k_xyz[ik * 3] = x; O.k_xyz[ik * 3 + 1] = y; O.k_xyz[ik * 3 + 2] = z;
+                if (O.k_corner) {
+                    uint4* kc = reinterpret_cast<uint4*>(O.k_corner + ik * 8);
+                    kc[0] = e[3];
+                    kc[1] = e[4];
+                }
+            }
+        }
     }
 }
 
@@ -556,6 +620,8 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     O.s_T = b->s_T; O.s_weight = b->s_weight;
     O.k_sample = b->k_sample; O.k_ray = b->k_ray; O.k_xyz = b->k_xyz; O.k_corner = b->k_corner;
     O.counters = b->counters;
+    O.scratch = reinterpret_cast<uint4*>(b->march_scratch);
+    O.scr_cap = b->march_scratch ? b->scratch_per_ray : 0;
     return 0;
 }
 
@@ -679,7 +745,9 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
                                           b->cap_keep);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("scan", st);
-        k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
+        PVDB_CHECK_ARG(!O.scratch || n_rays <= b->scratch_rays, "march_scratch holds fewer rays than this batch");
+        if (O.scratch) k_emit_scratch<<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
+        else k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
         int rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);

@@ -30,7 +30,8 @@ def mask_scale_shift(mask_shape, xyz_min, xyz_max):
 
 class FusedTrainer:
     def __init__(self, params, density, k0, mask, net, n_rays, device="cuda", use_tensor_cores=True,
-                 cap_alpha_per_ray=96, cap_keep_per_ray=64, parity_counts=False, n_rays_global=None):
+                 cap_alpha_per_ray=96, cap_keep_per_ray=64, parity_counts=False, n_rays_global=None,
+                 scratch_per_ray=128):
         """params: dict from synth.scene_params (or the equivalent run.py scalars).
         density: DensityVDB, k0: ColorVDB(12) on the SAME topology (k0.topo is density.topo).
         mask: bool [reso] mask_cache.mask.  net: float32[22019] packed rgbnet parameters."""
@@ -82,6 +83,9 @@ class FusedTrainer:
             self.t["k_corner"] = z(ck, 8, **i32)
             self.t["net_img"] = z(512 * 1024 // 4, **i32)
             self.t["net_partial"] = z(148, 22048, **f32)
+        self.scratch_per_ray = int(scratch_per_ray)
+        if self.scratch_per_ray > 0:
+            self.t["march_scratch"] = z(20 * n * self.scratch_per_ray, **i32)
         self.parity_counts = bool(parity_counts)
         self.n_rays_global = int(n_rays_global) if n_rays_global else self.n_rays
         self._bufs = None
@@ -129,6 +133,7 @@ class FusedTrainer:
         b.cap_alpha, b.cap_keep = self.cap_alpha, self.cap_keep
         for k, t in self.t.items():
             setattr(b, k, p(t))
+        b.scratch_rays, b.scratch_per_ray = self.n_rays, self.scratch_per_ray
         self._bufs = b
 
     def _set_step_scalars(self):

@@ -152,3 +152,24 @@ def test_data_parallel_shards_sum_to_full_batch(small):
         acc_n = acc_n + tr.net_grad.clone()
     for a, b in ((acc_d, dfull.grad), (acc_k, kfull.grad), (acc_n, full.net_grad)):
         assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("scratch_per_ray", [0, 4])
+def test_emit_by_compaction_equals_second_march(scratch_per_ray, small):
+    """The emit pass copies what the count pass parked in the per-ray scratch; rays that overflow the scratch (here almost all,
+    with 4 entries) and the scratch-less configuration march a second time.  All three must give identical lists."""
+    scene, net, rays = small
+    rays_d = [_cu(a) for a in rays]
+    ref, *_ = _trainer(scene, net, 2048)                       # default: 128 scratch entries per ray
+    alt, *_ = _trainer(scene, net, 2048, scratch_per_ray=scratch_per_ray)
+    for tr in (ref, alt):
+        tr.forward(*rays_d[:3])
+    torch.cuda.synchronize()
+    ca, cb = ref.counters(), alt.counters()
+    assert ca["M_alpha"] == cb["M_alpha"] and ca["M_keep"] == cb["M_keep"] and ca["M_alpha"] > 1000
+    ma, mk = ca["M_alpha"], ca["M_keep"]
+    for k in ("s_ray", "s_step", "s_xyz", "s_density", "s_alpha", "s_T", "s_weight"):
+        assert torch.equal(ref.t[k][:ma], alt.t[k][:ma]), k
+    for k in ("k_sample", "k_ray", "k_xyz", "k_corner", "k_rgb"):
+        assert torch.equal(ref.t[k][:mk], alt.t[k][:mk]), k
+    assert torch.equal(ref.t["rgb_marched"], alt.t["rgb_marched"])
