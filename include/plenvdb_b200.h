@@ -212,7 +212,8 @@ typedef struct pvdb_train_bufs {
     int32_t scratch_rays, scratch_per_ray;
     /* touched-leaf bookkeeping, [n_leaf] each */
     int32_t *den_touched, *k0_touched, *den_touched_list, *k0_touched_list;
-    int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0 */
+    int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0,
+                                                * 5 ray ticket of the count pass (zero between steps) */
     float *loss;                               /* [4]: total, mse, entropy_last, rgbper */
 } pvdb_train_bufs;
 

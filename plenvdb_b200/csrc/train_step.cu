@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int CNT_M_ALPHA = 0, CNT_M_KEEP = 1, CNT_N_TOUCHED_DEN = 2, CNT_OVERFLOW = 3, CNT_N_TOUCHED_K0 = 4;
+constexpr int CNT_M_ALPHA = 0, CNT_M_KEEP = 1, CNT_N_TOUCHED_DEN = 2, CNT_OVERFLOW = 3, CNT_N_TOUCHED_K0 = 4, CNT_RAY_TICKET = 5;
 
 struct MarchParams {
     pvdb_tree tree;
@@ -54,13 +54,33 @@ __device__ __forceinline__ float density_at(const MarchParams& P, float x, float
     PvdbTri tri;
     tri.set(x, y, z);
     // The eight corner lookups are independent (no accessor cache threading them together), so their table and value
-    // loads overlap: the march is latency bound, one dependent chain per sample instead of up to eight.
+    // loads overlap.  The root key and the three table offsets are bit-field unions of per-axis parts (NanoVDB.h:2702-2709,
+    // 3377-3385, 3893-3900), so they are formed once per axis for c and c+1 and OR-ed per corner.
+    const int c3[3] = {tri.i, tri.j, tri.k};
+    uint64_t kp[3][2];
+    int up[3][2], lp[3][2], fp[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const int c = c3[a] + d;
+            kp[a][d] = (uint64_t)((uint32_t)c >> 12) << (a == 0 ? 42 : a == 1 ? 21 : 0);
+            up[a][d] = ((c & 4095) >> 7) << (a == 0 ? 10 : a == 1 ? 5 : 0);
+            lp[a][d] = ((c & 127) >> 3) << (a == 0 ? 8 : a == 1 ? 4 : 0);
+            fp[a][d] = (c & 7) << (a == 0 ? 6 : a == 1 ? 3 : 0);
+        }
     int id[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const int cx = tri.i + PVDB_CORNER[q][0], cy = tri.j + PVDB_CORNER[q][1], cz = tri.k + PVDB_CORNER[q][2];
-        const int leaf = pvdb_find_leaf(P.tree, cx, cy, cz);
-        id[q] = leaf >= 0 ? leaf * 512 + pvdb_leaf_off(cx, cy, cz) : -1;
+        const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+        int leaf;
+        if ((kp[0][dx] | kp[1][dy] | kp[2][dz]) == P.tree.root_key0 && P.tree.n_upper > 0) {
+            const int l = __ldg(P.tree.upper_child + (up[0][dx] | up[1][dy] | up[2][dz]));
+            leaf = l >= 0 ? __ldg(P.tree.lower_child + (size_t)l * 4096 + (lp[0][dx] | lp[1][dy] | lp[2][dz])) : -1;
+        } else {
+            leaf = pvdb_find_leaf(P.tree, c3[0] + dx, c3[1] + dy, c3[2] + dz);
+        }
+        id[q] = leaf >= 0 ? leaf * 512 + (fp[0][dx] | fp[1][dy] | fp[2][dz]) : -1;
     }
     float v[8];
 #pragma unroll
@@ -111,26 +131,55 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
     int64_t oa = 0, ok = 0;
     if (MODE == 1) { oa = O.off_alpha[r]; ok = O.off_keep[r]; }
 
-    for (int base = 0; base < nsteps; base += 32) {
-        const int step = base + lane;
-        bool in_mask = false;
-        float px = 0, py = 0, pz = 0;
-        if (step < nsteps) {
-            pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, step, px, py, pz);
-            const bool outb = (P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) | (P.xyz_max[0] < px) |
-                              (P.xyz_max[1] < py) | (P.xyz_max[2] < pz);
-            if (!outb)
-                in_mask = occ_test(P, pvdb_mask_ijk(px, P.mask_scale[0], P.mask_shift[0]),
-                                   pvdb_mask_ijk(py, P.mask_scale[1], P.mask_shift[1]),
-                                   pvdb_mask_ijk(pz, P.mask_scale[2], P.mask_shift[2]));
+    // Two passes per segment of 1024 steps.  Pass A only tests occupancy (most steps are in empty space) and leaves one
+    // 32-step ballot word in each lane; pass B then visits the in-mask steps 32 at a time, in step order, so the expensive
+    // part (trilinear density, activation) runs with full lanes instead of the 2-3 live lanes a plain 32-step sweep has.
+    for (int seg = 0; seg < nsteps && !(stopped && !PARITY); seg += 1024) {
+        unsigned myword = 0;
+        const int n_it = min(32, (nsteps - seg + 31) >> 5);
+        for (int it = 0; it < n_it; ++it) {
+            const int step = seg + it * 32 + lane;
+            bool in_mask = false;
+            if (step < nsteps) {
+                float px, py, pz;
+                pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, step, px, py, pz);
+                const bool outb = (P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) | (P.xyz_max[0] < px) |
+                                  (P.xyz_max[1] < py) | (P.xyz_max[2] < pz);
+                if (!outb)
+                    in_mask = occ_test(P, pvdb_mask_ijk(px, P.mask_scale[0], P.mask_shift[0]),
+                                       pvdb_mask_ijk(py, P.mask_scale[1], P.mask_shift[1]),
+                                       pvdb_mask_ijk(pz, P.mask_scale[2], P.mask_shift[2]));
+            }
+            const unsigned bits = __ballot_sync(0xffffffffu, in_mask);
+            if (lane == it) myword = bits;
         }
-        const unsigned mbits = __ballot_sync(0xffffffffu, in_mask);
-        if (mbits == 0) continue;
-        n_mask += __popc(mbits);
+        const int cnt = __popc(myword);
+        int incl = cnt;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o2); if (lane >= o2) incl += u; }
+        const int excl = incl - cnt;
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        n_mask += total;
+      for (int b0 = 0; b0 < total; b0 += 32) {
+        const int t = b0 + lane;
+        const bool in_mask = t < total;
+        const int tt = in_mask ? t : total - 1;
+        // word holding the tt-th in-mask step: the largest j with excl[j] <= tt (its count is then non-zero)
+        int j = 0;
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+            const int e = __shfl_sync(0xffffffffu, excl, j + sft);
+            if (e <= tt) j += sft;
+        }
+        const unsigned word = __shfl_sync(0xffffffffu, myword, j);
+        const int ex = __shfl_sync(0xffffffffu, excl, j);
+        const int step = seg + j * 32 + (int)__fns(word, 0, tt - ex + 1);
         float x = 0, y = 0, z = 0, dens = 0, alpha = 0;
         int rec[8];
         bool a_ok = false;
         if (in_mask) {
+            float px, py, pz;
+            pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, step, px, py, pz);
             x = pvdb_wld2idx(px, P.xyz_min[0], P.xyz_max[0], P.rm1[0]);
             y = pvdb_wld2idx(py, P.xyz_min[1], P.xyz_max[1], P.rm1[1]);
             z = pvdb_wld2idx(pz, P.xyz_min[2], P.xyz_max[2], P.rm1[2]);
@@ -188,6 +237,7 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
             }
         }
         if (stopped && !PARITY) break;
+      }
     }
     if (MODE == 0 && lane == 0) {
         O.t_min[r] = tmin; O.t_max[r] = tmax; O.n_steps[r] = nsteps;
@@ -197,12 +247,26 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
     }
 }
 
+// ticket == nullptr: warp w marches ray w.  Otherwise a resident grid of warps draws rays from an atomic ticket counter
+// (rays differ 10x in length; 8192 of them are 1.4 waves of static warps, so the tail of a static grid idles a third of
+// the machine).  The counter is reset by k_scan_counts, which always follows the count pass.
 template <int MODE, bool PARITY>
-__global__ void __launch_bounds__(256) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
-                                               const float* __restrict__ rays_d, int n_rays) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= n_rays) return;
-    march_ray<MODE, PARITY>(P, O, rays_o, rays_d, r, threadIdx.x & 31);
+__global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
+                                                  const float* __restrict__ rays_d, int n_rays, int32_t* __restrict__ ticket) {
+    const int lane = threadIdx.x & 31;
+    if (ticket == nullptr) {
+        const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (r >= n_rays) return;
+        march_ray<MODE, PARITY>(P, O, rays_o, rays_d, r, lane);
+        return;
+    }
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(ticket, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= n_rays) return;
+        march_ray<MODE, PARITY>(P, O, rays_o, rays_d, r, lane);
+    }
 }
 
 // Emit pass as a compaction: one warp per ray copies the count pass's scratch entries to their final, scanned positions.
@@ -313,7 +377,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
             oa[n] = w.x; ok[n] = w.y;
             counters[CNT_M_ALPHA] = w.x; counters[CNT_M_KEEP] = w.y;
             counters[CNT_OVERFLOW] = (w.x > cap_alpha || w.y > cap_keep) ? 1 : 0;
-            counters[CNT_N_TOUCHED_DEN] = 0; counters[CNT_N_TOUCHED_K0] = 0;
+            counters[CNT_N_TOUCHED_DEN] = 0; counters[CNT_N_TOUCHED_K0] = 0; counters[CNT_RAY_TICKET] = 0;
         }
     }
     __syncthreads();
@@ -737,8 +801,17 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
 
     if (do_fwd) {
         PVDB_CHECK_ARG(rays_o && rays_d && viewdirs, "null rays");
-        if (cfg->parity_counts) k_march<0, true><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
-        else k_march<0, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
+        if (cfg->parity_counts) {
+            k_march<0, true><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+        } else {
+            static int resident = 0;   // CTAs of the count kernel that fit the device at once
+            if (!resident) {
+                int per_sm = 0;
+                PVDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<0, false>, 256, 0));
+                resident = PVDB_SMS * (per_sm > 0 ? per_sm : 1);
+            }
+            k_march<0, false><<<min(resident, warp_grid), 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, b->counters + CNT_RAY_TICKET);
+        }
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_count", st);
         k_scan_counts<<<1, 1024, 0, st>>>(b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays, b->counters, b->cap_alpha,
@@ -747,7 +820,7 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         pvdb_prof_mark("scan", st);
         PVDB_CHECK_ARG(!O.scratch || n_rays <= b->scratch_rays, "march_scratch holds fewer rays than this batch");
         if (O.scratch) k_emit_scratch<<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
-        else k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
+        else k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
         int rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
