@@ -259,11 +259,27 @@ def run_ours(args):
         mlp_pass = 3.0 if tr.use_tc else 1.0      # 3xTF32 issues three tensor-core products per algorithmic product
         kern_flops = {"rgbnet_fwd": mlp_flops_fwd, "rgbnet_bwd": 2.0 * mlp_flops_fwd,
                       "rgbnet_bwd_act": 2.0 * M3 * (128 * 128 + 128 * 12), "rgbnet_bwd_wgrad": 2.0 * M3 * (128 * 128 + 128 * 40 + 3 * 128)}
+        # dram bytes per launch of the same kernel from the committed ncu --set full capture (profiles/traffic_r01.json)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01.json")))
+            kname = {"rgbnet_fwd": "k_rgbnet_fwd_tc", "rgbnet_bwd_act": "k_rgbnet_bwd_act_tc", "rgbnet_bwd_wgrad": "k_rgbnet_bwd_wgrad_tc"}.get(top)
+            if tr.use_tc and kname in tj:
+                traffic = tj[kname]["dram_bytes"]
+        except Exception:
+            traffic = None
+        # bytes the three MLP kernels move by design (activations handed over through HBM), per kept sample
+        design_bytes = {"rgbnet_fwd": M3 * (512 + 512 + 160 + 32 + 48 + 12 + 44.0), "rgbnet_bwd_act": M3 * (512 + 512 + 88.0),
+                        "rgbnet_bwd_wgrad": M3 * (4 * 512 + 160 + 12.0) + 148 * 22048 * 4.0}
         if top in kern_flops:
             ach = kern_flops[top] / (kern[top] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
-                    "traffic": None, "peak_source": which,
+                    "traffic": traffic, "peak_source": which,
                     "tensor_core_flops_issued": kern_flops[top] * mlp_pass,
+                    "hbm_view": ({"design_bytes": design_bytes[top], "achieved_GBs": design_bytes[top] / (kern[top] * 1e-3) / 1e9,
+                                  "frac_of_hbm": design_bytes[top] / (kern[top] * 1e-3) / 1e9 / hbm,
+                                  "note": "activation tensors this kernel reads/writes through HBM by design; the real limiter of the tcgen05 kernels"}
+                                 if top in design_bytes and tr.use_tc else None),
                     "note": ("algorithmic fp32 FLOPs of the kernel / its duration, against the %s dense bf16 cuBLAS peak; "
                              "the tcgen05 path issues 3 TF32 products per algorithmic product (tf32 peak = bf16/2)" % which)}
         else:

@@ -47,5 +47,23 @@ def full(path):
         print()
 
 
+def traffic(path):
+    """JSON {kernel short name: dram bytes read + written per launch} — what bench.py reports as roofline.traffic."""
+    import json
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res = {}
+    for r in rows[2:]:
+        name = re.sub(r"^.*::", "", r[idx["Kernel Name"]].split("(")[0])
+        b = sum(float(r[idx[k]].replace(",", "")) * mult[units[idx[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        res[name] = {"dram_bytes": b, "duration_us": float(r[idx["gpu__time_duration.sum"]].replace(",", "")),
+                     "report": path.split("/")[-1]}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
