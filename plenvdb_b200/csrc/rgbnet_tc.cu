@@ -93,8 +93,10 @@ struct TcWeights {
 };
 
 // Build the weight image (see the smem map) in global memory.  Any grid; ~22 k elements.
-__global__ void __launch_bounds__(256) k_prep_fwd_image(TcWeights Wt, unsigned char* __restrict__ img) {
+// net_packed != nullptr (training): also the activation-gradient kernel's image, PVDB_BWD_IMG_OFFSET further on.
+__global__ void __launch_bounds__(256) k_prep_fwd_image(TcWeights Wt, unsigned char* __restrict__ img, const float* __restrict__ net_packed) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (net_packed) prep_bwd_image(net_packed, img + PVDB_BWD_IMG_OFFSET, gtid, gsz);
     for (int e = gtid; e < WD * K0P; e += gsz) {
         const int n = e / K0P, k = e % K0P;
         const float v = k < PVDB_NET_DIN ? __ldg(Wt.w0 + (size_t)n * Wt.w0_sn + (size_t)k * Wt.w0_sk) : 0.f;
@@ -469,7 +471,7 @@ int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     W.w1 = net + PVDB_NET_OFF_W1; W.w1_sn = WD; W.w1_sk = 1;
     W.w2 = net + PVDB_NET_OFF_W2; W.w2_sn = WD; W.w2_sk = 1;
     W.b0 = net + PVDB_NET_OFF_B0; W.b1 = net + PVDB_NET_OFF_B1; W.b2 = net + PVDB_NET_OFF_B2;
-    k_prep_fwd_image<<<32, 256, 0, st>>>(W, static_cast<unsigned char*>(b->net_img));
+    k_prep_fwd_image<<<PVDB_SMS, 256, 0, st>>>(W, static_cast<unsigned char*>(b->net_img), b->net);
     PVDB_LAUNCH_CHECK();
     k_rgbnet_fwd_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();
@@ -489,7 +491,7 @@ int pvdb_render_mlp_tc(const void* render_mlp_args, cudaStream_t st) {
     W.w2 = A.w2; W.w2_sn = 1; W.w2_sk = 3;
     W.b0 = A.b0; W.b1 = A.b1; W.b2 = A.b2;
     PVDB_CHECK_ARG(A.img, "w_img scratch missing (tensor-core rgbnet)");
-    k_prep_fwd_image<<<32, 256, 0, st>>>(W, A.img);
+    k_prep_fwd_image<<<PVDB_SMS, 256, 0, st>>>(W, A.img, nullptr);
     PVDB_LAUNCH_CHECK();
     k_render_mlp_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();

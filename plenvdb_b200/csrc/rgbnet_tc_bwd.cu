@@ -61,45 +61,18 @@ __device__ __forceinline__ void issue_ts(uint32_t tmem, uint32_t smem_hi, uint32
 // ---------------------------------------------------------------------------------------------- B1
 // Same warp-specialised structure as the forward (rgbnet_tc.cu): 8 lane warps (thread = sample lane x column half), one
 // issuer warp; the weight image (W1^T, W0[:, :12]^T as tf32 hi/lo in the canonical K-major layout + W2 as fp32) is built
-// once per step by k_prep_bwd_image and pulled into shared memory with one bulk async copy per CTA.
+// once per step (prep_bwd_image, run by the forward's prep kernel) and pulled into shared memory with one bulk async copy per CTA.
 //   step 1  dH1 = (g . W2) * [h1 > 0] on the CUDA cores, 32 columns at a time: to HBM (chunk-major, for B2) and into
 //           TMEM as the A operand; the issuer starts the matching k-steps of dH0 = dH1 . W1 (into D0) chunk by chunk
 //   step 2  dH0 = D0 * [h0 > 0]: to HBM and back into TMEM as A; the issuer follows with dX = dH0 . W0[:, :12] (into D1)
 //   step 3  dX -> k0 gradient scatter (colorvdb.cu:130-160) with the corner record ids the march saved; it is deferred
 //           until the NEXT tile's step 1 has been issued, so the scatter atomics run under that tile's MMAs
-constexpr int B1_W1HI = 0;                              // B[N=i][K=j] = w1[j][i], canonical K-major, [128][128]
-constexpr int B1_W1LO = B1_W1HI + WD * WD * 4;
-constexpr int B1_W0HI = B1_W1LO + WD * WD * 4;          // B[N=i<16][K=j] = w0[j][i], [16][128]
-constexpr int B1_W0LO = B1_W0HI + 16 * WD * 4;
-constexpr int B1_W2 = B1_W0LO + 16 * WD * 4;            // plain floats [3][128]
-constexpr int B1_IMG = B1_W2 + 3 * WD * 4;
 constexpr int B1_BAR = B1_IMG;                          // W, D0, D1, A1_RDY[4], A0_RDY[4]; tmem slot at +88
 constexpr int B1B_W = 0, B1B_D0 = 8, B1B_D1 = 16, B1B_A1 = 24, B1B_A0 = 56, B1_TMEM_SLOT = 88;
 constexpr int B1_TOTAL = B1_BAR + 96;
 constexpr uint32_t COL_D0 = 256, COL_D1 = 384;
 constexpr int B1_THREADS = 288, B1_LANES = 256;
 static_assert(B1_IMG % 16 == 0, "bulk copy granularity");
-
-__global__ void __launch_bounds__(256) k_prep_bwd_image(const float* __restrict__ net, unsigned char* __restrict__ img) {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (int e = gtid; e < WD * WD; e += gsz) {           // B[n = i][k = j] = w1[j][i]
-        const int n = e % WD, k = e / WD;                 // coalesced read of w1[k][n]
-        uint32_t hi, lo;
-        split_tf32(__ldg(net + PVDB_NET_OFF_W1 + k * WD + n), hi, lo);
-        const int o = canon_off(n, k, WD);
-        *reinterpret_cast<uint32_t*>(img + B1_W1HI + o) = hi;
-        *reinterpret_cast<uint32_t*>(img + B1_W1LO + o) = lo;
-    }
-    for (int e = gtid; e < 16 * WD; e += gsz) {           // B[n = c < 16][k = j] = w0[j][c] (c < 12), zero padding rows
-        const int n = e / WD, k = e % WD;
-        uint32_t hi, lo;
-        split_tf32(n < 12 ? __ldg(net + PVDB_NET_OFF_W0 + k * PVDB_NET_DIN + n) : 0.f, hi, lo);
-        const int o = canon_off(n, k, WD);
-        *reinterpret_cast<uint32_t*>(img + B1_W0HI + o) = hi;
-        *reinterpret_cast<uint32_t*>(img + B1_W0LO + o) = lo;
-    }
-    for (int e = gtid; e < 3 * WD; e += gsz) reinterpret_cast<float*>(img + B1_W2)[e] = __ldg(net + PVDB_NET_OFF_W2 + e);
-}
 
 struct BwdActArgs {
     const unsigned char* img;
@@ -611,25 +584,29 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-// net_grad[e] = sum over the CTAs' partials.  64 elements x 4 partial groups per CTA; coalesced across elements.
+// net_grad[e] = sum over the CTAs' partials.  32 elements x 8 partial groups per CTA: every thread has all of its ~19 loads
+// in flight at once (one latency), 128-byte coalesced across the 32 elements.
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad) {
-    __shared__ float red[4][64];
-    const int e = blockIdx.x * 64 + (threadIdx.x & 63), g = threadIdx.x >> 6;
-    float s = 0.f;
-    if (e < PVDB_NET_N) {
-        float a[8];
-        int c = g;
-        for (; c + 28 < n_part; c += 32) {
+    __shared__ float red[8][32];
+    const int e = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+    float a[19];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = __ldcg(partial + (size_t)(c + 4 * u) * PART_LD + e);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s += a[u];
-        }
-        for (; c < n_part; c += 4) s += __ldcg(partial + (size_t)c * PART_LD + e);
+    for (int u = 0; u < 19; ++u) {
+        const int c = g + 8 * u;
+        a[u] = (e < PVDB_NET_N && c < n_part) ? __ldcg(partial + (size_t)c * PART_LD + e) : 0.f;
     }
-    red[g][threadIdx.x & 63] = s;
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 19; ++u) s += a[u];
+    for (int c = g + 8 * 19; c < n_part && e < PVDB_NET_N; c += 8) s += __ldcg(partial + (size_t)c * PART_LD + e);
+    red[g][threadIdx.x & 31] = s;
     __syncthreads();
-    if (g == 0 && e < PVDB_NET_N) net_grad[e] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+    if (g == 0 && e < PVDB_NET_N) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+        net_grad[e] = t;
+    }
 }
 
 #ifdef PVDB_TC_TIMING
@@ -676,9 +653,8 @@ int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b,
         attr_set = true;
     }
     PVDB_CHECK_ARG(b->net_img && b->k_corner, "net_img / k_corner scratch missing (tensor-core backward)");
-    unsigned char* img = static_cast<unsigned char*>(b->net_img) + 256 * 1024;   // second half of the scratch: backward image
-    k_prep_bwd_image<<<32, 256, 0, st>>>(b->net, img);
-    PVDB_LAUNCH_CHECK();
+    // second half of the scratch: backward image, built together with the forward image by pvdb_rgbnet_forward_tc
+    const unsigned char* img = static_cast<const unsigned char*>(b->net_img) + PVDB_BWD_IMG_OFFSET;
     BwdActArgs A;
     A.img = img; A.k_glogit = b->k_rgb; A.k_mask = b->k_mask; A.k_xyz = b->k_xyz; A.k_corner = b->k_corner;
     A.k_dh1 = b->k_dh1; A.k_dh0 = b->k_dh0; A.k0_grad = b->k0_grad; A.k0_touched = b->k0_touched; A.k0_touched_list = b->k0_touched_list; A.counters_w = b->counters;
@@ -707,7 +683,7 @@ int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b,
     W.use_tma = maps_ok && !no_tma;
     k_rgbnet_bwd_wgrad_tc<<<PVDB_SMS, B2_THREADS, B2_TOTAL, st>>>(W, maps);
     PVDB_LAUNCH_CHECK();
-    k_wgrad_reduce<<<(PVDB_NET_N + 63) / 64, 256, 0, st>>>(b->net_partial, PVDB_SMS, b->net_grad);
+    k_wgrad_reduce<<<(PVDB_NET_N + 31) / 32, 256, 0, st>>>(b->net_partial, PVDB_SMS, b->net_grad);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

@@ -133,6 +133,35 @@ __device__ void load_weight(unsigned char* smem, int off_hi, int off_lo, const f
 }
 
 
+// ---- weight image of the activation-gradient kernel (rgbnet_tc_bwd.cu B1), built by the forward's prep kernel ----------
+constexpr int PVDB_BWD_IMG_OFFSET = 256 * 1024;         // inside pvdb_train_bufs.net_img
+constexpr int B1_W1HI = 0;                              // B[N=i][K=j] = w1[j][i], canonical K-major, [128][128]
+constexpr int B1_W1LO = B1_W1HI + 128 * 128 * 4;
+constexpr int B1_W0HI = B1_W1LO + 128 * 128 * 4;          // B[N=i<16][K=j] = w0[j][i], [16][128]
+constexpr int B1_W0LO = B1_W0HI + 16 * 128 * 4;
+constexpr int B1_W2 = B1_W0LO + 16 * 128 * 4;            // plain floats [3][128]
+constexpr int B1_IMG = B1_W2 + 3 * 128 * 4;
+__device__ __forceinline__ void prep_bwd_image(const float* __restrict__ net, unsigned char* __restrict__ img, int gtid, int gsz) {
+    constexpr int OFF_W0 = 0, OFF_W1 = 128 * 39 + 128, OFF_W2 = OFF_W1 + 128 * 128 + 128;   // rgbnet.cuh packed layout
+    for (int e = gtid; e < 128 * 128; e += gsz) {         // B[n = i][k = j] = w1[j][i]
+        const int n = e % 128, k = e / 128;               // coalesced read of w1[k][n]
+        uint32_t hi, lo;
+        split_tf32(__ldg(net + OFF_W1 + k * 128 + n), hi, lo);
+        const int o = canon_off(n, k, 128);
+        *reinterpret_cast<uint32_t*>(img + B1_W1HI + o) = hi;
+        *reinterpret_cast<uint32_t*>(img + B1_W1LO + o) = lo;
+    }
+    for (int e = gtid; e < 16 * 128; e += gsz) {          // B[n = c < 16][k = j] = w0[j][c] (c < 12), zero padding rows
+        const int n = e / 128, k = e % 128;
+        uint32_t hi, lo;
+        split_tf32(n < 12 ? __ldg(net + OFF_W0 + k * 39 + n) : 0.f, hi, lo);
+        const int o = canon_off(n, k, 128);
+        *reinterpret_cast<uint32_t*>(img + B1_W0HI + o) = hi;
+        *reinterpret_cast<uint32_t*>(img + B1_W0LO + o) = lo;
+    }
+    for (int e = gtid; e < 3 * 128; e += gsz) reinterpret_cast<float*>(img + B1_W2)[e] = __ldg(net + OFF_W2 + e);
+}
+
 // tcgen05.ld of 8 columns
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

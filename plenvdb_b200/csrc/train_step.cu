@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int CNT_M_ALPHA = 0, CNT_M_KEEP = 1, CNT_N_TOUCHED_DEN = 2, CNT_OVERFLOW = 3, CNT_N_TOUCHED_K0 = 4, CNT_RAY_TICKET = 5;
+constexpr int CNT_M_ALPHA = 0, CNT_M_KEEP = 1, CNT_N_TOUCHED_DEN = 2, CNT_OVERFLOW = 3, CNT_N_TOUCHED_K0 = 4, CNT_RAY_TICKET = 5, CNT_CTA_DONE = 6;
 
 struct MarchParams {
     pvdb_tree tree;
@@ -338,52 +338,77 @@ __global__ void __launch_bounds__(256) k_hit_mask(MarchParams P, const float* __
     if (lane == 0) hit[r] = any ? 1 : 0;
 }
 
-// Exclusive scans of the two per-ray counts -> segment offsets in ray order.  One CTA of 32 warps: warp w owns the
-// contiguous run [w*n/32, (w+1)*n/32) and walks it 32 rays at a time (coalesced loads, shuffle scan, running carry);
-// the 32 run totals are scanned by warp 0 and added in a second sweep.
+// Exclusive scans of the two per-ray counts -> segment offsets in ray order.  One CTA, one pass: each thread owns 8
+// consecutive rays (two 16-byte loads per array), scans them in registers, then warp shuffle scan + a 32-entry block scan;
+// batches of 8192 rays are chained through a running carry.  Also clears the per-step accumulators of the kernels that
+// follow (loss sums, touched-leaf counts, tickets), which saves two memsets in the stream.
 __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck,
                                                       int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
-                                                      int32_t* __restrict__ counters, int64_t cap_alpha, int64_t cap_keep) {
+                                                      int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha,
+                                                      int64_t cap_keep) {
     __shared__ int2 wtot[32];
+    __shared__ int2 carry_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int per = ((n + 31) / 32 + 31) & ~31;          // rays per warp, multiple of 32
-    const int lo = min(n, wid * per), hi = min(n, lo + per);
-    int2 carry = make_int2(0, 0);
-    for (int base = lo; base < hi; base += 32) {
-        const int i = base + lane;
-        const int2 own = i < hi ? make_int2(ca[i], ck[i]) : make_int2(0, 0);
-        int2 v = own;
+    if (threadIdx.x == 0) carry_s = make_int2(0, 0);
+    if (threadIdx.x < 4) loss[threadIdx.x] = 0.f;
+    __syncthreads();
+    for (int base = 0; base < n; base += 8192) {
+        const int i0 = base + threadIdx.x * 8;
+        int a[8], k[8];
+        if (i0 + 8 <= n) {
+            const int4 a0 = *reinterpret_cast<const int4*>(ca + i0), a1 = *reinterpret_cast<const int4*>(ca + i0 + 4);
+            const int4 k0 = *reinterpret_cast<const int4*>(ck + i0), k1 = *reinterpret_cast<const int4*>(ck + i0 + 4);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] = i0 + j < n ? ca[i0 + j] : 0; k[j] = i0 + j < n ? ck[i0 + j] : 0; }
+        }
+        int2 tot = make_int2(0, 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int ta = a[j], tk = k[j]; a[j] = tot.x; k[j] = tot.y; tot.x += ta; tot.y += tk; }   // exclusive in-thread
+        int2 v = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int ux = __shfl_up_sync(0xffffffffu, v.x, o), uy = __shfl_up_sync(0xffffffffu, v.y, o);
             if (lane >= o) { v.x += ux; v.y += uy; }
         }
-        if (i < hi) { oa[i] = carry.x + v.x - own.x; ok[i] = carry.y + v.y - own.y; }   // exclusive within the warp's run
-        carry.x += __shfl_sync(0xffffffffu, v.x, 31);
-        carry.y += __shfl_sync(0xffffffffu, v.y, 31);
-    }
-    if (lane == 0) wtot[wid] = carry;
-    __syncthreads();
-    if (wid == 0) {
-        const int2 own = wtot[lane];
-        int2 w = own;
+        if (lane == 31) wtot[wid] = v;
+        __syncthreads();
+        const int2 carry = carry_s;
+        if (wid == 0) {
+            const int2 own = wtot[lane];
+            int2 w = own;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int ux = __shfl_up_sync(0xffffffffu, w.x, o), uy = __shfl_up_sync(0xffffffffu, w.y, o);
-            if (lane >= o) { w.x += ux; w.y += uy; }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ux = __shfl_up_sync(0xffffffffu, w.x, o), uy = __shfl_up_sync(0xffffffffu, w.y, o);
+                if (lane >= o) { w.x += ux; w.y += uy; }
+            }
+            wtot[lane] = make_int2(w.x - own.x, w.y - own.y);   // exclusive prefix of each warp
+            if (lane == 31) carry_s = make_int2(carry.x + w.x, carry.y + w.y);
         }
-        wtot[lane] = make_int2(w.x - own.x, w.y - own.y);   // exclusive prefix of each warp's run
-        if (lane == 31) {
-            oa[n] = w.x; ok[n] = w.y;
-            counters[CNT_M_ALPHA] = w.x; counters[CNT_M_KEEP] = w.y;
-            counters[CNT_OVERFLOW] = (w.x > cap_alpha || w.y > cap_keep) ? 1 : 0;
-            counters[CNT_N_TOUCHED_DEN] = 0; counters[CNT_N_TOUCHED_K0] = 0; counters[CNT_RAY_TICKET] = 0;
+        __syncthreads();
+        const int2 pre = wtot[wid];
+        const int px = carry.x + pre.x + v.x - tot.x, py = carry.y + pre.y + v.y - tot.y;   // exclusive prefix of this thread
+        if (i0 + 8 <= n) {
+            *reinterpret_cast<int4*>(oa + i0) = make_int4(px + a[0], px + a[1], px + a[2], px + a[3]);
+            *reinterpret_cast<int4*>(oa + i0 + 4) = make_int4(px + a[4], px + a[5], px + a[6], px + a[7]);
+            *reinterpret_cast<int4*>(ok + i0) = make_int4(py + k[0], py + k[1], py + k[2], py + k[3]);
+            *reinterpret_cast<int4*>(ok + i0 + 4) = make_int4(py + k[4], py + k[5], py + k[6], py + k[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (i0 + j < n) { oa[i0 + j] = px + a[j]; ok[i0 + j] = py + k[j]; }
         }
+        __syncthreads();
     }
-    __syncthreads();
-    const int2 pre = wtot[wid];
-    if (pre.x | pre.y)
-        for (int i = lo + lane; i < hi; i += 32) { oa[i] += pre.x; ok[i] += pre.y; }
+    if (threadIdx.x == 0) {
+        const int2 w = carry_s;
+        oa[n] = w.x; ok[n] = w.y;
+        counters[CNT_M_ALPHA] = w.x; counters[CNT_M_KEEP] = w.y;
+        counters[CNT_OVERFLOW] = (w.x > cap_alpha || w.y > cap_keep) ? 1 : 0;
+        counters[CNT_N_TOUCHED_DEN] = 0; counters[CNT_N_TOUCHED_K0] = 0; counters[CNT_RAY_TICKET] = 0; counters[CNT_CTA_DONE] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -399,6 +424,7 @@ struct CompositeParams {
     float* k_gw;             // out: dL/dw per kept sample
     const float* alphainv_last; const float* target;
     float* rgb_marched; float* grad_last; float* loss;
+    int32_t* cta_done;       // zeroed by k_scan_counts; the last CTA to finish folds the three sums into loss[0]
     float bg, w_main, w_ent, w_per, inv_N;   // inv_N = 1/N_global
     int64_t cap_keep;
     int do_backward;
@@ -470,11 +496,16 @@ __global__ void __launch_bounds__(256) k_composite(CompositeParams C, int n_rays
         const float scale = threadIdx.x == 0 ? C.inv_N * (1.0f / 3.0f) : C.inv_N;
         atomicAdd(C.loss + 1 + threadIdx.x, s * scale);
     }
+    if (C.target) {   // last CTA out: total loss (run.py:551-574)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(C.cta_done, 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            const volatile float* L = C.loss;
+            C.loss[0] = C.w_main * L[1] + C.w_ent * L[2] + C.w_per * L[3];
+        }
+    }
 }
-__global__ void k_finish_loss(float* loss, float w_main, float w_ent, float w_per) {
-    loss[0] = w_main * loss[1] + w_ent * loss[2] + w_per * loss[3];
-}
-
 // ---------------------------------------------------------------------------------------------
 // B2 — per-ray reverse pass (alpha2weight_backward :654-677 + raw2alpha_backward :507-517).  One warp per ray: the
 // reference's sequential recurrence  back_cum += gw*w  is a suffix sum, evaluated here 32 samples at a time from the far
@@ -814,8 +845,8 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         }
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_count", st);
-        k_scan_counts<<<1, 1024, 0, st>>>(b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays, b->counters, b->cap_alpha,
-                                          b->cap_keep);
+        k_scan_counts<<<1, 1024, 0, st>>>(b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays, b->counters, b->loss,
+                                          b->cap_alpha, b->cap_keep);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("scan", st);
         PVDB_CHECK_ARG(!O.scratch || n_rays <= b->scratch_rays, "march_scratch holds fewer rays than this batch");
@@ -826,19 +857,14 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         int rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
         if (rc) return rc;
         pvdb_prof_mark("rgbnet_fwd", st);
-        PVDB_CUDA(cudaMemsetAsync(b->loss, 0, 4 * sizeof(float), st));
         CompositeParams C;
         C.off_keep = b->off_keep; C.k_sample = b->k_sample; C.s_weight = b->s_weight; C.k_rgb = b->k_rgb; C.k_gw = b->k_gw;
         C.alphainv_last = b->alphainv_last; C.target = target; C.rgb_marched = b->rgb_marched; C.grad_last = b->grad_last;
-        C.loss = b->loss; C.bg = cfg->bg; C.w_main = cfg->weight_main; C.w_ent = cfg->weight_entropy_last;
+        C.loss = b->loss; C.cta_done = b->counters + CNT_CTA_DONE; C.bg = cfg->bg; C.w_main = cfg->weight_main; C.w_ent = cfg->weight_entropy_last;
         C.w_per = cfg->weight_rgbper; C.inv_N = 1.0f / (float)n_glob; C.cap_keep = b->cap_keep; C.do_backward = do_bwd ? 1 : 0;
         k_composite<<<warp_grid, 256, 0, st>>>(C, n_rays);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("composite", st);
-        if (target) {
-            k_finish_loss<<<1, 1, 0, st>>>(b->loss, cfg->weight_main, cfg->weight_entropy_last, cfg->weight_rgbper);
-            PVDB_LAUNCH_CHECK();
-        }
     }
     if (do_bwd) {
         int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
