@@ -16,6 +16,7 @@ void pvdb_reset_launch_count();
 // launching stream after each kernel of a fused call; pvdb_profile_fetch() returns the elapsed ms between marks.
 void pvdb_prof_begin(cudaStream_t st);
 void pvdb_prof_mark(const char* name, cudaStream_t st);
+bool pvdb_prof_active();
 
 #define PVDB_CHECK_ARG(cond, msg)                 \
     do {                                          \

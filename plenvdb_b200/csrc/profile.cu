@@ -30,6 +30,8 @@ void pvdb_prof_mark(const char* name, cudaStream_t st) {
     ++g_n;
 }
 
+bool pvdb_prof_active() { return g_on; }
+
 extern "C" int pvdb_profile_enable(int on) {
     g_on = on != 0;
     if (!g_on) g_n = 0;

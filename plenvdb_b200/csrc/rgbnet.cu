@@ -368,10 +368,11 @@ constexpr size_t BWD_SMEM = (size_t)(W * W + W * KX + 3 * W + TS * 4 + TS * LDX 
 }  // namespace
 
 int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
+int pvdb_rgbnet_prep_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st);
 int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
 
 int pvdb_rgbnet_forward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
-    if (cfg->use_tensor_cores) return pvdb_rgbnet_forward_tc(cfg, b, viewdirs, st);
+    if (cfg->use_tensor_cores) return pvdb_rgbnet_forward_tc(cfg, b, viewdirs, st);   // after pvdb_rgbnet_prepare
     static bool attr_set = false;
     if (!attr_set) {
         PVDB_CUDA(cudaFuncSetAttribute(k_rgbnet_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
@@ -400,6 +401,12 @@ int pvdb_rgbnet_backward_fp32(const pvdb_train_cfg* cfg, const pvdb_train_bufs* 
     A.cap_keep = b->cap_keep;
     k_rgbnet_bwd<<<PVDB_SMS, NT, BWD_SMEM, st>>>(A);
     PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
+// Per-step preparation that does not depend on the samples (tensor-core path: weight images); a no-op for fp32.
+int pvdb_rgbnet_prepare(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st) {
+    if (cfg->use_tensor_cores) return pvdb_rgbnet_prep_tc(cfg, b, st);
     return PVDB_OK;
 }
 

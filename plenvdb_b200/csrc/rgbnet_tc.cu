@@ -453,6 +453,22 @@ extern "C" int pvdb_debug_tc_timing(long long* out) {
 }
 #endif
 
+// Weight images of the forward and of the activation-gradient kernel (independent of the march: the fused step runs it on
+// a side stream underneath the count pass).
+int pvdb_rgbnet_prep_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st) {
+    PVDB_CHECK_ARG(b->net_img, "net_img scratch missing (tensor-core rgbnet)");
+    const float* net = b->net;   // PyTorch layout: W[n][k] row-major
+    TcWeights W;
+    W.w0 = net + PVDB_NET_OFF_W0; W.w0_sn = PVDB_NET_DIN; W.w0_sk = 1;
+    W.w1 = net + PVDB_NET_OFF_W1; W.w1_sn = WD; W.w1_sk = 1;
+    W.w2 = net + PVDB_NET_OFF_W2; W.w2_sn = WD; W.w2_sk = 1;
+    W.b0 = net + PVDB_NET_OFF_B0; W.b1 = net + PVDB_NET_OFF_B1; W.b2 = net + PVDB_NET_OFF_B2;
+    k_prep_fwd_image<<<PVDB_SMS, 256, 0, st>>>(W, static_cast<unsigned char*>(b->net_img), b->net);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
+// Forward over the kept list; the weight images must be current (pvdb_rgbnet_prep_tc).
 int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -465,14 +481,6 @@ int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     A.k_h0 = b->k_h0; A.k_h1 = b->k_h1; A.k_rgb = b->k_rgb; A.k_x = b->k_x; A.k_mask = b->k_mask; A.counters = b->counters; A.cap_keep = b->cap_keep;
     A.k_corner = b->k_corner;
     A.img = static_cast<const unsigned char*>(b->net_img);
-    const float* net = b->net;   // PyTorch layout: W[n][k] row-major
-    TcWeights W;
-    W.w0 = net + PVDB_NET_OFF_W0; W.w0_sn = PVDB_NET_DIN; W.w0_sk = 1;
-    W.w1 = net + PVDB_NET_OFF_W1; W.w1_sn = WD; W.w1_sk = 1;
-    W.w2 = net + PVDB_NET_OFF_W2; W.w2_sn = WD; W.w2_sk = 1;
-    W.b0 = net + PVDB_NET_OFF_B0; W.b1 = net + PVDB_NET_OFF_B1; W.b2 = net + PVDB_NET_OFF_B2;
-    k_prep_fwd_image<<<PVDB_SMS, 256, 0, st>>>(W, static_cast<unsigned char*>(b->net_img), b->net);
-    PVDB_LAUNCH_CHECK();
     k_rgbnet_fwd_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;

@@ -829,9 +829,31 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
     fill_march(cfg, b, P, O);
     const int n_glob = cfg->n_rays_global > 0 ? cfg->n_rays_global : n_rays;
     const int warp_grid = pvdb_grid_for((int64_t)n_rays * 32, 256);
+    // Side stream for work that is independent of the main chain (weight-image prep under the march; the density branch of
+    // the backward under the rgbnet backward).  Not used while per-kernel profiling is on (serial, clean per-kernel times).
+    struct Side { cudaStream_t s; cudaEvent_t fork, join, fork2, join2; bool ok; };
+    static thread_local Side side[16] = {};
+    int dev = 0;
+    PVDB_CUDA(cudaGetDevice(&dev));
+    Side* sd = (dev >= 0 && dev < 16 && !pvdb_prof_active()) ? &side[dev] : nullptr;
+    if (sd && !sd->ok) {
+        PVDB_CUDA(cudaStreamCreateWithFlags(&sd->s, cudaStreamNonBlocking));
+        PVDB_CUDA(cudaEventCreateWithFlags(&sd->fork, cudaEventDisableTiming));
+        PVDB_CUDA(cudaEventCreateWithFlags(&sd->join, cudaEventDisableTiming));
+        PVDB_CUDA(cudaEventCreateWithFlags(&sd->fork2, cudaEventDisableTiming));
+        PVDB_CUDA(cudaEventCreateWithFlags(&sd->join2, cudaEventDisableTiming));
+        sd->ok = true;
+    }
 
     if (do_fwd) {
         PVDB_CHECK_ARG(rays_o && rays_d && viewdirs, "null rays");
+        if (sd) {
+            PVDB_CUDA(cudaEventRecord(sd->fork2, st));
+            PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));
+            int rc = pvdb_rgbnet_prepare(cfg, b, sd->s);
+            if (rc) return rc;
+            PVDB_CUDA(cudaEventRecord(sd->join2, sd->s));
+        }
         if (cfg->parity_counts) {
             k_march<0, true><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
         } else {
@@ -854,7 +876,14 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         else k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
-        int rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
+        int rc;
+        if (sd) {
+            PVDB_CUDA(cudaStreamWaitEvent(st, sd->join2, 0));
+        } else {
+            rc = pvdb_rgbnet_prepare(cfg, b, st);
+            if (rc) return rc;
+        }
+        rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
         if (rc) return rc;
         pvdb_prof_mark("rgbnet_fwd", st);
         CompositeParams C;
@@ -867,19 +896,34 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         pvdb_prof_mark("composite", st);
     }
     if (do_bwd) {
-        int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
-        if (rc) return rc;
-        pvdb_prof_mark(cfg->use_tensor_cores ? "rgbnet_bwd_wgrad" : "rgbnet_bwd", st);
-        k_ray_bwd<<<warp_grid, 256, 0, st>>>(b->off_alpha, b->off_keep, b->s_alpha, b->s_T, b->s_weight, b->s_density,
+        // The density branch of the backward (ray recurrence -> density scatter) depends only on the composite, not on the
+        // rgbnet backward: it runs on a side stream underneath the two tcgen05 kernels (which leave most thread slots of
+        // every SM free) and joins before the update.  Serial when per-kernel profiling is on.
+        cudaStream_t sb = sd ? sd->s : st;
+        if (sd) {
+            PVDB_CUDA(cudaEventRecord(sd->fork, st));
+            PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork, 0));
+        } else {
+            int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
+            if (rc) return rc;
+            pvdb_prof_mark(cfg->use_tensor_cores ? "rgbnet_bwd_wgrad" : "rgbnet_bwd", st);
+        }
+        k_ray_bwd<<<warp_grid, 256, 0, sb>>>(b->off_alpha, b->off_keep, b->s_alpha, b->s_T, b->s_weight, b->s_density,
                                                              b->k_gw, b->alphainv_last, b->grad_last, b->s_gden, n_rays,
                                                              cfg->fast_color_thres, cfg->act_shift, cfg->interval, b->cap_alpha,
                                                              b->cap_keep);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("ray_bwd", st);
-        k_density_scatter<<<PVDB_SMS * 8, 256, 0, st>>>(*b->tree, b->den_grad, b->s_xyz, b->s_gden, b->counters, b->den_touched,
+        k_density_scatter<<<PVDB_SMS * 8, 256, 0, sb>>>(*b->tree, b->den_grad, b->s_xyz, b->s_gden, b->counters, b->den_touched,
                                                         b->den_touched_list, b->counters, b->cap_alpha);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("density_scatter", st);
+        if (sd) {
+            PVDB_CUDA(cudaEventRecord(sd->join, sd->s));
+            int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
+            if (rc) return rc;
+            PVDB_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
+        }
     }
     if (do_upd) {
         UpdateArgs U;
