@@ -198,17 +198,19 @@ def run_ours(args):
     warm_ms = e0.elapsed_time(e1) / K
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + step + D2H(loss) inside the timed region
-    hro, hrd, hvd, htg = (x[Wm:].cpu().pin_memory() for x in (ro, rd, vd, tg))
-    dro, drd, dvd, dtg = (torch.empty_like(ro[0]) for _ in range(4))
+    hbatch = torch.stack([x[Wm:].cpu() for x in (ro, rd, vd, tg)], 1).contiguous().pin_memory()   # [K, 4, n, 3]
+    dstage = torch.empty_like(hbatch[0], device=dev)
     hloss = torch.empty(4, dtype=torch.float32).pin_memory()
     barrier()
     e0.record()
     for i in range(K):
-        dro.copy_(hro[i], non_blocking=True); drd.copy_(hrd[i], non_blocking=True)
-        dvd.copy_(hvd[i], non_blocking=True); dtg.copy_(htg[i], non_blocking=True)
-        stepper(dro, drd, dvd, dtg)
-        hloss.copy_(tr.t["loss"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()     # the caller reads the loss every iteration
+        if world == 1:
+            tr.step_from_host(hbatch[i])              # one H2D, the step, D2H of the loss, stream sync (the caller reads it)
+        else:
+            dstage.copy_(hbatch[i], non_blocking=True)
+            stepper(dstage[0], dstage[1], dstage[2], dstage[3])
+            hloss.copy_(tr.t["loss"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
