@@ -93,7 +93,10 @@ class FusedTrainer:
 
     # ---- state
     def set_mask(self, mask):
-        m = torch.as_tensor(np.ascontiguousarray(np.asarray(mask).astype(np.uint8))).to(self.dev)
+        if torch.is_tensor(mask):
+            m = mask.to(self.dev, torch.uint8).contiguous()
+        else:
+            m = torch.as_tensor(np.ascontiguousarray(np.asarray(mask).astype(np.uint8))).to(self.dev)
         self.mask_shape = tuple(m.shape)
         nb = [(s + 7) // 8 for s in self.mask_shape]
         nblk = nb[0] * nb[1] * nb[2]
@@ -226,3 +229,45 @@ def build_scene_grids(scene, device="cuda"):
     den.copyFromDense_torch(torch.from_numpy(scene["density"]))
     k0.copyFromDense_torch(torch.from_numpy(scene["k0"]))
     return den, k0
+
+
+def build_stress_scene(reso=512, device="cuda", bound=1.3, seed=6):
+    """SURVEY.md §8(d) cfg 5 (S512): noisy thick shell (~5 % of the voxels) on a PRUNED topology, built on the device — the
+    dense host arrays synth.make_scene works with would be 6.4 GB at 512^3.  Same formulas as synth.shell_occupancy /
+    make_scene (occupancy, N(6,1) density inside / -10 outside, U(-1,1) k0 on the dilated occupancy, mask = 3^3 max-pool),
+    torch RNG instead of numpy's.  Returns (params, density grid, k0 grid, mask [reso^3] uint8 cuda)."""
+    from . import synth
+    dev = torch.device(device)
+    P = synth.scene_params(reso, bound=bound)
+    R = reso
+    ax = torch.linspace(-bound, bound, R, dtype=torch.float64, device=dev)
+    X, Y, Z = ax.view(R, 1, 1), ax.view(1, R, 1), ax.view(1, 1, R)
+    ph = torch.from_numpy(np.random.default_rng(seed).uniform(0, 2 * np.pi, (4, 3))).to(dev)
+    r = torch.sqrt(X ** 2 + Y ** 2 + Z ** 2)
+    noise = torch.zeros((R, R, R), dtype=torch.float64, device=dev)
+    for k in range(4):
+        f = (2 ** k) * 3.0
+        noise += 0.5 ** k * torch.sin(f * X + ph[k, 0]) * torch.sin(f * Y + ph[k, 1]) * torch.sin(f * Z + ph[k, 2])
+    occ = (r - 0.8 - 0.06 * noise).abs() <= 0.022
+    del noise, r
+    mask = torch.nn.functional.max_pool3d(occ[None, None].to(torch.float16), 3, 1, 1)[0, 0] > 0
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    dens = torch.full((R, R, R), -10.0, dtype=torch.float32, device=dev)
+    dens[occ] = 6.0 + torch.randn(int(occ.sum()), generator=g, device=dev)
+    den = DensityVDB.__new__(DensityVDB)      # skip the dense-fill topology of the constructor (262 144 leaves at 512^3)
+    den.num, den.reso, den.ndim, den.device, den.timer = 1, [R, R, R], 1, dev, 0.0
+    den._set_topology(Topology.from_mask(mask.cpu().numpy(), device=device))   # pruned: leaves where the mask has voxels
+    k0 = ColorVDB.__new__(ColorVDB)
+    k0.num, k0.reso, k0.ndim, k0.device, k0.timer = 4, [R, R, R], 12, dev, 0.0
+    k0._set_topology(den.topo)
+    dens[~mask] = 0.0            # outside the tree: background
+    den.copyFromDense_torch(dens)
+    del dens
+    g.manual_seed(2)
+    k0d = torch.zeros((R, R, R, 12), dtype=torch.float32, device=dev)
+    k0d[mask] = torch.rand((int(mask.sum()), 12), generator=g, device=dev) * 2 - 1
+    k0.copyFromDense_torch(k0d)
+    del k0d
+    P.update(variant="pruned", occupied_fraction=float(occ.float().mean()), n_leaf=den.topo.n_leaf)
+    return P, den, k0, mask.to(torch.uint8)

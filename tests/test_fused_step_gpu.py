@@ -173,3 +173,49 @@ def test_emit_by_compaction_equals_second_march(scratch_per_ray, small):
     for k in ("k_sample", "k_ray", "k_xyz", "k_corner", "k_rgb"):
         assert torch.equal(ref.t[k][:mk], alt.t[k][:mk]), k
     assert torch.equal(ref.t["rgb_marched"], alt.t["rgb_marched"])
+
+
+def test_stress_scene_properties():
+    """Shell scene on a pruned topology built on the device (the S512 configuration of SURVEY.md §8d at 192^3 so that it runs
+    in seconds), inverse_y cameras.  No oracle at this size: size-independent properties instead —
+    determinism (two trainers give bit-identical lists), ray-ordered segments, sum of weights + T_last = 1 per ray,
+    kept subset of alpha list, and the emit-by-compaction path equals the second march."""
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import FusedTrainer, build_stress_scene
+    P, den, k0, mask = build_stress_scene(192)
+    assert 0.01 < P["occupied_fraction"] < 0.12 and den.topo.n_leaf < (192 // 8) ** 3
+    net = synth.rgbnet_init()
+    rng = np.random.default_rng(7)
+    n = 4096
+    K = np.array([[400.0, 0, 192.0], [0, 400.0, 144.0], [0, 0, 1]], np.float32)
+    poses = np.stack([synth.pose_spherical(rng.uniform(-180, 180), rng.uniform(-90, 0), rng.uniform(2.5, 3.5)) for _ in range(16)])
+    poses[:, :3, 1:3] *= -1      # inverse_y (OpenCV-style) cameras look along +z
+    cam = rng.integers(0, 16, n)
+    px, py = rng.integers(0, 384, n), rng.integers(0, 288, n)
+    ro, rd, vd = synth.rays_of_pixels(K, poses[cam], px, py, inverse_y=True)
+    tg = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    rays = [_cu(a) for a in (ro, rd, vd, tg)]
+    trs = [FusedTrainer(P, den, k0, mask, net, n, scratch_per_ray=spr) for spr in (128, 128, 0)]
+    for tr in trs:
+        tr.run(*rays, 3)
+    torch.cuda.synchronize()
+    c = trs[0].counters()
+    ma, mk = c["M_alpha"], c["M_keep"]
+    assert ma > 2000 and mk > 1000 and c["overflow"] == 0
+    for other in trs[1:]:
+        assert other.counters()["M_alpha"] == ma and other.counters()["M_keep"] == mk
+        for k in ("s_ray", "s_step", "s_xyz", "s_alpha", "s_T", "s_weight", "k_sample", "k_corner", "off_alpha", "off_keep"):
+            m = ma if k.startswith("s_") else mk if k.startswith("k_") else n + 1
+            assert torch.equal(trs[0].t[k][:m], other.t[k][:m]), k
+    t = trs[0].t
+    s_ray = t["s_ray"][:ma].long()
+    assert bool((s_ray[1:] >= s_ray[:-1]).all())                                   # ray order
+    off = t["off_alpha"][:n + 1].long()
+    assert bool((torch.bincount(s_ray, minlength=n) == off[1:] - off[:-1]).all())   # segments match the counts
+    wsum = torch.zeros(n, device="cuda").index_add_(0, s_ray, t["s_weight"][:ma])
+    np.testing.assert_allclose((wsum + t["alphainv_last"][:n]).cpu().numpy(), 1.0, atol=2e-5)   # transmittance partition
+    ks = t["k_sample"][:mk].long()
+    assert bool((ks[1:] > ks[:-1]).all()) and int(ks.max()) < ma                     # kept list = ordered subset
+    assert bool((t["s_weight"][:ma][ks] > P["fast_color_thres"]).all())
+    rgb = t["rgb_marched"][:n]
+    assert bool(torch.isfinite(rgb).all()) and float(rgb.min()) >= -1e-5 and float(rgb.max()) <= 1.0 + 1e-5
