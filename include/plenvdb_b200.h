@@ -253,6 +253,23 @@ int pvdb_dp_symm_close(void* ptr);
 int pvdb_dp_symm_free(void* ptr);
 int pvdb_dp_symm_error(const pvdb_dp_peers* peers, int32_t* err_out);
 int pvdb_dp_exchange(const pvdb_dp_peers* peers, const pvdb_train_bufs* bufs, uint32_t step, void* stream);
+/* ---- grid maintenance on the device: the reference does each through dense host arrays ----------
+ * scale_volume_grid (plenvdb/lib/grid.py:91-101): trilinear resample (F.interpolate, align_corners=True) of the dense view
+ * of (src_tree, src_plane) at resolution s* into the ACTIVE voxels of (dst_tree, dst_plane) at resolution d*. */
+int pvdb_resample_trilinear(const pvdb_tree* src_tree, const float* src_plane, int channels, int sx, int sy, int sz,
+                            const pvdb_tree* dst_tree, float* dst_plane, int dx, int dy, int dz, void* stream);
+/* Re-sparsification: every voxel slot of dst takes the value stored at the same coordinates in src (0 where src has no leaf). */
+int pvdb_plane_remap(const pvdb_tree* src_tree, const float* src_plane, const pvdb_tree* dst_tree, float* dst_plane, int channels,
+                     void* stream);
+/* update_occupancy_cache (plenvdb/lib/dvgo.py:201-210): mask &= maxpool3(raw2alpha(density(mask voxel centres))) > thres.
+ * mask: device uint8 [mx*my*mz]; alpha_tmp: device float scratch of the same count; xyz_min/xyz_max: HOST float[3]. */
+int pvdb_occupancy_update(const pvdb_tree* tree, const float* den_plane, int rx, int ry, int rz, const float* xyz_min,
+                          const float* xyz_max, float act_shift, float interval, float thres, uint8_t* mask, int mx, int my, int mz,
+                          float* alpha_tmp, void* stream);
+/* total_variation_add_grad (plenvdb/lib/cuda/total_variation_kernel.cu:14-35) on the sparse planes with the dense kernel's
+ * semantics (neighbours outside the tree read the background 0); dense_mode = 0 only touches voxels whose grad is non-zero. */
+int pvdb_total_variation_add_grad(const pvdb_tree* tree, const float* plane, float* grad, int channels, int rx, int ry, int rz,
+                                  float wx, float wy, float wz, int dense_mode, void* stream);
 /* hit_coarse_geo (plenvdb/lib/dvgo.py:253-270) for the 'in_maskcache' ray sampler: hit[r] = 1 iff some in-bbox sample
  * of ray r lands in an occupied voxel.  Uses cfg's scene scalars and bufs->occ_*. */
 int pvdb_rays_hit_mask(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs, const float* rays_o, const float* rays_d,

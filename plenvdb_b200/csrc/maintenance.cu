@@ -1,0 +1,178 @@
+// maintenance.cu — grid maintenance operations that sit either side of the hot loop, on the
+// device and on the sparse planes directly; the reference round-trips dense numpy arrays through the host for each:
+//   M1 resample    VDBGrid.scale_volume_grid (plenvdb/lib/grid.py:91-101): F.interpolate(trilinear, align_corners=True)
+//                  of the dense view, copied into a grid of the new resolution
+//   M2 remap       carry a payload plane over to another topology (re-sparsification: drop leaves whose mask is all false)
+//   M3 occupancy   DirectVoxGO.update_occupancy_cache (plenvdb/lib/dvgo.py:201-210): density at the mask voxel centres ->
+//                  raw2alpha -> 3^3 max-pool -> mask &= alpha > thres
+//   M4 TV          total_variation_add_grad (plenvdb/lib/cuda/total_variation_kernel.cu:14-35) with the dense kernel's
+//                  semantics evaluated on the leaf tiles: neighbours outside the tree read the background 0
+#include "common.cuh"
+#include "ray_math.cuh"
+
+namespace {
+
+__device__ __forceinline__ float value_at(const pvdb_tree& t, const float* __restrict__ plane, int C, int c, int x, int y, int z) {
+    const int leaf = pvdb_find_leaf(t, x, y, z);
+    return leaf >= 0 ? __ldg(plane + ((size_t)leaf * 512 + pvdb_leaf_off(x, y, z)) * C + c) : 0.f;
+}
+
+// ATen upsample_trilinear3d, align_corners=True: src = dst * (in-1)/(out-1); i1 = i0 + (i0 < in-1); l1 = src - i0.
+struct Lin { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lin lin_of(int dst, int in, int out) {
+    const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    const float src = scale * (float)dst;
+    Lin L;
+    L.i0 = (int)src;
+    L.i1 = L.i0 + (L.i0 < in - 1 ? 1 : 0);
+    L.l1 = src - (float)L.i0;
+    L.l0 = 1.f - L.l1;
+    return L;
+}
+
+__global__ void __launch_bounds__(256) k_resample(pvdb_tree ts, const float* __restrict__ src, int C, int sx, int sy, int sz, pvdb_tree td,
+                                                  float* __restrict__ dst, int dx, int dy, int dz) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)td.n_leaf * 512 * C) return;
+    const int64_t vox = idx / C;
+    const int c = (int)(idx - vox * C);
+    const int leaf = (int)(vox >> 9), off = (int)(vox & 511);
+    if (!pvdb_mask_bit(td.leaf_mask, leaf, off)) return;
+    const int x = td.leaf_origin[leaf * 3] + (off >> 6), y = td.leaf_origin[leaf * 3 + 1] + ((off >> 3) & 7), z = td.leaf_origin[leaf * 3 + 2] + (off & 7);
+    if (x >= dx || y >= dy || z >= dz) return;
+    const Lin X = lin_of(x, sx, dx), Y = lin_of(y, sy, dy), Z = lin_of(z, sz, dz);
+    auto v = [&](int a, int b, int cc) { return value_at(ts, src, C, c, a, b, cc); };
+    dst[idx] = X.l0 * (Y.l0 * (Z.l0 * v(X.i0, Y.i0, Z.i0) + Z.l1 * v(X.i0, Y.i0, Z.i1)) + Y.l1 * (Z.l0 * v(X.i0, Y.i1, Z.i0) + Z.l1 * v(X.i0, Y.i1, Z.i1))) +
+               X.l1 * (Y.l0 * (Z.l0 * v(X.i1, Y.i0, Z.i0) + Z.l1 * v(X.i1, Y.i0, Z.i1)) + Y.l1 * (Z.l0 * v(X.i1, Y.i1, Z.i0) + Z.l1 * v(X.i1, Y.i1, Z.i1)));
+}
+
+__global__ void __launch_bounds__(256) k_remap(pvdb_tree ts, const float* __restrict__ src, pvdb_tree td, float* __restrict__ dst, int C) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)td.n_leaf * 512 * C) return;
+    const int64_t vox = idx / C;
+    const int c = (int)(idx - vox * C);
+    const int leaf = (int)(vox >> 9), off = (int)(vox & 511);
+    const int x = td.leaf_origin[leaf * 3] + (off >> 6), y = td.leaf_origin[leaf * 3 + 1] + ((off >> 3) & 7), z = td.leaf_origin[leaf * 3 + 2] + (off & 7);
+    dst[idx] = value_at(ts, src, C, c, x, y, z);
+}
+
+// alpha at the mask voxel centres: torch.linspace(xyz_min, xyz_max, m) -> wld2idx -> D1 trilinear -> raw2alpha
+__device__ __forceinline__ float linspace_at(float lo, float hi, int steps, int i) {
+    // ATen linspace: step = (end - start) / (steps - 1); the lower half counts up from start, the upper half down from end
+    if (steps == 1) return lo;
+    const float step = (hi - lo) / (float)(steps - 1);
+    return i < steps / 2 ? lo + step * (float)i : hi - step * (float)(steps - 1 - i);
+}
+__global__ void __launch_bounds__(256) k_occ_alpha(pvdb_tree t, const float* __restrict__ den, int rx, int ry, int rz, int mx, int my, int mz,
+                                                   float x0, float y0, float z0, float x1, float y1, float z1, float act_shift, float interval,
+                                                   float* __restrict__ alpha) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)mx * my * mz) return;
+    const int k = (int)(idx % mz), j = (int)((idx / mz) % my), i = (int)(idx / ((int64_t)mz * my));
+    const float x = pvdb_wld2idx(linspace_at(x0, x1, mx, i), x0, x1, (float)(rx - 1));
+    const float y = pvdb_wld2idx(linspace_at(y0, y1, my, j), y0, y1, (float)(ry - 1));
+    const float z = pvdb_wld2idx(linspace_at(z0, z1, mz, k), z0, z1, (float)(rz - 1));
+    PvdbTri tri;
+    tri.set(x, y, z);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+        const float v = value_at(t, den, 1, 0, tri.i + dx, tri.j + dy, tri.k + dz);
+        acc = __fmaf_rn(tri.f(2, dz), __fmul_rn(tri.f(1, dy), __fmul_rn(tri.f(0, dx), v)), acc);
+    }
+    float e;
+    alpha[idx] = pvdb_raw2alpha(acc, act_shift, interval, e);
+}
+__global__ void __launch_bounds__(256) k_occ_pool_and(const float* __restrict__ alpha, int mx, int my, int mz, float thres, uint8_t* __restrict__ mask) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)mx * my * mz) return;
+    if (!mask[idx]) return;
+    const int k = (int)(idx % mz), j = (int)((idx / mz) % my), i = (int)(idx / ((int64_t)mz * my));
+    float m = -INFINITY;   // max_pool3d pads with -inf
+    for (int a = max(i - 1, 0); a <= min(i + 1, mx - 1); ++a)
+        for (int b = max(j - 1, 0); b <= min(j + 1, my - 1); ++b)
+            for (int c = max(k - 1, 0); c <= min(k + 1, mz - 1); ++c) m = fmaxf(m, alpha[((int64_t)a * my + b) * mz + c]);
+    mask[idx] = m > thres ? 1 : 0;
+}
+
+__device__ __forceinline__ float clamp1(float v) { return fminf(fmaxf(v, -1.f), 1.f); }
+template <bool DENSE>
+__global__ void __launch_bounds__(256) k_tv_add_grad(pvdb_tree t, const float* __restrict__ plane, float* __restrict__ grad, int C, int rx, int ry,
+                                                     int rz, float wx, float wy, float wz) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)t.n_leaf * 512 * C) return;
+    const int64_t vox = idx / C;
+    const int c = (int)(idx - vox * C);
+    const int leaf = (int)(vox >> 9), off = (int)(vox & 511);
+    const int x = t.leaf_origin[leaf * 3] + (off >> 6), y = t.leaf_origin[leaf * 3 + 1] + ((off >> 3) & 7), z = t.leaf_origin[leaf * 3 + 2] + (off & 7);
+    if (x >= rx || y >= ry || z >= rz) return;           // padding voxels of boundary leaves are not part of the dense grid
+    if (!DENSE && grad[idx] == 0.f) return;
+    const float p = plane[idx];
+    // neighbours inside this leaf are read directly; across a leaf face through the tree (background 0 where no leaf is)
+    auto nb = [&](int ax, int d) -> float {
+        const int lx = off >> 6, ly = (off >> 3) & 7, lz = off & 7;
+        const int l = ax == 0 ? lx : ax == 1 ? ly : lz;
+        if ((unsigned)(l + d) < 8u) return plane[idx + (int64_t)d * (ax == 0 ? 64 : ax == 1 ? 8 : 1) * C];
+        return value_at(t, plane, C, c, x + (ax == 0 ? d : 0), y + (ax == 1 ? d : 0), z + (ax == 2 ? d : 0));
+    };
+    float g = 0.f;   // same accumulation order as the dense kernel: k-, k+, j-, j+, i-, i+
+    g += z == 0 ? 0.f : wz * clamp1(p - nb(2, -1));
+    g += z == rz - 1 ? 0.f : wz * clamp1(p - nb(2, 1));
+    g += y == 0 ? 0.f : wy * clamp1(p - nb(1, -1));
+    g += y == ry - 1 ? 0.f : wy * clamp1(p - nb(1, 1));
+    g += x == 0 ? 0.f : wx * clamp1(p - nb(0, -1));
+    g += x == rx - 1 ? 0.f : wx * clamp1(p - nb(0, 1));
+    grad[idx] += g;
+}
+
+}  // namespace
+
+extern "C" int pvdb_resample_trilinear(const pvdb_tree* src_tree, const float* src_plane, int channels, int sx, int sy, int sz,
+                                       const pvdb_tree* dst_tree, float* dst_plane, int dx, int dy, int dz, void* stream) {
+    PVDB_CHECK_ARG(src_tree && src_plane && dst_tree && dst_plane && channels > 0, "bad arguments");
+    PVDB_CHECK_ARG(sx > 0 && sy > 0 && sz > 0 && dx > 0 && dy > 0 && dz > 0, "bad resolution");
+    if (dst_tree->n_leaf == 0) return PVDB_OK;
+    const int64_t total = (int64_t)dst_tree->n_leaf * 512 * channels;
+    k_resample<<<pvdb_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*src_tree, src_plane, channels, sx, sy, sz, *dst_tree, dst_plane, dx, dy, dz);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_plane_remap(const pvdb_tree* src_tree, const float* src_plane, const pvdb_tree* dst_tree, float* dst_plane, int channels,
+                                void* stream) {
+    PVDB_CHECK_ARG(src_tree && src_plane && dst_tree && dst_plane && channels > 0, "bad arguments");
+    if (dst_tree->n_leaf == 0) return PVDB_OK;
+    const int64_t total = (int64_t)dst_tree->n_leaf * 512 * channels;
+    k_remap<<<pvdb_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*src_tree, src_plane, *dst_tree, dst_plane, channels);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_occupancy_update(const pvdb_tree* tree, const float* den_plane, int rx, int ry, int rz, const float* xyz_min,
+                                     const float* xyz_max, float act_shift, float interval, float thres, uint8_t* mask, int mx, int my, int mz,
+                                     float* alpha_tmp, void* stream) {
+    PVDB_CHECK_ARG(tree && den_plane && xyz_min && xyz_max && mask && alpha_tmp, "null pointer");
+    const int64_t total = (int64_t)mx * my * mz;
+    if (total == 0) return PVDB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_occ_alpha<<<pvdb_grid_for(total, 256), 256, 0, st>>>(*tree, den_plane, rx, ry, rz, mx, my, mz, xyz_min[0], xyz_min[1], xyz_min[2], xyz_max[0],
+                                                          xyz_max[1], xyz_max[2], act_shift, interval, alpha_tmp);
+    PVDB_LAUNCH_CHECK();
+    k_occ_pool_and<<<pvdb_grid_for(total, 256), 256, 0, st>>>(alpha_tmp, mx, my, mz, thres, mask);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_total_variation_add_grad(const pvdb_tree* tree, const float* plane, float* grad, int channels, int rx, int ry, int rz,
+                                             float wx, float wy, float wz, int dense_mode, void* stream) {
+    PVDB_CHECK_ARG(tree && plane && grad && channels > 0, "bad arguments");
+    if (tree->n_leaf == 0) return PVDB_OK;
+    const int64_t total = (int64_t)tree->n_leaf * 512 * channels;
+    if (dense_mode)
+        k_tv_add_grad<true><<<pvdb_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*tree, plane, grad, channels, rx, ry, rz, wx, wy, wz);
+    else
+        k_tv_add_grad<false><<<pvdb_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*tree, plane, grad, channels, rx, ry, rz, wx, wy, wz);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}

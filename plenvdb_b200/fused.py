@@ -108,6 +108,12 @@ class FusedTrainer:
         if getattr(self, "_bufs", None) is not None:
             self._build_structs()
 
+    def update_occupancy_cache(self):
+        """dvgo.py:201-210 on the device: prune the mask with the current density and rebuild the occupancy bits."""
+        from . import maintenance
+        maintenance.update_occupancy_cache(self.density, self.mask_dev, self.P)
+        self.set_mask(self.mask_dev)
+
     def _build_structs(self):
         P = self.P
         c = _lib.pvdb_train_cfg()

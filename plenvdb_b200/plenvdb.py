@@ -36,6 +36,18 @@ class _BaseVDB:
         self.grid = topo.new_plane(self.ndim)   # value plane  [n_leaf,512,ndim]
         self.grad = topo.new_plane(self.ndim)   # gradient plane
 
+    # ---- maintenance on the device (the reference composes these from dense host round trips)
+    def total_variation_add_grad(self, wx, wy, wz, dense_mode=True):
+        """grid.py:103-106 calls this name on the VDB object (and returns early because the reference lacks it)."""
+        from . import maintenance
+        maintenance.total_variation_add_grad(self, wx, wy, wz, dense_mode)
+
+    def scale_volume_grid(self, new_world_size):
+        """In-place form of VDBGrid.scale_volume_grid (grid.py:91-101): this object becomes the resampled dense-fill grid."""
+        from . import maintenance
+        new = maintenance.scale_volume_grid(self, new_world_size)
+        self.reso, self.topo, self.grid, self.grad = new.reso, new.topo, new.grid, new.grad
+
     # ---- info / timers (plenvdb.h:397-399, 423-428)
     def getndim(self):
         return self.ndim

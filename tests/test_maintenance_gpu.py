@@ -1,0 +1,98 @@
+"""Device-side grid maintenance against the torch ops the reference composes them from
+(plenvdb/lib/grid.py:91-101, plenvdb/lib/dvgo.py:201-210, plenvdb/lib/cuda/total_variation_kernel.cu:14-35).
+Floating point: 1e-5 relative (ATen's interpolation / libdevice exp vs ours differ in contraction), masks exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def grids():
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import build_scene_grids
+    scene = synth.make_scene(64, "sparse")
+    den, k0 = build_scene_grids(scene)
+    return scene, den, k0
+
+
+def test_scale_volume_grid_matches_interpolate(grids):
+    from plenvdb_b200 import maintenance as mt
+    scene, den, k0 = grids
+    for vdb, new in ((den, (80, 80, 80)), (k0, (72, 80, 96)), (den, (48, 48, 48))):
+        dense = vdb.get_dense_grid_torch()                                   # [R,R,R,C]
+        want = F.interpolate(dense.permute(3, 0, 1, 2)[None], size=new, mode="trilinear", align_corners=True)[0].permute(1, 2, 3, 0)
+        out = mt.scale_volume_grid(vdb, new)
+        assert out.reso == list(new) and out.topo.n_leaf == int(np.prod([(r + 7) // 8 for r in new]))
+        got = out.get_dense_grid_torch()
+        torch.testing.assert_close(got, want.contiguous(), rtol=1e-5, atol=1e-5)
+
+
+def test_resparsify_keeps_values_and_drops_leaves(grids):
+    from plenvdb_b200 import maintenance as mt
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import build_scene_grids
+    scene = synth.make_scene(64, "dense")
+    den, k0 = build_scene_grids(scene)
+    mom = torch.rand_like(k0.grid)
+    dense_k0, dense_m = k0.get_dense_grid_torch().clone(), k0.get_dense_grid_torch(mom).clone()
+    n_before = den.topo.n_leaf
+    keep = torch.from_numpy(scene["mask"]).cuda()
+    new, (mom2,) = mt.resparsify([den, k0], keep, extra_planes=[mom])
+    assert den.topo is new and k0.topo is new and 0 < new.n_leaf < n_before
+    got = k0.get_dense_grid_torch()
+    # voxels of kept leaves keep their values, everything else reads background 0
+    blocks = F.max_pool3d(keep[None, None].float(), 8, 8)[0, 0] > 0
+    in_leaf = blocks.repeat_interleave(8, 0).repeat_interleave(8, 1).repeat_interleave(8, 2)
+    assert torch.equal(got[in_leaf], dense_k0[in_leaf]) and float(got[~in_leaf].abs().max()) == 0.0
+    assert torch.equal(k0.get_dense_grid_torch(mom2)[in_leaf], dense_m[in_leaf])
+    assert float(k0.grad.abs().max()) == 0.0
+
+
+def test_update_occupancy_cache_matches_torch_composition(grids):
+    from plenvdb_b200 import maintenance as mt
+    scene, den, k0 = grids
+    R = 64
+    for m in (64, 48):
+        mask = torch.ones((m, m, m), dtype=torch.uint8, device="cuda")
+        mask[:4] = 0                                                       # already-false voxels stay false
+        lo, hi = torch.tensor(scene["xyz_min"]).cuda(), torch.tensor(scene["xyz_max"]).cuda()
+        ax = [torch.linspace(float(lo[a]), float(hi[a]), m, device="cuda") for a in range(3)]
+        xyz = torch.stack(torch.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+        pts = ((xyz - lo) / (hi - lo) * (R - 1)).t().contiguous()
+        dens = den.forward_torch(pts).reshape(m, m, m)
+        alpha = 1 - torch.pow(1 + torch.exp(dens + scene["act_shift"]), -scene["interval"])
+        pooled = F.max_pool3d(alpha[None, None], 3, 1, 1)[0, 0]
+        want = mask.bool() & (pooled > scene["fast_color_thres"])
+        got = mt.update_occupancy_cache(den, mask.clone(), scene).bool()
+        # alpha within 1e-6 of the threshold may legitimately land on either side (libdevice vs ATen exp/pow)
+        unsure = (pooled - scene["fast_color_thres"]).abs() < 1e-6
+        assert torch.equal(got[~unsure], want[~unsure]) and int(got.sum()) > 0 and not bool(got[:4].any())
+
+
+@pytest.mark.parametrize("dense_mode", [True, False])
+def test_total_variation_matches_dense_kernel_semantics(dense_mode, grids):
+    from plenvdb_b200 import maintenance as mt
+    scene, den, k0 = grids
+    for vdb, w in ((den, (0.3, 0.2, 0.1)), (k0, (0.05, 0.07, 0.11))):
+        vdb.grad.zero_()
+        g0 = torch.randn_like(vdb.grad) * (torch.rand_like(vdb.grad) > 0.5)      # half of the gradients exactly zero
+        vdb.grad.copy_(g0)
+        p = vdb.get_dense_grid_torch()                                          # [R,R,R,C], background 0 outside the tree
+        gd = vdb.get_dense_grid_torch(vdb.grad).clone()
+        add = torch.zeros_like(p)
+        for ax, wa in ((2, w[2]), (1, w[1]), (0, w[0])):                        # kernel order: k-, k+, j-, j+, i-, i+
+            d = torch.diff(p, dim=ax).clamp(-1, 1)                              # p[i+1] - p[i]
+            lo = [slice(None)] * 4; hi = [slice(None)] * 4
+            lo[ax], hi[ax] = slice(0, -1), slice(1, None)
+            add[tuple(hi)] += wa * d                                            # index: p[idx] - p[idx-1]
+            add[tuple(lo)] += wa * (-d)                                         # index: p[idx] - p[idx+1]
+        want = gd + (add if dense_mode else add * (gd != 0))
+        mt.total_variation_add_grad(vdb, *w, dense_mode=dense_mode)
+        got = vdb.get_dense_grid_torch(vdb.grad)
+        # compare on voxels covered by leaves (the dense view of the gradient is 0 elsewhere by construction)
+        cov = vdb.get_dense_grid_torch(torch.ones_like(vdb.grad)) > 0
+        torch.testing.assert_close(got[cov], want[cov], rtol=1e-5, atol=1e-6)
+        vdb.grad.zero_()
