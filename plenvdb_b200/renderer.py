@@ -35,10 +35,11 @@ def merge_grids(density, k0, mask):
 
 
 def save_merged(basepath, den, col, idx_dense):
-    """mergeddata.npz with fp16 `den`, `col` (vdb_compression.py:56-59) + the index grid (see vdbio for the container)."""
+    """mergeddata.npz with fp16 `den`, `col` (vdb_compression.py:56-59) + mergedidxs.vdb, a FloatGrid of 1-based row ids."""
     np.savez_compressed(os.path.join(basepath, "mergeddata"), den=den.cpu().numpy().astype(np.float16),
                         col=col.cpu().numpy().astype(np.float16))
-    np.save(os.path.join(basepath, "mergedidxs.vdb.npy"), idx_dense.cpu().numpy().astype(np.int32))
+    from . import vdbio
+    vdbio.save_dense_as_vdb(os.path.join(basepath, "mergedidxs.vdb"), idx_dense.cpu().numpy().astype(np.float32), name="density")
 
 
 class MGRenderer:
@@ -74,7 +75,11 @@ class MGRenderer:
 
     def load_data(self, den, col, vdb_path, N):
         """Reference signature (plenvdb.h:959-983): flat den [N], col [N*dcol], path of mergedidxs.vdb, N = rows."""
-        idx = np.load(vdb_path + ".npy") if os.path.exists(vdb_path + ".npy") else np.load(vdb_path)
+        from . import vdbio
+        if os.path.exists(vdb_path + ".npy"):            # round-1 interim files
+            idx = np.load(vdb_path + ".npy")
+        else:
+            idx = vdbio.load_vdb_as_dense(vdb_path, tuple(int(r) for r in self.cfg.reso) if self.flags[2] else None)
         self.load_data_dense(np.asarray(den, np.float32).reshape(-1)[:N], np.asarray(col, np.float32).reshape(N, self.dcol), idx)
 
     def load_params(self, w0, b0, w1, b1, w2, b2):
