@@ -253,6 +253,16 @@ int pvdb_dp_symm_close(void* ptr);
 int pvdb_dp_symm_free(void* ptr);
 int pvdb_dp_symm_error(const pvdb_dp_peers* peers, int32_t* err_out);
 int pvdb_dp_exchange(const pvdb_dp_peers* peers, const pvdb_train_bufs* bufs, uint32_t step, void* stream);
+/* The two independent halves of pvdb_dp_exchange: grid-gradient tiles (needs the k0 / density scatters) and the rgbnet
+ * gradients (needs the weight-gradient kernel). */
+int pvdb_dp_exchange_tiles(const pvdb_dp_peers* peers, const pvdb_train_bufs* bufs, uint32_t step, void* stream);
+int pvdb_dp_exchange_net(const pvdb_dp_peers* peers, const pvdb_train_bufs* bufs, uint32_t step, void* stream);
+/* One data-parallel iteration on this rank's ray shard (cfg->n_rays_global = rays of all ranks): forward, backward with
+ * the tile exchange running on an internal side stream UNDER the weight-gradient kernel, rgbnet-gradient exchange, update.
+ * Every rank must call it with the same dp_step (0,1,2,...). */
+int pvdb_train_step_dp(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs, const pvdb_dp_peers* peers, uint32_t dp_step,
+                       const float* rays_o, const float* rays_d, const float* viewdirs, const float* target, int n_rays,
+                       void* stream);
 /* ---- grid maintenance on the device: the reference does each through dense host arrays ----------
  * scale_volume_grid (plenvdb/lib/grid.py:91-101): trilinear resample (F.interpolate, align_corners=True) of the dense view
  * of (src_tree, src_plane) at resolution s* into the ACTIVE voxels of (dst_tree, dst_plane) at resolution d*. */

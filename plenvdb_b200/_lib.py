@@ -148,6 +148,10 @@ _SIGS = {
     "pvdb_dp_symm_free": (None, [c_ptr]),
     "pvdb_dp_symm_error": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(C.c_int32)]),
     "pvdb_dp_exchange": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(pvdb_train_bufs), C.c_uint32, c_ptr]),
+    "pvdb_dp_exchange_tiles": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(pvdb_train_bufs), C.c_uint32, c_ptr]),
+    "pvdb_dp_exchange_net": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(pvdb_train_bufs), C.c_uint32, c_ptr]),
+    "pvdb_train_step_dp": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), C.POINTER(pvdb_dp_peers), C.c_uint32,
+                                  c_ptr, c_ptr, c_ptr, c_ptr, _i, c_ptr]),
     "pvdb_resample_trilinear": (None, [_TP, c_ptr, _i, _i, _i, _i, _TP, c_ptr, _i, _i, _i, c_ptr]),
     "pvdb_plane_remap": (None, [_TP, c_ptr, _TP, c_ptr, _i, c_ptr]),
     "pvdb_occupancy_update": (None, [_TP, c_ptr, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f, _f, _f, c_ptr, _i, _i, _i, c_ptr, c_ptr]),

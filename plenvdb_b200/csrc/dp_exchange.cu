@@ -1,44 +1,56 @@
 // dp_exchange.cu — data-parallel gradient exchange over NVLink peer memory (the reference is single-GPU,
 // so this has no counterpart there).  Each rank owns one "symmetric block" (cudaMalloc + CUDA IPC, mapped by every peer):
 //
-//   [0,256)      signal[src]      u32, monotone epoch written by rank `src` (st.release.sys), polled by the owner
-//   [256,512)    err, done_ctas
+//   [0,448)      signal words, u32, monotone epochs (step + 1) written by the peers with st.release.sys and polled by the
+//                owner: A[src] flags published, B[src] tiles packed, C[slice][src] rgbnet-gradient slice published
+//   [448,512)    err, done_ctas
 //   [1024,..)    flags[2][n_leaf] i32   touched flags published by the owner (double-buffered by step parity)
-//   [grad_off,.) grad[2][cap]     f32   packed gradient tiles of the union leaves + rgbnet gradients (double-buffered)
+//   [net_off,.)  net[2][NET_PAD]  f32   rgbnet gradients
+//   [grad_off,.) grad[2][cap]     f32   packed gradient tiles of the union leaves
 //
-// One exchange = three kernels on the training stream, no host synchronisation and no NCCL call:
-//   k_dp_union    1 CTA : publish own flags -> cross-GPU barrier -> OR of all peers' flags -> ascending union list
-//   k_dp_pack     grid  : own gradient tiles of the union leaves -> own grad[parity]; the last CTA signals the peers
-//   k_dp_reduce   grid  : wait for the peers' signals, then every rank sums the peers' tiles in rank order (identical
-//                         bits everywhere) straight into its gradient planes, ready for the fused sparse Adam.
-// Double buffering makes a third barrier unnecessary: a rank can only overwrite parity p two steps later, after every
-// peer passed the barrier of the step in between, which is stream-ordered after its reads of parity p.
+// Two phases, no host synchronisation and no NCCL call.  They are independent so that the fused step can run the tile
+// phase on a side stream UNDER the weight-gradient kernel (the grid gradients are final once the activation-gradient
+// kernel and the density scatter are done) and only the 88 KB rgbnet phase after it:
+//   tiles:  k_dp_union   1 CTA : publish own flags -> cross-GPU barrier A -> OR of all peers' flags -> ascending union list
+//           k_dp_pack    grid  : own gradient tiles of the union leaves -> own grad[parity]; the last CTA signals B
+//           k_dp_reduce  grid  : wait for B, then every rank sums the peers' tiles in rank order (identical bits
+//                                everywhere) straight into its gradient planes, ready for the fused sparse Adam
+//   net:    k_dp_net     8 CTAs: each publishes one slice of net_grad, signals C[slice], waits for the peers' C[slice] and
+//                                sums that slice in rank order — no grid-wide dependency
+// Double buffering makes further barriers unnecessary: a rank overwrites parity p two steps later, after it passed barrier
+// A of the step in between, which every peer reaches only after all of its reads of the earlier step (stream order).
 #include "common.cuh"
 #include "rgbnet.cuh"
 
 namespace {
 
 constexpr int TILE_F = PVDB_LEAF_VOX * 13;                 // density [512] + k0 [512][12]
-constexpr int NET_PAD = (PVDB_NET_N + 3) & ~3;
+constexpr int NET_PAD = (PVDB_NET_N + 255) & ~255;
+constexpr int NET_SLICES = 8;
 constexpr unsigned long long SPIN_TIMEOUT_NS = 2000000000ull;   // 2 s: a dead peer must not hang the GPU
+enum { SIG_A = 0, SIG_B = 16, SIG_C = 32 };                // word offsets inside the signal area (C: [slice][8])
 
 struct Blk {
     uint32_t* signal;
     int32_t* err;
     uint32_t* done;
     int32_t* flags[2];
+    float* net[2];
     float* grad[2];
 };
-__host__ __device__ inline size_t grad_off(int n_leaf) { return (1024 + (size_t)8 * n_leaf + 255) & ~(size_t)255; }
-__host__ __device__ inline size_t cap_floats(int cap_leaves) { return (size_t)cap_leaves * TILE_F + NET_PAD; }
+__host__ __device__ inline size_t net_off(int n_leaf) { return (1024 + (size_t)8 * n_leaf + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t grad_off(int n_leaf) { return net_off(n_leaf) + 2 * (size_t)NET_PAD * sizeof(float); }
+__host__ __device__ inline size_t cap_floats(int cap_leaves) { return (size_t)cap_leaves * TILE_F; }
 __host__ __device__ inline Blk view(void* base, int n_leaf, int cap_leaves) {
     char* p = static_cast<char*>(base);
     Blk b;
     b.signal = reinterpret_cast<uint32_t*>(p);
-    b.err = reinterpret_cast<int32_t*>(p + 256);
-    b.done = reinterpret_cast<uint32_t*>(p + 260);
+    b.err = reinterpret_cast<int32_t*>(p + 448);
+    b.done = reinterpret_cast<uint32_t*>(p + 452);
     b.flags[0] = reinterpret_cast<int32_t*>(p + 1024);
     b.flags[1] = b.flags[0] + n_leaf;
+    b.net[0] = reinterpret_cast<float*>(p + net_off(n_leaf));
+    b.net[1] = b.net[0] + NET_PAD;
     b.grad[0] = reinterpret_cast<float*>(p + grad_off(n_leaf));
     b.grad[1] = b.grad[0] + cap_floats(cap_leaves);
     return b;
@@ -56,14 +68,14 @@ __device__ __forceinline__ unsigned long long globaltimer() {
     return t;
 }
 // thread `peer` of a CTA: tell rank `peer` that this rank reached `epoch`
-__device__ __forceinline__ void signal_peer(const pvdb_dp_peers& P, int peer, uint32_t epoch) {
-    st_release_sys(view(P.base[peer], P.n_leaf, P.cap_leaves).signal + P.rank, epoch);
+__device__ __forceinline__ void signal_peer(const pvdb_dp_peers& P, int peer, int word, uint32_t epoch) {
+    st_release_sys(view(P.base[peer], P.n_leaf, P.cap_leaves).signal + word + P.rank, epoch);
 }
 // thread `peer` of a CTA: wait until rank `peer` reached `epoch`
-__device__ __forceinline__ void wait_peer(const pvdb_dp_peers& P, int peer, uint32_t epoch) {
+__device__ __forceinline__ void wait_peer(const pvdb_dp_peers& P, int peer, int word, uint32_t epoch) {
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
     const unsigned long long t0 = globaltimer();
-    while ((int32_t)(ld_acquire_sys(me.signal + peer) - epoch) < 0) {
+    while ((int32_t)(ld_acquire_sys(me.signal + word + peer) - epoch) < 0) {
         if (globaltimer() - t0 > SPIN_TIMEOUT_NS) { atomicExch(me.err, 1); break; }
         __nanosleep(64);
     }
@@ -80,8 +92,8 @@ __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epo
     if (threadIdx.x == 0) running = 0;
     __syncthreads();   // the st.release.sys below is cumulative over the CTA's flag writes ordered by this barrier
     if (threadIdx.x < P.world) {
-        signal_peer(P, threadIdx.x, epoch);
-        wait_peer(P, threadIdx.x, epoch);
+        signal_peer(P, threadIdx.x, SIG_A, epoch);
+        wait_peer(P, threadIdx.x, SIG_A, epoch);
     }
     __syncthreads();
     const int32_t* pf[8];
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epo
 }
 
 __global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch, int parity, const float* __restrict__ den_grad,
-                                                 const float* __restrict__ k0_grad, const float* __restrict__ net_grad,
+                                                 const float* __restrict__ k0_grad,
                                                  const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
     const int n = counters[cnt_den];
@@ -135,8 +147,6 @@ __global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch
                                  : reinterpret_cast<const float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128];
         reinterpret_cast<float4*>(buf)[idx] = v;
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < PVDB_NET_N; i += gridDim.x * blockDim.x)
-        buf[(size_t)n * TILE_F + i] = net_grad[i];
     // last CTA out tells every peer that this rank's tiles are in place (threadFenceReduction pattern; the final
     // st.release.sys is cumulative over everything the counter made visible)
     __syncthreads();
@@ -147,13 +157,13 @@ __global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch
         if (last) { *me.done = 0; __threadfence(); }
     }
     __syncthreads();
-    if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, epoch);
+    if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_B, epoch);
 }
 
 __global__ void __launch_bounds__(256) k_dp_reduce(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ den_grad,
-                                                   float* __restrict__ k0_grad, float* __restrict__ net_grad,
+                                                   float* __restrict__ k0_grad,
                                                    const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
-    if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, epoch);
+    if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_B, epoch);
     __syncthreads();
     const int n = counters[cnt_den];
     const float* pb[8];
@@ -176,12 +186,49 @@ __global__ void __launch_bounds__(256) k_dp_reduce(pvdb_dp_peers P, uint32_t epo
         if (i < 128) reinterpret_cast<float4*>(den_grad + (size_t)leaf * 512)[i] = s;
         else reinterpret_cast<float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128] = s;
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < PVDB_NET_N; i += gridDim.x * blockDim.x) {
-        const size_t off = (size_t)n * TILE_F + i;
-        float s = pb[0][off];
-        for (int r = 1; r < P.world; ++r) s += pb[r][off];
-        net_grad[i] = s;
+}
+
+// rgbnet gradients: CTA `g` owns slice g of the 22 019 values end to end (publish, signal, wait, sum), so there is no
+// grid-wide dependency and a single latency of peer loads.
+__global__ void __launch_bounds__(1024) k_dp_net(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ net_grad) {
+    constexpr int SL = NET_PAD / NET_SLICES;       // floats per slice (multiple of 4)
+    const int g = blockIdx.x;
+    const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
+    const int i = g * SL + threadIdx.x * 4;
+    const bool live = threadIdx.x * 4 < SL;
+    float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        own.x = i < PVDB_NET_N ? net_grad[i] : 0.f; own.y = i + 1 < PVDB_NET_N ? net_grad[i + 1] : 0.f;
+        own.z = i + 2 < PVDB_NET_N ? net_grad[i + 2] : 0.f; own.w = i + 3 < PVDB_NET_N ? net_grad[i + 3] : 0.f;
+        *reinterpret_cast<float4*>(me.net[parity] + i) = own;
     }
+    __syncthreads();   // the st.release.sys below is cumulative over the CTA's stores ordered by this barrier
+    if (threadIdx.x < P.world) {
+        signal_peer(P, threadIdx.x, SIG_C + g * 8, epoch);
+        wait_peer(P, threadIdx.x, SIG_C + g * 8, epoch);
+    }
+    __syncthreads();
+    if (!live) return;
+    float4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (r < P.world) v[r] = r == P.rank ? own : *reinterpret_cast<const float4*>(view(P.base[r], P.n_leaf, P.cap_leaves).net[parity] + i);
+    float4 s = v[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+        if (r < P.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    if (i < PVDB_NET_N) net_grad[i] = s.x;
+    if (i + 1 < PVDB_NET_N) net_grad[i + 1] = s.y;
+    if (i + 2 < PVDB_NET_N) net_grad[i + 2] = s.z;
+    if (i + 3 < PVDB_NET_N) net_grad[i + 3] = s.w;
+}
+
+int check_peers(const pvdb_dp_peers* P, const pvdb_train_bufs* b) {
+    PVDB_CHECK_ARG(P && b && b->tree, "null pointer");
+    PVDB_CHECK_ARG(P->world >= 1 && P->world <= 8 && P->rank >= 0 && P->rank < P->world, "world must be 1..8");
+    PVDB_CHECK_ARG(P->n_leaf == b->tree->n_leaf && P->cap_leaves >= 1, "peers block was sized for another tree");
+    for (int r = 0; r < P->world; ++r) PVDB_CHECK_ARG(P->base[r], "peer block not mapped");
+    return PVDB_OK;
 }
 
 }  // namespace
@@ -220,27 +267,37 @@ extern "C" int pvdb_dp_symm_error(const pvdb_dp_peers* P, int32_t* err_out) {
     return PVDB_OK;
 }
 
-extern "C" int pvdb_dp_exchange(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
-    PVDB_CHECK_ARG(P && b && b->tree, "null pointer");
-    PVDB_CHECK_ARG(P->world >= 1 && P->world <= 8 && P->rank >= 0 && P->rank < P->world, "world must be 1..8");
-    PVDB_CHECK_ARG(P->n_leaf == b->tree->n_leaf && P->cap_leaves >= 1, "peers block was sized for another tree");
-    for (int r = 0; r < P->world; ++r) PVDB_CHECK_ARG(P->base[r], "peer block not mapped");
+extern "C" int pvdb_dp_exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
+    if (int rc = check_peers(P, b)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int parity = step & 1;
-    const uint32_t e1 = 2 * step + 1, e2 = 2 * step + 2;   // monotone epochs; the pads start at 0
+    const uint32_t epoch = step + 1;                        // monotone; the signal words start at 0
     const int CNT_DEN = 2, CNT_K0 = 4;                      // counters[] slots of pvdb_train_bufs (include/plenvdb_b200.h)
-    pvdb_reset_launch_count();
-    pvdb_prof_begin(st);
-    k_dp_union<<<1, 1024, 0, st>>>(*P, e1, parity, b->den_touched, b->k0_touched, b->den_touched_list, b->k0_touched_list, b->counters,
+    k_dp_union<<<1, 1024, 0, st>>>(*P, epoch, parity, b->den_touched, b->k0_touched, b->den_touched_list, b->k0_touched_list, b->counters,
                                    CNT_DEN, CNT_K0);
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_union", st);
-    k_dp_pack<<<PVDB_SMS, 256, 0, st>>>(*P, e2, parity, b->den_grad, b->k0_grad, b->net_grad, b->den_touched_list, b->counters, CNT_DEN);
+    k_dp_pack<<<PVDB_SMS, 256, 0, st>>>(*P, epoch, parity, b->den_grad, b->k0_grad, b->den_touched_list, b->counters, CNT_DEN);
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_pack", st);
-    k_dp_reduce<<<PVDB_SMS * 2, 256, 0, st>>>(*P, e2, parity, b->den_grad, b->k0_grad, b->net_grad, b->den_touched_list, b->counters,
-                                              CNT_DEN);
+    k_dp_reduce<<<PVDB_SMS * 2, 256, 0, st>>>(*P, epoch, parity, b->den_grad, b->k0_grad, b->den_touched_list, b->counters, CNT_DEN);
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_reduce", st);
     return PVDB_OK;
+}
+
+extern "C" int pvdb_dp_exchange_net(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
+    if (int rc = check_peers(P, b)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_dp_net<<<NET_SLICES, 1024, 0, st>>>(*P, step + 1, step & 1, b->net_grad);
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("dp_net", st);
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_dp_exchange(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
+    pvdb_reset_launch_count();
+    pvdb_prof_begin((cudaStream_t)stream);
+    if (int rc = pvdb_dp_exchange_tiles(P, b, step, stream)) return rc;
+    return pvdb_dp_exchange_net(P, b, step, stream);
 }

@@ -20,3 +20,8 @@ int pvdb_rgbnet_prepare(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cud
 int pvdb_rgbnet_forward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
 // Backward: consumes g_logit (in k_rgb), produces net_grad (zeroed first) and scatters the k0 gradient.
 int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
+
+// The two halves of the tensor-core backward (cfg->use_tensor_cores only): the data-parallel step exchanges the grid
+// gradients, which are final after the first half, underneath the second.
+int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
+int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st);

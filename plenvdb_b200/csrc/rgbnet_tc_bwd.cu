@@ -644,14 +644,20 @@ int make_act_map(CUtensorMap* map, const float* base, int nf, int64_t cap_keep) 
 
 }  // namespace
 
-int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
-    PVDB_CHECK_ARG(b->k_h0 && b->k_h1 && b->k_dh0 && b->k_dh1 && b->k_x && b->k_mask, "the tcgen05 backward needs k_h0, k_h1, k_dh0, k_dh1, k_x, k_mask");
+static int bwd_attrs() {
     static bool attr_set = false;
     if (!attr_set) {
         PVDB_CUDA(cudaFuncSetAttribute(k_rgbnet_bwd_act_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, B1_TOTAL));
         PVDB_CUDA(cudaFuncSetAttribute(k_rgbnet_bwd_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_TOTAL));
         attr_set = true;
     }
+    return PVDB_OK;
+}
+
+// B1: activation gradients + k0 gradient scatter (final k0_grad / k0_touched once it completes)
+int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
+    PVDB_CHECK_ARG(b->k_h0 && b->k_h1 && b->k_dh0 && b->k_dh1 && b->k_x && b->k_mask, "the tcgen05 backward needs k_h0, k_h1, k_dh0, k_dh1, k_x, k_mask");
+    if (int rc = bwd_attrs()) return rc;
     PVDB_CHECK_ARG(b->net_img && b->k_corner, "net_img / k_corner scratch missing (tensor-core backward)");
     // second half of the scratch: backward image, built together with the forward image by pvdb_rgbnet_forward_tc
     const unsigned char* img = static_cast<const unsigned char*>(b->net_img) + PVDB_BWD_IMG_OFFSET;
@@ -663,6 +669,12 @@ int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b,
     k_rgbnet_bwd_act_tc<<<PVDB_SMS, B1_THREADS, B1_TOTAL, st>>>(A);
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("rgbnet_bwd_act", st);
+    return PVDB_OK;
+}
+
+// B2: weight gradients -> net_grad (overwritten)
+int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st) {
+    if (int rc = bwd_attrs()) return rc;
     BwdWgradArgs W;
     W.k_dh1 = b->k_dh1; W.k_h0 = b->k_h0; W.k_dh0 = b->k_dh0; W.k_x = b->k_x; W.k_h1 = b->k_h1; W.k_glogit = b->k_rgb;
     PVDB_CHECK_ARG(b->net_partial, "net_partial scratch missing (tensor-core backward)");
@@ -686,4 +698,9 @@ int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b,
     k_wgrad_reduce<<<(PVDB_NET_N + 31) / 32, 256, 0, st>>>(b->net_partial, PVDB_SMS, b->net_grad);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
+}
+
+int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
+    if (int rc = pvdb_rgbnet_backward_act_tc(cfg, b, viewdirs, st)) return rc;
+    return pvdb_rgbnet_backward_wgrad_tc(cfg, b, st);
 }

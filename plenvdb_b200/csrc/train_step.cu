@@ -812,8 +812,9 @@ extern "C" int pvdb_rays_hit_mask(const pvdb_train_cfg* cfg, const pvdb_train_bu
     return PVDB_OK;
 }
 
-extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* rays_o, const float* rays_d,
-                               const float* viewdirs, const float* target, int n_rays, int phases, void* stream) {
+static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* rays_o, const float* rays_d,
+                           const float* viewdirs, const float* target, int n_rays, int phases, void* stream,
+                           const pvdb_dp_peers* peers, uint32_t dp_step) {
     PVDB_CHECK_ARG(cfg && b && b->tree, "null cfg/bufs");
     PVDB_CHECK_ARG(cfg->k0_dim == 12 && cfg->net_width == 128, "the fused step is specialised for k0_dim=12, rgbnet_width=128");
     PVDB_CHECK_ARG(n_rays > 0, "n_rays must be positive");
@@ -918,11 +919,35 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
                                                         b->den_touched_list, b->counters, b->cap_alpha);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("density_scatter", st);
-        if (sd) {
+        if (sd && peers && cfg->use_tensor_cores) {
+            // data-parallel step: the grid gradients are final once the activation-gradient kernel (main) and the density
+            // scatter (side) are done, so their exchange over NVLink runs on the side stream UNDER the weight-gradient kernel;
+            // only the 88 KB of rgbnet gradients are exchanged after it.
+            int rc = pvdb_rgbnet_backward_act_tc(cfg, b, viewdirs, st);
+            if (rc) return rc;
+            PVDB_CUDA(cudaEventRecord(sd->fork2, st));
+            PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));
+            rc = pvdb_dp_exchange_tiles(peers, b, dp_step, sd->s);
+            if (rc) return rc;
             PVDB_CUDA(cudaEventRecord(sd->join, sd->s));
-            int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
+            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st);
+            if (rc) return rc;
+            rc = pvdb_dp_exchange_net(peers, b, dp_step, st);
             if (rc) return rc;
             PVDB_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
+        } else {
+            if (sd) {
+                PVDB_CUDA(cudaEventRecord(sd->join, sd->s));
+                int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
+                if (rc) return rc;
+                PVDB_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
+            }
+            if (peers) {
+                int rc = pvdb_dp_exchange_tiles(peers, b, dp_step, st);
+                if (rc) return rc;
+                rc = pvdb_dp_exchange_net(peers, b, dp_step, st);
+                if (rc) return rc;
+            }
         }
     }
     if (do_upd) {
@@ -954,4 +979,17 @@ extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs*
         pvdb_prof_mark("update_fused", st);
     }
     return PVDB_OK;
+}
+
+extern "C" int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* rays_o, const float* rays_d,
+                               const float* viewdirs, const float* target, int n_rays, int phases, void* stream) {
+    return train_step_impl(cfg, b, rays_o, rays_d, viewdirs, target, n_rays, phases, stream, nullptr, 0);
+}
+
+extern "C" int pvdb_train_step_dp(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const pvdb_dp_peers* peers, uint32_t dp_step,
+                                  const float* rays_o, const float* rays_d, const float* viewdirs, const float* target, int n_rays,
+                                  void* stream) {
+    PVDB_CHECK_ARG(peers, "null peers");
+    return train_step_impl(cfg, b, rays_o, rays_d, viewdirs, target, n_rays, PVDB_PHASE_FORWARD | PVDB_PHASE_BACKWARD | PVDB_PHASE_UPDATE,
+                           stream, peers, dp_step);
 }

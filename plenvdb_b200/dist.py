@@ -166,12 +166,11 @@ class DataParallelTrainer:
         if self.world == 1:
             tr.step(rays_o, rays_d, viewdirs, target)
             return
-        tr.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD)
         if self.peer is not None:
-            self.peer.exchange(tr._bufs)
-            tr.launches_total += 3
-            tr.update(lists_ready=True)
+            tr.step_dp(self.peer.peers, self.peer.step, rays_o, rays_d, viewdirs, target)
+            self.peer.step += 1
             return
+        tr.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD)
         n_leaf = tr.topo.n_leaf
         # 1. union of touched leaves: both flag arrays in one MAX all-reduce
         self.flags[:n_leaf].copy_(tr.t["den_touched"][:n_leaf])

@@ -189,6 +189,14 @@ class FusedTrainer:
         torch.cuda.current_stream().synchronize()
         return self._loss_host
 
+    def step_dp(self, peers, dp_step, rays_o, rays_d, viewdirs, target):
+        """One data-parallel iteration (pvdb_train_step_dp): the NVLink tile exchange overlaps the weight-gradient kernel."""
+        self.step_count += 1
+        self._set_step_scalars()
+        _lib.call("pvdb_train_step_dp", C.byref(self.cfg), C.byref(self._bufs), C.byref(peers), int(dp_step), _lib.ptr(rays_o),
+                  _lib.ptr(rays_d), _lib.ptr(viewdirs), _lib.ptr(target), rays_o.shape[0], _lib.current_stream())
+        self.launches_total += int(_lib.lib.pvdb_last_launch_count())
+
     def forward_backward(self, rays_o, rays_d, viewdirs, target):
         self.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD)
 
