@@ -219,3 +219,37 @@ def test_stress_scene_properties():
     assert bool((t["s_weight"][:ma][ks] > P["fast_color_thres"]).all())
     rgb = t["rgb_marched"][:n]
     assert bool(torch.isfinite(rgb).all()) and float(rgb.min()) >= -1e-5 and float(rgb.max()) <= 1.0 + 1e-5
+
+
+def test_edge_batches_no_hits_and_ragged(small):
+    """Edge cases of the fused step: a batch in which no ray hits anything (every list empty: the MLP, scatter and update
+    kernels see zero work), a batch smaller than the trainer's capacity, and a single ray."""
+    scene, net, rays = small
+    tr, den, k0 = _trainer(scene, net, 2048)
+    den0, k00, net0 = den.grid.clone(), k0.grid.clone(), tr.net.clone()
+    ro, rd, vd, tg = [_cu(a) for a in rays]
+    away = [ro, -rd, -vd, tg]                                  # cameras look away from the box
+    tr.step(*away)
+    torch.cuda.synchronize()
+    c = tr.counters()
+    assert c["M_alpha"] == 0 and c["M_keep"] == 0 and c["n_touched_den"] == 0 and c["overflow"] == 0
+    np.testing.assert_allclose(tr.t["rgb_marched"].cpu().numpy(), scene["bg"], rtol=0, atol=0)   # background only
+    assert torch.equal(den.grid, den0) and torch.equal(k0.grid, k00)                          # stepmode 1: nothing touched
+    assert bool(torch.isfinite(tr.t["loss"]).all()) and bool(torch.isfinite(tr.net).all())
+    # rgbnet: zero gradient -> Adam moves nothing (m = v = 0 -> p -= 0 / eps)
+    assert torch.equal(tr.net, net0)
+    # ragged: 777 rays through a 2048-ray trainer must equal a 777-ray trainer
+    part = [t[:777].contiguous() for t in (ro, rd, vd, tg)]
+    tr2, den2, k02 = _trainer(scene, net, 2048)
+    tr3, den3, k03 = _trainer(scene, net, 777)
+    for t_ in (tr2, tr3):
+        t_.run(*part, 3)
+    torch.cuda.synchronize()
+    assert tr2.counters()["M_keep"] == tr3.counters()["M_keep"] > 0
+    mk = tr2.counters()["M_keep"]
+    assert torch.equal(tr2.t["k_sample"][:mk], tr3.t["k_sample"][:mk]) and torch.equal(tr2.t["rgb_marched"][:777], tr3.t["rgb_marched"][:777])
+    # one ray
+    tr4, *_ = _trainer(scene, net, 64)
+    tr4.step(*[t[5:6].contiguous() for t in (ro, rd, vd, tg)])
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(tr4.t["loss"]).all())
