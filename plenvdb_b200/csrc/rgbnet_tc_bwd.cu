@@ -1,17 +1,14 @@
-// rgbnet_tc_bwd.cu — rgbnet backward on tcgen05 (3xTF32), two kernels:
+// rgbnet_tc_bwd.cu — rgbnet backward on tcgen05 (3xTF32), two kernels (details at each section):
 //
-//  B1 k_rgbnet_bwd_act_tc   activation gradients, 128-sample tiles, one TMEM lane per sample (same structure as the
-//                           forward):  dH1 = (g_logit . W2) * [h1>0]  (K = 3, CUDA cores, in registers)
-//                                      dH0 = (dH1 . W1)   * [h0>0]  (tcgen05, A = dH1 in TMEM, B = W1^T in smem)
+//  B1 k_rgbnet_bwd_act_tc   activation gradients, 128-sample tiles, warp specialised like the forward:
+//                                      dH1 = (g_logit . W2) * [h1>0]  (K = 3, CUDA cores, in registers)
+//                                      dH0 = (dH1 . W1)   * [h0>0]  (tcgen05, A = dH1 in TMEM, B = W1^T image in smem)
 //                                      dX  =  dH0 . W0[:, :12]       (tcgen05, N = 16) -> k0 gradient scatter
-//                           dH1, dH0 are also written to HBM for B2.
-//  B2 k_rgbnet_bwd_wgrad_tc weight gradients = sums over samples of outer products:  dW1 = dH1^T H0, dW0 = dH0^T X,
-//                           dW2 = G^T H1.  The contraction runs over SAMPLES, so both operands are activations
-//                           transposed: they are transposed while being staged into shared memory (K-major canonical
-//                           layout, 16-sample chunks, double buffered, hi/lo split on the fly) and consumed by
-//                           tcgen05.mma SS.  Bias gradients ride along as an extra "ones"
-//                           column of the B operand.  Accumulators live in TMEM for the CTA's lifetime and are
-//                           flushed once with red.global.add.
+//                           dH1, dH0 are also written to HBM (chunk-major) for B2.
+//  B2 k_rgbnet_bwd_wgrad_tc weight gradients = sums over samples of outer products:  dW1 = dH1^T H0, dW0 = dH0^T X
+//                           (tcgen05 SS, operands streamed by TMA into K-major SWIZZLE_64B tiles, bias gradients as a
+//                           ones row of B), dW2 = G^T H1 on the CUDA cores.  Accumulators live in TMEM for the CTA's
+//                           lifetime; per-CTA partial sums are stored and added by k_wgrad_reduce.
 // Reference semantics: autograd through nn.Sequential(Linear, ReLU, Linear, ReLU, Linear) (dvgo.py:99-107) and
 // QueryVerticalInVDB.backward -> color_backward (grid.py:53-60, colorvdb.cu:130-175).
 #include <cuda.h>
@@ -25,7 +22,7 @@ namespace {
 
 constexpr int WD = PVDB_NET_W;
 constexpr int CNT_M_KEEP = 1;
-constexpr uint32_t COL_AHI = 0, COL_ALO = 128, COL_D = 256;
+constexpr uint32_t COL_AHI = 0, COL_ALO = 128;
 
 __device__ __forceinline__ void red_add(float* addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
@@ -42,22 +39,6 @@ __device__ __forceinline__ void store_a_row32(uint32_t tmem_lane, int c0, const 
         tmem_st8(tmem_lane + COL_ALO + c0 + c, lo);
     }
 }
-// D[128 x N] = A(TMEM)[128 x K] * B(smem K-major)[N x K]^T, 3xTF32
-__device__ __forceinline__ void issue_ts(uint32_t tmem, uint32_t smem_hi, uint32_t smem_lo, int K, int N, uint32_t bar) {
-    const uint32_t idesc = make_idesc(N);
-    const uint64_t bhi = make_desc(smem_hi, K), blo = make_desc(smem_lo, K);
-    uint32_t acc = 0;
-    for (int ks = 0; ks < K / 8; ++ks) {
-        const uint64_t adv = (uint64_t)(ks * 256) >> 4;
-        const uint32_t ahi = tmem + COL_AHI + ks * 8, alo = tmem + COL_ALO + ks * 8;
-        umma_tf32_ts(tmem + COL_D, ahi, bhi + adv, idesc, acc);
-        acc = 1;
-        umma_tf32_ts(tmem + COL_D, alo, bhi + adv, idesc, 1);
-        umma_tf32_ts(tmem + COL_D, ahi, blo + adv, idesc, 1);
-    }
-    umma_commit(bar);
-}
-
 // ---------------------------------------------------------------------------------------------- B1
 // Same warp-specialised structure as the forward (rgbnet_tc.cu): 8 lane warps (thread = sample lane x column half), one
 // issuer warp; the weight image (W1^T, W0[:, :12]^T as tf32 hi/lo in the canonical K-major layout + W2 as fp32) is built

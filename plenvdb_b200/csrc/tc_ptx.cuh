@@ -118,21 +118,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int K) {
 __device__ __forceinline__ uint32_t make_idesc(int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24); }
 
 
-// Load W[n][k] (strides sn, sk in floats) for n < N_valid, k < K_valid into the canonical layout, split hi / lo.
-__device__ void load_weight(unsigned char* smem, int off_hi, int off_lo, const float* __restrict__ w, int sn, int sk, int N, int K,
-                            int N_valid, int K_valid) {
-    for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
-        const int n = e / K, k = e % K;
-        const float v = (n < N_valid && k < K_valid) ? __ldg(w + (size_t)n * sn + (size_t)k * sk) : 0.f;
-        uint32_t hi, lo;
-        split_tf32(v, hi, lo);
-        const int o = canon_off(n, k, K);
-        *reinterpret_cast<uint32_t*>(smem + off_hi + o) = hi;
-        *reinterpret_cast<uint32_t*>(smem + off_lo + o) = lo;
-    }
-}
-
-
 // ---- weight image of the activation-gradient kernel (rgbnet_tc_bwd.cu B1), built by the forward's prep kernel ----------
 constexpr int PVDB_BWD_IMG_OFFSET = 256 * 1024;         // inside pvdb_train_bufs.net_img
 constexpr int B1_W1HI = 0;                              // B[N=i][K=j] = w1[j][i], canonical K-major, [128][128]
