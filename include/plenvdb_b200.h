@@ -202,7 +202,8 @@ typedef struct pvdb_train_bufs {
     float *k_h0, *k_h1;                        /* post-ReLU activations kept for the backward: [.][128] row-major (fp32 path) or
                                                 * chunk-major [tile][8 chunks][128 features][16 samples] (tensor-core path) */
     float *k_x;                                /* chunk-major [tile][8][40][16] rgbnet inputs (12 k0 + 27 PE + a ones row), tensor-core path */
-    float *k_dh0, *k_dh1;                      /* chunk-major [tile][8][128][16] masked activation gradients, tensor-core backward */
+    float *k_dh0, *k_dh1;                      /* k_dh0: chunk-major [tile][8][128][16] masked activation gradient of layer 0 (tensor-core
+                                                * backward); k_dh1 is unused (the weight-gradient pass recomputes dH1), may be NULL */
     uint32_t *k_mask;                          /* [tile][8][128] ReLU sign bits of h0 (words 0-3) and h1 (words 4-7) */
     int32_t *k_corner;                         /* [cap_keep][8] record id (leaf*512+voxel) of the 8 trilinear corners, -1 = none */
     void *net_img;                             /* >= 512 KiB scratch: tf32 hi/lo weight images of the tensor-core kernels */

@@ -60,7 +60,7 @@ struct BwdActArgs {
     const float *k_glogit, *k_xyz;
     const uint32_t* k_mask;
     const int32_t* k_corner;
-    float *k_dh1, *k_dh0;
+    float* k_dh0;
     float* k0_grad; int32_t* k0_touched; int32_t* k0_touched_list; int32_t* counters_w;
     const int32_t* counters; int64_t cap_keep;
 };
@@ -167,10 +167,7 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bars + B1B_A1 + 8 * (c >> 5));
-                // chunk-major for B2; lanes past M write the zeros the weight-gradient pass relies on
-                float* o = A.k_dh1 + act_off(s, c, WD);
-#pragma unroll
-                for (int q = 0; q < 32; ++q) o[q * 16] = d[q];
+                // dH1 is not stored: the weight-gradient pass recomputes it from g, W2 and the mask bits
             }
         };
         uint32_t par0 = 0, par1 = 0;
@@ -268,7 +265,8 @@ constexpr int S_B1 = S_A1 + WD * ROWB;                   // [H0^T ; 1 ; 0..] [14
 constexpr int S_A0 = S_B1 + N1 * ROWB;                   // dH0^T [128][KC]
 constexpr int S_B0 = S_A0 + WD * ROWB;                   // [X^T(39) ; 1 ; 0..] [48][KC]  (k_x row 39 holds the ones)
 constexpr int S_H1 = S_B0 + N0 * ROWB;                   // H1^T [128][KC] raw, CUDA-core dW2
-constexpr int S_G = S_H1 + WD * ROWB;                    // logit gradients [KC][3]
+constexpr int S_G = S_H1 + WD * ROWB;                    // logit gradients [KC][3] (192 B), then at +256 the h1 ReLU mask words [4][KC]
+constexpr int S_M = S_G + 256;
 constexpr int STAGE = S_G + 512;                         // one raw stage (what TMA fills)
 constexpr int NSTAGE = 4;
 // lo tiles (same order / offsets as the first four raw tiles) only live between the converters and the MMAs of one chunk:
@@ -278,9 +276,10 @@ constexpr int LOSET = LO_B0 + N0 * ROWB;
 constexpr int S_LOSETS = NSTAGE * STAGE;
 constexpr int B2_BAR = S_LOSETS + 2 * LOSET;             // full[4], conv[4], free[4] mbarriers + tmem slot
 constexpr int BAR_FULL2 = 0, BAR_CONV2 = 32, BAR_FREE2 = 64, TMEM_SLOT2 = 96;
-constexpr int B2_TOTAL = B2_BAR + 112;
+constexpr int S_W2 = B2_BAR + 128;                       // W2 [3][128] fp32 (dH1 is recomputed here, not read from HBM)
+constexpr int B2_TOTAL = S_W2 + 3 * WD * 4;
 constexpr uint32_t ACC1 = 0, ACC0 = 144;                 // TMEM columns of the two accumulators (256 allocated)
-constexpr uint32_t TX_BYTES = 4 * WD * ROWB + 40 * ROWB + KC * 3 * 4;   // bytes landing per stage
+constexpr uint32_t TX_BYTES = 3 * WD * ROWB + 40 * ROWB + KC * 3 * 4 + 4 * KC * 4;   // bytes landing per stage
 static_assert(S_B1 % 512 == 0 && S_A0 % 512 == 0 && S_B0 % 512 == 0 && S_H1 % 512 == 0 && LO_B1 % 512 == 0 &&
               LO_A0 % 512 == 0 && LO_B0 % 512 == 0 && STAGE % 512 == 0 && LOSET % 512 == 0, "SW64 tiles must start on the 512-byte swizzle period");
 static_assert(B2_TOTAL <= 227 * 1024, "wgrad smem");
@@ -305,13 +304,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 
 struct BwdWgradArgs {
-    const float *k_dh1, *k_h0, *k_dh0, *k_x, *k_h1, *k_glogit;
+    const float *k_h0, *k_dh0, *k_x, *k_h1, *k_glogit;
+    const uint32_t* k_mask;
+    const float* w2;   // [3][128]
     float* partial;   // [gridDim.x][PART_LD] per-CTA weight-gradient partial sums (net_grad layout)
     const int32_t* counters; int64_t cap_keep;
     int use_tma;
 };
 constexpr int PART_LD = (PVDB_NET_N + 31) & ~31;
-struct WgradMaps { CUtensorMap dh1, h0, dh0, h1, x; };
+struct WgradMaps { CUtensorMap h0, dh0, h1, x; };
 
 #ifdef PVDB_TC_TIMING
 __device__ long long g_wg_t[PVDB_SMS][16];
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
         const int st = tid / KC, k = tid % KC;
         *reinterpret_cast<float*>(smem + st * STAGE + S_B1 + 128 * ROWB + k * 4) = 1.0f;
     }
+    for (int e = tid; e < 3 * WD; e += B2_THREADS) reinterpret_cast<float*>(smem + S_W2)[e] = __ldg(A.w2 + e);
     if (tid == 0)
         for (int st = 0; st < NSTAGE; ++st) {
             mbar_init(bar_full + 8 * st, A.use_tma ? 1 : 32);
@@ -401,16 +403,17 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
             if (A.use_tma) {
                 if (t == 0) {
                     mbar_expect_tx(full, TX_BYTES);
-                    tma_load_3d(base + S_A1, &maps.dh1, 0, 0, (int)ch, full);
                     tma_load_3d(base + S_B1, &maps.h0, 0, 0, (int)ch, full);
                     tma_load_3d(base + S_A0, &maps.dh0, 0, 0, (int)ch, full);
                     tma_load_3d(base + S_H1, &maps.h1, 0, 0, (int)ch, full);
                     tma_load_3d(base + S_B0, &maps.x, 0, 0, (int)ch, full);
                     bulk_g2s(base + S_G, A.k_glogit + ch * (KC * 3), KC * 3 * 4, full);
+                    const uint32_t* mk = A.k_mask + ((ch >> 3) * 8 + 4) * 128 + (ch & 7) * KC;   // [tile][8][128], words 4-7 = h1
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bulk_g2s(base + S_M + j * KC * 4, mk + j * 128, KC * 4, full);
                 }
             } else {
                 // fallback: 16-byte async copies straight into the swizzled positions (chunk `ch` of each tensor is contiguous)
-                const float* g_dh1 = A.k_dh1 + ch * (WD * KC);
                 const float* g_h0 = A.k_h0 + ch * (WD * KC);
                 const float* g_dh0 = A.k_dh0 + ch * (WD * KC);
                 const float* g_h1 = A.k_h1 + ch * (WD * KC);
@@ -420,7 +423,6 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
                     const int idx = t + 32 * i, f = idx >> 2, k4 = idx & 3;
                     const uint32_t o = sw64_off(f, k4);
                     const int go = f * KC + k4 * 4;
-                    cp_async16(base + S_A1 + o, g_dh1 + go);
                     cp_async16(base + S_B1 + o, g_h0 + go);
                     cp_async16(base + S_A0 + o, g_dh0 + go);
                     cp_async16(base + S_H1 + o, g_h1 + go);
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
                     cp_async16(base + S_B0 + sw64_off(f, k4), g_x + f * KC + k4 * 4);
                 }
                 if (t < 12) cp_async16(base + S_G + t * 16, A.k_glogit + ch * (KC * 3) + t * 4);
+                else if (t < 28) cp_async16(base + S_M + (t - 12) * 16, A.k_mask + ((ch >> 3) * 8 + 4 + ((t - 12) >> 2)) * 128 + (ch & 7) * KC + ((t - 12) & 3) * 4);
                 cp_async_arrive(full);
             }
         }
@@ -445,12 +448,32 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
             unsigned char* lo = smem + S_LOSETS + (it & 1) * LOSET;
             // this lo set was last read by the MMAs of chunk it-2
             if (it >= 2) { const long long t0 = clock64(); mbar_wait(bar_free + 8 * ((it - 2) % NSTAGE), ((it - 2) / NSTAGE) & 1); t_lo += clock64() - t0; }
-            // 1696 16-byte items: A1 512, B1 512 (rows 0..127), A0 512, B0 160 (rows 0..39).  All loads first (the two converter
-            // warps of a scheduler cannot hide shared-memory latency by themselves), then lo = x - trunc(x), then the stores.
-            // The raw tiles are the hi operands as they are: async-copied data tracked by the mbarrier needs no proxy fence.
+            // 1696 16-byte items: A1 512 (COMPUTED: dH1 = [h1 > 0] (g . W2), from the 16 x 3 logit gradients, W2 and the mask
+            // words — a fifth of the HBM reads of this kernel and half of the activation-gradient kernel's writes go away),
+            // B1 512 (rows 0..127), A0 512, B0 160 (rows 0..39).  All loads first (the two converter warps of a scheduler cannot
+            // hide shared-memory latency by themselves), then lo = x - trunc(x), then the stores.  The raw tiles are the hi
+            // operands as they are: async-copied data tracked by the mbarrier needs no proxy fence.
             float4 v[7];
+            {
+                const float* sW2 = reinterpret_cast<const float*>(smem + S_W2);
+                const uint32_t* sM = reinterpret_cast<const uint32_t*>(sb + S_M);
 #pragma unroll
-            for (int q = 0; q < 7; ++q) {
+                for (int q = 0; q < 2; ++q) {
+                    const int e = tid + q * B2_CONV, f = e >> 2, k4 = (e & 3) ^ ((f >> 1) & 3);   // physical column -> sample group
+                    const float w0 = sW2[f], w1 = sW2[WD + f], w2 = sW2[2 * WD + f];
+                    const float4 ga = *reinterpret_cast<const float4*>(sb + S_G + k4 * 48), gb = *reinterpret_cast<const float4*>(sb + S_G + k4 * 48 + 16),
+                                 gc = *reinterpret_cast<const float4*>(sb + S_G + k4 * 48 + 32);
+                    const uint4 mw = *reinterpret_cast<const uint4*>(sM + (f >> 5) * KC + k4 * 4);
+                    const int bit = f & 31;
+                    v[q].x = (mw.x >> bit) & 1u ? fmaf(ga.z, w2, fmaf(ga.y, w1, ga.x * w0)) : 0.f;
+                    v[q].y = (mw.y >> bit) & 1u ? fmaf(gb.y, w2, fmaf(gb.x, w1, ga.w * w0)) : 0.f;
+                    v[q].z = (mw.z >> bit) & 1u ? fmaf(gc.x, w2, fmaf(gb.w, w1, gb.z * w0)) : 0.f;
+                    v[q].w = (mw.w >> bit) & 1u ? fmaf(gc.w, w2, fmaf(gc.z, w1, gc.y * w0)) : 0.f;
+                    *reinterpret_cast<float4*>(sb + S_A1 + e * 16) = v[q];
+                }
+            }
+#pragma unroll
+            for (int q = 2; q < 7; ++q) {
                 const int e = tid + q * B2_CONV;
                 if (e < 1696) v[q] = *reinterpret_cast<const float4*>(sb + e * 16 + (e >= 1024 ? 1024 : 0));
             }
@@ -637,14 +660,14 @@ static int bwd_attrs() {
 
 // B1: activation gradients + k0 gradient scatter (final k0_grad / k0_touched once it completes)
 int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
-    PVDB_CHECK_ARG(b->k_h0 && b->k_h1 && b->k_dh0 && b->k_dh1 && b->k_x && b->k_mask, "the tcgen05 backward needs k_h0, k_h1, k_dh0, k_dh1, k_x, k_mask");
+    PVDB_CHECK_ARG(b->k_h0 && b->k_h1 && b->k_dh0 && b->k_x && b->k_mask, "the tcgen05 backward needs k_h0, k_h1, k_dh0, k_x, k_mask");
     if (int rc = bwd_attrs()) return rc;
     PVDB_CHECK_ARG(b->net_img && b->k_corner, "net_img / k_corner scratch missing (tensor-core backward)");
     // second half of the scratch: backward image, built together with the forward image by pvdb_rgbnet_forward_tc
     const unsigned char* img = static_cast<const unsigned char*>(b->net_img) + PVDB_BWD_IMG_OFFSET;
     BwdActArgs A;
     A.img = img; A.k_glogit = b->k_rgb; A.k_mask = b->k_mask; A.k_xyz = b->k_xyz; A.k_corner = b->k_corner;
-    A.k_dh1 = b->k_dh1; A.k_dh0 = b->k_dh0; A.k0_grad = b->k0_grad; A.k0_touched = b->k0_touched; A.k0_touched_list = b->k0_touched_list; A.counters_w = b->counters;
+    A.k_dh0 = b->k_dh0; A.k0_grad = b->k0_grad; A.k0_touched = b->k0_touched; A.k0_touched_list = b->k0_touched_list; A.counters_w = b->counters;
     A.counters = b->counters;
     A.cap_keep = b->cap_keep;
     k_rgbnet_bwd_act_tc<<<PVDB_SMS, B1_THREADS, B1_TOTAL, st>>>(A);
@@ -657,16 +680,17 @@ int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs
 int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st) {
     if (int rc = bwd_attrs()) return rc;
     BwdWgradArgs W;
-    W.k_dh1 = b->k_dh1; W.k_h0 = b->k_h0; W.k_dh0 = b->k_dh0; W.k_x = b->k_x; W.k_h1 = b->k_h1; W.k_glogit = b->k_rgb;
+    W.k_h0 = b->k_h0; W.k_dh0 = b->k_dh0; W.k_x = b->k_x; W.k_h1 = b->k_h1; W.k_glogit = b->k_rgb;
+    W.k_mask = b->k_mask; W.w2 = b->net + PVDB_NET_OFF_W2;
     PVDB_CHECK_ARG(b->net_partial, "net_partial scratch missing (tensor-core backward)");
     W.partial = b->net_partial; W.counters = b->counters; W.cap_keep = b->cap_keep;
     // tensor maps are pure host-side encodings of (pointer, shape): rebuilt when a buffer changes
     static thread_local WgradMaps maps;
     static thread_local const void* maps_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     static thread_local int maps_ok = 0;
-    const void* key[6] = {b->k_dh1, b->k_h0, b->k_dh0, b->k_h1, b->k_x, (const void*)(intptr_t)b->cap_keep};
+    const void* key[6] = {nullptr, b->k_h0, b->k_dh0, b->k_h1, b->k_x, (const void*)(intptr_t)b->cap_keep};
     if (memcmp(key, maps_key, sizeof(key)) != 0) {
-        const int rc = make_act_map(&maps.dh1, b->k_dh1, WD, b->cap_keep) | make_act_map(&maps.h0, b->k_h0, WD, b->cap_keep) |
+        const int rc = make_act_map(&maps.h0, b->k_h0, WD, b->cap_keep) |
                        make_act_map(&maps.dh0, b->k_dh0, WD, b->cap_keep) | make_act_map(&maps.h1, b->k_h1, WD, b->cap_keep) |
                        make_act_map(&maps.x, b->k_x, 40, b->cap_keep);
         maps_ok = rc == 0;

@@ -78,7 +78,6 @@ class FusedTrainer:
         if self.use_tc:   # tensor-core backward: input rows and masked activation gradients for the weight-gradient GEMM
             self.t["k_x"] = z(ck, 40, **f32)
             self.t["k_dh0"] = z(ck, 128, **f32)
-            self.t["k_dh1"] = z(ck, 128, **f32)
             self.t["k_mask"] = z(ck, 8, **i32)
             self.t["k_corner"] = z(ck, 8, **i32)
             self.t["net_img"] = z(512 * 1024 // 4, **i32)
