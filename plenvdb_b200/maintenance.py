@@ -68,3 +68,46 @@ def total_variation_add_grad(vdb, wx, wy, wz, dense_mode=True):
     """grad += TV gradient (total_variation_kernel.cu:14-35) with the dense kernel's semantics on the sparse planes."""
     _lib.call("pvdb_total_variation_add_grad", vdb.topo.ref, _lib.ptr(vdb.grid), _lib.ptr(vdb.grad), vdb.ndim, vdb.reso[0], vdb.reso[1],
               vdb.reso[2], float(wx), float(wy), float(wz), int(bool(dense_mode)), _lib.current_stream())
+
+
+@torch.no_grad()
+def voxel_count_views(world_size, xyz_min, xyz_max, rays_o_tr, rays_d_tr, imsz, near, far, stepsize, voxel_size, downrate=1,
+                      irregular_shape=False, device="cuda", ray_chunk=65536):
+    """DirectVoxGO.voxel_count_views (plenvdb/lib/dvgo.py:212-243) on the device: for every training view, scatter the
+    trilinear weights of all its sample points into a grid of ones' gradient and count the voxels whose accumulated weight
+    exceeds 1.  The reference builds a DenseGrid and back-propagates through F.grid_sample per 10 000 rays; here the sample
+    points go through the sparse gradient scatter (`pvdb_sample_backward`, C = 1) on a dense-fill topology.
+    Returns the count as a float tensor [1, 1, rx, ry, rz] like the reference."""
+    from .plenvdb import DensityVDB
+    dev = torch.device(device)
+    ws = [int(v) for v in world_size]
+    lo = torch.as_tensor(np.asarray(xyz_min, np.float32)).to(dev)
+    hi = torch.as_tensor(np.asarray(xyz_max, np.float32)).to(dev)
+    ones = DensityVDB(ws, 1, device=device)
+    far = 1e9                                                    # dvgo.py:214
+    n_samples = int(np.linalg.norm(np.array(ws) + 1) / stepsize) + 1
+    rng = torch.arange(n_samples, dtype=torch.float32, device=dev)[None]
+    count = torch.zeros(ws, dtype=torch.float32, device=dev)
+    scale = torch.tensor([w - 1 for w in ws], dtype=torch.float32, device=dev)
+    if not irregular_shape and torch.is_tensor(rays_o_tr) and rays_o_tr.dim() == 4:
+        views = zip(rays_o_tr, rays_d_tr)                        # [n_views, H, W, 3]
+    else:
+        views = zip(rays_o_tr.split(imsz), rays_d_tr.split(imsz))
+    for ro_v, rd_v in views:
+        if irregular_shape:
+            ro_v, rd_v = ro_v.to(dev).reshape(-1, 3), rd_v.to(dev).reshape(-1, 3)
+        else:
+            ro_v = ro_v[::downrate, ::downrate].to(dev).flatten(0, -2)
+            rd_v = rd_v[::downrate, ::downrate].to(dev).flatten(0, -2)
+        ones.grad.zero_()
+        for ro, rd in zip(ro_v.split(ray_chunk), rd_v.split(ray_chunk)):
+            vec = torch.where(rd == 0, torch.full_like(rd, 1e-6), rd)
+            rate_a, rate_b = (hi - ro) / vec, (lo - ro) / vec
+            t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)
+            step = stepsize * voxel_size * rng
+            interpx = t_min[..., None] + step / rd.norm(dim=-1, keepdim=True)
+            pts = ro[..., None, :] + rd[..., None, :] * interpx[..., None]          # [n, S, 3] world
+            idx = ((pts - lo) / (hi - lo) * scale).reshape(-1, 3).t().contiguous()    # DenseGrid: grid_sample, align_corners=True
+            ones.backward_torch(idx, torch.ones(idx.shape[1], dtype=torch.float32, device=dev))
+        count += (ones.get_dense_grid_torch(ones.grad)[..., 0] > 1).float()
+    return count[None, None]

@@ -96,3 +96,41 @@ def test_total_variation_matches_dense_kernel_semantics(dense_mode, grids):
         cov = vdb.get_dense_grid_torch(torch.ones_like(vdb.grad)) > 0
         torch.testing.assert_close(got[cov], want[cov], rtol=1e-5, atol=1e-6)
         vdb.grad.zero_()
+
+
+def test_voxel_count_views_matches_grid_sample_autograd():
+    """dvgo.py:212-243 restated with torch autograd through F.grid_sample (what DenseGrid does) vs the device scatter."""
+    from plenvdb_b200 import maintenance as mt
+    from plenvdb_b200 import synth
+    ws = (24, 20, 28)
+    lo, hi = np.array([-1.3, -1.3, -1.3], np.float32), np.array([1.3, 1.3, 1.3], np.float32)
+    K = synth.intrinsics(24, 24)
+    poses = synth.train_cameras(3)
+    H = W = 24
+    ros, rds = [], []
+    for p in poses:
+        py, px = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+        ro, rd, _ = synth.rays_of_pixels(K, np.broadcast_to(p, (H * W, 4, 4)), px.reshape(-1), py.reshape(-1))
+        ros.append(ro.reshape(H, W, 3)); rds.append(rd.reshape(H, W, 3))
+    ro_tr, rd_tr = torch.from_numpy(np.stack(ros)).cuda(), torch.from_numpy(np.stack(rds)).cuda()
+    stepsize, voxel_size, near = 0.5, 2.6 / 24, 0.2
+    got = mt.voxel_count_views(ws, lo, hi, ro_tr, rd_tr, [H * W] * 3, near, 1e9, stepsize, voxel_size)[0, 0]
+    # reference composition
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    n_samples = int(np.linalg.norm(np.array(ws) + 1) / stepsize) + 1
+    rng = torch.arange(n_samples, dtype=torch.float32, device="cuda")[None]
+    want = torch.zeros(ws, device="cuda")
+    margin = torch.zeros(ws, dtype=torch.bool, device="cuda")
+    for ro_v, rd_v in zip(ro_tr, rd_tr):
+        grid = torch.ones((1, 1) + ws, device="cuda", requires_grad=True)
+        ro, rd = ro_v.reshape(-1, 3), rd_v.reshape(-1, 3)
+        vec = torch.where(rd == 0, torch.full_like(rd, 1e-6), rd)
+        t_min = torch.minimum((hi_t - ro) / vec, (lo_t - ro) / vec).amax(-1).clamp(min=near, max=1e9)
+        interpx = t_min[..., None] + stepsize * voxel_size * rng / rd.norm(dim=-1, keepdim=True)
+        pts = ro[..., None, :] + rd[..., None, :] * interpx[..., None]
+        ind = ((pts - lo_t) / (hi_t - lo_t)).flip((-1,)) * 2 - 1
+        torch.nn.functional.grid_sample(grid, ind.reshape(1, 1, 1, -1, 3), mode="bilinear", align_corners=True).sum().backward()
+        want += (grid.grad[0, 0] > 1).float()
+        margin |= (grid.grad[0, 0] - 1).abs() < 1e-3                 # accumulated weight within rounding of the threshold
+    assert int(want.sum()) > 100
+    assert torch.equal(got[~margin], want[~margin])
