@@ -271,8 +271,8 @@ def run_ours(args):
         except Exception:
             traffic = None
         # bytes the three MLP kernels move by design (activations handed over through HBM), per kept sample
-        design_bytes = {"rgbnet_fwd": M3 * (512 + 512 + 160 + 32 + 48 + 12 + 44.0), "rgbnet_bwd_act": M3 * (512 + 512 + 88.0),
-                        "rgbnet_bwd_wgrad": M3 * (4 * 512 + 160 + 12.0) + 148 * 22048 * 4.0}
+        design_bytes = {"rgbnet_fwd": M3 * (512 + 512 + 160 + 32 + 48 + 12 + 44.0), "rgbnet_bwd_act": M3 * (512 + 88.0),
+                        "rgbnet_bwd_wgrad": M3 * (3 * 512 + 160 + 12 + 16.0) + 148 * 22048 * 4.0}
         if top in kern_flops:
             ach = kern_flops[top] / (kern[top] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
