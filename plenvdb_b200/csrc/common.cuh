@@ -46,6 +46,24 @@ bool pvdb_prof_active();
         }                                                                                \
     } while (0)
 
+// Programmatic dependent launch (PDL): the kernels of the fused step's main chain are launched with programmatic stream
+// serialisation.  Each of them lets its dependent be launched as soon as all of its own CTAs are resident
+// (pvdb_pdl_trigger at the top), and blocks at pvdb_pdl_wait until the kernel before it has completed and its memory is
+// visible — so the next kernel's launch latency and sample-independent prologue overlap the current kernel's tail, while
+// every access to dependent data stays ordered.  Both instructions are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pvdb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pvdb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pvdb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static inline int pvdb_grid_for(int64_t n, int block) {
     int64_t g = (n + block - 1) / block;
     if (g < 1) g = 1;

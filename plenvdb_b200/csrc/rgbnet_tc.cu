@@ -341,6 +341,8 @@ struct TrainFwdArgs {
 
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
     auto feat = [&](int64_t s, bool valid, float* x) {
         if (!valid) {   // lanes past M in the last tile: zero input row in HBM (the weight-gradient pass reads whole tiles)
@@ -481,7 +483,7 @@ int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     A.k_h0 = b->k_h0; A.k_h1 = b->k_h1; A.k_rgb = b->k_rgb; A.k_x = b->k_x; A.k_mask = b->k_mask; A.counters = b->counters; A.cap_keep = b->cap_keep;
     A.k_corner = b->k_corner;
     A.img = static_cast<const unsigned char*>(b->net_img);
-    k_rgbnet_fwd_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A);
+    PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_fwd_tc, dim3(PVDB_SMS), dim3(FWD_THREADS), SM_TOTAL, st, A));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

@@ -82,6 +82,8 @@ __device__ __forceinline__ void issue_b1(uint32_t tmem, uint32_t d_col, uint32_t
 
 __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + B1_BAR;
@@ -325,6 +327,8 @@ constexpr int B2_THREADS = 320;
 constexpr int B2_CONV = 256;
 __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradArgs A, const __grid_constant__ WgradMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long t_start = clock64();
     long long t_wait = 0, t_mma = 0, t_lo = 0;
@@ -592,6 +596,8 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
 // in flight at once (one latency), 128-byte coalesced across the 32 elements.
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad) {
     __shared__ float red[8][32];
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     const int e = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
     float a[19];
 #pragma unroll
@@ -670,7 +676,7 @@ int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs
     A.k_dh0 = b->k_dh0; A.k0_grad = b->k0_grad; A.k0_touched = b->k0_touched; A.k0_touched_list = b->k0_touched_list; A.counters_w = b->counters;
     A.counters = b->counters;
     A.cap_keep = b->cap_keep;
-    k_rgbnet_bwd_act_tc<<<PVDB_SMS, B1_THREADS, B1_TOTAL, st>>>(A);
+    PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_bwd_act_tc, dim3(PVDB_SMS), dim3(B1_THREADS), B1_TOTAL, st, A));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("rgbnet_bwd_act", st);
     return PVDB_OK;
@@ -698,9 +704,9 @@ int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bu
     }
     static const bool no_tma = getenv("PVDB_NO_TMA") != nullptr;   // bring-up switch: cp.async loader instead of TMA
     W.use_tma = maps_ok && !no_tma;
-    k_rgbnet_bwd_wgrad_tc<<<PVDB_SMS, B2_THREADS, B2_TOTAL, st>>>(W, maps);
+    PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_bwd_wgrad_tc, dim3(PVDB_SMS), dim3(B2_THREADS), B2_TOTAL, st, W, maps));
     PVDB_LAUNCH_CHECK();
-    k_wgrad_reduce<<<(PVDB_NET_N + 31) / 32, 256, 0, st>>>(b->net_partial, PVDB_SMS, b->net_grad);
+    PVDB_CUDA(pvdb_launch_pdl(k_wgrad_reduce, dim3((PVDB_NET_N + 31) / 32), dim3(256), 0, st, (const float*)b->net_partial, (int)PVDB_SMS, b->net_grad));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

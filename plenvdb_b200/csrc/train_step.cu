@@ -253,6 +253,8 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
 template <int MODE, bool PARITY>
 __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
                                                   const float* __restrict__ rays_d, int n_rays, int32_t* __restrict__ ticket) {
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     const int lane = threadIdx.x & 31;
     if (ticket == nullptr) {
         const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -273,6 +275,8 @@ __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, con
 // A ray with more alpha-passing samples than the scratch holds is simply marched again.
 __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
                                                       const float* __restrict__ rays_d, int n_rays) {
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_rays) return;
@@ -346,6 +350,8 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
                                                       int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
                                                       int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha,
                                                       int64_t cap_keep) {
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     __shared__ int2 wtot[32];
     __shared__ int2 carry_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -430,6 +436,8 @@ struct CompositeParams {
     int do_backward;
 };
 __global__ void __launch_bounds__(256) k_composite(CompositeParams C, int n_rays) {
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     float l_mse = 0, l_ent = 0, l_per = 0;
@@ -616,6 +624,8 @@ struct UpdateArgs {
 };
 // Work items: (touched density leaf) and (touched k0 leaf, quarter); a persistent grid strides over them.
 __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
+    // pvdb_pdl_trigger();
+    pvdb_pdl_wait();
     if ((int)blockIdx.x >= U.leaf_blocks) {
         const int i = ((int)blockIdx.x - U.leaf_blocks) * blockDim.x + threadIdx.x;
         if (i < PVDB_NET_N) {
@@ -864,16 +874,17 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                 PVDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<0, false>, 256, 0));
                 resident = PVDB_SMS * (per_sm > 0 ? per_sm : 1);
             }
-            k_march<0, false><<<min(resident, warp_grid), 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, b->counters + CNT_RAY_TICKET);
+            PVDB_CUDA(pvdb_launch_pdl(k_march<0, false>, dim3(min(resident, warp_grid)), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays,
+                                      b->counters + CNT_RAY_TICKET));
         }
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_count", st);
-        k_scan_counts<<<1, 1024, 0, st>>>(b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays, b->counters, b->loss,
-                                          b->cap_alpha, b->cap_keep);
+        PVDB_CUDA(pvdb_launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays,
+                                  b->counters, b->loss, b->cap_alpha, b->cap_keep));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("scan", st);
         PVDB_CHECK_ARG(!O.scratch || n_rays <= b->scratch_rays, "march_scratch holds fewer rays than this batch");
-        if (O.scratch) k_emit_scratch<<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays);
+        if (O.scratch) PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
         else k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
@@ -892,7 +903,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         C.alphainv_last = b->alphainv_last; C.target = target; C.rgb_marched = b->rgb_marched; C.grad_last = b->grad_last;
         C.loss = b->loss; C.cta_done = b->counters + CNT_CTA_DONE; C.bg = cfg->bg; C.w_main = cfg->weight_main; C.w_ent = cfg->weight_entropy_last;
         C.w_per = cfg->weight_rgbper; C.inv_N = 1.0f / (float)n_glob; C.cap_keep = b->cap_keep; C.do_backward = do_bwd ? 1 : 0;
-        k_composite<<<warp_grid, 256, 0, st>>>(C, n_rays);
+        PVDB_CUDA(pvdb_launch_pdl(k_composite, dim3(warp_grid), dim3(256), 0, st, C, n_rays));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("composite", st);
     }
@@ -974,7 +985,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         U.eps = cfg->eps; U.b0 = cfg->beta0; U.b1 = cfg->beta1;
         U.leaf_blocks = PVDB_SMS * 4;
         const int net_blocks = (PVDB_NET_N + 255) / 256;
-        k_update_fused<<<U.leaf_blocks + net_blocks, 256, 0, st>>>(U);
+        PVDB_CUDA(pvdb_launch_pdl(k_update_fused, dim3(U.leaf_blocks + net_blocks), dim3(256), 0, st, U));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("update_fused", st);
     }
