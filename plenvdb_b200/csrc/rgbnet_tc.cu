@@ -341,7 +341,6 @@ struct TrainFwdArgs {
 
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
     auto feat = [&](int64_t s, bool valid, float* x) {

@@ -82,7 +82,6 @@ __device__ __forceinline__ void issue_b1(uint32_t tmem, uint32_t d_col, uint32_t
 
 __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
@@ -327,7 +326,6 @@ constexpr int B2_THREADS = 320;
 constexpr int B2_CONV = 256;
 __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradArgs A, const __grid_constant__ WgradMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long t_start = clock64();
@@ -596,7 +594,6 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
 // in flight at once (one latency), 128-byte coalesced across the 32 elements.
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad) {
     __shared__ float red[8][32];
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     const int e = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
     float a[19];

@@ -253,7 +253,6 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
 template <int MODE, bool PARITY>
 __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
                                                   const float* __restrict__ rays_d, int n_rays, int32_t* __restrict__ ticket) {
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     const int lane = threadIdx.x & 31;
     if (ticket == nullptr) {
@@ -275,7 +274,6 @@ __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, con
 // A ray with more alpha-passing samples than the scratch holds is simply marched again.
 __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
                                                       const float* __restrict__ rays_d, int n_rays) {
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -350,7 +348,6 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
                                                       int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
                                                       int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha,
                                                       int64_t cap_keep) {
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     __shared__ int2 wtot[32];
     __shared__ int2 carry_s;
@@ -436,7 +433,6 @@ struct CompositeParams {
     int do_backward;
 };
 __global__ void __launch_bounds__(256) k_composite(CompositeParams C, int n_rays) {
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -624,7 +620,6 @@ struct UpdateArgs {
 };
 // Work items: (touched density leaf) and (touched k0 leaf, quarter); a persistent grid strides over them.
 __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
-    // pvdb_pdl_trigger();
     pvdb_pdl_wait();
     if ((int)blockIdx.x >= U.leaf_blocks) {
         const int i = ((int)blockIdx.x - U.leaf_blocks) * blockDim.x + threadIdx.x;
