@@ -65,6 +65,7 @@ __device__ __forceinline__ int pixel_of_thread(int W, int rows, int& local) {
 __global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float* __restrict__ c2w, int row_begin, int rows,
                                                       int32_t* __restrict__ n_samples, float* __restrict__ tmins,
                                                       float* __restrict__ tmaxs) {
+    pvdb_pdl_wait();
     int local;
     if (pixel_of_thread(C.W, rows, local) < 0) return;
     const int n = row_begin * C.W + local;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float
 // ---- exclusive scan over npix ints: 4096 items per CTA, then the block sums, then the offsets
 __global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n,
                                                       int32_t* __restrict__ block_sums) {
+    pvdb_pdl_wait();
     __shared__ int wsum[32];
     const int base = blockIdx.x * 4096 + threadIdx.x * 4;
     int v[4], s = 0;
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t* __restrict_
     if (threadIdx.x == 1023) block_sums[blockIdx.x] = excl;
 }
 __global__ void __launch_bounds__(1024) k_scan_tops(int32_t* __restrict__ block_sums, int nb) {
+    pvdb_pdl_wait();
     __shared__ int wsum[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int own = threadIdx.x < nb ? block_sums[threadIdx.x] : 0;
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(1024) k_scan_tops(int32_t* __restrict__ block_
 }
 __global__ void __launch_bounds__(1024) k_scan_add(int32_t* __restrict__ out, int n, const int32_t* __restrict__ block_sums, int nb,
                                                    int32_t* __restrict__ counters, int64_t cap) {
+    pvdb_pdl_wait();
     const int base = blockIdx.x * 4096 + threadIdx.x * 4;
     const int off = block_sums[blockIdx.x];
 #pragma unroll
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float
                                                       int32_t* __restrict__ s_ray, float* __restrict__ s_weight,
                                                       float* __restrict__ s_feat, int64_t cap, float* __restrict__ out_rgb,
                                                       int32_t* __restrict__ counters) {
+    pvdb_pdl_wait();
     int local;
     if (pixel_of_thread(C.W, rows, local) < 0) return;
     const int ns = n_samples[local];
@@ -347,6 +352,7 @@ __global__ void __launch_bounds__(NT, 1) k_render_mlp(RenderMlpArgs A) {
 __global__ void __launch_bounds__(256) k_render_composite(const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
                                                           const float* __restrict__ s_rgb, int npix, int64_t cap,
                                                           float* __restrict__ out_rgb) {
+    pvdb_pdl_wait();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npix) return;
     const int ns = n_samples[p];
@@ -403,20 +409,20 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
     const int rows = row_end - row_begin, npix = rows * cfg->W;
     const int tiles = ((cfg->W + 7) / 8) * ((rows + 3) / 4);
     const int pgrid = pvdb_grid_for((int64_t)tiles * 32, 256);
-    k_render_pass1<<<pgrid, 256, 0, st>>>(C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs);
+    PVDB_CUDA(pvdb_launch_pdl(k_render_pass1, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_pass1", st);
     const int nb = (npix + 4095) / 4096;
     PVDB_CHECK_ARG(nb <= 1023, "row band too large for the scan (max 4M pixels per call)");
-    k_scan_blocks<<<nb, 1024, 0, st>>>(b->n_samples, b->i_starts, npix, b->scan_tmp);
+    PVDB_CUDA(pvdb_launch_pdl(k_scan_blocks, dim3(nb), dim3(1024), 0, st, (const int32_t*)b->n_samples, b->i_starts, npix, b->scan_tmp));
     PVDB_LAUNCH_CHECK();
-    k_scan_tops<<<1, 1024, 0, st>>>(b->scan_tmp, nb);
+    PVDB_CUDA(pvdb_launch_pdl(k_scan_tops, dim3(1), dim3(1024), 0, st, b->scan_tmp, nb));
     PVDB_LAUNCH_CHECK();
-    k_scan_add<<<nb, 1024, 0, st>>>(b->i_starts, npix, b->scan_tmp, nb, b->counters, b->cap_samples);
+    PVDB_CUDA(pvdb_launch_pdl(k_scan_add, dim3(nb), dim3(1024), 0, st, b->i_starts, npix, (const int32_t*)b->scan_tmp, nb, b->counters, b->cap_samples));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_scan", st);
-    k_render_pass2<<<pgrid, 256, 0, st>>>(C, c2w, row_begin, rows, b->n_samples, b->i_starts, b->tmins, b->tmaxs, b->s_ray,
-                                          b->s_weight, b->s_feat, b->cap_samples, out_rgb, b->counters);
+    PVDB_CUDA(pvdb_launch_pdl(k_render_pass2, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->i_starts, b->tmins, b->tmaxs, b->s_ray,
+                                          b->s_weight, b->s_feat, b->cap_samples, out_rgb, b->counters));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_pass2", st);
     static bool attr_set = false;
@@ -436,7 +442,8 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
         PVDB_LAUNCH_CHECK();
     }
     pvdb_prof_mark("render_mlp", st);
-    k_render_composite<<<pvdb_grid_for(npix, 256), 256, 0, st>>>(b->n_samples, b->i_starts, b->s_rgb, npix, b->cap_samples, out_rgb);
+    PVDB_CUDA(pvdb_launch_pdl(k_render_composite, dim3(pvdb_grid_for(npix, 256)), dim3(256), 0, st, (const int32_t*)b->n_samples, (const int32_t*)b->i_starts,
+                              (const float*)b->s_rgb, npix, b->cap_samples, out_rgb));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_composite", st);
     return PVDB_OK;

@@ -95,6 +95,7 @@ struct TcWeights {
 // Build the weight image (see the smem map) in global memory.  Any grid; ~22 k elements.
 // net_packed != nullptr (training): also the activation-gradient kernel's image, PVDB_BWD_IMG_OFFSET further on.
 __global__ void __launch_bounds__(256) k_prep_fwd_image(TcWeights Wt, unsigned char* __restrict__ img, const float* __restrict__ net_packed) {
+    pvdb_pdl_wait();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     if (net_packed) prep_bwd_image(net_packed, img + PVDB_BWD_IMG_OFFSET, gtid, gsz);
     for (int e = gtid; e < WD * K0P; e += gsz) {
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
 // ---- merged renderer MLP (renderer.cu:83-119): features from the gathered list, PE from the pixel's view direction
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
+    pvdb_pdl_wait();
     const int64_t M = min((int64_t)A.counters[0], A.cap);
     auto feat = [&](int64_t s, bool valid, float* x) {
         if (!valid) return;
@@ -500,9 +502,9 @@ int pvdb_render_mlp_tc(const void* render_mlp_args, cudaStream_t st) {
     W.w2 = A.w2; W.w2_sn = 1; W.w2_sk = 3;
     W.b0 = A.b0; W.b1 = A.b1; W.b2 = A.b2;
     PVDB_CHECK_ARG(A.img, "w_img scratch missing (tensor-core rgbnet)");
-    k_prep_fwd_image<<<PVDB_SMS, 256, 0, st>>>(W, A.img, nullptr);
+    PVDB_CUDA(pvdb_launch_pdl(k_prep_fwd_image, dim3(PVDB_SMS), dim3(256), 0, st, W, A.img, (const float*)nullptr));
     PVDB_LAUNCH_CHECK();
-    k_render_mlp_tc<<<PVDB_SMS, FWD_THREADS, SM_TOTAL, st>>>(A);
+    PVDB_CUDA(pvdb_launch_pdl(k_render_mlp_tc, dim3(PVDB_SMS), dim3(FWD_THREADS), SM_TOTAL, st, A));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

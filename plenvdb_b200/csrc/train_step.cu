@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(256) k_density_scatter(pvdb_tree t, float* __r
                                                          const float* __restrict__ s_gden, const int32_t* __restrict__ counters,
                                                          int32_t* __restrict__ touched, int32_t* __restrict__ touched_list,
                                                          int32_t* __restrict__ counters_w, int64_t cap_alpha) {
+    pvdb_pdl_wait();
     const int64_t n = min((int64_t)counters[CNT_M_ALPHA], cap_alpha);
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
         const float g = s_gden[s];
@@ -921,8 +922,9 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                                                              b->cap_keep);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("ray_bwd", st);
-        k_density_scatter<<<PVDB_SMS * 8, 256, 0, sb>>>(*b->tree, b->den_grad, b->s_xyz, b->s_gden, b->counters, b->den_touched,
-                                                        b->den_touched_list, b->counters, b->cap_alpha);
+        PVDB_CUDA(pvdb_launch_pdl(k_density_scatter, dim3(PVDB_SMS * 8), dim3(256), 0, sb, *b->tree, b->den_grad, (const float*)b->s_xyz,
+                                  (const float*)b->s_gden, (const int32_t*)b->counters, b->den_touched, b->den_touched_list, b->counters,
+                                  b->cap_alpha));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("density_scatter", st);
         if (sd && peers && cfg->use_tensor_cores) {
