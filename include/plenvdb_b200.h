@@ -320,8 +320,10 @@ typedef struct pvdb_render_bufs {
     float *s_weight;                 /* [cap] */
     float *s_feat;                   /* [cap][12] */
     float *s_rgb;                    /* [cap][3] weight * sigmoid(rgbnet) */
-    int32_t *counters;               /* [8]: 0 total samples, 1 overflow flag, 2 rays whose two passes disagree */
+    int32_t *counters;               /* [8]: 0 total samples, 1 overflow flag, 2 rays whose two passes disagree,
+                                      * 3 pixels with samples (zero between frames) */
     void *w_img;                     /* >= 256 KiB scratch: tf32 hi/lo weight image (use_tensor_cores) */
+    int32_t *active_list;            /* [npix] pixels with samples, built by pass 1 for pass 2 */
 } pvdb_render_bufs;
 
 /* Renders rows [row_begin,row_end) of the H x W image for camera `c2w` (device float[16], row-major 4x4) into

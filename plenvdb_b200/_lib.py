@@ -93,7 +93,7 @@ class pvdb_render_bufs(C.Structure):
         ("n_samples", c_ptr), ("i_starts", c_ptr), ("tmins", c_ptr), ("tmaxs", c_ptr), ("scan_tmp", c_ptr),
         ("cap_samples", C.c_int64),
         ("s_ray", c_ptr), ("s_weight", c_ptr), ("s_feat", c_ptr), ("s_rgb", c_ptr), ("counters", c_ptr),
-        ("w_img", c_ptr),
+        ("w_img", c_ptr), ("active_list", c_ptr),
     ]
 
 

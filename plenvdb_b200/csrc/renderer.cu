@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int RC_TOTAL = 0, RC_OVERFLOW = 1, RC_INCONSISTENT = 2;
+constexpr int RC_TOTAL = 0, RC_OVERFLOW = 1, RC_INCONSISTENT = 2, RC_ACTIVE = 3;   // RC_ACTIVE: pixels with samples (pass 1 -> pass 2)
 
 // alpha = 1 - pow(1 + exp(v + shift), -interval) exactly as nvcc compiles renderer.cu:256 / :350: the final scale
 // multiply of expf is contracted with the "+ 1" into one fma, so this expression is deliberately left to the
@@ -62,12 +62,9 @@ __device__ __forceinline__ int pixel_of_thread(int W, int rows, int& local) {
     return local;
 }
 
-__global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float* __restrict__ c2w, int row_begin, int rows,
-                                                      int32_t* __restrict__ n_samples, float* __restrict__ tmins,
-                                                      float* __restrict__ tmaxs) {
-    pvdb_pdl_wait();
-    int local;
-    if (pixel_of_thread(C.W, rows, local) < 0) return;
+// Pass 1 of one pixel: counts the kept samples and tightens [tmin, tmax] (renderer.cu:222-268).
+__device__ __forceinline__ int pass1_march(const RenderConst& C, const float* __restrict__ c2w, int row_begin, int local,
+                                           float* __restrict__ tmins, float* __restrict__ tmaxs) {
     const int n = row_begin * C.W + local;
     Ray R;
     ray_setup(C, c2w, n, R);
@@ -102,10 +99,36 @@ __global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float
         if (!update_tmin) { tmin_out = __fsub_rn(t, R.steplen); update_tmin = true; }
         if ((double)T_cum < 1e-3) { tmax_out = t; break; }
     }
-    n_samples[local] = ns;
     tmins[local] = tmin_out;
     tmaxs[local] = tmax_out;
+    return ns;
 }
+
+__global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float* __restrict__ c2w, int row_begin, int rows,
+                                                      int32_t* __restrict__ n_samples, float* __restrict__ tmins,
+                                                      float* __restrict__ tmaxs, int32_t* __restrict__ active_list,
+                                                      int32_t* __restrict__ counters, float* __restrict__ out_rgb) {
+    pvdb_pdl_wait();
+    int local;
+    const bool in_image = pixel_of_thread(C.W, rows, local) >= 0;
+    int ns = 0;
+    if (in_image) ns = pass1_march(C, c2w, row_begin, local, tmins, tmaxs);
+    if (in_image) {
+        n_samples[local] = ns;
+        if (ns == 0) { out_rgb[local * 3] = C.bg; out_rgb[local * 3 + 1] = C.bg; out_rgb[local * 3 + 2] = C.bg; }   // :324-329
+    }
+    // pixels that have samples are appended to the work list of pass 2 (one atomic per warp; a warp's pixels stay together)
+    const unsigned act = __ballot_sync(0xffffffffu, ns > 0);
+    if (act) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counters + RC_ACTIVE, __popc(act));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (ns > 0) active_list[base + __popc(act & ((1u << lane) - 1))] = local;
+    }
+}
+
+
 
 // ---- exclusive scan over npix ints: 4096 items per CTA, then the block sums, then the offsets
 __global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n,
@@ -176,16 +199,14 @@ __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float
                                                       const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
                                                       const float* __restrict__ tmins, const float* __restrict__ tmaxs,
                                                       int32_t* __restrict__ s_ray, float* __restrict__ s_weight,
-                                                      float* __restrict__ s_feat, int64_t cap, float* __restrict__ out_rgb,
-                                                      int32_t* __restrict__ counters) {
+                                                      float* __restrict__ s_feat, int64_t cap, const int32_t* __restrict__ active_list,
+                                                      float* __restrict__ out_rgb, int32_t* __restrict__ counters) {
     pvdb_pdl_wait();
-    int local;
-    if (pixel_of_thread(C.W, rows, local) < 0) return;
+    // one thread per pixel that has samples (the list pass 1 built): full warps instead of the ~15 live lanes of a pixel tile
+    const int n_active = counters[RC_ACTIVE];
+  for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_active; slot += gridDim.x * blockDim.x) {
+    const int local = active_list[slot];
     const int ns = n_samples[local];
-    if (ns == 0) {   // :324-329
-        out_rgb[local * 3] = C.bg; out_rgb[local * 3 + 1] = C.bg; out_rgb[local * 3 + 2] = C.bg;
-        return;
-    }
     const int n = row_begin * C.W + local;
     Ray R;
     ray_setup(C, c2w, n, R);
@@ -258,6 +279,7 @@ __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float
     }
     const float last = __fmul_rn(T_cum, C.bg);   // :364-365
     out_rgb[local * 3] = last; out_rgb[local * 3 + 1] = last; out_rgb[local * 3 + 2] = last;
+  }
 }
 
 __global__ void __launch_bounds__(NT, 1) k_render_mlp(RenderMlpArgs A) {
@@ -351,9 +373,10 @@ __global__ void __launch_bounds__(NT, 1) k_render_mlp(RenderMlpArgs A) {
 
 __global__ void __launch_bounds__(256) k_render_composite(const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
                                                           const float* __restrict__ s_rgb, int npix, int64_t cap,
-                                                          float* __restrict__ out_rgb) {
+                                                          float* __restrict__ out_rgb, int32_t* __restrict__ counters) {
     pvdb_pdl_wait();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) counters[RC_ACTIVE] = 0;      // pass 2 of this frame is done with it; pass 1 of the next frame counts from 0
     if (p >= npix) return;
     const int ns = n_samples[p];
     if (ns == 0) return;
@@ -409,7 +432,9 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
     const int rows = row_end - row_begin, npix = rows * cfg->W;
     const int tiles = ((cfg->W + 7) / 8) * ((rows + 3) / 4);
     const int pgrid = pvdb_grid_for((int64_t)tiles * 32, 256);
-    PVDB_CUDA(pvdb_launch_pdl(k_render_pass1, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs));
+    PVDB_CHECK_ARG(b->active_list, "active_list scratch missing");
+    PVDB_CUDA(pvdb_launch_pdl(k_render_pass1, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs, b->active_list,
+                              b->counters, out_rgb));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_pass1", st);
     const int nb = (npix + 4095) / 4096;
@@ -421,8 +446,9 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
     PVDB_CUDA(pvdb_launch_pdl(k_scan_add, dim3(nb), dim3(1024), 0, st, b->i_starts, npix, (const int32_t*)b->scan_tmp, nb, b->counters, b->cap_samples));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_scan", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_render_pass2, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->i_starts, b->tmins, b->tmaxs, b->s_ray,
-                                          b->s_weight, b->s_feat, b->cap_samples, out_rgb, b->counters));
+    PVDB_CUDA(pvdb_launch_pdl(k_render_pass2, dim3(min(pgrid, PVDB_SMS * 8)), dim3(256), 0, st, C, c2w, row_begin, rows, (const int32_t*)b->n_samples,
+                              (const int32_t*)b->i_starts, (const float*)b->tmins, (const float*)b->tmaxs, b->s_ray, b->s_weight, b->s_feat, b->cap_samples,
+                              (const int32_t*)b->active_list, out_rgb, b->counters));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_pass2", st);
     static bool attr_set = false;
@@ -443,7 +469,7 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
     }
     pvdb_prof_mark("render_mlp", st);
     PVDB_CUDA(pvdb_launch_pdl(k_render_composite, dim3(pvdb_grid_for(npix, 256)), dim3(256), 0, st, (const int32_t*)b->n_samples, (const int32_t*)b->i_starts,
-                              (const float*)b->s_rgb, npix, b->cap_samples, out_rgb));
+                              (const float*)b->s_rgb, npix, b->cap_samples, out_rgb, b->counters));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_composite", st);
     return PVDB_OK;

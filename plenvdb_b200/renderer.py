@@ -119,7 +119,8 @@ class MGRenderer:
         self.s = dict(n_samples=torch.zeros(npix, **i32), i_starts=torch.zeros(npix + 1, **i32), tmins=torch.zeros(npix, **f32),
                       tmaxs=torch.zeros(npix, **f32), scan_tmp=torch.zeros(npix // 4096 + 3, **i32), s_ray=torch.zeros(cap, **i32),
                       s_weight=torch.zeros(cap, **f32), s_feat=torch.zeros(cap, 12, **f32), s_rgb=torch.zeros(cap, 3, **f32),
-                      counters=torch.zeros(8, **i32), w_img=torch.zeros(256 * 1024 // 4, **i32))
+                      counters=torch.zeros(8, **i32), w_img=torch.zeros(256 * 1024 // 4, **i32),
+                      active_list=torch.zeros(npix, **i32))
         b = _lib.pvdb_render_bufs()
         b.idx_tree = C.pointer(self.idx_topo.c)
         b.idx_plane, b.dendata, b.coldata = self.idx_plane.data_ptr(), self.dendata.data_ptr(), self.coldata.data_ptr()
