@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epo
                                                    int32_t* __restrict__ k0_list, int32_t* __restrict__ counters, int cnt_den, int cnt_k0) {
     __shared__ int warp_cnt[32];
     __shared__ int running;
+    pvdb_pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
     for (int i = threadIdx.x; i < P.n_leaf; i += 1024) me.flags[parity][i] = (den_touched[i] | k0_touched[i]) != 0;
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epo
 __global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch, int parity, const float* __restrict__ den_grad,
                                                  const float* __restrict__ k0_grad,
                                                  const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
+    pvdb_pdl_wait();
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
     const int n = counters[cnt_den];
     float* buf = me.grad[parity];
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch
 __global__ void __launch_bounds__(256) k_dp_reduce(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ den_grad,
                                                    float* __restrict__ k0_grad,
                                                    const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
+    pvdb_pdl_wait();
     if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_B, epoch);
     __syncthreads();
     const int n = counters[cnt_den];
@@ -192,6 +195,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce(pvdb_dp_peers P, uint32_t epo
 // grid-wide dependency and a single latency of peer loads.
 __global__ void __launch_bounds__(1024) k_dp_net(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ net_grad) {
     constexpr int SL = NET_PAD / NET_SLICES;       // floats per slice (multiple of 4)
+    pvdb_pdl_wait();
     const int g = blockIdx.x;
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
     const int i = g * SL + threadIdx.x * 4;
@@ -273,14 +277,16 @@ extern "C" int pvdb_dp_exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_b
     const int parity = step & 1;
     const uint32_t epoch = step + 1;                        // monotone; the signal words start at 0
     const int CNT_DEN = 2, CNT_K0 = 4;                      // counters[] slots of pvdb_train_bufs (include/plenvdb_b200.h)
-    k_dp_union<<<1, 1024, 0, st>>>(*P, epoch, parity, b->den_touched, b->k0_touched, b->den_touched_list, b->k0_touched_list, b->counters,
-                                   CNT_DEN, CNT_K0);
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_union, dim3(1), dim3(1024), 0, st, *P, epoch, parity, b->den_touched, b->k0_touched, b->den_touched_list,
+                              b->k0_touched_list, b->counters, CNT_DEN, CNT_K0));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_union", st);
-    k_dp_pack<<<PVDB_SMS, 256, 0, st>>>(*P, epoch, parity, b->den_grad, b->k0_grad, b->den_touched_list, b->counters, CNT_DEN);
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_pack, dim3(PVDB_SMS), dim3(256), 0, st, *P, epoch, parity, (const float*)b->den_grad, (const float*)b->k0_grad,
+                              (const int32_t*)b->den_touched_list, (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_pack", st);
-    k_dp_reduce<<<PVDB_SMS * 2, 256, 0, st>>>(*P, epoch, parity, b->den_grad, b->k0_grad, b->den_touched_list, b->counters, CNT_DEN);
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_reduce, dim3(PVDB_SMS * 2), dim3(256), 0, st, *P, epoch, parity, b->den_grad, b->k0_grad,
+                              (const int32_t*)b->den_touched_list, (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_reduce", st);
     return PVDB_OK;
@@ -289,7 +295,7 @@ extern "C" int pvdb_dp_exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_b
 extern "C" int pvdb_dp_exchange_net(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
     if (int rc = check_peers(P, b)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    k_dp_net<<<NET_SLICES, 1024, 0, st>>>(*P, step + 1, step & 1, b->net_grad);
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_net, dim3(NET_SLICES), dim3(1024), 0, st, *P, (uint32_t)(step + 1), (int)(step & 1), b->net_grad));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_net", st);
     return PVDB_OK;
