@@ -618,12 +618,14 @@ struct UpdateArgs {
     int32_t *den_touched, *k0_touched, *den_list, *k0_list, *counters;
     float den_stepsz, k0_stepsz, net_stepsize, eps, b0, b1;
     int leaf_blocks;
+    int block_offset;   // 0: leaf work starts at CTA 0; leaf_blocks: a launch of the rgbnet Adam CTAs only
 };
 // Work items: (touched density leaf) and (touched k0 leaf, quarter); a persistent grid strides over them.
 __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
     pvdb_pdl_wait();
-    if ((int)blockIdx.x >= U.leaf_blocks) {
-        const int i = ((int)blockIdx.x - U.leaf_blocks) * blockDim.x + threadIdx.x;
+    const int bid = (int)blockIdx.x + U.block_offset;
+    if (bid >= U.leaf_blocks) {
+        const int i = (bid - U.leaf_blocks) * blockDim.x + threadIdx.x;
         if (i < PVDB_NET_N) {
             pvdb_dense_adam_update(U.net[i], U.net_m[i], U.net_v[i], U.net_g[i], 1.f, false, U.net_stepsize, U.b0, U.b1, U.eps);
             U.net_g[i] = 0.f;
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
     }
     const int nd = U.counters[CNT_N_TOUCHED_DEN], nk = U.counters[CNT_N_TOUCHED_K0];
     const float omb0 = __fsub_rn(1.0f, U.b0), omb1 = __fsub_rn(1.0f, U.b1);
-    for (int w = blockIdx.x; w < nd + nk * 4; w += U.leaf_blocks) {
+    for (int w = bid; w < nd + nk * 4; w += U.leaf_blocks) {
         const bool is_den = w < nd;
         const int leaf = is_den ? U.den_list[w] : U.k0_list[(w - nd) >> 2];
         const int part = is_den ? 0 : (w - nd) & 3;
@@ -852,6 +854,31 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         sd->ok = true;
     }
 
+    // the fused sparse Adam: CTAs [0, leaf_blocks) walk the touched leaves, the rest update the rgbnet.  part 0 = both in one
+    // launch, 1 = leaves only, 2 = rgbnet only (the leaf half can run on the side stream under the weight-gradient kernel)
+    UpdateArgs U;
+    U.tree = *b->tree;
+    U.den = b->den; U.den_g = b->den_grad; U.den_m = b->den_m; U.den_v = b->den_v;
+    U.k0 = b->k0; U.k0_g = b->k0_grad; U.k0_m = b->k0_m; U.k0_v = b->k0_v;
+    U.net = b->net; U.net_g = b->net_grad; U.net_m = b->net_m; U.net_v = b->net_v;
+    U.den_touched = b->den_touched; U.k0_touched = b->k0_touched; U.counters = b->counters;
+    U.den_list = b->den_touched_list; U.k0_list = b->k0_touched_list;
+    U.den_stepsz = cfg->den_stepsz; U.k0_stepsz = cfg->k0_stepsz;
+    U.net_stepsize = pvdb_dense_adam_stepsize(cfg->net_lr, cfg->beta0, cfg->beta1, cfg->net_step);
+    U.eps = cfg->eps; U.b0 = cfg->beta0; U.b1 = cfg->beta1;
+    U.leaf_blocks = PVDB_SMS * 4;
+    U.block_offset = 0;
+    const int net_blocks = (PVDB_NET_N + 255) / 256;
+    auto launch_update = [&](cudaStream_t s_, int part) -> int {
+        UpdateArgs V = U;
+        V.block_offset = part == 2 ? U.leaf_blocks : 0;
+        const int grid = part == 0 ? U.leaf_blocks + net_blocks : part == 1 ? U.leaf_blocks : net_blocks;
+        PVDB_CUDA(pvdb_launch_pdl(k_update_fused, dim3(grid), dim3(256), 0, s_, V));
+        PVDB_LAUNCH_CHECK();
+        return PVDB_OK;
+    };
+    bool update_done = false;
+
     if (do_fwd) {
         PVDB_CHECK_ARG(rays_o && rays_d && viewdirs, "null rays");
         if (sd) {
@@ -927,21 +954,35 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                                   b->cap_alpha));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("density_scatter", st);
-        if (sd && peers && cfg->use_tensor_cores) {
-            // data-parallel step: the grid gradients are final once the activation-gradient kernel (main) and the density
-            // scatter (side) are done, so their exchange over NVLink runs on the side stream UNDER the weight-gradient kernel;
-            // only the 88 KB of rgbnet gradients are exchanged after it.
+        if (sd && cfg->use_tensor_cores && (peers || do_upd)) {
+            // The grid gradients are final once the activation-gradient kernel (main) and the density scatter (side) are done.
+            // Everything that only needs them runs on the side stream UNDER the weight-gradient kernel: the NVLink tile
+            // exchange of a data-parallel step, and the sparse Adam of the touched leaves.  After the weight-gradient kernel
+            // only the 88 KB rgbnet exchange and the rgbnet Adam are left.
             int rc = pvdb_rgbnet_backward_act_tc(cfg, b, viewdirs, st);
             if (rc) return rc;
             PVDB_CUDA(cudaEventRecord(sd->fork2, st));
             PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));
-            rc = pvdb_dp_exchange_tiles(peers, b, dp_step, sd->s);
-            if (rc) return rc;
+            if (peers) {
+                rc = pvdb_dp_exchange_tiles(peers, b, dp_step, sd->s);
+                if (rc) return rc;
+            }
+            if (do_upd) {
+                rc = launch_update(sd->s, 1);
+                if (rc) return rc;
+            }
             PVDB_CUDA(cudaEventRecord(sd->join, sd->s));
             rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st);
             if (rc) return rc;
-            rc = pvdb_dp_exchange_net(peers, b, dp_step, st);
-            if (rc) return rc;
+            if (peers) {
+                rc = pvdb_dp_exchange_net(peers, b, dp_step, st);
+                if (rc) return rc;
+            }
+            if (do_upd) {
+                rc = launch_update(st, 2);
+                if (rc) return rc;
+                update_done = true;
+            }
             PVDB_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
         } else {
             if (sd) {
@@ -958,14 +999,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             }
         }
     }
-    if (do_upd) {
-        UpdateArgs U;
-        U.tree = *b->tree;
-        U.den = b->den; U.den_g = b->den_grad; U.den_m = b->den_m; U.den_v = b->den_v;
-        U.k0 = b->k0; U.k0_g = b->k0_grad; U.k0_m = b->k0_m; U.k0_v = b->k0_v;
-        U.net = b->net; U.net_g = b->net_grad; U.net_m = b->net_m; U.net_v = b->net_v;
-        U.den_touched = b->den_touched; U.k0_touched = b->k0_touched; U.counters = b->counters;
-        U.den_list = b->den_touched_list; U.k0_list = b->k0_touched_list;
+    if (do_upd && !update_done) {
         if (!do_bwd && !(phases & PVDB_PHASE_LISTS_READY)) {   // gradients (and flags) came from elsewhere, e.g. a data-parallel all-reduce: rebuild the lists
             const int n_leaf = b->tree->n_leaf;
             PVDB_CUDA(cudaMemsetAsync(b->counters + CNT_N_TOUCHED_DEN, 0, sizeof(int32_t), st));
@@ -977,13 +1011,8 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                                                                           b->counters + CNT_N_TOUCHED_K0);
             PVDB_LAUNCH_CHECK();
         }
-        U.den_stepsz = cfg->den_stepsz; U.k0_stepsz = cfg->k0_stepsz;
-        U.net_stepsize = pvdb_dense_adam_stepsize(cfg->net_lr, cfg->beta0, cfg->beta1, cfg->net_step);
-        U.eps = cfg->eps; U.b0 = cfg->beta0; U.b1 = cfg->beta1;
-        U.leaf_blocks = PVDB_SMS * 4;
-        const int net_blocks = (PVDB_NET_N + 255) / 256;
-        PVDB_CUDA(pvdb_launch_pdl(k_update_fused, dim3(U.leaf_blocks + net_blocks), dim3(256), 0, st, U));
-        PVDB_LAUNCH_CHECK();
+        int rc = launch_update(st, 0);
+        if (rc) return rc;
         pvdb_prof_mark("update_fused", st);
     }
     return PVDB_OK;
