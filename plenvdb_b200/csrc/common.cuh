@@ -50,8 +50,9 @@ bool pvdb_prof_active();
 // serialisation and block at pvdb_pdl_wait (first statement) until the kernel before them has completed and its memory is
 // visible: the launch itself no longer waits for the predecessor's completion handshake, which takes ~1.5 us off each of
 // the ten kernel boundaries of a step (measured: 0.224 -> 0.209 ms).  Letting the dependents start even earlier
-// (griddepcontrol.launch_dependents at the top of every kernel) was measured slower (0.233 ms): the early-resident CTAs
-// of the next kernels take registers and thread slots from the running one.  The wait is a no-op in a normally launched
+// (griddepcontrol.launch_dependents at the top of every kernel: 0.233 ms; only in the two small kernels that precede a
+// tensor-core kernel, so that its weight-image TMA overlaps their tail: 0.204 vs 0.2005 ms) was measured slower: the
+// early-resident CTAs of the next kernel take registers and thread slots from the running one.  The wait is a no-op in a normally launched
 // kernel.
 __device__ __forceinline__ void pvdb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 template <typename... KArgs, typename... Args>

@@ -140,7 +140,8 @@ constexpr int FWD_THREADS = 416;
 constexpr int N_LANE_THREADS = 256;
 
 template <class FeatFn, class OutFn, class ActFn>
-__device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__ img, int64_t M, FeatFn feat, OutFn out, ActFn act) {
+__device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__ img, const int32_t* __restrict__ m_ptr, int64_t m_cap,
+                          FeatFn feat, OutFn out, ActFn act) {
     const int tid = threadIdx.x, warp = tid >> 5;
     int tile_no = 0;
     TC_T(0);
@@ -169,6 +170,10 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Everything above (barriers, TMEM, the weight image in flight) is independent of the kernel before this one: with a
+    // programmatic dependent launch it overlaps that kernel's tail.  The sample count and the lists are read after the wait.
+    pvdb_pdl_wait();
+    const int64_t M = min((int64_t)*m_ptr, m_cap);
     const int64_t n_tiles = (M + TM - 1) / TM;
     TC_T(1);
 
@@ -342,8 +347,6 @@ struct TrainFwdArgs {
 
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    pvdb_pdl_wait();
-    const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
     auto feat = [&](int64_t s, bool valid, float* x) {
         if (!valid) {   // lanes past M in the last tile: zero input row in HBM (the weight-gradient pass reads whole tiles)
             if (A.k_x) {
@@ -410,14 +413,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
 #pragma unroll
         for (int i = 0; i < 32; ++i) g[i * 16] = valid ? h[i] : 0.f;   // zero rows past M: the weight-gradient pass reads whole tiles
     };
-    mlp_tiles(smem, A.img, M, feat, out, act);
+    mlp_tiles(smem, A.img, A.counters + CNT_M_KEEP, A.cap_keep, feat, out, act);
 }
 
 // ---- merged renderer MLP (renderer.cu:83-119): features from the gathered list, PE from the pixel's view direction
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    pvdb_pdl_wait();
-    const int64_t M = min((int64_t)A.counters[0], A.cap);
     auto feat = [&](int64_t s, bool valid, float* x) {
         if (!valid) return;
         const float4* f = reinterpret_cast<const float4*>(A.s_feat + s * 12);
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs 
         for (int j = 0; j < 3; ++j) A.s_rgb[s * 3 + j] = w / (1 + expf(-raw[j]));   // final_render (:115-117)
     };
     auto act = [&](int64_t, bool, int, int, const float*) {};
-    mlp_tiles(smem, A.img, M, feat, out, act);
+    mlp_tiles(smem, A.img, A.counters, A.cap, feat, out, act);
 }
 
 }  // namespace

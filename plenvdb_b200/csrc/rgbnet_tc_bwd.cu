@@ -82,7 +82,6 @@ __device__ __forceinline__ void issue_b1(uint32_t tmem, uint32_t d_col, uint32_t
 
 __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    pvdb_pdl_wait();
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + B1_BAR;
@@ -103,6 +102,7 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pvdb_pdl_wait();   // the prologue above (barriers, TMEM, weight image in flight) does not depend on the kernel before
     const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
     const int64_t n_tiles = (M + TM - 1) / TM;
 
