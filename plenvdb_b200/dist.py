@@ -67,6 +67,10 @@ def allreduce_sparse_grads(den_grad, k0_grad, net_grad, leaves, group=None):
     return buf.numel() * 4
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank cannot set up the CUDA-IPC symmetric blocks."""
+
+
 class PeerExchange:
     """The NVLink peer-memory exchange (csrc/dp_exchange.cu): one symmetric block per rank, mapped by every peer through
     CUDA IPC; the handles travel over torch.distributed (plumbing), the gradients never touch NCCL."""
@@ -81,21 +85,39 @@ class PeerExchange:
         nbytes = _lib.lib.pvdb_dp_symm_bytes(int(n_leaf), cap)
         own = C.c_void_p()
         handle = C.create_string_buffer(64)
-        _lib.call("pvdb_dp_symm_alloc", nbytes, C.byref(own), handle)
+        self._own, self._opened = None, []
+        # Every rank takes part in both collectives whatever happens locally, and all ranks agree on the outcome: a rank
+        # whose allocation or mapping fails (no peer access, IPC disabled in the container) must not leave the others hanging.
+        err = None
+        try:
+            _lib.call("pvdb_dp_symm_alloc", nbytes, C.byref(own), handle)
+            self._own = own
+        except _lib.PvdbError as e:
+            err = str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        dist.all_gather_object(handles, None if err else bytes(handle.raw), group=group)
         self.peers = _lib.pvdb_dp_peers()
         self.peers.world, self.peers.rank, self.peers.n_leaf, self.peers.cap_leaves = self.world, self.rank, int(n_leaf), cap
-        self._own, self._opened = own, []
-        for r in range(self.world):
-            if r == self.rank:
-                self.peers.base[r] = own.value
-            else:
-                p = C.c_void_p()
-                _lib.call("pvdb_dp_symm_open", C.create_string_buffer(handles[r], 64), C.byref(p))
-                self.peers.base[r] = p.value
-                self._opened.append(p)
-        dist.barrier(group=group)   # every block is zeroed and mapped before the first signal is written
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.peers.base[r] = own.value
+                    else:
+                        p = C.c_void_p()
+                        _lib.call("pvdb_dp_symm_open", C.create_string_buffer(handles[r], 64), C.byref(p))
+                        self.peers.base[r] = p.value
+                        self._opened.append(p)
+            except _lib.PvdbError as e:
+                err = str(e)
+        elif err is None:
+            err = "a peer could not allocate its symmetric block"
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err, group=group)   # also the barrier: every block is zeroed and mapped before the first signal
+        bad = [(r, e) for r, e in enumerate(oks) if e is not None]
+        if bad:
+            self.close()
+            raise PeerExchangeUnavailable("NVLink peer exchange unavailable (rank %d: %s)" % bad[0])
         self.step = 0
         self.nbytes = nbytes
 
@@ -142,8 +164,13 @@ class DataParallelTrainer:
         self.peer = None
         self.last_exchange_bytes = 0
         if self.world > 1 and exchange == "nvlink":
-            self.peer = PeerExchange(tr.topo.n_leaf, group=self.group)
-            return
+            try:
+                self.peer = PeerExchange(tr.topo.n_leaf, group=self.group)
+                return
+            except PeerExchangeUnavailable as e:      # raised on all ranks together: fall back to NCCL everywhere
+                import warnings
+                warnings.warn("%s; using the NCCL all-reduce of packed tiles instead" % e)
+                self.exchange = "nccl"
         self.flags = torch.zeros(2 * n_leaf, dtype=torch.int32, device=dev)
         self.union_list = torch.zeros(n_leaf, dtype=torch.int32, device=dev)
         self.union_count = torch.zeros(1, dtype=torch.int32, device=dev)
