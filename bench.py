@@ -350,18 +350,30 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
                 False, H, W)
     poses = torch.from_numpy(synth.render_cameras(200).reshape(200, 16)).to(dev)
     nf = args.frames
+    # N > 1: interleaved 4-row groups, every rank's composite kernel writes its pixels into rank 0's frame over NVLink peer
+    # memory (no collective); --render-gather nccl = contiguous row bands + an NCCL gather
+    peer = None
+    sharding = "single GPU"
+    if world > 1:
+        sharding = "contiguous row bands + NCCL gather"
+        if args.render_gather == "peer":
+            try:
+                peer = pdist.PeerFrame(H, W, band_rows=4)
+                sharding = "interleaved 4-row groups, frame assembled in rank 0's memory by peer stores over NVLink (no collective)"
+            except pdist.PeerExchangeUnavailable as e:
+                sys.stderr.write("render: %s; falling back to the NCCL gather\n" % e)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
     for i in range(3):
-        pdist.render_sharded(r, poses[i], rank, world)
+        pdist.render_sharded(r, poses[i], rank, world, peer=peer)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(nf):
-        pdist.render_sharded(r, poses[(3 + i) % 200], rank, world)
+        pdist.render_sharded(r, poses[(3 + i) % 200], rank, world, peer=peer)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -375,7 +387,7 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
     e0.record()
     for i in range(nf):
         r.c2w.copy_(hposes[(3 + i) % 200], non_blocking=True)
-        img = pdist.render_sharded(r, r.c2w, rank, world)
+        img = pdist.render_sharded(r, r.c2w, rank, world, peer=peer)
         if rank == 0:
             himg.copy_(img, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -385,7 +397,12 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     c = r.counters()
-    return {"metric": "merged-VDB render FPS 800x800", "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "frames": nf,
+    if peer is not None:
+        perr = peer.error()
+        peer.close()
+        if perr:
+            raise RuntimeError("peer frame assembly reported error %d (a rank did not arrive in time)" % perr)
+    return {"metric": "merged-VDB render FPS 800x800", "sharding": sharding, "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "frames": nf,
             "e2e_fps": nf * 1e3 / float(t.item()), "d2h_bytes_per_frame": H * W * 3 * 4, "samples_last_band": c["total"],
             "inconsistent_rays_last_band": c["inconsistent"], "merged_voxels": n, "row_bands": world,
             "gpu_launches_per_frame": r.launches_last_call()}
@@ -449,6 +466,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=20, help="frames timed for the render FPS sub-result")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--render-gather", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: how rank 0 gets the frame (peer stores over NVLink, or contiguous bands + NCCL gather)")
     ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl"],
                     help="N>1 gradient exchange: own kernels over NVLink peer memory, or NCCL all-reduce of the packed tiles")
     ap.add_argument("--fp32-rgbnet", action="store_true", help="use the fp32 CUDA-core rgbnet instead of the tcgen05 one")

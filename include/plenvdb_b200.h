@@ -330,6 +330,35 @@ typedef struct pvdb_render_bufs {
  * out_rgb (device float[(row_end-row_begin)*W*3]).  No allocation, no synchronisation. */
 int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bufs* bufs, const float* c2w,
                      int row_begin, int row_end, float* out_rgb, void* stream);
+/* ---- tile-sharded rendering across the GPUs of one box (the reference renders on one GPU) ---------------------
+ * Rows are dealt to the ranks in groups of band_rows rows, round-robin (row r belongs to rank (r / band_rows) % world), so
+ * every rank gets the same share of the object whatever rows it occupies.  pvdb_interleaved_rows = rows that fall to `rank`. */
+int pvdb_interleaved_rows(int H, int band_rows, int rank, int world);
+/* Renders this rank's rows into band_out (device float[rows*W*3], local rows in ascending image order) and, when frame_out is
+ * not NULL, also stores every pixel at its place in the full frame frame_out (device float[H*W*3]; it may be ANOTHER GPU's
+ * memory mapped through CUDA IPC — plain stores over NVLink).  No allocation, no synchronisation. */
+int pvdb_render_rows_interleaved(const pvdb_render_cfg* cfg, const pvdb_render_bufs* bufs, const float* c2w, int band_rows,
+                                 int rank, int world, float* band_out, float* frame_out, void* stream);
+/* Frame assembly without a collective: every rank owns one symmetric block of pvdb_frame_symm_bytes(H, W) bytes (allocate with
+ * pvdb_dp_symm_alloc, exchange the IPC handles by any transport, map with pvdb_dp_symm_open; base[r] = rank r's block as mapped
+ * in THIS process).  pvdb_render_frame_sharded(frame_no = 0,1,2,... identical on all ranks) renders this rank's interleaved rows
+ * and its composite kernel writes them straight into ROOT's frame buffer (frame_no & 1) over NVLink; a release/acquire signal
+ * per rank replaces the gather.  When the call's work has completed on root's stream, pvdb_frame_ptr(frame_no) on root is the
+ * full frame; it stays valid until root's call for frame_no + 2 starts (consume it in stream order before that).  A rank that
+ * does not arrive within 2 s sets the error word (pvdb_frame_error: 1) instead of hanging the GPU. */
+typedef struct {
+    int32_t world, rank, root;   /* world <= 8 (one NVSwitch domain) */
+    int32_t H, W;
+    int32_t reserved;
+    void* base[8];
+} pvdb_frame_peers;
+size_t pvdb_frame_symm_bytes(int H, int W);
+int pvdb_render_frame_sharded(const pvdb_render_cfg* cfg, const pvdb_render_bufs* bufs, const pvdb_frame_peers* peers,
+                              const float* c2w, int band_rows, uint32_t frame_no, float* band_out, void* stream);
+int pvdb_frame_ptr(const pvdb_frame_peers* peers, uint32_t frame_no, float** frame);
+/* Stream-ordered copy of the assembled frame into caller memory (device float[H*W*3]) for callers that cannot alias the block. */
+int pvdb_frame_copy(const pvdb_frame_peers* peers, uint32_t frame_no, float* dst, void* stream);
+int pvdb_frame_error(const pvdb_frame_peers* peers, int32_t* err_out);
 /* Device-side half of the merge (vdb_compression.py:36-57): gathers density / colour rows of every masked voxel and
  * rounds them through fp16.  row_of_voxel [rx*ry*rz]: 1-based row id or 0. */
 int pvdb_merge_gather(const pvdb_tree* tree, const float* den, const float* k0, int k0_dim,

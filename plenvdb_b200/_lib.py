@@ -102,6 +102,11 @@ class pvdb_dp_peers(C.Structure):
                 ("base", C.c_void_p * 8)]
 
 
+class pvdb_frame_peers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("root", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("reserved", C.c_int32), ("base", C.c_void_p * 8)]
+
+
 _TP = C.POINTER(pvdb_tree)
 _i, _i64, _f = C.c_int, C.c_int64, C.c_float
 
@@ -160,6 +165,15 @@ _SIGS = {
     "pvdb_profile_fetch": (C.c_int, [_i, c_ptr, c_ptr]),
     "pvdb_rays_hit_mask": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, _i, c_ptr, c_ptr]),
     "pvdb_render_rows": (None, [C.POINTER(pvdb_render_cfg), C.POINTER(pvdb_render_bufs), c_ptr, _i, _i, c_ptr, c_ptr]),
+    "pvdb_interleaved_rows": (C.c_int, [_i, _i, _i, _i]),
+    "pvdb_render_rows_interleaved": (None, [C.POINTER(pvdb_render_cfg), C.POINTER(pvdb_render_bufs), c_ptr, _i, _i, _i, c_ptr, c_ptr,
+                                            c_ptr]),
+    "pvdb_frame_symm_bytes": (C.c_size_t, [_i, _i]),
+    "pvdb_render_frame_sharded": (None, [C.POINTER(pvdb_render_cfg), C.POINTER(pvdb_render_bufs), C.POINTER(pvdb_frame_peers), c_ptr,
+                                         _i, C.c_uint32, c_ptr, c_ptr]),
+    "pvdb_frame_ptr": (None, [C.POINTER(pvdb_frame_peers), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "pvdb_frame_copy": (None, [C.POINTER(pvdb_frame_peers), C.c_uint32, c_ptr, c_ptr]),
+    "pvdb_frame_error": (None, [C.POINTER(pvdb_frame_peers), C.POINTER(C.c_int32)]),
     "pvdb_merge_gather": (None, [_TP, c_ptr, c_ptr, _i, c_ptr, _i, _i, _i, c_ptr, c_ptr, c_ptr]),
     "pvdb_train_step": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, c_ptr, c_ptr, _i, _i,
                                c_ptr]),
@@ -199,6 +213,21 @@ def ptr(t):
     if t is None:
         return None
     return C.c_void_p(t.data_ptr())
+
+
+class _DevicePointer:
+    """Exposes a raw device allocation (not owned by torch) through __cuda_array_interface__."""
+
+    def __init__(self, address, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(address), False), "version": 2,
+                                         "strides": None}
+
+
+def tensor_from_ptr(address, shape, device):
+    """float32 CUDA tensor VIEW of `shape` over a device allocation made by the library (e.g. a symmetric block); the caller
+    keeps the allocation alive."""
+    import torch
+    return torch.as_tensor(_DevicePointer(address, shape), device=device)
 
 
 def current_stream():

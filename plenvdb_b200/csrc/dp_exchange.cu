@@ -21,13 +21,13 @@
 // A of the step in between, which every peer reaches only after all of its reads of the earlier step (stream order).
 #include "common.cuh"
 #include "rgbnet.cuh"
+#include "peer_sync.cuh"
 
 namespace {
 
 constexpr int TILE_F = PVDB_LEAF_VOX * 13;                 // density [512] + k0 [512][12]
 constexpr int NET_PAD = (PVDB_NET_N + 255) & ~255;
 constexpr int NET_SLICES = 8;
-constexpr unsigned long long SPIN_TIMEOUT_NS = 2000000000ull;   // 2 s: a dead peer must not hang the GPU
 enum { SIG_A = 0, SIG_B = 16, SIG_C = 32 };                // word offsets inside the signal area (C: [slice][8])
 
 struct Blk {
@@ -56,17 +56,6 @@ __host__ __device__ inline Blk view(void* base, int n_leaf, int cap_leaves) {
     return b;
 }
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 // thread `peer` of a CTA: tell rank `peer` that this rank reached `epoch`
 __device__ __forceinline__ void signal_peer(const pvdb_dp_peers& P, int peer, int word, uint32_t epoch) {
     st_release_sys(view(P.base[peer], P.n_leaf, P.cap_leaves).signal + word + P.rank, epoch);
@@ -74,11 +63,7 @@ __device__ __forceinline__ void signal_peer(const pvdb_dp_peers& P, int peer, in
 // thread `peer` of a CTA: wait until rank `peer` reached `epoch`
 __device__ __forceinline__ void wait_peer(const pvdb_dp_peers& P, int peer, int word, uint32_t epoch) {
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
-    const unsigned long long t0 = globaltimer();
-    while ((int32_t)(ld_acquire_sys(me.signal + word + peer) - epoch) < 0) {
-        if (globaltimer() - t0 > SPIN_TIMEOUT_NS) { atomicExch(me.err, 1); break; }
-        __nanosleep(64);
-    }
+    wait_epoch(me.signal + word + peer, epoch, me.err, 1);   // a dead peer must not hang the GPU
 }
 
 __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epoch, int parity, int32_t* __restrict__ den_touched,

@@ -14,7 +14,19 @@ struct RenderConst {
     float wld[3];                 // reso - 1
     float near, stepdist, act_shift, interval, thres, bg;
     int inverse_y, H, W;
+    // Row layout of one call: local row lr of the band buffer is image row
+    //   row_begin + lr                                                      (band_stride == 0: one contiguous band)
+    //   row_begin + (lr / band_rows) * band_stride + lr % band_rows         (interleaved: every band_stride-th group of band_rows rows)
+    int band_rows, band_stride;
 };
+
+// image pixel index (row * W + col) of local pixel `local` of the band buffer
+__device__ __forceinline__ int render_gpix(const RenderConst& C, int row_begin, int local) {
+    if (C.band_stride == 0) return row_begin * C.W + local;
+    const int lr = local / C.W, col = local - lr * C.W;
+    const int k = lr / C.band_rows;
+    return (row_begin + k * C.band_stride + (lr - k * C.band_rows)) * C.W + col;
+}
 
 struct Ray {
     float ro[3], rd[3], vd[3];

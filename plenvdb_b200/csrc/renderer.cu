@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "mlp_tile.cuh"
 #include "render_ray.cuh"
+#include "peer_sync.cuh"
 
 namespace {
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ int pixel_of_thread(int W, int rows, int& local) {
 // Pass 1 of one pixel: counts the kept samples and tightens [tmin, tmax] (renderer.cu:222-268).
 __device__ __forceinline__ int pass1_march(const RenderConst& C, const float* __restrict__ c2w, int row_begin, int local,
                                            float* __restrict__ tmins, float* __restrict__ tmaxs) {
-    const int n = row_begin * C.W + local;
+    const int n = render_gpix(C, row_begin, local);
     Ray R;
     ray_setup(C, c2w, n, R);
     MarchState S;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float
   for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_active; slot += gridDim.x * blockDim.x) {
     const int local = active_list[slot];
     const int ns = n_samples[local];
-    const int n = row_begin * C.W + local;
+    const int n = render_gpix(C, row_begin, local);
     Ray R;
     ray_setup(C, c2w, n, R);
     MarchState S;
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(NT, 1) k_render_mlp(RenderMlpArgs A) {
             for (int i = 0; i < 27; ++i) pe[i] = 0.f;
             if (s0 + s < M) {
                 Ray R;
-                ray_setup(A.C, A.c2w, A.row_begin * A.C.W + A.s_ray[s0 + s], R);
+                ray_setup(A.C, A.c2w, render_gpix(A.C, A.row_begin, A.s_ray[s0 + s]), R);
                 pe[0] = R.vd[0]; pe[1] = R.vd[1]; pe[2] = R.vd[2];
                 // pefeat (:153-166): sin/cos(viewdir * pebase), pebase = 1,2,4,8 as int -> float
 #pragma unroll
@@ -371,21 +372,80 @@ __global__ void __launch_bounds__(NT, 1) k_render_mlp(RenderMlpArgs A) {
     }
 }
 
+// Local pixel -> image pixel of the call's row layout (see RenderConst::band_rows).
+struct RowMap { int W, row_begin, band_rows, band_stride; };
+
 __global__ void __launch_bounds__(256) k_render_composite(const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
                                                           const float* __restrict__ s_rgb, int npix, int64_t cap,
-                                                          float* __restrict__ out_rgb, int32_t* __restrict__ counters) {
+                                                          float* __restrict__ out_rgb, int32_t* __restrict__ counters, RowMap M,
+                                                          float* __restrict__ frame_out) {
     pvdb_pdl_wait();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) counters[RC_ACTIVE] = 0;      // pass 2 of this frame is done with it; pass 1 of the next frame counts from 0
     if (p >= npix) return;
     const int ns = n_samples[p];
-    if (ns == 0) return;
-    const int64_t i0 = i_starts[p];
+    if (ns == 0 && !frame_out) return;
     float r = out_rgb[p * 3], g = out_rgb[p * 3 + 1], b = out_rgb[p * 3 + 2];
-    for (int64_t s = i0; s < i0 + ns && s < cap; ++s) {
-        r = __fadd_rn(r, s_rgb[s * 3]); g = __fadd_rn(g, s_rgb[s * 3 + 1]); b = __fadd_rn(b, s_rgb[s * 3 + 2]);
+    if (ns) {
+        const int64_t i0 = i_starts[p];
+        for (int64_t s = i0; s < i0 + ns && s < cap; ++s) {
+            r = __fadd_rn(r, s_rgb[s * 3]); g = __fadd_rn(g, s_rgb[s * 3 + 1]); b = __fadd_rn(b, s_rgb[s * 3 + 2]);
+        }
+        out_rgb[p * 3] = r; out_rgb[p * 3 + 1] = g; out_rgb[p * 3 + 2] = b;
     }
-    out_rgb[p * 3] = r; out_rgb[p * 3 + 1] = g; out_rgb[p * 3 + 2] = b;
+    if (frame_out) {
+        // Every pixel of the band goes to its place in the full frame.  frame_out may be another GPU's memory (NVLink peer
+        // mapping): plain stores, a warp covers 384 contiguous bytes; the frame-done signal that follows publishes them.
+        int gp = M.row_begin * M.W + p;
+        if (M.band_stride) {
+            const int lr = p / M.W, col = p - lr * M.W, k = lr / M.band_rows;
+            gp = (M.row_begin + k * M.band_stride + (lr - k * M.band_rows)) * M.W + col;
+        }
+        float* dst = frame_out + (size_t)gp * 3;
+        dst[0] = r; dst[1] = g; dst[2] = b;
+    }
+}
+
+// ---- frame assembly over NVLink peer memory (no counterpart in the reference, which is single-GPU) ---------------------------
+// One symmetric block per rank (pvdb_dp_symm_alloc + CUDA IPC):  [0,32) done[8] u32 | [32,36) free u32 | [36,40) err i32 |
+// [1024,..) frame[2][H*W*3] f32.  Frame f is assembled in ROOT's frame[f & 1]: every rank's composite kernel stores its rows
+// straight into it, then signals done[rank] = f + 1 in root's block; root waits for all of them.  Before it starts frame f, root
+// writes free = f + 1 into every peer's block (frame f - 2, the previous user of that buffer, has been consumed in stream order);
+// a peer waits for it only in front of its composite kernel, so its march overlaps root's wait.
+struct FrameBlk { uint32_t* done; uint32_t* free_; int32_t* err; float* frame[2]; };
+__host__ __device__ inline FrameBlk frame_view(void* base, int H, int W) {
+    char* p = static_cast<char*>(base);
+    FrameBlk b;
+    b.done = reinterpret_cast<uint32_t*>(p);
+    b.free_ = reinterpret_cast<uint32_t*>(p + 32);
+    b.err = reinterpret_cast<int32_t*>(p + 36);
+    b.frame[0] = reinterpret_cast<float*>(p + 1024);
+    b.frame[1] = b.frame[0] + (size_t)H * W * 3;
+    return b;
+}
+// root, first kernel of frame f: buffer f & 1 may be written
+__global__ void k_frame_release(pvdb_frame_peers P, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r < P.world && r != P.root) st_release_sys(frame_view(P.base[r], P.H, P.W).free_, epoch);
+}
+// peer, in front of its composite kernel
+__global__ void k_frame_wait_free(pvdb_frame_peers P, uint32_t epoch) {
+    const FrameBlk me = frame_view(P.base[P.rank], P.H, P.W);
+    wait_epoch(me.free_, epoch, me.err, 1);
+}
+// after the composite kernel: a peer publishes its rows (the kernel boundary orders the composite's stores before this thread,
+// the release is cumulative over them), root collects every peer's signal
+__global__ void k_frame_done(pvdb_frame_peers P, uint32_t epoch) {
+    if (P.rank != P.root) {
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(frame_view(P.base[P.root], P.H, P.W).done + P.rank, epoch);
+        }
+        return;
+    }
+    const int r = threadIdx.x;
+    const FrameBlk me = frame_view(P.base[P.rank], P.H, P.W);
+    if (r < P.world && r != P.root) wait_epoch(me.done + r, epoch, me.err, 1);
 }
 
 constexpr size_t RENDER_MLP_SMEM = (size_t)(KX * W + W * W + 3 * W + W + W + 4 + TS * LDX + 2 * TS * LDH) * sizeof(float);
@@ -410,15 +470,24 @@ __global__ void __launch_bounds__(256) k_merge_gather(pvdb_tree t, const float* 
 
 int pvdb_render_mlp_tc(const void* render_mlp_args, cudaStream_t st);   // rgbnet_tc.cu
 
-extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const float* c2w, int row_begin, int row_end,
-                                float* out_rgb, void* stream) {
+// Rows of an H-row image that fall to `rank` when groups of band_rows rows are dealt round-robin to `world` ranks.
+extern "C" int pvdb_interleaved_rows(int H, int band_rows, int rank, int world) {
+    if (H <= 0 || band_rows <= 0 || world <= 0 || rank < 0 || rank >= world) return 0;
+    int rows = 0;
+    for (int r0 = rank * band_rows; r0 < H; r0 += world * band_rows) rows += min(band_rows, H - r0);
+    return rows;
+}
+
+// The frame as a fixed sequence of kernels on one stream.  Local row lr of the band buffer out_rgb is image row
+// row_begin + lr (band_stride == 0) or row_begin + (lr / band_rows) * band_stride + lr % band_rows.  frame_out (optional):
+// the full H x W x 3 frame, possibly peer memory, that also receives every pixel of the band.  fp (optional): the peer
+// protocol of pvdb_render_frame_sharded around the composite kernel.
+static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const float* c2w, int row_begin, int rows, int band_rows,
+                       int band_stride, float* out_rgb, float* frame_out, const pvdb_frame_peers* fp, uint32_t epoch, void* stream) {
     PVDB_CHECK_ARG(cfg && b && b->idx_tree && c2w && out_rgb, "null pointer");
     PVDB_CHECK_ARG(cfg->dcol == 12 && cfg->dpe == 27 && cfg->dhid == 128 && cfg->dout == 3,
                    "the merged renderer is specialised for MGRenderer(12, 27, 128, 3) (run.py:77-82)");
-    PVDB_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= cfg->H, "bad row range");
     cudaStream_t st = (cudaStream_t)stream;
-    pvdb_reset_launch_count();
-    pvdb_prof_begin(st);
     RenderConst C;
     C.tree = *b->idx_tree; C.idx_plane = b->idx_plane; C.dendata = b->dendata; C.coldata = b->coldata;
     for (int i = 0; i < 9; ++i) C.K[i] = cfg->K[i];
@@ -429,7 +498,8 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
     }
     C.near = cfg->near; C.stepdist = cfg->stepdist; C.act_shift = cfg->act_shift; C.interval = cfg->interval;
     C.thres = cfg->fast_color_thres; C.bg = cfg->bg; C.inverse_y = cfg->inverse_y; C.H = cfg->H; C.W = cfg->W;
-    const int rows = row_end - row_begin, npix = rows * cfg->W;
+    C.band_rows = band_stride ? band_rows : rows; C.band_stride = band_stride;
+    const int npix = rows * cfg->W;
     const int tiles = ((cfg->W + 7) / 8) * ((rows + 3) / 4);
     const int pgrid = pvdb_grid_for((int64_t)tiles * 32, 256);
     PVDB_CHECK_ARG(b->active_list, "active_list scratch missing");
@@ -468,10 +538,98 @@ extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bu
         PVDB_LAUNCH_CHECK();
     }
     pvdb_prof_mark("render_mlp", st);
+    if (fp && fp->rank != fp->root) {
+        k_frame_wait_free<<<1, 32, 0, st>>>(*fp, epoch);
+        PVDB_LAUNCH_CHECK();
+    }
+    RowMap M;
+    M.W = cfg->W; M.row_begin = row_begin; M.band_rows = C.band_rows; M.band_stride = band_stride;
     PVDB_CUDA(pvdb_launch_pdl(k_render_composite, dim3(pvdb_grid_for(npix, 256)), dim3(256), 0, st, (const int32_t*)b->n_samples, (const int32_t*)b->i_starts,
-                              (const float*)b->s_rgb, npix, b->cap_samples, out_rgb, b->counters));
+                              (const float*)b->s_rgb, npix, b->cap_samples, out_rgb, b->counters, M, frame_out));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_composite", st);
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_render_rows(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const float* c2w, int row_begin, int row_end,
+                                float* out_rgb, void* stream) {
+    PVDB_CHECK_ARG(cfg, "null pointer");
+    PVDB_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= cfg->H, "bad row range");
+    pvdb_reset_launch_count();
+    pvdb_prof_begin((cudaStream_t)stream);
+    return render_impl(cfg, b, c2w, row_begin, row_end - row_begin, 0, 0, out_rgb, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int pvdb_render_rows_interleaved(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const float* c2w, int band_rows, int rank,
+                                            int world, float* band_out, float* frame_out, void* stream) {
+    PVDB_CHECK_ARG(cfg, "null pointer");
+    PVDB_CHECK_ARG(band_rows > 0 && world > 0 && rank >= 0 && rank < world, "bad band_rows / rank / world");
+    const int rows = pvdb_interleaved_rows(cfg->H, band_rows, rank, world);
+    PVDB_CHECK_ARG(rows > 0, "this rank has no rows (H < rank * band_rows)");
+    pvdb_reset_launch_count();
+    pvdb_prof_begin((cudaStream_t)stream);
+    return render_impl(cfg, b, c2w, rank * band_rows, rows, band_rows, world * band_rows, band_out, frame_out, nullptr, 0, stream);
+}
+
+extern "C" size_t pvdb_frame_symm_bytes(int H, int W) {
+    if (H <= 0 || W <= 0) return 0;
+    return 1024 + 2 * (size_t)H * W * 3 * sizeof(float);
+}
+
+static int check_frame_peers(const pvdb_frame_peers* P) {
+    PVDB_CHECK_ARG(P, "null peers");
+    PVDB_CHECK_ARG(P->world >= 1 && P->world <= 8 && P->rank >= 0 && P->rank < P->world && P->root >= 0 && P->root < P->world,
+                   "world must be 1..8, rank and root inside it");
+    PVDB_CHECK_ARG(P->H > 0 && P->W > 0, "bad frame size");
+    for (int r = 0; r < P->world; ++r) PVDB_CHECK_ARG(P->base[r], "peer block not mapped");
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_render_frame_sharded(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const pvdb_frame_peers* P, const float* c2w,
+                                         int band_rows, uint32_t frame_no, float* band_out, void* stream) {
+    if (int rc = check_frame_peers(P)) return rc;
+    PVDB_CHECK_ARG(cfg && cfg->H == P->H && cfg->W == P->W, "the peer blocks were sized for another frame");
+    PVDB_CHECK_ARG(band_rows > 0, "bad band_rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t epoch = frame_no + 1;      // monotone; the signal words start at 0
+    pvdb_reset_launch_count();
+    pvdb_prof_begin(st);
+    if (P->rank == P->root && P->world > 1) {
+        k_frame_release<<<1, 32, 0, st>>>(*P, epoch);
+        PVDB_LAUNCH_CHECK();
+    }
+    const int rows = pvdb_interleaved_rows(cfg->H, band_rows, P->rank, P->world);
+    if (rows > 0) {
+        float* frame = frame_view(P->base[P->root], P->H, P->W).frame[frame_no & 1];
+        int rc = render_impl(cfg, b, c2w, P->rank * band_rows, rows, band_rows, P->world * band_rows, band_out, frame, P, epoch, stream);
+        if (rc) return rc;
+    }
+    if (P->world > 1) {
+        k_frame_done<<<1, 32, 0, st>>>(*P, epoch);
+        PVDB_LAUNCH_CHECK();
+    }
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_frame_ptr(const pvdb_frame_peers* P, uint32_t frame_no, float** frame) {
+    if (int rc = check_frame_peers(P)) return rc;
+    PVDB_CHECK_ARG(frame, "null pointer");
+    *frame = frame_view(P->base[P->root], P->H, P->W).frame[frame_no & 1];
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_frame_copy(const pvdb_frame_peers* P, uint32_t frame_no, float* dst, void* stream) {
+    if (int rc = check_frame_peers(P)) return rc;
+    PVDB_CHECK_ARG(dst, "null pointer");
+    PVDB_CUDA(cudaMemcpyAsync(dst, frame_view(P->base[P->root], P->H, P->W).frame[frame_no & 1], (size_t)P->H * P->W * 3 * sizeof(float),
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PVDB_OK;
+}
+
+extern "C" int pvdb_frame_error(const pvdb_frame_peers* P, int32_t* err_out) {
+    if (int rc = check_frame_peers(P)) return rc;
+    PVDB_CHECK_ARG(err_out, "null pointer");
+    PVDB_CUDA(cudaMemcpy(err_out, frame_view(P->base[P->rank], P->H, P->W).err, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return PVDB_OK;
 }
 

@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs 
             x[c4 * 4] = a.x; x[c4 * 4 + 1] = a.y; x[c4 * 4 + 2] = a.z; x[c4 * 4 + 3] = a.w;
         }
         Ray R;
-        ray_setup(A.C, A.c2w, A.row_begin * A.C.W + A.s_ray[s], R);
+        ray_setup(A.C, A.c2w, render_gpix(A.C, A.row_begin, A.s_ray[s]), R);
         x[12] = R.vd[0]; x[13] = R.vd[1]; x[14] = R.vd[2];
 #pragma unroll
         for (int k = 0; k < 4; ++k)

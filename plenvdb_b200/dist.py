@@ -8,7 +8,9 @@ iteration between the backward and the update phases of the fused step:
 after which every rank runs the identical sparse Adam.  The losses are means over the GLOBAL batch
 (cfg.n_rays_global), so the summed shard gradients equal the single-GPU full-batch gradients.
 
-Rendering: replicas + contiguous row bands, no collective but the final gather.
+Rendering: replicas + row sharding.  Default on CUDA: interleaved row groups whose pixels each rank's composite kernel
+stores straight into rank 0's frame buffer over NVLink peer memory (PeerFrame; no collective at all).  Fallback: contiguous
+row bands + an NCCL gather.
 """
 import torch
 import torch.distributed as dist
@@ -227,8 +229,118 @@ class DataParallelTrainer:
         return self.last_exchange_bytes
 
 
-def render_sharded(renderer, c2w_dev, rank, world, gather=True, group=None):
-    """Rank `rank` renders its contiguous row band; rank 0 gets the full [H, W, 3] frame when gather=True."""
+def open_symmetric_blocks(nbytes, group=None):
+    """One cudaMalloc'ed block of `nbytes` per rank, mapped by every peer through CUDA IPC.  The handles travel over
+    torch.distributed (plumbing).  Returns (own c_void_p, [base address of rank r's block in THIS process], [opened mappings]).
+    Every rank takes part in both collectives whatever happens locally and all ranks agree on the outcome: on any failure
+    PeerExchangeUnavailable is raised on EVERY rank after whatever was set up has been released."""
+    import ctypes as C
+    from . import _lib
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    assert world <= 8, "one NVSwitch domain (<= 8 GPUs)"
+    own, handle, opened, bases, err = C.c_void_p(), C.create_string_buffer(64), [], [None] * world, None
+    try:
+        _lib.call("pvdb_dp_symm_alloc", int(nbytes), C.byref(own), handle)
+    except _lib.PvdbError as e:
+        err, own = str(e), None
+    handles = [None] * world
+    dist.all_gather_object(handles, None if err else bytes(handle.raw), group=group)
+    if err is None and all(h is not None for h in handles):
+        try:
+            for r in range(world):
+                if r == rank:
+                    bases[r] = own.value
+                else:
+                    p = C.c_void_p()
+                    _lib.call("pvdb_dp_symm_open", C.create_string_buffer(handles[r], 64), C.byref(p))
+                    bases[r] = p.value
+                    opened.append(p)
+        except _lib.PvdbError as e:
+            err = str(e)
+    elif err is None:
+        err = "a peer could not allocate its symmetric block"
+    oks = [None] * world
+    dist.all_gather_object(oks, err, group=group)   # also the barrier: every block is zeroed and mapped before the first signal
+    bad = [(r, e) for r, e in enumerate(oks) if e is not None]
+    if bad:
+        close_symmetric_blocks(own, opened)
+        raise PeerExchangeUnavailable("NVLink peer memory unavailable (rank %d: %s)" % bad[0])
+    return own, bases, opened
+
+
+def close_symmetric_blocks(own, opened, group=None, barrier=False):
+    """Unmap the peers' blocks, then free the own one.  barrier=True (collective: every rank must call it): no rank frees its
+    block while a peer still has it mapped."""
+    from . import _lib
+    for p in opened:
+        _lib.call("pvdb_dp_symm_close", p)
+    if barrier and dist.is_initialized():
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+    if own is not None:
+        _lib.call("pvdb_dp_symm_free", own)
+
+
+def interleaved_rows_of(H, band_rows, rank, world):
+    """Image rows of `rank` when groups of band_rows rows are dealt round-robin to the ranks (row r -> rank (r // band_rows)
+    % world), ascending — the order of the local rows of pvdb_render_rows_interleaved."""
+    return [r for r in range(H) if (r // band_rows) % world == rank]
+
+
+class PeerFrame:
+    """Frame assembly over NVLink peer memory (csrc/renderer.cu: pvdb_render_frame_sharded): every rank renders interleaved
+    groups of `band_rows` rows and its composite kernel stores them straight into root's frame buffer; one release/acquire
+    signal per rank replaces the gather.  No NCCL call and no host synchronisation per frame."""
+
+    def __init__(self, H, W, band_rows=4, root=0, group=None):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.H, self.W, self.band_rows, self.root = int(H), int(W), int(band_rows), int(root)
+        self._own, self._opened, self._group = None, [], group
+        self._own, bases, self._opened = open_symmetric_blocks(_lib.lib.pvdb_frame_symm_bytes(self.H, self.W), group)
+        self.peers = _lib.pvdb_frame_peers()
+        self.peers.world, self.peers.rank, self.peers.root, self.peers.H, self.peers.W = self.world, self.rank, self.root, self.H, self.W
+        for r in range(self.world):
+            self.peers.base[r] = bases[r]
+        self.frame_no = 0
+        self._views = None
+
+    def render(self, renderer, c2w_dev):
+        """All ranks call it with the same camera.  Root gets the full [H, W, 3] frame: a VIEW of its frame buffer that stays
+        valid until root's call after the next one starts (consume it on the same stream before that); the others get None."""
+        f = self.frame_no
+        renderer.render_frame_sharded(self.peers, c2w_dev, self.band_rows, f)
+        self.frame_no += 1
+        if self.rank != self.root:
+            return None
+        if self._views is None:
+            views = []
+            for k in range(2):
+                p = self._C.c_void_p()
+                self._lib.call("pvdb_frame_ptr", self._C.byref(self.peers), k, self._C.byref(p))
+                views.append(self._lib.tensor_from_ptr(p.value, (self.H, self.W, 3), renderer.dev))
+            self._views = views
+        return self._views[f & 1]
+
+    def error(self):
+        e = self._C.c_int32(0)
+        self._lib.call("pvdb_frame_error", self._C.byref(self.peers), self._C.byref(e))
+        return int(e.value)
+
+    def close(self):
+        """Collective: every rank calls it (the owners free their blocks only after all peers have unmapped them)."""
+        self._views = None
+        close_symmetric_blocks(self._own, self._opened, self._group, barrier=True)
+        self._own, self._opened = None, []
+
+
+def render_sharded(renderer, c2w_dev, rank, world, gather=True, group=None, peer=None):
+    """Rank 0 gets the full [H, W, 3] frame.  peer: a PeerFrame — interleaved row groups written straight into rank 0's frame
+    over NVLink (no collective).  Otherwise: contiguous row bands + an NCCL gather (gather=False: just this rank's band)."""
+    if peer is not None and world > 1:
+        return peer.render(renderer, c2w_dev)
     H, W = renderer.cfg.H, renderer.cfg.W
     lo, hi = shard_range(H, rank, world)
     band = renderer.render_rows_torch(c2w_dev, lo, hi)

@@ -143,6 +143,34 @@ class MGRenderer:
                   _lib.current_stream())
         return out
 
+    def interleaved_rows(self, band_rows, rank, world):
+        return int(_lib.lib.pvdb_interleaved_rows(self.cfg.H, int(band_rows), int(rank), int(world)))
+
+    def render_interleaved_torch(self, c2w_dev, band_rows, rank, world, frame_out=None, out=None):
+        """Render the rows that fall to `rank` when groups of `band_rows` rows are dealt round-robin to `world` ranks; returns the
+        band [rows, W, 3] (local rows in ascending image order).  frame_out: optional full [H, W, 3] CUDA tensor (or a raw device
+        address, possibly another GPU's memory) that also receives every pixel of the band at its place in the frame."""
+        assert all(self.flags[:4]), "load_data, load_params, setScene and setKwargs must be called first"
+        rows = self.interleaved_rows(band_rows, rank, world)
+        self._ensure_scratch(rows)
+        if out is None:
+            out = torch.empty((rows, self.cfg.W, 3), dtype=torch.float32, device=self.dev)
+        fo = C.c_void_p(frame_out) if isinstance(frame_out, int) else _lib.ptr(frame_out)
+        _lib.call("pvdb_render_rows_interleaved", C.byref(self.cfg), C.byref(self.bufs), _lib.ptr(c2w_dev), int(band_rows), int(rank),
+                  int(world), _lib.ptr(out), fo, _lib.current_stream())
+        return out
+
+    def render_frame_sharded(self, peers, c2w_dev, band_rows, frame_no):
+        """This rank's part of pvdb_render_frame_sharded (see dist.PeerFrame): interleaved rows, stored by the composite kernel
+        straight into root's frame buffer over NVLink, one signal per rank instead of a gather."""
+        assert all(self.flags[:4]), "load_data, load_params, setScene and setKwargs must be called first"
+        rows = max(self.interleaved_rows(band_rows, peers.rank, peers.world), 1)
+        self._ensure_scratch(rows)
+        if getattr(self, "_band", None) is None or self._band.shape[0] != rows:
+            self._band = torch.empty((rows, self.cfg.W, 3), dtype=torch.float32, device=self.dev)
+        _lib.call("pvdb_render_frame_sharded", C.byref(self.cfg), C.byref(self.bufs), C.byref(peers), _lib.ptr(c2w_dev),
+                  int(band_rows), int(frame_no), _lib.ptr(self._band), _lib.current_stream())
+
     def render_an_image(self):
         """plenvdb.h:1027-1036: silently does nothing until all five setup calls happened."""
         if not all(self.flags):

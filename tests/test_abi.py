@@ -47,8 +47,9 @@ def test_struct_sizes_match_the_header():
     import subprocess
     import tempfile
     from plenvdb_b200 import _lib
-    code = '#include <stdio.h>\n#include "plenvdb_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(pvdb_tree), ' \
-           'sizeof(pvdb_train_cfg), sizeof(pvdb_train_bufs), sizeof(pvdb_render_cfg), sizeof(pvdb_render_bufs));return 0;}\n'
+    code = '#include <stdio.h>\n#include "plenvdb_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pvdb_tree), ' \
+           'sizeof(pvdb_train_cfg), sizeof(pvdb_train_bufs), sizeof(pvdb_render_cfg), sizeof(pvdb_render_bufs), ' \
+           'sizeof(pvdb_dp_peers), sizeof(pvdb_frame_peers));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "p.c")
         open(src, "w").write(code)
@@ -56,5 +57,5 @@ def test_struct_sizes_match_the_header():
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     mine = [ctypes.sizeof(c) for c in (_lib.pvdb_tree, _lib.pvdb_train_cfg, _lib.pvdb_train_bufs, _lib.pvdb_render_cfg,
-                                       _lib.pvdb_render_bufs)]
+                                       _lib.pvdb_render_bufs, _lib.pvdb_dp_peers, _lib.pvdb_frame_peers)]
     assert sizes == mine, (sizes, mine)

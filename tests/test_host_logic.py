@@ -104,3 +104,23 @@ def test_plane_container_round_trip(tmp_path):
     assert all(r2 <= r for r2, r in zip(reso2, R))
     with pytest.raises(ValueError):
         vdbio.load_planes(p, 12, "cpu")
+
+
+def test_interleaved_row_groups_partition_exactly():
+    """Tile sharding of the renderer (SURVEY.md 8e): row r belongs to rank (r // band_rows) % world; the C-ABI's row count per
+    rank agrees with the host enumeration and the ranks' rows partition the image, ragged last group included."""
+    from plenvdb_b200 import _lib
+    from plenvdb_b200 import dist as pdist
+    for H, B, world in [(800, 4, 8), (800, 4, 1), (801, 4, 8), (122, 4, 2), (122, 5, 4), (7, 4, 2), (3, 4, 2), (1, 1, 8)]:
+        seen = []
+        for rank in range(world):
+            rows = pdist.interleaved_rows_of(H, B, rank, world)
+            assert len(rows) == _lib.lib.pvdb_interleaved_rows(H, B, rank, world)
+            assert rows == sorted(rows)
+            # local row lr -> image row, the mapping the kernels use
+            want = [rank * B + (lr // B) * world * B + lr % B for lr in range(len(rows))]
+            assert rows == want
+            seen += rows
+        assert sorted(seen) == list(range(H))
+    assert _lib.lib.pvdb_interleaved_rows(0, 4, 0, 2) == 0 and _lib.lib.pvdb_interleaved_rows(8, 0, 0, 2) == 0
+    assert _lib.lib.pvdb_frame_symm_bytes(800, 800) == 1024 + 2 * 800 * 800 * 3 * 4

@@ -110,3 +110,33 @@ def test_render_matches_reference_kernels(merged, use_tc):
             ok = np.abs(img - want).max(1) < 1e-3
             assert (~ok).sum() <= 4 * bad
         np.testing.assert_allclose(img[ok], want[ok], rtol=1e-5, atol=3e-6)
+
+
+@pytest.mark.parametrize("world,band_rows", [(1, 4), (3, 4), (8, 4), (4, 5), (2, 64)])
+def test_interleaved_row_groups_assemble_the_exact_frame(merged, world, band_rows):
+    """Tile sharding for N GPUs, exercised rank by rank on one GPU: groups of band_rows rows dealt round-robin.
+    Each rank's band equals its rows of the full frame bit for bit, and the frame_out stores assemble the whole frame."""
+    from plenvdb_b200 import synth
+    from plenvdb_b200 import dist as pdist
+    scene, (dend, cold, idx, n), _ = merged
+    H, W = 122, 120      # H is not a multiple of band_rows * world: the last group is ragged
+    r, mlp, K = _renderer(scene, dend, cold, idx, H, W)
+    c2w = torch.from_numpy(synth.render_cameras(8)[2].reshape(-1).copy()).cuda()
+    full = r.render_rows_torch(c2w, 0, H).clone()
+    assert int(r.s["n_samples"].sum()) > 2000, "degenerate view"
+    frame = torch.full((H, W, 3), -1.0, device="cuda")
+    total = 0
+    for rank in range(world):
+        rows = pdist.interleaved_rows_of(H, band_rows, rank, world)
+        assert len(rows) == r.interleaved_rows(band_rows, rank, world)
+        total += len(rows)
+        if not rows:
+            continue
+        band = r.render_interleaved_torch(c2w, band_rows, rank, world, frame_out=frame)
+        assert torch.equal(band, full[torch.tensor(rows, device="cuda")]), "rank %d" % rank
+        assert r.counters()["overflow"] == 0
+    assert total == H
+    assert torch.equal(frame, full)
+    # without frame_out nothing but the band is written, and the band is the same
+    rows = pdist.interleaved_rows_of(H, band_rows, 0, world)
+    assert torch.equal(r.render_interleaved_torch(c2w, band_rows, 0, world), full[torch.tensor(rows, device="cuda")])
