@@ -324,7 +324,13 @@ typedef struct pvdb_render_bufs {
                                       * 3 pixels with samples (zero between frames) */
     void *w_img;                     /* >= 256 KiB scratch: tf32 hi/lo weight image (use_tensor_cores) */
     int32_t *active_list;            /* [npix] pixels with samples, built by pass 1 for pass 2 */
+    const uint32_t *skip_bits;       /* optional [pvdb_render_block_bits_words(reso)]: dilated block map of idx_tree built by
+                                      * pvdb_render_block_bits; runs of march steps that cannot touch a leaf are skipped (their
+                                      * `t += steplen` chain is still evaluated, so results are bit-identical).  NULL = march
+                                      * every step like the reference */
 } pvdb_render_bufs;
+size_t pvdb_render_block_bits_words(int rx, int ry, int rz);
+int pvdb_render_block_bits(const pvdb_tree* idx_tree, int rx, int ry, int rz, uint32_t* bits, void* stream);
 
 /* Renders rows [row_begin,row_end) of the H x W image for camera `c2w` (device float[16], row-major 4x4) into
  * out_rgb (device float[(row_end-row_begin)*W*3]).  No allocation, no synchronisation. */

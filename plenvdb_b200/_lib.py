@@ -93,7 +93,7 @@ class pvdb_render_bufs(C.Structure):
         ("n_samples", c_ptr), ("i_starts", c_ptr), ("tmins", c_ptr), ("tmaxs", c_ptr), ("scan_tmp", c_ptr),
         ("cap_samples", C.c_int64),
         ("s_ray", c_ptr), ("s_weight", c_ptr), ("s_feat", c_ptr), ("s_rgb", c_ptr), ("counters", c_ptr),
-        ("w_img", c_ptr), ("active_list", c_ptr),
+        ("w_img", c_ptr), ("active_list", c_ptr), ("skip_bits", c_ptr),
     ]
 
 
@@ -174,6 +174,8 @@ _SIGS = {
     "pvdb_frame_ptr": (None, [C.POINTER(pvdb_frame_peers), C.c_uint32, C.POINTER(C.c_void_p)]),
     "pvdb_frame_copy": (None, [C.POINTER(pvdb_frame_peers), C.c_uint32, c_ptr, c_ptr]),
     "pvdb_frame_error": (None, [C.POINTER(pvdb_frame_peers), C.POINTER(C.c_int32)]),
+    "pvdb_render_block_bits_words": (C.c_size_t, [_i, _i, _i]),
+    "pvdb_render_block_bits": (None, [_TP, _i, _i, _i, c_ptr, c_ptr]),
     "pvdb_merge_gather": (None, [_TP, c_ptr, c_ptr, _i, c_ptr, _i, _i, _i, c_ptr, c_ptr, c_ptr]),
     "pvdb_train_step": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, c_ptr, c_ptr, _i, _i,
                                c_ptr]),

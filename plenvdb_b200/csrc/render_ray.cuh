@@ -18,6 +18,10 @@ struct RenderConst {
     //   row_begin + lr                                                      (band_stride == 0: one contiguous band)
     //   row_begin + (lr / band_rows) * band_stride + lr % band_rows         (interleaved: every band_stride-th group of band_rows rows)
     int band_rows, band_stride;
+    // Empty-space skipping (optional, NULL = every step is marched): one bit per 8^3 block, set when the block or one of its
+    // +1 neighbours along any axes holds a leaf of the index tree (pvdb_render_block_bits); nb = blocks per axis.
+    const uint32_t* skip_bits;
+    int nb[3];
 };
 
 // image pixel index (row * W + col) of local pixel `local` of the band buffer

@@ -63,6 +63,39 @@ __device__ __forceinline__ int pixel_of_thread(int W, int rows, int& local) {
     return local;
 }
 
+// Empty-space skipping.  The reference marches every step; a step has an effect only when its voxel is active, so a run of
+// steps none of which can be active may be replaced by its `t += steplen` chain alone (the chain itself is kept: t must go
+// through the same roundings).  For steps t_a <= t <= t_b every coordinate p(t) = fma(rd, t, ro) lies between p(t_a) and
+// p(t_b) — one rounding of a linear function is monotone — and so do p * wld and rint(.): the voxels of the run lie in the
+// index box spanned by the two ends (clamped to the unit box, outside of which a step is skipped anyway).  When that box
+// covers at most two 8^3 blocks per axis, one bit of the dilated block map says whether any of them holds a leaf.
+constexpr int SKIP_K = 16;     // steps per run: 16 x 0.5 voxel <= 8 voxels, i.e. at most two blocks per axis
+__device__ __forceinline__ bool run_is_empty(const RenderConst& C, const Ray& R, float ta, float tb) {
+    int b[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float pa = __fmaf_rn(R.rd[a], ta, R.ro[a]), pb = __fmaf_rn(R.rd[a], tb, R.ro[a]);
+        if (pa != pa || pb != pb) return false;                       // NaN: leave it to the step-by-step code
+        const float lo = fmaxf(fminf(pa, pb), 0.f), hi = fminf(fmaxf(pa, pb), 1.f);
+        if (lo > hi) return true;                                     // every step of the run is outside the box on this axis
+        const int ilo = __float2int_rn(__fmul_rn(lo, C.wld[a])) >> 3, ihi = __float2int_rn(__fmul_rn(hi, C.wld[a])) >> 3;
+        if (ihi - ilo > 1 || ilo < 0 || ihi >= C.nb[a]) return false;
+        b[a] = ilo;
+    }
+    const int bit = (b[0] * C.nb[1] + b[1]) * C.nb[2] + b[2];
+    return !((__ldg(C.skip_bits + (bit >> 5)) >> (bit & 31)) & 1u);
+}
+// Chain of up to SKIP_K steps from t (t < tmax): returns the number of steps, t1 = t after the first, tk = after the last.
+__device__ __forceinline__ int run_chain(float t, float steplen, float tmax, float& t1, float& tk) {
+    t1 = __fadd_rn(t, steplen);
+    tk = t1;
+    int k = 1;
+#pragma unroll
+    for (int q = 1; q < SKIP_K; ++q)
+        if (tk < tmax) { tk = __fadd_rn(tk, steplen); ++k; }
+    return k;
+}
+
 // Pass 1 of one pixel: counts the kept samples and tightens [tmin, tmax] (renderer.cu:222-268).
 __device__ __forceinline__ int pass1_march(const RenderConst& C, const float* __restrict__ c2w, int row_begin, int local,
                                            float* __restrict__ tmins, float* __restrict__ tmaxs) {
@@ -73,32 +106,40 @@ __device__ __forceinline__ int pass1_march(const RenderConst& C, const float* __
     PvdbLeafCache vcache;
     float T_cum = 1.0f, t = R.tmin, tmin_out = R.tmin, tmax_out = R.tmax;
     const float tmax0 = R.tmax;
-    bool update_tmin = false;
+    bool update_tmin = false, done = false;
     int ns = 0;
-    while (t < tmax0) {
-        t = __fadd_rn(t, R.steplen);
-        float xyz[3];
-        int leaf;
-        if (!step_active(C, R, S, t, xyz, leaf)) continue;
-        // trigetDensity (:191-220): int() truncation, res += d*f0*f1*f2 -> fma(f2, f1*(f0*d), res)
-        const int i = (int)xyz[0], j = (int)xyz[1], k = (int)xyz[2];
-        const float u = __fsub_rn(xyz[0], (float)i), v = __fsub_rn(xyz[1], (float)j), w = __fsub_rn(xyz[2], (float)k);
-        float res = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
-            const float d = __ldg(C.dendata + idx_at(C, vcache, i + dx, j + dy, k + dz));
-            const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
-            res = __fmaf_rn(f2, __fmul_rn(f1, __fmul_rn(f0, d)), res);
+    while (!done && t < tmax0) {
+        int nslow = 0x7fffffff;
+        if (C.skip_bits) {
+            float t1, tk;
+            nslow = run_chain(t, R.steplen, tmax0, t1, tk);
+            if (run_is_empty(C, R, t1, tk)) { t = tk; continue; }
         }
-        const float alpha = render_alpha(res, C.act_shift, C.interval);
-        if (alpha <= C.thres) continue;
-        const float weight = __fmul_rn(T_cum, alpha);
-        T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, alpha));
-        if (weight <= C.thres) continue;
-        ++ns;
-        if (!update_tmin) { tmin_out = __fsub_rn(t, R.steplen); update_tmin = true; }
-        if ((double)T_cum < 1e-3) { tmax_out = t; break; }
+        for (int s = 0; s < nslow && t < tmax0; ++s) {
+            t = __fadd_rn(t, R.steplen);
+            float xyz[3];
+            int leaf;
+            if (!step_active(C, R, S, t, xyz, leaf)) continue;
+            // trigetDensity (:191-220): int() truncation, res += d*f0*f1*f2 -> fma(f2, f1*(f0*d), res)
+            const int i = (int)xyz[0], j = (int)xyz[1], k = (int)xyz[2];
+            const float u = __fsub_rn(xyz[0], (float)i), v = __fsub_rn(xyz[1], (float)j), w = __fsub_rn(xyz[2], (float)k);
+            float res = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+                const float d = __ldg(C.dendata + idx_at(C, vcache, i + dx, j + dy, k + dz));
+                const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
+                res = __fmaf_rn(f2, __fmul_rn(f1, __fmul_rn(f0, d)), res);
+            }
+            const float alpha = render_alpha(res, C.act_shift, C.interval);
+            if (alpha <= C.thres) continue;
+            const float weight = __fmul_rn(T_cum, alpha);
+            T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, alpha));
+            if (weight <= C.thres) continue;
+            ++ns;
+            if (!update_tmin) { tmin_out = __fsub_rn(t, R.steplen); update_tmin = true; }
+            if ((double)T_cum < 1e-3) { tmax_out = t; done = true; break; }
+        }
     }
     tmins[local] = tmin_out;
     tmaxs[local] = tmax_out;
@@ -196,6 +237,11 @@ __global__ void __launch_bounds__(1024) k_scan_add(int32_t* __restrict__ out, in
     }
 }
 
+// Pass 2 (renderer.cu:312-367) is split in two.  The march itself stays one thread per listed pixel, but it only FINDS the kept
+// samples (density, alpha, the sequential transmittance): per sample it stores weight, pixel and the index-space position in
+// the first three floats of the sample's feature row.  The 8 x 12-channel colour gather (trigetColor, :303-310) — the bulk of
+// the dependent loads, serial per pixel in the reference and the floor of a row band's latency — runs afterwards with one
+// thread per SAMPLE (k_render_gather), same arithmetic in the same order.
 __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float* __restrict__ c2w, int row_begin, int rows,
                                                       const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
                                                       const float* __restrict__ tmins, const float* __restrict__ tmaxs,
@@ -218,13 +264,73 @@ __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float
     const int64_t i0 = i_starts[local];
     int r = 0;
     while (t < tmax) {
-        t = __fadd_rn(t, R.steplen);
-        float xyz[3];
-        int leaf;
-        if (!step_active(C, R, S, t, xyz, leaf)) continue;
-        // trigetDensity2 (:271-300)
-        const int i = (int)xyz[0], j = (int)xyz[1], k = (int)xyz[2];
-        const float u = __fsub_rn(xyz[0], (float)i), v = __fsub_rn(xyz[1], (float)j), w = __fsub_rn(xyz[2], (float)k);
+        int nslow = 0x7fffffff;
+        if (C.skip_bits) {
+            float t1, tk;
+            nslow = run_chain(t, R.steplen, tmax, t1, tk);
+            if (run_is_empty(C, R, t1, tk)) { t = tk; continue; }
+        }
+        for (int s = 0; s < nslow && t < tmax; ++s) {
+            t = __fadd_rn(t, R.steplen);
+            float xyz[3];
+            int leaf;
+            if (!step_active(C, R, S, t, xyz, leaf)) continue;
+            // trigetDensity2 (:271-300)
+            const int i = (int)xyz[0], j = (int)xyz[1], k = (int)xyz[2];
+            const float u = __fsub_rn(xyz[0], (float)i), v = __fsub_rn(xyz[1], (float)j), w = __fsub_rn(xyz[2], (float)k);
+            float den[8], sc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+                den[q] = __ldg(C.dendata + idx_at(C, vcache, i + dx, j + dy, k + dz));
+                const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
+                sc[q] = __fmul_rn(__fmul_rn(f0, f1), f2);
+            }
+            // d0*s0 + d1*s1 + ... -> fma(d7,s7, ... fma(d2,s2, fma(d0,s0, d1*s1)))
+            float vden = __fmaf_rn(den[0], sc[0], __fmul_rn(den[1], sc[1]));
+#pragma unroll
+            for (int q = 2; q < 8; ++q) vden = __fmaf_rn(den[q], sc[q], vden);
+            const float alpha = render_alpha(vden, C.act_shift, C.interval);
+            if (alpha <= C.thres) continue;
+            const float weight = __fmul_rn(T_cum, alpha);
+            T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, alpha));
+            if (weight <= C.thres) continue;
+            if (r < ns && i0 + r < cap) {
+                float* dst = s_feat + (i0 + r) * 12;      // position now, colour features after k_render_gather
+                dst[0] = xyz[0]; dst[1] = xyz[1]; dst[2] = xyz[2];
+                s_weight[i0 + r] = weight;
+                s_ray[i0 + r] = local;
+            }
+            ++r;
+        }
+    }
+    if (r != ns) {
+        atomicAdd(counters + RC_INCONSISTENT, 1);
+        // keep the tail of the segment well defined: zero weight contributes nothing
+        for (int q = r; q < ns; ++q)
+            if (i0 + q < cap) {
+                s_weight[i0 + q] = 0.f; s_ray[i0 + q] = local;
+                float* dst = s_feat + (i0 + q) * 12;
+                dst[0] = dst[1] = dst[2] = 0.f;
+            }
+    }
+    const float last = __fmul_rn(T_cum, C.bg);   // :364-365
+    out_rgb[local * 3] = last; out_rgb[local * 3 + 1] = last; out_rgb[local * 3 + 2] = last;
+  }
+}
+
+// trigetColor (:303-310) of every kept sample: one thread per sample, 8 index lookups, then 24 independent 16-byte loads and
+// the reference's accumulation order per channel: c0*s0 + c1*s1 -> fma(c7,s7, ... fma(c2,s2, fma(c0,s0, c1*s1))).
+__global__ void __launch_bounds__(256) k_render_gather(RenderConst C, float* __restrict__ s_feat, const int32_t* __restrict__ counters,
+                                                       int64_t cap) {
+    pvdb_pdl_wait();
+    const int64_t total = min((int64_t)counters[RC_TOTAL], cap);
+    for (int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < total; sidx += (int64_t)gridDim.x * blockDim.x) {
+        float* row = s_feat + sidx * 12;
+        const float x = row[0], y = row[1], z = row[2];
+        const int i = (int)x, j = (int)y, k = (int)z;
+        const float u = __fsub_rn(x, (float)i), v = __fsub_rn(y, (float)j), w = __fsub_rn(z, (float)k);
+        PvdbLeafCache vcache;
         int idx[8];
         float sc[8];
 #pragma unroll
@@ -234,53 +340,38 @@ __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float
             const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
             sc[q] = __fmul_rn(__fmul_rn(f0, f1), f2);
         }
-        // d0*s0 + d1*s1 + ... -> fma(d7,s7, ... fma(d2,s2, fma(d0,s0, d1*s1)))
-        float vden = __fmaf_rn(__ldg(C.dendata + idx[0]), sc[0], __fmul_rn(__ldg(C.dendata + idx[1]), sc[1]));
+        float4 f[3];
 #pragma unroll
-        for (int q = 2; q < 8; ++q) vden = __fmaf_rn(__ldg(C.dendata + idx[q]), sc[q], vden);
-        const float alpha = render_alpha(vden, C.act_shift, C.interval);
-        if (alpha <= C.thres) continue;
-        const float weight = __fmul_rn(T_cum, alpha);
-        T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, alpha));
-        if (weight <= C.thres) continue;
-        if (r < ns && i0 + r < cap) {
-            // trigetColor (:303-310), 12 channels as 3 float4 rows per corner
-            float4 f[3];
+        for (int c4 = 0; c4 < 3; ++c4) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[0] * 12) + c4);
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[1] * 12) + c4);
+            f[c4].x = __fmaf_rn(a0.x, sc[0], __fmul_rn(a1.x, sc[1])); f[c4].y = __fmaf_rn(a0.y, sc[0], __fmul_rn(a1.y, sc[1]));
+            f[c4].z = __fmaf_rn(a0.z, sc[0], __fmul_rn(a1.z, sc[1])); f[c4].w = __fmaf_rn(a0.w, sc[0], __fmul_rn(a1.w, sc[1]));
+        }
+#pragma unroll
+        for (int q = 2; q < 8; ++q)
 #pragma unroll
             for (int c4 = 0; c4 < 3; ++c4) {
-                const float4 a0 = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[0] * 12) + c4);
-                const float4 a1 = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[1] * 12) + c4);
-                f[c4].x = __fmaf_rn(a0.x, sc[0], __fmul_rn(a1.x, sc[1])); f[c4].y = __fmaf_rn(a0.y, sc[0], __fmul_rn(a1.y, sc[1]));
-                f[c4].z = __fmaf_rn(a0.z, sc[0], __fmul_rn(a1.z, sc[1])); f[c4].w = __fmaf_rn(a0.w, sc[0], __fmul_rn(a1.w, sc[1]));
+                const float4 a = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[q] * 12) + c4);
+                f[c4].x = __fmaf_rn(a.x, sc[q], f[c4].x); f[c4].y = __fmaf_rn(a.y, sc[q], f[c4].y);
+                f[c4].z = __fmaf_rn(a.z, sc[q], f[c4].z); f[c4].w = __fmaf_rn(a.w, sc[q], f[c4].w);
             }
-#pragma unroll
-            for (int q = 2; q < 8; ++q)
-#pragma unroll
-                for (int c4 = 0; c4 < 3; ++c4) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(C.coldata + (size_t)idx[q] * 12) + c4);
-                    f[c4].x = __fmaf_rn(a.x, sc[q], f[c4].x); f[c4].y = __fmaf_rn(a.y, sc[q], f[c4].y);
-                    f[c4].z = __fmaf_rn(a.z, sc[q], f[c4].z); f[c4].w = __fmaf_rn(a.w, sc[q], f[c4].w);
-                }
-            float4* dst = reinterpret_cast<float4*>(s_feat + (i0 + r) * 12);
-            dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];
-            s_weight[i0 + r] = weight;
-            s_ray[i0 + r] = local;
-        }
-        ++r;
+        float4* dst = reinterpret_cast<float4*>(row);
+        dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];
     }
-    if (r != ns) {
-        atomicAdd(counters + RC_INCONSISTENT, 1);
-        // keep the tail of the segment well defined: zero weight contributes nothing
-        for (int q = r; q < ns; ++q)
-            if (i0 + q < cap) {
-                s_weight[i0 + q] = 0.f; s_ray[i0 + q] = local;
-                float4* dst = reinterpret_cast<float4*>(s_feat + (i0 + q) * 12);
-                dst[0] = dst[1] = dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+}
+
+// Dilated block map of the index tree for run_is_empty: bit b is set when block b or one of its +1 neighbours holds a leaf.
+__global__ void __launch_bounds__(256) k_block_bits(pvdb_tree t, int nbx, int nby, int nbz, uint32_t* __restrict__ bits) {
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= t.n_leaf) return;
+    const int bx = t.leaf_origin[leaf * 3] >> 3, by = t.leaf_origin[leaf * 3 + 1] >> 3, bz = t.leaf_origin[leaf * 3 + 2] >> 3;
+    for (int d = 0; d < 8; ++d) {
+        const int x = bx - (d & 1), y = by - ((d >> 1) & 1), z = bz - (d >> 2);
+        if (x < 0 || y < 0 || z < 0 || x >= nbx || y >= nby || z >= nbz) continue;
+        const int bit = (x * nby + y) * nbz + z;
+        atomicOr(bits + (bit >> 5), 1u << (bit & 31));
     }
-    const float last = __fmul_rn(T_cum, C.bg);   // :364-365
-    out_rgb[local * 3] = last; out_rgb[local * 3 + 1] = last; out_rgb[local * 3 + 2] = last;
-  }
 }
 
 __global__ void __launch_bounds__(NT, 1) k_render_mlp(RenderMlpArgs A) {
@@ -499,6 +590,8 @@ static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, co
     C.near = cfg->near; C.stepdist = cfg->stepdist; C.act_shift = cfg->act_shift; C.interval = cfg->interval;
     C.thres = cfg->fast_color_thres; C.bg = cfg->bg; C.inverse_y = cfg->inverse_y; C.H = cfg->H; C.W = cfg->W;
     C.band_rows = band_stride ? band_rows : rows; C.band_stride = band_stride;
+    C.skip_bits = b->skip_bits;
+    for (int a = 0; a < 3; ++a) C.nb[a] = (cfg->reso[a] + 7) / 8;
     const int npix = rows * cfg->W;
     const int tiles = ((cfg->W + 7) / 8) * ((rows + 3) / 4);
     const int pgrid = pvdb_grid_for((int64_t)tiles * 32, 256);
@@ -521,6 +614,9 @@ static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, co
                               (const int32_t*)b->active_list, out_rgb, b->counters));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_pass2", st);
+    PVDB_CUDA(pvdb_launch_pdl(k_render_gather, dim3(PVDB_SMS * 8), dim3(256), 0, st, C, b->s_feat, (const int32_t*)b->counters, b->cap_samples));
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("render_gather", st);
     static bool attr_set = false;
     if (!attr_set) {
         PVDB_CUDA(cudaFuncSetAttribute(k_render_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RENDER_MLP_SMEM));
@@ -630,6 +726,22 @@ extern "C" int pvdb_frame_error(const pvdb_frame_peers* P, int32_t* err_out) {
     if (int rc = check_frame_peers(P)) return rc;
     PVDB_CHECK_ARG(err_out, "null pointer");
     PVDB_CUDA(cudaMemcpy(err_out, frame_view(P->base[P->rank], P->H, P->W).err, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return PVDB_OK;
+}
+
+extern "C" size_t pvdb_render_block_bits_words(int rx, int ry, int rz) {
+    if (rx <= 0 || ry <= 0 || rz <= 0) return 0;
+    return ((size_t)((rx + 7) / 8) * ((ry + 7) / 8) * ((rz + 7) / 8) + 31) / 32;
+}
+
+extern "C" int pvdb_render_block_bits(const pvdb_tree* tree, int rx, int ry, int rz, uint32_t* bits, void* stream) {
+    PVDB_CHECK_ARG(tree && bits && rx > 0 && ry > 0 && rz > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PVDB_CUDA(cudaMemsetAsync(bits, 0, pvdb_render_block_bits_words(rx, ry, rz) * sizeof(uint32_t), st));
+    if (tree->n_leaf > 0) {
+        k_block_bits<<<pvdb_grid_for(tree->n_leaf, 256), 256, 0, st>>>(*tree, (rx + 7) / 8, (ry + 7) / 8, (rz + 7) / 8, bits);
+        PVDB_LAUNCH_CHECK();
+    }
     return PVDB_OK;
 }
 

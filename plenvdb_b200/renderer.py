@@ -45,7 +45,7 @@ def save_merged(basepath, den, col, idx_dense):
 class MGRenderer:
     """MGRenderer(dcol, dpe, dhid, dout) (plenvdb.h:936-945)."""
 
-    def __init__(self, dcol=12, dpe=27, dhid=128, dout=3, device="cuda", use_tensor_cores=True):
+    def __init__(self, dcol=12, dpe=27, dhid=128, dout=3, device="cuda", use_tensor_cores=True, skip_empty=True):
         self.dcol, self.dpe, self.dhid, self.dout = int(dcol), int(dpe), int(dhid), int(dout)
         self.dev = torch.device(device)
         self.flags = [False] * 5   # load_data, load_params, setScene, setKwargs, input_a_c2w (plenvdb.h:1056)
@@ -54,6 +54,8 @@ class MGRenderer:
         self.cfg.dcol, self.cfg.dpe, self.cfg.dhid, self.cfg.dout = self.dcol, self.dpe, self.dhid, self.dout
         self.cfg.use_tensor_cores = int(bool(use_tensor_cores))   # tcgen05 3xTF32 MLP (fp32 CUDA-core MLP when 0)
         self._scratch_rows = -1
+        self.skip_empty = bool(skip_empty)   # skip runs of march steps that cannot touch a leaf (bit-identical results)
+        self._skip_key, self._skip_bits, self._topo_version = None, None, 0
         self.c2w = torch.zeros(16, dtype=torch.float32, device=self.dev)
         self.out = None
 
@@ -71,6 +73,8 @@ class MGRenderer:
         self.dendata = torch.as_tensor(np.asarray(den.cpu() if torch.is_tensor(den) else den, np.float32)).to(self.dev).contiguous()
         self.coldata = torch.as_tensor(np.asarray(col.cpu() if torch.is_tensor(col) else col, np.float32)).to(self.dev).reshape(-1, self.dcol).contiguous()
         assert self.dendata.numel() == self.coldata.shape[0]
+        self._topo_version += 1
+        self._scratch_rows = -1          # the buffer struct holds pointers into the data just replaced
         self.flags[0] = True
 
     def load_data(self, den, col, vdb_path, N):
@@ -87,6 +91,7 @@ class MGRenderer:
         up = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, np.float32)).reshape(-1)).to(self.dev)
         self.w0, self.b0, self.w1, self.b1, self.w2, self.b2 = up(w0), up(b0), up(w1), up(b1), up(w2), up(b2)
         assert self.w0.numel() == (self.dcol + self.dpe) * self.dhid and self.w2.numel() == self.dhid * self.dout
+        self._scratch_rows = -1
         self.flags[1] = True
 
     def setScene(self, reso, K, xyz_min, xyz_max):
@@ -109,8 +114,22 @@ class MGRenderer:
         self.flags[4] = True
 
     # ---- execution
+    def _ensure_skip_bits(self):
+        """Dilated block map of the index tree for the empty-space skipping; rebuilt when the tree or the resolution changes."""
+        key = (self._topo_version, tuple(int(r) for r in self.cfg.reso)) if self.skip_empty else None
+        if key != self._skip_key:
+            self._skip_key, self._skip_bits = key, None
+            if key is not None:
+                rx, ry, rz = key[1]
+                words = int(_lib.lib.pvdb_render_block_bits_words(rx, ry, rz))
+                self._skip_bits = torch.zeros(max(words, 1), dtype=torch.int32, device=self.dev)
+                _lib.call("pvdb_render_block_bits", self.idx_topo.ref, rx, ry, rz, _lib.ptr(self._skip_bits), _lib.current_stream())
+        if getattr(self, "bufs", None) is not None:
+            self.bufs.skip_bits = self._skip_bits.data_ptr() if self._skip_bits is not None else None
+
     def _ensure_scratch(self, rows, cap_per_pixel=6):
         if rows == self._scratch_rows:
+            self._ensure_skip_bits()
             return
         npix = rows * self.cfg.W
         i32 = dict(dtype=torch.int32, device=self.dev)
@@ -131,6 +150,7 @@ class MGRenderer:
         b.cap_samples = cap
         self.bufs = b
         self._scratch_rows = rows
+        self._ensure_skip_bits()
 
     def render_rows_torch(self, c2w_dev, row_begin, row_end, out=None):
         """Render rows [row_begin,row_end) for a device-resident c2w (float32[16]); returns a CUDA tensor [rows, W, 3]."""

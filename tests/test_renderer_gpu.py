@@ -140,3 +140,33 @@ def test_interleaved_row_groups_assemble_the_exact_frame(merged, world, band_row
     # without frame_out nothing but the band is written, and the band is the same
     rows = pdist.interleaved_rows_of(H, band_rows, 0, world)
     assert torch.equal(r.render_interleaved_torch(c2w, band_rows, 0, world), full[torch.tensor(rows, device="cuda")])
+
+
+@pytest.mark.parametrize("variant", ["dense", "sparse"])
+def test_empty_space_skipping_is_bit_identical(variant):
+    """Runs of march steps that cannot touch a leaf are skipped (only their `t += steplen` chain is evaluated).  Everything
+    the frame produces — per-pixel counts, tightened t ranges, offsets, samples, RGB — equals the step-by-step march bit for bit."""
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import build_scene_grids
+    from plenvdb_b200.renderer import merge_grids
+    scene = synth.make_scene(96, variant)
+    den, k0 = build_scene_grids(scene)
+    dend, cold, idx, n = merge_grids(den, k0, scene["mask"])
+    H, W = 150, 170
+    out = {}
+    for skip in (False, True):
+        r, mlp, K = _renderer(scene, dend, cold, idx, H, W)
+        r.skip_empty = skip
+        res = []
+        for cam in (1, 4, 6):
+            c2w = torch.from_numpy(synth.render_cameras(8)[cam].reshape(-1).copy()).cuda()
+            img = r.render_rows_torch(c2w, 0, H).clone()
+            tot = r.counters()["total"]
+            res.append((img, r.s["n_samples"].clone(), r.s["i_starts"].clone(), r.s["tmins"].clone(), r.s["tmaxs"].clone(),
+                        r.s["s_weight"][:tot].clone(), r.s["s_ray"][:tot].clone(), r.s["s_feat"][:tot].clone(), r.counters()))
+        assert (r.bufs.skip_bits is not None) == skip
+        out[skip] = res
+    for a, b in zip(out[False], out[True]):
+        assert a[8] == b[8] and a[8]["total"] > 2000 and a[8]["overflow"] == 0
+        for x, y in zip(a[:8], b[:8]):
+            assert torch.equal(x, y)
