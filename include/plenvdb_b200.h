@@ -321,13 +321,20 @@ typedef struct pvdb_render_bufs {
     float *s_feat;                   /* [cap][12] */
     float *s_rgb;                    /* [cap][3] weight * sigmoid(rgbnet) */
     int32_t *counters;               /* [8]: 0 total samples, 1 overflow flag, 2 rays whose two passes disagree,
-                                      * 3 pixels with samples (zero between frames) */
+                                      * 3 pixels with samples (zero between frames), 4 pixels marched a second time */
     void *w_img;                     /* >= 256 KiB scratch: tf32 hi/lo weight image (use_tensor_cores) */
     int32_t *active_list;            /* [npix] pixels with samples, built by pass 1 for pass 2 */
     const uint32_t *skip_bits;       /* optional [pvdb_render_block_bits_words(reso)]: dilated block map of idx_tree built by
                                       * pvdb_render_block_bits; runs of march steps that cannot touch a leaf are skipped (their
                                       * `t += steplen` chain is still evaluated, so results are bit-identical).  NULL = march
                                       * every step like the reference */
+    /* optional hand-over of pass 1's samples (all three or none): pass 1 also runs pass 2's arithmetic on the corner values it
+     * has loaded and parks (t, weight) of the first px_entries kept samples of every pixel in px_scratch[npix][px_entries]
+     * (8 bytes each); k_render_emit turns them into the pixel's segment of the sample list.  Only pixels with more samples,
+     * or for which the simulation is not exact (restarted `t` chain, count at a threshold), are marched a second time */
+    void *px_scratch;
+    int32_t *fallback_list;          /* [npix] */
+    int32_t px_entries, reserved;
 } pvdb_render_bufs;
 size_t pvdb_render_block_bits_words(int rx, int ry, int rz);
 int pvdb_render_block_bits(const pvdb_tree* idx_tree, int rx, int ry, int rz, uint32_t* bits, void* stream);

@@ -94,6 +94,7 @@ class pvdb_render_bufs(C.Structure):
         ("cap_samples", C.c_int64),
         ("s_ray", c_ptr), ("s_weight", c_ptr), ("s_feat", c_ptr), ("s_rgb", c_ptr), ("counters", c_ptr),
         ("w_img", c_ptr), ("active_list", c_ptr), ("skip_bits", c_ptr),
+        ("px_scratch", c_ptr), ("fallback_list", c_ptr), ("px_entries", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -22,6 +22,8 @@
 namespace {
 
 constexpr int RC_TOTAL = 0, RC_OVERFLOW = 1, RC_INCONSISTENT = 2, RC_ACTIVE = 3;   // RC_ACTIVE: pixels with samples (pass 1 -> pass 2)
+constexpr int RC_FALLBACK = 4;   // pixels whose samples pass 1 could not hand over (k_render_emit -> pass 2)
+constexpr int PX_FALLBACK_BIT = (int)0x80000000;
 
 // alpha = 1 - pow(1 + exp(v + shift), -interval) exactly as nvcc compiles renderer.cu:256 / :350: the final scale
 // multiply of expf is contracted with the "+ 1" into one fma, so this expression is deliberately left to the
@@ -97,8 +99,18 @@ __device__ __forceinline__ int run_chain(float t, float steplen, float tmax, flo
 }
 
 // Pass 1 of one pixel: counts the kept samples and tightens [tmin, tmax] (renderer.cu:222-268).
+// With a per-pixel slot (px_slot, P entries of (t, weight)) pass 1 also SIMULATES pass 2 for the pixel and hands its samples
+// over, so that the pixel need not be marched a second time.  The reference's second pass (renderer.cu:312-367) is not a replay
+// of the first: it restarts the `t` chain from the tightened tmin = t_first - steplen and interpolates the density in another
+// association order (trigetDensity2, :271-300, vs trigetDensity, :191-220), so its alphas, weights and — at a threshold — even
+// its sample count can differ in the last bit.  The simulation therefore runs pass 2's own arithmetic on the corner values
+// pass 1 has already loaded, from the first kept sample on, with its own transmittance and its own thresholds.  It is exact
+// when the restarted chain reproduces this one ((t_first - steplen) + steplen == t_first in float); the pixel is handed over
+// when in addition the simulated count equals pass 1's (a "consistent" ray) and fits the slot.  Every other pixel is marched
+// again by k_render_pass2, exactly like the reference does.
 __device__ __forceinline__ int pass1_march(const RenderConst& C, const float* __restrict__ c2w, int row_begin, int local,
-                                           float* __restrict__ tmins, float* __restrict__ tmaxs) {
+                                           float* __restrict__ tmins, float* __restrict__ tmaxs, float2* __restrict__ px_slot, int P,
+                                           bool& handed, float& T_last) {
     const int n = render_gpix(C, row_begin, local);
     Ray R;
     ray_setup(C, c2w, n, R);
@@ -106,8 +118,9 @@ __device__ __forceinline__ int pass1_march(const RenderConst& C, const float* __
     PvdbLeafCache vcache;
     float T_cum = 1.0f, t = R.tmin, tmin_out = R.tmin, tmax_out = R.tmax;
     const float tmax0 = R.tmax;
-    bool update_tmin = false, done = false;
-    int ns = 0;
+    bool update_tmin = false, done = false, sim = false;
+    float T2 = 1.0f;       // pass 2's transmittance
+    int ns = 0, r2 = 0;    // kept samples of pass 1 / of the simulated pass 2
     while (!done && t < tmax0) {
         int nslow = 0x7fffffff;
         if (C.skip_bits) {
@@ -120,44 +133,85 @@ __device__ __forceinline__ int pass1_march(const RenderConst& C, const float* __
             float xyz[3];
             int leaf;
             if (!step_active(C, R, S, t, xyz, leaf)) continue;
-            // trigetDensity (:191-220): int() truncation, res += d*f0*f1*f2 -> fma(f2, f1*(f0*d), res)
             const int i = (int)xyz[0], j = (int)xyz[1], k = (int)xyz[2];
             const float u = __fsub_rn(xyz[0], (float)i), v = __fsub_rn(xyz[1], (float)j), w = __fsub_rn(xyz[2], (float)k);
+            float den[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                den[q] = __ldg(C.dendata + idx_at(C, vcache, i + PVDB_CORNER[q][0], j + PVDB_CORNER[q][1], k + PVDB_CORNER[q][2]));
+            // trigetDensity (:191-220): int() truncation, res += d*f0*f1*f2 -> fma(f2, f1*(f0*d), res)
             float res = 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
-                const float d = __ldg(C.dendata + idx_at(C, vcache, i + dx, j + dy, k + dz));
                 const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
-                res = __fmaf_rn(f2, __fmul_rn(f1, __fmul_rn(f0, d)), res);
+                res = __fmaf_rn(f2, __fmul_rn(f1, __fmul_rn(f0, den[q])), res);
             }
             const float alpha = render_alpha(res, C.act_shift, C.interval);
-            if (alpha <= C.thres) continue;
-            const float weight = __fmul_rn(T_cum, alpha);
-            T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, alpha));
-            if (weight <= C.thres) continue;
-            ++ns;
-            if (!update_tmin) { tmin_out = __fsub_rn(t, R.steplen); update_tmin = true; }
-            if ((double)T_cum < 1e-3) { tmax_out = t; done = true; break; }
+            bool kept = false;
+            if (alpha > C.thres) {
+                const float weight = __fmul_rn(T_cum, alpha);
+                T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, alpha));
+                kept = weight > C.thres;
+            }
+            if (kept) {
+                ++ns;
+                if (!update_tmin) {
+                    tmin_out = __fsub_rn(t, R.steplen);
+                    update_tmin = true;
+                    sim = px_slot != nullptr && __fadd_rn(tmin_out, R.steplen) == t;
+                }
+            }
+            if (sim) {
+                // pass 2 on this step: trigetDensity2 (:271-300), d0*s0 + d1*s1 + ... -> fma(d7,s7, ... fma(d2,s2, fma(d0,s0, d1*s1)))
+                float sc[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+                    const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
+                    sc[q] = __fmul_rn(__fmul_rn(f0, f1), f2);
+                }
+                float vden = __fmaf_rn(den[0], sc[0], __fmul_rn(den[1], sc[1]));
+#pragma unroll
+                for (int q = 2; q < 8; ++q) vden = __fmaf_rn(den[q], sc[q], vden);
+                const float alpha2 = render_alpha(vden, C.act_shift, C.interval);
+                if (alpha2 > C.thres) {
+                    const float w2 = __fmul_rn(T2, alpha2);
+                    T2 = __fmul_rn(T2, __fsub_rn(1.f, alpha2));
+                    if (w2 > C.thres) {
+                        if (r2 < P) px_slot[r2] = make_float2(t, w2);
+                        ++r2;
+                    }
+                }
+            }
+            if (kept && (double)T_cum < 1e-3) { tmax_out = t; done = true; break; }
         }
     }
     tmins[local] = tmin_out;
     tmaxs[local] = tmax_out;
+    handed = sim && r2 == ns && ns <= P;
+    T_last = T2;
     return ns;
 }
 
 __global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float* __restrict__ c2w, int row_begin, int rows,
                                                       int32_t* __restrict__ n_samples, float* __restrict__ tmins,
                                                       float* __restrict__ tmaxs, int32_t* __restrict__ active_list,
-                                                      int32_t* __restrict__ counters, float* __restrict__ out_rgb) {
+                                                      int32_t* __restrict__ counters, float* __restrict__ out_rgb,
+                                                      float2* __restrict__ px_scratch, int P) {
     pvdb_pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[RC_FALLBACK] = 0;   // k_render_emit of this frame counts from 0; stays readable after the frame
     int local;
     const bool in_image = pixel_of_thread(C.W, rows, local) >= 0;
     int ns = 0;
-    if (in_image) ns = pass1_march(C, c2w, row_begin, local, tmins, tmaxs);
+    bool handed = false;
+    float T_last = 1.f;
+    if (in_image) ns = pass1_march(C, c2w, row_begin, local, tmins, tmaxs, px_scratch ? px_scratch + (size_t)local * P : nullptr, P, handed, T_last);
     if (in_image) {
         n_samples[local] = ns;
-        if (ns == 0) { out_rgb[local * 3] = C.bg; out_rgb[local * 3 + 1] = C.bg; out_rgb[local * 3 + 2] = C.bg; }   // :324-329
+        // :324-329 for a pixel without samples; :364-365 (T * bg, the composite adds the samples) for one handed over
+        const float last = ns == 0 ? C.bg : __fmul_rn(T_last, C.bg);
+        if (ns == 0 || handed) { out_rgb[local * 3] = last; out_rgb[local * 3 + 1] = last; out_rgb[local * 3 + 2] = last; }
     }
     // pixels that have samples are appended to the work list of pass 2 (one atomic per warp; a warp's pixels stay together)
     const unsigned act = __ballot_sync(0xffffffffu, ns > 0);
@@ -166,11 +220,43 @@ __global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float
         int base = 0;
         if (lane == 0) base = atomicAdd(counters + RC_ACTIVE, __popc(act));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (ns > 0) active_list[base + __popc(act & ((1u << lane) - 1))] = local;
+        if (ns > 0) active_list[base + __popc(act & ((1u << lane) - 1))] = (px_scratch && !handed) ? (local | PX_FALLBACK_BIT) : local;
     }
 }
 
-
+// Hand-over of pass 1's samples (one thread per listed pixel): the pixel's (t, weight) slot becomes its segment of the sample
+// list — position as step_active computes it, in the first three floats of the feature row; the pixels pass 1 could not hand
+// over go to the fallback list, which pass 2 marches like the reference does.
+__global__ void __launch_bounds__(256) k_render_emit(RenderConst C, const float* __restrict__ c2w, int row_begin,
+                                                     const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
+                                                     const int32_t* __restrict__ active_list, const float2* __restrict__ px_scratch, int P,
+                                                     int32_t* __restrict__ s_ray, float* __restrict__ s_weight, float* __restrict__ s_feat,
+                                                     int64_t cap, int32_t* __restrict__ fallback_list, int32_t* __restrict__ counters) {
+    pvdb_pdl_wait();
+    const int n_active = counters[RC_ACTIVE];
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_active; slot += gridDim.x * blockDim.x) {
+        const int e = active_list[slot];
+        const int local = e & ~PX_FALLBACK_BIT;
+        if (e & PX_FALLBACK_BIT) {
+            fallback_list[atomicAdd(counters + RC_FALLBACK, 1)] = local;
+            continue;
+        }
+        const int ns = n_samples[local];
+        const int64_t i0 = i_starts[local];
+        const float2* src = px_scratch + (size_t)local * P;
+        Ray R;
+        ray_setup(C, c2w, render_gpix(C, row_begin, local), R);
+        for (int r = 0; r < ns; ++r) {
+            if (i0 + r >= cap) break;
+            const float2 v = src[r];
+            float* dst = s_feat + (i0 + r) * 12;      // position now, colour features after k_render_gather
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dst[a] = __fmul_rn(__fmaf_rn(R.rd[a], v.x, R.ro[a]), C.wld[a]);
+            s_weight[i0 + r] = v.y;
+            s_ray[i0 + r] = local;
+        }
+    }
+}
 
 // ---- exclusive scan over npix ints: 4096 items per CTA, then the block sums, then the offsets
 __global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n,
@@ -247,10 +333,11 @@ __global__ void __launch_bounds__(256) k_render_pass2(RenderConst C, const float
                                                       const float* __restrict__ tmins, const float* __restrict__ tmaxs,
                                                       int32_t* __restrict__ s_ray, float* __restrict__ s_weight,
                                                       float* __restrict__ s_feat, int64_t cap, const int32_t* __restrict__ active_list,
-                                                      float* __restrict__ out_rgb, int32_t* __restrict__ counters) {
+                                                      float* __restrict__ out_rgb, int32_t* __restrict__ counters, int count_slot) {
     pvdb_pdl_wait();
-    // one thread per pixel that has samples (the list pass 1 built): full warps instead of the ~15 live lanes of a pixel tile
-    const int n_active = counters[RC_ACTIVE];
+    // one thread per listed pixel (every pixel with samples, or just those pass 1 could not hand over): full warps instead of
+    // the ~15 live lanes of a pixel tile
+    const int n_active = counters[count_slot];
   for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_active; slot += gridDim.x * blockDim.x) {
     const int local = active_list[slot];
     const int ns = n_samples[local];
@@ -472,7 +559,7 @@ __global__ void __launch_bounds__(256) k_render_composite(const int32_t* __restr
                                                           float* __restrict__ frame_out) {
     pvdb_pdl_wait();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) counters[RC_ACTIVE] = 0;      // pass 2 of this frame is done with it; pass 1 of the next frame counts from 0
+    if (p == 0) counters[RC_ACTIVE] = 0;      // this frame is done with it; pass 1 of the next frame counts from 0
     if (p >= npix) return;
     const int ns = n_samples[p];
     if (ns == 0 && !frame_out) return;
@@ -596,8 +683,10 @@ static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, co
     const int tiles = ((cfg->W + 7) / 8) * ((rows + 3) / 4);
     const int pgrid = pvdb_grid_for((int64_t)tiles * 32, 256);
     PVDB_CHECK_ARG(b->active_list, "active_list scratch missing");
+    const bool hand_over = b->px_scratch && b->fallback_list && b->px_entries > 0;
+    float2* px = hand_over ? static_cast<float2*>(b->px_scratch) : nullptr;
     PVDB_CUDA(pvdb_launch_pdl(k_render_pass1, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs, b->active_list,
-                              b->counters, out_rgb));
+                              b->counters, out_rgb, px, (int)b->px_entries));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_pass1", st);
     const int nb = (npix + 4095) / 4096;
@@ -609,9 +698,17 @@ static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, co
     PVDB_CUDA(pvdb_launch_pdl(k_scan_add, dim3(nb), dim3(1024), 0, st, b->i_starts, npix, (const int32_t*)b->scan_tmp, nb, b->counters, b->cap_samples));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_scan", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_render_pass2, dim3(min(pgrid, PVDB_SMS * 8)), dim3(256), 0, st, C, c2w, row_begin, rows, (const int32_t*)b->n_samples,
-                              (const int32_t*)b->i_starts, (const float*)b->tmins, (const float*)b->tmaxs, b->s_ray, b->s_weight, b->s_feat, b->cap_samples,
-                              (const int32_t*)b->active_list, out_rgb, b->counters));
+    if (hand_over) {
+        PVDB_CUDA(pvdb_launch_pdl(k_render_emit, dim3(min(pgrid, PVDB_SMS * 8)), dim3(256), 0, st, C, c2w, row_begin, (const int32_t*)b->n_samples,
+                                  (const int32_t*)b->i_starts, (const int32_t*)b->active_list, (const float2*)px, (int)b->px_entries, b->s_ray, b->s_weight, b->s_feat, b->cap_samples,
+                                  b->fallback_list, b->counters));
+        PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("render_emit", st);
+    }
+    PVDB_CUDA(pvdb_launch_pdl(k_render_pass2, dim3(hand_over ? PVDB_SMS : min(pgrid, PVDB_SMS * 8)), dim3(256), 0, st, C, c2w, row_begin, rows,
+                              (const int32_t*)b->n_samples, (const int32_t*)b->i_starts, (const float*)b->tmins, (const float*)b->tmaxs, b->s_ray, b->s_weight,
+                              b->s_feat, b->cap_samples, (const int32_t*)(hand_over ? b->fallback_list : b->active_list), out_rgb, b->counters,
+                              hand_over ? RC_FALLBACK : RC_ACTIVE));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("render_pass2", st);
     PVDB_CUDA(pvdb_launch_pdl(k_render_gather, dim3(PVDB_SMS * 8), dim3(256), 0, st, C, b->s_feat, (const int32_t*)b->counters, b->cap_samples));

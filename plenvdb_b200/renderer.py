@@ -45,7 +45,7 @@ def save_merged(basepath, den, col, idx_dense):
 class MGRenderer:
     """MGRenderer(dcol, dpe, dhid, dout) (plenvdb.h:936-945)."""
 
-    def __init__(self, dcol=12, dpe=27, dhid=128, dout=3, device="cuda", use_tensor_cores=True, skip_empty=True):
+    def __init__(self, dcol=12, dpe=27, dhid=128, dout=3, device="cuda", use_tensor_cores=True, skip_empty=True, px_entries=64):
         self.dcol, self.dpe, self.dhid, self.dout = int(dcol), int(dpe), int(dhid), int(dout)
         self.dev = torch.device(device)
         self.flags = [False] * 5   # load_data, load_params, setScene, setKwargs, input_a_c2w (plenvdb.h:1056)
@@ -56,6 +56,8 @@ class MGRenderer:
         self._scratch_rows = -1
         self.skip_empty = bool(skip_empty)   # skip runs of march steps that cannot touch a leaf (bit-identical results)
         self._skip_key, self._skip_bits, self._topo_version = None, None, 0
+        # pass 1 hands its first px_entries kept samples per pixel over to the sample list (0: every pixel is marched twice)
+        self.px_entries = int(px_entries)
         self.c2w = torch.zeros(16, dtype=torch.float32, device=self.dev)
         self.out = None
 
@@ -148,6 +150,11 @@ class MGRenderer:
         for k, t in self.s.items():
             setattr(b, k, t.data_ptr())
         b.cap_samples = cap
+        if self.px_entries > 0:
+            self.s["px_scratch"] = torch.empty(npix * self.px_entries * 2, **f32)
+            self.s["fallback_list"] = torch.zeros(npix, **i32)
+            b.px_scratch, b.fallback_list = self.s["px_scratch"].data_ptr(), self.s["fallback_list"].data_ptr()
+            b.px_entries = self.px_entries
         self.bufs = b
         self._scratch_rows = rows
         self._ensure_skip_bits()
@@ -215,7 +222,12 @@ class MGRenderer:
 
     def counters(self):
         c = self.s["counters"].cpu().numpy()
-        return dict(total=int(c[0]), overflow=int(c[1]), inconsistent=int(c[2]))
+        return dict(total=int(c[0]), overflow=int(c[1]), inconsistent=int(c[2]), remarched=int(c[4]))
+
+    def set_px_entries(self, n):
+        """Change the hand-over slot size (0 = march every pixel twice like the reference); takes effect on the next call."""
+        self.px_entries = int(n)
+        self._scratch_rows = -1
 
     def launches_last_call(self):
         return int(_lib.lib.pvdb_last_launch_count())

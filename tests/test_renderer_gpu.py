@@ -170,3 +170,35 @@ def test_empty_space_skipping_is_bit_identical(variant):
         assert a[8] == b[8] and a[8]["total"] > 2000 and a[8]["overflow"] == 0
         for x, y in zip(a[:8], b[:8]):
             assert torch.equal(x, y)
+
+
+def test_sample_hand_over_equals_the_second_march(merged):
+    """Pass 1 hands its kept samples over to the sample list (px_entries per pixel); pixels with more samples, or whose
+    restarted t chain would differ, are marched a second time like in the reference.  Whatever the slot size — 0 (every pixel
+    marched twice), 2 (most pixels fall back) or 32 — the sample list and the frame are the same bit for bit."""
+    from plenvdb_b200 import synth
+    scene, (dend, cold, idx, n), _ = merged
+    H, W = 150, 170
+    out = {}
+    for P in (0, 2, 32):
+        r, mlp, K = _renderer(scene, dend, cold, idx, H, W)
+        r.set_px_entries(P)
+        res = []
+        for cam in (1, 4, 6):
+            c2w = torch.from_numpy(synth.render_cameras(8)[cam].reshape(-1).copy()).cuda()
+            img = r.render_rows_torch(c2w, 0, H).clone()
+            c = r.counters()
+            tot = c["total"]
+            res.append((img, r.s["n_samples"].clone(), r.s["i_starts"].clone(), r.s["s_weight"][:tot].clone(), r.s["s_ray"][:tot].clone(),
+                        r.s["s_feat"][:tot].clone(), c))
+        out[P] = res
+    for P in (2, 32):
+        for a, b in zip(out[0], out[P]):
+            assert a[6]["total"] == b[6]["total"] > 2000 and b[6]["overflow"] == 0 and a[6]["inconsistent"] == b[6]["inconsistent"]
+            for x, y in zip(a[:6], b[:6]):
+                assert torch.equal(x, y)
+    active = int((out[0][0][1] > 0).sum())
+    big = int((out[0][0][1] > 2).sum())
+    assert out[0][0][6]["remarched"] == 0                       # nothing is handed over, nothing falls back
+    assert big <= out[2][0][6]["remarched"] <= active and big > 100
+    assert out[32][0][6]["remarched"] <= active // 20           # the restarted chain almost always reproduces pass 1's
