@@ -350,7 +350,7 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
                 False, H, W)
     poses = torch.from_numpy(synth.render_cameras(200).reshape(200, 16)).to(dev)
     nf = args.frames
-    # N > 1: interleaved 4-row groups, every rank's composite kernel writes its pixels into rank 0's frame over NVLink peer
+    # N > 1: interleaved 16-row groups, every rank's composite kernel writes its pixels into rank 0's frame over NVLink peer
     # memory (no collective); --render-gather nccl = contiguous row bands + an NCCL gather
     peer = None
     sharding = "single GPU"
@@ -358,8 +358,8 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
         sharding = "contiguous row bands + NCCL gather"
         if args.render_gather == "peer":
             try:
-                peer = pdist.PeerFrame(H, W, band_rows=4)
-                sharding = "interleaved 4-row groups, frame assembled in rank 0's memory by peer stores over NVLink (no collective)"
+                peer = pdist.PeerFrame(H, W, band_rows=16)
+                sharding = "interleaved 16-row groups, frame assembled in rank 0's memory by peer stores over NVLink (no collective)"
             except pdist.PeerExchangeUnavailable as e:
                 sys.stderr.write("render: %s; falling back to the NCCL gather\n" % e)
 
@@ -404,7 +404,7 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
             raise RuntimeError("peer frame assembly reported error %d (a rank did not arrive in time)" % perr)
     return {"metric": "merged-VDB render FPS 800x800", "sharding": sharding, "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "frames": nf,
             "e2e_fps": nf * 1e3 / float(t.item()), "d2h_bytes_per_frame": H * W * 3 * 4, "samples_last_band": c["total"],
-            "inconsistent_rays_last_band": c["inconsistent"], "merged_voxels": n, "row_bands": world,
+            "inconsistent_rays_last_band": c["inconsistent"], "pixels_marched_twice_last_band": c["remarched"], "merged_voxels": n, "row_bands": world,
             "gpu_launches_per_frame": r.launches_last_call()}
 
 

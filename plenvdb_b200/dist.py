@@ -292,7 +292,7 @@ class PeerFrame:
     groups of `band_rows` rows and its composite kernel stores them straight into root's frame buffer; one release/acquire
     signal per rank replaces the gather.  No NCCL call and no host synchronisation per frame."""
 
-    def __init__(self, H, W, band_rows=4, root=0, group=None):
+    def __init__(self, H, W, band_rows=16, root=0, group=None):
         import ctypes as C
         from . import _lib
         self._C, self._lib = C, _lib
