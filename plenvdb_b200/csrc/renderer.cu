@@ -224,9 +224,11 @@ __global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float
     }
 }
 
-// Hand-over of pass 1's samples (one thread per listed pixel): the pixel's (t, weight) slot becomes its segment of the sample
-// list — position as step_active computes it, in the first three floats of the feature row; the pixels pass 1 could not hand
-// over go to the fallback list, which pass 2 marches like the reference does.
+// Hand-over of pass 1's samples: the pixel's (t, weight) slot becomes its segment of the sample list — position as step_active
+// computes it, in the first three floats of the feature row; the pixels pass 1 could not hand over go to the fallback list,
+// which pass 2 marches like the reference does.  A warp takes 32 listed pixels: every lane sets up one pixel's ray, then the
+// warp walks the 32 pixels together, lane r copying sample r (and r + 32) — coalesced slot reads and list writes instead of
+// one thread looping over its pixel's samples (38 us -> see profiles/).
 __global__ void __launch_bounds__(256) k_render_emit(RenderConst C, const float* __restrict__ c2w, int row_begin,
                                                      const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
                                                      const int32_t* __restrict__ active_list, const float2* __restrict__ px_scratch, int P,
@@ -234,26 +236,47 @@ __global__ void __launch_bounds__(256) k_render_emit(RenderConst C, const float*
                                                      int64_t cap, int32_t* __restrict__ fallback_list, int32_t* __restrict__ counters) {
     pvdb_pdl_wait();
     const int n_active = counters[RC_ACTIVE];
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_active; slot += gridDim.x * blockDim.x) {
-        const int e = active_list[slot];
-        const int local = e & ~PX_FALLBACK_BIT;
-        if (e & PX_FALLBACK_BIT) {
-            fallback_list[atomicAdd(counters + RC_FALLBACK, 1)] = local;
-            continue;
-        }
-        const int ns = n_samples[local];
-        const int64_t i0 = i_starts[local];
-        const float2* src = px_scratch + (size_t)local * P;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n_active; base += warps * 32) {
+        // lane j: metadata and ray of listed pixel base + j
+        const int slot = base + lane;
+        int e = 0, ns = 0;
+        int64_t i0 = 0;
         Ray R;
-        ray_setup(C, c2w, render_gpix(C, row_begin, local), R);
-        for (int r = 0; r < ns; ++r) {
-            if (i0 + r >= cap) break;
-            const float2 v = src[r];
-            float* dst = s_feat + (i0 + r) * 12;      // position now, colour features after k_render_gather
 #pragma unroll
-            for (int a = 0; a < 3; ++a) dst[a] = __fmul_rn(__fmaf_rn(R.rd[a], v.x, R.ro[a]), C.wld[a]);
-            s_weight[i0 + r] = v.y;
-            s_ray[i0 + r] = local;
+        for (int a = 0; a < 3; ++a) { R.ro[a] = 0.f; R.rd[a] = 0.f; }
+        if (slot < n_active) {
+            e = active_list[slot];
+            const int local = e & ~PX_FALLBACK_BIT;
+            if (e & PX_FALLBACK_BIT) {
+                fallback_list[atomicAdd(counters + RC_FALLBACK, 1)] = local;
+            } else {
+                ns = n_samples[local];
+                i0 = i_starts[local];
+                ray_setup(C, c2w, render_gpix(C, row_begin, local), R);
+            }
+        }
+        const int cnt = min(32, n_active - base);
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const int nsj = __shfl_sync(0xffffffffu, ns, j);
+            if (nsj == 0) continue;                 // marched again by pass 2 (or past the end of the list)
+            const int local = __shfl_sync(0xffffffffu, e, j) & ~PX_FALLBACK_BIT;
+            const int64_t i0j = __shfl_sync(0xffffffffu, i0, j);
+            float ro[3], rd[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { ro[a] = __shfl_sync(0xffffffffu, R.ro[a], j); rd[a] = __shfl_sync(0xffffffffu, R.rd[a], j); }
+            const float2* src = px_scratch + (size_t)local * P;
+            for (int r = lane; r < nsj; r += 32) {
+                if (i0j + r >= cap) break;
+                const float2 v = src[r];
+                float* dst = s_feat + (i0j + r) * 12;      // position now, colour features after k_render_gather
+#pragma unroll
+                for (int a = 0; a < 3; ++a) dst[a] = __fmul_rn(__fmaf_rn(rd[a], v.x, ro[a]), C.wld[a]);
+                s_weight[i0j + r] = v.y;
+                s_ray[i0j + r] = local;
+            }
         }
     }
 }
