@@ -197,26 +197,43 @@ def run_ours(args):
     barrier()
     warm_ms = e0.elapsed_time(e1) / K
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + step + D2H(loss) inside the timed region
+    # ---- end to end through the public API with HOST buffers (pinned): every iteration's rays and targets are copied H2D and its
+    # loss words D2H inside the timed region.  Two ways to drive it: the strictly synchronous one (copy, step, read the loss,
+    # synchronise, every iteration: what `loss.item()` costs run.py) — the headline e2e — and, reported beside it, the pipelined
+    # loop a trainer that logs the loss later would use (copy stream, two staging buffers, iteration i's loss read while i + 1
+    # runs).  Measured on B200 the two are within noise of each other at this step size: the host needs ~95 us to issue an
+    # iteration either way (63 us of it inside pvdb_train_step's ~25 CUDA calls), the 393 KB copy ~10 us.
     hbatch = torch.stack([x[Wm:].cpu() for x in (ro, rd, vd, tg)], 1).contiguous().pin_memory()   # [K, 4, n, 3]
     dstage = torch.empty_like(hbatch[0], device=dev)
     hloss = torch.empty(4, dtype=torch.float32).pin_memory()
-    barrier()
-    e0.record()
-    for i in range(K):
-        if world == 1:
-            tr.step_from_host(hbatch[i])              # one H2D, the step, D2H of the loss, stream sync (the caller reads it)
-        else:
-            dstage.copy_(hbatch[i], non_blocking=True)
-            stepper(dstage[0], dstage[1], dstage[2], dstage[3])
-            hloss.copy_(tr.t["loss"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = world * N_RAYS * K / (float(t.item()) * 1e-3)
+    e2e_ms = {}
+    for i in range(min(3, K)):        # untimed: the pipeline's streams, staging and pinned buffers are created on first use
+        tr.step_from_host_async(hbatch[i], stepper=None if world == 1 else stepper)
+    tr.host_pipeline_flush()
+    for mode in ("sync", "pipelined"):
+        barrier()
+        e0.record()
+        for i in range(K):
+            if mode == "pipelined":
+                tr.step_from_host_async(hbatch[i], stepper=None if world == 1 else stepper)
+            elif world == 1:
+                tr.step_from_host(hbatch[i])              # one H2D, the step, D2H of the loss, stream sync (the caller reads it)
+            else:
+                dstage.copy_(hbatch[i], non_blocking=True)
+                stepper(dstage[0], dstage[1], dstage[2], dstage[3])
+                hloss.copy_(tr.t["loss"], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        if mode == "pipelined":
+            last = tr.host_pipeline_flush()
+            assert last is not None and bool(torch.isfinite(last).all())
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms[mode] = float(t.item())
+    e2e_value = world * N_RAYS * K / (e2e_ms["sync"] * 1e-3)
+    e2e_pipe_value = world * N_RAYS * K / (e2e_ms["pipelined"] * 1e-3)
     h2d = 4 * N_RAYS * 3 * 4
     clk.__exit__()
 
@@ -302,7 +319,10 @@ def run_ours(args):
                        "samples": {"M_alpha": cnt["M_alpha"], "M_keep": M3, "touched_leaves_density": cnt["n_touched_den"],
                                    "touched_leaves_k0": cnt["n_touched_k0"]}},
             "warm_l2_ms_per_step": warm_ms,
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                    "how": "FusedTrainer.step_from_host: pinned host batch -> one H2D -> step -> loss words D2H -> stream synchronise, "
+                           "every iteration",
+                    "pipelined_value": e2e_pipe_value},
             "gpu_launches": launches,
             "kernel_ms": kern,
             "roofline": roof,

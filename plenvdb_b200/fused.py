@@ -188,6 +188,51 @@ class FusedTrainer:
         torch.cuda.current_stream().synchronize()
         return self._loss_host
 
+    def step_from_host_async(self, batch_host, stepper=None):
+        """Pipelined variant of step_from_host for a training loop that does not need the loss of iteration i before it issues
+        iteration i + 1 (run.py only prints it every few hundred iterations).  The H2D copy of `batch_host` (pinned float32
+        [4, n, 3]) goes through a copy stream into one of two staging buffers, so it overlaps the previous iteration still
+        running; the step waits for it on the current stream; the loss words follow into one of two pinned buffers.  Returns
+        the PREVIOUS call's loss words (None on the first call) after waiting for that iteration only — the GPU always has the
+        next iteration queued behind the running one.  host_pipeline_flush() returns the last one.
+        stepper: callable(rays_o, rays_d, viewdirs, target) issuing the iteration (default self.step; DataParallelTrainer.step
+        for a sharded run)."""
+        n = batch_host.shape[1]
+        p = getattr(self, "_pipe", None)
+        if p is None or p["n"] != n:
+            p = dict(n=n, i=0, copy=torch.cuda.Stream(device=self.dev),
+                     stage=[torch.empty((4, n, 3), dtype=torch.float32, device=self.dev) for _ in range(2)],
+                     loss=[torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)],
+                     copied=[torch.cuda.Event() for _ in range(2)], done=[torch.cuda.Event() for _ in range(2)], used=[False, False])
+            self._pipe = p
+        k = p["i"] & 1
+        cur = torch.cuda.current_stream()
+        if p["used"][k]:
+            p["copy"].wait_event(p["done"][k])      # the iteration that read stage[k] (two calls ago) has finished
+        with torch.cuda.stream(p["copy"]):
+            p["stage"][k].copy_(batch_host, non_blocking=True)
+            p["copied"][k].record(p["copy"])
+        cur.wait_event(p["copied"][k])
+        st = p["stage"][k]
+        (stepper or self.step)(st[0], st[1], st[2], st[3])
+        p["loss"][k].copy_(self.t["loss"], non_blocking=True)
+        p["done"][k].record(cur)
+        p["used"][k] = True
+        p["i"] += 1
+        if p["used"][k ^ 1]:
+            p["done"][k ^ 1].synchronize()
+            return p["loss"][k ^ 1]
+        return None
+
+    def host_pipeline_flush(self):
+        """Wait for the last iteration issued through step_from_host_async and return its loss words (pinned host tensor)."""
+        p = getattr(self, "_pipe", None)
+        if p is None or p["i"] == 0:
+            return None
+        k = (p["i"] - 1) & 1
+        p["done"][k].synchronize()
+        return p["loss"][k]
+
     def step_dp(self, peers, dp_step, rays_o, rays_d, viewdirs, target):
         """One data-parallel iteration (pvdb_train_step_dp): the NVLink tile exchange overlaps the weight-gradient kernel."""
         self.step_count += 1

@@ -274,3 +274,31 @@ def test_training_reduces_the_loss(small):
     assert np.isfinite(losses).all()
     assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
     assert tr.counters()["overflow"] == 0
+
+
+def test_host_pipeline_matches_synchronous_steps(small):
+    """step_from_host_async (H2D on a copy stream into two staging buffers, losses one call late) drives exactly the same
+    iterations as the synchronous step_from_host: same losses in the same order, same parameters."""
+    scene, net, rays = small
+    rng = np.random.default_rng(3)
+    batches = []
+    for _ in range(6):
+        perm = rng.permutation(2048)[:1024]
+        batches.append(torch.from_numpy(np.stack([a[perm] for a in rays], 0).copy()).pin_memory())   # [4, 1024, 3]
+    tr_a, den_a, k0_a = _trainer(scene, net, 1024)
+    tr_b, den_b, k0_b = _trainer(scene, net, 1024)
+    la = [tr_a.step_from_host(b).clone() for b in batches]
+    lb = []
+    for i, b in enumerate(batches):
+        prev = tr_b.step_from_host_async(b)
+        assert (prev is None) == (i == 0)
+        if prev is not None:
+            lb.append(prev.clone())
+    lb.append(tr_b.host_pipeline_flush().clone())
+    assert len(lb) == len(la) == 6
+    for x, y in zip(la, lb):
+        np.testing.assert_allclose(y.numpy(), x.numpy(), rtol=1e-4, atol=1e-6)
+    assert tr_a.step_count == tr_b.step_count == 6
+    np.testing.assert_allclose(tr_b.net.cpu().numpy(), tr_a.net.cpu().numpy(), rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(den_b.grid.cpu().numpy(), den_a.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(k0_b.grid.cpu().numpy(), k0_a.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
