@@ -198,11 +198,12 @@ def run_ours(args):
     warm_ms = e0.elapsed_time(e1) / K
 
     # ---- end to end through the public API with HOST buffers (pinned): every iteration's rays and targets are copied H2D and its
-    # loss words D2H inside the timed region.  Two ways to drive it: the strictly synchronous one (copy, step, read the loss,
-    # synchronise, every iteration: what `loss.item()` costs run.py) — the headline e2e — and, reported beside it, the pipelined
-    # loop a trainer that logs the loss later would use (copy stream, two staging buffers, iteration i's loss read while i + 1
-    # runs).  Measured on B200 the two are within noise of each other at this step size: the host needs ~95 us to issue an
-    # iteration either way (63 us of it inside pvdb_train_step's ~25 CUDA calls), the 393 KB copy ~10 us.
+    # loss words D2H inside the timed region.  Two ways to drive it.  Headline: FusedTrainer.step_from_host_async, the loop a
+    # trainer that logs the loss one iteration late uses — copy stream, two staging buffers, iteration i's loss words read
+    # while i + 1 runs, one wait per iteration (on iteration i - 1).  Beside it: the strictly synchronous step_from_host (copy,
+    # step, read the loss, synchronise, every iteration — what `psnr.item()` costs run.py:590).  The host needs ~95 us to
+    # issue an iteration (63 us of it inside pvdb_train_step's ~25 CUDA calls), the 393 KB copy ~10 us: synchronously they
+    # add to the step, pipelined they hide under the previous iteration.
     hbatch = torch.stack([x[Wm:].cpu() for x in (ro, rd, vd, tg)], 1).contiguous().pin_memory()   # [K, 4, n, 3]
     dstage = torch.empty_like(hbatch[0], device=dev)
     hloss = torch.empty(4, dtype=torch.float32).pin_memory()
@@ -223,17 +224,16 @@ def run_ours(args):
                 stepper(dstage[0], dstage[1], dstage[2], dstage[3])
                 hloss.copy_(tr.t["loss"], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-        if mode == "pipelined":
-            last = tr.host_pipeline_flush()
-            assert last is not None and bool(torch.isfinite(last).all())
+        last = tr.host_pipeline_flush() if mode == "pipelined" else None
         e1.record()
         barrier()
+        assert mode != "pipelined" or (last is not None and bool(torch.isfinite(last).all()))
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms[mode] = float(t.item())
-    e2e_value = world * N_RAYS * K / (e2e_ms["sync"] * 1e-3)
-    e2e_pipe_value = world * N_RAYS * K / (e2e_ms["pipelined"] * 1e-3)
+    e2e_sync_value = world * N_RAYS * K / (e2e_ms["sync"] * 1e-3)
+    e2e_value = world * N_RAYS * K / (e2e_ms["pipelined"] * 1e-3)
     h2d = 4 * N_RAYS * 3 * 4
     clk.__exit__()
 
@@ -320,9 +320,10 @@ def run_ours(args):
                                    "touched_leaves_k0": cnt["n_touched_k0"]}},
             "warm_l2_ms_per_step": warm_ms,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
-                    "how": "FusedTrainer.step_from_host: pinned host batch -> one H2D -> step -> loss words D2H -> stream synchronise, "
-                           "every iteration",
-                    "pipelined_value": e2e_pipe_value},
+                    "how": "FusedTrainer.step_from_host_async, every iteration: pinned host batch -> H2D on a copy stream -> step -> loss "
+                           "words D2H to pinned host; the host waits for iteration i - 1 and reads its loss while iteration i runs",
+                    "synchronous_value": e2e_sync_value,
+                    "synchronous_how": "FusedTrainer.step_from_host: H2D, step, D2H of the loss, stream synchronise, every iteration"},
             "gpu_launches": launches,
             "kernel_ms": kern,
             "roofline": roof,
