@@ -73,3 +73,45 @@ def test_sparse_gradient_exchange_world2():
     assert bytes0 == bytes1 == (n0 * 512 * 13 + 22019) * 4
     assert span0 == (0, 4096) and span1 == (4096, 8192)
     assert img0 == [0.0] * 5 + [1.0] * 5
+
+
+def _peer_setup_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from plenvdb_b200 import dist as pdist
+    pdist.init_from_env(backend="gloo")
+    outcomes = []
+    # without a CUDA device the symmetric blocks cannot be allocated: every rank must learn that in the same collective and
+    # raise the same exception — nobody is left waiting for a peer's handle (the NVLink paths then fall back to NCCL together)
+    for make in (lambda: pdist.open_symmetric_blocks(1 << 20), lambda: pdist.PeerFrame(64, 64), lambda: pdist.PeerExchange(40)):
+        try:
+            make()
+            outcomes.append("ok")
+        except pdist.PeerExchangeUnavailable as e:
+            outcomes.append("unavailable: %s" % str(e)[:40])
+    # the rows the sharded renderer gives each rank partition the image
+    rows = pdist.interleaved_rows_of(122, 16, rank, world)
+    all_rows = [None] * world
+    dist.all_gather_object(all_rows, rows)
+    q.put((rank, outcomes, sorted(sum(all_rows, [])) == list(range(122))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_memory_setup_fails_together_world2():
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("exercises the no-device failure path; the working path is covered by tests/test_dp_gpu.py")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_setup_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, outcomes, partition in out:
+        assert len(outcomes) == 3 and all(o.startswith("unavailable") for o in outcomes), outcomes
+        assert partition
+    assert out[0][1] == out[1][1]      # the same diagnosis (first failing rank's message) everywhere
