@@ -295,3 +295,21 @@ def render(cfg, idx_grid, dendata, coldata, mlp, c2w, row_begin=0, row_end=None)
     lib.orc_render(C.byref(c), idx_grid.h, _p(dd), _p(cd), cd.shape[1], _p(w0), _p(b0), _p(w1), _p(b1), _p(w2), _p(b2),
                    _p(cw), row_begin, row_end, _p(out), _p(ns), C.byref(bad))
     return out, ns, bad.value
+
+
+def march_check(cfg, idx_grid, dendata, c2w, skip_k=16, lanes=8, slot=64):
+    """Exactness of the fast march of csrc/renderer.cu (empty-space skipping, lane-parallel evaluation, simulated second march)
+    against the reference's step-by-step marches, pixel by pixel, on the CPU (orc_march_check)."""
+    c = RenderCfg()
+    c.reso = (C.c_int32 * 3)(*cfg["reso"])
+    c.K = (C.c_float * 9)(*[float(t) for t in np.asarray(cfg["K"]).reshape(-1)])
+    c.xyz_min = (C.c_float * 3)(*[float(t) for t in cfg["xyz_min"]])
+    c.xyz_max = (C.c_float * 3)(*[float(t) for t in cfg["xyz_max"]])
+    for k in ("near", "stepdist", "act_shift", "interval", "fast_color_thres", "bg", "inverse_y", "H", "W", "threads"):
+        setattr(c, k, cfg[k])
+    dd, cw = _f32(dendata), _f32(c2w)
+    stats = np.zeros(10, np.int64)
+    lib.orc_march_check(C.byref(c), idx_grid.h, _p(dd), _p(cw), int(skip_k), int(lanes), int(slot), _p(stats))
+    keys = ("pixels", "with_samples", "handed_over", "not_handed_t_chain", "not_handed_count", "not_handed_slot", "mismatches",
+            "steps_skipped", "steps_total", "reference_inconsistent")
+    return dict(zip(keys, [int(v) for v in stats]))

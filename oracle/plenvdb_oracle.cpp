@@ -790,6 +790,31 @@ struct IdxAcc {
 inline void tri_setup(const float* xyz, int* ijk, float* uvw) {
     for (int a = 0; a < 3; ++a) { ijk[a] = (int)xyz[a]; uvw[a] = xyz[a] - (float)ijk[a]; }   // int() truncation (:194-199)
 }
+// get_rays (:134-166) + get_tminmax (:50-64) of pixel n: direction in unit-box coordinates, unit view direction, step length in t
+// and the t range against the unit box.
+inline void pixel_ray(const orc_render_cfg* cfg, const float* c2w, const float* ro, const float* ext, int n, float* rd, float* vd,
+                      float& steplen, float& tmin, float& tmax) {
+    const int Wd = cfg->W;
+    const float far = 1e9f;   // setKwargs ignores `far` (plenvdb.h:1008)
+    const float pixeli = (float)((double)(n % Wd) + 0.5), pixelj = (float)((double)(n / Wd) + 0.5);
+    float dir[3];
+    if (cfg->inverse_y) { dir[0] = (pixeli - cfg->K[2]) / cfg->K[0]; dir[1] = (pixelj - cfg->K[5]) / cfg->K[4]; dir[2] = 1.f; }
+    else { dir[0] = (pixeli - cfg->K[2]) / cfg->K[0]; dir[1] = -((pixelj - cfg->K[5]) / cfg->K[4]); dir[2] = -1.f; }
+    float rdw[3];
+    for (int a = 0; a < 3; ++a)   // d0*c0 + d1*c1 + d2*c2 compiles to fma(d2,c2, fma(d0,c0, d1*c1)) (:140-142)
+        rdw[a] = fmaf(dir[2], c2w[a * 4 + 2], fmaf(dir[0], c2w[a * 4], dir[1] * c2w[a * 4 + 1]));
+    const float len = sqrtf(fmaf(rdw[2], rdw[2], fmaf(rdw[0], rdw[0], rdw[1] * rdw[1])));   // Vec3::length -> fma(z,z, fma(x,x, y*y))
+    steplen = cfg->stepdist / len;
+    for (int a = 0; a < 3; ++a) rd[a] = rdw[a] / ext[a];
+    const float inv = 1.0f / len;   // normalize(): *this *= 1/length (NanoVDB.h:1122-1123)
+    for (int a = 0; a < 3; ++a) vd[a] = rdw[a] * inv;
+    // get_tminmax (:50-64) against the unit box
+    const float vx = rd[0] == 0 ? 1e-6f : rd[0], vy = rd[1] == 0 ? 1e-6f : rd[1], vz = rd[2] == 0 ? 1e-6f : rd[2];
+    const float ax = (1 - ro[0]) / vx, ay = (1 - ro[1]) / vy, az = (1 - ro[2]) / vz;
+    const float bx = -ro[0] / vx, by = -ro[1] / vy, bz = -ro[2] / vz;
+    tmin = fmaxf(fminf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), far), cfg->near);
+    tmax = fmaxf(fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), far), cfg->near);
+}
 }  // namespace
 
 extern "C" void orc_render(const orc_render_cfg* cfg, const orc_grid* idx_grid, const float* dendata, const float* coldata, int cdim,
@@ -810,28 +835,8 @@ extern "C" void orc_render(const orc_render_cfg* cfg, const orc_grid* idx_grid, 
         std::vector<float> feats, weights, h0(W), h1(W);
         for (int64_t pp = pb; pp < pe; ++pp) {
             const int n = (int)(row_begin * (int64_t)Wd + pp);
-            // get_rays (:134-166)
-            const float pixeli = (float)((double)(n % Wd) + 0.5), pixelj = (float)((double)(n / Wd) + 0.5);
-            float dir[3];
-            if (cfg->inverse_y) { dir[0] = (pixeli - cfg->K[2]) / cfg->K[0]; dir[1] = (pixelj - cfg->K[5]) / cfg->K[4]; dir[2] = 1.f; }
-            else { dir[0] = (pixeli - cfg->K[2]) / cfg->K[0]; dir[1] = -((pixelj - cfg->K[5]) / cfg->K[4]); dir[2] = -1.f; }
-            float rdw[3];
-            for (int a = 0; a < 3; ++a)   // d0*c0 + d1*c1 + d2*c2 compiles to fma(d2,c2, fma(d0,c0, d1*c1)) (:140-142)
-                rdw[a] = fmaf(dir[2], c2w[a * 4 + 2], fmaf(dir[0], c2w[a * 4], dir[1] * c2w[a * 4 + 1]));
-            const float len = sqrtf(fmaf(rdw[2], rdw[2], fmaf(rdw[0], rdw[0], rdw[1] * rdw[1])));   // Vec3::length -> fma(z,z, fma(x,x, y*y))
-            const float steplen = cfg->stepdist / len;
-            float rd[3] = {rdw[0] / ext[0], rdw[1] / ext[1], rdw[2] / ext[2]};
-            const float inv = 1.0f / len;   // normalize(): *this *= 1/length (NanoVDB.h:1122-1123)
-            const float vd[3] = {rdw[0] * inv, rdw[1] * inv, rdw[2] * inv};
-            // get_tminmax (:50-64) against the unit box
-            float tmin, tmax;
-            {
-                const float vx = rd[0] == 0 ? 1e-6f : rd[0], vy = rd[1] == 0 ? 1e-6f : rd[1], vz = rd[2] == 0 ? 1e-6f : rd[2];
-                const float ax = (1 - ro[0]) / vx, ay = (1 - ro[1]) / vy, az = (1 - ro[2]) / vz;
-                const float bx = -ro[0] / vx, by = -ro[1] / vy, bz = -ro[2] / vz;
-                tmin = fmaxf(fminf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), far), cfg->near);
-                tmax = fmaxf(fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), far), cfg->near);
-            }
+            float rd[3], vd[3], steplen, tmin, tmax;
+            pixel_ray(cfg, c2w, ro, ext, n, rd, vd, steplen, tmin, tmax);
             float pe_feat[PE];
             pe_feat[0] = vd[0]; pe_feat[1] = vd[1]; pe_feat[2] = vd[2];
             {
@@ -947,4 +952,198 @@ extern "C" void orc_render(const orc_render_cfg* cfg, const orc_grid* idx_grid, 
         }
     });
     if (inconsistent_rays) *inconsistent_rays = bad.load();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exactness check of the fast march of plenvdb_b200/csrc/renderer.cu (test infrastructure, like everything here).
+// For every pixel it runs (A) the reference's two marches step by step, as orc_render does, and (B) a restatement of the
+// fast march: runs of `skip_k` steps whose index box cannot touch a leaf are replaced by their `t += steplen` chain alone
+// (dilated block map: a block or one of its +1 neighbours holds a leaf), the remaining steps are evaluated `lanes` at a time
+// BEFORE the ordered bookkeeping (the lane-parallel form: values of later steps are computed speculatively and ignored
+// after an early stop), and the second march is simulated on the corner values of the first — its own interpolation order,
+// transmittance and thresholds — from the first kept sample on.  Compared: sample count and tightened t range of every
+// pixel; for a pixel the fast march would hand over ((t_first - steplen) + steplen == t_first, simulated count == count,
+// count <= slot) the (t, weight) of every sample of the reference's second march and its final transmittance, bit for bit.
+// stats: 0 pixels, 1 pixels with samples, 2 handed over, 3 not handed: t chain, 4 not handed: count differs, 5 not handed:
+// slot too small, 6 MISMATCHES (must be 0), 7 steps skipped, 8 steps in total, 9 reference-inconsistent pixels (r != ns).
+// ------------------------------------------------------------------------------------------------
+extern "C" void orc_march_check(const orc_render_cfg* cfg, const orc_grid* idx_grid, const float* dendata, const float* c2w,
+                                int skip_k, int lanes, int slot, int64_t* stats) {
+    const int Wd = cfg->W, Hd = cfg->H;
+    const IdxAcc acc{idx_grid};
+    const float ext[3] = {cfg->xyz_max[0] - cfg->xyz_min[0], cfg->xyz_max[1] - cfg->xyz_min[1], cfg->xyz_max[2] - cfg->xyz_min[2]};
+    const float ro[3] = {(c2w[3] - cfg->xyz_min[0]) / ext[0], (c2w[7] - cfg->xyz_min[1]) / ext[1], (c2w[11] - cfg->xyz_min[2]) / ext[2]};
+    const float wld[3] = {(float)(cfg->reso[0] - 1), (float)(cfg->reso[1] - 1), (float)(cfg->reso[2] - 1)};
+    const float thres = cfg->fast_color_thres;
+    // dilated block map
+    const int nb[3] = {(cfg->reso[0] + 7) / 8, (cfg->reso[1] + 7) / 8, (cfg->reso[2] + 7) / 8};
+    std::vector<uint8_t> blk((size_t)nb[0] * nb[1] * nb[2], 0);
+    for (int l = 0; l < idx_grid->n_leaf(); ++l) {
+        const int bx = idx_grid->origin[l * 3] >> 3, by = idx_grid->origin[l * 3 + 1] >> 3, bz = idx_grid->origin[l * 3 + 2] >> 3;
+        for (int d = 0; d < 8; ++d) {
+            const int x = bx - (d & 1), y = by - ((d >> 1) & 1), z = bz - (d >> 2);
+            if (x < 0 || y < 0 || z < 0 || x >= nb[0] || y >= nb[1] || z >= nb[2]) continue;
+            blk[((size_t)x * nb[1] + y) * nb[2] + z] = 1;
+        }
+    }
+    std::atomic<int64_t> st[10];
+    for (auto& v : st) v = 0;
+    struct Sample { float t, w; };
+    // one step of either march: position, active test, corner densities; returns false when the step has no effect
+    auto step_values = [&](const float* rd, float t, float* uvw, float* den) -> bool {
+        float p[3], xyz[3];
+        for (int a = 0; a < 3; ++a) p[a] = fmaf(t, rd[a], ro[a]);
+        if ((0 > p[0]) | (0 > p[1]) | (0 > p[2]) | (1 < p[0]) | (1 < p[1]) | (1 < p[2])) return false;
+        for (int a = 0; a < 3; ++a) xyz[a] = p[a] * wld[a];
+        if (!acc.active((int)rintf(xyz[0]), (int)rintf(xyz[1]), (int)rintf(xyz[2]))) return false;
+        int ijk[3];
+        tri_setup(xyz, ijk, uvw);
+        for (int q = 0; q < 8; ++q) den[q] = dendata[acc.value(ijk[0] + CORNER[q][0], ijk[1] + CORNER[q][1], ijk[2] + CORNER[q][2])];
+        return true;
+    };
+    auto alpha_first = [&](const float* u, const float* den) {    // trigetDensity (:191-220)
+        float res = 0;
+        for (int q = 0; q < 8; ++q) {
+            const float f0 = CORNER[q][0] ? u[0] : 1 - u[0], f1 = CORNER[q][1] ? u[1] : 1 - u[1], f2 = CORNER[q][2] ? u[2] : 1 - u[2];
+            res = fmaf(f2, f1 * (f0 * den[q]), res);
+        }
+        return 1 - powf(1 + expf(res + cfg->act_shift), -cfg->interval);
+    };
+    auto alpha_second = [&](const float* u, const float* den) {   // trigetDensity2 (:271-300)
+        float sc[8];
+        for (int q = 0; q < 8; ++q) {
+            const float f0 = CORNER[q][0] ? u[0] : 1 - u[0], f1 = CORNER[q][1] ? u[1] : 1 - u[1], f2 = CORNER[q][2] ? u[2] : 1 - u[2];
+            sc[q] = (f0 * f1) * f2;
+        }
+        float vden = fmaf(den[0], sc[0], den[1] * sc[1]);
+        for (int q = 2; q < 8; ++q) vden = fmaf(den[q], sc[q], vden);
+        return 1 - powf(1 + expf(vden + cfg->act_shift), -cfg->interval);
+    };
+    parallel_for((int64_t)Hd * Wd, std::max(1, cfg->threads), [&](int64_t pb, int64_t pe) {
+        std::vector<Sample> ref2, sim2;
+        std::vector<float> lt(lanes), la1(lanes), la2(lanes);
+        std::vector<uint8_t> lact(lanes);
+        for (int64_t pp = pb; pp < pe; ++pp) {
+            float rd[3], vd[3], steplen, tmin0, tmax0;
+            pixel_ray(cfg, c2w, ro, ext, (int)pp, rd, vd, steplen, tmin0, tmax0);
+            // ---- (A) the reference, step by step
+            int ns = 0, r = 0;
+            float tmin = tmin0, tmax = tmax0, T_last;
+            {
+                float T_cum = 1.f, t = tmin0, u[3], den[8];
+                bool update_tmin = false;
+                while (t < tmax0) {
+                    t += steplen;
+                    if (!step_values(rd, t, u, den)) continue;
+                    const float alpha = alpha_first(u, den);
+                    if (alpha <= thres) continue;
+                    const float weight = T_cum * alpha;
+                    T_cum *= (1 - alpha);
+                    if (weight <= thres) continue;
+                    ++ns;
+                    if (!update_tmin) { tmin = t - steplen; update_tmin = true; }
+                    if (T_cum < 1e-3) { tmax = t; break; }
+                }
+                ref2.clear();
+                T_cum = 1.f; t = tmin;
+                if (ns > 0)
+                    while (t < tmax) {
+                        t += steplen;
+                        if (!step_values(rd, t, u, den)) continue;
+                        const float alpha = alpha_second(u, den);
+                        if (alpha <= thres) continue;
+                        const float weight = T_cum * alpha;
+                        T_cum *= (1 - alpha);
+                        if (weight <= thres) continue;
+                        ref2.push_back({t, weight});
+                        ++r;
+                    }
+                T_last = T_cum;
+            }
+            // ---- (B) the fast march
+            int ns_f = 0, r2 = 0;
+            float tmin_f = tmin0, tmax_f = tmax0, T2 = 1.f;
+            bool sim = false, chain_exact = true;
+            int64_t skipped = 0, total = 0;
+            {
+                float T_cum = 1.f, t = tmin0;
+                bool update_tmin = false, done = false;
+                sim2.clear();
+                while (!done && t < tmax0) {
+                    // chain of up to skip_k steps
+                    float t1 = t + steplen, tk = t1;
+                    int k = 1;
+                    for (int q = 1; q < skip_k; ++q)
+                        if (tk < tmax0) { tk += steplen; ++k; }
+                    total += k;
+                    bool empty = true, decided = false;
+                    int b[3];
+                    for (int a = 0; a < 3 && !decided; ++a) {
+                        const float pa = fmaf(rd[a], t1, ro[a]), pbb = fmaf(rd[a], tk, ro[a]);
+                        if (pa != pa || pbb != pbb) { empty = false; decided = true; break; }
+                        const float lo = fmaxf(fminf(pa, pbb), 0.f), hi = fminf(fmaxf(pa, pbb), 1.f);
+                        if (lo > hi) { empty = true; decided = true; break; }
+                        const int ilo = (int)rintf(lo * wld[a]) >> 3, ihi = (int)rintf(hi * wld[a]) >> 3;
+                        if (ihi - ilo > 1 || ilo < 0 || ihi >= nb[a]) { empty = false; decided = true; break; }
+                        b[a] = ilo;
+                    }
+                    if (!decided) empty = !blk[((size_t)b[0] * nb[1] + b[1]) * nb[2] + b[2]];
+                    if (empty) { t = tk; skipped += k; continue; }
+                    // the k steps of the run, `lanes` at a time: values first, ordered bookkeeping second
+                    for (int base = 0; base < k && !done; base += lanes) {
+                        const int m = std::min(lanes, k - base);
+                        float tt = t;
+                        for (int q = 0; q < m; ++q) {
+                            tt += steplen;
+                            lt[q] = tt;
+                            float u[3], den[8];
+                            lact[q] = step_values(rd, tt, u, den);
+                            if (lact[q]) { la1[q] = alpha_first(u, den); la2[q] = alpha_second(u, den); }
+                        }
+                        for (int q = 0; q < m; ++q) {
+                            t = lt[q];
+                            if (!lact[q]) continue;
+                            bool kept = false;
+                            if (la1[q] > thres) {
+                                const float weight = T_cum * la1[q];
+                                T_cum *= (1 - la1[q]);
+                                kept = weight > thres;
+                            }
+                            if (kept) {
+                                ++ns_f;
+                                if (!update_tmin) {
+                                    tmin_f = t - steplen;
+                                    update_tmin = true;
+                                    sim = true;
+                                    chain_exact = (tmin_f + steplen) == t;
+                                }
+                            }
+                            if (sim && la2[q] > thres) {
+                                const float w2 = T2 * la2[q];
+                                T2 *= (1 - la2[q]);
+                                if (w2 > thres) { sim2.push_back({t, w2}); ++r2; }
+                            }
+                            if (kept && T_cum < 1e-3) { tmax_f = t; done = true; break; }
+                        }
+                    }
+                }
+            }
+            st[0]++; st[7] += skipped; st[8] += total;
+            if (ns > 0) st[1]++;
+            if (ns > 0 && r != ns) st[9]++;
+            bool bad = ns_f != ns || std::memcmp(&tmin_f, &tmin, 4) || std::memcmp(&tmax_f, &tmax, 4);
+            if (ns > 0) {
+                if (!chain_exact) st[3]++;
+                else if (r2 != ns) st[4]++;
+                else if (ns > slot) st[5]++;
+                else {
+                    st[2]++;
+                    bad = bad || r != ns || (int)ref2.size() != ns || (int)sim2.size() != ns || std::memcmp(&T2, &T_last, 4);
+                    if (!bad) bad = std::memcmp(ref2.data(), sim2.data(), sizeof(Sample) * ns) != 0;
+                }
+            }
+            if (bad) st[6]++;
+        }
+    });
+    for (int i = 0; i < 10; ++i) stats[i] = st[i].load();
 }

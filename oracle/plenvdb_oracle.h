@@ -120,6 +120,11 @@ void orc_render(const orc_render_cfg* cfg, const orc_grid* idx_grid, const float
                 const float* c2w, int row_begin, int row_end, float* out_rgb, int32_t* n_samples_out,
                 int32_t* inconsistent_rays);
 
+/* Exactness check of the fast march of plenvdb_b200/csrc/renderer.cu (empty-space skipping, lane-parallel evaluation,
+ * simulated second march) against the step-by-step reference marches, pixel by pixel; see the .cpp.  stats: int64[10]. */
+void orc_march_check(const orc_render_cfg* cfg, const orc_grid* idx_grid, const float* dendata, const float* c2w,
+                     int skip_k, int lanes, int slot, int64_t* stats);
+
 #ifdef __cplusplus
 }
 #endif
