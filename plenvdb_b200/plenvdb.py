@@ -37,8 +37,16 @@ class _BaseVDB:
         self.grad = topo.new_plane(self.ndim)   # gradient plane
 
     # ---- maintenance on the device (the reference composes these from dense host round trips)
+    # The reference's VDB classes do not implement the TV regulariser: the method prints "Not Supported Now..." and returns
+    # (plenvdb.h:497-501, 574-578; grid.py:103-106 returns before calling it).  A drop-in must not silently change what a run
+    # with non-zero TV weights computes, so that stays the default; set `enable_total_variation = True` (class or instance)
+    # to run the dense kernel's semantics (total_variation_kernel.cu:14-35) on the sparse planes instead.
+    enable_total_variation = False
+
     def total_variation_add_grad(self, wx, wy, wz, dense_mode=True):
-        """grid.py:103-106 calls this name on the VDB object (and returns early because the reference lacks it)."""
+        if not self.enable_total_variation:
+            print("Not Supported Now...")
+            return
         from . import maintenance
         maintenance.total_variation_add_grad(self, wx, wy, wz, dense_mode)
 
@@ -152,10 +160,6 @@ class _BaseVDB:
         # the reference re-creates only `grid`; we keep grad congruent by construction
         self.grad = topo.new_plane(self.ndim)
         self.reso = list(reso)
-
-    def total_variation_add_grad(self, wx, wy, wz, dense_mode):
-        # plenvdb.h:497-501, 574-578: unimplemented in the reference as well
-        print("Not Supported Now...")
 
 
 class DensityVDB(_BaseVDB):
