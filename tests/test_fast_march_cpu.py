@@ -3,7 +3,6 @@ fast march — runs of steps whose index box cannot touch a leaf replaced by the
 at a time before the ordered transmittance bookkeeping, the reference's second march simulated on the first march's corner
 values — and compares it, pixel by pixel and bit for bit, with the reference's own two step-by-step marches
 (renderer.cu:222-268, 312-367).  The -m gpu tests check the kernels; this checks the argument on many more rays."""
-import numpy as np
 import pytest
 
 
