@@ -417,6 +417,53 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_sync_fps = nf * 1e3 / float(t.item())
+    e2e_fps, e2e_how = e2e_sync_fps, "pose H2D, frame, 7.68 MB D2H, stream synchronise, every frame"
+    if world == 1:
+        # the same with the D2H of frame i overlapping the render of frame i + 1 (two device frames, two pinned host frames, a
+        # copy stream); the caller has frame i - 1 on the host while frame i renders.  Checked against a synchronous render.
+        try:
+            copy = torch.cuda.Stream(device=dev)
+            cur = torch.cuda.current_stream()
+            outs = [torch.empty((H, W, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+            himgs = [torch.empty((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+            rendered = [torch.cuda.Event() for _ in range(2)]
+            copied = [torch.cuda.Event() for _ in range(2)]
+
+            def pipelined(n_frames):
+                used = [False, False]
+                for i in range(n_frames):
+                    k = i & 1
+                    if used[k]:
+                        cur.wait_event(copied[k])            # frame i - 2 has left outs[k]
+                    r.c2w.copy_(hposes[(3 + i) % 200], non_blocking=True)
+                    r.render_rows_torch(r.c2w, 0, H, out=outs[k])
+                    rendered[k].record(cur)
+                    copy.wait_event(rendered[k])
+                    with torch.cuda.stream(copy):
+                        himgs[k].copy_(outs[k], non_blocking=True)
+                        copied[k].record(copy)
+                    used[k] = True
+                    if i >= 1:
+                        copied[k ^ 1].synchronize()          # frame i - 1 is on the host
+                copied[(n_frames - 1) & 1].synchronize()
+
+            pipelined(3)
+            barrier()
+            e0.record()
+            pipelined(nf)
+            e1.record()
+            barrier()
+            pipe_ms = e0.elapsed_time(e1)
+            want = r.render_rows_torch(poses[(3 + nf - 1) % 200], 0, H).cpu()
+            if torch.equal(himgs[(nf - 1) & 1], want):
+                e2e_fps = nf * 1e3 / pipe_ms
+                e2e_how = ("pose H2D, frame, 7.68 MB D2H on a copy stream overlapping the next frame's render, every frame; the host "
+                           "waits for frame i - 1 while frame i renders")
+            else:
+                log("[bench] pipelined render e2e: last host frame differs from a synchronous render; reporting the synchronous loop")
+        except Exception as e:      # noqa: BLE001 — the synchronous number above stands
+            log("[bench] pipelined render e2e failed (%s); reporting the synchronous loop" % e)
     c = r.counters()
     if peer is not None:
         perr = peer.error()
@@ -424,7 +471,7 @@ def run_render(args, scene, net, den, k0, dev, rank, world):
         if perr:
             raise RuntimeError("peer frame assembly reported error %d (a rank did not arrive in time)" % perr)
     return {"metric": "merged-VDB render FPS 800x800", "sharding": sharding, "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "frames": nf,
-            "e2e_fps": nf * 1e3 / float(t.item()), "d2h_bytes_per_frame": H * W * 3 * 4, "samples_last_band": c["total"],
+            "e2e_fps": e2e_fps, "e2e_how": e2e_how, "e2e_fps_synchronous": e2e_sync_fps, "d2h_bytes_per_frame": H * W * 3 * 4, "samples_last_band": c["total"],
             "inconsistent_rays_last_band": c["inconsistent"], "pixels_marched_twice_last_band": c["remarched"], "merged_voxels": n, "row_bands": world,
             "gpu_launches_per_frame": r.launches_last_call()}
 
