@@ -20,8 +20,15 @@ sources; every function cites the code it follows (paths relative to openvdb/ope
                            only the active values stored) and io/Compression.cc:79-110 the zlib chunk format
                            (int64 size; <= 0 means that many raw bytes follow)
 
-Supported on read: compression NONE / ZIP with or without ACTIVE_MASK, half-float grids, tiles at any level (expanded into
-voxels), file versions >= 222.  Blosc chunks are rejected with a clear error (no Blosc codec in this image).
+  io/Compression.cc:172-187, 266-307  the Blosc chunk format (int64 size; <= 0 means raw bytes): one Blosc-1 chunk per buffer,
+                           written with blosc_compress_ctx(clevel 9, byte shuffle, typesize 4, LZ4, blocksize = buffer size)
+
+Supported on read: compression NONE / ZIP / BLOSC with or without ACTIVE_MASK, half-float grids, tiles at any level (expanded
+into voxels), file versions >= 222.  c-blosc is not vendored in the reference tree and not installed here, so the Blosc-1
+chunk container (16-byte header, block offsets, per-block byte-shuffle splits) and the LZ4 block format are restated from
+their published specifications (c-blosc README_HEADER.rst / blosc.c: blosc_d; lz4_Block_format.md); chunks compressed
+with LZ4 / LZ4HC (what OpenVDB writes) or zlib, stored raw ("memcpyed") or byte-shuffled are decoded, BloscLZ / Snappy / Zstd
+and bit-shuffled chunks are rejected with a clear error.
 Written: version 224, ZIP | ACTIVE_MASK by default (what OpenVDB itself writes when built without Blosc).
 
 PARITY UNPINNED: there is no OpenVDB build and no ``.vdb`` sample in this environment, so the codec is checked by
@@ -48,6 +55,139 @@ _TOTAL = (12, 7, 3)          # log2 of the voxel span of a node at each level
 
 class VdbError(ValueError):
     pass
+
+
+# ------------------------------------------------------------------------------------------------ Blosc-1 chunks (read only)
+def lz4_block_decode(src, out_size):
+    """One LZ4 block (lz4_Block_format.md): sequences of token (literal length << 4 | match length - 4), optional 255-run
+    length extensions, literals, 2-byte little-endian offset; the last sequence ends after its literals."""
+    src = bytes(src)
+    n = len(src)
+    dst = bytearray(out_size)
+    i = o = 0
+    while i < n:
+        tok = src[i]
+        i += 1
+        lit = tok >> 4
+        if lit == 15:
+            while True:
+                if i >= n:
+                    raise VdbError("LZ4 block: truncated literal length")
+                b = src[i]
+                i += 1
+                lit += b
+                if b != 255:
+                    break
+        if i + lit > n or o + lit > out_size:
+            raise VdbError("LZ4 block: literals run past the end of the buffer")
+        dst[o:o + lit] = src[i:i + lit]
+        i += lit
+        o += lit
+        if i >= n:
+            break
+        if i + 2 > n:
+            raise VdbError("LZ4 block: truncated match offset")
+        off = src[i] | (src[i + 1] << 8)
+        i += 2
+        ml = tok & 15
+        if ml == 15:
+            while True:
+                if i >= n:
+                    raise VdbError("LZ4 block: truncated match length")
+                b = src[i]
+                i += 1
+                ml += b
+                if b != 255:
+                    break
+        ml += 4
+        m = o - off
+        if off == 0 or m < 0 or o + ml > out_size:
+            raise VdbError("LZ4 block: bad match (offset %d, length %d at %d)" % (off, ml, o))
+        if off >= ml:
+            dst[o:o + ml] = dst[m:m + ml]
+        else:                                   # overlapping match: the last `off` bytes repeat
+            pat = bytes(dst[m:o])
+            dst[o:o + ml] = (pat * (ml // off + 1))[:ml]
+        o += ml
+    if o != out_size:
+        raise VdbError("LZ4 block: decoded %d bytes, expected %d" % (o, out_size))
+    return bytes(dst)
+
+
+_BLOSC_SHUFFLE, _BLOSC_MEMCPYED, _BLOSC_BITSHUFFLE, _BLOSC_DONT_SPLIT = 0x1, 0x2, 0x4, 0x10
+_BLOSC_MAX_SPLITS, _BLOSC_MIN_BUFFERSIZE = 16, 128
+_BLOSC_FORMATS = {0: "blosclz", 1: "lz4", 2: "snappy", 3: "zlib", 4: "zstd"}
+
+
+def blosc_decompress(buf, expect_nbytes=None):
+    """One Blosc-1 chunk -> bytes.  Header (c-blosc README_HEADER.rst): version, versionlz, flags, typesize, then uint32
+    nbytes, blocksize, cbytes; then one int32 offset per block; a block holds `typesize` byte-shuffle splits (or one), each an
+    int32 compressed size followed by that many bytes — stored raw when the size equals the split's length (blosc.c: blosc_d)."""
+    buf = bytes(buf)
+    if len(buf) < 16:
+        raise VdbError("Blosc chunk: shorter than its 16-byte header")
+    version, _versionlz, flags, typesize = buf[0], buf[1], buf[2], buf[3]
+    nbytes, blocksize, cbytes = struct.unpack_from("<III", buf, 4)
+    if version != 2:
+        raise VdbError("Blosc chunk: format version %d is not supported (expected 2)" % version)
+    if expect_nbytes is not None and nbytes != expect_nbytes:
+        raise VdbError("Blosc chunk: holds %d bytes, expected %d" % (nbytes, expect_nbytes))
+    if cbytes > len(buf):
+        raise VdbError("Blosc chunk: header says %d compressed bytes, only %d present" % (cbytes, len(buf)))
+    if nbytes == 0:
+        return b""
+    if flags & _BLOSC_MEMCPYED:
+        if 16 + nbytes > len(buf):
+            raise VdbError("Blosc chunk: truncated raw payload")
+        return buf[16:16 + nbytes]
+    if flags & _BLOSC_BITSHUFFLE:
+        raise VdbError("Blosc chunk: bit-shuffled chunks are not supported")
+    fmt = flags >> 5
+    if fmt not in (1, 3):
+        raise VdbError("Blosc chunk: compressor '%s' is not supported (LZ4 and zlib are)" % _BLOSC_FORMATS.get(fmt, fmt))
+    if blocksize == 0 or typesize == 0:
+        raise VdbError("Blosc chunk: zero block size / type size")
+    nblocks = (nbytes + blocksize - 1) // blocksize
+    if 16 + 4 * nblocks > len(buf):
+        raise VdbError("Blosc chunk: truncated block offsets")
+    bstarts = struct.unpack_from("<%di" % nblocks, buf, 16)
+    out = bytearray(nbytes)
+    for j in range(nblocks):
+        bsize, leftover = blocksize, False
+        if j == nblocks - 1 and nbytes % blocksize:
+            bsize, leftover = nbytes % blocksize, True
+        split = (not (flags & _BLOSC_DONT_SPLIT) and typesize <= _BLOSC_MAX_SPLITS and bsize // typesize >= _BLOSC_MIN_BUFFERSIZE
+                 and not leftover)
+        nsplits = typesize if split else 1
+        neblock = bsize // nsplits
+        p = bstarts[j]
+        parts = []
+        for _ in range(nsplits):
+            if p < 16 or p + 4 > len(buf):
+                raise VdbError("Blosc chunk: block offset out of range")
+            c = struct.unpack_from("<i", buf, p)[0]
+            p += 4
+            if c < 0 or p + c > len(buf):
+                raise VdbError("Blosc chunk: split of %d bytes runs past the end" % c)
+            if c == neblock:
+                parts.append(buf[p:p + c])
+            elif fmt == 1:
+                parts.append(lz4_block_decode(buf[p:p + c], neblock))
+            else:
+                d = zlib.decompress(buf[p:p + c])
+                if len(d) != neblock:
+                    raise VdbError("Blosc chunk: zlib split decoded to %d bytes, expected %d" % (len(d), neblock))
+                parts.append(d)
+            p += c
+        block = b"".join(parts)
+        if len(block) != bsize:
+            raise VdbError("Blosc chunk: block of %d bytes, expected %d" % (len(block), bsize))
+        if (flags & _BLOSC_SHUFFLE) and typesize > 1:
+            ne = bsize // typesize                      # byte j of element i sits at j * ne + i; the tail bytes are not shuffled
+            body = np.frombuffer(block, np.uint8, ne * typesize).reshape(typesize, ne).T.tobytes()
+            block = body + block[ne * typesize:]
+        out[j * blocksize:j * blocksize + bsize] = block
+    return bytes(out)
 
 
 # ------------------------------------------------------------------------------------------------ byte stream helpers
@@ -198,9 +338,11 @@ def _read_data(r, dtype, count, comps, compression):
     if compression & COMPRESS_BLOSC:
         n = r.unpack("q")
         if n <= 0:                                  # bloscToStream stores incompressible data raw, like zipToStream
+            if -n != nbytes:
+                raise VdbError("expected a %d-byte chunk, got %d" % (nbytes, -n))
             return np.frombuffer(bytes(r.raw(-n)), dtype=dtype).reshape(count, comps).copy()
-        raise VdbError("this .vdb file has Blosc-compressed buffers; re-save it with ZIP or no compression "
-                       "(no Blosc codec is available here)")
+        b = blosc_decompress(r.raw(n), nbytes)      # io/Compression.cc:285-304
+        return np.frombuffer(b, dtype=dtype).reshape(count, comps).copy()
     if compression & COMPRESS_ZIP:
         n = r.unpack("q")
         if n <= 0:
@@ -492,6 +634,7 @@ def decode_grids(data, tile_limit=1 << 24):
         if has_offsets and end_pos > 0:
             r.p = end_pos
         out.append(dict(name=uname.split("\x1e")[0], type=gtype, components=comps, background=background, metadata=meta, transform=transform,
+                        compression=_compression_name(compression),
                         coords=np.concatenate(coords) if coords else np.zeros((0, 3), np.int32),
                         values=np.concatenate(values) if values else np.zeros((0, comps), np.float32)))
     return out

@@ -133,14 +133,121 @@ def test_zip_chunk_format():
     assert w.getvalue() == struct.pack("<q", 0)
 
 
-def test_half_float_and_blosc_paths():
+def _blosc_chunk(data, typesize=4, blocksize=None, shuffle=True, fmt="lz4", dont_split=False, memcpyed=False):
+    """Test-side Blosc-1 chunk writer following c-blosc's blosc_c / blosc_compress_ctx (README_HEADER.rst): header, block
+    offsets, per block the byte shuffle, then `typesize` splits (or one), each int32 size + LZ4 / zlib stream, stored raw when
+    compression does not shrink it.  LZ4 streams come from liblz4 through pyarrow."""
+    import pyarrow as pa
+    import zlib
+    data = bytes(data)
+    nbytes = len(data)
+    blocksize = nbytes if not blocksize else min(blocksize, nbytes)
+    if blocksize > typesize:
+        blocksize = blocksize // typesize * typesize          # blosc.c compute_blocksize: a multiple of the type size
+    flags = (1 if shuffle else 0) | (0x10 if dont_split else 0) | ({"lz4": 1, "zlib": 3}[fmt] << 5)
+    if memcpyed:
+        flags |= 0x2
+        return struct.pack("<BBBBIII", 2, 1, flags, typesize, nbytes, blocksize, 16 + nbytes) + data
+    nblocks = (nbytes + blocksize - 1) // blocksize
+    body, bstarts = b"", []
+    for j in range(nblocks):
+        blk = data[j * blocksize:(j + 1) * blocksize]
+        leftover = len(blk) < blocksize
+        if shuffle and typesize > 1:
+            ne = len(blk) // typesize
+            blk = np.frombuffer(blk, np.uint8, ne * typesize).reshape(ne, typesize).T.tobytes() + blk[ne * typesize:]
+        split = not dont_split and typesize <= 16 and len(blk) // typesize >= 128 and not leftover
+        nsplits = typesize if split else 1
+        ne = len(blk) // nsplits
+        bstarts.append(16 + 4 * nblocks + len(body))
+        for k in range(nsplits):
+            part = blk[k * ne:(k + 1) * ne]
+            z = pa.Codec("lz4_raw").compress(part, asbytes=True) if fmt == "lz4" else zlib.compress(part)
+            if len(z) >= len(part):
+                z = part
+            body += struct.pack("<i", len(z)) + z
+    head = struct.pack("<BBBBIII", 2, 1, flags, typesize, nbytes, blocksize, 16 + 4 * nblocks + len(body))
+    return head + struct.pack("<%di" % nblocks, *bstarts) + body
+
+
+def test_lz4_blocks_from_liblz4_decode():
+    """The LZ4 block decoder against streams produced by the real liblz4 (through pyarrow's lz4_raw codec)."""
+    import pyarrow as pa
+    rng = np.random.default_rng(0)
+    cases = [b"a", b"abcabcabcabc" * 50 + bytes(range(256)), bytes(1000), rng.integers(0, 4, 5000, dtype=np.uint8).tobytes(),
+             rng.bytes(3000), np.arange(2048, dtype=np.float32).tobytes(), b"x" * 70000,
+             np.repeat(rng.standard_normal(64).astype(np.float32), 8).tobytes()]
+    for data in cases:
+        z = pa.Codec("lz4_raw").compress(data, asbytes=True)
+        assert vio.lz4_block_decode(z, len(data)) == data
+        with pytest.raises(vio.VdbError):
+            vio.lz4_block_decode(z, len(data) + 1)
+        if len(z) > 4:
+            with pytest.raises(vio.VdbError):
+                vio.lz4_block_decode(z[:-3], len(data))
+
+
+def test_blosc_chunks_decode():
+    """Blosc-1 chunks as OpenVDB writes them (byte shuffle, typesize 4, LZ4, one block = the whole buffer: io/Compression.cc:172-187)
+    and the variants a different Blosc build may produce: unsplit blocks, several blocks with a leftover, zlib, raw copies."""
+    rng = np.random.default_rng(1)
+    leaf = np.where(rng.random(512) < 0.3, rng.standard_normal(512), 0).astype(np.float32).tobytes()      # one leaf buffer
+    vec = np.repeat(rng.standard_normal((40, 3)).astype(np.float32), 5, 0).tobytes()                       # Vec3f values
+    small = rng.standard_normal(20).astype(np.float32).tobytes()                                           # too small to split
+    for data in (leaf, vec, small, rng.bytes(2048), bytes(4096)):
+        for kw in (dict(), dict(dont_split=True), dict(shuffle=False), dict(fmt="zlib"), dict(blocksize=1024), dict(blocksize=1000, typesize=4),
+                   dict(typesize=12), dict(memcpyed=True), dict(typesize=1)):
+            chunk = _blosc_chunk(data, **kw)
+            assert vio.blosc_decompress(chunk, len(data)) == data, kw
+            assert vio.blosc_decompress(chunk + b"junk", len(data)) == data           # cbytes, not the buffer length, delimits it
+    with pytest.raises(vio.VdbError, match="expected"):
+        vio.blosc_decompress(_blosc_chunk(leaf), len(leaf) + 4)
+    with pytest.raises(vio.VdbError):
+        vio.blosc_decompress(_blosc_chunk(leaf)[:40], len(leaf))
+    bad = bytearray(_blosc_chunk(leaf))
+    bad[2] = (bad[2] & 0x1f) | (0 << 5)                                                # BloscLZ stream: not supported, said clearly
+    with pytest.raises(vio.VdbError, match="blosclz"):
+        vio.blosc_decompress(bytes(bad), len(leaf))
+
+
+def test_blosc_compressed_file_reads_back(monkeypatch):
+    """A whole .vdb whose buffers are Blosc chunks (the default of OpenVDB builds with Blosc, COMPRESS_BLOSC | ACTIVE_MASK)
+    decodes to the same voxels as the ZIP file of the same grids."""
+    from plenvdb_b200.tree import Topology
+    rng = np.random.default_rng(2)
+    active = rng.random((20, 17, 12)) < 0.2
+    topo = Topology.from_mask(active, device="cpu")
+    den = (rng.standard_normal((topo.n_leaf, 512, 1)) * 3).astype(np.float32)
+    col = rng.standard_normal((topo.n_leaf, 512, 3)).astype(np.float32)
+    planes = [("density", den), ("color0", col)]
+
+    def write_blosc(w, arr, compression):
+        b = np.ascontiguousarray(arr).tobytes()
+        chunk = _blosc_chunk(b) if len(b) >= 128 else b""       # blosc_compress refuses tiny buffers: stored raw (bloscToStream)
+        if chunk and len(chunk) < len(b) + 16:
+            w.pack("q", len(chunk))
+            w.raw(chunk)
+        else:
+            w.pack("q", -len(b))
+            w.raw(b)
+    want = vio.decode_grids(vio.encode_grids(topo, planes))
+    monkeypatch.setattr(vio, "_write_data", write_blosc)
+    data = vio.encode_grids(topo, planes, compression=vio.COMPRESS_BLOSC | vio.COMPRESS_ACTIVE_MASK)
+    monkeypatch.undo()
+    got = vio.decode_grids(data)
+    assert [g["name"] for g in got] == ["density", "color0"] and "blosc" in got[0]["compression"]
+    for a, b in zip(got, want):
+        assert np.array_equal(a["coords"], b["coords"]) and np.array_equal(a["values"], b["values"])
+
+
+def test_half_float_paths_and_bad_magic():
     vmask = np.ones(8, bool)
     vals = np.arange(8, dtype=np.float16).reshape(8, 1)
     r = vio._Reader(bytes([vio.NO_MASK_AND_ALL_VALS]) + vals.tobytes())
     out = vio._read_values(r, 8, 1, vmask, np.zeros(1, np.float32), vio.COMPRESS_NONE, True, 224)
     assert out.dtype == np.float32 and np.array_equal(out[:, 0], np.arange(8, dtype=np.float32))
     r = vio._Reader(bytes([vio.NO_MASK_AND_ALL_VALS]) + struct.pack("<q", 100) + b"\0" * 100)
-    with pytest.raises(vio.VdbError, match="Blosc"):
+    with pytest.raises(vio.VdbError, match="Blosc"):                                   # 100 zero bytes are not a Blosc chunk
         vio._read_values(r, 8, 1, vmask, np.zeros(1, np.float32), vio.COMPRESS_BLOSC, False, 224)
     with pytest.raises(vio.VdbError, match="not a VDB"):
         vio.decode_grids(b"\0" * 64)
