@@ -172,7 +172,7 @@ def _blosc_chunk(data, typesize=4, blocksize=None, shuffle=True, fmt="lz4", dont
 
 def test_lz4_blocks_from_liblz4_decode():
     """The LZ4 block decoder against streams produced by the real liblz4 (through pyarrow's lz4_raw codec)."""
-    import pyarrow as pa
+    pa = pytest.importorskip("pyarrow")
     rng = np.random.default_rng(0)
     cases = [b"a", b"abcabcabcabc" * 50 + bytes(range(256)), bytes(1000), rng.integers(0, 4, 5000, dtype=np.uint8).tobytes(),
              rng.bytes(3000), np.arange(2048, dtype=np.float32).tobytes(), b"x" * 70000,
@@ -190,6 +190,7 @@ def test_lz4_blocks_from_liblz4_decode():
 def test_blosc_chunks_decode():
     """Blosc-1 chunks as OpenVDB writes them (byte shuffle, typesize 4, LZ4, one block = the whole buffer: io/Compression.cc:172-187)
     and the variants a different Blosc build may produce: unsplit blocks, several blocks with a leftover, zlib, raw copies."""
+    pytest.importorskip("pyarrow")
     rng = np.random.default_rng(1)
     leaf = np.where(rng.random(512) < 0.3, rng.standard_normal(512), 0).astype(np.float32).tobytes()      # one leaf buffer
     vec = np.repeat(rng.standard_normal((40, 3)).astype(np.float32), 5, 0).tobytes()                       # Vec3f values
@@ -213,6 +214,7 @@ def test_blosc_chunks_decode():
 def test_blosc_compressed_file_reads_back(monkeypatch):
     """A whole .vdb whose buffers are Blosc chunks (the default of OpenVDB builds with Blosc, COMPRESS_BLOSC | ACTIVE_MASK)
     decodes to the same voxels as the ZIP file of the same grids."""
+    pytest.importorskip("pyarrow")
     from plenvdb_b200.tree import Topology
     rng = np.random.default_rng(2)
     active = rng.random((20, 17, 12)) < 0.2
