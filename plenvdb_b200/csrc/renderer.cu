@@ -4,11 +4,18 @@
 //   P1 k_render_pass1     thread per pixel (8x4 pixel tile per warp): ray from (pixel, K, c2w), unit-box t range,
 //                         fixed-step march with the reference's `t += steplen` recurrence, active test on the index
 //                         grid, density trilinear through the index -> data indirection, alpha, thresholds;
-//                         counts kept samples and tightens [tmin, tmax]                       (renderer.cu:222-268)
+//                         counts kept samples and tightens [tmin, tmax]                       (renderer.cu:222-268).
+//                         Runs of steps that cannot touch a leaf are skipped (only their t chain is evaluated), and the
+//                         reference's second march is simulated on the same corner values so that the pixel's samples
+//                         can be handed over instead of marched again — both bit-identical, see the comments below
 //   SC k_scan_*           exclusive scan of the per-pixel counts in pixel order -> i_starts    (renderer.cu:401-402)
-//   P2 k_render_pass2     second march from the tightened range, gathers the 12 colour features (renderer.cu:312-367)
+//   EM k_render_emit      the (t, weight) slots of the pixels handed over -> their segments of the sample list
+//   P2 k_render_pass2     the reference's second march (renderer.cu:312-367) for the pixels that were not handed over
+//   GA k_render_gather    thread per sample: the 12 colour features (trigetColor, renderer.cu:303-310)
 //   ML k_render_mlp       64-sample tiles: view PE + MLP(39->128->128->3), weight*sigmoid       (renderer.cu:83-119)
-//   CO k_render_composite per-pixel ordered sum (deterministic; the reference uses float atomics)
+//                         (tcgen05 version: rgbnet_tc.cu)
+//   CO k_render_composite per-pixel ordered sum (deterministic; the reference uses float atomics); optionally stores the
+//                         pixel into a full frame that may live on another GPU (tile-sharded rendering, k_frame_*)
 //
 // Differences from the reference by design: no per-frame cudaMalloc/cudaFree or host sync, no race on rays_o
 // (renderer.cu:128-132), pass 2 cannot overrun its segment (such rays are counted), the
