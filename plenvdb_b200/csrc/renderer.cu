@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float
 // Hand-over of pass 1's samples: the pixel's (t, weight) slot becomes its segment of the sample list — position as step_active
 // computes it, in the first three floats of the feature row; the pixels pass 1 could not hand over go to the fallback list,
 // which pass 2 marches like the reference does.  A warp takes 32 listed pixels: every lane sets up one pixel's ray, then the
-// warp walks the 32 pixels together, lane r copying sample r (and r + 32) — coalesced slot reads and list writes instead of
-// one thread looping over its pixel's samples (38 us -> see profiles/).
+// warp walks the 32 pixels together, lane r copying sample r (and r + 32): coalesced slot reads and list writes instead of
+// one thread looping over its pixel's samples.
 __global__ void __launch_bounds__(256) k_render_emit(RenderConst C, const float* __restrict__ c2w, int row_begin,
                                                      const int32_t* __restrict__ n_samples, const int32_t* __restrict__ i_starts,
                                                      const int32_t* __restrict__ active_list, const float2* __restrict__ px_scratch, int P,
