@@ -28,6 +28,29 @@ def mask_scale_shift(mask_shape, xyz_min, xyz_max):
     return scale.astype(np.float32), shift.astype(np.float32)
 
 
+def get_rays_of_a_view(H, W, K, c2w, inverse_y=False, flip_x=False, flip_y=False, device=None):
+    """dvgo.get_rays_of_a_view (dvgo.py:470-499, 518-526) with mode 'center', no NDC: rays_o, rays_d, viewdirs as float32
+    [H, W, 3] torch tensors on `device`.  Same torch expressions as the reference, so the rays carry the same bits."""
+    c2w = torch.as_tensor(np.asarray(c2w.cpu() if torch.is_tensor(c2w) else c2w, np.float32)).reshape(-1)[:16].reshape(4, 4)
+    K = np.asarray(K.cpu() if torch.is_tensor(K) else K, np.float32).reshape(3, 3)
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    c2w = c2w.to(dev)
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev), indexing="ij")
+    i, j = i.t().float() + 0.5, j.t().float() + 0.5
+    if flip_x:
+        i = i.flip((1,))
+    if flip_y:
+        j = j.flip((0,))
+    if inverse_y:
+        dirs = torch.stack([(i - K[0][2]) / K[0][0], (j - K[1][2]) / K[1][1], torch.ones_like(i)], -1)
+    else:
+        dirs = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, 3].expand(rays_d.shape)
+    viewdirs = rays_d / rays_d.norm(dim=-1, keepdim=True)
+    return rays_o.contiguous(), rays_d.contiguous(), viewdirs.contiguous()
+
+
 class FusedTrainer:
     def __init__(self, params, density, k0, mask, net, n_rays, device="cuda", use_tensor_cores=True,
                  cap_alpha_per_ray=96, cap_keep_per_ray=64, parity_counts=False, n_rays_global=None,
@@ -258,6 +281,17 @@ class FusedTrainer:
         """Render rays through the training model (run.py:171-189); returns rgb_marched [n,3]."""
         self.run(rays_o, rays_d, viewdirs, None, PHASE_FORWARD)
         return self.t["rgb_marched"][: rays_o.shape[0]]
+
+    def render_view(self, H, W, K, c2w, inverse_y=False, flip_x=False, flip_y=False):
+        """The non-merged render path of run.py:171-189: the rays of one view through the TRAINING grids and rgbnet (forward
+        phase of the fused step), in chunks of this trainer's batch size; returns rgb_marched as a [H, W, 3] CUDA tensor."""
+        ro, rd, vd = get_rays_of_a_view(H, W, K, c2w, inverse_y, flip_x, flip_y, device=self.dev)
+        ro, rd, vd = ro.reshape(-1, 3), rd.reshape(-1, 3), vd.reshape(-1, 3)
+        out = torch.empty((H * W, 3), dtype=torch.float32, device=self.dev)
+        for a in range(0, H * W, self.n_rays):
+            b = min(a + self.n_rays, H * W)
+            out[a:b] = self.forward(ro[a:b].contiguous(), rd[a:b].contiguous(), vd[a:b].contiguous())
+        return out.reshape(H, W, 3)
 
     def hit_mask(self, rays_o, rays_d):
         """hit_coarse_geo (dvgo.py:253-270): bool [n] — does the ray touch the occupancy mask?"""

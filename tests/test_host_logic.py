@@ -124,3 +124,26 @@ def test_interleaved_row_groups_partition_exactly():
         assert sorted(seen) == list(range(H))
     assert _lib.lib.pvdb_interleaved_rows(0, 4, 0, 2) == 0 and _lib.lib.pvdb_interleaved_rows(8, 0, 0, 2) == 0
     assert _lib.lib.pvdb_frame_symm_bytes(800, 800) == 1024 + 2 * 800 * 800 * 3 * 4
+
+
+def test_rays_of_a_view_match_the_pixel_formula():
+    """fused.get_rays_of_a_view (the torch expressions of dvgo.py:470-499) against the per-pixel numpy formula the ray batches
+    of every other test come from, for both y conventions; flips mirror the image."""
+    import torch
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import get_rays_of_a_view
+    H, W = 37, 52
+    K = synth.intrinsics(H, W)
+    c2w = synth.render_cameras(8)[3]
+    py, px = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    for inverse_y in (False, True):
+        ro, rd, vd = get_rays_of_a_view(H, W, K, c2w, inverse_y=inverse_y)
+        wo, wd, wv = synth.rays_of_pixels(K, c2w, px.reshape(-1), py.reshape(-1), inverse_y)
+        assert ro.shape == (H, W, 3) and ro.dtype == torch.float32
+        assert np.array_equal(ro.reshape(-1, 3).numpy(), wo)
+        np.testing.assert_allclose(rd.reshape(-1, 3).numpy(), wd, rtol=2e-7, atol=1e-7)      # same formula, torch.sum vs numpy sum order
+        np.testing.assert_allclose(vd.reshape(-1, 3).numpy(), wv, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(np.linalg.norm(vd.numpy(), axis=-1), 1.0, rtol=1e-6)
+    a = get_rays_of_a_view(H, W, K, c2w)[1]
+    assert torch.equal(get_rays_of_a_view(H, W, K, c2w, flip_x=True)[1], a.flip((1,)))
+    assert torch.equal(get_rays_of_a_view(H, W, K, c2w, flip_y=True)[1], a.flip((0,)))
