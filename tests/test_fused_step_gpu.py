@@ -302,3 +302,20 @@ def test_host_pipeline_matches_synchronous_steps(small):
     np.testing.assert_allclose(tr_b.net.cpu().numpy(), tr_a.net.cpu().numpy(), rtol=1e-3, atol=2e-5)
     np.testing.assert_allclose(den_b.grid.cpu().numpy(), den_a.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
     np.testing.assert_allclose(k0_b.grid.cpu().numpy(), k0_a.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
+
+
+def test_render_view_equals_the_forward_phase_on_the_same_rays():
+    """The non-merged render path (run.py:171-189): FusedTrainer.render_view = get_rays_of_a_view + the forward phase in
+    batch-sized chunks, bit for bit."""
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import get_rays_of_a_view
+    scene = synth.make_scene(64, "dense")
+    tr, den, k0 = _trainer(scene, synth.rgbnet_init(), 2048)
+    H, W = 60, 70
+    K, c2w = synth.intrinsics(H, W), synth.render_cameras(8)[2]
+    img = tr.render_view(H, W, K, c2w)
+    ro, rd, vd = [t.reshape(-1, 3) for t in get_rays_of_a_view(H, W, K, c2w, device="cuda")]
+    ref = torch.cat([tr.forward(ro[a:a + 2048].contiguous(), rd[a:a + 2048].contiguous(), vd[a:a + 2048].contiguous()).clone()
+                     for a in range(0, H * W, 2048)])
+    assert img.shape == (H, W, 3) and torch.equal(img.reshape(-1, 3), ref)
+    assert float((img != scene["bg"]).float().mean()) > 0.03, "degenerate view"
