@@ -263,7 +263,7 @@ def open_symmetric_blocks(nbytes, group=None):
     dist.all_gather_object(oks, err, group=group)   # also the barrier: every block is zeroed and mapped before the first signal
     bad = [(r, e) for r, e in enumerate(oks) if e is not None]
     if bad:
-        close_symmetric_blocks(own, opened)
+        close_symmetric_blocks(own, opened, group, barrier=True)     # every rank is here: unmap everywhere, then free
         raise PeerExchangeUnavailable("NVLink peer memory unavailable (rank %d: %s)" % bad[0])
     return own, bases, opened
 
@@ -275,7 +275,8 @@ def close_symmetric_blocks(own, opened, group=None, barrier=False):
     for p in opened:
         _lib.call("pvdb_dp_symm_close", p)
     if barrier and dist.is_initialized():
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
         dist.barrier(group=group)
     if own is not None:
         _lib.call("pvdb_dp_symm_free", own)
