@@ -34,7 +34,7 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def build_workload(n_batches, device, seed=777, pool_candidates=1 << 21, n_rays=N_RAYS, use_tc=True):
+def build_workload(n_batches, device, seed=777, pool_candidates=1 << 21, n_rays=N_RAYS, use_tc=True, **trainer_kw):
     """Scene + grids + trainer + `n_batches` device-resident ray batches drawn like the fine stage does
     (ray_sampler='in_maskcache', configs/default.py:73; dvgo.py:583-625 keeps the rays that hit the mask)."""
     import torch
@@ -43,7 +43,7 @@ def build_workload(n_batches, device, seed=777, pool_candidates=1 << 21, n_rays=
     scene = synth.make_scene(RESO, "sparse")
     net = synth.rgbnet_init()
     den, k0 = build_scene_grids(scene, device=device)
-    tr = FusedTrainer(scene, den, k0, scene["mask"], net, n_rays, device=device, use_tensor_cores=use_tc)
+    tr = FusedTrainer(scene, den, k0, scene["mask"], net, n_rays, device=device, use_tensor_cores=use_tc, **trainer_kw)
     poses, K = synth.train_cameras(100), synth.intrinsics(800, 800)
     rng = np.random.default_rng(seed)
     need = n_batches * n_rays
@@ -488,7 +488,7 @@ def run_reference(args):
     net = synth.rgbnet_init()
     # in_maskcache rays found with the oracle's own sampler + mask lookup on a candidate pool
     from oracle import oracle as orc
-    from plenvdb_b200.fused import mask_scale_shift
+    from plenvdb_b200.synth import mask_scale_shift
     poses, K = synth.train_cameras(100), synth.intrinsics(800, 800)
     n_sub = args.cpu_rays
     rng = np.random.default_rng(777)

@@ -79,6 +79,17 @@ class Grid:
     def fill(self, v):
         lib.orc_grid_fill(self.h, C.c_float(v))
 
+    def set_values(self, plane):
+        """Leaf-major payload [n_leaf, 512, channels] (the caller has checked the leaf order against leaf_origins())."""
+        p = _f32(plane)
+        assert p.size == self.n_leaf * 512 * self.channels
+        lib.orc_grid_set_values(self.h, _p(p))
+
+    def get_values(self):
+        out = np.zeros((self.n_leaf, 512, self.channels), np.float32)
+        lib.orc_grid_get_values(self.h, _p(out))
+        return out
+
     def forward(self, x, y, z, corners=False, threads=1):
         x, y, z = _f32(x), _f32(y), _f32(z)
         n = x.size

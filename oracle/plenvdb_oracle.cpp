@@ -107,6 +107,10 @@ extern "C" int orc_grid_leaf_count(const orc_grid* g) { return g->n_leaf(); }
 extern "C" void orc_grid_leaf_origins(const orc_grid* g, int32_t* out) { std::memcpy(out, g->origin.data(), g->origin.size() * 4); }
 extern "C" void orc_grid_leaf_masks(const orc_grid* g, uint64_t* out) { std::memcpy(out, g->mask.data(), g->mask.size() * 8); }
 extern "C" void orc_grid_fill(orc_grid* g, float v) { std::fill(g->values.begin(), g->values.end(), v); }
+// Leaf-major payload [n_leaf][512][C] in and out (test helper for grids too large for a dense host array: the caller
+// checks orc_grid_leaf_origins against its own leaf order first).
+extern "C" void orc_grid_set_values(orc_grid* g, const float* plane) { std::memcpy(g->values.data(), plane, g->values.size() * 4); }
+extern "C" void orc_grid_get_values(const orc_grid* g, float* plane) { std::memcpy(plane, g->values.data(), g->values.size() * 4); }
 
 // densityvdb.cu:31-49 / colorvdb.cu:42-63 — every ACTIVE voxel slot takes the dense value at its coordinate
 extern "C" void orc_grid_copy_from_dense(orc_grid* g, const float* dense) {

@@ -35,6 +35,9 @@ void orc_grid_copy_from_dense(orc_grid*, const float* dense);   /* active voxels
 void orc_grid_copy_to_dense(const orc_grid*, float* dense);     /* stored values where a leaf exists, else 0 */
 void orc_grid_set_on_by_mask(orc_grid*, const uint8_t* mask, float val);   /* densityvdb.cu:64-84 */
 void orc_grid_fill(orc_grid*, float v);                          /* every slot of every leaf (test helper) */
+/* leaf-major payload [n_leaf][512][channels] in / out, for grids too large for a dense host array (test helper) */
+void orc_grid_set_values(orc_grid*, const float* plane);
+void orc_grid_get_values(const orc_grid*, float* plane);
 
 /* D1/C1, D2/C2 (densityvdb.cu:101-167, colorvdb.cu:81-160).  corner_* optional [n][8]. */
 void orc_sample_forward(const orc_grid*, const float* xs, const float* ys, const float* zs, int64_t n, float* out,

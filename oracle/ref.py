@@ -95,6 +95,10 @@ class RefGrid:
     def gpu_copy_from_dense(self, dense):
         self.lib.ref_gpu_copy_from_dense(self.h, _p(_f32(dense)))
 
+    def gpu_copy_from_dense_dev(self, dense_cuda_tensor):
+        """dense_cuda_tensor: contiguous float32 CUDA tensor [rx, ry, rz(, channels)] on the current device."""
+        self.lib.ref_gpu_copy_from_dense_dev(self.h, C.c_void_p(dense_cuda_tensor.data_ptr()))
+
     def gpu_set_on_by_mask(self, mask, val):
         m = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
         self.lib.ref_gpu_set_on_by_mask(self.h, _p(m), C.c_float(val))

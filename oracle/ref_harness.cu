@@ -351,6 +351,12 @@ extern "C" void ref_gpu_copy_from_dense(ref_grid* g, const float* dense) {   // 
     else color_copyFromDense(g->dev_arr, d, g->rx, g->ry, g->rz, g->nleafCount, g->num);
     cudaFree(d);
 }
+// the same with the dense array already on the device (512^3 x 12 channels is 6.4 GB: built there by the caller)
+extern "C" void ref_gpu_copy_from_dense_dev(ref_grid* g, float* d_dense) {
+    if (g->num == 0) density_copyFromDense((NanoFloatGridT*)g->dev[0], d_dense, g->rx, g->ry, g->rz, g->nleafCount);
+    else color_copyFromDense(g->dev_arr, d_dense, g->rx, g->ry, g->rz, g->nleafCount, g->num);
+    cudaDeviceSynchronize();
+}
 extern "C" void ref_gpu_set_on_by_mask(ref_grid* g, const uint8_t* mask, float val) {   // plenvdb.h:487-495
     const size_t n = (size_t)g->rx * g->ry * g->rz;
     bool* d = to_dev(reinterpret_cast<const bool*>(mask), n);

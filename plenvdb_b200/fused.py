@@ -13,19 +13,11 @@ import torch
 
 from . import _lib
 from .plenvdb import ColorVDB, DensityVDB
+from .synth import mask_scale_shift  # noqa: F401  (numpy-only helper; re-exported for callers of this module)
 from .tree import Topology
 
 PHASE_FORWARD, PHASE_BACKWARD, PHASE_UPDATE, PHASE_LISTS_READY = 1, 2, 4, 8
 NET_N = 22019
-
-
-def mask_scale_shift(mask_shape, xyz_min, xyz_max):
-    """MaskGrid buffers (plenvdb/lib/grid.py:229-231) in float32, like torch computes them."""
-    xyz_min = np.asarray(xyz_min, np.float32)
-    xyz_max = np.asarray(xyz_max, np.float32)
-    scale = (np.asarray(mask_shape, np.float32) - np.float32(1)) / (xyz_max - xyz_min)
-    shift = -xyz_min * scale
-    return scale.astype(np.float32), shift.astype(np.float32)
 
 
 def get_rays_of_a_view(H, W, K, c2w, inverse_y=False, flip_x=False, flip_y=False, device=None):
@@ -323,8 +315,9 @@ def build_scene_grids(scene, device="cuda"):
     return den, k0
 
 
-def build_stress_scene(reso=512, device="cuda", bound=1.3, seed=6):
-    """SURVEY.md §8(d) cfg 5 (S512): noisy thick shell (~5 % of the voxels) on a PRUNED topology, built on the device — the
+def build_stress_scene(reso=512, device="cuda", bound=1.3, seed=6, half_thickness=0.055):
+    """SURVEY.md §8(d) cfg 5 (S512): noisy thick shell (half_thickness 0.055 -> ~5 % of the voxels, ~10 % of the 262 144 leaf
+    blocks at 512^3, as the survey specifies) on a PRUNED topology, built on the device — the
     dense host arrays synth.make_scene works with would be 6.4 GB at 512^3.  Same formulas as synth.shell_occupancy /
     make_scene (occupancy, N(6,1) density inside / -10 outside, U(-1,1) k0 on the dilated occupancy, mask = 3^3 max-pool),
     torch RNG instead of numpy's.  Returns (params, density grid, k0 grid, mask [reso^3] uint8 cuda)."""
@@ -340,7 +333,7 @@ def build_stress_scene(reso=512, device="cuda", bound=1.3, seed=6):
     for k in range(4):
         f = (2 ** k) * 3.0
         noise += 0.5 ** k * torch.sin(f * X + ph[k, 0]) * torch.sin(f * Y + ph[k, 1]) * torch.sin(f * Z + ph[k, 2])
-    occ = (r - 0.8 - 0.06 * noise).abs() <= 0.022
+    occ = (r - 0.8 - 0.06 * noise).abs() <= half_thickness
     del noise, r
     mask = torch.nn.functional.max_pool3d(occ[None, None].to(torch.float16), 3, 1, 1)[0, 0] > 0
     g = torch.Generator(device=dev)

@@ -10,10 +10,34 @@ from . import _lib
 from ._lib import call, current_stream, ptr
 
 
+_FLOAT_OK = (torch.float32,)
+_OTHER_OK = (torch.int64, torch.bool, torch.uint8)
+
+
 def _check(*ts):
+    """CHECK_INPUT (render_utils.cpp:46-48) plus the dtype contract: the reference dispatches on float / double
+    (AT_DISPATCH_FLOATING_TYPES); these kernels are float32 only (ids int64, masks bool), so anything else is refused
+    instead of being reinterpreted."""
     for t in ts:
         if not (t.is_cuda and t.is_contiguous()):
-            raise RuntimeError("expected a contiguous CUDA tensor")   # CHECK_INPUT, render_utils.cpp:46-48
+            raise RuntimeError("expected a contiguous CUDA tensor")
+        if t.dtype not in _FLOAT_OK and t.dtype not in _OTHER_OK:
+            raise RuntimeError("render_utils_cuda (B200): float32 tensors only (got %s); the reference's float64 dispatch is not built" % t.dtype)
+
+
+def _out_of_scope(name, users):
+    def fn(*a, **k):
+        raise NotImplementedError("render_utils_cuda.%s serves %s only, which is outside the ported hot path (SURVEY.md 8b, B2)" % (name, users))
+    fn.__name__ = name
+    return fn
+
+
+# the four ops of the extension that only the unbounded / MPI / non-uniform model variants call (dmpigo.py:240, dbvgo.py:235,243,
+# dvgo.py's raw2alpha_nonuni): present so that attribute lookups succeed, loud when called
+sample_ndc_pts_on_rays = _out_of_scope("sample_ndc_pts_on_rays", "DirectMPIGO (dmpigo.py)")
+sample_bg_pts_on_rays = _out_of_scope("sample_bg_pts_on_rays", "DirectBiVoxGO (dbvgo.py)")
+raw2alpha_nonuni = _out_of_scope("raw2alpha_nonuni", "the non-uniform step models (dbvgo.py / dcvgo.py)")
+raw2alpha_nonuni_backward = _out_of_scope("raw2alpha_nonuni_backward", "the non-uniform step models (dbvgo.py / dcvgo.py)")
 
 
 def infer_t_minmax(rays_o, rays_d, xyz_min, xyz_max, near, far):
@@ -91,7 +115,8 @@ def raw2alpha_backward(exp_d, grad_back, interval):
 
 def alpha2weight(alpha, ray_id, n_rays):
     _check(alpha, ray_id)
-    assert ray_id.dtype == torch.int64
+    if ray_id.dtype != torch.int64 or alpha.dtype != torch.float32:
+        raise RuntimeError("alpha2weight: alpha float32 and ray_id int64 expected")
     n_pts = alpha.shape[0]
     dev = alpha.device
     weight = torch.zeros_like(alpha)

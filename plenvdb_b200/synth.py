@@ -100,6 +100,15 @@ def make_scene(reso=160, variant="dense", seed_density=1, seed_k0=2, seed_leaf=3
     return P
 
 
+def mask_scale_shift(mask_shape, xyz_min, xyz_max):
+    """MaskGrid buffers (plenvdb/lib/grid.py:229-231) in float32, like torch computes them."""
+    xyz_min = np.asarray(xyz_min, F32)
+    xyz_max = np.asarray(xyz_max, F32)
+    scale = (np.asarray(mask_shape, F32) - F32(1)) / (xyz_max - xyz_min)
+    shift = -xyz_min * scale
+    return scale.astype(F32), shift.astype(F32)
+
+
 # ---- cameras and rays
 def pose_spherical(theta, phi, radius):
     """load_blender.py:29-34 (float32 matrices like torch.Tensor)."""

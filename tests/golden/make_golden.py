@@ -69,7 +69,7 @@ def render_utils(out):
         res[n] = t.cpu().numpy()
     rng = np.random.default_rng(101)
     world = rng.random((20, 24, 17)) < 0.3
-    from plenvdb_b200.fused import mask_scale_shift
+    from plenvdb_b200.synth import mask_scale_shift
     sc, sh = mask_scale_shift(world.shape, P["xyz_min"], P["xyz_max"])
     xyz = (rng.random((3000, 3)) * 3.0 - 1.5).astype(np.float32)
     res.update(world=world, mxyz=xyz, mscale=sc, mshift=sh,

@@ -74,7 +74,7 @@ def test_shard_ranges_partition_exactly():
 
 def test_mask_scale_shift_matches_torch():
     import torch
-    from plenvdb_b200.fused import mask_scale_shift
+    from plenvdb_b200.synth import mask_scale_shift
     mn, mx = torch.tensor([-1.3, -1.0, -0.7]), torch.tensor([1.3, 1.1, 0.9])
     shape = torch.tensor([160.0, 33.0, 75.0])
     scale = (shape - 1) / (mx - mn)          # grid.py:229-231

@@ -66,7 +66,7 @@ def test_sample_pts_on_rays_bit_exact_vs_reference_ext():
 def test_maskcache_lookup():
     from oracle import oracle as orc
     from plenvdb_b200 import render_utils_cuda as ru
-    from plenvdb_b200.fused import mask_scale_shift
+    from plenvdb_b200.synth import mask_scale_shift
     rng = np.random.default_rng(3)
     shape = (33, 40, 17)
     world = rng.random(shape) < 0.3

@@ -1,0 +1,323 @@
+"""Parity AT THE BASELINE CONFIGURATIONS (BASELINE.json configs[1], [2], [4]), not at reduced sizes:
+
+  F160  the timed workload of bench.py itself — random-sparse 160^3 scene, 8192 `in_maskcache` rays — one whole fused
+        iteration against the CPU oracle (dvgo.py:296-388, run.py:541-588; render_utils_kernel.cu:196-242, 577-651)
+  R800  full 800x800 merged-VDB frames of the dense-fill F160 scene for three of the 200 orbit poses against the
+        reference's own render_an_image_cuda (renderer.cu:370-424) compiled for sm_100a
+  S512  the 512^3 stress scene at the survey's occupancy (~5 % of the voxels): trilinear forward against the reference's
+        own density_forward / color_forward kernels, and a fused step on a 4096-ray sub-batch against the oracle
+
+Integers (step / sample counts, segment offsets, ray / step ids, leaf / voxel ids of the eight corners) must be equal bit
+for bit; values within 1e-5 relative.
+
+Gradient planes and parameters: a voxel's gradient is a float32 sum of up to thousands of signed contributions, accumulated
+with `red.global.add.f32` here and with `atomicAdd` in the reference — an unordered sum on BOTH sides (the reference does not
+reproduce itself bit for bit either).  The error of such a sum is bounded relative to the sum of the
+|contributions|, not relative to the (possibly cancelling) result.  `_check_sum` therefore accepts an element when
+    |got - want| <= 1e-5 * |want|   or   |got - want| <= 1e-5 * A,
+where A is the local magnitude scale of the plane: for density the exact sum of |contributions| of that voxel (scattered
+with the oracle from |dL/d density|), for k0 / rgbnet the largest |gradient| of the tensor row the element belongs to (the
+12 channels of the voxel's leaf / the weight matrix).  The test prints how many elements needed the second clause.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+THREADS = os.cpu_count() or 1
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _oracle_cfg(P, step=1, do_update=1, n_rays_global=0):
+    keys = ["xyz_min", "xyz_max", "reso", "near", "far", "stepdist", "act_shift", "interval", "fast_color_thres", "bg",
+            "weight_main", "weight_entropy_last", "weight_rgbper", "lr_density", "lr_k0", "lr_net", "eps", "beta0", "beta1",
+            "den_mode", "k0_mode"]
+    c = {k: P[k] for k in keys}
+    c.update(step=step, do_update=do_update, n_rays_global=n_rays_global, threads=THREADS)
+    return c
+
+
+def _check_sum(got, want, scale, name, rtol=RTOL):
+    """Element-wise check of an unordered float32 sum (see the module docstring).  scale: array broadcastable to want."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    err = np.abs(got - want)
+    rel_ok = err <= rtol * np.abs(want)
+    abs_ok = err <= rtol * np.broadcast_to(scale, want.shape)
+    bad = ~(rel_ok | abs_ok)
+    nz = want != 0
+    print("[parity] %-18s n=%d nonzero=%d  max|err|/max|want|=%.2e  beyond 1e-5 relative: %d (%.3f %% of nonzero), "
+          "of which beyond the magnitude clause: %d" % (name, want.size, int(nz.sum()), err.max() / max(np.abs(want).max(), 1e-30),
+                                                        int((~rel_ok).sum()), 100.0 * (~rel_ok).sum() / max(int(nz.sum()), 1), int(bad.sum())))
+    assert not bad.any(), "%s: %d elements differ by more than 1e-5 (worst |err| %.3e at |want| %.3e, scale %.3e)" % (
+        name, int(bad.sum()), err[bad].max(), np.abs(want)[bad][np.argmax(err[bad])], np.broadcast_to(scale, want.shape)[bad][np.argmax(err[bad])])
+
+
+# ------------------------------------------------------------------------------------------------ F160
+@pytest.fixture(scope="module")
+def f160():
+    """bench.py's own workload: F160-sparse scene, trainer, one batch of 8192 in_maskcache rays (same seed as the bench)."""
+    import bench
+    scene, net, den, k0, tr, (ro, rd, vd, tg) = bench.build_workload(1, torch.device("cuda", 0), seed=777, parity_counts=True)
+    rays = [x[0].cpu().numpy() for x in (ro, rd, vd, tg)]
+    return scene, net, den, k0, tr, rays
+
+
+def test_f160_8192_rays_whole_iteration_matches_the_oracle(f160):
+    from oracle import oracle as orc
+    scene, net, den, k0, tr, rays = f160
+    n = rays[0].shape[0]
+    assert n == 8192 and tuple(scene["reso"]) == (160, 160, 160) and scene["variant"] == "sparse"
+    # ---- oracle: one full iteration (gradients stay in the *_grad grids after the update)
+    R, act = scene["reso"], scene["active"]
+    oden, ok0 = orc.Grid(R, 1, act), orc.Grid(R, 12, act)
+    oden.copy_from_dense(scene["density"])
+    ok0.copy_from_dense(scene["k0"])
+    aux = [orc.Grid(R, c, act) for c in (1, 1, 1, 12, 12, 12)]
+    onet, onm, onv = net.copy(), np.zeros_like(net), np.zeros_like(net)
+    o = orc.train_step(_oracle_cfg(scene, 1, 1), oden, aux[0], aux[1], aux[2], ok0, aux[3], aux[4], aux[5], scene["mask"], onet, onm, onv,
+                       *rays, cap_keep=400000)
+    assert o["M3"] > 50000, "degenerate batch"
+    # ---- ours: forward + backward, compare, then the update phase, compare
+    cu = [_cu(a) for a in rays]
+    tr.forward_backward(*cu)
+    torch.cuda.synchronize()
+    t = {k: v.cpu().numpy() for k, v in tr.t.items() if k in ("n_steps", "cnt_mask", "cnt_alpha_full", "cnt_alpha", "cnt_keep", "off_keep",
+                                                              "off_alpha", "k_ray", "s_step", "k_sample", "s_weight", "k_feat",
+                                                              "alphainv_last", "rgb_marched", "loss", "k_rgb")}
+    c = tr.counters()
+    assert c["overflow"] == 0
+    # integers: bit exact
+    assert np.array_equal(t["n_steps"], o["n_steps"].astype(np.int32))
+    assert np.array_equal(t["cnt_mask"], o["cnt_mask"])
+    assert np.array_equal(t["cnt_alpha_full"], o["cnt_alpha_full"])
+    assert np.array_equal(t["cnt_alpha"], o["cnt_alpha"])
+    assert np.array_equal(t["cnt_keep"], o["cnt_keep"])
+    assert c["M_alpha"] == o["M2_trim"] and c["M_keep"] == o["M3"]
+    assert np.array_equal(t["off_keep"], np.concatenate([[0], np.cumsum(o["cnt_keep"])]).astype(np.int32))
+    assert np.array_equal(t["off_alpha"], np.concatenate([[0], np.cumsum(o["cnt_alpha"])]).astype(np.int32))
+    M3 = o["M3"]
+    assert np.array_equal(t["k_ray"][:M3], o["keep_ray"])
+    assert np.array_equal(t["s_step"][t["k_sample"][:M3]], o["keep_step"])
+    kc = tr.t["k_corner"][:M3].cpu().numpy()            # record ids leaf*512+voxel saved by the march
+    want_rec = np.where(o["keep_leaf"] >= 0, o["keep_leaf"] * 512 + o["keep_off"], -1)
+    assert np.array_equal(kc, want_rec)
+    print("[parity] F160 counts: M1=%d M2=%d M2_trim=%d M3=%d rays=%d" % (o["M1"], o["M2"], o["M2_trim"], M3, n))
+    # values: 1e-5 relative
+    np.testing.assert_allclose(t["s_weight"][t["k_sample"][:M3]], o["keep_weight"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(t["k_feat"][:M3], o["keep_feat"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(t["alphainv_last"], o["alphainv_last"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(t["rgb_marched"], o["rgb_marched"], rtol=RTOL, atol=2e-6)
+    np.testing.assert_allclose(t["loss"], o["loss"], rtol=1e-4)
+    # gradients
+    gd, wd = den.grad.cpu().numpy().reshape(-1), aux[0].get_values().reshape(-1)
+    # exact sum of |contributions| per density voxel: scatter |dL/d density| of OUR alpha list with the oracle
+    ma = c["M_alpha"]
+    sx = tr.t["s_xyz"][:ma].cpu().numpy()
+    sg = np.abs(tr.t["s_gden"][:ma].cpu().numpy())
+    absacc = orc.Grid(R, 1, act)
+    absacc.backward(sx[:, 0], sx[:, 1], sx[:, 2], sg, threads=1)
+    _check_sum(gd, wd, absacc.get_values().reshape(-1), "density grad")
+    gk, wk = k0.grad.cpu().numpy().reshape(-1, 512 * 12), aux[3].get_values().reshape(-1, 512 * 12)
+    _check_sum(gk, wk, np.abs(wk).max(1, keepdims=True), "k0 grad (per leaf)")
+    assert ((gk != 0) == (wk != 0)).mean() > 0.9999
+    gn, wn = tr.net_grad.cpu().numpy(), o["net_grad"]
+    from plenvdb_b200 import synth
+    parts_g, parts_w = synth.unpack_net(gn), synth.unpack_net(wn)
+    for g_, w_, nm in zip(parts_g, parts_w, ("w0", "b0", "w1", "b1", "w2", "b2")):
+        _check_sum(g_, w_, np.abs(w_).max(), "rgbnet grad " + nm)
+    # ---- update: Adam moves every touched parameter by ~lr * g / (|g| + eps) = +-lr at step 1 whatever |g| is, so a
+    # gradient whose last bits differ still lands on the same parameter unless the gradient is at cancellation level;
+    # parameters are compared at 1e-5 relative with the step size lr as the magnitude scale of the moved ones
+    tr.update()
+    torch.cuda.synchronize()
+    for got, want, lr, name in ((den.grid.cpu().numpy().reshape(-1), oden.get_values().reshape(-1), scene["lr_density"], "density"),
+                                (k0.grid.cpu().numpy().reshape(-1), ok0.get_values().reshape(-1), scene["lr_k0"], "k0"),
+                                (tr.net.cpu().numpy(), onet, scene["lr_net"], "rgbnet")):
+        err = np.abs(got.astype(np.float64) - want)
+        ok = err <= RTOL * np.abs(want) + RTOL * lr
+        frac = 1.0 - ok.mean()
+        print("[parity] %-8s after 1 update: max|err|=%.2e, beyond 1e-5 (relative + 1e-5*lr): %d of %d" % (name, err.max(), int((~ok).sum()), ok.size))
+        # elements beyond it are sign flips of g/(sqrt(g^2)+eps) at gradients that cancel to ~0: bounded by 2*lr, and rare
+        assert err.max() <= 2.0 * lr * (1 + 1e-3) and frac < 1e-4, name
+
+
+def test_f160_ops_through_the_reference_call_sequence_match_the_fused_step(f160):
+    """The drop-in ops (B1/B2) composed the way dvgo.py:272-388 composes them give the same kept-sample list as the fused step
+    at the bench configuration: sample_pts_on_rays -> mask -> DensityVDB.forward -> Raw2Alpha -> Alphas2Weights."""
+    from plenvdb_b200 import render_utils_cuda as ru
+    from plenvdb_b200.synth import mask_scale_shift
+    scene, net, den, k0, tr, rays = f160
+    ro, rd, vd, tg = [_cu(a) for a in rays]
+    tr.forward(ro, rd, vd)
+    torch.cuda.synchronize()
+    mn, mx = _cu(scene["xyz_min"]), _cu(scene["xyz_max"])
+    pts, mob, ray_id, step_id, n_steps, tmin, tmax = ru.sample_pts_on_rays(ro, rd, mn, mx, scene["near"], scene["far"], scene["stepdist"])
+    inb = ~mob
+    pts, ray_id, step_id = pts[inb], ray_id[inb], step_id[inb]
+    sc, sh = mask_scale_shift(scene["mask"].shape, scene["xyz_min"], scene["xyz_max"])
+    m = ru.maskcache_lookup(_cu(scene["mask"].astype(np.uint8)).bool(), pts.contiguous(), _cu(sc), _cu(sh))
+    pts, ray_id, step_id = pts[m], ray_id[m], step_id[m]
+    idx = ((pts - mn) / (mx - mn) * (torch.tensor(scene["reso"], device="cuda", dtype=torch.float32) - 1))   # grid.py:77-78
+    dens = den.forward_torch(idx.t().contiguous()).reshape(-1)
+    exp_d, alpha = ru.raw2alpha(dens, scene["act_shift"], scene["interval"])
+    keep = alpha > scene["fast_color_thres"]
+    alpha, ray_id, step_id = alpha[keep], ray_id[keep], step_id[keep]
+    w, T, ail, i_s, i_e = ru.alpha2weight(alpha.contiguous(), ray_id.contiguous(), ro.shape[0])
+    keep = w > scene["fast_color_thres"]
+    mk = tr.counters()["M_keep"]
+    assert int(keep.sum()) == mk
+    assert torch.equal(ray_id[keep].int(), tr.t["k_ray"][:mk])
+    assert torch.equal(step_id[keep].int(), tr.t["s_step"][tr.t["k_sample"][:mk].long()])
+    wf = tr.t["s_weight"][tr.t["k_sample"][:mk].long()]
+    print("[parity] F160 op sequence vs fused step: %d kept samples, weights bit-identical: %s, alphainv_last bit-identical: %s" % (
+        mk, bool(torch.equal(w[keep], wf)), bool(torch.equal(ail, tr.t["alphainv_last"][: ro.shape[0]]))))
+    np.testing.assert_allclose(w[keep].cpu().numpy(), wf.cpu().numpy(), rtol=1e-6, atol=0)
+    np.testing.assert_allclose(ail.cpu().numpy(), tr.t["alphainv_last"][: ro.shape[0]].cpu().numpy(), rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ R800
+def test_r800_full_frames_match_the_reference_renderer():
+    """BASELINE configs[2]: the dense-fill F160 mic scene merged (vdb_compression.py:28-58), 800x800, poses 0 / 67 / 133 of the
+    200-pose orbit.  Per-pixel sample counts bit-exact against render_an_image_cuda; RGB 1e-5."""
+    from oracle import oracle as orc
+    from oracle import ref
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import build_scene_grids
+    from plenvdb_b200.plenvdb import MGRenderer
+    from plenvdb_b200.renderer import merge_grids
+    if not ref.available("gpu"):
+        pytest.skip("oracle/_ref/libref_gpu.so not present")
+    scene = synth.make_scene(160, "dense")
+    den, k0 = build_scene_grids(scene)
+    dend, cold, idx, n = merge_grids(den, k0, scene["mask"])
+    oden, ok0 = orc.Grid(scene["reso"], 1), orc.Grid(scene["reso"], 12)
+    oden.copy_from_dense(scene["density"])
+    ok0.copy_from_dense(scene["k0"])
+    wd, wc, widx = orc.merge(oden, ok0, scene["mask"])
+    assert np.array_equal(idx.cpu().numpy(), widx.astype(np.int32)) and np.array_equal(dend.cpu().numpy(), wd) and np.array_equal(cold.cpu().numpy(), wc)
+    H = W = 800
+    net = synth.rgbnet_init()
+    w0, b0, w1, b1, w2, b2 = synth.unpack_net(net)
+    mlp = (np.ascontiguousarray(w0.T), b0, np.ascontiguousarray(w1.T), b1, np.ascontiguousarray(w2.T), b2)
+    K = synth.intrinsics(H, W)
+    r = MGRenderer(12, 27, 128, 3)
+    r.load_data_dense(dend, cold, idx)
+    r.load_params(mlp[0].reshape(-1), mlp[1], mlp[2].reshape(-1), mlp[3], mlp[4].reshape(-1), mlp[5])
+    r.setScene(list(scene["reso"]), K.reshape(-1), scene["xyz_min"], scene["xyz_max"])
+    r.setKwargs(scene["near"], 6.0, scene["stepdist"], scene["act_shift"], scene["interval"], scene["fast_color_thres"], scene["bg"], False, H, W)
+    rg = ref.RefGrid(scene["reso"], 1, widx != 0, kind="gpu")
+    rg.gpu_copy_from_dense(widx)
+    poses = synth.render_cameras(200)
+    for cam in (0, 67, 133):
+        c2w = poses[cam]
+        r.input_a_c2w(c2w.reshape(-1))
+        r.render_an_image()
+        img = r.output_an_image().reshape(H * W, 3)
+        ns = r.s["n_samples"].cpu().numpy()
+        want, wns, sec = ref.gpu_render(rg, wd, wc, mlp, scene["reso"], K, scene["xyz_min"], scene["xyz_max"], scene["near"], scene["stepdist"],
+                                        scene["act_shift"], scene["interval"], scene["fast_color_thres"], scene["bg"], False, H, W, c2w)
+        assert ns.sum() > 100000, "degenerate view"
+        assert np.array_equal(ns, wns), "pose %d: per-pixel sample counts differ from the reference kernel on %d pixels" % (cam, (ns != wns).sum())
+        cnt = r.counters()
+        ok = np.ones(H * W, bool)
+        if cnt["inconsistent"]:   # rays where the reference's own two passes disagree: it overruns its segments there
+            ok = np.abs(img - want).max(1) < 1e-3
+            assert (~ok).sum() <= 4 * cnt["inconsistent"]
+        np.testing.assert_allclose(img[ok], want[ok], rtol=RTOL, atol=3e-6)
+        print("[parity] R800 pose %d: %d samples, %d pixels with samples, counts bit-exact, max|rgb err|=%.2e, reference-inconsistent rays %d, "
+              "reference frame %.2f ms" % (cam, int(ns.sum()), int((ns > 0).sum()), float(np.abs(img[ok] - want[ok]).max()), cnt["inconsistent"], sec * 1e3))
+
+
+# ------------------------------------------------------------------------------------------------ S512
+@pytest.fixture(scope="module")
+def s512():
+    from plenvdb_b200.fused import build_stress_scene
+    P, den, k0, mask = build_stress_scene(512)
+    return P, den, k0, mask
+
+
+def test_s512_trilinear_forward_matches_the_reference_kernels(s512):
+    """BASELINE configs[4] scene: density_forward / color_forward of the reference (densityvdb.cu:101-139, colorvdb.cu:81-126) on
+    NanoVDB grids built by the reference's GridBuilder from the same mask, against pvdb_sample_forward: bit-exact."""
+    from oracle import ref
+    if not ref.available("gpu"):
+        pytest.skip("oracle/_ref/libref_gpu.so not present")
+    P, den, k0, mask = s512
+    R = 512
+    assert 0.04 < P["occupied_fraction"] < 0.07, P["occupied_fraction"]
+    mask_h = mask.cpu().numpy()
+    rng = np.random.default_rng(11)
+    # sample points: inside the shell's bounding region, jittered around occupied voxels (most corners exist) + some outside
+    occ_idx = np.argwhere(mask_h)[rng.integers(0, int(mask_h.sum()), 200000)]
+    pts = (occ_idx + rng.uniform(-1.5, 1.5, occ_idx.shape)).astype(np.float32)
+    pts = np.clip(pts, 0, R - 1.001).astype(np.float32)
+    x, y, z = [np.ascontiguousarray(pts[:, a]) for a in range(3)]
+    pc = _cu(pts.T.copy())
+    for grid, ch in ((den, 1), (k0, 12)):
+        rg = ref.RefGrid((R, R, R), ch, mask_h, kind="gpu")
+        assert rg.n_leaf == grid.topo.n_leaf
+        assert np.array_equal(rg.leaf_origins(), grid.topo.h_leaf_origin[: grid.topo.n_leaf])
+        dense = grid.get_dense_grid_torch()                      # [R,R,R,ch] on the device (6.4 GB for k0)
+        rg.gpu_copy_from_dense_dev(dense)
+        del dense
+        want = rg.gpu_forward(x, y, z)
+        got = grid.forward_torch(pc).cpu().numpy()
+        assert np.abs(want).max() > 0.5
+        assert np.array_equal(got, want), "%d-channel forward differs from the reference kernel on %d values" % (ch, (got != want).sum())
+        del rg
+        torch.cuda.empty_cache()
+    print("[parity] S512: %d leaves, occupancy %.3f, D1/C1 forward bit-exact on %d points" % (den.topo.n_leaf, P["occupied_fraction"], len(x)))
+
+
+def test_s512_fused_step_counts_match_the_oracle(s512):
+    from oracle import oracle as orc
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import FusedTrainer
+    P, den, k0, mask = s512
+    R = 512
+    net = synth.rgbnet_init()
+    n = 4096
+    rng = np.random.default_rng(7)
+    K = np.array([[800.0, 0, 384.0], [0, 800.0, 288.0], [0, 0, 1]], np.float32)
+    poses = np.stack([synth.pose_spherical(rng.uniform(-180, 180), rng.uniform(-90, 0), rng.uniform(2.5, 3.5)) for _ in range(100)])
+    poses[:, :3, 1:3] *= -1
+    cam, px, py = rng.integers(0, 100, n), rng.integers(0, 768, n), rng.integers(0, 576, n)
+    ro, rd, vd = synth.rays_of_pixels(K, poses[cam], px, py, inverse_y=True)
+    tg = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    tr = FusedTrainer(P, den, k0, mask, net, n, parity_counts=True, cap_alpha_per_ray=256, cap_keep_per_ray=192, scratch_per_ray=128)
+    tr.forward_backward(*[_cu(a) for a in (ro, rd, vd, tg)])
+    torch.cuda.synchronize()
+    c = tr.counters()
+    assert c["overflow"] == 0 and c["M_keep"] > 20000
+    # oracle grids on the same pruned topology, filled leaf by leaf (the dense arrays would be 6.4 GB)
+    mask_h = mask.cpu().numpy()
+    oden, ok0 = orc.Grid((R, R, R), 1, mask_h), orc.Grid((R, R, R), 12, mask_h)
+    assert np.array_equal(oden.leaf_origins(), den.topo.h_leaf_origin[: den.topo.n_leaf])
+    oden.set_values(den.grid.cpu().numpy())
+    ok0.set_values(k0.grid.cpu().numpy())
+    aux = [orc.Grid((R, R, R), ch, mask_h) for ch in (1, 1, 1, 12, 12, 12)]
+    o = orc.train_step(_oracle_cfg(P, 1, 0), oden, aux[0], aux[1], aux[2], ok0, aux[3], aux[4], aux[5], mask_h, net.copy(), np.zeros_like(net),
+                       np.zeros_like(net), ro, rd, vd, tg, cap_keep=800000)
+    t = {k: tr.t[k].cpu().numpy() for k in ("n_steps", "cnt_mask", "cnt_alpha_full", "cnt_alpha", "cnt_keep", "k_ray", "s_step", "k_sample",
+                                           "rgb_marched", "alphainv_last", "k_corner")}
+    assert np.array_equal(t["n_steps"], o["n_steps"].astype(np.int32))
+    assert np.array_equal(t["cnt_mask"], o["cnt_mask"]) and np.array_equal(t["cnt_alpha_full"], o["cnt_alpha_full"])
+    assert np.array_equal(t["cnt_alpha"], o["cnt_alpha"]) and np.array_equal(t["cnt_keep"], o["cnt_keep"])
+    M3 = o["M3"]
+    assert c["M_keep"] == M3 and c["M_alpha"] == o["M2_trim"]
+    assert np.array_equal(t["k_ray"][:M3], o["keep_ray"]) and np.array_equal(t["s_step"][t["k_sample"][:M3]], o["keep_step"])
+    assert np.array_equal(t["k_corner"][:M3], np.where(o["keep_leaf"] >= 0, o["keep_leaf"] * 512 + o["keep_off"], -1))
+    np.testing.assert_allclose(t["alphainv_last"], o["alphainv_last"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(t["rgb_marched"], o["rgb_marched"], rtol=RTOL, atol=2e-6)
+    gk, wk = k0.grad.cpu().numpy().reshape(-1, 512 * 12), aux[3].get_values().reshape(-1, 512 * 12)
+    _check_sum(gk, wk, np.abs(wk).max(1, keepdims=True), "S512 k0 grad")
+    print("[parity] S512 step: n_steps max %d, M1=%d M2_trim=%d M3=%d on %d rays, counts and corner ids bit-exact" % (
+        int(t["n_steps"].max()), o["M1"], o["M2_trim"], M3, n))
+    tr.update()      # leave the shared grids' gradient planes clean for other tests
