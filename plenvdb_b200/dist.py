@@ -80,46 +80,17 @@ class PeerExchange:
     def __init__(self, n_leaf, cap_leaves=None, group=None):
         import ctypes as C
         from . import _lib
-        self._C, self._lib = C, _lib
+        self._C, self._lib, self._group = C, _lib, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        assert self.world <= 8, "one NVSwitch domain (<= 8 GPUs)"
         cap = int(cap_leaves) if cap_leaves else max(int(n_leaf), 1)
         nbytes = _lib.lib.pvdb_dp_symm_bytes(int(n_leaf), cap)
-        own = C.c_void_p()
-        handle = C.create_string_buffer(64)
         self._own, self._opened = None, []
-        # Every rank takes part in both collectives whatever happens locally, and all ranks agree on the outcome: a rank
-        # whose allocation or mapping fails (no peer access, IPC disabled in the container) must not leave the others hanging.
-        err = None
-        try:
-            _lib.call("pvdb_dp_symm_alloc", nbytes, C.byref(own), handle)
-            self._own = own
-        except _lib.PvdbError as e:
-            err = str(e)
-        handles = [None] * self.world
-        dist.all_gather_object(handles, None if err else bytes(handle.raw), group=group)
+        # collective; on any rank's failure every rank raises PeerExchangeUnavailable after everything was unmapped and freed
+        self._own, bases, self._opened = open_symmetric_blocks(nbytes, group)
         self.peers = _lib.pvdb_dp_peers()
         self.peers.world, self.peers.rank, self.peers.n_leaf, self.peers.cap_leaves = self.world, self.rank, int(n_leaf), cap
-        if err is None and all(h is not None for h in handles):
-            try:
-                for r in range(self.world):
-                    if r == self.rank:
-                        self.peers.base[r] = own.value
-                    else:
-                        p = C.c_void_p()
-                        _lib.call("pvdb_dp_symm_open", C.create_string_buffer(handles[r], 64), C.byref(p))
-                        self.peers.base[r] = p.value
-                        self._opened.append(p)
-            except _lib.PvdbError as e:
-                err = str(e)
-        elif err is None:
-            err = "a peer could not allocate its symmetric block"
-        oks = [None] * self.world
-        dist.all_gather_object(oks, err, group=group)   # also the barrier: every block is zeroed and mapped before the first signal
-        bad = [(r, e) for r, e in enumerate(oks) if e is not None]
-        if bad:
-            self.close()
-            raise PeerExchangeUnavailable("NVLink peer exchange unavailable (rank %d: %s)" % bad[0])
+        for r in range(self.world):
+            self.peers.base[r] = bases[r]
         self.step = 0
         self.nbytes = nbytes
 
@@ -133,12 +104,12 @@ class PeerExchange:
         return int(e.value)
 
     def close(self):
-        for p in self._opened:
-            self._lib.call("pvdb_dp_symm_close", p)
-        self._opened = []
-        if self._own is not None:
-            self._lib.call("pvdb_dp_symm_free", self._own)
-            self._own = None
+        """Collective: every rank calls it.  The stream is drained, the peers' blocks are unmapped on every rank, and only after a
+        barrier does a rank free its own block (CUDA IPC leaves freeing a block that a peer still maps undefined)."""
+        if self._own is None and not self._opened:
+            return
+        close_symmetric_blocks(self._own, self._opened, self._group, barrier=True)
+        self._own, self._opened = None, []
 
 
 class DataParallelTrainer:
@@ -227,6 +198,12 @@ class DataParallelTrainer:
             n = int(self.tr.t["counters"][2].item())
             return (self.world - 1) * (n * 512 * 13 + 22019) * 4 + (self.world - 1) * self.tr.topo.n_leaf * 4
         return self.last_exchange_bytes
+
+    def close(self):
+        """Collective: releases the NVLink symmetric blocks (no-op for the NCCL exchange)."""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
 
 def open_symmetric_blocks(nbytes, group=None):

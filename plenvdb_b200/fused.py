@@ -189,16 +189,18 @@ class FusedTrainer:
         """One full iteration: forward + backward + sparse Adam (grids) + Adam (rgbnet)."""
         self.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE)
 
-    def step_from_host(self, batch_host):
+    def step_from_host(self, batch_host, stepper=None):
         """One iteration fed from HOST memory, the way run.py:541-588 is driven: `batch_host` is a pinned float32 tensor
         [4, n, 3] = (rays_o, rays_d, viewdirs, target).  One H2D copy, the fused step, one D2H of the four loss words;
-        returns them as a pinned host tensor (valid after this call: it synchronises the stream, like `loss.item()`)."""
+        returns them as a pinned host tensor (valid after this call: it synchronises the stream, like `loss.item()`; it is
+        overwritten by the next call).  stepper: callable(rays_o, rays_d, viewdirs, target) issuing the iteration (default
+        self.step; DataParallelTrainer.step for a sharded run)."""
         n = batch_host.shape[1]
         if getattr(self, "_stage", None) is None or self._stage.shape[1] != n:
             self._stage = torch.empty((4, n, 3), dtype=torch.float32, device=self.dev)
             self._loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
         self._stage.copy_(batch_host, non_blocking=True)
-        self.step(self._stage[0], self._stage[1], self._stage[2], self._stage[3])
+        (stepper or self.step)(self._stage[0], self._stage[1], self._stage[2], self._stage[3])
         self._loss_host.copy_(self.t["loss"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._loss_host

@@ -20,7 +20,10 @@ def merge_grids(density, k0, mask):
     """vdb_compression.py:19-59 on the device.  density: DensityVDB, k0: ColorVDB, mask: bool [reso] (mask_cache.mask).
     Returns (den[N+1] f32, col[N+1,C] f32 — both rounded through fp16 —, idx_dense int32 [reso] 1-based, N)."""
     dev = density.device
-    m = torch.as_tensor(np.ascontiguousarray(np.asarray(mask).astype(np.bool_))).to(dev)
+    if torch.is_tensor(mask):
+        m = mask.to(dev).bool().contiguous()
+    else:
+        m = torch.as_tensor(np.ascontiguousarray(np.asarray(mask).astype(np.bool_))).to(dev)
     reso = tuple(m.shape)
     flat = m.reshape(-1)
     row = torch.cumsum(flat.to(torch.int32), 0, dtype=torch.int32) * flat.to(torch.int32)   # idxs = arange(1, N+1) in C order
@@ -45,7 +48,8 @@ def save_merged(basepath, den, col, idx_dense):
 class MGRenderer:
     """MGRenderer(dcol, dpe, dhid, dout) (plenvdb.h:936-945)."""
 
-    def __init__(self, dcol=12, dpe=27, dhid=128, dout=3, device="cuda", use_tensor_cores=True, skip_empty=True, px_entries=64):
+    def __init__(self, dcol=12, dpe=27, dhid=128, dout=3, device="cuda", use_tensor_cores=True, skip_empty=True, px_entries=64,
+                 cap_per_pixel=6):
         self.dcol, self.dpe, self.dhid, self.dout = int(dcol), int(dpe), int(dhid), int(dout)
         self.dev = torch.device(device)
         self.flags = [False] * 5   # load_data, load_params, setScene, setKwargs, input_a_c2w (plenvdb.h:1056)
@@ -58,6 +62,7 @@ class MGRenderer:
         self._skip_key, self._skip_bits, self._topo_version = None, None, 0
         # pass 1 hands its first px_entries kept samples per pixel over to the sample list (0: every pixel is marched twice)
         self.px_entries = int(px_entries)
+        self.cap_per_pixel = int(cap_per_pixel)    # capacity of the frame's sample list, in kept samples per pixel (overflow is counted)
         self.c2w = torch.zeros(16, dtype=torch.float32, device=self.dev)
         self.out = None
 
@@ -129,14 +134,14 @@ class MGRenderer:
         if getattr(self, "bufs", None) is not None:
             self.bufs.skip_bits = self._skip_bits.data_ptr() if self._skip_bits is not None else None
 
-    def _ensure_scratch(self, rows, cap_per_pixel=6):
+    def _ensure_scratch(self, rows):
         if rows == self._scratch_rows:
             self._ensure_skip_bits()
             return
         npix = rows * self.cfg.W
         i32 = dict(dtype=torch.int32, device=self.dev)
         f32 = dict(dtype=torch.float32, device=self.dev)
-        cap = max(int(npix * cap_per_pixel), 4096)
+        cap = max(int(npix * self.cap_per_pixel), 4096)
         self.s = dict(n_samples=torch.zeros(npix, **i32), i_starts=torch.zeros(npix + 1, **i32), tmins=torch.zeros(npix, **f32),
                       tmaxs=torch.zeros(npix, **f32), scan_tmp=torch.zeros(npix // 4096 + 3, **i32), s_ray=torch.zeros(cap, **i32),
                       s_weight=torch.zeros(cap, **f32), s_feat=torch.zeros(cap, 12, **f32), s_rgb=torch.zeros(cap, 3, **f32),
