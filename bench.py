@@ -841,19 +841,29 @@ def bench_s512(args, dev, rank, world, flush, headline):
         hbm, tf, which = measured_peaks()
         kern = kernel_times(tr, batches, K, Wm, flush, full_step=(world == 1))
         top = max(kern, key=kern.get)
-        # compulsory bytes of the dominant phases from the device-side counts: the sparse Adam of the touched leaves reads p, g, m, v
-        # and writes p, m, v (28 B per voxel-channel) — the HBM-bound part at this size
-        upd_bytes = 28.0 * 512 * (cnt["n_touched_den"] + 12 * cnt["n_touched_k0"])
+        # Compulsory bytes of the sparse Adam (the HBM-bound kernel at this size) from device-side counts: it reads the gradient of
+        # every voxel-channel of every touched leaf (4 B) and, where the gradient is non-zero (stepmode 1 skips the rest), reads
+        # p, m, v and writes p, m, v, g (28 B more).  The non-zero count is taken from one extra forward+backward at N = 1.
+        roof = None
+        if world == 1:
+            ro, rd, vd, tg = batches
+            tr.forward_backward(ro[Wm], rd[Wm], vd[Wm], tg[Wm])
+            nz = int(torch.count_nonzero(tr.density.grad).item()) + int(torch.count_nonzero(tr.k0.grad).item())
+            c2 = tr.counters()
+            tr.update()
+            upd_bytes = 4.0 * 512 * (c2["n_touched_den"] + 12 * c2["n_touched_k0"]) + 28.0 * nz
+            t_upd = kern.get("update_fused", float("nan")) * 1e-3
+            roof = {"bound": "hbm", "kernel": "update_fused", "achieved": upd_bytes / t_upd / 1e9, "peak": hbm, "unit": "GB/s",
+                    "frac": upd_bytes / t_upd / 1e9 / hbm, "algorithmic_bytes": upd_bytes, "nonzero_gradient_channels": nz,
+                    "top_kernel": top, "peak_source": which,
+                    "note": "sparse Adam over the touched leaves: 4 B per voxel-channel of every touched leaf + 28 B per channel with a non-zero gradient"}
         out = {"workload": "S512: 512^3 noisy shell, %.1f %% of the voxels occupied, %d leaves (pruned topology), %d in_maskcache rays/GPU/iteration, "
                            "768x576 inverse_y cameras" % (100 * P["occupied_fraction"], den.topo.n_leaf, S512_RAYS),
                "train": {"value": T["value"], "unit": "rays/s", "ms_per_step": T["ms_total"] / K, "steps": K, "warmup": Wm, "n_gpus": world,
                          "warm_l2_ms_per_step": T["warm_ms"], "gpu_launches": T["launches"], "kernel_ms": kern,
                          "samples": {"M_alpha": cnt["M_alpha"], "M_keep": cnt["M_keep"], "touched_leaves_density": cnt["n_touched_den"],
                                      "touched_leaves_k0": cnt["n_touched_k0"]},
-                         "roofline": {"bound": "hbm", "kernel": "update_fused", "achieved": upd_bytes / (kern.get("update_fused", float("nan")) * 1e-3) / 1e9,
-                                      "peak": hbm, "unit": "GB/s", "frac": upd_bytes / (kern.get("update_fused", float("nan")) * 1e-3) / 1e9 / hbm,
-                                      "algorithmic_bytes": upd_bytes, "top_kernel": top, "peak_source": which,
-                                      "note": "sparse Adam over the touched leaves: 28 B per voxel-channel of every touched leaf"}}}
+                         "roofline": roof}}
         if rep is not None:
             out["train"]["parity"] = rep
         if world > 1:

@@ -239,8 +239,10 @@ int pvdb_dp_unpack(const pvdb_train_bufs* bufs, const int32_t* union_list, const
  * are exchanged by the caller's own transport (torch.distributed all_gather_object here) and opened with
  * pvdb_dp_symm_open; base[r] is rank r's block as mapped in THIS process (base[rank] = the own allocation).
  * pvdb_dp_exchange(step) runs after the backward phase on every rank with the same monotone `step` (0,1,2,...):
- * cross-GPU barrier, union of touched leaves, pack, barrier, peer-read sum in rank order into den_grad/k0_grad/net_grad,
- * and leaves den/k0_touched_list + counters[2],[4] ready for pvdb_train_step(PVDB_PHASE_UPDATE|PVDB_PHASE_LISTS_READY).
+ * cross-GPU barrier, union of touched leaves, pack, reduce-scatter + all-gather over peer memory (every rank sums the union
+ * slots it owns in rank order and stores the sums into every rank's block: O(1) NVLink bytes per rank), unpack into
+ * den_grad/k0_grad, rgbnet gradients into net_grad, and leaves den/k0_touched_list + counters[2],[4] ready for
+ * pvdb_train_step(PVDB_PHASE_UPDATE|PVDB_PHASE_LISTS_READY).
  * A peer that does not arrive within 2 s sets the block's error word (pvdb_dp_symm_error: 1 timeout, 2 union > cap). */
 typedef struct {
     int32_t world, rank;      /* world <= 8 (one NVSwitch domain) */
@@ -258,9 +260,12 @@ int pvdb_dp_exchange(const pvdb_dp_peers* peers, const pvdb_train_bufs* bufs, ui
  * gradients (needs the weight-gradient kernel). */
 int pvdb_dp_exchange_tiles(const pvdb_dp_peers* peers, const pvdb_train_bufs* bufs, uint32_t step, void* stream);
 int pvdb_dp_exchange_net(const pvdb_dp_peers* peers, const pvdb_train_bufs* bufs, uint32_t step, void* stream);
-/* One data-parallel iteration on this rank's ray shard (cfg->n_rays_global = rays of all ranks): forward, backward with
- * the tile exchange running on an internal side stream UNDER the weight-gradient kernel, rgbnet-gradient exchange, update.
- * Every rank must call it with the same dp_step (0,1,2,...). */
+/* One data-parallel iteration on this rank's ray shard (cfg->n_rays_global = rays of all ranks).  The emit kernel writes the
+ * rank's touched-leaf flags (they follow from the sample lists), so the union and its cross-GPU barrier run on an internal
+ * side stream UNDER the rgbnet forward; pack / reduce / unpack and the leaf Adam run UNDER the weight-gradient kernel; the
+ * rgbnet gradients are pushed to the peers by the weight-gradient reduction and summed by the rgbnet Adam (no exchange kernel
+ * on the critical path).  Every rank must call it with the same dp_step (0,1,2,...) and the same step as pvdb_dp_exchange
+ * would get: the two share the epoch counters of the symmetric block. */
 int pvdb_train_step_dp(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs, const pvdb_dp_peers* peers, uint32_t dp_step,
                        const float* rays_o, const float* rays_d, const float* viewdirs, const float* target, int n_rays,
                        void* stream);

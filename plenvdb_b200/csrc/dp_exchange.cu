@@ -2,44 +2,56 @@
 // so this has no counterpart there).  Each rank owns one "symmetric block" (cudaMalloc + CUDA IPC, mapped by every peer):
 //
 //   [0,448)      signal words, u32, monotone epochs (step + 1) written by the peers with st.release.sys and polled by the
-//                owner: A[src] flags published, B[src] tiles packed, C[slice][src] rgbnet-gradient slice published
-//   [448,512)    err, done_ctas
-//   [1024,..)    flags[2][n_leaf] i32   touched flags published by the owner (double-buffered by step parity)
-//   [net_off,.)  net[2][NET_PAD]  f32   rgbnet gradients
-//   [grad_off,.) grad[2][cap]     f32   packed gradient tiles of the union leaves
+//                owner: A[src] flags published, B[src] tiles packed, D[src] reduced tiles delivered, C[src] rgbnet gradients
+//                delivered, CS[slice][src] (stand-alone rgbnet exchange)
+//   [448,512)    err, done counters
+//   [1024,..)    flags[2][n_leaf] i32      touched flags published by the owner (double-buffered by step parity)
+//   [net_off,.)  net[2][NET_PAD]  f32      stand-alone rgbnet exchange: the owner's gradients, read by the peers
+//   [netx_off,.) netx[2][8][NET_PAD] f32   fused rgbnet exchange: slot [src] is WRITTEN BY rank src (peer stores)
+//   [grad_off,.) grad[2][cap]     f32      the owner's packed gradient tiles of the union leaves, read by the peers
+//   [red_off,.)  red[2][cap]      f32      reduced tiles, slot s WRITTEN BY its owner rank s % world (peer stores)
 //
-// Two phases, no host synchronisation and no NCCL call.  They are independent so that the fused step can run the tile
-// phase on a side stream UNDER the weight-gradient kernel (the grid gradients are final once the activation-gradient
-// kernel and the density scatter are done) and only the 88 KB rgbnet phase after it:
-//   tiles:  k_dp_union   1 CTA : publish own flags -> cross-GPU barrier A -> OR of all peers' flags -> ascending union list
-//           k_dp_pack    grid  : own gradient tiles of the union leaves -> own grad[parity]; the last CTA signals B
-//           k_dp_reduce  grid  : wait for B, then every rank sums the peers' tiles in rank order (identical bits
-//                                everywhere) straight into its gradient planes, ready for the fused sparse Adam
-//   net:    k_dp_net     8 CTAs: each publishes one slice of net_grad, signals C[slice], waits for the peers' C[slice] and
-//                                sums that slice in rank order — no grid-wide dependency
+// No host synchronisation and no NCCL call.  Per step and rank the NVLink traffic is O(1) in the number of ranks:
+//   k_dp_union   1 CTA : cross-GPU barrier A -> OR of all peers' flags -> ascending union list (identical everywhere)
+//   k_dp_pack    grid  : own gradient tiles of the union leaves -> own grad[parity]; the last CTA signals B
+//   k_dp_rs      grid  : reduce-scatter + all-gather in one kernel.  Rank r owns the union slots s with s % world == r: it
+//                        reads that slot from every rank's grad[parity] (world - 1 peer loads of 1/world of the data), sums in
+//                        rank order (identical bits everywhere) and stores the result into EVERY rank's red[parity]
+//                        (world - 1 peer stores); the last CTA signals D
+//   k_dp_unpack  grid  : wait for D, copy red[parity] (local memory) into the gradient planes
+// The rgbnet gradients (88 KB) ride on the kernels that produce and consume them: the weight-gradient reduction stores its
+// sums straight into every peer's netx[parity][rank] (pvdb_dp_net_push_args) and the rgbnet Adam waits for C and adds the
+// world slots of its own block in rank order (pvdb_dp_net_wait_args) — no exchange kernel at all on that path.
+// In the fused step (pvdb_train_step_dp) the flags are written by the emit kernel (the sample lists determine the touched
+// leaves before any gradient exists), so k_dp_union — and with it the barrier that absorbs the ranks' skew — runs on the side
+// stream under the rgbnet forward; pack / rs / unpack run under the weight-gradient kernel.
 // Double buffering makes further barriers unnecessary: a rank overwrites parity p two steps later, after it passed barrier
 // A of the step in between, which every peer reaches only after all of its reads of the earlier step (stream order).
 #include "common.cuh"
 #include "rgbnet.cuh"
 #include "peer_sync.cuh"
+#include "dp_exchange.cuh"
 
 namespace {
 
 constexpr int TILE_F = PVDB_LEAF_VOX * 13;                 // density [512] + k0 [512][12]
-constexpr int NET_PAD = (PVDB_NET_N + 255) & ~255;
+constexpr int NET_PAD = PVDB_DP_NET_PAD;
 constexpr int NET_SLICES = 8;
-enum { SIG_A = 0, SIG_B = 16, SIG_C = 32 };                // word offsets inside the signal area (C: [slice][8])
+enum { SIG_A = 0, SIG_B = 8, SIG_D = 16, SIG_C = 24, SIG_CS = 32 };   // word offsets inside the signal area (CS: [slice][8])
 
 struct Blk {
     uint32_t* signal;
     int32_t* err;
-    uint32_t* done;
+    uint32_t* done;      // [4] last-CTA counters
     int32_t* flags[2];
     float* net[2];
+    float* netx[2];      // [8][NET_PAD] each
     float* grad[2];
+    float* red[2];
 };
 __host__ __device__ inline size_t net_off(int n_leaf) { return (1024 + (size_t)8 * n_leaf + 255) & ~(size_t)255; }
-__host__ __device__ inline size_t grad_off(int n_leaf) { return net_off(n_leaf) + 2 * (size_t)NET_PAD * sizeof(float); }
+__host__ __device__ inline size_t netx_off(int n_leaf) { return net_off(n_leaf) + 2 * (size_t)NET_PAD * sizeof(float); }
+__host__ __device__ inline size_t grad_off(int n_leaf) { return netx_off(n_leaf) + 2 * 8 * (size_t)NET_PAD * sizeof(float); }
 __host__ __device__ inline size_t cap_floats(int cap_leaves) { return (size_t)cap_leaves * TILE_F; }
 __host__ __device__ inline Blk view(void* base, int n_leaf, int cap_leaves) {
     char* p = static_cast<char*>(base);
@@ -51,8 +63,12 @@ __host__ __device__ inline Blk view(void* base, int n_leaf, int cap_leaves) {
     b.flags[1] = b.flags[0] + n_leaf;
     b.net[0] = reinterpret_cast<float*>(p + net_off(n_leaf));
     b.net[1] = b.net[0] + NET_PAD;
+    b.netx[0] = reinterpret_cast<float*>(p + netx_off(n_leaf));
+    b.netx[1] = b.netx[0] + 8 * (size_t)NET_PAD;
     b.grad[0] = reinterpret_cast<float*>(p + grad_off(n_leaf));
     b.grad[1] = b.grad[0] + cap_floats(cap_leaves);
+    b.red[0] = b.grad[1] + cap_floats(cap_leaves);
+    b.red[1] = b.red[0] + cap_floats(cap_leaves);
     return b;
 }
 
@@ -65,8 +81,23 @@ __device__ __forceinline__ void wait_peer(const pvdb_dp_peers& P, int peer, int 
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
     wait_epoch(me.signal + word + peer, epoch, me.err, 1);   // a dead peer must not hang the GPU
 }
+// Called by every thread of every CTA after its last store: the last CTA of the grid to get here signals `word` to every peer.
+// threadFenceReduction pattern; the fence is system-wide because the stores it publishes may be peer stores.
+__device__ __forceinline__ void last_cta_signals(const pvdb_dp_peers& P, uint32_t* done, int word, uint32_t epoch) {
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(done, 1u) == gridDim.x - 1;
+        if (last) { *done = 0; __threadfence_system(); }
+    }
+    __syncthreads();
+    if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, word, epoch);
+}
 
-__global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epoch, int parity, int32_t* __restrict__ den_touched,
+// publish != 0 (stand-alone exchange): the flags are taken from den_touched | k0_touched here; publish == 0 (fused step): the
+// emit kernel has already written them into flags[parity].
+__global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epoch, int parity, int publish, int32_t* __restrict__ den_touched,
                                                    int32_t* __restrict__ k0_touched, int32_t* __restrict__ den_list,
                                                    int32_t* __restrict__ k0_list, int32_t* __restrict__ counters, int cnt_den, int cnt_k0) {
     __shared__ int warp_cnt[32];
@@ -74,7 +105,8 @@ __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epo
     pvdb_pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
-    for (int i = threadIdx.x; i < P.n_leaf; i += 1024) me.flags[parity][i] = (den_touched[i] | k0_touched[i]) != 0;
+    if (publish)
+        for (int i = threadIdx.x; i < P.n_leaf; i += 1024) me.flags[parity][i] = (den_touched[i] | k0_touched[i]) != 0;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();   // the st.release.sys below is cumulative over the CTA's flag writes ordered by this barrier
     if (threadIdx.x < P.world) {
@@ -90,7 +122,12 @@ __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epo
         if (i < P.n_leaf)
             for (int r = 0; r < P.world; ++r) f |= __ldcv(pf[r] + i);
         const bool t = f != 0;
-        if (i < P.n_leaf) { den_touched[i] = t; k0_touched[i] = t; }
+        if (i < P.n_leaf) {
+            den_touched[i] = t; k0_touched[i] = t;
+            // every peer has passed barrier A of this step, i.e. finished the union of the previous one: the other parity's flags
+            // have no reader left and are cleared for the emit kernel of the next step
+            me.flags[parity ^ 1][i] = 0;
+        }
         const unsigned bits = __ballot_sync(0xffffffffu, t);
         if (lane == 0) warp_cnt[warp] = __popc(bits);
         __syncthreads();
@@ -126,58 +163,75 @@ __global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch
     const int n = counters[cnt_den];
     float* buf = me.grad[parity];
     constexpr int T4 = TILE_F / 4;
-    const int total = n * T4;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int slot = idx / T4, i = idx - slot * T4;
+    const int64_t total = (int64_t)n * T4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(idx / T4), i = (int)(idx - (int64_t)slot * T4);
         const int leaf = list[slot];
         const float4 v = i < 128 ? reinterpret_cast<const float4*>(den_grad + (size_t)leaf * 512)[i]
                                  : reinterpret_cast<const float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128];
         reinterpret_cast<float4*>(buf)[idx] = v;
     }
-    // last CTA out tells every peer that this rank's tiles are in place (threadFenceReduction pattern; the final
-    // st.release.sys is cumulative over everything the counter made visible)
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = atomicAdd(me.done, 1u) == gridDim.x - 1;
-        if (last) { *me.done = 0; __threadfence(); }
-    }
-    __syncthreads();
-    if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_B, epoch);
+    last_cta_signals(P, me.done + 0, SIG_B, epoch);
 }
 
-__global__ void __launch_bounds__(256) k_dp_reduce(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ den_grad,
-                                                   float* __restrict__ k0_grad,
-                                                   const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
+// Reduce-scatter + all-gather: this rank sums the union slots it owns (slot % world == rank) over all ranks, in rank order, and
+// stores the sums into every rank's red[parity].
+__global__ void __launch_bounds__(256) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, int parity, const int32_t* __restrict__ counters, int cnt_den) {
     pvdb_pdl_wait();
     if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_B, epoch);
     __syncthreads();
     const int n = counters[cnt_den];
-    const float* pb[8];
-    for (int r = 0; r < 8; ++r) pb[r] = view(P.base[r < P.world ? r : 0], P.n_leaf, P.cap_leaves).grad[parity];
+    const float4* pb[8];
+    float4* pr[8];
+    for (int r = 0; r < 8; ++r) {
+        const Blk b = view(P.base[r < P.world ? r : 0], P.n_leaf, P.cap_leaves);
+        pb[r] = reinterpret_cast<const float4*>(b.grad[parity]);
+        pr[r] = reinterpret_cast<float4*>(b.red[parity]);
+    }
     constexpr int T4 = TILE_F / 4;
-    const int total = n * T4;
+    const int mine = n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
+    const int64_t total = (int64_t)mine * T4;
     // plain loads: these peer addresses were last read two steps ago in another launch, and the acquire + barrier above
     // orders them after the peers' packs
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / T4), i = (int)(idx - (int64_t)j * T4);
+        const int64_t off = (int64_t)(P.rank + j * P.world) * T4 + i;
         float4 v[8];
         #pragma unroll
         for (int r = 0; r < 8; ++r)
-            if (r < P.world) v[r] = reinterpret_cast<const float4*>(pb[r])[idx];
+            if (r < P.world) v[r] = pb[r][off];
         float4 s = v[0];
         #pragma unroll
         for (int r = 1; r < 8; ++r)
             if (r < P.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
-        const int slot = idx / T4, i = idx - slot * T4;
+        #pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < P.world) pr[r][off] = s;
+    }
+    last_cta_signals(P, view(P.base[P.rank], P.n_leaf, P.cap_leaves).done + 1, SIG_D, epoch);
+}
+
+__global__ void __launch_bounds__(256) k_dp_unpack(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ den_grad,
+                                                   float* __restrict__ k0_grad,
+                                                   const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
+    pvdb_pdl_wait();
+    if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_D, epoch);
+    __syncthreads();
+    const int n = counters[cnt_den];
+    const float4* red = reinterpret_cast<const float4*>(view(P.base[P.rank], P.n_leaf, P.cap_leaves).red[parity]);
+    constexpr int T4 = TILE_F / 4;
+    const int64_t total = (int64_t)n * T4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const float4 s = __ldcg(red + idx);          // written by the peers through NVLink: lives in L2, never in this SM's L1
+        const int slot = (int)(idx / T4), i = (int)(idx - (int64_t)slot * T4);
         const int leaf = list[slot];
         if (i < 128) reinterpret_cast<float4*>(den_grad + (size_t)leaf * 512)[i] = s;
         else reinterpret_cast<float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128] = s;
     }
 }
 
-// rgbnet gradients: CTA `g` owns slice g of the 22 019 values end to end (publish, signal, wait, sum), so there is no
-// grid-wide dependency and a single latency of peer loads.
+// Stand-alone rgbnet exchange (pvdb_dp_exchange_net): CTA `g` owns slice g of the 22 019 values end to end (publish, signal,
+// wait, sum), so there is no grid-wide dependency and a single latency of peer loads.
 __global__ void __launch_bounds__(1024) k_dp_net(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ net_grad) {
     constexpr int SL = NET_PAD / NET_SLICES;       // floats per slice (multiple of 4)
     pvdb_pdl_wait();
@@ -193,8 +247,8 @@ __global__ void __launch_bounds__(1024) k_dp_net(pvdb_dp_peers P, uint32_t epoch
     }
     __syncthreads();   // the st.release.sys below is cumulative over the CTA's stores ordered by this barrier
     if (threadIdx.x < P.world) {
-        signal_peer(P, threadIdx.x, SIG_C + g * 8, epoch);
-        wait_peer(P, threadIdx.x, SIG_C + g * 8, epoch);
+        signal_peer(P, threadIdx.x, SIG_CS + g * 8, epoch);
+        wait_peer(P, threadIdx.x, SIG_CS + g * 8, epoch);
     }
     __syncthreads();
     if (!live) return;
@@ -224,7 +278,7 @@ int check_peers(const pvdb_dp_peers* P, const pvdb_train_bufs* b) {
 
 extern "C" size_t pvdb_dp_symm_bytes(int n_leaf, int cap_leaves) {
     if (n_leaf < 0 || cap_leaves < 0) return 0;
-    return grad_off(n_leaf) + 2 * cap_floats(cap_leaves) * sizeof(float);
+    return grad_off(n_leaf) + 4 * cap_floats(cap_leaves) * sizeof(float);
 }
 extern "C" int pvdb_dp_symm_alloc(size_t bytes, void** ptr, void* handle64) {
     PVDB_CHECK_ARG(ptr && handle64 && bytes > 0, "null pointer / zero size");
@@ -256,25 +310,67 @@ extern "C" int pvdb_dp_symm_error(const pvdb_dp_peers* P, int32_t* err_out) {
     return PVDB_OK;
 }
 
-extern "C" int pvdb_dp_exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
+static int exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st, bool do_union, int publish,
+                          bool do_move) {
     if (int rc = check_peers(P, b)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
     const int parity = step & 1;
     const uint32_t epoch = step + 1;                        // monotone; the signal words start at 0
     const int CNT_DEN = 2, CNT_K0 = 4;                      // counters[] slots of pvdb_train_bufs (include/plenvdb_b200.h)
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_union, dim3(1), dim3(1024), 0, st, *P, epoch, parity, b->den_touched, b->k0_touched, b->den_touched_list,
-                              b->k0_touched_list, b->counters, CNT_DEN, CNT_K0));
-    PVDB_LAUNCH_CHECK();
-    pvdb_prof_mark("dp_union", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_pack, dim3(PVDB_SMS), dim3(256), 0, st, *P, epoch, parity, (const float*)b->den_grad, (const float*)b->k0_grad,
+    if (do_union) {
+        PVDB_CUDA(pvdb_launch_pdl(k_dp_union, dim3(1), dim3(1024), 0, st, *P, epoch, parity, publish, b->den_touched, b->k0_touched,
+                                  b->den_touched_list, b->k0_touched_list, b->counters, CNT_DEN, CNT_K0));
+        PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("dp_union", st);
+    }
+    if (!do_move) return PVDB_OK;
+    // grids sized for the F160 case (74 union leaves = 2 MB: latency bound) and grid-striding for S512 (~0.5 GB)
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_pack, dim3(PVDB_SMS * 2), dim3(256), 0, st, *P, epoch, parity, (const float*)b->den_grad, (const float*)b->k0_grad,
                               (const int32_t*)b->den_touched_list, (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_pack", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_reduce, dim3(PVDB_SMS * 2), dim3(256), 0, st, *P, epoch, parity, b->den_grad, b->k0_grad,
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS * 2), dim3(256), 0, st, *P, epoch, parity, (const int32_t*)b->counters, CNT_DEN));
+    PVDB_LAUNCH_CHECK();
+    pvdb_prof_mark("dp_rs", st);
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_unpack, dim3(PVDB_SMS * 2), dim3(256), 0, st, *P, epoch, parity, b->den_grad, b->k0_grad,
                               (const int32_t*)b->den_touched_list, (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
-    pvdb_prof_mark("dp_reduce", st);
+    pvdb_prof_mark("dp_unpack", st);
     return PVDB_OK;
+}
+
+extern "C" int pvdb_dp_exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
+    return exchange_tiles(P, b, step, (cudaStream_t)stream, true, 1, true);
+}
+// The fused step's two halves: the union alone (flags already written by the emit kernel), and pack / reduce / unpack alone.
+int pvdb_dp_union_early(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st) {
+    return exchange_tiles(P, b, step, st, true, 0, false);
+}
+int pvdb_dp_move_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st) {
+    return exchange_tiles(P, b, step, st, false, 0, true);
+}
+int32_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step) {
+    return view(P->base[P->rank], P->n_leaf, P->cap_leaves).flags[step & 1];
+}
+// Arguments for the kernels that carry the rgbnet exchange of the fused step (dp_exchange.cuh).
+PvdbDpNetPush pvdb_dp_net_push_args(const pvdb_dp_peers* P, uint32_t step) {
+    PvdbDpNetPush a;
+    a.world = P->world; a.rank = P->rank; a.epoch = step + 1;
+    for (int r = 0; r < 8; ++r) {
+        const Blk b = view(P->base[r < P->world ? r : 0], P->n_leaf, P->cap_leaves);
+        a.dst[r] = b.netx[step & 1] + (size_t)P->rank * NET_PAD;
+        a.signal[r] = b.signal + SIG_C + P->rank;
+    }
+    a.done = view(P->base[P->rank], P->n_leaf, P->cap_leaves).done + 2;
+    return a;
+}
+PvdbDpNetWait pvdb_dp_net_wait_args(const pvdb_dp_peers* P, uint32_t step) {
+    PvdbDpNetWait a;
+    const Blk me = view(P->base[P->rank], P->n_leaf, P->cap_leaves);
+    a.world = P->world; a.epoch = step + 1;
+    a.src = me.netx[step & 1];
+    a.signal = me.signal + SIG_C;
+    a.err = me.err;
+    return a;
 }
 
 extern "C" int pvdb_dp_exchange_net(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {

@@ -24,4 +24,5 @@ int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, co
 // The two halves of the tensor-core backward (cfg->use_tensor_cores only): the data-parallel step exchanges the grid
 // gradients, which are final after the first half, underneath the second.
 int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
-int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st);
+struct PvdbDpNetPush;   // dp_exchange.cuh; nullptr outside a data-parallel step
+int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st, const PvdbDpNetPush* dp_push);

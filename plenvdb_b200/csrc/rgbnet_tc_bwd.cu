@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "rgbnet.cuh"
 #include "tc_ptx.cuh"
+#include "dp_exchange.cuh"
 
 namespace {
 
@@ -592,8 +593,11 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
 
 // net_grad[e] = sum over the CTAs' partials.  32 elements x 8 partial groups per CTA: every thread has all of its ~19 loads
 // in flight at once (one latency), 128-byte coalesced across the 32 elements.
-__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad) {
+// DP (push.world > 1): the sums also go straight into every rank's netx[parity][this rank] over NVLink and the last CTA
+// signals C — the rgbnet-gradient exchange of the data-parallel step has no kernel of its own (dp_exchange.cu).
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad, PvdbDpNetPush push) {
     __shared__ float red[8][32];
+    __shared__ bool last;
     pvdb_pdl_wait();
     const int e = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
     float a[19];
@@ -613,6 +617,21 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
 #pragma unroll
         for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
         net_grad[e] = t;
+        if (push.world > 1) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < push.world) push.dst[r][e] = t;
+        }
+    }
+    if (push.world > 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            last = atomicAdd(push.done, 1u) == gridDim.x - 1;
+            if (last) { *push.done = 0; __threadfence_system(); }
+        }
+        __syncthreads();
+        if (last && threadIdx.x < push.world) st_release_sys(push.signal[threadIdx.x], push.epoch);
     }
 }
 
@@ -680,7 +699,7 @@ int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs
 }
 
 // B2: weight gradients -> net_grad (overwritten)
-int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st) {
+int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st, const PvdbDpNetPush* dp_push) {
     if (int rc = bwd_attrs()) return rc;
     BwdWgradArgs W;
     W.k_h0 = b->k_h0; W.k_dh0 = b->k_dh0; W.k_x = b->k_x; W.k_h1 = b->k_h1; W.k_glogit = b->k_rgb;
@@ -703,12 +722,14 @@ int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bu
     W.use_tma = maps_ok && !no_tma;
     PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_bwd_wgrad_tc, dim3(PVDB_SMS), dim3(B2_THREADS), B2_TOTAL, st, W, maps));
     PVDB_LAUNCH_CHECK();
-    PVDB_CUDA(pvdb_launch_pdl(k_wgrad_reduce, dim3((PVDB_NET_N + 31) / 32), dim3(256), 0, st, (const float*)b->net_partial, (int)PVDB_SMS, b->net_grad));
+    PvdbDpNetPush push = {};
+    if (dp_push) push = *dp_push;
+    PVDB_CUDA(pvdb_launch_pdl(k_wgrad_reduce, dim3((PVDB_NET_N + 31) / 32), dim3(256), 0, st, (const float*)b->net_partial, (int)PVDB_SMS, b->net_grad, push));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }
 
 int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
     if (int rc = pvdb_rgbnet_backward_act_tc(cfg, b, viewdirs, st)) return rc;
-    return pvdb_rgbnet_backward_wgrad_tc(cfg, b, st);
+    return pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, nullptr);
 }

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "ray_math.cuh"
 #include "rgbnet.cuh"
+#include "dp_exchange.cuh"
 
 namespace {
 
@@ -111,7 +112,21 @@ struct MarchOut {
     // compaction instead of a second march.  Entry (ray, i) = 5 x 16 bytes at ((ray * scr_cap + i) * 5):
     // {step, x, y, z} {density, alpha, T, weight} {keep index, -, -, -} {corner ids 0-3} {corner ids 4-7}
     uint4* scratch; int scr_cap;
+    // data-parallel step only: this rank's touched-leaf flags in its symmetric block (dp_exchange.cu).  The sample lists
+    // determine the touched leaves before any gradient exists, so the cross-GPU union runs under the rgbnet forward.
+    int32_t* dp_flags;
 };
+
+// Flag the leaves of the eight corners of one alpha-list sample (every such sample feeds the density gradient, the kept ones
+// the k0 gradient as well).  Plain stores of 1: benign races.
+__device__ __forceinline__ void dp_flag_corners(int32_t* __restrict__ flags, const int* rec) {
+    int prev = -1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int leaf = rec[q] >> 9;      // -1 stays -1
+        if (rec[q] >= 0 && leaf != prev) { flags[leaf] = 1; prev = leaf; }
+    }
+}
 
 // One warp per ray.  MODE 0 = count, 1 = emit.  PARITY (count only): keep marching past the early stop so the
 // full M1 / M2 counts of the reference are produced too.
@@ -211,12 +226,13 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
             e[0] = make_uint4((uint32_t)step, __float_as_uint(x), __float_as_uint(y), __float_as_uint(z));
             e[1] = make_uint4(__float_as_uint(dens), __float_as_uint(alpha), __float_as_uint(myT), __float_as_uint(myW));
             e[2] = make_uint4((uint32_t)my_ki, 0u, 0u, 0u);
-            if (my_ki >= 0) {
+            if (my_ki >= 0 || O.dp_flags) {
                 e[3] = make_uint4((uint32_t)rec[0], (uint32_t)rec[1], (uint32_t)rec[2], (uint32_t)rec[3]);
                 e[4] = make_uint4((uint32_t)rec[4], (uint32_t)rec[5], (uint32_t)rec[6], (uint32_t)rec[7]);
             }
         }
         if (MODE == 1 && my_ai >= 0) {
+            if (O.dp_flags) dp_flag_corners(O.dp_flags, rec);
             const int64_t ia = oa + my_ai;
             if (ia < O.cap_alpha) {
                 O.s_ray[ia] = r; O.s_step[ia] = step;
@@ -295,6 +311,11 @@ __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O,
             O.s_T[ia] = __uint_as_float(e1.z); O.s_weight[ia] = __uint_as_float(e1.w);
         }
         const int ki = (int32_t)e2.x;
+        if (O.dp_flags) {
+            const uint4 c0 = e[3], c1 = e[4];
+            const int rec[8] = {(int)c0.x, (int)c0.y, (int)c0.z, (int)c0.w, (int)c1.x, (int)c1.y, (int)c1.z, (int)c1.w};
+            dp_flag_corners(O.dp_flags, rec);
+        }
         if (ki >= 0) {
             const int64_t ik = ok + ki;
             if (ik < O.cap_keep && ia < O.cap_alpha) {
@@ -621,6 +642,7 @@ struct UpdateArgs {
     float den_stepsz, k0_stepsz, net_stepsize, eps, b0, b1;
     int leaf_blocks;
     int block_offset;   // 0: leaf work starts at CTA 0; leaf_blocks: a launch of the rgbnet Adam CTAs only
+    PvdbDpNetWait dp;   // dp.world > 1: the rgbnet gradient is the rank-ordered sum of the world slots the peers pushed into this block
 };
 // Work items: (touched density leaf) and (touched k0 leaf, quarter); a persistent grid strides over them.
 __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
@@ -628,8 +650,17 @@ __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
     const int bid = (int)blockIdx.x + U.block_offset;
     if (bid >= U.leaf_blocks) {
         const int i = (bid - U.leaf_blocks) * blockDim.x + threadIdx.x;
+        if (U.dp.world > 1) {
+            if (threadIdx.x < U.dp.world) wait_epoch(U.dp.signal + threadIdx.x, U.dp.epoch, U.dp.err, 1);
+            __syncthreads();
+        }
         if (i < PVDB_NET_N) {
-            pvdb_dense_adam_update(U.net[i], U.net_m[i], U.net_v[i], U.net_g[i], 1.f, false, U.net_stepsize, U.b0, U.b1, U.eps);
+            float g = U.net_g[i];
+            if (U.dp.world > 1) {
+                g = __ldcg(U.dp.src + i);
+                for (int r = 1; r < U.dp.world; ++r) g += __ldcg(U.dp.src + (size_t)r * PVDB_DP_NET_PAD + i);
+            }
+            pvdb_dense_adam_update(U.net[i], U.net_m[i], U.net_v[i], g, 1.f, false, U.net_stepsize, U.b0, U.b1, U.eps);
             U.net_g[i] = 0.f;
         }
         return;
@@ -727,6 +758,7 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     O.counters = b->counters;
     O.scratch = reinterpret_cast<uint4*>(b->march_scratch);
     O.scr_cap = b->march_scratch ? b->scratch_per_ray : 0;
+    O.dp_flags = nullptr;
     return 0;
 }
 
@@ -842,7 +874,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     const int warp_grid = pvdb_grid_for((int64_t)n_rays * 32, 256);
     // Side stream for work that is independent of the main chain (weight-image prep under the march; the density branch of
     // the backward under the rgbnet backward).  Not used while per-kernel profiling is on (serial, clean per-kernel times).
-    struct Side { cudaStream_t s; cudaEvent_t fork, join, fork2, join2; bool ok; };
+    struct Side { cudaStream_t s; cudaEvent_t fork, join, fork2, join2, fork3, join3; bool ok; };
     static thread_local Side side[16] = {};
     int dev = 0;
     PVDB_CUDA(cudaGetDevice(&dev));
@@ -853,6 +885,8 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         PVDB_CUDA(cudaEventCreateWithFlags(&sd->join, cudaEventDisableTiming));
         PVDB_CUDA(cudaEventCreateWithFlags(&sd->fork2, cudaEventDisableTiming));
         PVDB_CUDA(cudaEventCreateWithFlags(&sd->join2, cudaEventDisableTiming));
+        PVDB_CUDA(cudaEventCreateWithFlags(&sd->fork3, cudaEventDisableTiming));
+        PVDB_CUDA(cudaEventCreateWithFlags(&sd->join3, cudaEventDisableTiming));
         sd->ok = true;
     }
 
@@ -870,6 +904,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     U.eps = cfg->eps; U.b0 = cfg->beta0; U.b1 = cfg->beta1;
     U.leaf_blocks = PVDB_SMS * 4;
     U.block_offset = 0;
+    U.dp = PvdbDpNetWait{};
     const int net_blocks = (PVDB_NET_N + 255) / 256;
     auto launch_update = [&](cudaStream_t s_, int part) -> int {
         UpdateArgs V = U;
@@ -880,6 +915,13 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         return PVDB_OK;
     };
     bool update_done = false;
+    // Fused data-parallel step: the emit kernel writes this rank's touched-leaf flags into its symmetric block, the union (with
+    // the cross-GPU barrier that absorbs the ranks' skew) runs on the side stream under the rgbnet forward, pack / reduce-scatter /
+    // unpack and the leaf Adam under the weight-gradient kernel, and the rgbnet gradients ride on the weight-gradient reduction
+    // (peer stores) and the rgbnet Adam (wait + rank-ordered sum).  Needs the side stream and the tensor-core backward;
+    // otherwise the stand-alone exchange runs after the backward.
+    const bool dp_fused = peers && sd && cfg->use_tensor_cores && do_fwd && do_bwd && do_upd;
+    if (dp_fused) O.dp_flags = pvdb_dp_flags_ptr(peers, dp_step);
 
     if (do_fwd) {
         PVDB_CHECK_ARG(rays_o && rays_d && viewdirs, "null rays");
@@ -914,6 +956,13 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
         int rc;
+        if (dp_fused) {      // side stream: union of the ranks' touched leaves (after the weight-image prep already queued there)
+            PVDB_CUDA(cudaEventRecord(sd->fork3, st));
+            PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork3, 0));
+            rc = pvdb_dp_union_early(peers, b, dp_step, sd->s);
+            if (rc) return rc;
+            PVDB_CUDA(cudaEventRecord(sd->join3, sd->s));
+        }
         if (sd) {
             PVDB_CUDA(cudaStreamWaitEvent(st, sd->join2, 0));
         } else {
@@ -961,12 +1010,15 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             // Everything that only needs them runs on the side stream UNDER the weight-gradient kernel: the NVLink tile
             // exchange of a data-parallel step, and the sparse Adam of the touched leaves.  After the weight-gradient kernel
             // only the 88 KB rgbnet exchange and the rgbnet Adam are left.
+            // dp_fused: the union list and the touched flags (all set) must be in place before the k0 scatter of the
+            // activation-gradient kernel looks at them
+            if (dp_fused) PVDB_CUDA(cudaStreamWaitEvent(st, sd->join3, 0));
             int rc = pvdb_rgbnet_backward_act_tc(cfg, b, viewdirs, st);
             if (rc) return rc;
             PVDB_CUDA(cudaEventRecord(sd->fork2, st));
             PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));
             if (peers) {
-                rc = pvdb_dp_exchange_tiles(peers, b, dp_step, sd->s);
+                rc = dp_fused ? pvdb_dp_move_tiles(peers, b, dp_step, sd->s) : pvdb_dp_exchange_tiles(peers, b, dp_step, sd->s);
                 if (rc) return rc;
             }
             if (do_upd) {
@@ -974,14 +1026,18 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                 if (rc) return rc;
             }
             PVDB_CUDA(cudaEventRecord(sd->join, sd->s));
-            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st);
+            PvdbDpNetPush push;
+            if (dp_fused) push = pvdb_dp_net_push_args(peers, dp_step);
+            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, dp_fused ? &push : nullptr);
             if (rc) return rc;
-            if (peers) {
+            if (peers && !dp_fused) {
                 rc = pvdb_dp_exchange_net(peers, b, dp_step, st);
                 if (rc) return rc;
             }
             if (do_upd) {
+                if (dp_fused) U.dp = pvdb_dp_net_wait_args(peers, dp_step);
                 rc = launch_update(st, 2);
+                U.dp = PvdbDpNetWait{};
                 if (rc) return rc;
                 update_done = true;
             }

@@ -115,8 +115,9 @@ class PeerExchange:
 class DataParallelTrainer:
     """FusedTrainer + the gradient exchange.  `n_rays` is the PER-RANK shard size.
 
-    exchange="nvlink" (default on CUDA): forward+backward -> pvdb_dp_exchange (device-side barrier, union of touched
-    leaves, pack, peer-read sum over NVLink; no NCCL, no host sync) -> the fused sparse Adam, identical on every rank.
+    exchange="nvlink" (default on CUDA): pvdb_train_step_dp — the union of the ranks' touched leaves (device-side barrier) runs
+    under the rgbnet forward, pack / reduce-scatter + all-gather over NVLink peer memory / unpack under the weight-gradient
+    kernel, the rgbnet gradients ride on the weight-gradient reduction; no NCCL, no host sync; identical bits on every rank.
     exchange="nccl": MAX all-reduce of the touched flags -> pvdb_dp_pack -> one host read of the union size -> ONE SUM
     all-reduce of the packed tiles + rgbnet gradients -> pvdb_dp_unpack -> update."""
 
@@ -195,8 +196,10 @@ class DataParallelTrainer:
     def exchange_bytes(self):
         """Bytes this rank moved over NVLink in the last exchange (peer reads, or the all-reduce payload)."""
         if self.peer is not None:
-            n = int(self.tr.t["counters"][2].item())
-            return (self.world - 1) * (n * 512 * 13 + 22019) * 4 + (self.world - 1) * self.tr.topo.n_leaf * 4
+            n, w = int(self.tr.t["counters"][2].item()), self.world
+            own = (n - self.peer.rank + w - 1) // w if n > self.peer.rank else 0       # union slots this rank reduces
+            tiles = 2 * (w - 1) * own * 512 * 13 * 4          # peer loads of the owned slots + peer stores of their sums
+            return tiles + (w - 1) * 22019 * 4 + (w - 1) * self.tr.topo.n_leaf * 4     # + rgbnet pushes + the peers' flags
         return self.last_exchange_bytes
 
     def close(self):

@@ -16,7 +16,7 @@ reproduce itself bit for bit either).  The error of such a sum
 |contributions|, not relative to the (possibly cancelling) result.  `_check_sum` therefore accepts an element when
     |got - want| <= 1e-5 * |want|   or   |got - want| <= 1e-5 * A,
 where A is the local magnitude scale of the plane: for density the sum over the voxel's samples of trilinear weight x the
-largest |dL/d density| on the sample's ray (see the comment at its use), for k0 / rgbnet the largest |gradient| of the tensor row the element belongs to (the
+sum of the |terms| of the sample's dL/d density (see the comment at its use), for k0 / rgbnet the largest |gradient| of the tensor row the element belongs to (the
 12 channels of the voxel's leaf / the weight matrix).  The test prints how many elements needed the second clause.
 """
 import os
@@ -134,18 +134,27 @@ def test_f160_8192_rays_whole_iteration_matches_the_oracle(f160):
     # gradients
     gd, wd = den.grad.cpu().numpy().reshape(-1), aux[0].get_values().reshape(-1)
     # exact sum of |contributions| per density voxel: scatter |dL/d density| of OUR alpha list with the oracle
-    # A sample's dL/d density = raw2alpha'(gw * T - back_cum / (1 - alpha)) is itself a DIFFERENCE whose second term is a running
-    # sum along the ray (alpha2weight_backward, render_utils_kernel.cu:654-677): its rounding error is absolute with respect to
-    # the largest term of the ray, so the magnitude each sample contributes to a voxel's scale is the largest |dL/d density| of
-    # its ray (not its own, possibly cancelled, value).
+    # A sample's dL/d density = alpha'(density) * (gw * T - back_cum / (1 - alpha)) is itself a DIFFERENCE whose second term is
+    # a running sum along the ray (alpha2weight_backward, render_utils_kernel.cu:654-677; raw2alpha_backward :507-517), fed by
+    # the rgbnet outputs (3xTF32 here, cuBLAS fp32 in the reference: ~1e-6 relative each).  The magnitude a sample contributes to
+    # a voxel's scale A is therefore the sum of the |terms| of that expression, alpha' * (|gw| T + (|g_last| ail + sum_later
+    # |gw w|) / (1 - alpha)), evaluated in float64 from the device lists — not the (possibly cancelled) value.
     ma = c["M_alpha"]
     sx = tr.t["s_xyz"][:ma].cpu().numpy()
-    sg = np.abs(tr.t["s_gden"][:ma].cpu().numpy())
     sr = tr.t["s_ray"][:ma].cpu().numpy()
-    ray_max = np.zeros(n, np.float32)
-    np.maximum.at(ray_max, sr, sg)
+    sw, sa, sT, sd = (tr.t[k][:ma].cpu().numpy().astype(np.float64) for k in ("s_weight", "s_alpha", "s_T", "s_density"))
+    gw = np.zeros(ma)
+    gw[t["k_sample"][:M3]] = tr.t["k_gw"][:M3].cpu().numpy()
+    cabs = np.abs(gw * sw)
+    S = np.cumsum(cabs)
+    seg_last = t["off_alpha"][1:n + 1].astype(np.int64) - 1                # last sample of each ray (valid where the ray has samples)
+    later = S[np.clip(seg_last, 0, ma - 1)][sr] - S                         # sum over the ray's LATER samples of |gw w|
+    glast = np.abs(tr.t["grad_last"][:n].cpu().numpy().astype(np.float64) * t["alphainv_last"].astype(np.float64))
+    ex = np.exp(sd + scene["act_shift"])
+    dalpha = scene["interval"] * ex * (1.0 + ex) ** (-scene["interval"] - 1.0)
+    mag = dalpha * (np.abs(gw) * sT + (glast[sr] + later) / np.maximum(1.0 - sa, 1e-10))
     absacc = orc.Grid(R, 1, act)
-    absacc.backward(sx[:, 0], sx[:, 1], sx[:, 2], ray_max[sr], threads=1)
+    absacc.backward(sx[:, 0], sx[:, 1], sx[:, 2], mag.astype(np.float32), threads=1)
     _check_sum(gd, wd, absacc.get_values().reshape(-1), "density grad")
     gk, wk = k0.grad.cpu().numpy().reshape(-1, 512 * 12), aux[3].get_values().reshape(-1, 512 * 12)
     _check_sum(gk, wk, np.abs(wk).max(1, keepdims=True), "k0 grad (per leaf)")
