@@ -646,7 +646,8 @@ def run_render_f160(args, net, dev, rank, world):
                          "rgb_within_1e-5": rgb_ok, "reference_inconsistent_rays": int(bad)}
         if not out["parity"]["ok"]:
             log("[bench] RENDER PARITY FAILURE against the oracle: %s" % out["parity"])
-    out.pop("_renderer", None)
+    if out is not None:
+        out.pop("_renderer", None)
     return out
 
 

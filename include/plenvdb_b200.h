@@ -225,6 +225,9 @@ typedef struct pvdb_train_bufs {
 int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs,
                     const float* rays_o, const float* rays_d, const float* viewdirs, const float* target,
                     int n_rays, int phases, void* stream);
+/* Test switch: 0 makes the march of pvdb_train_step test the occupancy of every step one by one instead of skipping runs of
+ * steps that provably cannot hit the mask (the results are bit-identical either way; default 1). */
+void pvdb_debug_set_run_skip(int on);
 /* Data-parallel gradient exchange (no counterpart in the reference, which is single-GPU).  Call after the ranks' touched
  * flags (bufs->den_touched / k0_touched) were MAX-all-reduced: builds the union leaf list on the device, copies its
  * length to *union_count_host (pinned; valid after the stream is synchronised) and packs the union leaves' gradient

@@ -162,6 +162,7 @@ _SIGS = {
     "pvdb_plane_remap": (None, [_TP, c_ptr, _TP, c_ptr, _i, c_ptr]),
     "pvdb_occupancy_update": (None, [_TP, c_ptr, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f, _f, _f, c_ptr, _i, _i, _i, c_ptr, c_ptr]),
     "pvdb_total_variation_add_grad": (None, [_TP, c_ptr, c_ptr, _i, _i, _i, _i, _f, _f, _f, _i, c_ptr]),
+    "pvdb_debug_set_run_skip": (None, [_i]),
     "pvdb_profile_enable": (None, [_i]),
     "pvdb_profile_fetch": (C.c_int, [_i, c_ptr, c_ptr]),
     "pvdb_rays_hit_mask": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, _i, c_ptr, c_ptr]),

@@ -37,6 +37,7 @@ struct MarchParams {
     int nb[3];                    // blocks of the occupancy bit grid
     float mask_scale[3], mask_shift[3];
     float near, far, stepdist, act_shift, interval, thres;
+    int run_skip;                 // pass A skips runs of steps that cannot hit the mask (bit-identical; 0 = test every step)
 };
 
 __device__ __forceinline__ bool occ_test(const MarchParams& P, int i, int j, int k) {
@@ -96,6 +97,46 @@ __device__ __forceinline__ float density_at(const MarchParams& P, float x, float
     return acc;
 }
 
+// One step of the reference's sampler + mask lookup (sample_pts_on_rays :181-192, maskcache_lookup :385-395): is the step's
+// point inside the bounding box and in an occupied mask voxel?
+__device__ __forceinline__ bool step_in_mask(const MarchParams& P, const float* st, const float* dir, int step) {
+    float px, py, pz;
+    pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, step, px, py, pz);
+    const bool outb = (P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) | (P.xyz_max[0] < px) |
+                      (P.xyz_max[1] < py) | (P.xyz_max[2] < pz);
+    if (outb) return false;
+    return occ_test(P, pvdb_mask_ijk(px, P.mask_scale[0], P.mask_shift[0]), pvdb_mask_ijk(py, P.mask_scale[1], P.mask_shift[1]),
+                    pvdb_mask_ijk(pz, P.mask_scale[2], P.mask_shift[2]));
+}
+
+// Can any step of the run [a, b] be in the mask?  Exact, not a heuristic: the point of step i is ONE rounding of a function
+// that is monotone in i per axis (dist = fl(stepdist * i); p = fl(fma(dir, dist, start))), and the mask index is one more
+// rounding of a monotone function of p (roundf(fl(fma(p, scale, shift))), scale > 0), so per axis every step of the run has its
+// mask index between those of the two end steps.  A step is in the mask only if its voxel's bit is set, which requires the
+// coarse bit of its 8^3 block: when no block of the index box spanned by the two ends has its coarse bit set, no step of the run
+// passes occ_test, whatever the bounding-box test says.
+__device__ __forceinline__ bool run_may_hit(const MarchParams& P, const float* st, const float* dir, int a, int b) {
+    float pa[3], pb[3];
+    pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, a, pa[0], pa[1], pa[2]);
+    pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, b, pb[0], pb[1], pb[2]);
+    int lo[3], hi[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const int ia = pvdb_mask_ijk(pa[ax], P.mask_scale[ax], P.mask_shift[ax]), ib = pvdb_mask_ijk(pb[ax], P.mask_scale[ax], P.mask_shift[ax]);
+        lo[ax] = max(min(ia, ib), 0);
+        hi[ax] = min(max(ia, ib), P.mask_reso[ax] - 1);
+        if (lo[ax] > hi[ax]) return false;
+        lo[ax] >>= 3; hi[ax] >>= 3;
+    }
+    for (int bx = lo[0]; bx <= hi[0]; ++bx)
+        for (int by = lo[1]; by <= hi[1]; ++by)
+            for (int bz = lo[2]; bz <= hi[2]; ++bz) {
+                const int blk = (bx * P.nb[1] + by) * P.nb[2] + bz;
+                if ((__ldg(P.occ_coarse + (blk >> 6)) >> (blk & 63)) & 1ull) return true;
+            }
+    return false;
+}
+
 struct MarchOut {
     // per ray
     float* t_min; float* t_max; int32_t* n_steps;
@@ -146,27 +187,53 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
     int64_t oa = 0, ok = 0;
     if (MODE == 1) { oa = O.off_alpha[r]; ok = O.off_keep[r]; }
 
-    // Two passes per segment of 1024 steps.  Pass A only tests occupancy (most steps are in empty space) and leaves one
-    // 32-step ballot word in each lane; pass B then visits the in-mask steps 32 at a time, in step order, so the expensive
-    // part (trilinear density, activation) runs with full lanes instead of the 2-3 live lanes a plain 32-step sweep has.
+    // Per segment of 1024 steps: pass A finds the in-mask steps (one 32-step ballot word per lane), pass B visits them 32 at a
+    // time, in step order, so the expensive part (trilinear density, activation) runs with full lanes instead of the 2-3 live
+    // lanes a plain 32-step sweep has.
+    // Pass A is itself two-level (most steps are in empty space: 355 steps per ray, 17 of them in the mask at F160).  A0: one
+    // lane per RUN of 8 consecutive steps asks whether the run can hit the mask at all — run_may_hit, exact, see there.  A1: only
+    // the steps of the runs that can are tested one by one, four runs per warp iteration.  Same bits as testing every step.
     for (int seg = 0; seg < nsteps && !(stopped && !PARITY); seg += 1024) {
         unsigned myword = 0;
-        const int n_it = min(32, (nsteps - seg + 31) >> 5);
-        for (int it = 0; it < n_it; ++it) {
-            const int step = seg + it * 32 + lane;
-            bool in_mask = false;
-            if (step < nsteps) {
-                float px, py, pz;
-                pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, step, px, py, pz);
-                const bool outb = (P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) | (P.xyz_max[0] < px) |
-                                  (P.xyz_max[1] < py) | (P.xyz_max[2] < pz);
-                if (!outb)
-                    in_mask = occ_test(P, pvdb_mask_ijk(px, P.mask_scale[0], P.mask_shift[0]),
-                                       pvdb_mask_ijk(py, P.mask_scale[1], P.mask_shift[1]),
-                                       pvdb_mask_ijk(pz, P.mask_scale[2], P.mask_shift[2]));
+        if (P.run_skip) {
+            const int n_runs = (min(1024, nsteps - seg) + 7) >> 3;      // <= 128
+            unsigned rw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                if (it * 32 < n_runs) {
+                    const int run = it * 32 + lane;
+                    bool maybe = false;
+                    if (run < n_runs) maybe = run_may_hit(P, st, dir, seg + run * 8, min(seg + run * 8 + 7, nsteps - 1));
+                    rw[it] = __ballot_sync(0xffffffffu, maybe);
+                }
             }
-            const unsigned bits = __ballot_sync(0xffffffffu, in_mask);
-            if (lane == it) myword = bits;
+            const int c0 = __popc(rw[0]), c1 = c0 + __popc(rw[1]), c2 = c1 + __popc(rw[2]), n_flag = c2 + __popc(rw[3]);
+            for (int f0 = 0; f0 < n_flag; f0 += 4) {
+                const int f = f0 + (lane >> 3);
+                int run = -1;
+                if (f < n_flag) {
+                    const int k = (f >= c0) + (f >= c1) + (f >= c2);
+                    const int base = k == 0 ? 0 : k == 1 ? c0 : k == 2 ? c1 : c2;
+                    const unsigned w = k == 0 ? rw[0] : k == 1 ? rw[1] : k == 2 ? rw[2] : rw[3];
+                    run = k * 32 + (int)__fns(w, 0, f - base + 1);
+                }
+                const int step = seg + run * 8 + (lane & 7);
+                const bool in_mask = run >= 0 && step < nsteps && step_in_mask(P, st, dir, step);
+                const unsigned bits = __ballot_sync(0xffffffffu, in_mask);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int rg = __shfl_sync(0xffffffffu, run, g * 8);
+                    if (rg >= 0 && lane == (rg >> 2)) myword |= ((bits >> (g * 8)) & 0xffu) << ((rg & 3) * 8);
+                }
+            }
+        } else {
+            const int n_it = min(32, (nsteps - seg + 31) >> 5);
+            for (int it = 0; it < n_it; ++it) {
+                const int step = seg + it * 32 + lane;
+                const bool in_mask = step < nsteps && step_in_mask(P, st, dir, step);
+                const unsigned bits = __ballot_sync(0xffffffffu, in_mask);
+                if (lane == it) myword = bits;
+            }
         }
         const int cnt = __popc(myword);
         int incl = cnt;
@@ -347,17 +414,7 @@ __global__ void __launch_bounds__(256) k_hit_mask(MarchParams P, const float* __
     bool any = false;
     for (int base = 0; base < nsteps && !any; base += 32) {
         const int step = base + lane;
-        bool in_mask = false;
-        if (step < nsteps) {
-            float px, py, pz;
-            pvdb_ray_point(st[0], st[1], st[2], dir[0], dir[1], dir[2], P.stepdist, step, px, py, pz);
-            const bool outb = (P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) | (P.xyz_max[0] < px) |
-                              (P.xyz_max[1] < py) | (P.xyz_max[2] < pz);
-            if (!outb)
-                in_mask = occ_test(P, pvdb_mask_ijk(px, P.mask_scale[0], P.mask_shift[0]),
-                                   pvdb_mask_ijk(py, P.mask_scale[1], P.mask_shift[1]),
-                                   pvdb_mask_ijk(pz, P.mask_scale[2], P.mask_shift[2]));
-        }
+        const bool in_mask = step < nsteps && step_in_mask(P, st, dir, step);
         any = __ballot_sync(0xffffffffu, in_mask) != 0;
     }
     if (lane == 0) hit[r] = any ? 1 : 0;
@@ -734,6 +791,10 @@ extern "C" int pvdb_occ_build(const uint8_t* mask, int rx, int ry, int rz, uint6
     return PVDB_OK;
 }
 
+// test switch (pvdb_debug_set_run_skip): 0 = pass A of the march tests every step one by one
+static int g_run_skip = 1;
+extern "C" void pvdb_debug_set_run_skip(int on) { g_run_skip = on ? 1 : 0; }
+
 static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, MarchParams& P, MarchOut& O) {
     P.tree = *b->tree;
     P.den = b->den;
@@ -748,6 +809,7 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     }
     P.near = cfg->near; P.far = cfg->far; P.stepdist = cfg->stepdist; P.act_shift = cfg->act_shift;
     P.interval = cfg->interval; P.thres = cfg->fast_color_thres;
+    P.run_skip = g_run_skip;
     O.t_min = b->t_min; O.t_max = b->t_max; O.n_steps = b->n_steps;
     O.cnt_mask = b->cnt_mask; O.cnt_alpha = b->cnt_alpha; O.cnt_keep = b->cnt_keep; O.cnt_alpha_full = b->cnt_alpha_full;
     O.off_alpha = b->off_alpha; O.off_keep = b->off_keep; O.alphainv_last = b->alphainv_last;

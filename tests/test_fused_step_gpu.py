@@ -175,6 +175,37 @@ def test_emit_by_compaction_equals_second_march(scratch_per_ray, small):
     assert torch.equal(ref.t["rgb_marched"], alt.t["rgb_marched"])
 
 
+@pytest.mark.parametrize("parity_counts", [False, True])
+def test_run_skip_of_the_march_is_bit_identical(parity_counts, small):
+    """Pass A of the march skips runs of 8 steps that provably cannot hit the mask (train_step.cu: run_may_hit).  With the skip
+    switched off every step is tested one by one like the reference does (render_utils_kernel.cu:181-192, 385-395): the per-ray
+    counts (incl. the in-mask count of every ray), both sample lists and the rendered colours must be the same bits."""
+    from plenvdb_b200 import _lib
+    scene, net, rays = small
+    rays_d = [_cu(a) for a in rays]
+    res = []
+    try:
+        for on in (1, 0):
+            _lib.lib.pvdb_debug_set_run_skip(on)
+            tr, *_ = _trainer(scene, net, 2048, parity_counts=parity_counts)
+            tr.forward(*rays_d[:3])
+            torch.cuda.synchronize()
+            res.append(tr)
+    finally:
+        _lib.lib.pvdb_debug_set_run_skip(1)
+    a, b = res
+    ca, cb = a.counters(), b.counters()
+    assert ca == cb and ca["M_alpha"] > 1000
+    ma, mk = ca["M_alpha"], ca["M_keep"]
+    for k in ("n_steps", "cnt_mask", "cnt_alpha", "cnt_keep", "cnt_alpha_full", "off_alpha", "off_keep", "alphainv_last", "rgb_marched"):
+        assert torch.equal(a.t[k], b.t[k]), k
+    assert int(a.t["cnt_mask"].sum()) > ma
+    for k in ("s_ray", "s_step", "s_xyz", "s_density", "s_alpha", "s_T", "s_weight"):
+        assert torch.equal(a.t[k][:ma], b.t[k][:ma]), k
+    for k in ("k_sample", "k_ray", "k_xyz", "k_corner", "k_rgb"):
+        assert torch.equal(a.t[k][:mk], b.t[k][:mk]), k
+
+
 def test_stress_scene_properties():
     """Shell scene on a pruned topology built on the device (the S512 configuration of SURVEY.md §8d at 192^3 so that it runs
     in seconds), inverse_y cameras.  No oracle at this size: size-independent properties instead —

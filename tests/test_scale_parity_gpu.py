@@ -134,25 +134,29 @@ def test_f160_8192_rays_whole_iteration_matches_the_oracle(f160):
     # gradients
     gd, wd = den.grad.cpu().numpy().reshape(-1), aux[0].get_values().reshape(-1)
     # exact sum of |contributions| per density voxel: scatter |dL/d density| of OUR alpha list with the oracle
-    # A sample's dL/d density = alpha'(density) * (gw * T - back_cum / (1 - alpha)) is itself a DIFFERENCE whose second term is
-    # a running sum along the ray (alpha2weight_backward, render_utils_kernel.cu:654-677; raw2alpha_backward :507-517), fed by
-    # the rgbnet outputs (3xTF32 here, cuBLAS fp32 in the reference: ~1e-6 relative each).  The magnitude a sample contributes to
-    # a voxel's scale A is therefore the sum of the |terms| of that expression, alpha' * (|gw| T + (|g_last| ail + sum_later
-    # |gw w|) / (1 - alpha)), evaluated in float64 from the device lists — not the (possibly cancelled) value.
+    # A sample's dL/d density = alpha'(density) * (gw * T - back_cum / (1 - alpha)) is a chain of DIFFERENCES: gw = sum_c rgb_c *
+    # g_marched_c with g_marched = 2 (marched - target) / 3N (marched ~ target cancels), back_cum = g_last * ail + the running sum
+    # of gw * w over the ray's later samples (alpha2weight_backward, render_utils_kernel.cu:654-677; raw2alpha_backward :507-517),
+    # all fed by the rgbnet outputs (3xTF32 here, cuBLAS fp32 in the reference: ~1e-6 relative each).  The magnitude a sample
+    # contributes to a voxel's scale A is therefore the sum of the |terms| of that whole expression, evaluated in float64 from
+    # the device lists and the oracle's colours — not the (possibly cancelled) value.
     ma = c["M_alpha"]
     sx = tr.t["s_xyz"][:ma].cpu().numpy()
     sr = tr.t["s_ray"][:ma].cpu().numpy()
     sw, sa, sT, sd = (tr.t[k][:ma].cpu().numpy().astype(np.float64) for k in ("s_weight", "s_alpha", "s_T", "s_density"))
-    gw = np.zeros(ma)
-    gw[t["k_sample"][:M3]] = tr.t["k_gw"][:M3].cpu().numpy()
-    cabs = np.abs(gw * sw)
+    ail = t["alphainv_last"].astype(np.float64)
+    Gc = (2.0 / (3.0 * n)) * (np.abs(o["rgb_marched"].astype(np.float64)) + np.abs(rays[3].astype(np.float64)))      # [n, 3] >= |g_marched|
+    gwmag = np.zeros(ma)
+    gwmag[t["k_sample"][:M3]] = (o["keep_rgb"].astype(np.float64) * Gc[o["keep_ray"]]).sum(1)
+    cabs = gwmag * sw
     S = np.cumsum(cabs)
     seg_last = t["off_alpha"][1:n + 1].astype(np.int64) - 1                # last sample of each ray (valid where the ray has samples)
-    later = S[np.clip(seg_last, 0, ma - 1)][sr] - S                         # sum over the ray's LATER samples of |gw w|
-    glast = np.abs(tr.t["grad_last"][:n].cpu().numpy().astype(np.float64) * t["alphainv_last"].astype(np.float64))
+    later = S[np.clip(seg_last, 0, ma - 1)][sr] - S                         # sum over the ray's LATER samples of |gw| w
+    pc = np.clip(ail, 1e-6, 1 - 1e-6)
+    glast = (Gc.sum(1) * scene["bg"] + scene["weight_entropy_last"] * np.abs(np.log(pc) - np.log(1 - pc)) / n) * ail
     ex = np.exp(sd + scene["act_shift"])
     dalpha = scene["interval"] * ex * (1.0 + ex) ** (-scene["interval"] - 1.0)
-    mag = dalpha * (np.abs(gw) * sT + (glast[sr] + later) / np.maximum(1.0 - sa, 1e-10))
+    mag = dalpha * (gwmag * sT + (glast[sr] + later) / np.maximum(1.0 - sa, 1e-10))
     absacc = orc.Grid(R, 1, act)
     absacc.backward(sx[:, 0], sx[:, 1], sx[:, 2], mag.astype(np.float32), threads=1)
     _check_sum(gd, wd, absacc.get_values().reshape(-1), "density grad")
