@@ -71,7 +71,7 @@ class pvdb_train_bufs(C.Structure):
         ("k_corner", c_ptr), ("net_img", c_ptr), ("net_partial", c_ptr),
         ("march_scratch", c_ptr), ("scratch_rays", C.c_int32), ("scratch_per_ray", C.c_int32),
         ("den_touched", c_ptr), ("k0_touched", c_ptr), ("den_touched_list", c_ptr), ("k0_touched_list", c_ptr),
-        ("counters", c_ptr), ("loss", c_ptr),
+        ("counters", c_ptr), ("loss", c_ptr), ("step_scalars", c_ptr),
     ]
 
 
@@ -163,6 +163,7 @@ _SIGS = {
     "pvdb_occupancy_update": (None, [_TP, c_ptr, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f, _f, _f, c_ptr, _i, _i, _i, c_ptr, c_ptr]),
     "pvdb_total_variation_add_grad": (None, [_TP, c_ptr, c_ptr, _i, _i, _i, _i, _f, _f, _f, _i, c_ptr]),
     "pvdb_debug_set_run_skip": (None, [_i]),
+    "pvdb_dense_adam_stepsize_host": (C.c_float, [_f, _f, _f, _i]),
     "pvdb_profile_enable": (None, [_i]),
     "pvdb_profile_fetch": (C.c_int, [_i, c_ptr, c_ptr]),
     "pvdb_rays_hit_mask": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, _i, c_ptr, c_ptr]),

@@ -17,6 +17,7 @@
 //
 // The per-sample arithmetic is shared with the drop-in ops through ray_math.cuh / common.cuh, so sample
 // counts, segment offsets and voxel indices are the reference's bit for bit.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ray_math.cuh"
 #include "rgbnet.cuh"
@@ -699,6 +700,7 @@ struct UpdateArgs {
     float den_stepsz, k0_stepsz, net_stepsize, eps, b0, b1;
     int leaf_blocks;
     int block_offset;   // 0: leaf work starts at CTA 0; leaf_blocks: a launch of the rgbnet Adam CTAs only
+    const float* scalars;   // optional device array {den_stepsz, k0_stepsz, net_stepsize}: overrides the three values above (CUDA-graph replay)
     PvdbDpNetWait dp;   // dp.world > 1: the rgbnet gradient is the rank-ordered sum of the world slots the peers pushed into this block
 };
 // Work items: (touched density leaf) and (touched k0 leaf, quarter); a persistent grid strides over them.
@@ -717,7 +719,7 @@ __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
                 g = __ldcg(U.dp.src + i);
                 for (int r = 1; r < U.dp.world; ++r) g += __ldcg(U.dp.src + (size_t)r * PVDB_DP_NET_PAD + i);
             }
-            pvdb_dense_adam_update(U.net[i], U.net_m[i], U.net_v[i], g, 1.f, false, U.net_stepsize, U.b0, U.b1, U.eps);
+            pvdb_dense_adam_update(U.net[i], U.net_m[i], U.net_v[i], g, 1.f, false, U.scalars ? __ldg(U.scalars + 2) : U.net_stepsize, U.b0, U.b1, U.eps);
             U.net_g[i] = 0.f;
         }
         return;
@@ -729,7 +731,7 @@ __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
         const int leaf = is_den ? U.den_list[w] : U.k0_list[(w - nd) >> 2];
         const int part = is_den ? 0 : (w - nd) & 3;
         float *p = is_den ? U.den : U.k0, *g = is_den ? U.den_g : U.k0_g, *m = is_den ? U.den_m : U.k0_m, *v = is_den ? U.den_v : U.k0_v;
-        const float stepsz = is_den ? U.den_stepsz : U.k0_stepsz;
+        const float stepsz = U.scalars ? __ldg(U.scalars + (is_den ? 0 : 1)) : (is_den ? U.den_stepsz : U.k0_stepsz);
         const int C = is_den ? 1 : 12, G = is_den ? 1 : 3, ngrp = C / G;
         // density: 512 voxels by 256 threads (2 each); k0 quarter: 128 voxels x 4 groups = 512 items (2 each)
         for (int e = threadIdx.x; e < 512; e += blockDim.x) {
@@ -792,8 +794,12 @@ extern "C" int pvdb_occ_build(const uint8_t* mask, int rx, int ry, int rz, uint6
 }
 
 // test switch (pvdb_debug_set_run_skip): 0 = pass A of the march tests every step one by one
-static int g_run_skip = 1;
+static int g_run_skip = -1;     // -1: not decided yet (environment PVDB_RUN_SKIP, else the default)
 extern "C" void pvdb_debug_set_run_skip(int on) { g_run_skip = on ? 1 : 0; }
+
+// The rgbnet Adam step size (adam_upd_kernel.cu:72) as the fused step computes it from cfg->net_lr / net_step: exported so that a
+// caller who feeds pvdb_train_bufs.step_scalars (CUDA-graph replay) writes the same bits.
+extern "C" float pvdb_dense_adam_stepsize_host(float lr, float beta0, float beta1, int step) { return pvdb_dense_adam_stepsize(lr, beta0, beta1, step); }
 
 static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, MarchParams& P, MarchOut& O) {
     P.tree = *b->tree;
@@ -809,6 +815,7 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     }
     P.near = cfg->near; P.far = cfg->far; P.stepdist = cfg->stepdist; P.act_shift = cfg->act_shift;
     P.interval = cfg->interval; P.thres = cfg->fast_color_thres;
+    if (g_run_skip < 0) { const char* e = getenv("PVDB_RUN_SKIP"); g_run_skip = e ? (atoi(e) != 0) : 1; }
     P.run_skip = g_run_skip;
     O.t_min = b->t_min; O.t_max = b->t_max; O.n_steps = b->n_steps;
     O.cnt_mask = b->cnt_mask; O.cnt_alpha = b->cnt_alpha; O.cnt_keep = b->cnt_keep; O.cnt_alpha_full = b->cnt_alpha_full;
@@ -967,6 +974,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     U.leaf_blocks = PVDB_SMS * 4;
     U.block_offset = 0;
     U.dp = PvdbDpNetWait{};
+    U.scalars = b->step_scalars;
     const int net_blocks = (PVDB_NET_N + 255) / 256;
     auto launch_update = [&](cudaStream_t s_, int part) -> int {
         UpdateArgs V = U;

@@ -46,7 +46,7 @@ def get_rays_of_a_view(H, W, K, c2w, inverse_y=False, flip_x=False, flip_y=False
 class FusedTrainer:
     def __init__(self, params, density, k0, mask, net, n_rays, device="cuda", use_tensor_cores=True,
                  cap_alpha_per_ray=96, cap_keep_per_ray=64, parity_counts=False, n_rays_global=None,
-                 scratch_per_ray=128):
+                 scratch_per_ray=128, use_graph=True):
         """params: dict from synth.scene_params (or the equivalent run.py scalars).
         density: DensityVDB, k0: ColorVDB(12) on the SAME topology (k0.topo is density.topo).
         mask: bool [reso] mask_cache.mask.  net: float32[22019] packed rgbnet parameters."""
@@ -103,6 +103,9 @@ class FusedTrainer:
         self.parity_counts = bool(parity_counts)
         self.n_rays_global = int(n_rays_global) if n_rays_global else self.n_rays
         self._bufs = None
+        self._scal_dev = self._scal_host = None     # device copy / pinned ring of the per-iteration scalars (CUDA-graph replay)
+        self._graph = None
+        self.use_graph = bool(use_graph)
         self._build_structs()
 
     # ---- state
@@ -157,7 +160,9 @@ class FusedTrainer:
         for k, t in self.t.items():
             setattr(b, k, p(t))
         b.scratch_rays, b.scratch_per_ray = self.n_rays, self.scratch_per_ray
+        b.step_scalars = self._scal_dev.data_ptr() if self._scal_dev is not None else None
         self._bufs = b
+        self._graph = None          # a captured graph holds the old pointers
 
     def _set_step_scalars(self):
         s = self.step_count
@@ -165,6 +170,48 @@ class FusedTrainer:
         self.cfg.k0_stepsz = _lib.lib.pvdb_adam_stepsize(self.lr_k0, self.P["beta0"], self.P["beta1"], s)
         self.cfg.net_lr = self.lr_net
         self.cfg.net_step = s
+        if self._scal_dev is not None:
+            # the update kernels read the scalars from device memory (pvdb_train_bufs.step_scalars): copy this iteration's values
+            # there in stream order, from a pinned ring (at most two or three iterations are ever in flight)
+            h = self._scal_host[s % self._scal_host.shape[0]]
+            h[0], h[1] = self.cfg.den_stepsz, self.cfg.k0_stepsz
+            h[2] = _lib.lib.pvdb_dense_adam_stepsize_host(self.lr_net, self.P["beta0"], self.P["beta1"], s)
+            self._scal_dev.copy_(h, non_blocking=True)
+
+    def _enable_step_scalars(self):
+        if self._scal_dev is None:
+            self._scal_dev = torch.zeros(4, dtype=torch.float32, device=self.dev)
+            self._scal_host = torch.zeros((8, 4), dtype=torch.float32).pin_memory()
+            self._bufs.step_scalars = self._scal_dev.data_ptr()
+
+    def _step_graphed(self, stage):
+        """One full iteration on the staging buffer `stage` [4, n, 3] as a CUDA-graph replay: the ~25 launches, events and the
+        side-stream fork / join of pvdb_train_step cost the host ~95 us when issued one by one, a replay ~10 us.  The graph is
+        captured on the second call for a staging buffer (the first runs directly, which also initialises everything the
+        library creates lazily); the per-iteration scalars travel through pvdb_train_bufs.step_scalars."""
+        key = (stage.data_ptr(), stage.shape[1])
+        g = self._graph
+        if g is None or g["key"] != key:                 # first call for this buffer: run directly
+            self._enable_step_scalars()
+            self._graph = dict(key=key, graph=None)
+            self.step(stage[0], stage[1], stage[2], stage[3])
+            return
+        if g["graph"] is None:                           # second call: capture, then replay once for this iteration
+            graph = torch.cuda.CUDAGraph()
+            self.step_count += 1
+            self._set_step_scalars()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(stage[0]), _lib.ptr(stage[1]),
+                          _lib.ptr(stage[2]), _lib.ptr(stage[3]), stage.shape[1], PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE,
+                          _lib.current_stream())
+            g["graph"], g["launches"] = graph, int(_lib.lib.pvdb_last_launch_count())
+            graph.replay()          # the capture itself executed nothing
+            self.launches_total += g["launches"]
+            return
+        self.step_count += 1
+        self._set_step_scalars()
+        g["graph"].replay()
+        self.launches_total += g["launches"]
 
     def decay_lr(self, factor):
         """run.py:592-598: multiply every lr by `factor` (float32 for the grids, like the C++ members)."""
@@ -200,7 +247,10 @@ class FusedTrainer:
             self._stage = torch.empty((4, n, 3), dtype=torch.float32, device=self.dev)
             self._loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
         self._stage.copy_(batch_host, non_blocking=True)
-        (stepper or self.step)(self._stage[0], self._stage[1], self._stage[2], self._stage[3])
+        if stepper is None and self.use_graph:
+            self._step_graphed(self._stage)
+        else:
+            (stepper or self.step)(self._stage[0], self._stage[1], self._stage[2], self._stage[3])
         self._loss_host.copy_(self.t["loss"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._loss_host

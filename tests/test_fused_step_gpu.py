@@ -335,6 +335,36 @@ def test_host_pipeline_matches_synchronous_steps(small):
     np.testing.assert_allclose(k0_b.grid.cpu().numpy(), k0_a.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
 
 
+def test_graph_replay_drives_the_same_iterations(small):
+    """step_from_host replays a CUDA graph of the whole iteration from its third call on (the per-iteration Adam step sizes
+    travel through pvdb_train_bufs.step_scalars): same losses and parameters as issuing every kernel directly, including the
+    bias corrections of later steps and an lr decay in between."""
+    scene, net, rays = small
+    rng = np.random.default_rng(4)
+    batches = []
+    for _ in range(7):
+        perm = rng.permutation(2048)[:1024]
+        batches.append(torch.from_numpy(np.stack([a[perm] for a in rays], 0).copy()).pin_memory())   # [4, 1024, 3]
+    tr_a, den_a, k0_a = _trainer(scene, net, 1024, use_graph=False)
+    tr_b, den_b, k0_b = _trainer(scene, net, 1024, use_graph=True)
+    la, lb = [], []
+    for i, b in enumerate(batches):
+        if i == 4:
+            tr_a.decay_lr(0.5)
+            tr_b.decay_lr(0.5)
+        la.append(tr_a.step_from_host(b).clone())
+        lb.append(tr_b.step_from_host(b).clone())
+    assert tr_b._graph is not None and tr_b._graph["graph"] is not None and tr_a._graph is None
+    assert tr_a.step_count == tr_b.step_count == 7 and tr_a.launches_total == tr_b.launches_total
+    for x, y in zip(la, lb):
+        np.testing.assert_allclose(y.numpy(), x.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(tr_b.net.cpu().numpy(), tr_a.net.cpu().numpy(), rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(den_b.grid.cpu().numpy(), den_a.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(k0_b.grid.cpu().numpy(), k0_a.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
+    # the moments carry the step sizes' history: a stale bias correction would show here first
+    np.testing.assert_allclose(tr_b.net_m.cpu().numpy(), tr_a.net_m.cpu().numpy(), rtol=1e-3, atol=1e-7)
+
+
 def test_render_view_equals_the_forward_phase_on_the_same_rays():
     """The non-merged render path (run.py:171-189): FusedTrainer.render_view = get_rays_of_a_view + the forward phase in
     batch-sized chunks, bit for bit."""
