@@ -216,7 +216,7 @@ typedef struct pvdb_train_bufs {
     int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0,
                                                 * 5 ray ticket of the count pass (zero between steps) */
     float *loss;                               /* [4]: total, mse, entropy_last, rgbper */
-    const float *step_scalars;                 /* optional DEVICE array [4]: den_stepsz, k0_stepsz, rgbnet Adam step size (lr with the
+    const float *step_scalars;                 /* optional device-readable array [4] (device memory or pinned host memory): den_stepsz, k0_stepsz, rgbnet Adam step size (lr with the
                                                 * bias corrections, pvdb_dense_adam_stepsize), reserved.  When non-NULL the update
                                                 * kernels read the per-iteration scalars from here instead of cfg, so that a captured
                                                 * CUDA graph of the step can be replayed for every iteration */
@@ -229,6 +229,10 @@ typedef struct pvdb_train_bufs {
 int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs,
                     const float* rays_o, const float* rays_d, const float* viewdirs, const float* target,
                     int n_rays, int phases, void* stream);
+/* Gather a batch ([n][3] arrays anywhere in device memory; target may be NULL) into one staging buffer [4][n][3] with a single
+ * launch, so that a captured CUDA graph of pvdb_train_step can read its inputs from fixed addresses. */
+int pvdb_stage_rays(const float* rays_o, const float* rays_d, const float* viewdirs, const float* target, int n_rays, float* stage,
+                    void* stream);
 /* rgbnet Adam step size, lr * sqrt(1 - beta1^step) / (1 - beta0^step) in float (adam_upd_kernel.cu:72): what the fused step
  * derives from cfg->net_lr / net_step, for callers that feed pvdb_train_bufs.step_scalars[2] themselves. */
 float pvdb_dense_adam_stepsize_host(float lr, float beta0, float beta1, int step);

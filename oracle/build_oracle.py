@@ -118,7 +118,25 @@ def _build_torch_ext(name, cpp, cu, force=False):
 
 def build_ref_torch_exts(force=False):
     return [_build_torch_ext("render_utils_ref", "render_utils.cpp", "render_utils_kernel.cu", force),
-            _build_torch_ext("adam_upd_ref", "adam_upd.cpp", "adam_upd_kernel.cu", force)]
+            _build_torch_ext("adam_upd_ref", "adam_upd.cpp", "adam_upd_kernel.cu", force),
+            _build_torch_ext("total_variation_ref", "total_variation.cpp", "total_variation_kernel.cu", force)]
+
+
+def build_ref_callers(force=False):
+    """The reference's own Python CALLERS of the boundary — plenvdb/lib/grid.py (QueryVerticalInVDB, VDBGrid) and
+    plenvdb/lib/masked_adam.py (VDBAdam) — byte-compiled from where they lie into oracle/_ref/*.pyc, like the C++ / CUDA
+    reference is compiled into oracle/_ref/*.so: no source enters the repo, and the compiled modules travel to the GPU box,
+    where tests/test_reference_callers_gpu.py runs them on top of plenvdb_b200 (the drop-in exercised by the reference's code)."""
+    import py_compile
+    outs = []
+    for name in ("grid", "masked_adam"):
+        src = os.path.join(REF, "plenvdb", "lib", name + ".py")
+        out = os.path.join(OUT, "ref_caller_%s.pyc" % name)
+        if force or _stale(out, [src]):
+            os.makedirs(OUT, exist_ok=True)
+            py_compile.compile(src, cfile=out, dfile="reference:plenvdb/lib/%s.py" % name, doraise=True)
+        outs.append(out)
+    return outs
 
 
 def build_all(force=False, with_torch_exts=True):
@@ -128,6 +146,7 @@ def build_all(force=False, with_torch_exts=True):
         built.append(build_ref_gpu(force))
         if with_torch_exts:
             built += build_ref_torch_exts(force)
+        built += build_ref_callers(force)
     return built
 
 

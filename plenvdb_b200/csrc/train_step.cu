@@ -815,7 +815,10 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     }
     P.near = cfg->near; P.far = cfg->far; P.stepdist = cfg->stepdist; P.act_shift = cfg->act_shift;
     P.interval = cfg->interval; P.thres = cfg->fast_color_thres;
-    if (g_run_skip < 0) { const char* e = getenv("PVDB_RUN_SKIP"); g_run_skip = e ? (atoi(e) != 0) : 1; }
+    // Default OFF: measured on B200 (profiles/prof_march_r02.md) the two-level pass A issues MORE instructions than testing every
+    // step (19.2 M vs 17.7 M warp instructions at F160, 39 vs 36 us; 0.297 vs 0.270 ms at S512) — the 8^3 coarse blocks are not
+    // selective enough for runs of 8 steps, and pass A is only a third of the kernel.  Kept (exact, tested) behind PVDB_RUN_SKIP=1.
+    if (g_run_skip < 0) { const char* e = getenv("PVDB_RUN_SKIP"); g_run_skip = e ? (atoi(e) != 0) : 0; }
     P.run_skip = g_run_skip;
     O.t_min = b->t_min; O.t_max = b->t_max; O.n_steps = b->n_steps;
     O.cnt_mask = b->cnt_mask; O.cnt_alpha = b->cnt_alpha; O.cnt_keep = b->cnt_keep; O.cnt_alpha_full = b->cnt_alpha_full;
@@ -907,6 +910,23 @@ extern "C" int pvdb_dp_unpack(const pvdb_train_bufs* b, const int32_t* union_lis
                               void* stream) {
     PVDB_CHECK_ARG(b && b->tree && union_list && union_count_dev && buf, "null pointer");
     k_dp_move<false><<<PVDB_SMS * 2, 256, 0, (cudaStream_t)stream>>>(b->den_grad, b->k0_grad, b->net_grad, union_list, union_count_dev, buf);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+}
+
+// One launch that gathers a batch (rays_o, rays_d, viewdirs, target: [n][3] each, anywhere in device memory) into one staging
+// buffer [4][n][3]: a captured CUDA graph of the step reads its inputs from fixed addresses.
+__global__ void __launch_bounds__(256) k_stage_rays(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                                    const float* __restrict__ d, int n3, float* __restrict__ stage) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3) return;
+    stage[i] = a[i]; stage[n3 + i] = b[i]; stage[2 * n3 + i] = c[i];
+    if (d) stage[3 * n3 + i] = d[i];
+}
+extern "C" int pvdb_stage_rays(const float* rays_o, const float* rays_d, const float* viewdirs, const float* target, int n_rays, float* stage,
+                               void* stream) {
+    PVDB_CHECK_ARG(rays_o && rays_d && viewdirs && stage && n_rays > 0, "bad arguments");
+    k_stage_rays<<<pvdb_grid_for((int64_t)n_rays * 3, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, viewdirs, target, n_rays * 3, stage);
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

@@ -56,6 +56,7 @@ class FusedTrainer:
         self.density, self.k0 = density, k0
         topo = density.topo
         self.topo = topo
+        self._bound = (density.topo_version, k0.topo_version)
         self.n_rays = int(n_rays)
         self.use_tc = bool(use_tensor_cores)
         self.step_count = 0
@@ -103,8 +104,8 @@ class FusedTrainer:
         self.parity_counts = bool(parity_counts)
         self.n_rays_global = int(n_rays_global) if n_rays_global else self.n_rays
         self._bufs = None
-        self._scal_dev = self._scal_host = None     # device copy / pinned ring of the per-iteration scalars (CUDA-graph replay)
-        self._graph = None
+        self._graphs = {}          # staging buffer address -> captured graph of the whole iteration (+ its pinned scalar slot)
+        self._dstage = None
         self.use_graph = bool(use_graph)
         self._build_structs()
 
@@ -160,9 +161,9 @@ class FusedTrainer:
         for k, t in self.t.items():
             setattr(b, k, p(t))
         b.scratch_rays, b.scratch_per_ray = self.n_rays, self.scratch_per_ray
-        b.step_scalars = self._scal_dev.data_ptr() if self._scal_dev is not None else None
+        b.step_scalars = None
         self._bufs = b
-        self._graph = None          # a captured graph holds the old pointers
+        self._graphs = {}           # captured graphs hold the old pointers
 
     def _set_step_scalars(self):
         s = self.step_count
@@ -170,46 +171,40 @@ class FusedTrainer:
         self.cfg.k0_stepsz = _lib.lib.pvdb_adam_stepsize(self.lr_k0, self.P["beta0"], self.P["beta1"], s)
         self.cfg.net_lr = self.lr_net
         self.cfg.net_step = s
-        if self._scal_dev is not None:
-            # the update kernels read the scalars from device memory (pvdb_train_bufs.step_scalars): copy this iteration's values
-            # there in stream order, from a pinned ring (at most two or three iterations are ever in flight)
-            h = self._scal_host[s % self._scal_host.shape[0]]
-            h[0], h[1] = self.cfg.den_stepsz, self.cfg.k0_stepsz
-            h[2] = _lib.lib.pvdb_dense_adam_stepsize_host(self.lr_net, self.P["beta0"], self.P["beta1"], s)
-            self._scal_dev.copy_(h, non_blocking=True)
-
-    def _enable_step_scalars(self):
-        if self._scal_dev is None:
-            self._scal_dev = torch.zeros(4, dtype=torch.float32, device=self.dev)
-            self._scal_host = torch.zeros((8, 4), dtype=torch.float32).pin_memory()
-            self._bufs.step_scalars = self._scal_dev.data_ptr()
 
     def _step_graphed(self, stage):
-        """One full iteration on the staging buffer `stage` [4, n, 3] as a CUDA-graph replay: the ~25 launches, events and the
-        side-stream fork / join of pvdb_train_step cost the host ~95 us when issued one by one, a replay ~10 us.  The graph is
-        captured on the second call for a staging buffer (the first runs directly, which also initialises everything the
-        library creates lazily); the per-iteration scalars travel through pvdb_train_bufs.step_scalars."""
+        """One full iteration on the staging buffer `stage` [4, n, 3] as a CUDA-graph replay.  Issued one by one, the ~25 launches,
+        events and the side-stream fork / join of pvdb_train_step cost the host ~95 us and leave ~1 us gaps between the kernels
+        on the device; a replay costs the host ~10 us and runs the same kernels 8 % faster (measured: 183 vs 199 us per
+        iteration, scratch/graph_timing.py).  The graph is captured on the second call for a staging buffer (the first runs
+        directly, which also initialises what the library creates lazily).  The per-iteration scalars (Adam step sizes with their
+        bias corrections, after any lr decay) are read by the update kernels from a pinned host word of this graph
+        (pvdb_train_bufs.step_scalars), written just before the replay: the caller must not have more than one iteration per
+        staging buffer in flight (step_from_host synchronises; step_from_host_async alternates two buffers and waits for
+        iteration i - 1 before it issues i + 1; step() waits for the previous replay of its buffer)."""
+        self._check_bound()
         key = (stage.data_ptr(), stage.shape[1])
-        g = self._graph
-        if g is None or g["key"] != key:                 # first call for this buffer: run directly
-            self._enable_step_scalars()
-            self._graph = dict(key=key, graph=None)
-            self.step(stage[0], stage[1], stage[2], stage[3])
-            return
-        if g["graph"] is None:                           # second call: capture, then replay once for this iteration
-            graph = torch.cuda.CUDAGraph()
-            self.step_count += 1
-            self._set_step_scalars()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(stage[0]), _lib.ptr(stage[1]),
-                          _lib.ptr(stage[2]), _lib.ptr(stage[3]), stage.shape[1], PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE,
-                          _lib.current_stream())
-            g["graph"], g["launches"] = graph, int(_lib.lib.pvdb_last_launch_count())
-            graph.replay()          # the capture itself executed nothing
-            self.launches_total += g["launches"]
+        g = self._graphs.get(key)
+        if g is None:                                    # first call for this buffer: run directly
+            self._graphs[key] = dict(graph=None, scal=torch.zeros(4, dtype=torch.float32).pin_memory(), done=torch.cuda.Event())
+            self.run(stage[0], stage[1], stage[2], stage[3], PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE)
             return
         self.step_count += 1
         self._set_step_scalars()
+        h = g["scal"]
+        h[0], h[1] = self.cfg.den_stepsz, self.cfg.k0_stepsz
+        h[2] = _lib.lib.pvdb_dense_adam_stepsize_host(self.lr_net, self.P["beta0"], self.P["beta1"], self.step_count)
+        if g["graph"] is None:                           # second call: capture
+            graph = torch.cuda.CUDAGraph()
+            self._bufs.step_scalars = h.data_ptr()       # pinned host memory, device-readable at the same address (UVA)
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(stage[0]), _lib.ptr(stage[1]),
+                              _lib.ptr(stage[2]), _lib.ptr(stage[3]), stage.shape[1], PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE,
+                              _lib.current_stream())
+            finally:
+                self._bufs.step_scalars = None           # direct launches keep taking the scalars from cfg
+            g["graph"], g["launches"] = graph, int(_lib.lib.pvdb_last_launch_count())
         g["graph"].replay()
         self.launches_total += g["launches"]
 
@@ -219,8 +214,32 @@ class FusedTrainer:
         self.lr_k0 = float(np.float32(self.lr_k0) * np.float32(factor))
         self.lr_net = self.lr_net * factor
 
+    def _check_bound(self):
+        """The buffer struct holds raw pointers into the grids' planes and a copy of the tree: a grid that got another topology
+        or other planes since (load_from, scale_volume_grid, maintenance.resparsify) must be bound again before any launch."""
+        if self._bound != (self.density.topo_version, self.k0.topo_version):
+            raise RuntimeError("the density / k0 grids changed their topology or planes after this FusedTrainer was built: call "
+                               "rebind() (Adam moments restart from zero unless remapped planes are passed) before stepping")
+
+    def rebind(self, den_m=None, den_v=None, k0_m=None, k0_v=None):
+        """Bind the trainer to the grids' CURRENT topology and planes.  The grid Adam moments restart from zero unless planes
+        congruent with the new topology are given (maintenance.resparsify returns the remapped ones)."""
+        assert self.k0.topo is self.density.topo, "density and k0 must share one topology"
+        topo = self.density.topo
+        self.topo = topo
+        self.den_m = topo.new_plane(1) if den_m is None else den_m
+        self.den_v = topo.new_plane(1) if den_v is None else den_v
+        self.k0_m = topo.new_plane(12) if k0_m is None else k0_m
+        self.k0_v = topo.new_plane(12) if k0_v is None else k0_v
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        for k in ("den_touched", "k0_touched", "den_touched_list", "k0_touched_list"):
+            self.t[k] = torch.zeros(max(topo.n_leaf, 1), **i32)
+        self._bound = (self.density.topo_version, self.k0.topo_version)
+        self._build_structs()
+
     # ---- execution
     def run(self, rays_o, rays_d, viewdirs, target, phases):
+        self._check_bound()
         n = rays_o.shape[0]
         assert n <= self.n_rays
         for t in (rays_o, rays_d, viewdirs) + ((target,) if target is not None else ()):
@@ -233,8 +252,28 @@ class FusedTrainer:
         self.launches_total += int(_lib.lib.pvdb_last_launch_count())
 
     def step(self, rays_o, rays_d, viewdirs, target):
-        """One full iteration: forward + backward + sparse Adam (grids) + Adam (rgbnet)."""
-        self.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE)
+        """One full iteration: forward + backward + sparse Adam (grids) + Adam (rgbnet).  With use_graph (default) the batch is
+        gathered into a staging buffer by one kernel and the iteration is a CUDA-graph replay (_step_graphed); the host blocks
+        only if the previous replay has not finished yet.  Per-kernel profiling and use_graph=False issue the kernels directly."""
+        n = rays_o.shape[0]
+        if not self.use_graph or _lib.PROFILING or n != self.n_rays:
+            self.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE)
+            return
+        for t in (rays_o, rays_d, viewdirs, target):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        if self._dstage is None:       # two staging buffers (two graphs): the host issues iteration i while i - 1 runs
+            self._dstage = [torch.empty((4, n, 3), dtype=torch.float32, device=self.dev) for _ in range(2)]
+            self._dstage_i = 0
+        st = self._dstage[self._dstage_i & 1]
+        self._dstage_i += 1
+        g = self._graphs.get((st.data_ptr(), n))
+        if g is not None:
+            g["done"].synchronize()          # iteration i - 2 has finished: this graph's pinned scalar slot is free again
+        _lib.call("pvdb_stage_rays", _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(viewdirs), _lib.ptr(target), n, _lib.ptr(st),
+                  _lib.current_stream())
+        self.launches_total += 1
+        self._step_graphed(st)
+        self._graphs[(st.data_ptr(), n)]["done"].record(torch.cuda.current_stream())
 
     def step_from_host(self, batch_host, stepper=None):
         """One iteration fed from HOST memory, the way run.py:541-588 is driven: `batch_host` is a pinned float32 tensor
@@ -247,7 +286,7 @@ class FusedTrainer:
             self._stage = torch.empty((4, n, 3), dtype=torch.float32, device=self.dev)
             self._loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
         self._stage.copy_(batch_host, non_blocking=True)
-        if stepper is None and self.use_graph:
+        if stepper is None and self.use_graph and not _lib.PROFILING:
             self._step_graphed(self._stage)
         else:
             (stepper or self.step)(self._stage[0], self._stage[1], self._stage[2], self._stage[3])
@@ -261,7 +300,8 @@ class FusedTrainer:
         [4, n, 3]) goes through a copy stream into one of two staging buffers, so it overlaps the previous iteration still
         running; the step waits for it on the current stream; the loss words follow into one of two pinned buffers.  Returns
         the PREVIOUS call's loss words (None on the first call) after waiting for that iteration only — the GPU always has the
-        next iteration queued behind the running one.  host_pipeline_flush() returns the last one.
+        next iteration queued behind the running one.  host_pipeline_flush() returns the last one.  `batch_host` may be refilled
+        as soon as the call returns (its copy has completed); a returned loss tensor is overwritten two calls later.
         stepper: callable(rays_o, rays_d, viewdirs, target) issuing the iteration (default self.step; DataParallelTrainer.step
         for a sharded run)."""
         n = batch_host.shape[1]
@@ -281,11 +321,15 @@ class FusedTrainer:
             p["copied"][k].record(p["copy"])
         cur.wait_event(p["copied"][k])
         st = p["stage"][k]
-        (stepper or self.step)(st[0], st[1], st[2], st[3])
+        if stepper is None and self.use_graph and not _lib.PROFILING:
+            self._step_graphed(st)           # iteration i - 2, the previous user of this buffer's graph, was waited for one call ago
+        else:
+            (stepper or self.step)(st[0], st[1], st[2], st[3])
         p["loss"][k].copy_(self.t["loss"], non_blocking=True)
         p["done"][k].record(cur)
         p["used"][k] = True
         p["i"] += 1
+        p["copied"][k].synchronize()         # the caller may refill `batch_host` as soon as this returns (~10 us, under the running iteration)
         if p["used"][k ^ 1]:
             p["done"][k ^ 1].synchronize()
             return p["loss"][k ^ 1]
@@ -302,6 +346,11 @@ class FusedTrainer:
 
     def step_dp(self, peers, dp_step, rays_o, rays_d, viewdirs, target):
         """One data-parallel iteration (pvdb_train_step_dp): the NVLink tile exchange overlaps the weight-gradient kernel."""
+        self._check_bound()
+        n = rays_o.shape[0]
+        assert n <= self.n_rays
+        for t in (rays_o, rays_d, viewdirs, target):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
         self.step_count += 1
         self._set_step_scalars()
         _lib.call("pvdb_train_step_dp", C.byref(self.cfg), C.byref(self._bufs), C.byref(peers), int(dp_step), _lib.ptr(rays_o),
@@ -314,6 +363,7 @@ class FusedTrainer:
     def update(self, lists_ready=False):
         """Apply the optimisers to whatever gradients are accumulated (after a gradient all-reduce).  lists_ready: the
         touched-leaf lists were already rebuilt by pvdb_dp_exchange."""
+        self._check_bound()
         dummy = self.t["t_min"]
         self.step_count += 1
         self._set_step_scalars()

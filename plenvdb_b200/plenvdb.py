@@ -31,10 +31,16 @@ class _BaseVDB:
         self.timer = 0.0
         self._set_topology(Topology.dense(self.reso, device=self.device))
 
-    def _set_topology(self, topo):
+    def _set_topology(self, topo, grid=None, grad=None):
+        """The ONE place where a grid changes its tree or its planes.  `topo_version` counts the changes: objects that hold
+        state congruent with the old planes (optimiser moments, the fused trainer's raw pointers) compare it before every use
+        and rebuild instead of indexing the new leaf order with old planes (the reference has this as a latent bug on
+        load_from)."""
         self.topo = topo
-        self.grid = topo.new_plane(self.ndim)   # value plane  [n_leaf,512,ndim]
-        self.grad = topo.new_plane(self.ndim)   # gradient plane
+        self.grid = topo.new_plane(self.ndim) if grid is None else grid   # value plane  [n_leaf,512,ndim]
+        self.grad = topo.new_plane(self.ndim) if grad is None else grad   # gradient plane
+        assert self.grid.shape[0] == max(topo.n_leaf, 1) and self.grad.shape == self.grid.shape
+        self.topo_version = getattr(self, "topo_version", 0) + 1
 
     # ---- maintenance on the device (SURVEY 8f-3/4; the reference composes these from dense host round trips)
     # The reference's VDB classes do not implement the TV regulariser: the method prints "Not Supported Now..." and returns
@@ -54,7 +60,8 @@ class _BaseVDB:
         """In-place form of VDBGrid.scale_volume_grid (grid.py:91-101): this object becomes the resampled dense-fill grid."""
         from . import maintenance
         new = maintenance.scale_volume_grid(self, new_world_size)
-        self.reso, self.topo, self.grid, self.grad = new.reso, new.topo, new.grid, new.grad
+        self.reso = new.reso
+        self._set_topology(new.topo, new.grid, new.grad)
 
     # ---- info / timers (plenvdb.h:397-399, 423-428)
     def getndim(self):
@@ -155,10 +162,8 @@ class _BaseVDB:
 
     def load_from(self, path):
         topo, plane, reso = vdbio.load_planes(path, self.ndim, self.device)
-        self.topo = topo
-        self.grid = plane
         # the reference re-creates only `grid`; we keep grad congruent by construction
-        self.grad = topo.new_plane(self.ndim)
+        self._set_topology(topo, plane, None)
         self.reso = list(reso)
 
 
@@ -202,10 +207,26 @@ class _BaseOptimizer:
         self.params = pvdb
         self.lr, self.eps, self.beta0, self.beta1 = float(lr), float(eps), float(beta0), float(beta1)
         self.step_count = 0
-        self.exp_avg = pvdb.topo.new_plane(pvdb.ndim)
-        self.exp_avg_sq = pvdb.topo.new_plane(pvdb.ndim)
         self.has_per_lr = False
         self.per_lr = None
+        self._bind()
+
+    def _bind(self):
+        """(Re)allocate the moments for the parameter grid's CURRENT topology.  The reference builds the optimiser before
+        model.load_from (utils.py:64-76; run.py:386-388) and --no_reload_optimizer skips opt.load_from: after the grid got
+        another tree its moments must not be indexed with the old leaf order, so they restart from zero (what a fresh optimiser
+        has); a per-voxel lr plane is dropped for the same reason and must be set again."""
+        p = self.params
+        self.exp_avg = p.topo.new_plane(p.ndim)
+        self.exp_avg_sq = p.topo.new_plane(p.ndim)
+        if self.per_lr is not None:
+            self.per_lr, self.has_per_lr = None, False
+        self._bound = (p.topo_version, p.topo)
+
+    def _check_bound(self):
+        p = self.params
+        if self._bound[0] != p.topo_version or self._bound[1] is not p.topo:
+            self._bind()
 
     # scalars (plenvdb.h:697-706)
     def getStep(self): return self.step_count
@@ -227,6 +248,7 @@ class _BaseOptimizer:
         self.params.copyFromDense_torch(torch.from_numpy(_f32(arr)), plane=self.params.grad)
 
     def set_pervoxel_lr(self, count):
+        self._check_bound()
         p = self.params
         arr = _f32(count)
         assert arr.size == p.reso[0] * p.reso[1] * p.reso[2]
@@ -243,7 +265,10 @@ class _BaseOptimizer:
 
     def step(self, stepmode):
         """step_optimizer (plenvdb.h:751-767, 774-789)."""
+        self._check_bound()
         p = self.params
+        if stepmode == 2 and self.per_lr is None:
+            raise RuntimeError("stepmode 2 needs set_pervoxel_lr() on the grid's current topology")
         self.step_count += 1
         _lib.call("pvdb_adam_step", p.topo.ref, _lib.ptr(p.grid), _lib.ptr(p.grad), _lib.ptr(self.exp_avg),
                   _lib.ptr(self.exp_avg_sq), p.ndim, int(stepmode), self.stepsize(), self.eps, self.beta0, self.beta1,
@@ -255,6 +280,7 @@ class _BaseOptimizer:
         vdbio.save_planes(prefix + "exp_avg_sq.vdb", p.topo, self.exp_avg_sq, p.reso, p._grid_names())
 
     def load_from(self, prefix):
+        self._check_bound()
         p = self.params
         self.exp_avg = vdbio.load_plane_onto(prefix + "exp_avg.vdb", p.topo, p.ndim, p.reso, p.device)
         self.exp_avg_sq = vdbio.load_plane_onto(prefix + "exp_avg_sq.vdb", p.topo, p.ndim, p.reso, p.device)

@@ -134,3 +134,39 @@ def test_voxel_count_views_matches_grid_sample_autograd():
         margin |= (grid.grad[0, 0] - 1).abs() < 1e-3                 # accumulated weight within rounding of the threshold
     assert int(want.sum()) > 100
     assert torch.equal(got[~margin], want[~margin])
+
+
+def test_state_bound_to_a_topology_is_rebuilt_or_refused_after_the_topology_changes():
+    """load_from / scale_volume_grid / resparsify give a grid another tree and other planes.  An optimiser built
+    before (the reference builds it before model.load_from, utils.py:64-76) restarts its moments on the new tree instead of
+    indexing it with the old leaf order; a FusedTrainer refuses to launch with its stale raw pointers until rebind()."""
+    from plenvdb_b200 import maintenance as mt
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import FusedTrainer, build_scene_grids
+    from plenvdb_b200.plenvdb import DensityOpt
+    scene = synth.make_scene(64, "dense")
+    net = synth.rgbnet_init()
+    den, k0 = build_scene_grids(scene)
+    rays = [torch.from_numpy(a).cuda() for a in synth.ray_batch(1024, H=160, W=160, K=synth.intrinsics(160, 160), seed=3)]
+    tr = FusedTrainer(scene, den, k0, scene["mask"], net, 1024)
+    opt = DensityOpt(den, 0.1, 1e-8, 0.9, 0.99)
+    tr.step(*rays)
+    opt.exp_avg.fill_(1.0)
+    v0 = den.topo_version
+    n_before = den.topo.n_leaf
+    new, (m1, v1, m2, v2) = mt.resparsify([den, k0], torch.from_numpy(scene["mask"]).cuda(), extra_planes=[tr.den_m, tr.den_v, tr.k0_m, tr.k0_v])
+    assert den.topo_version == v0 + 1 and den.topo.n_leaf < n_before
+    with pytest.raises(RuntimeError, match="rebind"):
+        tr.step(*rays)
+    with pytest.raises(RuntimeError, match="rebind"):
+        tr.forward(*rays[:3])
+    tr.rebind(m1, v1, m2, v2)
+    for _ in range(3):
+        tr.step(*rays)
+    torch.cuda.synchronize()
+    assert tr.counters()["overflow"] == 0 and bool(torch.isfinite(tr.t["loss"]).all())
+    assert tr.den_m.shape[0] == den.topo.n_leaf and tr.t["den_touched"].shape[0] == den.topo.n_leaf
+    # the optimiser follows by itself: moments of the new size, restarted from zero
+    den.grad.normal_()
+    opt.step(1)
+    assert opt.exp_avg.shape[0] == den.topo.n_leaf and float(opt.exp_avg.abs().max()) < 1.0
