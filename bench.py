@@ -331,8 +331,8 @@ def time_training(tr, stepper, batches, K, Wm, world, dev, n_rays, flush, with_e
     # ---- end to end through the public API with HOST buffers (pinned): every iteration's rays and targets are copied H2D and its
     # loss words D2H inside the timed region.  Headline: FusedTrainer.step_from_host_async, the loop a trainer that logs the loss
     # one iteration late uses — copy stream, two staging buffers, iteration i's loss words read while i + 1 runs, one wait per
-    # iteration (on iteration i - 1).  Beside it: the strictly synchronous step_from_host (copy, step — replayed as a CUDA graph
-    # when the trainer captured one —, read the loss, synchronise, every iteration: what `psnr.item()` costs run.py:590).
+    # iteration (on iteration i - 1).  Beside it: the strictly synchronous step_from_host (copy, step, read the loss, synchronise,
+    # every iteration: what `psnr.item()` costs run.py:590).
     hbatch = torch.stack([x[Wm:].cpu() for x in (ro, rd, vd, tg)], 1).contiguous().pin_memory()   # [K, 4, n, 3]
     e2e_ms = {}
     sync_stepper = None if world == 1 else stepper
@@ -565,8 +565,7 @@ def bench_f160(args, dev, rank, world, flush, clk):
                     "how": "FusedTrainer.step_from_host_async, every iteration: pinned host batch -> H2D on a copy stream -> step -> loss "
                            "words D2H to pinned host; the host waits for iteration i - 1 and reads its loss while iteration i runs",
                     "synchronous_value": T["e2e_sync_value"],
-                    "synchronous_how": "FusedTrainer.step_from_host: H2D, step (a CUDA-graph replay where captured), D2H of the loss, "
-                                       "stream synchronise, every iteration",
+                    "synchronous_how": "FusedTrainer.step_from_host: H2D, step, D2H of the loss, stream synchronise, every iteration",
                     "cache_regime": "warm L2 (iterations back to back, no flush inside the loop): compare with warm_l2_value, the device "
                                     "rate under the same regime; `value` flushes L2 between steps",
                     "frac_of_warm_device_rate": T["e2e_value"] / warm_value, "synchronous_frac_of_warm_device_rate": T["e2e_sync_value"] / warm_value},

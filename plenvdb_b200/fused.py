@@ -46,7 +46,7 @@ def get_rays_of_a_view(H, W, K, c2w, inverse_y=False, flip_x=False, flip_y=False
 class FusedTrainer:
     def __init__(self, params, density, k0, mask, net, n_rays, device="cuda", use_tensor_cores=True,
                  cap_alpha_per_ray=96, cap_keep_per_ray=64, parity_counts=False, n_rays_global=None,
-                 scratch_per_ray=128, use_graph=True):
+                 scratch_per_ray=128, use_graph=False):
         """params: dict from synth.scene_params (or the equivalent run.py scalars).
         density: DensityVDB, k0: ColorVDB(12) on the SAME topology (k0.topo is density.topo).
         mask: bool [reso] mask_cache.mask.  net: float32[22019] packed rgbnet parameters."""
@@ -252,9 +252,13 @@ class FusedTrainer:
         self.launches_total += int(_lib.lib.pvdb_last_launch_count())
 
     def step(self, rays_o, rays_d, viewdirs, target):
-        """One full iteration: forward + backward + sparse Adam (grids) + Adam (rgbnet).  With use_graph (default) the batch is
+        """One full iteration: forward + backward + sparse Adam (grids) + Adam (rgbnet).  With use_graph=True the batch is
         gathered into a staging buffer by one kernel and the iteration is a CUDA-graph replay (_step_graphed); the host blocks
-        only if the previous replay has not finished yet.  Per-kernel profiling and use_graph=False issue the kernels directly."""
+        only if the replay before the previous one has not finished yet.  Default off — measured on B200
+        (scratch/graph_timing.py): back-to-back replays alone run at 183-194 us per iteration against 198 us for the direct
+        launches (which already overlap kernel boundaries through programmatic dependent launch), but the per-iteration host work
+        between replays (scalars, staging) brings a replayed loop to 203-214 us; a strictly synchronous loop gains 10 us
+        (224 -> 214 us).  Per-kernel profiling always issues the kernels directly."""
         n = rays_o.shape[0]
         if not self.use_graph or _lib.PROFILING or n != self.n_rays:
             self.run(rays_o, rays_d, viewdirs, target, PHASE_FORWARD | PHASE_BACKWARD | PHASE_UPDATE)

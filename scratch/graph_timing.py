@@ -29,18 +29,7 @@ timed(lambda i: tr.step_from_host(hb[i & 3]), "step_from_host graph")
 st = tr._stage
 timed(lambda i: tr._step_graphed(st), "graph replay only, async")
 timed(lambda i: tr._step_graphed(st), "graph replay only, sync each", True)
-g = tr._graph["graph"]
-timed(lambda i: g.replay(), "raw replay (no scalars), async")
-# host cost of the pieces
-t0 = time.perf_counter()
-for i in range(K):
-    tr._stage.copy_(hb[i & 3], non_blocking=True)
-torch.cuda.synchronize(); print("H2D enqueue %.1f us" % ((time.perf_counter() - t0) / K * 1e6))
-t0 = time.perf_counter()
-for i in range(K):
-    tr.step_count += 1; tr._set_step_scalars()
-torch.cuda.synchronize(); print("scalars %.1f us" % ((time.perf_counter() - t0) / K * 1e6))
-t0 = time.perf_counter()
-for i in range(K):
-    tr._loss_host.copy_(tr.t["loss"], non_blocking=True); torch.cuda.current_stream().synchronize()
-print("D2H + sync %.1f us" % ((time.perf_counter() - t0) / K * 1e6))
+g = tr._graphs[(st.data_ptr(), st.shape[1])]["graph"]
+timed(lambda i: g.replay(), "raw replay (pinned scalars not rewritten), async")
+import torch.cuda.nvtx
+# per-kernel view of one replay vs one direct step is in the ncu launch list; here: the update kernel alone cannot be isolated

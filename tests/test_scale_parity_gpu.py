@@ -179,7 +179,9 @@ def test_f160_8192_rays_whole_iteration_matches_the_oracle(f160):
     from plenvdb_b200 import synth
     parts_g, parts_w = synth.unpack_net(gn), synth.unpack_net(wn)
     for g_, w_, nm in zip(parts_g, parts_w, ("w0", "b0", "w1", "b1", "w2", "b2")):
-        _check_sum(g_, w_, np.abs(w_).max(), "rgbnet grad " + nm)
+        # a flipped hidden unit changes one sample's whole contribution to a row of the weight gradient: up to 5 % of the elements
+        # may exceed 1e-5, none by more than 1 % of the tensor's largest gradient
+        _check_sum(g_, w_, np.abs(w_).max(), "rgbnet grad " + nm, relu_flips=(0.05, 0.01))
     # ---- update: Adam moves every touched parameter by ~lr * g / (|g| + eps) = +-lr at step 1 whatever |g| is, so a
     # gradient whose last bits differ still lands on the same parameter unless the gradient is at cancellation level;
     # parameters are compared at 1e-5 relative with the step size lr as the magnitude scale of the moved ones
