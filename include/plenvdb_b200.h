@@ -236,6 +236,9 @@ int pvdb_stage_rays(const float* rays_o, const float* rays_d, const float* viewd
 /* rgbnet Adam step size, lr * sqrt(1 - beta1^step) / (1 - beta0^step) in float (adam_upd_kernel.cu:72): what the fused step
  * derives from cfg->net_lr / net_step, for callers that feed pvdb_train_bufs.step_scalars[2] themselves. */
 float pvdb_dense_adam_stepsize_host(float lr, float beta0, float beta1, int step);
+/* Test switch: 0 makes the renderer's first pass march one pixel per thread (k_render_pass1) instead of probing every pixel and
+ * marching the hit ones with 8 lanes each (bit-identical results; default 1, environment PVDB_RENDER_LANES). */
+void pvdb_debug_set_render_lanes(int on);
 /* Test switch: 0 makes the march of pvdb_train_step test the occupancy of every step one by one instead of skipping runs of
  * steps that provably cannot hit the mask (the results are bit-identical either way; default 1). */
 void pvdb_debug_set_run_skip(int on);

@@ -83,13 +83,14 @@ __device__ __forceinline__ void wait_peer(const pvdb_dp_peers& P, int peer, int 
 }
 // Called by every thread of every CTA after its last store: the last CTA of the grid to get here signals `word` to every peer.
 // threadFenceReduction pattern; the fence is system-wide because the stores it publishes may be peer stores.
+template <bool PEER_STORES>
 __device__ __forceinline__ void last_cta_signals(const pvdb_dp_peers& P, uint32_t* done, int word, uint32_t epoch) {
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        if (PEER_STORES) __threadfence_system(); else __threadfence();
         last = atomicAdd(done, 1u) == gridDim.x - 1;
-        if (last) { *done = 0; __threadfence_system(); }
+        if (last) { *done = 0; if (PEER_STORES) __threadfence_system(); else __threadfence(); }
     }
     __syncthreads();
     if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, word, epoch);
@@ -97,16 +98,19 @@ __device__ __forceinline__ void last_cta_signals(const pvdb_dp_peers& P, uint32_
 
 // publish != 0 (stand-alone exchange): the flags are taken from den_touched | k0_touched here; publish == 0 (fused step): the
 // emit kernel has already written them into flags[parity].
-__global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epoch, int parity, int publish, int32_t* __restrict__ den_touched,
+// 256 threads and 32 registers: the CTA must fit on an SM NEXT TO a persistent tcgen05 CTA (rgbnet forward: 416 threads x 128
+// registers), or it would keep that SM's forward CTA from starting while it spins on the peers.
+constexpr int UNION_T = 256;
+__global__ void __launch_bounds__(UNION_T) k_dp_union(pvdb_dp_peers P, uint32_t epoch, int parity, int publish, int32_t* __restrict__ den_touched,
                                                    int32_t* __restrict__ k0_touched, int32_t* __restrict__ den_list,
                                                    int32_t* __restrict__ k0_list, int32_t* __restrict__ counters, int cnt_den, int cnt_k0) {
-    __shared__ int warp_cnt[32];
+    __shared__ int warp_cnt[UNION_T / 32];
     __shared__ int running;
     pvdb_pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
     if (publish)
-        for (int i = threadIdx.x; i < P.n_leaf; i += 1024) me.flags[parity][i] = (den_touched[i] | k0_touched[i]) != 0;
+        for (int i = threadIdx.x; i < P.n_leaf; i += UNION_T) me.flags[parity][i] = (den_touched[i] | k0_touched[i]) != 0;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();   // the st.release.sys below is cumulative over the CTA's flag writes ordered by this barrier
     if (threadIdx.x < P.world) {
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epo
     __syncthreads();
     const int32_t* pf[8];
     for (int r = 0; r < 8; ++r) pf[r] = view(P.base[r < P.world ? r : 0], P.n_leaf, P.cap_leaves).flags[parity];
-    for (int base = 0; base < P.n_leaf; base += 1024) {
+    for (int base = 0; base < P.n_leaf; base += UNION_T) {
         const int i = base + threadIdx.x;
         int f = 0;
         if (i < P.n_leaf)
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(1024) k_dp_union(pvdb_dp_peers P, uint32_t epo
         const unsigned bits = __ballot_sync(0xffffffffu, t);
         if (lane == 0) warp_cnt[warp] = __popc(bits);
         __syncthreads();
-        const int c = warp_cnt[lane];
+        const int c = lane < UNION_T / 32 ? warp_cnt[lane] : 0;
         int incl = c;
         #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
@@ -171,12 +175,14 @@ __global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch
                                  : reinterpret_cast<const float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128];
         reinterpret_cast<float4*>(buf)[idx] = v;
     }
-    last_cta_signals(P, me.done + 0, SIG_B, epoch);
+    last_cta_signals<false>(P, me.done + 0, SIG_B, epoch);      // local stores only
 }
 
 // Reduce-scatter + all-gather: this rank sums the union slots it owns (slot % world == rank) over all ranks, in rank order, and
 // stores the sums into every rank's red[parity].
-__global__ void __launch_bounds__(256) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, int parity, const int32_t* __restrict__ counters, int cnt_den) {
+// 128 threads: with its ~100 registers (eight float4 in flight per thread) a 256-thread CTA would not fit next to the persistent
+// weight-gradient CTA it is meant to run under.
+__global__ void __launch_bounds__(128) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, int parity, const int32_t* __restrict__ counters, int cnt_den) {
     pvdb_pdl_wait();
     if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_B, epoch);
     __syncthreads();
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(256) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, 
         for (int r = 0; r < 8; ++r)
             if (r < P.world) pr[r][off] = s;
     }
-    last_cta_signals(P, view(P.base[P.rank], P.n_leaf, P.cap_leaves).done + 1, SIG_D, epoch);
+    last_cta_signals<true>(P, view(P.base[P.rank], P.n_leaf, P.cap_leaves).done + 1, SIG_D, epoch);
 }
 
 __global__ void __launch_bounds__(256) k_dp_unpack(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ den_grad,
@@ -317,21 +323,21 @@ static int exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint
     const uint32_t epoch = step + 1;                        // monotone; the signal words start at 0
     const int CNT_DEN = 2, CNT_K0 = 4;                      // counters[] slots of pvdb_train_bufs (include/plenvdb_b200.h)
     if (do_union) {
-        PVDB_CUDA(pvdb_launch_pdl(k_dp_union, dim3(1), dim3(1024), 0, st, *P, epoch, parity, publish, b->den_touched, b->k0_touched,
+        PVDB_CUDA(pvdb_launch_pdl(k_dp_union, dim3(1), dim3(UNION_T), 0, st, *P, epoch, parity, publish, b->den_touched, b->k0_touched,
                                   b->den_touched_list, b->k0_touched_list, b->counters, CNT_DEN, CNT_K0));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("dp_union", st);
     }
     if (!do_move) return PVDB_OK;
     // grids sized for the F160 case (74 union leaves = 2 MB: latency bound) and grid-striding for S512 (~0.5 GB)
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_pack, dim3(PVDB_SMS * 2), dim3(256), 0, st, *P, epoch, parity, (const float*)b->den_grad, (const float*)b->k0_grad,
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_pack, dim3(PVDB_SMS), dim3(256), 0, st, *P, epoch, parity, (const float*)b->den_grad, (const float*)b->k0_grad,
                               (const int32_t*)b->den_touched_list, (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_pack", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS * 2), dim3(256), 0, st, *P, epoch, parity, (const int32_t*)b->counters, CNT_DEN));
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS * 4), dim3(128), 0, st, *P, epoch, parity, (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_rs", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_unpack, dim3(PVDB_SMS * 2), dim3(256), 0, st, *P, epoch, parity, b->den_grad, b->k0_grad,
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_unpack, dim3(PVDB_SMS), dim3(256), 0, st, *P, epoch, parity, b->den_grad, b->k0_grad,
                               (const int32_t*)b->den_touched_list, (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_unpack", st);

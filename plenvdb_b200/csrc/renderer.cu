@@ -21,6 +21,7 @@
 // (renderer.cu:128-132), pass 2 cannot overrun its segment (such rays are counted), the
 // per-ray PE contribution is folded into the layer-0 tile GEMM instead of a separate HW x 128 GEMM.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "mlp_tile.cuh"
 #include "render_ray.cuh"
@@ -231,6 +232,169 @@ __global__ void __launch_bounds__(256) k_render_pass1(RenderConst C, const float
     }
 }
 
+// ---- lane-parallel first pass -------------------------------------------------------------------------------------------
+// k_render_pass1 is bounded by the serial instruction stream of the warps that cover the object (one thread marches one pixel:
+// ~250 occupied steps x ~80 dependent instructions for the longest).  The same work split in two:
+//   k_render_probe        thread per pixel, empty-space skipping only: finds the `t` in front of the first run of steps that may
+//                         touch a leaf.  ~93 % of the pixels of the bench frame end here (no samples, background colour).
+//   k_render_march_lanes  LANES = 8 lanes per hit pixel (4 pixels per warp): the steps of a run are evaluated 8 at a time, one
+//                         per lane (position, active test, 8 corner densities, both alphas), then the ordered bookkeeping —
+//                         transmittance, thresholds, early stop, the simulated second march — runs identically in all 8 lanes
+//                         on values exchanged by shuffles.  Values of steps behind an early stop are computed and ignored.
+// The order (values of `lanes` steps first, bookkeeping second) is bit-identical to the reference's step-by-step marches:
+// proven on the CPU by oracle `orc_march_check(lanes = 8)` (tests/test_fast_march_cpu.py) and on the GPU against
+// k_render_pass1 / px_entries = 0 by tests/test_renderer_gpu.py.  `active_list` then holds every HIT pixel; the march rewrites
+// each entry with PX_FALLBACK_BIT (march again) or PX_EMPTY_BIT (no samples after all).
+constexpr int LANES = 8;
+constexpr int PX_EMPTY_BIT = 0x40000000;
+
+__global__ void __launch_bounds__(256) k_render_probe(RenderConst C, const float* __restrict__ c2w, int row_begin, int rows,
+                                                      int32_t* __restrict__ n_samples, float* __restrict__ tmins,
+                                                      float* __restrict__ tmaxs, int32_t* __restrict__ hit_list,
+                                                      int32_t* __restrict__ counters, float* __restrict__ out_rgb) {
+    pvdb_pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[RC_FALLBACK] = 0;
+    int local;
+    const bool in_image = pixel_of_thread(C.W, rows, local) >= 0;
+    bool hit = false;
+    if (in_image) {
+        Ray R;
+        ray_setup(C, c2w, render_gpix(C, row_begin, local), R);
+        float t = R.tmin;
+        while (t < R.tmax) {
+            float t1, tk;
+            run_chain(t, R.steplen, R.tmax, t1, tk);
+            if (!run_is_empty(C, R, t1, tk)) { hit = true; break; }
+            t = tk;
+        }
+        // what pass 1 leaves behind for a pixel without samples (:324-329); a hit pixel's entries are rewritten by the march,
+        // which resumes at tmins[local]: every run before it was empty, so nothing has happened to the ray yet
+        n_samples[local] = 0;
+        tmins[local] = hit ? t : R.tmin;
+        tmaxs[local] = R.tmax;
+        out_rgb[local * 3] = C.bg; out_rgb[local * 3 + 1] = C.bg; out_rgb[local * 3 + 2] = C.bg;
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, hit);
+    if (act) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counters + RC_ACTIVE, __popc(act));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) hit_list[base + __popc(act & ((1u << lane) - 1))] = local;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_render_march_lanes(RenderConst C, const float* __restrict__ c2w, int row_begin,
+                                                            int32_t* __restrict__ n_samples, float* __restrict__ tmins,
+                                                            float* __restrict__ tmaxs, int32_t* __restrict__ hit_list,
+                                                            const int32_t* __restrict__ counters, float* __restrict__ out_rgb,
+                                                            float2* __restrict__ px_scratch, int P) {
+    pvdb_pdl_wait();
+    const int n_hit = counters[RC_ACTIVE];
+    const int lane = threadIdx.x & 31, sub = lane & (LANES - 1), gbase = lane & ~(LANES - 1);
+    const unsigned gmask = ((1u << LANES) - 1u) << gbase;          // the 8 lanes that share this pixel
+    const int groups = (gridDim.x * blockDim.x) / LANES;
+    // every lane of a group runs the same control flow on replicated state, so the group-masked shuffles below are always
+    // reached by all 8 lanes together; different groups of a warp may diverge from each other (independent thread scheduling)
+    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) / LANES; slot < n_hit; slot += groups) {
+        const int local = hit_list[slot];
+        Ray R;
+        ray_setup(C, c2w, render_gpix(C, row_begin, local), R);
+        MarchState S;
+        PvdbLeafCache vcache;
+        float2* px_slot = px_scratch ? px_scratch + (size_t)local * P : nullptr;
+        float T_cum = 1.0f, T2 = 1.0f, t = tmins[local], tmin_out = R.tmin, tmax_out = R.tmax;
+        const float tmax0 = R.tmax;
+        bool update_tmin = false, done = false, sim = false;
+        int ns = 0, r2 = 0;
+        while (!done && t < tmax0) {
+            float t1, tk;
+            const int k = run_chain(t, R.steplen, tmax0, t1, tk);
+            if (run_is_empty(C, R, t1, tk)) { t = tk; continue; }
+            for (int base = 0; base < k && !done; base += LANES) {
+                const int m = min(LANES, k - base);
+                // this lane's step of the round: t advanced (sub + 1) times, through the same roundings as the serial chain
+                float tq = t;
+#pragma unroll
+                for (int q = 0; q < LANES; ++q)
+                    if (q <= sub && q < m) tq = __fadd_rn(tq, R.steplen);
+                bool act = false;
+                float a1 = 0.f, a2 = 0.f;
+                if (sub < m) {
+                    float xyz[3];
+                    int leaf;
+                    if (step_active(C, R, S, tq, xyz, leaf)) {
+                        act = true;
+                        const int i = (int)xyz[0], j = (int)xyz[1], kk = (int)xyz[2];
+                        const float u = __fsub_rn(xyz[0], (float)i), v = __fsub_rn(xyz[1], (float)j), w = __fsub_rn(xyz[2], (float)kk);
+                        float den[8], sc[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            den[q] = __ldg(C.dendata + idx_at(C, vcache, i + PVDB_CORNER[q][0], j + PVDB_CORNER[q][1], kk + PVDB_CORNER[q][2]));
+                        float res = 0.f;      // trigetDensity (:191-220)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int dx = PVDB_CORNER[q][0], dy = PVDB_CORNER[q][1], dz = PVDB_CORNER[q][2];
+                            const float f0 = dx ? u : __fsub_rn(1.f, u), f1 = dy ? v : __fsub_rn(1.f, v), f2 = dz ? w : __fsub_rn(1.f, w);
+                            res = __fmaf_rn(f2, __fmul_rn(f1, __fmul_rn(f0, den[q])), res);
+                            sc[q] = __fmul_rn(__fmul_rn(f0, f1), f2);
+                        }
+                        float vden = __fmaf_rn(den[0], sc[0], __fmul_rn(den[1], sc[1]));      // trigetDensity2 (:271-300)
+#pragma unroll
+                        for (int q = 2; q < 8; ++q) vden = __fmaf_rn(den[q], sc[q], vden);
+                        a1 = render_alpha(res, C.act_shift, C.interval);
+                        a2 = render_alpha(vden, C.act_shift, C.interval);
+                    }
+                }
+                // ordered bookkeeping over the steps of the round that can have an effect, identical in all lanes of the group
+                unsigned todo = (__ballot_sync(gmask, act && (a1 > C.thres || a2 > C.thres)) >> gbase) & ((1u << LANES) - 1u);
+                while (todo) {
+                    const int q = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const float tb = __shfl_sync(gmask, tq, gbase + q);
+                    const float a1b = __shfl_sync(gmask, a1, gbase + q), a2b = __shfl_sync(gmask, a2, gbase + q);
+                    bool kept = false;
+                    if (a1b > C.thres) {
+                        const float weight = __fmul_rn(T_cum, a1b);
+                        T_cum = __fmul_rn(T_cum, __fsub_rn(1.f, a1b));
+                        kept = weight > C.thres;
+                    }
+                    if (kept) {
+                        ++ns;
+                        if (!update_tmin) {
+                            tmin_out = __fsub_rn(tb, R.steplen);
+                            update_tmin = true;
+                            sim = px_slot != nullptr && __fadd_rn(tmin_out, R.steplen) == tb;
+                        }
+                    }
+                    if (sim && a2b > C.thres) {
+                        const float w2 = __fmul_rn(T2, a2b);
+                        T2 = __fmul_rn(T2, __fsub_rn(1.f, a2b));
+                        if (w2 > C.thres) {
+                            if (r2 < P && sub == 0) px_slot[r2] = make_float2(tb, w2);
+                            ++r2;
+                        }
+                    }
+                    if (kept && (double)T_cum < 1e-3) { tmax_out = tb; done = true; break; }
+                }
+                t = __shfl_sync(gmask, tq, gbase + m - 1);      // t after the m steps of the round
+            }
+        }
+        if (sub == 0) {
+            const bool handed = sim && r2 == ns && ns <= P;
+            n_samples[local] = ns;
+            tmins[local] = tmin_out;
+            tmaxs[local] = tmax_out;
+            if (ns > 0 && handed) {
+                const float last = __fmul_rn(T2, C.bg);      // :364-365; the composite adds the samples
+                out_rgb[local * 3] = last; out_rgb[local * 3 + 1] = last; out_rgb[local * 3 + 2] = last;
+            }
+            hit_list[slot] = ns == 0 ? (local | PX_EMPTY_BIT) : handed ? local : (local | PX_FALLBACK_BIT);
+        }
+    }
+}
+
+
 // Hand-over of pass 1's samples: the pixel's (t, weight) slot becomes its segment of the sample list — position as step_active
 // computes it, in the first three floats of the feature row; the pixels pass 1 could not hand over go to the fallback list,
 // which pass 2 marches like the reference does.  A warp takes 32 listed pixels: every lane sets up one pixel's ray, then the
@@ -255,8 +419,10 @@ __global__ void __launch_bounds__(256) k_render_emit(RenderConst C, const float*
         for (int a = 0; a < 3; ++a) { R.ro[a] = 0.f; R.rd[a] = 0.f; }
         if (slot < n_active) {
             e = active_list[slot];
-            const int local = e & ~PX_FALLBACK_BIT;
-            if (e & PX_FALLBACK_BIT) {
+            const int local = e & ~(PX_FALLBACK_BIT | PX_EMPTY_BIT);
+            if (e & PX_EMPTY_BIT) {
+                // a hit pixel of the lane-parallel march that has no samples after all: nothing to emit
+            } else if (e & PX_FALLBACK_BIT) {
                 fallback_list[atomicAdd(counters + RC_FALLBACK, 1)] = local;
             } else {
                 ns = n_samples[local];
@@ -269,7 +435,7 @@ __global__ void __launch_bounds__(256) k_render_emit(RenderConst C, const float*
         for (int j = 0; j < cnt; ++j) {
             const int nsj = __shfl_sync(0xffffffffu, ns, j);
             if (nsj == 0) continue;                 // marched again by pass 2 (or past the end of the list)
-            const int local = __shfl_sync(0xffffffffu, e, j) & ~PX_FALLBACK_BIT;
+            const int local = __shfl_sync(0xffffffffu, e, j) & ~(PX_FALLBACK_BIT | PX_EMPTY_BIT);
             const int64_t i0j = __shfl_sync(0xffffffffu, i0, j);
             float ro[3], rd[3];
 #pragma unroll
@@ -690,6 +856,10 @@ extern "C" int pvdb_interleaved_rows(int H, int band_rows, int rank, int world) 
 // row_begin + lr (band_stride == 0) or row_begin + (lr / band_rows) * band_stride + lr % band_rows.  frame_out (optional):
 // the full H x W x 3 frame, possibly peer memory, that also receives every pixel of the band.  fp (optional): the peer
 // protocol of pvdb_render_frame_sharded around the composite kernel.
+// 1 (default): probe + lane-parallel march as the first pass; 0: k_render_pass1 (thread per pixel).  Bit-identical results.
+static int g_render_lanes = -1;
+extern "C" void pvdb_debug_set_render_lanes(int on) { g_render_lanes = on ? 1 : 0; }
+
 static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const float* c2w, int row_begin, int rows, int band_rows,
                        int band_stride, float* out_rgb, float* frame_out, const pvdb_frame_peers* fp, uint32_t epoch, void* stream) {
     PVDB_CHECK_ARG(cfg && b && b->idx_tree && c2w && out_rgb, "null pointer");
@@ -715,10 +885,22 @@ static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, co
     PVDB_CHECK_ARG(b->active_list, "active_list scratch missing");
     const bool hand_over = b->px_scratch && b->fallback_list && b->px_entries > 0;
     float2* px = hand_over ? static_cast<float2*>(b->px_scratch) : nullptr;
-    PVDB_CUDA(pvdb_launch_pdl(k_render_pass1, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs, b->active_list,
-                              b->counters, out_rgb, px, (int)b->px_entries));
-    PVDB_LAUNCH_CHECK();
-    pvdb_prof_mark("render_pass1", st);
+    if (g_render_lanes < 0) { const char* e = getenv("PVDB_RENDER_LANES"); g_render_lanes = e ? (atoi(e) != 0) : 1; }
+    if (g_render_lanes && hand_over && C.skip_bits) {
+        PVDB_CUDA(pvdb_launch_pdl(k_render_probe, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs, b->active_list,
+                                  b->counters, out_rgb));
+        PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("render_probe", st);
+        PVDB_CUDA(pvdb_launch_pdl(k_render_march_lanes, dim3(PVDB_SMS * 8), dim3(256), 0, st, C, c2w, row_begin, b->n_samples, b->tmins, b->tmaxs,
+                                  b->active_list, (const int32_t*)b->counters, out_rgb, px, (int)b->px_entries));
+        PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("render_march_lanes", st);
+    } else {
+        PVDB_CUDA(pvdb_launch_pdl(k_render_pass1, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs, b->active_list,
+                                  b->counters, out_rgb, px, (int)b->px_entries));
+        PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("render_pass1", st);
+    }
     const int nb = (npix + 4095) / 4096;
     PVDB_CHECK_ARG(nb <= 1023, "row band too large for the scan (max 4M pixels per call)");
     PVDB_CUDA(pvdb_launch_pdl(k_scan_blocks, dim3(nb), dim3(1024), 0, st, (const int32_t*)b->n_samples, b->i_starts, npix, b->scan_tmp));

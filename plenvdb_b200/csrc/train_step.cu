@@ -1046,13 +1046,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
         int rc;
-        if (dp_fused) {      // side stream: union of the ranks' touched leaves (after the weight-image prep already queued there)
-            PVDB_CUDA(cudaEventRecord(sd->fork3, st));
-            PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork3, 0));
-            rc = pvdb_dp_union_early(peers, b, dp_step, sd->s);
-            if (rc) return rc;
-            PVDB_CUDA(cudaEventRecord(sd->join3, sd->s));
-        }
+        if (dp_fused) PVDB_CUDA(cudaEventRecord(sd->fork3, st));      // the emit kernel has written this rank's touched-leaf flags
         if (sd) {
             PVDB_CUDA(cudaStreamWaitEvent(st, sd->join2, 0));
         } else {
@@ -1062,6 +1056,12 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
         if (rc) return rc;
         pvdb_prof_mark("rgbnet_fwd", st);
+        if (dp_fused) {      // side stream, under the rgbnet forward (launched first, see the backward): union of the ranks' touched leaves
+            PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork3, 0));
+            rc = pvdb_dp_union_early(peers, b, dp_step, sd->s);
+            if (rc) return rc;
+            PVDB_CUDA(cudaEventRecord(sd->join3, sd->s));
+        }
         CompositeParams C;
         C.off_keep = b->off_keep; C.k_sample = b->k_sample; C.s_weight = b->s_weight; C.k_rgb = b->k_rgb; C.k_gw = b->k_gw;
         C.alphainv_last = b->alphainv_last; C.target = target; C.rgb_marched = b->rgb_marched; C.grad_last = b->grad_last;
@@ -1106,6 +1106,14 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             int rc = pvdb_rgbnet_backward_act_tc(cfg, b, viewdirs, st);
             if (rc) return rc;
             PVDB_CUDA(cudaEventRecord(sd->fork2, st));
+            // The persistent weight-gradient kernel is launched FIRST: the side-stream kernels below become eligible at the same
+            // moment (both wait for the activation-gradient kernel) and are small enough to fit next to its CTAs (<= 10 K
+            // registers per CTA), but CTAs of theirs that got an SM first — spinning on a peer's signal — would keep that SM's
+            // weight-gradient CTA from starting at all.
+            PvdbDpNetPush push;
+            if (dp_fused) push = pvdb_dp_net_push_args(peers, dp_step);
+            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, dp_fused ? &push : nullptr);
+            if (rc) return rc;
             PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));
             if (peers) {
                 rc = dp_fused ? pvdb_dp_move_tiles(peers, b, dp_step, sd->s) : pvdb_dp_exchange_tiles(peers, b, dp_step, sd->s);
@@ -1116,10 +1124,6 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                 if (rc) return rc;
             }
             PVDB_CUDA(cudaEventRecord(sd->join, sd->s));
-            PvdbDpNetPush push;
-            if (dp_fused) push = pvdb_dp_net_push_args(peers, dp_step);
-            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, dp_fused ? &push : nullptr);
-            if (rc) return rc;
             if (peers && !dp_fused) {
                 rc = pvdb_dp_exchange_net(peers, b, dp_step, st);
                 if (rc) return rc;
