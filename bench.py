@@ -474,21 +474,21 @@ def bench_f160(args, dev, rank, world, flush, clk):
     t_setup = time.time()
     scene, net, den, k0, tr, batches = build_workload(nb, dev, seed=777 + rank, use_tc=not args.fp32_rgbnet)
     dp = None
-    if world > 1:
+    if world > 1 and args.exchange != "none":
         dp = pdist.DataParallelTrainer.wrap(tr, world, exchange=args.exchange)
         stepper = dp.step
     else:
-        stepper = tr.step
+        stepper = tr.step        # --exchange none at N > 1: independent replicas (diagnosis of what the exchange costs; not a DP run)
     ro, rd, vd, tg = batches
     log("[bench] rank %d setup %.1fs, pool ready" % (rank, time.time() - t_setup))
     T = time_training(tr, stepper, batches, K, Wm, world, dev, N_RAYS, flush)
     cnt, ms_total, value = T["counters"], T["ms_total"], T["value"]
     clocks = clk.summary()
-    rep = replica_check(tr, world, dev) if world > 1 else None
+    rep = replica_check(tr, world, dev) if (world > 1 and dp is not None) else None
 
     # ---- exchange kernels (all ranks step together; rank 0 reports)
     xchg = {}
-    if world > 1 and dp.peer is not None:
+    if world > 1 and dp is not None and dp.peer is not None:
         from plenvdb_b200 import _lib
         _lib.profile_enable(True)
         for i in range(K):
@@ -578,7 +578,9 @@ def bench_f160(args, dev, rank, world, flush, clk):
             "parity": par,
             "clocks": clocks,
         }
-        if world > 1:
+        if world > 1 and dp is None:
+            result["config"]["exchange"] = "NONE (--exchange none): independent replicas, diagnosis only"
+        if world > 1 and dp is not None:
             result["config"]["exchange_bytes_per_step"] = dp.exchange_bytes()
             if xchg:
                 result["exchange_kernel_ms"] = xchg
@@ -828,13 +830,13 @@ def bench_s512(args, dev, rank, world, flush, headline):
     P, net, den, k0, tr, batches, mask = build_workload_s512(K + Wm, dev, use_tc=not args.fp32_rgbnet)
     log("[bench] rank %d S512 setup %.1fs: %d leaves, occupied %.3f" % (rank, time.time() - t0, den.topo.n_leaf, P["occupied_fraction"]))
     dp = None
-    if world > 1:
+    if world > 1 and args.exchange != "none":
         dp = pdist.DataParallelTrainer.wrap(tr, world, exchange=args.exchange)
         stepper = dp.step
     else:
         stepper = tr.step
     T = time_training(tr, stepper, batches, K, Wm, world, dev, S512_RAYS, flush, with_e2e=headline)
-    rep = replica_check(tr, world, dev) if world > 1 else None
+    rep = replica_check(tr, world, dev) if (world > 1 and dp is not None) else None
     cnt = T["counters"]
     out = None
     if rank == 0:
@@ -866,7 +868,7 @@ def bench_s512(args, dev, rank, world, flush, headline):
                          "roofline": roof}}
         if rep is not None:
             out["train"]["parity"] = rep
-        if world > 1:
+        if world > 1 and dp is not None:
             out["train"]["exchange_bytes_per_step"] = dp.exchange_bytes()
     if dp is not None:
         dp.close()
@@ -964,7 +966,7 @@ def main():
     ap.add_argument("--s512-steps", type=int, default=10)
     ap.add_argument("--render-gather", choices=["peer", "nccl"], default="peer",
                     help="N > 1: how rank 0 gets the frame (peer stores over NVLink, or contiguous bands + NCCL gather)")
-    ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl"],
+    ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl", "none"],
                     help="N>1 gradient exchange: own kernels over NVLink peer memory, or NCCL all-reduce of the packed tiles")
     ap.add_argument("--fp32-rgbnet", action="store_true", help="use the fp32 CUDA-core rgbnet instead of the tcgen05 one")
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays of the CPU legs (oracle parity step, sampling-path baseline)")

@@ -239,6 +239,11 @@ float pvdb_dense_adam_stepsize_host(float lr, float beta0, float beta1, int step
 /* Test switch: 0 makes the renderer's first pass march one pixel per thread (k_render_pass1) instead of probing every pixel and
  * marching the hit ones with 8 lanes each (bit-identical results; default 1, environment PVDB_RENDER_LANES). */
 void pvdb_debug_set_render_lanes(int on);
+/* Debug timeline (environment PVDB_STAMPS=1): %globaltimer stamps written by one-thread kernels at marked points of the fused
+ * step (main stream: 0 start, 1 emit, 2 rgbnet forward, 3 composite, 4 activation gradients, 5 weight gradients + reduction,
+ * 6 rgbnet Adam, 7 join; side stream: 10/11 around the union, 12 start of the tile exchange, 13 its end, 14 leaf Adam).
+ * Copies the 64 stamps of the last step to the host; returns non-zero when stamping is off. */
+int pvdb_debug_stamps_fetch(unsigned long long* out64);
 /* Test switch: 0 makes the march of pvdb_train_step test the occupancy of every step one by one instead of skipping runs of
  * steps that provably cannot hit the mask (the results are bit-identical either way; default 1). */
 void pvdb_debug_set_run_skip(int on);

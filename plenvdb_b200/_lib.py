@@ -163,6 +163,7 @@ _SIGS = {
     "pvdb_occupancy_update": (None, [_TP, c_ptr, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f, _f, _f, c_ptr, _i, _i, _i, c_ptr, c_ptr]),
     "pvdb_total_variation_add_grad": (None, [_TP, c_ptr, c_ptr, _i, _i, _i, _i, _f, _f, _f, _i, c_ptr]),
     "pvdb_debug_set_run_skip": (None, [_i]),
+    "pvdb_debug_stamps_fetch": (C.c_int, [c_ptr]),
     "pvdb_debug_set_render_lanes": (None, [_i]),
     "pvdb_stage_rays": (None, [c_ptr, c_ptr, c_ptr, c_ptr, _i, c_ptr, c_ptr]),
     "pvdb_dense_adam_stepsize_host": (C.c_float, [_f, _f, _f, _i]),

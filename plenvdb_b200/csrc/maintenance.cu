@@ -116,13 +116,17 @@ __global__ void __launch_bounds__(256) k_tv_add_grad(pvdb_tree t, const float* _
         if ((unsigned)(l + d) < 8u) return plane[idx + (int64_t)d * (ax == 0 ? 64 : ax == 1 ? 8 : 1) * C];
         return value_at(t, plane, C, c, x + (ax == 0 ? d : 0), y + (ax == 1 ? d : 0), z + (ax == 2 ? d : 0));
     };
-    float g = 0.f;   // same accumulation order as the dense kernel: k-, k+, j-, j+, i-, i+
+    // total_variation_kernel.cu:25-32, statement for statement: accumulation order k-, k+, j-, j+, i-, i+, and the i-axis terms
+    // are weighted with wz like the k-axis ones (the reference never reads wx in the kernel; kept, since parity means the same
+    // numbers).  wx is passed through for the day the reference fixes that line.
+    (void)wx;
+    float g = 0.f;
     g += z == 0 ? 0.f : wz * clamp1(p - nb(2, -1));
     g += z == rz - 1 ? 0.f : wz * clamp1(p - nb(2, 1));
     g += y == 0 ? 0.f : wy * clamp1(p - nb(1, -1));
     g += y == ry - 1 ? 0.f : wy * clamp1(p - nb(1, 1));
-    g += x == 0 ? 0.f : wx * clamp1(p - nb(0, -1));
-    g += x == rx - 1 ? 0.f : wx * clamp1(p - nb(0, 1));
+    g += x == 0 ? 0.f : wz * clamp1(p - nb(0, -1));
+    g += x == rx - 1 ? 0.f : wz * clamp1(p - nb(0, 1));
     grad[idx] += g;
 }
 
@@ -169,6 +173,7 @@ extern "C" int pvdb_total_variation_add_grad(const pvdb_tree* tree, const float*
     PVDB_CHECK_ARG(tree && plane && grad && channels > 0, "bad arguments");
     if (tree->n_leaf == 0) return PVDB_OK;
     const int64_t total = (int64_t)tree->n_leaf * 512 * channels;
+    wx /= 6; wy /= 6; wz /= 6;      // total_variation_kernel.cu:46-48
     if (dense_mode)
         k_tv_add_grad<true><<<pvdb_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*tree, plane, grad, channels, rx, ry, rz, wx, wy, wz);
     else

@@ -793,6 +793,27 @@ extern "C" int pvdb_occ_build(const uint8_t* mask, int rx, int ry, int rz, uint6
     return PVDB_OK;
 }
 
+// Debug timeline (environment PVDB_STAMPS=1): one-thread kernels write %globaltimer into a device array at the marked points of
+// the fused step, on the stream they are enqueued on; pvdb_debug_stamps_fetch copies the last step's stamps to the host.  Used
+// by scratch/dp_timeline.py to see where a data-parallel step waits.  Off: no kernel is launched.
+__global__ void k_stamp(unsigned long long* out, int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    out[slot] = t;
+}
+static unsigned long long* g_stamps = nullptr;
+static int g_stamps_on = -1;
+static void stamp(cudaStream_t st, int slot) {
+    if (g_stamps_on < 0) { const char* e = getenv("PVDB_STAMPS"); g_stamps_on = e && atoi(e) != 0; }
+    if (!g_stamps_on) return;
+    if (!g_stamps) { cudaMalloc(&g_stamps, 64 * sizeof(unsigned long long)); cudaMemset(g_stamps, 0, 64 * sizeof(unsigned long long)); }
+    k_stamp<<<1, 1, 0, st>>>(g_stamps, slot);
+}
+extern "C" int pvdb_debug_stamps_fetch(unsigned long long* out64) {
+    if (!g_stamps) return 1;
+    return cudaMemcpy(out64, g_stamps, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
+
 // test switch (pvdb_debug_set_run_skip): 0 = pass A of the march tests every step one by one
 static int g_run_skip = -1;     // -1: not decided yet (environment PVDB_RUN_SKIP, else the default)
 extern "C" void pvdb_debug_set_run_skip(int on) { g_run_skip = on ? 1 : 0; }
@@ -1012,6 +1033,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     // otherwise the stand-alone exchange runs after the backward.
     const bool dp_fused = peers && sd && cfg->use_tensor_cores && do_fwd && do_bwd && do_upd;
     if (dp_fused) O.dp_flags = pvdb_dp_flags_ptr(peers, dp_step);
+    stamp(st, 0);
 
     if (do_fwd) {
         PVDB_CHECK_ARG(rays_o && rays_d && viewdirs, "null rays");
@@ -1045,6 +1067,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         else k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
+        stamp(st, 1);
         int rc;
         if (dp_fused) PVDB_CUDA(cudaEventRecord(sd->fork3, st));      // the emit kernel has written this rank's touched-leaf flags
         if (sd) {
@@ -1055,11 +1078,14 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         }
         rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
         if (rc) return rc;
+        stamp(st, 2);
         pvdb_prof_mark("rgbnet_fwd", st);
         if (dp_fused) {      // side stream, under the rgbnet forward (launched first, see the backward): union of the ranks' touched leaves
             PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork3, 0));
+            stamp(sd->s, 10);
             rc = pvdb_dp_union_early(peers, b, dp_step, sd->s);
             if (rc) return rc;
+            stamp(sd->s, 11);
             PVDB_CUDA(cudaEventRecord(sd->join3, sd->s));
         }
         CompositeParams C;
@@ -1070,6 +1096,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         PVDB_CUDA(pvdb_launch_pdl(k_composite, dim3(warp_grid), dim3(256), 0, st, C, n_rays));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("composite", st);
+        stamp(st, 3);
     }
     if (do_bwd) {
         // The density branch of the backward (ray recurrence -> density scatter) depends only on the composite, not on the
@@ -1105,6 +1132,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             if (dp_fused) PVDB_CUDA(cudaStreamWaitEvent(st, sd->join3, 0));
             int rc = pvdb_rgbnet_backward_act_tc(cfg, b, viewdirs, st);
             if (rc) return rc;
+            stamp(st, 4);
             PVDB_CUDA(cudaEventRecord(sd->fork2, st));
             // The persistent weight-gradient kernel is launched FIRST: the side-stream kernels below become eligible at the same
             // moment (both wait for the activation-gradient kernel) and are small enough to fit next to its CTAs (<= 10 K
@@ -1114,14 +1142,18 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             if (dp_fused) push = pvdb_dp_net_push_args(peers, dp_step);
             rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, dp_fused ? &push : nullptr);
             if (rc) return rc;
+            stamp(st, 5);
             PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));
+            stamp(sd->s, 12);
             if (peers) {
                 rc = dp_fused ? pvdb_dp_move_tiles(peers, b, dp_step, sd->s) : pvdb_dp_exchange_tiles(peers, b, dp_step, sd->s);
                 if (rc) return rc;
+                stamp(sd->s, 13);
             }
             if (do_upd) {
                 rc = launch_update(sd->s, 1);
                 if (rc) return rc;
+                stamp(sd->s, 14);
             }
             PVDB_CUDA(cudaEventRecord(sd->join, sd->s));
             if (peers && !dp_fused) {
@@ -1134,8 +1166,10 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                 U.dp = PvdbDpNetWait{};
                 if (rc) return rc;
                 update_done = true;
+                stamp(st, 6);
             }
             PVDB_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
+            stamp(st, 7);
         } else {
             if (sd) {
                 PVDB_CUDA(cudaEventRecord(sd->join, sd->s));

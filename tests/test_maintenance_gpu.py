@@ -83,7 +83,8 @@ def test_total_variation_matches_dense_kernel_semantics(dense_mode, grids):
         p = vdb.get_dense_grid_torch()                                          # [R,R,R,C], background 0 outside the tree
         gd = vdb.get_dense_grid_torch(vdb.grad).clone()
         add = torch.zeros_like(p)
-        for ax, wa in ((2, w[2]), (1, w[1]), (0, w[0])):                        # kernel order: k-, k+, j-, j+, i-, i+
+        # the reference's wrapper divides the weights by 6 and its kernel weights the i-axis terms with wz (total_variation_kernel.cu:46-48, :31-32)
+        for ax, wa in ((2, w[2] / 6), (1, w[1] / 6), (0, w[2] / 6)):            # kernel order: k-, k+, j-, j+, i-, i+
             d = torch.diff(p, dim=ax).clamp(-1, 1)                              # p[i+1] - p[i]
             lo = [slice(None)] * 4; hi = [slice(None)] * 4
             lo[ax], hi[ax] = slice(0, -1), slice(1, None)
@@ -95,6 +96,17 @@ def test_total_variation_matches_dense_kernel_semantics(dense_mode, grids):
         # compare on voxels covered by leaves (the dense view of the gradient is 0 elsewhere by construction)
         cov = vdb.get_dense_grid_torch(torch.ones_like(vdb.grad)) > 0
         torch.testing.assert_close(got[cov], want[cov], rtol=1e-5, atol=1e-6)
+        # pinned against the reference's own kernel (total_variation_kernel.cu compiled for sm_100a into oracle/_ref/): the dense
+        # tensors in the layout DenseGrid holds them, [1, C, i, j, k] (grid.py:146-158); same statements, same order -> same bits
+        from oracle import ref
+        ext = ref.torch_ext("total_variation_ref")
+        if ext is not None:
+            rp = p.permute(3, 0, 1, 2)[None].contiguous()
+            rg = gd.permute(3, 0, 1, 2)[None].contiguous()
+            ext.total_variation_add_grad(rp, rg, float(w[0]), float(w[1]), float(w[2]), bool(dense_mode))
+            torch.cuda.synchronize()
+            rg = rg[0].permute(1, 2, 3, 0)
+            assert torch.equal(got[cov], rg[cov]), "sparse TV differs from the reference kernel on %d values" % int((got[cov] != rg[cov]).sum())
         vdb.grad.zero_()
 
 
