@@ -261,17 +261,20 @@ int pvdb_dp_unpack(const pvdb_train_bufs* bufs, const int32_t* union_list, const
  * are exchanged by the caller's own transport (torch.distributed all_gather_object here) and opened with
  * pvdb_dp_symm_open; base[r] is rank r's block as mapped in THIS process (base[rank] = the own allocation).
  * pvdb_dp_exchange(step) runs after the backward phase on every rank with the same monotone `step` (0,1,2,...):
- * cross-GPU barrier, union of touched leaves, pack, reduce-scatter + all-gather over peer memory (every rank sums the union
- * slots it owns in rank order and stores the sums into every rank's block: O(1) NVLink bytes per rank), unpack into
- * den_grad/k0_grad, rgbnet gradients into net_grad, and leaves den/k0_touched_list + counters[2],[4] ready for
- * pvdb_train_step(PVDB_PHASE_UPDATE|PVDB_PHASE_LISTS_READY).
- * A peer that does not arrive within 2 s sets the block's error word (pvdb_dp_symm_error: 1 timeout, 2 union > cap). */
+ * cross-GPU barrier, union of touched leaves, reduce-scatter + all-gather over peer memory IN PLACE on the gradient planes,
+ * which live inside the symmetric blocks (every rank sums the union leaves it owns over all ranks' planes in rank order and
+ * stores the sums into every rank's planes: O(1) NVLink bytes per rank, no staging copy), rgbnet gradients into net_grad, and
+ * leaves den/k0_touched_list + counters[2],[4] ready for pvdb_train_step(PVDB_PHASE_UPDATE|PVDB_PHASE_LISTS_READY).
+ * A peer that does not arrive within 2 s sets the block's error word (pvdb_dp_symm_error: 1 timeout). */
 typedef struct {
     int32_t world, rank;      /* world <= 8 (one NVSwitch domain) */
     int32_t n_leaf, cap_leaves;
     void* base[8];
 } pvdb_dp_peers;
-size_t pvdb_dp_symm_bytes(int n_leaf, int cap_leaves);
+size_t pvdb_dp_symm_bytes(int n_leaf, int cap_leaves /* unused */);
+/* The gradient planes INSIDE this rank's symmetric block: den_grad [n_leaf][512], k0_grad [n_leaf][512][12].  The exchange reads
+ * and writes the peers' planes in place (no pack / unpack), so pvdb_train_bufs.den_grad / k0_grad must be exactly these. */
+int pvdb_dp_grad_planes(const pvdb_dp_peers* peers, float** den_grad, float** k0_grad);
 int pvdb_dp_symm_alloc(size_t bytes, void** ptr, void* handle64);
 int pvdb_dp_symm_open(const void* handle64, void** ptr);
 int pvdb_dp_symm_close(void* ptr);

@@ -152,6 +152,7 @@ _SIGS = {
     "pvdb_dp_symm_open": (None, [c_ptr, C.POINTER(C.c_void_p)]),
     "pvdb_dp_symm_close": (None, [c_ptr]),
     "pvdb_dp_symm_free": (None, [c_ptr]),
+    "pvdb_dp_grad_planes": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "pvdb_dp_symm_error": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(C.c_int32)]),
     "pvdb_dp_exchange": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(pvdb_train_bufs), C.c_uint32, c_ptr]),
     "pvdb_dp_exchange_tiles": (None, [C.POINTER(pvdb_dp_peers), C.POINTER(pvdb_train_bufs), C.c_uint32, c_ptr]),

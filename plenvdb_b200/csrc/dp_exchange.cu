@@ -2,31 +2,33 @@
 // so this has no counterpart there).  Each rank owns one "symmetric block" (cudaMalloc + CUDA IPC, mapped by every peer):
 //
 //   [0,448)      signal words, u32, monotone epochs (step + 1) written by the peers with st.release.sys and polled by the
-//                owner: A[src] flags published, B[src] tiles packed, D[src] reduced tiles delivered, C[src] rgbnet gradients
-//                delivered, CS[slice][src] (stand-alone rgbnet exchange)
-//   [448,512)    err, done counters
-//   [1024,..)    flags[2][n_leaf] i32      touched flags published by the owner (double-buffered by step parity)
+//                owner: A[src] flags published, B[src] gradients final, D[src] sums delivered, C[src] rgbnet gradients delivered,
+//                CS[slice][src] (stand-alone rgbnet exchange)
+//   [448,512)    err, last-CTA counters
+//   [1024,..)    flags[2][ceil(n_leaf / 32)] u32   touched-leaf BITS published by the owner (double-buffered by step parity)
 //   [net_off,.)  net[2][NET_PAD]  f32      stand-alone rgbnet exchange: the owner's gradients, read by the peers
 //   [netx_off,.) netx[2][8][NET_PAD] f32   fused rgbnet exchange: slot [src] is WRITTEN BY rank src (peer stores)
-//   [grad_off,.) grad[2][cap]     f32      the owner's packed gradient tiles of the union leaves, read by the peers
-//   [red_off,.)  red[2][cap]      f32      reduced tiles, slot s WRITTEN BY its owner rank s % world (peer stores)
+//   [den_off,.)  den_grad[n_leaf][512]     THE gradient planes of this rank's grids (dist.py binds DensityVDB.grad /
+//   [k0_off,.)   k0_grad[n_leaf][512][12]  ColorVDB.grad to them): the scatter kernels accumulate straight into peer-visible memory
 //
-// No host synchronisation and no NCCL call.  Per step and rank the NVLink traffic is O(1) in the number of ranks:
-//   k_dp_union   1 CTA : cross-GPU barrier A -> OR of all peers' flags -> ascending union list (identical everywhere)
-//   k_dp_pack    grid  : own gradient tiles of the union leaves -> own grad[parity]; the last CTA signals B
+// No host synchronisation, no NCCL call, no staging copy.  Per step and rank the NVLink traffic is O(1) in the number of ranks:
+//   k_dp_union   1 CTA : cross-GPU barrier A -> OR of all peers' flag words -> ascending union list (identical everywhere)
+//   k_dp_ready   1 warp: this rank's gradient planes are final (signal B)
 //   k_dp_rs      grid  : reduce-scatter + all-gather in one kernel.  Rank r owns the union slots s with s % world == r: it
-//                        reads that slot from every rank's grad[parity] (world - 1 peer loads of 1/world of the data), sums in
-//                        rank order (identical bits everywhere) and stores the result into EVERY rank's red[parity]
-//                        (world - 1 peer stores); the last CTA signals D
-//   k_dp_unpack  grid  : wait for D, copy red[parity] (local memory) into the gradient planes
+//                        reads that leaf's tile from every rank's planes (world - 1 peer loads of 1/world of the data), sums in
+//                        rank order (identical bits everywhere) and stores the sum into EVERY rank's planes (world - 1 peer
+//                        stores); the last CTA signals D
+//   k_dp_wait    1 warp: all owners have delivered (wait for D) — in front of the sparse Adam
 // The rgbnet gradients (88 KB) ride on the kernels that produce and consume them: the weight-gradient reduction stores its
 // sums straight into every peer's netx[parity][rank] (pvdb_dp_net_push_args) and the rgbnet Adam waits for C and adds the
 // world slots of its own block in rank order (pvdb_dp_net_wait_args) — no exchange kernel at all on that path.
-// In the fused step (pvdb_train_step_dp) the flags are written by the emit kernel (the sample lists determine the touched
+// In the fused step (pvdb_train_step_dp) the flag bits are set by the emit kernel (the sample lists determine the touched
 // leaves before any gradient exists), so k_dp_union — and with it the barrier that absorbs the ranks' skew — runs on the side
-// stream under the rgbnet forward; pack / rs / unpack run under the weight-gradient kernel.
-// Double buffering makes further barriers unnecessary: a rank overwrites parity p two steps later, after it passed barrier
-// A of the step in between, which every peer reaches only after all of its reads of the earlier step (stream order).
+// stream under the rgbnet forward; ready / rs / wait run under the weight-gradient kernel.
+// A plane element of a union leaf has one remote reader and one remote writer, the leaf's owner, which reads all ranks' values
+// before it stores the sum, element by element; a rank touches its planes again (Adam clears them) only after D from every
+// owner.  The flag words and netx are double-buffered: a rank overwrites parity p two steps later, after it passed barrier A
+// of the step in between, which every peer reaches only after all of its reads of the earlier step (stream order).
 #include "common.cuh"
 #include "rgbnet.cuh"
 #include "peer_sync.cuh"
@@ -34,7 +36,6 @@
 
 namespace {
 
-constexpr int TILE_F = PVDB_LEAF_VOX * 13;                 // density [512] + k0 [512][12]
 constexpr int NET_PAD = PVDB_DP_NET_PAD;
 constexpr int NET_SLICES = 8;
 enum { SIG_A = 0, SIG_B = 8, SIG_D = 16, SIG_C = 24, SIG_CS = 32 };   // word offsets inside the signal area (CS: [slice][8])
@@ -43,74 +44,70 @@ struct Blk {
     uint32_t* signal;
     int32_t* err;
     uint32_t* done;      // [4] last-CTA counters
-    int32_t* flags[2];
+    uint32_t* flags[2];  // bit per leaf
     float* net[2];
     float* netx[2];      // [8][NET_PAD] each
-    float* grad[2];
-    float* red[2];
+    float* den_grad;
+    float* k0_grad;
 };
-__host__ __device__ inline size_t net_off(int n_leaf) { return (1024 + (size_t)8 * n_leaf + 255) & ~(size_t)255; }
+__host__ __device__ inline int flag_words(int n_leaf) { return (n_leaf + 31) >> 5; }
+__host__ __device__ inline size_t net_off(int n_leaf) { return (1024 + (size_t)8 * flag_words(n_leaf) + 255) & ~(size_t)255; }
 __host__ __device__ inline size_t netx_off(int n_leaf) { return net_off(n_leaf) + 2 * (size_t)NET_PAD * sizeof(float); }
-__host__ __device__ inline size_t grad_off(int n_leaf) { return netx_off(n_leaf) + 2 * 8 * (size_t)NET_PAD * sizeof(float); }
-__host__ __device__ inline size_t cap_floats(int cap_leaves) { return (size_t)cap_leaves * TILE_F; }
-__host__ __device__ inline Blk view(void* base, int n_leaf, int cap_leaves) {
+__host__ __device__ inline size_t den_off(int n_leaf) { return netx_off(n_leaf) + 2 * 8 * (size_t)NET_PAD * sizeof(float); }
+__host__ __device__ inline size_t k0_off(int n_leaf) { return den_off(n_leaf) + (size_t)(n_leaf > 0 ? n_leaf : 1) * PVDB_LEAF_VOX * sizeof(float); }
+__host__ __device__ inline Blk view(void* base, int n_leaf) {
     char* p = static_cast<char*>(base);
     Blk b;
     b.signal = reinterpret_cast<uint32_t*>(p);
     b.err = reinterpret_cast<int32_t*>(p + 448);
     b.done = reinterpret_cast<uint32_t*>(p + 452);
-    b.flags[0] = reinterpret_cast<int32_t*>(p + 1024);
-    b.flags[1] = b.flags[0] + n_leaf;
+    b.flags[0] = reinterpret_cast<uint32_t*>(p + 1024);
+    b.flags[1] = b.flags[0] + flag_words(n_leaf);
     b.net[0] = reinterpret_cast<float*>(p + net_off(n_leaf));
     b.net[1] = b.net[0] + NET_PAD;
     b.netx[0] = reinterpret_cast<float*>(p + netx_off(n_leaf));
     b.netx[1] = b.netx[0] + 8 * (size_t)NET_PAD;
-    b.grad[0] = reinterpret_cast<float*>(p + grad_off(n_leaf));
-    b.grad[1] = b.grad[0] + cap_floats(cap_leaves);
-    b.red[0] = b.grad[1] + cap_floats(cap_leaves);
-    b.red[1] = b.red[0] + cap_floats(cap_leaves);
+    b.den_grad = reinterpret_cast<float*>(p + den_off(n_leaf));
+    b.k0_grad = reinterpret_cast<float*>(p + k0_off(n_leaf));
     return b;
 }
 
 // thread `peer` of a CTA: tell rank `peer` that this rank reached `epoch`
 __device__ __forceinline__ void signal_peer(const pvdb_dp_peers& P, int peer, int word, uint32_t epoch) {
-    st_release_sys(view(P.base[peer], P.n_leaf, P.cap_leaves).signal + word + P.rank, epoch);
+    st_release_sys(view(P.base[peer], P.n_leaf).signal + word + P.rank, epoch);
 }
 // thread `peer` of a CTA: wait until rank `peer` reached `epoch`
 __device__ __forceinline__ void wait_peer(const pvdb_dp_peers& P, int peer, int word, uint32_t epoch) {
-    const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
+    const Blk me = view(P.base[P.rank], P.n_leaf);
     wait_epoch(me.signal + word + peer, epoch, me.err, 1);   // a dead peer must not hang the GPU
 }
-// Called by every thread of every CTA after its last store: the last CTA of the grid to get here signals `word` to every peer.
-// threadFenceReduction pattern; the fence is system-wide because the stores it publishes may be peer stores.
-template <bool PEER_STORES>
-__device__ __forceinline__ void last_cta_signals(const pvdb_dp_peers& P, uint32_t* done, int word, uint32_t epoch) {
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (PEER_STORES) __threadfence_system(); else __threadfence();
-        last = atomicAdd(done, 1u) == gridDim.x - 1;
-        if (last) { *done = 0; if (PEER_STORES) __threadfence_system(); else __threadfence(); }
-    }
-    __syncthreads();
-    if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, word, epoch);
-}
 
-// publish != 0 (stand-alone exchange): the flags are taken from den_touched | k0_touched here; publish == 0 (fused step): the
-// emit kernel has already written them into flags[parity].
+// publish != 0 (stand-alone exchange): the flag bits are taken from den_touched | k0_touched here; publish == 0 (fused step):
+// the emit kernel has already set them in flags[parity].
 // 256 threads and 32 registers: the CTA must fit on an SM NEXT TO a persistent tcgen05 CTA (rgbnet forward: 416 threads x 128
-// registers), or it would keep that SM's forward CTA from starting while it spins on the peers.
+// registers), or it would keep that SM's forward CTA from starting while it spins on the peers.  Every thread owns a contiguous
+// run of flag words, so that all of its peer loads are in flight together (one NVLink latency) and the list comes out in
+// ascending leaf order.
 constexpr int UNION_T = 256;
+constexpr int UNION_WPT = 4;                      // words per thread and round: 256 x 4 x 32 = 32 768 leaves per round
 __global__ void __launch_bounds__(UNION_T) k_dp_union(pvdb_dp_peers P, uint32_t epoch, int parity, int publish, int32_t* __restrict__ den_touched,
-                                                   int32_t* __restrict__ k0_touched, int32_t* __restrict__ den_list,
-                                                   int32_t* __restrict__ k0_list, int32_t* __restrict__ counters, int cnt_den, int cnt_k0) {
+                                                      int32_t* __restrict__ k0_touched, int32_t* __restrict__ den_list,
+                                                      int32_t* __restrict__ k0_list, int32_t* __restrict__ counters, int cnt_den, int cnt_k0) {
     __shared__ int warp_cnt[UNION_T / 32];
     __shared__ int running;
     pvdb_pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
+    const Blk me = view(P.base[P.rank], P.n_leaf);
+    const int W = flag_words(P.n_leaf);
     if (publish)
-        for (int i = threadIdx.x; i < P.n_leaf; i += UNION_T) me.flags[parity][i] = (den_touched[i] | k0_touched[i]) != 0;
+        for (int w = threadIdx.x; w < W; w += UNION_T) {
+            uint32_t bits = 0;
+            for (int j = 0; j < 32; ++j) {
+                const int i = w * 32 + j;
+                if (i < P.n_leaf && (den_touched[i] | k0_touched[i]) != 0) bits |= 1u << j;
+            }
+            me.flags[parity][w] = bits;
+        }
     if (threadIdx.x == 0) running = 0;
     __syncthreads();   // the st.release.sys below is cumulative over the CTA's flag writes ordered by this barrier
     if (threadIdx.x < P.world) {
@@ -118,122 +115,120 @@ __global__ void __launch_bounds__(UNION_T) k_dp_union(pvdb_dp_peers P, uint32_t 
         wait_peer(P, threadIdx.x, SIG_A, epoch);
     }
     __syncthreads();
-    const int32_t* pf[8];
-    for (int r = 0; r < 8; ++r) pf[r] = view(P.base[r < P.world ? r : 0], P.n_leaf, P.cap_leaves).flags[parity];
-    for (int base = 0; base < P.n_leaf; base += UNION_T) {
-        const int i = base + threadIdx.x;
-        int f = 0;
-        if (i < P.n_leaf)
-            for (int r = 0; r < P.world; ++r) f |= __ldcv(pf[r] + i);
-        const bool t = f != 0;
-        if (i < P.n_leaf) {
-            den_touched[i] = t; k0_touched[i] = t;
-            // every peer has passed barrier A of this step, i.e. finished the union of the previous one: the other parity's flags
-            // have no reader left and are cleared for the emit kernel of the next step
-            me.flags[parity ^ 1][i] = 0;
+    const uint32_t* pf[8];
+    for (int r = 0; r < 8; ++r) pf[r] = view(P.base[r < P.world ? r : 0], P.n_leaf).flags[parity];
+    for (int base = 0; base < W; base += UNION_T * UNION_WPT) {
+        const int w0 = base + threadIdx.x * UNION_WPT;
+        uint32_t u[UNION_WPT];
+#pragma unroll
+        for (int k = 0; k < UNION_WPT; ++k) {
+            u[k] = 0;
+            if (w0 + k < W)
+                for (int r = 0; r < P.world; ++r) u[k] |= __ldcv(pf[r] + w0 + k);
         }
-        const unsigned bits = __ballot_sync(0xffffffffu, t);
-        if (lane == 0) warp_cnt[warp] = __popc(bits);
-        __syncthreads();
-        const int c = lane < UNION_T / 32 ? warp_cnt[lane] : 0;
-        int incl = c;
-        #pragma unroll
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < UNION_WPT; ++k) {
+            if (w0 + k < W) {
+                // every peer has passed barrier A of this step, i.e. finished the union of the previous one: the other parity's
+                // words have no reader left and are cleared for the emit kernel of the next step
+                me.flags[parity ^ 1][w0 + k] = 0;
+                if (w0 + k == W - 1 && (P.n_leaf & 31)) u[k] &= (1u << (P.n_leaf & 31)) - 1u;
+            }
+            cnt += __popc(u[k]);
+        }
+        int incl = cnt;
+#pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-        const int warp_off = __shfl_sync(0xffffffffu, incl - c, warp);
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int start = running;
-        if (t) {
-            const int slot = start + warp_off + __popc(bits & ((1u << lane) - 1));
-            den_list[slot] = i;
-            k0_list[slot] = i;
+        if (lane == 31) warp_cnt[warp] = incl;
+        __syncthreads();
+        int before = running;
+        for (int q = 0; q < warp; ++q) before += warp_cnt[q];
+        int total = 0;
+        for (int q = 0; q < UNION_T / 32; ++q) total += warp_cnt[q];
+        int slot = before + incl - cnt;
+#pragma unroll
+        for (int k = 0; k < UNION_WPT; ++k) {
+            if (w0 + k >= W) continue;
+            for (int j = 0; j < 32; ++j) {
+                const int i = (w0 + k) * 32 + j;
+                if (i >= P.n_leaf) break;
+                const int t = (u[k] >> j) & 1;
+                den_touched[i] = t; k0_touched[i] = t;
+                if (t) { den_list[slot] = i; k0_list[slot] = i; ++slot; }
+            }
         }
         __syncthreads();
-        if (threadIdx.x == 0) running = start + total;
+        if (threadIdx.x == 0) running += total;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        int n = running;
-        if (n > P.cap_leaves) { atomicExch(me.err, 2); n = P.cap_leaves; }
-        counters[cnt_den] = n;
-        counters[cnt_k0] = n;
+        counters[cnt_den] = running;
+        counters[cnt_k0] = running;
     }
 }
 
-__global__ void __launch_bounds__(256) k_dp_pack(pvdb_dp_peers P, uint32_t epoch, int parity, const float* __restrict__ den_grad,
-                                                 const float* __restrict__ k0_grad,
-                                                 const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
+// This rank's gradient planes are final: enqueued behind the kernels that scatter into them.
+__global__ void __launch_bounds__(32) k_dp_ready(pvdb_dp_peers P, uint32_t epoch) {
     pvdb_pdl_wait();
-    const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
-    const int n = counters[cnt_den];
-    float* buf = me.grad[parity];
-    constexpr int T4 = TILE_F / 4;
-    const int64_t total = (int64_t)n * T4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int slot = (int)(idx / T4), i = (int)(idx - (int64_t)slot * T4);
-        const int leaf = list[slot];
-        const float4 v = i < 128 ? reinterpret_cast<const float4*>(den_grad + (size_t)leaf * 512)[i]
-                                 : reinterpret_cast<const float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128];
-        reinterpret_cast<float4*>(buf)[idx] = v;
-    }
-    last_cta_signals<false>(P, me.done + 0, SIG_B, epoch);      // local stores only
+    if (threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_B, epoch);
+}
+// Every owner has stored its sums into this rank's planes.
+__global__ void __launch_bounds__(32) k_dp_wait(pvdb_dp_peers P, uint32_t epoch, int word) {
+    pvdb_pdl_wait();
+    if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, word, epoch);
 }
 
-// Reduce-scatter + all-gather: this rank sums the union slots it owns (slot % world == rank) over all ranks, in rank order, and
-// stores the sums into every rank's red[parity].
-// 128 threads: with its ~100 registers (eight float4 in flight per thread) a 256-thread CTA would not fit next to the persistent
-// weight-gradient CTA it is meant to run under.
-__global__ void __launch_bounds__(128) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, int parity, const int32_t* __restrict__ counters, int cnt_den) {
+// Reduce-scatter + all-gather: this rank sums the union leaves it owns (slot % world == rank) over all ranks' planes, in rank
+// order, and stores the sums into every rank's planes.  128 threads: with eight float4 in flight per thread (~100 registers) a
+// 256-thread CTA would not fit next to the persistent weight-gradient CTA it is meant to run under.
+__global__ void __launch_bounds__(128) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, const int32_t* __restrict__ list, const int32_t* __restrict__ counters,
+                                               int cnt_den) {
     pvdb_pdl_wait();
     if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_B, epoch);
     __syncthreads();
     const int n = counters[cnt_den];
-    const float4* pb[8];
-    float4* pr[8];
+    float4* pd[8];
+    float4* pk[8];
     for (int r = 0; r < 8; ++r) {
-        const Blk b = view(P.base[r < P.world ? r : 0], P.n_leaf, P.cap_leaves);
-        pb[r] = reinterpret_cast<const float4*>(b.grad[parity]);
-        pr[r] = reinterpret_cast<float4*>(b.red[parity]);
+        const Blk b = view(P.base[r < P.world ? r : 0], P.n_leaf);
+        pd[r] = reinterpret_cast<float4*>(b.den_grad);
+        pk[r] = reinterpret_cast<float4*>(b.k0_grad);
     }
-    constexpr int T4 = TILE_F / 4;
+    constexpr int T4 = PVDB_LEAF_VOX * 13 / 4;       // 128 float4 of density + 1536 of k0 per leaf
     const int mine = n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
     const int64_t total = (int64_t)mine * T4;
-    // plain loads: these peer addresses were last read two steps ago in another launch, and the acquire + barrier above
-    // orders them after the peers' packs
+    // plain loads: the acquire + barrier above orders them after the peers' scatter kernels, and nothing on this GPU has read
+    // these peer addresses since the previous step's exchange (another launch)
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int j = (int)(idx / T4), i = (int)(idx - (int64_t)j * T4);
-        const int64_t off = (int64_t)(P.rank + j * P.world) * T4 + i;
+        const int leaf = list[P.rank + j * P.world];
+        const bool is_den = i < 128;
+        const int64_t off = is_den ? (int64_t)leaf * 128 + i : (int64_t)leaf * 1536 + (i - 128);
         float4 v[8];
         #pragma unroll
         for (int r = 0; r < 8; ++r)
-            if (r < P.world) v[r] = pb[r][off];
+            if (r < P.world) v[r] = (is_den ? pd[r] : pk[r])[off];
         float4 s = v[0];
         #pragma unroll
         for (int r = 1; r < 8; ++r)
             if (r < P.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
         #pragma unroll
         for (int r = 0; r < 8; ++r)
-            if (r < P.world) pr[r][off] = s;
+            if (r < P.world) (is_den ? pd[r] : pk[r])[off] = s;
     }
-    last_cta_signals<true>(P, view(P.base[P.rank], P.n_leaf, P.cap_leaves).done + 1, SIG_D, epoch);
-}
-
-__global__ void __launch_bounds__(256) k_dp_unpack(pvdb_dp_peers P, uint32_t epoch, int parity, float* __restrict__ den_grad,
-                                                   float* __restrict__ k0_grad,
-                                                   const int32_t* __restrict__ list, const int32_t* __restrict__ counters, int cnt_den) {
-    pvdb_pdl_wait();
-    if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_D, epoch);
+    // last CTA out tells every peer that this rank's sums are in place (threadFenceReduction pattern with system-wide fences:
+    // the stores it publishes are peer stores; the final st.release.sys is cumulative over what the counter made visible)
+    __shared__ bool last;
+    uint32_t* done = view(P.base[P.rank], P.n_leaf).done + 1;
     __syncthreads();
-    const int n = counters[cnt_den];
-    const float4* red = reinterpret_cast<const float4*>(view(P.base[P.rank], P.n_leaf, P.cap_leaves).red[parity]);
-    constexpr int T4 = TILE_F / 4;
-    const int64_t total = (int64_t)n * T4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const float4 s = __ldcg(red + idx);          // written by the peers through NVLink: lives in L2, never in this SM's L1
-        const int slot = (int)(idx / T4), i = (int)(idx - (int64_t)slot * T4);
-        const int leaf = list[slot];
-        if (i < 128) reinterpret_cast<float4*>(den_grad + (size_t)leaf * 512)[i] = s;
-        else reinterpret_cast<float4*>(k0_grad + (size_t)leaf * 512 * 12)[i - 128] = s;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(done, 1u) == gridDim.x - 1;
+        if (last) { *done = 0; __threadfence_system(); }
     }
+    __syncthreads();
+    if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_D, epoch);
 }
 
 // Stand-alone rgbnet exchange (pvdb_dp_exchange_net): CTA `g` owns slice g of the 22 019 values end to end (publish, signal,
@@ -242,7 +237,7 @@ __global__ void __launch_bounds__(1024) k_dp_net(pvdb_dp_peers P, uint32_t epoch
     constexpr int SL = NET_PAD / NET_SLICES;       // floats per slice (multiple of 4)
     pvdb_pdl_wait();
     const int g = blockIdx.x;
-    const Blk me = view(P.base[P.rank], P.n_leaf, P.cap_leaves);
+    const Blk me = view(P.base[P.rank], P.n_leaf);
     const int i = g * SL + threadIdx.x * 4;
     const bool live = threadIdx.x * 4 < SL;
     float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -261,7 +256,7 @@ __global__ void __launch_bounds__(1024) k_dp_net(pvdb_dp_peers P, uint32_t epoch
     float4 v[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
-        if (r < P.world) v[r] = r == P.rank ? own : *reinterpret_cast<const float4*>(view(P.base[r], P.n_leaf, P.cap_leaves).net[parity] + i);
+        if (r < P.world) v[r] = r == P.rank ? own : *reinterpret_cast<const float4*>(view(P.base[r], P.n_leaf).net[parity] + i);
     float4 s = v[0];
 #pragma unroll
     for (int r = 1; r < 8; ++r)
@@ -275,16 +270,27 @@ __global__ void __launch_bounds__(1024) k_dp_net(pvdb_dp_peers P, uint32_t epoch
 int check_peers(const pvdb_dp_peers* P, const pvdb_train_bufs* b) {
     PVDB_CHECK_ARG(P && b && b->tree, "null pointer");
     PVDB_CHECK_ARG(P->world >= 1 && P->world <= 8 && P->rank >= 0 && P->rank < P->world, "world must be 1..8");
-    PVDB_CHECK_ARG(P->n_leaf == b->tree->n_leaf && P->cap_leaves >= 1, "peers block was sized for another tree");
+    PVDB_CHECK_ARG(P->n_leaf == b->tree->n_leaf, "peers block was sized for another tree");
     for (int r = 0; r < P->world; ++r) PVDB_CHECK_ARG(P->base[r], "peer block not mapped");
+    const Blk me = view(P->base[P->rank], P->n_leaf);
+    PVDB_CHECK_ARG(b->den_grad == me.den_grad && b->k0_grad == me.k0_grad,
+                   "the gradient planes must be the ones inside this rank's symmetric block (pvdb_dp_grad_planes; dist.PeerExchange binds them)");
     return PVDB_OK;
 }
 
 }  // namespace
 
 extern "C" size_t pvdb_dp_symm_bytes(int n_leaf, int cap_leaves) {
-    if (n_leaf < 0 || cap_leaves < 0) return 0;
-    return grad_off(n_leaf) + 4 * cap_floats(cap_leaves) * sizeof(float);
+    (void)cap_leaves;
+    if (n_leaf < 0) return 0;
+    return k0_off(n_leaf) + (size_t)(n_leaf > 0 ? n_leaf : 1) * PVDB_LEAF_VOX * 12 * sizeof(float);
+}
+extern "C" int pvdb_dp_grad_planes(const pvdb_dp_peers* P, float** den_grad, float** k0_grad) {
+    PVDB_CHECK_ARG(P && den_grad && k0_grad && P->rank >= 0 && P->rank < 8 && P->base[P->rank], "bad peers");
+    const Blk me = view(P->base[P->rank], P->n_leaf);
+    *den_grad = me.den_grad;
+    *k0_grad = me.k0_grad;
+    return PVDB_OK;
 }
 extern "C" int pvdb_dp_symm_alloc(size_t bytes, void** ptr, void* handle64) {
     PVDB_CHECK_ARG(ptr && handle64 && bytes > 0, "null pointer / zero size");
@@ -312,7 +318,7 @@ extern "C" int pvdb_dp_symm_free(void* ptr) {
 }
 extern "C" int pvdb_dp_symm_error(const pvdb_dp_peers* P, int32_t* err_out) {
     PVDB_CHECK_ARG(P && err_out && P->rank >= 0 && P->rank < 8 && P->base[P->rank], "bad peers");
-    PVDB_CUDA(cudaMemcpy(err_out, view(P->base[P->rank], P->n_leaf, P->cap_leaves).err, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    PVDB_CUDA(cudaMemcpy(err_out, view(P->base[P->rank], P->n_leaf).err, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return PVDB_OK;
 }
 
@@ -329,18 +335,16 @@ static int exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint
         pvdb_prof_mark("dp_union", st);
     }
     if (!do_move) return PVDB_OK;
-    // grids sized for the F160 case (74 union leaves = 2 MB: latency bound) and grid-striding for S512 (~0.5 GB)
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_pack, dim3(PVDB_SMS), dim3(256), 0, st, *P, epoch, parity, (const float*)b->den_grad, (const float*)b->k0_grad,
-                              (const int32_t*)b->den_touched_list, (const int32_t*)b->counters, CNT_DEN));
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_ready, dim3(1), dim3(32), 0, st, *P, epoch));
     PVDB_LAUNCH_CHECK();
-    pvdb_prof_mark("dp_pack", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS * 4), dim3(128), 0, st, *P, epoch, parity, (const int32_t*)b->counters, CNT_DEN));
+    // grid sized for the F160 case (74 union leaves = 2 MB: latency bound) and grid-striding for S512 (~0.5 GB)
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS * 4), dim3(128), 0, st, *P, epoch, (const int32_t*)b->den_touched_list,
+                              (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_rs", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_unpack, dim3(PVDB_SMS), dim3(256), 0, st, *P, epoch, parity, b->den_grad, b->k0_grad,
-                              (const int32_t*)b->den_touched_list, (const int32_t*)b->counters, CNT_DEN));
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_wait, dim3(1), dim3(32), 0, st, *P, epoch, (int)SIG_D));
     PVDB_LAUNCH_CHECK();
-    pvdb_prof_mark("dp_unpack", st);
+    pvdb_prof_mark("dp_wait", st);
     return PVDB_OK;
 }
 
@@ -354,24 +358,24 @@ int pvdb_dp_union_early(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32
 int pvdb_dp_move_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st) {
     return exchange_tiles(P, b, step, st, false, 0, true);
 }
-int32_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step) {
-    return view(P->base[P->rank], P->n_leaf, P->cap_leaves).flags[step & 1];
+uint32_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step) {
+    return view(P->base[P->rank], P->n_leaf).flags[step & 1];
 }
 // Arguments for the kernels that carry the rgbnet exchange of the fused step (dp_exchange.cuh).
 PvdbDpNetPush pvdb_dp_net_push_args(const pvdb_dp_peers* P, uint32_t step) {
     PvdbDpNetPush a;
     a.world = P->world; a.rank = P->rank; a.epoch = step + 1;
     for (int r = 0; r < 8; ++r) {
-        const Blk b = view(P->base[r < P->world ? r : 0], P->n_leaf, P->cap_leaves);
+        const Blk b = view(P->base[r < P->world ? r : 0], P->n_leaf);
         a.dst[r] = b.netx[step & 1] + (size_t)P->rank * NET_PAD;
         a.signal[r] = b.signal + SIG_C + P->rank;
     }
-    a.done = view(P->base[P->rank], P->n_leaf, P->cap_leaves).done + 2;
+    a.done = view(P->base[P->rank], P->n_leaf).done + 2;
     return a;
 }
 PvdbDpNetWait pvdb_dp_net_wait_args(const pvdb_dp_peers* P, uint32_t step) {
     PvdbDpNetWait a;
-    const Blk me = view(P->base[P->rank], P->n_leaf, P->cap_leaves);
+    const Blk me = view(P->base[P->rank], P->n_leaf);
     a.world = P->world; a.epoch = step + 1;
     a.src = me.netx[step & 1];
     a.signal = me.signal + SIG_C;

@@ -24,6 +24,6 @@ struct PvdbDpNetWait {        // consumer side: the rgbnet Adam CTAs of k_update
 
 int pvdb_dp_union_early(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st);
 int pvdb_dp_move_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st);
-int32_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step);
+uint32_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step);   // bit per leaf
 PvdbDpNetPush pvdb_dp_net_push_args(const pvdb_dp_peers* P, uint32_t step);
 PvdbDpNetWait pvdb_dp_net_wait_args(const pvdb_dp_peers* P, uint32_t step);

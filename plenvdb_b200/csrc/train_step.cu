@@ -156,17 +156,21 @@ struct MarchOut {
     uint4* scratch; int scr_cap;
     // data-parallel step only: this rank's touched-leaf flags in its symmetric block (dp_exchange.cu).  The sample lists
     // determine the touched leaves before any gradient exists, so the cross-GPU union runs under the rgbnet forward.
-    int32_t* dp_flags;
+    uint32_t* dp_flags;      // one bit per leaf
 };
 
 // Flag the leaves of the eight corners of one alpha-list sample (every such sample feeds the density gradient, the kept ones
-// the k0 gradient as well).  Plain stores of 1: benign races.
-__device__ __forceinline__ void dp_flag_corners(int32_t* __restrict__ flags, const int* rec) {
+// the k0 gradient as well).  One atomicOr per leaf and warp at most (the plain read filters the rest).
+__device__ __forceinline__ void dp_flag_corners(uint32_t* __restrict__ flags, const int* rec) {
     int prev = -1;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int leaf = rec[q] >> 9;      // -1 stays -1
-        if (rec[q] >= 0 && leaf != prev) { flags[leaf] = 1; prev = leaf; }
+        if (rec[q] >= 0 && leaf != prev) {
+            const uint32_t bit = 1u << (leaf & 31);
+            if (!(flags[leaf >> 5] & bit)) atomicOr(flags + (leaf >> 5), bit);     // the plain read filters almost every call
+            prev = leaf;
+        }
     }
 }
 

@@ -93,6 +93,30 @@ class PeerExchange:
             self.peers.base[r] = bases[r]
         self.step = 0
         self.nbytes = nbytes
+        # the gradient planes inside the own block: the exchange works on the ranks' planes in place
+        pd, pk = C.c_void_p(), C.c_void_p()
+        _lib.call("pvdb_dp_grad_planes", C.byref(self.peers), C.byref(pd), C.byref(pk))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nl = max(int(n_leaf), 1)
+        self.den_grad = _lib.tensor_from_ptr(pd.value, (nl, 512, 1), dev)
+        self.k0_grad = _lib.tensor_from_ptr(pk.value, (nl, 512, 12), dev)
+
+    def bind(self, trainer):
+        """Make the trainer's grids accumulate their gradients in this block's planes (they are what the peers read and write)."""
+        den, k0 = trainer.density, trainer.k0
+        self.den_grad.copy_(den.grad)
+        self.k0_grad.copy_(k0.grad)
+        den._set_topology(den.topo, den.grid, self.den_grad)
+        k0._set_topology(k0.topo, k0.grid, self.k0_grad)
+        trainer.rebind(trainer.den_m, trainer.den_v, trainer.k0_m, trainer.k0_v)
+
+    def unbind(self, trainer):
+        """Give the grids ordinary gradient planes again (before the block is freed)."""
+        den, k0 = trainer.density, trainer.k0
+        if den.grad.data_ptr() == self.den_grad.data_ptr():
+            den._set_topology(den.topo, den.grid, self.den_grad.clone())
+            k0._set_topology(k0.topo, k0.grid, self.k0_grad.clone())
+            trainer.rebind(trainer.den_m, trainer.den_v, trainer.k0_m, trainer.k0_v)
 
     def exchange(self, bufs):
         self._lib.call("pvdb_dp_exchange", self._C.byref(self.peers), self._C.byref(bufs), self.step, self._lib.current_stream())
@@ -108,6 +132,7 @@ class PeerExchange:
         barrier does a rank free its own block (CUDA IPC leaves freeing a block that a peer still maps undefined)."""
         if self._own is None and not self._opened:
             return
+        self.den_grad = self.k0_grad = None
         close_symmetric_blocks(self._own, self._opened, self._group, barrier=True)
         self._own, self._opened = None, []
 
@@ -140,6 +165,7 @@ class DataParallelTrainer:
         if self.world > 1 and exchange == "nvlink":
             try:
                 self.peer = PeerExchange(tr.topo.n_leaf, group=self.group)
+                self.peer.bind(tr)
                 return
             except PeerExchangeUnavailable as e:      # raised on all ranks together: fall back to NCCL everywhere
                 import warnings
@@ -198,13 +224,14 @@ class DataParallelTrainer:
         if self.peer is not None:
             n, w = int(self.tr.t["counters"][2].item()), self.world
             own = (n - self.peer.rank + w - 1) // w if n > self.peer.rank else 0       # union slots this rank reduces
-            tiles = 2 * (w - 1) * own * 512 * 13 * 4          # peer loads of the owned slots + peer stores of their sums
-            return tiles + (w - 1) * 22019 * 4 + (w - 1) * self.tr.topo.n_leaf * 4     # + rgbnet pushes + the peers' flags
+            tiles = 2 * (w - 1) * own * 512 * 13 * 4          # peer loads of the owned leaves + peer stores of their sums
+            return tiles + (w - 1) * 22019 * 4 + (w - 1) * ((self.tr.topo.n_leaf + 31) // 32) * 4     # + rgbnet pushes + the peers' flag words
         return self.last_exchange_bytes
 
     def close(self):
         """Collective: releases the NVLink symmetric blocks (no-op for the NCCL exchange)."""
         if self.peer is not None:
+            self.peer.unbind(self.tr)
             self.peer.close()
             self.peer = None
 
