@@ -5,7 +5,7 @@
 //                owner: A[src] flags published, B[src] gradients final, D[src] sums delivered, C[src] rgbnet gradients delivered,
 //                CS[slice][src] (stand-alone rgbnet exchange)
 //   [448,512)    err, last-CTA counters
-//   [1024,..)    flags[2][ceil(n_leaf / 32)] u32   touched-leaf BITS published by the owner (double-buffered by step parity)
+//   [1024,..)    flags[2][n_leaf rounded up to 16] u8   touched-leaf flags published by the owner (double-buffered by step parity)
 //   [net_off,.)  net[2][NET_PAD]  f32      stand-alone rgbnet exchange: the owner's gradients, read by the peers
 //   [netx_off,.) netx[2][8][NET_PAD] f32   fused rgbnet exchange: slot [src] is WRITTEN BY rank src (peer stores)
 //   [den_off,.)  den_grad[n_leaf][512]     THE gradient planes of this rank's grids (dist.py binds DensityVDB.grad /
@@ -13,12 +13,11 @@
 //
 // No host synchronisation, no NCCL call, no staging copy.  Per step and rank the NVLink traffic is O(1) in the number of ranks:
 //   k_dp_union   1 CTA : cross-GPU barrier A -> OR of all peers' flag words -> ascending union list (identical everywhere)
-//   k_dp_ready   1 warp: this rank's gradient planes are final (signal B)
-//   k_dp_rs      grid  : reduce-scatter + all-gather in one kernel.  Rank r owns the union slots s with s % world == r: it
+//   k_dp_rs      grid  : signals B (this rank's planes are final), then reduce-scatter + all-gather in one kernel.  Rank r owns the union slots s with s % world == r: it
 //                        reads that leaf's tile from every rank's planes (world - 1 peer loads of 1/world of the data), sums in
 //                        rank order (identical bits everywhere) and stores the sum into EVERY rank's planes (world - 1 peer
 //                        stores); the last CTA signals D
-//   k_dp_wait    1 warp: all owners have delivered (wait for D) — in front of the sparse Adam
+//   k_dp_wait    1 warp: all owners have delivered (wait for D) — stand-alone exchange; in the fused step the leaf Adam waits itself
 // The rgbnet gradients (88 KB) ride on the kernels that produce and consume them: the weight-gradient reduction stores its
 // sums straight into every peer's netx[parity][rank] (pvdb_dp_net_push_args) and the rgbnet Adam waits for C and adds the
 // world slots of its own block in rank order (pvdb_dp_net_wait_args) — no exchange kernel at all on that path.
@@ -44,14 +43,14 @@ struct Blk {
     uint32_t* signal;
     int32_t* err;
     uint32_t* done;      // [4] last-CTA counters
-    uint32_t* flags[2];  // bit per leaf
+    uint8_t* flags[2];   // byte per leaf, rows padded to 16 bytes
     float* net[2];
     float* netx[2];      // [8][NET_PAD] each
     float* den_grad;
     float* k0_grad;
 };
-__host__ __device__ inline int flag_words(int n_leaf) { return (n_leaf + 31) >> 5; }
-__host__ __device__ inline size_t net_off(int n_leaf) { return (1024 + (size_t)8 * flag_words(n_leaf) + 255) & ~(size_t)255; }
+__host__ __device__ inline int flag_bytes(int n_leaf) { return (n_leaf + 15) & ~15; }
+__host__ __device__ inline size_t net_off(int n_leaf) { return (1024 + (size_t)2 * flag_bytes(n_leaf) + 255) & ~(size_t)255; }
 __host__ __device__ inline size_t netx_off(int n_leaf) { return net_off(n_leaf) + 2 * (size_t)NET_PAD * sizeof(float); }
 __host__ __device__ inline size_t den_off(int n_leaf) { return netx_off(n_leaf) + 2 * 8 * (size_t)NET_PAD * sizeof(float); }
 __host__ __device__ inline size_t k0_off(int n_leaf) { return den_off(n_leaf) + (size_t)(n_leaf > 0 ? n_leaf : 1) * PVDB_LEAF_VOX * sizeof(float); }
@@ -61,8 +60,8 @@ __host__ __device__ inline Blk view(void* base, int n_leaf) {
     b.signal = reinterpret_cast<uint32_t*>(p);
     b.err = reinterpret_cast<int32_t*>(p + 448);
     b.done = reinterpret_cast<uint32_t*>(p + 452);
-    b.flags[0] = reinterpret_cast<uint32_t*>(p + 1024);
-    b.flags[1] = b.flags[0] + flag_words(n_leaf);
+    b.flags[0] = reinterpret_cast<uint8_t*>(p + 1024);
+    b.flags[1] = b.flags[0] + flag_bytes(n_leaf);
     b.net[0] = reinterpret_cast<float*>(p + net_off(n_leaf));
     b.net[1] = b.net[0] + NET_PAD;
     b.netx[0] = reinterpret_cast<float*>(p + netx_off(n_leaf));
@@ -89,53 +88,67 @@ __device__ __forceinline__ void wait_peer(const pvdb_dp_peers& P, int peer, int 
 // run of flag words, so that all of its peer loads are in flight together (one NVLink latency) and the list comes out in
 // ascending leaf order.
 constexpr int UNION_T = 256;
-constexpr int UNION_WPT = 4;                      // words per thread and round: 256 x 4 x 32 = 32 768 leaves per round
+constexpr int UNION_WORDS = 1024;                 // flag words per round: 32 768 leaves
 __global__ void __launch_bounds__(UNION_T) k_dp_union(pvdb_dp_peers P, uint32_t epoch, int parity, int publish, int32_t* __restrict__ den_touched,
                                                       int32_t* __restrict__ k0_touched, int32_t* __restrict__ den_list,
-                                                      int32_t* __restrict__ k0_list, int32_t* __restrict__ counters, int cnt_den, int cnt_k0) {
+                                                      int32_t* __restrict__ k0_list, int32_t* __restrict__ counters, int cnt_den, int cnt_k0,
+                                                      unsigned long long* __restrict__ dbg) {
     __shared__ int warp_cnt[UNION_T / 32];
     __shared__ int running;
+    __shared__ uint32_t s_word[UNION_WORDS];
+    __shared__ int s_pre[UNION_WORDS];
     pvdb_pdl_wait();
+    if (dbg && threadIdx.x == 0) dbg[20] = globaltimer();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Blk me = view(P.base[P.rank], P.n_leaf);
-    const int W = flag_words(P.n_leaf);
+    const int NB = flag_bytes(P.n_leaf) / 16;          // 16-byte groups of flags
+    const int W = (P.n_leaf + 31) >> 5;                // union bit words
     if (publish)
-        for (int w = threadIdx.x; w < W; w += UNION_T) {
-            uint32_t bits = 0;
-            for (int j = 0; j < 32; ++j) {
-                const int i = w * 32 + j;
-                if (i < P.n_leaf && (den_touched[i] | k0_touched[i]) != 0) bits |= 1u << j;
-            }
-            me.flags[parity][w] = bits;
-        }
+        for (int i = threadIdx.x; i < P.n_leaf; i += UNION_T) me.flags[parity][i] = (den_touched[i] | k0_touched[i]) != 0;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();   // the st.release.sys below is cumulative over the CTA's flag writes ordered by this barrier
+    if (dbg && threadIdx.x == 0) dbg[21] = globaltimer();
     if (threadIdx.x < P.world) {
         signal_peer(P, threadIdx.x, SIG_A, epoch);
+        if (dbg && threadIdx.x == 0) dbg[22] = globaltimer();
         wait_peer(P, threadIdx.x, SIG_A, epoch);
     }
     __syncthreads();
-    const uint32_t* pf[8];
-    for (int r = 0; r < 8; ++r) pf[r] = view(P.base[r < P.world ? r : 0], P.n_leaf).flags[parity];
-    for (int base = 0; base < W; base += UNION_T * UNION_WPT) {
-        const int w0 = base + threadIdx.x * UNION_WPT;
-        uint32_t u[UNION_WPT];
+    if (dbg && threadIdx.x == 0) dbg[23] = globaltimer();
+    const uint4* pf[8];
+    for (int r = 0; r < 8; ++r) pf[r] = reinterpret_cast<const uint4*>(view(P.base[r < P.world ? r : 0], P.n_leaf).flags[parity]);
+    uint4* other = reinterpret_cast<uint4*>(me.flags[parity ^ 1]);
+    // rounds of UNION_WORDS bit words (32 768 leaves): the ranks' byte flags are OR-ed 16 at a time into bit words in shared
+    // memory, then the exclusive popcount prefix of the words, then one thread per LEAF writes the int flags and the list entry
+    // (ascending leaf order)
+    for (int base = 0; base < W; base += UNION_WORDS) {
+        const int nw = min(UNION_WORDS, W - base);
+        for (int w = threadIdx.x; w < nw; w += UNION_T) s_word[w] = 0;
+        __syncthreads();
+        const int g0 = base * 2, ng = min(nw * 2, NB - g0);            // 16-byte groups of this round (two per word)
+        for (int g = threadIdx.x; g < ng; g += UNION_T) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            for (int r = 0; r < P.world; ++r) {                        // independent loads: one NVLink latency
+                const uint4 v = __ldcv(pf[r] + g0 + g);
+                u.x |= v.x; u.y |= v.y; u.z |= v.z; u.w |= v.w;
+            }
+            // every peer has passed barrier A of this step, i.e. finished the union of the previous one: the other parity's
+            // flags have no reader left and are cleared for the emit kernel of the next step
+            other[g0 + g] = make_uint4(0, 0, 0, 0);
+            uint32_t bits = 0;
+            const uint32_t q[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int k = 0; k < UNION_WPT; ++k) {
-            u[k] = 0;
-            if (w0 + k < W)
-                for (int r = 0; r < P.world; ++r) u[k] |= __ldcv(pf[r] + w0 + k);
+            for (int k = 0; k < 16; ++k) bits |= ((q[k >> 2] >> ((k & 3) * 8)) & 0xffu ? 1u : 0u) << k;
+            if (bits) atomicOr(&s_word[g >> 1], bits << ((g & 1) * 16));
         }
+        __syncthreads();
+        // exclusive prefix of the popcounts: UNION_WORDS / UNION_T consecutive words per thread, then a block scan
+        constexpr int WPT = UNION_WORDS / UNION_T;
         int cnt = 0;
 #pragma unroll
-        for (int k = 0; k < UNION_WPT; ++k) {
-            if (w0 + k < W) {
-                // every peer has passed barrier A of this step, i.e. finished the union of the previous one: the other parity's
-                // words have no reader left and are cleared for the emit kernel of the next step
-                me.flags[parity ^ 1][w0 + k] = 0;
-                if (w0 + k == W - 1 && (P.n_leaf & 31)) u[k] &= (1u << (P.n_leaf & 31)) - 1u;
-            }
-            cnt += __popc(u[k]);
+        for (int k = 0; k < WPT; ++k) {
+            const int w = threadIdx.x * WPT + k;
+            if (w < nw) cnt += __popc(s_word[w]);
         }
         int incl = cnt;
 #pragma unroll
@@ -146,16 +159,21 @@ __global__ void __launch_bounds__(UNION_T) k_dp_union(pvdb_dp_peers P, uint32_t 
         for (int q = 0; q < warp; ++q) before += warp_cnt[q];
         int total = 0;
         for (int q = 0; q < UNION_T / 32; ++q) total += warp_cnt[q];
-        int slot = before + incl - cnt;
+        int run = before + incl - cnt;
 #pragma unroll
-        for (int k = 0; k < UNION_WPT; ++k) {
-            if (w0 + k >= W) continue;
-            for (int j = 0; j < 32; ++j) {
-                const int i = (w0 + k) * 32 + j;
-                if (i >= P.n_leaf) break;
-                const int t = (u[k] >> j) & 1;
-                den_touched[i] = t; k0_touched[i] = t;
-                if (t) { den_list[slot] = i; k0_list[slot] = i; ++slot; }
+        for (int k = 0; k < WPT; ++k) {
+            const int w = threadIdx.x * WPT + k;
+            if (w < nw) { s_pre[w] = run; run += __popc(s_word[w]); }
+        }
+        __syncthreads();
+        const int leaf0 = base * 32, nleaf = min(nw * 32, P.n_leaf - leaf0);
+        for (int j = threadIdx.x; j < nleaf; j += UNION_T) {
+            const uint32_t u = s_word[j >> 5];
+            const int t = (u >> (j & 31)) & 1;      // bits of padding leaves (>= n_leaf) are never set: their flags are never written
+            den_touched[leaf0 + j] = t; k0_touched[leaf0 + j] = t;
+            if (t) {
+                const int slot = s_pre[j >> 5] + __popc(u & ((1u << (j & 31)) - 1u));
+                den_list[slot] = leaf0 + j; k0_list[slot] = leaf0 + j;
             }
         }
         __syncthreads();
@@ -165,14 +183,10 @@ __global__ void __launch_bounds__(UNION_T) k_dp_union(pvdb_dp_peers P, uint32_t 
     if (threadIdx.x == 0) {
         counters[cnt_den] = running;
         counters[cnt_k0] = running;
+        if (dbg) dbg[24] = globaltimer();
     }
 }
 
-// This rank's gradient planes are final: enqueued behind the kernels that scatter into them.
-__global__ void __launch_bounds__(32) k_dp_ready(pvdb_dp_peers P, uint32_t epoch) {
-    pvdb_pdl_wait();
-    if (threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_B, epoch);
-}
 // Every owner has stored its sums into this rank's planes.
 __global__ void __launch_bounds__(32) k_dp_wait(pvdb_dp_peers P, uint32_t epoch, int word) {
     pvdb_pdl_wait();
@@ -185,6 +199,8 @@ __global__ void __launch_bounds__(32) k_dp_wait(pvdb_dp_peers P, uint32_t epoch,
 __global__ void __launch_bounds__(128) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, const int32_t* __restrict__ list, const int32_t* __restrict__ counters,
                                                int cnt_den) {
     pvdb_pdl_wait();
+    // this kernel is enqueued behind the kernels that scatter into this rank's planes: they are final (signal B, first CTA)
+    if (blockIdx.x == 0 && threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_B, epoch);
     if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_B, epoch);
     __syncthreads();
     const int n = counters[cnt_den];
@@ -322,43 +338,56 @@ extern "C" int pvdb_dp_symm_error(const pvdb_dp_peers* P, int32_t* err_out) {
     return PVDB_OK;
 }
 
+// Kernels meant to run on an SM NEXT TO a persistent tcgen05 CTA ask for the same shared-memory carve-out as that CTA (maximum
+// shared memory): an SM is configured for one carve-out at a time, and a CTA that prefers another one waits until the SM drains.
+template <typename K>
+static void prefer_max_smem(K kernel) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
+static void dp_kernel_attrs() {
+    static bool done = false;
+    if (done) return;
+    prefer_max_smem(k_dp_union); prefer_max_smem(k_dp_rs); prefer_max_smem(k_dp_wait);
+    done = true;
+}
+
 static int exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st, bool do_union, int publish,
-                          bool do_move) {
+                          bool do_move, bool wait_sums) {
     if (int rc = check_peers(P, b)) return rc;
+    dp_kernel_attrs();
     const int parity = step & 1;
     const uint32_t epoch = step + 1;                        // monotone; the signal words start at 0
     const int CNT_DEN = 2, CNT_K0 = 4;                      // counters[] slots of pvdb_train_bufs (include/plenvdb_b200.h)
     if (do_union) {
         PVDB_CUDA(pvdb_launch_pdl(k_dp_union, dim3(1), dim3(UNION_T), 0, st, *P, epoch, parity, publish, b->den_touched, b->k0_touched,
-                                  b->den_touched_list, b->k0_touched_list, b->counters, CNT_DEN, CNT_K0));
+                                  b->den_touched_list, b->k0_touched_list, b->counters, CNT_DEN, CNT_K0, pvdb_debug_stamps_ptr()));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("dp_union", st);
     }
     if (!do_move) return PVDB_OK;
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_ready, dim3(1), dim3(32), 0, st, *P, epoch));
-    PVDB_LAUNCH_CHECK();
-    // grid sized for the F160 case (74 union leaves = 2 MB: latency bound) and grid-striding for S512 (~0.5 GB)
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS * 4), dim3(128), 0, st, *P, epoch, (const int32_t*)b->den_touched_list,
+    // ONE wave of CTAs (one fits on each SM next to the persistent weight-gradient CTA), grid-striding over the owned tiles:
+    // 74 union leaves = 2 MB at F160 (latency bound), ~0.5 GB at S512
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS), dim3(128), 0, st, *P, epoch, (const int32_t*)b->den_touched_list,
                               (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_rs", st);
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_wait, dim3(1), dim3(32), 0, st, *P, epoch, (int)SIG_D));
-    PVDB_LAUNCH_CHECK();
-    pvdb_prof_mark("dp_wait", st);
+    if (wait_sums) {
+        PVDB_CUDA(pvdb_launch_pdl(k_dp_wait, dim3(1), dim3(32), 0, st, *P, epoch, (int)SIG_D));
+        PVDB_LAUNCH_CHECK();
+        pvdb_prof_mark("dp_wait", st);
+    }
     return PVDB_OK;
 }
 
 extern "C" int pvdb_dp_exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, void* stream) {
-    return exchange_tiles(P, b, step, (cudaStream_t)stream, true, 1, true);
+    return exchange_tiles(P, b, step, (cudaStream_t)stream, true, 1, true, true);
 }
 // The fused step's two halves: the union alone (flags already written by the emit kernel), and pack / reduce / unpack alone.
 int pvdb_dp_union_early(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st) {
-    return exchange_tiles(P, b, step, st, true, 0, false);
+    return exchange_tiles(P, b, step, st, true, 0, false, false);
 }
 int pvdb_dp_move_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st) {
-    return exchange_tiles(P, b, step, st, false, 0, true);
+    return exchange_tiles(P, b, step, st, false, 0, true, false);   // the leaf Adam waits for the sums itself
 }
-uint32_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step) {
+uint8_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step) {
     return view(P->base[P->rank], P->n_leaf).flags[step & 1];
 }
 // Arguments for the kernels that carry the rgbnet exchange of the fused step (dp_exchange.cuh).
@@ -371,6 +400,12 @@ PvdbDpNetPush pvdb_dp_net_push_args(const pvdb_dp_peers* P, uint32_t step) {
         a.signal[r] = b.signal + SIG_C + P->rank;
     }
     a.done = view(P->base[P->rank], P->n_leaf).done + 2;
+    return a;
+}
+PvdbDpTilesWait pvdb_dp_tiles_wait_args(const pvdb_dp_peers* P, uint32_t step) {
+    PvdbDpTilesWait a;
+    const Blk me = view(P->base[P->rank], P->n_leaf);
+    a.world = P->world; a.epoch = step + 1; a.signal = me.signal + SIG_D; a.err = me.err;
     return a;
 }
 PvdbDpNetWait pvdb_dp_net_wait_args(const pvdb_dp_peers* P, uint32_t step) {

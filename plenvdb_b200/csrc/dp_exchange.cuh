@@ -22,8 +22,16 @@ struct PvdbDpNetWait {        // consumer side: the rgbnet Adam CTAs of k_update
     int32_t* err;
 };
 
+struct PvdbDpTilesWait {      // consumer side of the tile exchange: the leaf-Adam CTAs of k_update_fused
+    int world;
+    uint32_t epoch;
+    const uint32_t* signal;   // own D[0..world)
+    int32_t* err;
+};
+PvdbDpTilesWait pvdb_dp_tiles_wait_args(const pvdb_dp_peers* P, uint32_t step);
 int pvdb_dp_union_early(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st);
 int pvdb_dp_move_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint32_t step, cudaStream_t st);
-uint32_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step);   // bit per leaf
+uint8_t* pvdb_dp_flags_ptr(const pvdb_dp_peers* P, uint32_t step);   // byte per leaf
 PvdbDpNetPush pvdb_dp_net_push_args(const pvdb_dp_peers* P, uint32_t step);
 PvdbDpNetWait pvdb_dp_net_wait_args(const pvdb_dp_peers* P, uint32_t step);
+unsigned long long* pvdb_debug_stamps_ptr();   // train_step.cu: debug timeline (nullptr when off)

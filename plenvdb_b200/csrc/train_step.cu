@@ -156,21 +156,16 @@ struct MarchOut {
     uint4* scratch; int scr_cap;
     // data-parallel step only: this rank's touched-leaf flags in its symmetric block (dp_exchange.cu).  The sample lists
     // determine the touched leaves before any gradient exists, so the cross-GPU union runs under the rgbnet forward.
-    uint32_t* dp_flags;      // one bit per leaf
+    uint8_t* dp_flags;       // one byte per leaf; plain stores of 1 (idempotent: no atomics, benign races)
 };
 
 // Flag the leaves of the eight corners of one alpha-list sample (every such sample feeds the density gradient, the kept ones
-// the k0 gradient as well).  One atomicOr per leaf and warp at most (the plain read filters the rest).
-__device__ __forceinline__ void dp_flag_corners(uint32_t* __restrict__ flags, const int* rec) {
-    int prev = -1;
+// the k0 gradient as well).  Plain stores of 1, skipped while a lane stays in the leaf it flagged last.
+__device__ __forceinline__ void dp_flag_corners(uint8_t* __restrict__ flags, const int* rec, int& last_leaf) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int leaf = rec[q] >> 9;      // -1 stays -1
-        if (rec[q] >= 0 && leaf != prev) {
-            const uint32_t bit = 1u << (leaf & 31);
-            if (!(flags[leaf >> 5] & bit)) atomicOr(flags + (leaf >> 5), bit);     // the plain read filters almost every call
-            prev = leaf;
-        }
+        if (rec[q] >= 0 && leaf != last_leaf) { flags[leaf] = 1; last_leaf = leaf; }     // consecutive samples mostly share the leaf
     }
 }
 
@@ -188,6 +183,7 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
 
     float T_cum = 1.f;
     bool stopped = false;
+    int dp_last_leaf = -1;
     int n_mask = 0, n_alpha = 0, n_keep = 0, n_alpha_full = 0;
     int64_t oa = 0, ok = 0;
     if (MODE == 1) { oa = O.off_alpha[r]; ok = O.off_keep[r]; }
@@ -304,7 +300,7 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
             }
         }
         if (MODE == 1 && my_ai >= 0) {
-            if (O.dp_flags) dp_flag_corners(O.dp_flags, rec);
+            if (O.dp_flags) dp_flag_corners(O.dp_flags, rec, dp_last_leaf);
             const int64_t ia = oa + my_ai;
             if (ia < O.cap_alpha) {
                 O.s_ray[ia] = r; O.s_step[ia] = step;
@@ -371,6 +367,7 @@ __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O,
     const int na = O.cnt_alpha[r];
     if (na > O.scr_cap) { march_ray<1, false>(P, O, rays_o, rays_d, r, lane); return; }
     const int64_t oa = O.off_alpha[r], ok = O.off_keep[r];
+    int dp_last_leaf = -1;
     for (int i = lane; i < na; i += 32) {
         const uint4* e = O.scratch + ((int64_t)r * O.scr_cap + i) * 5;
         const uint4 e0 = e[0], e1 = e[1], e2 = e[2];
@@ -386,7 +383,7 @@ __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O,
         if (O.dp_flags) {
             const uint4 c0 = e[3], c1 = e[4];
             const int rec[8] = {(int)c0.x, (int)c0.y, (int)c0.z, (int)c0.w, (int)c1.x, (int)c1.y, (int)c1.z, (int)c1.w};
-            dp_flag_corners(O.dp_flags, rec);
+            dp_flag_corners(O.dp_flags, rec, dp_last_leaf);
         }
         if (ki >= 0) {
             const int64_t ik = ok + ki;
@@ -704,6 +701,9 @@ struct UpdateArgs {
     float den_stepsz, k0_stepsz, net_stepsize, eps, b0, b1;
     int leaf_blocks;
     int block_offset;   // 0: leaf work starts at CTA 0; leaf_blocks: a launch of the rgbnet Adam CTAs only
+    const uint32_t* dp_tiles_signal;   // data-parallel step: D[0..world) of the own block — every owner has stored its sums into
+    uint32_t dp_tiles_epoch;           // this rank's gradient planes once these words reached the epoch (nullptr: no wait)
+    int dp_world; int32_t* dp_err;
     const float* scalars;   // optional device array {den_stepsz, k0_stepsz, net_stepsize}: overrides the three values above (CUDA-graph replay)
     PvdbDpNetWait dp;   // dp.world > 1: the rgbnet gradient is the rank-ordered sum of the world slots the peers pushed into this block
 };
@@ -727,6 +727,10 @@ __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
             U.net_g[i] = 0.f;
         }
         return;
+    }
+    if (U.dp_tiles_signal) {
+        if (threadIdx.x < U.dp_world) wait_epoch(U.dp_tiles_signal + threadIdx.x, U.dp_tiles_epoch, U.dp_err, 1);
+        __syncthreads();
     }
     const int nd = U.counters[CNT_N_TOUCHED_DEN], nk = U.counters[CNT_N_TOUCHED_K0];
     const float omb0 = __fsub_rn(1.0f, U.b0), omb1 = __fsub_rn(1.0f, U.b1);
@@ -812,6 +816,12 @@ static void stamp(cudaStream_t st, int slot) {
     if (!g_stamps_on) return;
     if (!g_stamps) { cudaMalloc(&g_stamps, 64 * sizeof(unsigned long long)); cudaMemset(g_stamps, 0, 64 * sizeof(unsigned long long)); }
     k_stamp<<<1, 1, 0, st>>>(g_stamps, slot);
+}
+unsigned long long* pvdb_debug_stamps_ptr() {      // device array of 64 stamps, or nullptr when stamping is off (dp_exchange.cu)
+    if (g_stamps_on < 0) { const char* e = getenv("PVDB_STAMPS"); g_stamps_on = e && atoi(e) != 0; }
+    if (!g_stamps_on) return nullptr;
+    if (!g_stamps) { cudaMalloc(&g_stamps, 64 * sizeof(unsigned long long)); cudaMemset(g_stamps, 0, 64 * sizeof(unsigned long long)); }
+    return g_stamps;
 }
 extern "C" int pvdb_debug_stamps_fetch(unsigned long long* out64) {
     if (!g_stamps) return 1;
@@ -1019,6 +1029,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     U.leaf_blocks = PVDB_SMS * 4;
     U.block_offset = 0;
     U.dp = PvdbDpNetWait{};
+    U.dp_tiles_signal = nullptr; U.dp_tiles_epoch = 0; U.dp_world = 0; U.dp_err = nullptr;
     U.scalars = b->step_scalars;
     const int net_blocks = (PVDB_NET_N + 255) / 256;
     auto launch_update = [&](cudaStream_t s_, int part) -> int {
@@ -1029,6 +1040,16 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         PVDB_LAUNCH_CHECK();
         return PVDB_OK;
     };
+    {   // side-stream kernels run next to persistent tcgen05 CTAs: same shared-memory carve-out preference (see dp_exchange.cu)
+        static bool attrs = false;
+        if (!attrs) {
+            cudaFuncSetAttribute(k_update_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_ray_bwd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_density_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_stamp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attrs = true;
+        }
+    }
     bool update_done = false;
     // Fused data-parallel step: the emit kernel writes this rank's touched-leaf flags into its symmetric block, the union (with
     // the cross-GPU barrier that absorbs the ranks' skew) runs on the side stream under the rgbnet forward, pack / reduce-scatter /
@@ -1061,10 +1082,12 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                                       b->counters + CNT_RAY_TICKET));
         }
         PVDB_LAUNCH_CHECK();
+        stamp(st, 8);
         pvdb_prof_mark("march_count", st);
         PVDB_CUDA(pvdb_launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays,
                                   b->counters, b->loss, b->cap_alpha, b->cap_keep));
         PVDB_LAUNCH_CHECK();
+        stamp(st, 9);
         pvdb_prof_mark("scan", st);
         PVDB_CHECK_ARG(!O.scratch || n_rays <= b->scratch_rays, "march_scratch holds fewer rays than this batch");
         if (O.scratch) PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
@@ -1155,7 +1178,12 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                 stamp(sd->s, 13);
             }
             if (do_upd) {
+                if (dp_fused) {      // the leaf Adam itself waits for the owners' sums (no separate wait kernel)
+                    const PvdbDpTilesWait w = pvdb_dp_tiles_wait_args(peers, dp_step);
+                    U.dp_tiles_signal = w.signal; U.dp_tiles_epoch = w.epoch; U.dp_world = w.world; U.dp_err = w.err;
+                }
                 rc = launch_update(sd->s, 1);
+                U.dp_tiles_signal = nullptr;
                 if (rc) return rc;
                 stamp(sd->s, 14);
             }

@@ -225,7 +225,7 @@ class DataParallelTrainer:
             n, w = int(self.tr.t["counters"][2].item()), self.world
             own = (n - self.peer.rank + w - 1) // w if n > self.peer.rank else 0       # union slots this rank reduces
             tiles = 2 * (w - 1) * own * 512 * 13 * 4          # peer loads of the owned leaves + peer stores of their sums
-            return tiles + (w - 1) * 22019 * 4 + (w - 1) * ((self.tr.topo.n_leaf + 31) // 32) * 4     # + rgbnet pushes + the peers' flag words
+            return tiles + (w - 1) * 22019 * 4 + (w - 1) * self.tr.topo.n_leaf     # + rgbnet pushes + the peers' flag bytes
         return self.last_exchange_bytes
 
     def close(self):
