@@ -236,8 +236,9 @@ int pvdb_stage_rays(const float* rays_o, const float* rays_d, const float* viewd
 /* rgbnet Adam step size, lr * sqrt(1 - beta1^step) / (1 - beta0^step) in float (adam_upd_kernel.cu:72): what the fused step
  * derives from cfg->net_lr / net_step, for callers that feed pvdb_train_bufs.step_scalars[2] themselves. */
 float pvdb_dense_adam_stepsize_host(float lr, float beta0, float beta1, int step);
-/* Test switch: 0 makes the renderer's first pass march one pixel per thread (k_render_pass1) instead of probing every pixel and
- * marching the hit ones with 8 lanes each (bit-identical results; default 1, environment PVDB_RENDER_LANES). */
+/* Test switch for the renderer's first pass: 0 = one pixel per thread (k_render_pass1), 1 = probe every pixel and march the hit
+ * ones with 8 lanes each, negative = the default rule (lane-parallel when a call renders at most half of the frame's rows).
+ * Bit-identical results; environment PVDB_RENDER_LANES = 0 / 1 forces a mode at start-up. */
 void pvdb_debug_set_render_lanes(int on);
 /* Debug timeline (environment PVDB_STAMPS=1): %globaltimer stamps written by one-thread kernels at marked points of the fused
  * step (main stream: 0 start, 1 emit, 2 rgbnet forward, 3 composite, 4 activation gradients, 5 weight gradients + reduction,

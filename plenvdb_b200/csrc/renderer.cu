@@ -856,9 +856,10 @@ extern "C" int pvdb_interleaved_rows(int H, int band_rows, int rank, int world) 
 // row_begin + lr (band_stride == 0) or row_begin + (lr / band_rows) * band_stride + lr % band_rows.  frame_out (optional):
 // the full H x W x 3 frame, possibly peer memory, that also receives every pixel of the band.  fp (optional): the peer
 // protocol of pvdb_render_frame_sharded around the composite kernel.
-// 1 (default): probe + lane-parallel march as the first pass; 0: k_render_pass1 (thread per pixel).  Bit-identical results.
-static int g_render_lanes = -1;
-extern "C" void pvdb_debug_set_render_lanes(int on) { g_render_lanes = on ? 1 : 0; }
+// First pass of the renderer: 1 probe + lane-parallel march, 0 k_render_pass1 (thread per pixel), -1 chosen per call by the share
+// of the frame (see render_impl), -2 not read from the environment yet.  Bit-identical results either way.
+static int g_render_lanes = -2;
+extern "C" void pvdb_debug_set_render_lanes(int on) { g_render_lanes = on < 0 ? -1 : (on ? 1 : 0); }
 
 static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, const float* c2w, int row_begin, int rows, int band_rows,
                        int band_stride, float* out_rgb, float* frame_out, const pvdb_frame_peers* fp, uint32_t epoch, void* stream) {
@@ -885,8 +886,14 @@ static int render_impl(const pvdb_render_cfg* cfg, const pvdb_render_bufs* b, co
     PVDB_CHECK_ARG(b->active_list, "active_list scratch missing");
     const bool hand_over = b->px_scratch && b->fallback_list && b->px_entries > 0;
     float2* px = hand_over ? static_cast<float2*>(b->px_scratch) : nullptr;
-    if (g_render_lanes < 0) { const char* e = getenv("PVDB_RENDER_LANES"); g_render_lanes = e ? (atoi(e) != 0) : 1; }
-    if (g_render_lanes && hand_over && C.skip_bits) {
+    // First pass: measured on B200 on the 800x800 bench frame (profiles/render_share_timing_r02.json, us for a full frame and for
+    // a 1/2, 1/4, 1/8 share of its rows): thread per pixel 243 / 201 / 169 / 165 — bounded below by its longest warps —, probe +
+    // 8-lane march 305 / 166 / 102 / 76 — more instructions (replicated bookkeeping, shuffles), but they scale with the share.
+    // So the whole frame on one GPU takes the thread-per-pixel pass and a row share (tile-sharded rendering) the lane-parallel
+    // one.  g_render_lanes: -1 that rule, 0 / 1 force one of them (environment PVDB_RENDER_LANES, pvdb_debug_set_render_lanes).
+    if (g_render_lanes == -2) { const char* e = getenv("PVDB_RENDER_LANES"); g_render_lanes = e ? (atoi(e) != 0) : -1; }
+    const bool lanes = g_render_lanes < 0 ? rows * 2 <= cfg->H : g_render_lanes != 0;
+    if (lanes && hand_over && C.skip_bits) {
         PVDB_CUDA(pvdb_launch_pdl(k_render_probe, dim3(pgrid), dim3(256), 0, st, C, c2w, row_begin, rows, b->n_samples, b->tmins, b->tmaxs, b->active_list,
                                   b->counters, out_rgb));
         PVDB_LAUNCH_CHECK();

@@ -16,7 +16,7 @@ from plenvdb_b200.renderer import merge_grids              # noqa: E402
 
 dev = torch.device("cuda", 0)
 H = W = 800
-scene = synth.make_scene(160, "sparse")
+scene = synth.make_scene(160, os.environ.get("SCENE", "dense"))      # cfg 3: the dense-fill scene
 den, k0 = build_scene_grids(scene, device=dev)
 dend, cold, idx, n = merge_grids(den, k0, scene["mask"])
 w0, b0, w1, b1, w2, b2 = synth.unpack_net(synth.rgbnet_init())
@@ -54,14 +54,14 @@ def timed(fn, nf=20):
 
 out = []
 for world in (1, 2, 4, 8):
-    for band_rows in ((4,) if world == 1 else (4, 16)):
+    for band_rows in ((16,) if world == 1 else (16,)):
         ms, acc = timed(lambda c: r.render_interleaved_torch(c, band_rows, 0, world))
         out.append(dict(mode="interleaved", world=world, band_rows=band_rows, ms_per_frame=ms, kernels_us={k: round(v * 1e3, 1) for k, v in acc.items()}))
         print(json.dumps(out[-1]), flush=True)
-    if world > 1:
+    if False:
         lo, hi = pdist.shard_range(H, world // 2, world)
         ms, acc = timed(lambda c: r.render_rows_torch(c, lo, hi))
         out.append(dict(mode="contiguous middle band", world=world, rows=[lo, hi], ms_per_frame=ms, kernels_us={k: round(v * 1e3, 1) for k, v in acc.items()}))
         print(json.dumps(out[-1]), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/render_share_timing.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/render_share_timing_lanes%s.json" % os.environ.get("PVDB_RENDER_LANES", "1"), "w"), indent=1)

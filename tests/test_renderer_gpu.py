@@ -202,3 +202,37 @@ def test_sample_hand_over_equals_the_second_march(merged):
     assert out[0][0][6]["remarched"] == 0                       # nothing is handed over, nothing falls back
     assert big <= out[2][0][6]["remarched"] <= active and big > 100
     assert out[32][0][6]["remarched"] <= active // 20           # the restarted chain almost always reproduces pass 1's
+
+
+@pytest.mark.parametrize("px_entries", [2, 64])
+def test_lane_parallel_first_pass_is_bit_identical(merged, px_entries):
+    """The two forms of the first pass — one pixel per thread (k_render_pass1) and probe + 8 lanes per hit pixel
+    (k_render_probe, k_render_march_lanes) — give the same per-pixel counts, tightened ranges, hand-over decisions, sample list
+    and frame, bit for bit, for the whole frame and for a row band, with a slot so small that most pixels fall back to the
+    second march and with the default slot.  (The library picks one by the share of the frame a call renders.)"""
+    from plenvdb_b200 import _lib, synth
+    scene, (dend, cold, idx, n), _ = merged
+    H, W = 160, 168
+    res = {}
+    try:
+        for lanes in (0, 1):
+            _lib.lib.pvdb_debug_set_render_lanes(lanes)
+            r, mlp, K = _renderer(scene, dend, cold, idx, H, W)
+            r.set_px_entries(px_entries)
+            out = []
+            for cam, (lo, hi) in ((1, (0, H)), (4, (40, 104)), (6, (0, H))):
+                c2w = torch.from_numpy(synth.render_cameras(8)[cam].reshape(-1).copy()).cuda()
+                img = r.render_rows_torch(c2w, lo, hi).clone()
+                c = r.counters()
+                tot = c["total"]
+                out.append((img, r.s["n_samples"].clone(), r.s["i_starts"].clone(), r.s["tmins"].clone(), r.s["tmaxs"].clone(),
+                            r.s["s_weight"][:tot].clone(), r.s["s_ray"][:tot].clone(), r.s["s_feat"][:tot].clone(), c))
+            res[lanes] = out
+    finally:
+        _lib.lib.pvdb_debug_set_render_lanes(-1)
+    for a, b in zip(res[0], res[1]):
+        assert a[8] == b[8] and a[8]["total"] > 1000 and a[8]["overflow"] == 0
+        hit = a[1] > 0                      # tmins / tmaxs of pixels without samples are never read (the probe leaves its resume point there)
+        assert torch.equal(a[3][hit], b[3][hit]) and torch.equal(a[4][hit], b[4][hit])
+        for k in (0, 1, 2, 5, 6, 7):
+            assert torch.equal(a[k], b[k]), k
