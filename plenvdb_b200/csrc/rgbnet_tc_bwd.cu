@@ -312,6 +312,7 @@ struct BwdWgradArgs {
     float* partial;   // [gridDim.x][PART_LD] per-CTA weight-gradient partial sums (net_grad layout)
     const int32_t* counters; int64_t cap_keep;
     int use_tma;
+    int l2_discard;   // after a chunk has landed in shared memory, drop its (dead) global lines from L2 without write-back
 };
 constexpr int PART_LD = (PVDB_NET_N + 31) & ~31;
 struct WgradMaps { CUtensorMap h0, dh0, h1, x; };
@@ -449,6 +450,20 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
             { const long long t0 = clock64(); mbar_wait(bar_full + 8 * st, (it / NSTAGE) & 1); t_wait += clock64() - t0; }
             unsigned char* sb = smem + st * STAGE;
             unsigned char* lo = smem + S_LOSETS + (it & 1) * LOSET;
+            // The chunk is in shared memory and nobody will ever read its global copy again (h0, dH0, h1, x are rewritten by the
+            // next step's forward): discard.global.L2 drops the lines — most of them still DIRTY in L2, written by the forward /
+            // activation-gradient kernels — without writing them back.  Measured in situ (ncu
+            // --cache-control none): without it the step moves 318 MB through DRAM, 148 MB of it these dead tensors on their way
+            // out, and every line read here displaces a dirty line another CTA is about to read (113 of 148 MB re-read from
+            // DRAM); see profiles/insitu_traffic_r02.md.  212 lines of 128 bytes per chunk: one per converter thread.
+            if (A.l2_discard && tid < 212) {
+                const int64_t ch = ch_lo + it;
+                const char* line = tid < 64    ? reinterpret_cast<const char*>(A.k_h0 + ch * (WD * KC)) + tid * 128
+                                   : tid < 128 ? reinterpret_cast<const char*>(A.k_dh0 + ch * (WD * KC)) + (tid - 64) * 128
+                                   : tid < 192 ? reinterpret_cast<const char*>(A.k_h1 + ch * (WD * KC)) + (tid - 128) * 128
+                                               : reinterpret_cast<const char*>(A.k_x + ch * (40 * KC)) + (tid - 192) * 128;
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+            }
             // this lo set was last read by the MMAs of chunk it-2
             if (it >= 2) { const long long t0 = clock64(); mbar_wait(bar_free + 8 * ((it - 2) % NSTAGE), ((it - 2) / NSTAGE) & 1); t_lo += clock64() - t0; }
             // 1696 16-byte items: A1 512 (COMPUTED: dH1 = [h1 > 0] (g . W2), from the 16 x 3 logit gradients, W2 and the mask
@@ -720,6 +735,11 @@ int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bu
     }
     static const bool no_tma = getenv("PVDB_NO_TMA") != nullptr;   // bring-up switch: cp.async loader instead of TMA
     W.use_tma = maps_ok && !no_tma;
+    // Off by default: it takes 86 MB per step off the DRAM (319 -> 233 MB in situ) but not a microsecond off the kernels, which
+    // are not DRAM-bound in situ (1.2 - 3.2 TB/s); the weight-gradient kernel even loses 2 us to the 212 extra instructions per
+    // chunk (profiles/insitu_traffic_r02.md).  PVDB_L2_DISCARD=1 switches it on.
+    static const bool discard = getenv("PVDB_L2_DISCARD") != nullptr && atoi(getenv("PVDB_L2_DISCARD")) != 0;
+    W.l2_discard = discard ? 1 : 0;
     PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_bwd_wgrad_tc, dim3(PVDB_SMS), dim3(B2_THREADS), B2_TOTAL, st, W, maps));
     PVDB_LAUNCH_CHECK();
     PvdbDpNetPush push = {};
