@@ -525,14 +525,15 @@ def bench_f160(args, dev, rank, world, flush, clk):
         kname = {"rgbnet_fwd": "k_rgbnet_fwd_tc", "rgbnet_bwd_act": "k_rgbnet_bwd_act_tc", "rgbnet_bwd_wgrad": "k_rgbnet_bwd_wgrad_tc",
                  "march_count": "k_march"}.get(top)
         traffic = tj[kname]["dram_bytes"] if (tr.use_tc and kname in tj) else None
+        traffic_in_situ = tj[kname].get("dram_bytes_in_situ") if (tr.use_tc and kname in tj) else None
         # bytes the three MLP kernels move by design (activations handed over through HBM), per kept sample
         design_bytes = {"rgbnet_fwd": M3 * (512 + 512 + 160 + 32 + 48 + 12 + 44.0), "rgbnet_bwd_act": M3 * (512 + 88.0),
                         "rgbnet_bwd_wgrad": M3 * (3 * 512 + 160 + 12 + 16.0) + 148 * 22048 * 4.0}
         if top in kern_flops:
             ach = kern_flops[top] / (kern[top] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
-                    "traffic": traffic, "traffic_source": tj_name, "traffic_commit": tj.get("commit"), "peak_source": which,
-                    "tensor_core_flops_issued": kern_flops[top] * mlp_pass,
+                    "traffic": traffic, "traffic_in_situ": traffic_in_situ, "traffic_source": tj_name, "traffic_commit": tj.get("commit"),
+                    "peak_source": which, "tensor_core_flops_issued": kern_flops[top] * mlp_pass,
                     "hbm_view": ({"design_bytes": design_bytes[top], "achieved_GBs": design_bytes[top] / (kern[top] * 1e-3) / 1e9,
                                   "frac_of_hbm": design_bytes[top] / (kern[top] * 1e-3) / 1e9 / hbm,
                                   "note": "activation tensors this kernel reads/writes through HBM by design; the real limiter of the tcgen05 kernels"}
@@ -544,7 +545,7 @@ def bench_f160(args, dev, rank, world, flush, clk):
                   "march_emit": 60 * N_RAYS / 2 + o["V_mask"] * scale + 4 * o["V_den"] * scale + 36 * cnt["M_alpha"]}.get(top, b_train)
             ach = kb / (kern[top] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
-                    "traffic_source": tj_name, "traffic_commit": tj.get("commit"), "peak_source": which}
+                    "traffic_in_situ": traffic_in_situ, "traffic_source": tj_name, "traffic_commit": tj.get("commit"), "peak_source": which}
         step_roof = b_train / (ms_total / K * 1e-3) / 1e9
         base = cpu_baseline_sampling(scene, rays0[0], rays0[1], cpu_threads)
         base["oracle_full_step"] = {"value": n_sub / cpu_s, "unit": "rays/s", "kind": "port", "cores": cpu_threads,
@@ -798,7 +799,7 @@ def time_render(args, scene, net, dend, cold, idx, n, dev, rank, world, workload
         steps = int(ru.infer_n_samples(rd.reshape(-1, 3).contiguous(), tmin, tmax, scene["stepdist"]).sum().item())
         b_frame = 12 * H * W + (4 + 4 + 48) * n + 88 * 1024
         tj, tj_name = latest_traffic()
-        kr = {k: v for k, v in tj.items() if k.startswith("k_render")} if tj else {}
+        kr = {k: v for k, v in tj.items() if k.startswith("k_render") and isinstance(v, dict)} if tj else {}
         out = {"metric": "merged-VDB render FPS 800x800", "workload": workload, "sharding": sharding, "value": 1e3 / ms, "unit": "frames/s",
                "ms_per_frame": ms, "frames": nf, "poses": "200-pose orbit (pose_spherical(angle, -30, 4)), frame i = pose i mod 200",
                "e2e_fps": e2e_fps, "e2e_how": e2e_how, "e2e_fps_synchronous": e2e_sync_fps, "d2h_bytes_per_frame": H * W * 3 * 4,

@@ -408,6 +408,54 @@ int pvdb_frame_error(const pvdb_frame_peers* peers, int32_t* err_out);
 int pvdb_merge_gather(const pvdb_tree* tree, const float* den, const float* k0, int k0_dim,
                       const int32_t* row_of_voxel, int rx, int ry, int rz, float* dendata, float* coldata, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * B1 as opaque handles (csrc/handles.cu) — one handle per class of the reference's pybind11 module `plenvdb`
+ * (plenvdb/lib/vdb/plenvdb.cpp:3-172): what a C / C++ / pybind11 binder calls instead of managing topology upload, plane
+ * allocation and optimiser step counting itself.  Host-buffer contract like the pybind11 module (every call is complete when
+ * it returns); the device pointers behind a handle are exposed for zero-copy callers.  `.vdb` load / save is not part of the
+ * C layer (plenvdb_b200/openvdb_io.py): the handles take and return dense host arrays, like copyFromDense / get_dense_grid.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pvdb_grid pvdb_grid;          /* DensityVDB (channels 1) / ColorVDB (channels 12): plenvdb.h:389-429 */
+typedef struct pvdb_opt pvdb_opt;            /* DensityOpt / ColorOpt: plenvdb.h:686-789 */
+typedef struct pvdb_renderer pvdb_renderer;  /* MGRenderer: plenvdb.h:933-1068 */
+/* active == NULL: denseFill topology (plenvdb.h:117-125); else uint8 [rx*ry*rz]: leaves where it has a voxel, value mask = active */
+pvdb_grid* pvdb_grid_create(int rx, int ry, int rz, int channels, const uint8_t* active);
+void pvdb_grid_destroy(pvdb_grid*);
+int pvdb_grid_info(const pvdb_grid*, int32_t* reso3, int32_t* channels, int32_t* n_leaf);
+const pvdb_tree* pvdb_grid_tree(const pvdb_grid*);     /* for the stateless entry points */
+float* pvdb_grid_values(pvdb_grid*);                   /* device plane [n_leaf][512][channels] */
+float* pvdb_grid_grad(pvdb_grid*);
+int pvdb_grid_copy_from_dense(pvdb_grid*, const float* dense_host);   /* [rx][ry][rz][channels]; plenvdb.h:149-157, 241-250 */
+int pvdb_grid_copy_to_dense(const pvdb_grid*, float* dense_host);     /* plenvdb.h:158-167, 251-271 */
+int pvdb_grid_forward(const pvdb_grid*, const float* x, const float* y, const float* z, int64_t n, float* out_host);   /* plenvdb.cpp:10-31 */
+int pvdb_grid_backward(pvdb_grid*, const float* x, const float* y, const float* z, const float* grad_host, int64_t n);  /* plenvdb.cpp:47-67 */
+int pvdb_grid_set_values_on_by_mask(pvdb_grid*, const uint8_t* mask_host, float val);                                 /* plenvdb.h:487-495 */
+pvdb_opt* pvdb_opt_create(pvdb_grid*, float lr, float eps, float beta0, float beta1);
+void pvdb_opt_destroy(pvdb_opt*);
+int pvdb_opt_zero_grad(pvdb_opt*);
+int pvdb_opt_step(pvdb_opt*, int stepmode);            /* 0 plain, 1 skip zero gradients, 2 per-voxel lr (plenvdb.h:751-789) */
+int pvdb_opt_update_lr(pvdb_opt*, float factor);
+int pvdb_opt_set_pervoxel_lr(pvdb_opt*, const float* dense_host);     /* [rx*ry*rz]; plenvdb.h:714-722 */
+int pvdb_opt_get(const pvdb_opt*, int32_t* step, float* lr, float* eps, float* beta0, float* beta1);
+int pvdb_opt_set(pvdb_opt*, int32_t step, float lr, float eps, float beta0, float beta1);
+float* pvdb_opt_exp_avg(pvdb_opt*);
+float* pvdb_opt_exp_avg_sq(pvdb_opt*);
+pvdb_renderer* pvdb_renderer_create(int dcol, int dpe, int dhid, int dout);   /* (12, 27, 128, 3) */
+void pvdb_renderer_destroy(pvdb_renderer*);
+/* den [n_rows], col [n_rows][12] (row 0 = zeros), idx_dense_host int32 [rx][ry][rz] of 1-based row ids (plenvdb.h:959-983) */
+int pvdb_renderer_load_data(pvdb_renderer*, const float* den_host, const float* col_host, int64_t n_rows, const int32_t* idx_dense_host,
+                            int rx, int ry, int rz);
+int pvdb_renderer_load_params(pvdb_renderer*, const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2);
+int pvdb_renderer_set_scene(pvdb_renderer*, const int32_t* reso3, const float* K9, const float* xyz_min3, const float* xyz_max3);
+int pvdb_renderer_set_kwargs(pvdb_renderer*, float near, float far, float stepdist, float act_shift, float interval, float fast_color_thres,
+                             float bg, int inverse_y, int H, int W);
+int pvdb_renderer_input_c2w(pvdb_renderer*, const float* c2w16_host);
+/* render_an_image + output_an_image: out_host float [H][W][3] (NULL: leave the frame on the device, pvdb_renderer_frame).  Like the
+ * reference it does nothing until all five setup calls were made: *rendered tells. */
+int pvdb_renderer_render(pvdb_renderer*, float* out_host, int* rendered);
+const float* pvdb_renderer_frame(const pvdb_renderer*);
+int pvdb_renderer_counters(const pvdb_renderer*, int32_t* counters8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -186,6 +186,38 @@ _SIGS = {
     "pvdb_merge_gather": (None, [_TP, c_ptr, c_ptr, _i, c_ptr, _i, _i, _i, c_ptr, c_ptr, c_ptr]),
     "pvdb_train_step": (None, [C.POINTER(pvdb_train_cfg), C.POINTER(pvdb_train_bufs), c_ptr, c_ptr, c_ptr, c_ptr, _i, _i,
                                c_ptr]),
+    # opaque handles (csrc/handles.cu)
+    "pvdb_grid_create": (c_ptr, [_i, _i, _i, _i, c_ptr]),
+    "pvdb_grid_destroy": (type(None), [c_ptr]),
+    "pvdb_grid_info": (None, [c_ptr, c_ptr, c_ptr, c_ptr]),
+    "pvdb_grid_tree": (c_ptr, [c_ptr]),
+    "pvdb_grid_values": (c_ptr, [c_ptr]),
+    "pvdb_grid_grad": (c_ptr, [c_ptr]),
+    "pvdb_grid_copy_from_dense": (None, [c_ptr, c_ptr]),
+    "pvdb_grid_copy_to_dense": (None, [c_ptr, c_ptr]),
+    "pvdb_grid_forward": (None, [c_ptr, c_ptr, c_ptr, c_ptr, _i64, c_ptr]),
+    "pvdb_grid_backward": (None, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, _i64]),
+    "pvdb_grid_set_values_on_by_mask": (None, [c_ptr, c_ptr, _f]),
+    "pvdb_opt_create": (c_ptr, [c_ptr, _f, _f, _f, _f]),
+    "pvdb_opt_destroy": (type(None), [c_ptr]),
+    "pvdb_opt_zero_grad": (None, [c_ptr]),
+    "pvdb_opt_step": (None, [c_ptr, _i]),
+    "pvdb_opt_update_lr": (None, [c_ptr, _f]),
+    "pvdb_opt_set_pervoxel_lr": (None, [c_ptr, c_ptr]),
+    "pvdb_opt_get": (None, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "pvdb_opt_set": (None, [c_ptr, C.c_int32, _f, _f, _f, _f]),
+    "pvdb_opt_exp_avg": (c_ptr, [c_ptr]),
+    "pvdb_opt_exp_avg_sq": (c_ptr, [c_ptr]),
+    "pvdb_renderer_create": (c_ptr, [_i, _i, _i, _i]),
+    "pvdb_renderer_destroy": (type(None), [c_ptr]),
+    "pvdb_renderer_load_data": (None, [c_ptr, c_ptr, c_ptr, _i64, c_ptr, _i, _i, _i]),
+    "pvdb_renderer_load_params": (None, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "pvdb_renderer_set_scene": (None, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "pvdb_renderer_set_kwargs": (None, [c_ptr, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i]),
+    "pvdb_renderer_input_c2w": (None, [c_ptr, c_ptr]),
+    "pvdb_renderer_render": (None, [c_ptr, c_ptr, c_ptr]),
+    "pvdb_renderer_frame": (c_ptr, [c_ptr]),
+    "pvdb_renderer_counters": (None, [c_ptr, c_ptr]),
 }
 
 DECLARED_SYMBOLS = sorted(_SIGS)
