@@ -171,7 +171,9 @@ __device__ __forceinline__ void dp_flag_corners(uint8_t* __restrict__ flags, con
 
 // One warp per ray.  MODE 0 = count, 1 = emit.  PARITY (count only): keep marching past the early stop so the
 // full M1 / M2 counts of the reference are produced too.
-template <int MODE, bool PARITY>
+// VAR: compile-time variant bits, so that the default kernel carries neither feature's code: 1 = pass A skips runs (P.run_skip),
+// 2 = data-parallel step (O.dp_flags is set: the emit path flags the touched leaves, the count pass parks every sample's corners).
+template <int MODE, bool PARITY, int VAR>
 __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& O, const float* __restrict__ rays_o,
                                           const float* __restrict__ rays_d, const int r, const int lane) {
     float o[3] = {__ldg(rays_o + r * 3), __ldg(rays_o + r * 3 + 1), __ldg(rays_o + r * 3 + 2)};
@@ -196,7 +198,7 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
     // the steps of the runs that can are tested one by one, four runs per warp iteration.  Same bits as testing every step.
     for (int seg = 0; seg < nsteps && !(stopped && !PARITY); seg += 1024) {
         unsigned myword = 0;
-        if (P.run_skip) {
+        if (VAR & 1) {
             const int n_runs = (min(1024, nsteps - seg) + 7) >> 3;      // <= 128
             unsigned rw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -294,13 +296,13 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
             e[0] = make_uint4((uint32_t)step, __float_as_uint(x), __float_as_uint(y), __float_as_uint(z));
             e[1] = make_uint4(__float_as_uint(dens), __float_as_uint(alpha), __float_as_uint(myT), __float_as_uint(myW));
             e[2] = make_uint4((uint32_t)my_ki, 0u, 0u, 0u);
-            if (my_ki >= 0 || O.dp_flags) {
+            if (my_ki >= 0 || (VAR & 2)) {
                 e[3] = make_uint4((uint32_t)rec[0], (uint32_t)rec[1], (uint32_t)rec[2], (uint32_t)rec[3]);
                 e[4] = make_uint4((uint32_t)rec[4], (uint32_t)rec[5], (uint32_t)rec[6], (uint32_t)rec[7]);
             }
         }
         if (MODE == 1 && my_ai >= 0) {
-            if (O.dp_flags) dp_flag_corners(O.dp_flags, rec, dp_last_leaf);
+            if (VAR & 2) dp_flag_corners(O.dp_flags, rec, dp_last_leaf);
             const int64_t ia = oa + my_ai;
             if (ia < O.cap_alpha) {
                 O.s_ray[ia] = r; O.s_step[ia] = step;
@@ -334,7 +336,7 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
 // ticket == nullptr: warp w marches ray w.  Otherwise a resident grid of warps draws rays from an atomic ticket counter
 // (rays differ 10x in length; 8192 of them are 1.4 waves of static warps, so the tail of a static grid idles a third of
 // the machine).  The counter is reset by k_scan_counts, which always follows the count pass.
-template <int MODE, bool PARITY>
+template <int MODE, bool PARITY, int VAR>
 __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
                                                   const float* __restrict__ rays_d, int n_rays, int32_t* __restrict__ ticket) {
     pvdb_pdl_wait();
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, con
     if (ticket == nullptr) {
         const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if (r >= n_rays) return;
-        march_ray<MODE, PARITY>(P, O, rays_o, rays_d, r, lane);
+        march_ray<MODE, PARITY, VAR>(P, O, rays_o, rays_d, r, lane);
         return;
     }
     // first ray of every resident warp: its own index (no atomic — thousands of warps drawing their first ticket at once
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, con
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     while (r < n_rays) {
-        march_ray<MODE, PARITY>(P, O, rays_o, rays_d, r, lane);
+        march_ray<MODE, PARITY, VAR>(P, O, rays_o, rays_d, r, lane);
         if (lane == 0) r = n_warps + atomicAdd(ticket, 1);
         r = __shfl_sync(0xffffffffu, r, 0);
     }
@@ -358,6 +360,7 @@ __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, con
 
 // Emit pass as a compaction: one warp per ray copies the count pass's scratch entries to their final, scanned positions.
 // A ray with more alpha-passing samples than the scratch holds is simply marched again.
+template <int VAR>
 __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
                                                       const float* __restrict__ rays_d, int n_rays) {
     pvdb_pdl_wait();
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O,
     const int lane = threadIdx.x & 31;
     if (r >= n_rays) return;
     const int na = O.cnt_alpha[r];
-    if (na > O.scr_cap) { march_ray<1, false>(P, O, rays_o, rays_d, r, lane); return; }
+    if (na > O.scr_cap) { march_ray<1, false, VAR & 2>(P, O, rays_o, rays_d, r, lane); return; }
     const int64_t oa = O.off_alpha[r], ok = O.off_keep[r];
     int dp_last_leaf = -1;
     for (int i = lane; i < na; i += 32) {
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O,
             O.s_T[ia] = __uint_as_float(e1.z); O.s_weight[ia] = __uint_as_float(e1.w);
         }
         const int ki = (int32_t)e2.x;
-        if (O.dp_flags) {
+        if (VAR & 2) {
             const uint4 c0 = e[3], c1 = e[4];
             const int rec[8] = {(int)c0.x, (int)c0.y, (int)c0.z, (int)c0.w, (int)c1.x, (int)c1.y, (int)c1.z, (int)c1.w};
             dp_flag_corners(O.dp_flags, rec, dp_last_leaf);
@@ -1108,17 +1111,24 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             if (rc) return rc;
             PVDB_CUDA(cudaEventRecord(sd->join2, sd->s));
         }
+        const int var = (P.run_skip ? 1 : 0) | (O.dp_flags ? 2 : 0);
         if (cfg->parity_counts) {
-            k_march<0, true><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+            if (var & 1) k_march<0, true, 1><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+            else k_march<0, true, 0><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+            PVDB_CHECK_ARG(!(var & 2), "parity_counts is a single-GPU diagnostic (not available in the data-parallel step)");
         } else {
             static int resident = 0;   // CTAs of the count kernel that fit the device at once
             if (!resident) {
                 int per_sm = 0;
-                PVDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<0, false>, 256, 0));
+                PVDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<0, false, 0>, 256, 0));
                 resident = PVDB_SMS * (per_sm > 0 ? per_sm : 1);
             }
-            PVDB_CUDA(pvdb_launch_pdl(k_march<0, false>, dim3(min(resident, warp_grid)), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays,
-                                      b->counters + CNT_RAY_TICKET));
+            const dim3 grid(min(resident, warp_grid));
+            int32_t* ticket = b->counters + CNT_RAY_TICKET;
+            if (var == 0) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 0>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket));
+            else if (var == 1) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 1>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket));
+            else if (var == 2) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 2>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket));
+            else PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 3>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket));
         }
         PVDB_LAUNCH_CHECK();
         stamp(st, 8);
@@ -1129,8 +1139,14 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         stamp(st, 9);
         pvdb_prof_mark("scan", st);
         PVDB_CHECK_ARG(!O.scratch || n_rays <= b->scratch_rays, "march_scratch holds fewer rays than this batch");
-        if (O.scratch) PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
-        else k_march<1, false><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+        if (O.scratch) {
+            if (O.dp_flags) PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch<2>, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
+            else PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch<0>, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
+        } else if (O.dp_flags) {
+            k_march<1, false, 2><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+        } else {
+            k_march<1, false, 0><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+        }
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
         stamp(st, 1);
