@@ -306,6 +306,11 @@ def time_training(tr, stepper, batches, K, Wm, world, dev, n_rays, flush, with_e
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
     l0 = tr.launches_total
+    # The barrier leaves the host with no lead over the GPU: a host thread that is descheduled for a few hundred microseconds
+    # while it issues the first timed step would stall the device (and, in a data-parallel run, every peer waiting for this
+    # rank inside ITS timed step).  One millisecond of device-side delay in front of the first step lets the host queue the
+    # first steps before the device gets to them, like in steady state; it is outside the timed events.
+    torch.cuda._sleep(2_000_000)
     for i in range(K):
         flush.fill_(i & 0xFF)                      # flush L2 between timed iterations (outside the timed events)
         ev[i][0].record()
@@ -313,7 +318,10 @@ def time_training(tr, stepper, batches, K, Wm, world, dev, n_rays, flush, with_e
         ev[i][1].record()
     res["launches"] = tr.launches_total - l0
     barrier()
-    ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    ms_total = max_over_ranks(sum(per_step))
+    res["step_ms"] = {"median": float(np.median(per_step)), "min": float(np.min(per_step)), "max": float(np.max(per_step)),
+                      "slowest_step": int(np.argmax(per_step)), "note": "per-step CUDA-event times on rank 0; `value` uses the sum over the K steps, maximum over the ranks"}
     cnt = tr.counters()
     assert cnt["overflow"] == 0, "sample list overflow: raise cap_*_per_ray"
     res.update(ms_total=ms_total, value=world * n_rays * K / (ms_total * 1e-3), counters=cnt)
@@ -561,7 +569,7 @@ def bench_f160(args, dev, rank, world, flush, clk):
                        "rgbnet": "fp32 cuda cores" if not tr.use_tc else "tcgen05 3xTF32 forward + backward", "parallelism": "dp%d" % world,
                        "samples": {"M_alpha": cnt["M_alpha"], "M_keep": M3, "touched_leaves_density": cnt["n_touched_den"],
                                    "touched_leaves_k0": cnt["n_touched_k0"]}},
-            "warm_l2_ms_per_step": T["warm_ms"], "warm_l2_value": warm_value,
+            "step_ms": T["step_ms"], "warm_l2_ms_per_step": T["warm_ms"], "warm_l2_value": warm_value,
             "e2e": {"value": T["e2e_value"], "unit": "rays/s", "h2d_bytes_per_step": 4 * N_RAYS * 3 * 4, "d2h_bytes_per_step": 16,
                     "how": "FusedTrainer.step_from_host_async, every iteration: pinned host batch -> H2D on a copy stream -> step -> loss "
                            "words D2H to pinned host; the host waits for iteration i - 1 and reads its loss while iteration i runs",

@@ -736,73 +736,37 @@ __global__ void __launch_bounds__(256) k_update_fused(UpdateArgs U) {
     }
     const int nd = U.counters[CNT_N_TOUCHED_DEN], nk = U.counters[CNT_N_TOUCHED_K0];
     const float omb0 = __fsub_rn(1.0f, U.b0), omb1 = __fsub_rn(1.0f, U.b1);
-    // Work items: touched density leaves (512 voxels by 256 threads, 2 each) and touched k0 leaves in halves (256 voxels, one
-    // per thread: the voxel's 12 channels are one 48-byte record = 3 x 16-byte loads per plane instead of 12 scalar ones; at
-    // S512 — 18 k touched leaves, the kernel at the HBM roofline — that took the update from 449 to ... us).
-    for (int w = bid; w < nd + nk * 2; w += U.leaf_blocks) {
+    // Work items: (touched density leaf) and (touched k0 leaf, quarter); a persistent grid strides over them.  One thread per
+    // (voxel, Vec3 group) with scalar loads: a variant with one thread per k0 voxel and 3 x 16-byte loads per plane needed 80
+    // registers instead of 31 and was 10 % SLOWER at S512 (0.49 vs 0.45 ms for 18 k touched leaves: the kernel lives on loads
+    // in flight, i.e. on occupancy), equal at F160.
+    for (int w = bid; w < nd + nk * 4; w += U.leaf_blocks) {
         const bool is_den = w < nd;
-        if (is_den) {
-            const int leaf = U.den_list[w];
-            const float stepsz = U.scalars ? __ldg(U.scalars) : U.den_stepsz;
-            for (int off = threadIdx.x; off < 512; off += blockDim.x) {
-                if (!pvdb_mask_bit(U.tree.leaf_mask, leaf, off)) continue;
-                const size_t i = (size_t)leaf * 512 + off;
-                const float g = U.den_g[i];
-                if (g == 0.0f) continue;
-                const float nm = __fmaf_rn(omb0, g, __fmul_rn(U.b0, U.den_m[i]));
-                const float nv = __fmaf_rn(g, __fmul_rn(omb1, g), __fmul_rn(U.b1, U.den_v[i]));
-                U.den_m[i] = nm;
-                U.den_v[i] = nv;
-                U.den[i] = __fsub_rn(U.den[i], __fdiv_rn(__fmul_rn(stepsz, nm), __fadd_rn(U.eps, __fsqrt_rn(nv))));
-                U.den_g[i] = 0.f;
+        const int leaf = is_den ? U.den_list[w] : U.k0_list[(w - nd) >> 2];
+        const int part = is_den ? 0 : (w - nd) & 3;
+        float *p = is_den ? U.den : U.k0, *g = is_den ? U.den_g : U.k0_g, *m = is_den ? U.den_m : U.k0_m, *v = is_den ? U.den_v : U.k0_v;
+        const float stepsz = U.scalars ? __ldg(U.scalars + (is_den ? 0 : 1)) : (is_den ? U.den_stepsz : U.k0_stepsz);
+        const int C = is_den ? 1 : 12, G = is_den ? 1 : 3, ngrp = C / G;
+        // density: 512 voxels by 256 threads (2 each); k0 quarter: 128 voxels x 4 groups = 512 items (2 each)
+        for (int e = threadIdx.x; e < 512; e += blockDim.x) {
+            const int off = is_den ? e : part * 128 + (e >> 2), grp = is_den ? 0 : (e & 3);
+            if (!pvdb_mask_bit(U.tree.leaf_mask, leaf, off)) continue;
+            const size_t base = ((size_t)leaf * 512 + off) * C + (size_t)grp * G;
+            float gg[3];
+            bool allzero = true;
+            for (int c = 0; c < G; ++c) { gg[c] = g[base + c]; allzero = allzero && gg[c] == 0.0f; }
+            if (allzero) continue;
+            for (int c = 0; c < G; ++c) {
+                const float nm = __fmaf_rn(omb0, gg[c], __fmul_rn(U.b0, m[base + c]));
+                const float nv = __fmaf_rn(gg[c], __fmul_rn(omb1, gg[c]), __fmul_rn(U.b1, v[base + c]));
+                m[base + c] = nm;
+                v[base + c] = nv;
+                p[base + c] = __fsub_rn(p[base + c], __fdiv_rn(__fmul_rn(stepsz, nm), __fadd_rn(U.eps, __fsqrt_rn(nv))));
+                g[base + c] = 0.f;
             }
-            if (threadIdx.x == 0) U.den_touched[leaf] = 0;
-            continue;
         }
-        const int leaf = U.k0_list[(w - nd) >> 1], half = (w - nd) & 1;
-        const float stepsz = U.scalars ? __ldg(U.scalars + 1) : U.k0_stepsz;
-        const int off = half * 256 + threadIdx.x;
-        if (threadIdx.x == 0 && half == 0) U.k0_touched[leaf] = 0;
-        if (!pvdb_mask_bit(U.tree.leaf_mask, leaf, off)) continue;
-        const size_t base = ((size_t)leaf * 512 + off) * 12;
-        float4* g4 = reinterpret_cast<float4*>(U.k0_g + base);
-        float gg[12];
-        { const float4 a = g4[0], b = g4[1], c = g4[2];
-          gg[0] = a.x; gg[1] = a.y; gg[2] = a.z; gg[3] = a.w; gg[4] = b.x; gg[5] = b.y; gg[6] = b.z; gg[7] = b.w;
-          gg[8] = c.x; gg[9] = c.y; gg[10] = c.z; gg[11] = c.w; }
-        // stepmode 1 skips a Vec3 group only when all three of its components are zero (colorvdb.cu:318)
-        bool live[4];
-        bool any = false;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { live[q] = gg[3 * q] != 0.0f || gg[3 * q + 1] != 0.0f || gg[3 * q + 2] != 0.0f; any = any || live[q]; }
-        if (!any) continue;
-        float4* p4 = reinterpret_cast<float4*>(U.k0 + base);
-        float4* m4 = reinterpret_cast<float4*>(U.k0_m + base);
-        float4* v4 = reinterpret_cast<float4*>(U.k0_v + base);
-        float pp[12], mm[12], vv[12];
-#pragma unroll
-        for (int c4 = 0; c4 < 3; ++c4) {
-            const float4 a = p4[c4], b = m4[c4], c = v4[c4];
-            pp[c4 * 4] = a.x; pp[c4 * 4 + 1] = a.y; pp[c4 * 4 + 2] = a.z; pp[c4 * 4 + 3] = a.w;
-            mm[c4 * 4] = b.x; mm[c4 * 4 + 1] = b.y; mm[c4 * 4 + 2] = b.z; mm[c4 * 4 + 3] = b.w;
-            vv[c4 * 4] = c.x; vv[c4 * 4 + 1] = c.y; vv[c4 * 4 + 2] = c.z; vv[c4 * 4 + 3] = c.w;
-        }
-#pragma unroll
-        for (int c = 0; c < 12; ++c) {
-            if (!live[c / 3]) continue;          // untouched groups are written back unchanged
-            const float nm = __fmaf_rn(omb0, gg[c], __fmul_rn(U.b0, mm[c]));
-            const float nv = __fmaf_rn(gg[c], __fmul_rn(omb1, gg[c]), __fmul_rn(U.b1, vv[c]));
-            mm[c] = nm;
-            vv[c] = nv;
-            pp[c] = __fsub_rn(pp[c], __fdiv_rn(__fmul_rn(stepsz, nm), __fadd_rn(U.eps, __fsqrt_rn(nv))));
-        }
-#pragma unroll
-        for (int c4 = 0; c4 < 3; ++c4) {
-            p4[c4] = make_float4(pp[c4 * 4], pp[c4 * 4 + 1], pp[c4 * 4 + 2], pp[c4 * 4 + 3]);
-            m4[c4] = make_float4(mm[c4 * 4], mm[c4 * 4 + 1], mm[c4 * 4 + 2], mm[c4 * 4 + 3]);
-            v4[c4] = make_float4(vv[c4 * 4], vv[c4 * 4 + 1], vv[c4 * 4 + 2], vv[c4 * 4 + 3]);
-            g4[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        if (threadIdx.x == 0 && part == 0) (is_den ? U.den_touched : U.k0_touched)[leaf] = 0;
+        (void)ngrp;
     }
 }
 
