@@ -31,7 +31,8 @@ def test_reference_arm_prints_the_contract_line():
 
 
 def test_committed_gpu_lines_carry_the_full_contract():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r01[g-z]_n1*.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r01[g-z]_n1*.json")) + glob.glob(os.path.join(ROOT, "profiles", "bench_r02_final_n*.json")) +
+                   glob.glob(os.path.join(ROOT, "profiles", "bench_r02_n8.json")))
     assert files, "no bench line of the final state under profiles/"
     for f in files:
         d = _last_json_line(open(f).read())
@@ -50,3 +51,13 @@ def test_committed_gpu_lines_carry_the_full_contract():
         k = d["clocks"]
         assert k["sm_mhz"] and k["sm_max_mhz"] and not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         assert "workload" in d["config"] and "l2" in d["config"]
+        if "bench_r02" in f:      # round 2: parity inside the bench, the render and S512 sub-benchmarks with their own objects
+            assert d["parity"]["ok"] is True and all(d["parity"]["integers_bit_exact"].values())
+            assert d["n_gpus"] == 1 or d["parity"]["replicas_identical"] is True
+            r = d["render"]
+            assert r["frames"] == 200 and "dense" in r["workload"] and {"roofline", "value", "e2e_fps"} <= set(r)
+            assert r["roofline"]["march_steps_per_frame"] > 1e8 and abs(r["roofline"]["frac"] - r["roofline"]["achieved"] / r["roofline"]["peak"]) < 1e-9
+            assert d["stress_s512"]["train"]["value"] > 0 and d["stress_s512"]["render"]["value"] > 0
+            if d["n_gpus"] == 1:
+                assert r["parity"]["ok"] is True and r["parity"]["per_pixel_sample_counts_bit_exact"] is True and r["cpu_baseline"]["value"] > 0
+                assert c["kind"] == "reference"
