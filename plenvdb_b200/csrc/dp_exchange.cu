@@ -201,9 +201,26 @@ __global__ void __launch_bounds__(128) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, 
     pvdb_pdl_wait();
     // this kernel is enqueued behind the kernels that scatter into this rank's planes: they are final (signal B, first CTA)
     if (blockIdx.x == 0 && threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_B, epoch);
+    const int n = counters[cnt_den];
+    // The grid is sized for the large case (S512: ~0.5 GB of tiles, five CTAs per SM once the weight-gradient kernel has left);
+    // at F160 (74 union leaves, 2 MB) only the first ~120 CTAs have a tile element: the rest leave at once, without waiting for
+    // the peers, and only take part in the last-CTA count.
+    {
+        const int mine0 = n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
+        if ((int64_t)blockIdx.x * blockDim.x >= (int64_t)mine0 * (PVDB_LEAF_VOX * 13 / 4) && blockIdx.x != 0) {
+            if (threadIdx.x == 0) {
+                uint32_t* done0 = view(P.base[P.rank], P.n_leaf).done + 1;
+                if (atomicAdd(done0, 1u) == gridDim.x - 1) {      // cannot be the last one unless every working CTA is done: they count after their fences
+                    *done0 = 0;
+                    __threadfence_system();
+                    for (int r = 0; r < P.world; ++r) signal_peer(P, r, SIG_D, epoch);
+                }
+            }
+            return;
+        }
+    }
     if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_B, epoch);
     __syncthreads();
-    const int n = counters[cnt_den];
     float4* pd[8];
     float4* pk[8];
     for (int r = 0; r < 8; ++r) {
@@ -363,9 +380,9 @@ static int exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint
         pvdb_prof_mark("dp_union", st);
     }
     if (!do_move) return PVDB_OK;
-    // ONE wave of CTAs (one fits on each SM next to the persistent weight-gradient CTA), grid-striding over the owned tiles:
-    // 74 union leaves = 2 MB at F160 (latency bound), ~0.5 GB at S512
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS), dim3(128), 0, st, *P, epoch, (const int32_t*)b->den_touched_list,
+    // One CTA fits on each SM next to the persistent weight-gradient CTA, five once it has left; CTAs without a tile element
+    // leave at once: 74 union leaves = 2 MB at F160 (latency bound, one wave of working CTAs), ~0.5 GB at S512
+    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS * 5), dim3(128), 0, st, *P, epoch, (const int32_t*)b->den_touched_list,
                               (const int32_t*)b->counters, CNT_DEN));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_rs", st);
