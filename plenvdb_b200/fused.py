@@ -44,6 +44,8 @@ def get_rays_of_a_view(H, W, K, c2w, inverse_y=False, flip_x=False, flip_y=False
 
 
 class FusedTrainer:
+    OVERFLOW_CHECK_EVERY = 64     # step_from_host reads the overflow flag of the sample lists every that many calls (and on the first)
+
     def __init__(self, params, density, k0, mask, net, n_rays, device="cuda", use_tensor_cores=True,
                  cap_alpha_per_ray=96, cap_keep_per_ray=64, parity_counts=False, n_rays_global=None,
                  scratch_per_ray=128, use_graph=False):
@@ -294,8 +296,18 @@ class FusedTrainer:
             self._step_graphed(self._stage)
         else:
             (stepper or self.step)(self._stage[0], self._stage[1], self._stage[2], self._stage[3])
+        self._host_calls = getattr(self, "_host_calls", 0) + 1
+        check = self._host_calls % self.OVERFLOW_CHECK_EVERY == 1
+        if check:      # at logging cadence: the sample-list overflow flag travels with the loss (one more 64-byte D2H, same sync)
+            if getattr(self, "_cnt_host", None) is None:
+                self._cnt_host = torch.zeros(16, dtype=torch.int32).pin_memory()
+            self._cnt_host.copy_(self.t["counters"], non_blocking=True)
         self._loss_host.copy_(self.t["loss"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if check and int(self._cnt_host[3]) != 0:
+            raise RuntimeError("sample lists overflowed (M_alpha %d > %d or M_keep %d > %d): rays were truncated and gradients dropped; "
+                               "build the trainer with larger cap_alpha_per_ray / cap_keep_per_ray" % (
+                                   int(self._cnt_host[0]), self.cap_alpha, int(self._cnt_host[1]), self.cap_keep))
         return self._loss_host
 
     def step_from_host_async(self, batch_host, stepper=None):

@@ -405,3 +405,24 @@ def test_render_view_equals_the_forward_phase_on_the_same_rays():
                      for a in range(0, H * W, 2048)])
     assert img.shape == (H, W, 3) and torch.equal(img.reshape(-1, 3), ref)
     assert float((img != scene["bg"]).float().mean()) > 0.03, "degenerate view"
+    # ... and against the oracle: the forward of DirectVoxGO (dvgo.py:296-388) on the same rays (the ray construction itself is
+    # checked against the pixel formula on the CPU, tests/test_host_logic.py)
+    tg = np.zeros((H * W, 3), np.float32)
+    o, *_ = _run_oracle(scene, synth.rgbnet_init(), (ro.cpu().numpy(), rd.cpu().numpy(), vd.cpu().numpy(), tg), do_update=0)
+    np.testing.assert_allclose(img.reshape(-1, 3).cpu().numpy(), o["rgb_marched"], rtol=1e-5, atol=2e-6)
+    assert int((o["cnt_keep"] > 0).sum()) > 100
+
+
+def test_sample_list_overflow_is_reported_not_silent(small):
+    """A trainer whose lists are too small for the batch clamps them (no out-of-bounds write) and sets the overflow flag;
+    step_from_host reads the flag with the loss at logging cadence and raises instead of training on truncated rays."""
+    scene, net, rays = small
+    batch = torch.from_numpy(np.stack([a[:1024] for a in rays], 0).copy()).pin_memory()
+    tr, den, k0 = _trainer(scene, net, 1024, cap_alpha_per_ray=1, cap_keep_per_ray=1)
+    tr.cap_alpha = tr.cap_keep = tr._bufs.cap_alpha = tr._bufs.cap_keep = 64      # far fewer entries than this batch produces
+    with pytest.raises(RuntimeError, match="overflowed"):
+        tr.step_from_host(batch)
+    assert tr.counters()["overflow"] == 1
+    ok, *_ = _trainer(scene, net, 1024)
+    loss = ok.step_from_host(batch)
+    assert bool(torch.isfinite(loss).all()) and ok.counters()["overflow"] == 0
