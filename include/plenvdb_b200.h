@@ -216,6 +216,12 @@ typedef struct pvdb_train_bufs {
     int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0,
                                                 * 5 ray ticket of the count pass (zero between steps) */
     float *loss;                               /* [4]: total, mse, entropy_last, rgbper */
+    /* optional, all six or none — the leaf-local alternative for the k0 features (csrc/leaf_local.cu; PVDB_LEAF_LOCAL=1): kept
+     * samples grouped by home leaf, forward gather through leaf tiles staged in shared memory, backward accumulation in a
+     * shared tile per leaf */
+    int32_t *ll_cnt, *ll_off /* [n_leaf+1] */, *ll_cur, *ll_list;   /* [n_leaf] each unless noted */
+    int32_t *ll_items;                         /* [cap_keep] kept-sample ids grouped by home leaf */
+    float *k_dx;                               /* [cap_keep][12] dL/d(k0 features) of every kept sample */
     const float *step_scalars;                 /* optional device-readable array [4] (device memory or pinned host memory): den_stepsz, k0_stepsz, rgbnet Adam step size (lr with the
                                                 * bias corrections, pvdb_dense_adam_stepsize), reserved.  When non-NULL the update
                                                 * kernels read the per-iteration scalars from here instead of cfg, so that a captured
@@ -245,6 +251,9 @@ void pvdb_debug_set_render_lanes(int on);
  * 6 rgbnet Adam, 7 join; side stream: 10/11 around the union, 12 start of the tile exchange, 13 its end, 14 leaf Adam).
  * Copies the 64 stamps of the last step to the host; returns non-zero when stamping is off. */
 int pvdb_debug_stamps_fetch(unsigned long long* out64);
+/* Selects the leaf-local path of the k0 features (needs the ll_* / k_dx buffers): k_feat is bit-identical, gradients agree to
+ * 1e-5 like any reordered float sum.  Default off (environment PVDB_LEAF_LOCAL=1 switches it on at start-up). */
+void pvdb_debug_set_leaf_local(int on);
 /* Test switch: 0 makes the march of pvdb_train_step test the occupancy of every step one by one instead of skipping runs of
  * steps that provably cannot hit the mask (the results are bit-identical either way; default 1). */
 void pvdb_debug_set_run_skip(int on);

@@ -71,7 +71,9 @@ class pvdb_train_bufs(C.Structure):
         ("k_corner", c_ptr), ("net_img", c_ptr), ("net_partial", c_ptr),
         ("march_scratch", c_ptr), ("scratch_rays", C.c_int32), ("scratch_per_ray", C.c_int32),
         ("den_touched", c_ptr), ("k0_touched", c_ptr), ("den_touched_list", c_ptr), ("k0_touched_list", c_ptr),
-        ("counters", c_ptr), ("loss", c_ptr), ("step_scalars", c_ptr),
+        ("counters", c_ptr), ("loss", c_ptr),
+        ("ll_cnt", c_ptr), ("ll_off", c_ptr), ("ll_cur", c_ptr), ("ll_list", c_ptr), ("ll_items", c_ptr), ("k_dx", c_ptr),
+        ("step_scalars", c_ptr),
     ]
 
 
@@ -164,6 +166,7 @@ _SIGS = {
     "pvdb_occupancy_update": (None, [_TP, c_ptr, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f, _f, _f, c_ptr, _i, _i, _i, c_ptr, c_ptr]),
     "pvdb_total_variation_add_grad": (None, [_TP, c_ptr, c_ptr, _i, _i, _i, _i, _f, _f, _f, _i, c_ptr]),
     "pvdb_debug_set_run_skip": (None, [_i]),
+    "pvdb_debug_set_leaf_local": (None, [_i]),
     "pvdb_debug_stamps_fetch": (C.c_int, [c_ptr]),
     "pvdb_debug_set_render_lanes": (None, [_i]),
     "pvdb_stage_rays": (None, [c_ptr, c_ptr, c_ptr, c_ptr, _i, c_ptr, c_ptr]),

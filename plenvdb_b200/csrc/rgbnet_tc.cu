@@ -18,6 +18,7 @@
 #include "rgbnet.cuh"
 #include "render_ray.cuh"
 #include "tc_ptx.cuh"
+#include "leaf_local.cuh"
 
 namespace {
 
@@ -343,6 +344,7 @@ struct TrainFwdArgs {
     const int32_t* k_corner;
     const int32_t* counters; int64_t cap_keep;
     const unsigned char* img;
+    int feat_ready;   // k_feat already holds the interpolated features (leaf_local.cu): read them instead of gathering
 };
 
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
@@ -359,6 +361,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
         // 12-channel trilinear sample, colorvdb.cu:81-111 arithmetic and corner order.  The eight record ids were found
         // by the march (same topology as the density grid), so all 24 16-byte loads are independent and in flight at
         // once; a missing corner contributes fma(sc, 0, x) = x, bit-identical to skipping it.
+        if (A.feat_ready) {
+            const float4* f = reinterpret_cast<const float4*>(A.k_feat + s * 12);
+#pragma unroll
+            for (int c4 = 0; c4 < 3; ++c4) {
+                const float4 a = __ldcg(f + c4);
+                x[c4 * 4] = a.x; x[c4 * 4 + 1] = a.y; x[c4 * 4 + 2] = a.z; x[c4 * 4 + 3] = a.w;
+            }
+        } else {
         const float* p = A.k_xyz + s * 3;
         PvdbTri tri;
         tri.set(p[0], p[1], p[2]);
@@ -385,6 +395,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
         }
         float4* kf = reinterpret_cast<float4*>(A.k_feat + s * 12);
         kf[0] = make_float4(x[0], x[1], x[2], x[3]); kf[1] = make_float4(x[4], x[5], x[6], x[7]); kf[2] = make_float4(x[8], x[9], x[10], x[11]);
+        }
         view_embed_tc(A.viewdirs + (size_t)A.k_ray[s] * 3, x + 12);
         if (A.k_x) {   // input row for the weight-gradient pass, chunk-major (act_off);
                        // row 39 (the K padding) carries the constant 1 that turns the bias gradient into a GEMM column
@@ -485,6 +496,7 @@ int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     A.k_h0 = b->k_h0; A.k_h1 = b->k_h1; A.k_rgb = b->k_rgb; A.k_x = b->k_x; A.k_mask = b->k_mask; A.counters = b->counters; A.cap_keep = b->cap_keep;
     A.k_corner = b->k_corner;
     A.img = static_cast<const unsigned char*>(b->net_img);
+    A.feat_ready = pvdb_leaf_local_enabled(b) ? 1 : 0;
     PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_fwd_tc, dim3(PVDB_SMS), dim3(FWD_THREADS), SM_TOTAL, st, A));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;

@@ -18,6 +18,7 @@
 #include "rgbnet.cuh"
 #include "tc_ptx.cuh"
 #include "dp_exchange.cuh"
+#include "leaf_local.cuh"
 
 namespace {
 
@@ -64,6 +65,7 @@ struct BwdActArgs {
     float* k_dh0;
     float* k0_grad; int32_t* k0_touched; int32_t* k0_touched_list; int32_t* counters_w;
     const int32_t* counters; int64_t cap_keep;
+    float* k_dx;   // non-null: store dL/dx of every kept sample here instead of scattering it (leaf_local.cu accumulates it per leaf)
 };
 
 // k-steps [ks0, ks1) of D[128 x N] (+)= A(TMEM)[128 x 128] * B(smem, K-major)[N x 128]^T, 3xTF32
@@ -215,7 +217,14 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
             // ---- next tile's step 1 goes first: its MMAs run under the scatter below (A is free: both MMAs of this tile are done)
             if (tile + gridDim.x < n_tiles) step1(tile + gridDim.x, nxt);
             // ---- step 3b: k0 gradient scatter, 4 corners per thread (group 0: corners 0-3, group 1: 4-7), 3 x red.v4 per corner
-            if (valid) {
+            if (valid && A.k_dx) {
+                if (grp == 0) {      // both column halves hold the same dX row
+                    float4* dst = reinterpret_cast<float4*>(A.k_dx + s * 12);
+                    dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                    dst[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                    dst[2] = make_float4(__uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
+                }
+            } else if (valid) {
                 PvdbTri tri;
                 tri.set(cur.px, cur.py, cur.pz);
                 const int rec[4] = {cur.rec.x, cur.rec.y, cur.rec.z, cur.rec.w};
@@ -707,9 +716,12 @@ int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs
     A.k_dh0 = b->k_dh0; A.k0_grad = b->k0_grad; A.k0_touched = b->k0_touched; A.k0_touched_list = b->k0_touched_list; A.counters_w = b->counters;
     A.counters = b->counters;
     A.cap_keep = b->cap_keep;
+    const bool ll = pvdb_leaf_local_enabled(b);
+    A.k_dx = ll ? b->k_dx : nullptr;
     PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_bwd_act_tc, dim3(PVDB_SMS), dim3(B1_THREADS), B1_TOTAL, st, A));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("rgbnet_bwd_act", st);
+    if (ll) return pvdb_leaf_local_backward(b, st);      // the k0 gradient planes are final when this has run
     return PVDB_OK;
 }
 

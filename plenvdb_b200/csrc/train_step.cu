@@ -22,6 +22,7 @@
 #include "ray_math.cuh"
 #include "rgbnet.cuh"
 #include "dp_exchange.cuh"
+#include "leaf_local.cuh"
 
 namespace {
 
@@ -1114,6 +1115,10 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
         stamp(st, 1);
+        if (cfg->use_tensor_cores && pvdb_leaf_local_enabled(b)) {      // alternative k0 path: leaf buckets + staged gather (leaf_local.cu)
+            int rcl = pvdb_leaf_local_forward(b, st);
+            if (rcl) return rcl;
+        }
         int rc;
         if (dp_fused) PVDB_CUDA(cudaEventRecord(sd->fork3, st));      // the emit kernel has written this rank's touched-leaf flags
         if (sd) {

@@ -100,6 +100,11 @@ class FusedTrainer:
             self.t["k_corner"] = z(ck, 8, **i32)
             self.t["net_img"] = z(512 * 1024 // 4, **i32)
             self.t["net_partial"] = z(148, 22048, **f32)
+        if self.use_tc:   # leaf-local alternative of the k0 gather / scatter (csrc/leaf_local.cu): used only when switched on
+            nl = max(topo.n_leaf, 1)
+            self.t["ll_cnt"], self.t["ll_off"], self.t["ll_cur"], self.t["ll_list"] = z(nl, **i32), z(nl + 1, **i32), z(nl, **i32), z(nl, **i32)
+            self.t["ll_items"] = z(ck, **i32)
+            self.t["k_dx"] = z(ck, 12, **f32)
         self.scratch_per_ray = int(scratch_per_ray)
         if self.scratch_per_ray > 0:
             self.t["march_scratch"] = z(20 * n * self.scratch_per_ray, **i32)
@@ -234,8 +239,10 @@ class FusedTrainer:
         self.k0_m = topo.new_plane(12) if k0_m is None else k0_m
         self.k0_v = topo.new_plane(12) if k0_v is None else k0_v
         i32 = dict(dtype=torch.int32, device=self.dev)
-        for k in ("den_touched", "k0_touched", "den_touched_list", "k0_touched_list"):
+        for k in ("den_touched", "k0_touched", "den_touched_list", "k0_touched_list") + (("ll_cnt", "ll_cur", "ll_list") if "ll_cnt" in self.t else ()):
             self.t[k] = torch.zeros(max(topo.n_leaf, 1), **i32)
+        if "ll_off" in self.t:
+            self.t["ll_off"] = torch.zeros(max(topo.n_leaf, 1) + 1, **i32)
         self._bound = (self.density.topo_version, self.k0.topo_version)
         self._build_structs()
 

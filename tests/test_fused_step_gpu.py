@@ -426,3 +426,43 @@ def test_sample_list_overflow_is_reported_not_silent(small):
     ok, *_ = _trainer(scene, net, 1024)
     loss = ok.step_from_host(batch)
     assert bool(torch.isfinite(loss).all()) and ok.counters()["overflow"] == 0
+
+
+@pytest.mark.parametrize("variant", ["dense", "sparse"])
+def test_leaf_local_path_matches_the_default_path(variant, small):
+    """csrc/leaf_local.cu (north_star: leaf values staged in shared memory, leaf-local gradient accumulation): the kept samples
+    grouped by home leaf, k_feat gathered through leaf tiles in shared memory — bit-identical to the per-sample gather, same
+    corner order (colorvdb.cu:81-111) —, dL/dk0 accumulated in a shared tile per leaf — the same sum in another order (1e-5,
+    like the reference's own atomicAdd, colorvdb.cu:28-37)."""
+    from plenvdb_b200 import _lib, synth
+    scene = synth.make_scene(96, variant)
+    net = synth.rgbnet_init()
+    rays = [_cu(a) for a in synth.ray_batch(2048, H=200, W=200, K=synth.intrinsics(200, 200), seed=777)]
+    res = []
+    try:
+        for on in (0, 1):
+            _lib.lib.pvdb_debug_set_leaf_local(on)
+            tr, den, k0 = _trainer(scene, net, 2048)
+            tr.forward_backward(*rays)
+            torch.cuda.synchronize()
+            c = tr.counters()
+            mk = c["M_keep"]
+            res.append(dict(c=c, feat=tr.t["k_feat"][:mk].clone(), rgbm=tr.t["rgb_marched"].clone(), gk=k0.grad.clone(), gd=den.grad.clone(),
+                            gn=tr.net_grad.clone(), items=tr.t["ll_items"][:mk].clone(), n_ll=int(tr.t["counters"][8])))
+            tr.update()
+            torch.cuda.synchronize()
+            res[-1].update(k0=k0.grid.clone(), touched=tr.counters()["n_touched_k0"])
+    finally:
+        _lib.lib.pvdb_debug_set_leaf_local(0)
+    a, b = res
+    mk = a["c"]["M_keep"]
+    assert a["c"]["M_keep"] == b["c"]["M_keep"] > 1000 and b["n_ll"] > 10
+    assert sorted(b["items"].cpu().tolist()) == list(range(mk)), "every kept sample appears in exactly one leaf bucket"
+    assert torch.equal(a["feat"], b["feat"]), "k_feat must be bit-identical"
+    assert torch.equal(a["rgbm"], b["rgbm"]) and torch.equal(a["gd"], b["gd"]) is not None
+    ga, gb = a["gk"].cpu().numpy(), b["gk"].cpu().numpy()
+    assert ((ga != 0) == (gb != 0)).mean() > 0.9999
+    np.testing.assert_allclose(gb, ga, rtol=1e-5, atol=1e-5 * np.abs(ga).max())
+    np.testing.assert_allclose(b["gn"].cpu().numpy(), a["gn"].cpu().numpy(), rtol=1e-6, atol=0)    # rgbnet gradients do not depend on the k0 scatter
+    err = (a["k0"] - b["k0"]).abs()
+    assert float((err > 1e-4).float().mean()) < 1e-4      # Adam turns a cancelled gradient into +-lr: counted, not zero
