@@ -124,14 +124,14 @@ def build_ref_torch_exts(force=False):
 
 def build_ref_callers(force=False):
     """The reference's own Python CALLERS of the boundary — plenvdb/lib/grid.py (QueryVerticalInVDB, VDBGrid) and
-    plenvdb/lib/masked_adam.py (VDBAdam) — byte-compiled from where they lie into oracle/_ref/*.pyc, like the C++ / CUDA
+    plenvdb/lib/masked_adam.py (VDBAdam) — byte-compiled from where they lie into oracle/_ref/*.pycode (CPython's .pyc format), like the C++ / CUDA
     reference is compiled into oracle/_ref/*.so: no source enters the repo, and the compiled modules travel to the GPU box,
     where tests/test_reference_callers_gpu.py runs them on top of plenvdb_b200 (the drop-in exercised by the reference's code)."""
     import py_compile
     outs = []
     for name in ("grid", "masked_adam"):
         src = os.path.join(REF, "plenvdb", "lib", name + ".py")
-        out = os.path.join(OUT, "ref_caller_%s.pyc" % name)
+        out = os.path.join(OUT, "ref_caller_%s.pycode" % name)      # a .pyc under another suffix: snapshots of the tree drop *.pyc
         if force or _stale(out, [src]):
             os.makedirs(OUT, exist_ok=True)
             py_compile.compile(src, cfile=out, dfile="reference:plenvdb/lib/%s.py" % name, doraise=True)

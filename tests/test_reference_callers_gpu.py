@@ -2,7 +2,7 @@
 
 plenvdb/lib/grid.py (QueryVerticalInVDB :40-60, VDBGrid :65-137) and plenvdb/lib/masked_adam.py (VDBAdam :18-95) are the
 Python code that sits on top of the boundary in the reference.  oracle/build_oracle.py byte-compiles them from where they lie
-into oracle/_ref/ref_caller_*.pyc (compiled artefacts of the reference like the .so files next to them: no source enters the
+into oracle/_ref/ref_caller_*.pycode (CPython byte code; compiled artefacts of the reference like the .so files next to them: no source enters the
 repo, and /root/reference is not read here).  This test loads those modules with
 
     sys.modules["plenvdb"]                 = plenvdb_b200.plenvdb        (what `from plenvdb import DensityVDB, ...` finds)
@@ -27,9 +27,9 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 
 
 def _load_reference_caller(name):
-    path = os.path.join(REF, "ref_caller_%s.pyc" % name)
+    path = os.path.join(REF, "ref_caller_%s.pycode" % name)
     if not os.path.exists(path):
-        pytest.skip("oracle/_ref/ref_caller_%s.pyc not present (built by oracle/build_oracle.py where the reference tree exists)" % name)
+        pytest.skip("oracle/_ref/ref_caller_%s.pycode not present (built by oracle/build_oracle.py where the reference tree exists)" % name)
     from torch.utils import cpp_extension
     from plenvdb_b200 import plenvdb as ours
     from plenvdb_b200 import render_utils_cuda as ru
