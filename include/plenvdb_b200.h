@@ -171,8 +171,8 @@ typedef struct pvdb_train_cfg {
     float den_stepsz, k0_stepsz, eps, beta0, beta1;
     int32_t den_mode, k0_mode;       /* the fused update implements stepmode 1 (fine stage, configs/default.py:77) */
     float net_lr; int32_t net_step;  /* rgbnet MaskedAdam: lr and step (>=1) of this iteration */
-    int32_t k0_dim;                  /* 12 */
-    int32_t net_width;               /* 128 */
+    int32_t k0_dim;                  /* 12 (fine stage) or 3 (coarse stage: rgb = sigmoid(k0), dvgo.py:344-346) */
+    int32_t net_width;               /* 128, or 0 with k0_dim 3 (no rgbnet) */
     int32_t use_tensor_cores;        /* 1 = tcgen05 rgbnet, 0 = fp32 CUDA-core rgbnet */
     int32_t n_rays_global;           /* N in the means of the losses (== n_rays on one GPU; world*n_rays when sharded) */
     int32_t parity_counts;           /* 1: also produce the reference's untrimmed per-ray M2 counts (cnt_alpha_full) */
@@ -216,6 +216,7 @@ typedef struct pvdb_train_bufs {
     int32_t *counters;                         /* [16]: 0 M_alpha, 1 M_keep, 2 n_touched_den, 3 overflow flag, 4 n_touched_k0,
                                                 * 5 ray ticket of the count pass (zero between steps) */
     float *loss;                               /* [4]: total, mse, entropy_last, rgbper */
+    const float *den_perlr;                    /* coarse stage, den_mode 2: per-voxel lr plane [n_leaf][512] (masked_adam.py:43-46) */
     /* optional, all six or none — the leaf-local alternative for the k0 features (csrc/leaf_local.cu; PVDB_LEAF_LOCAL=1): kept
      * samples grouped by home leaf, forward gather through leaf tiles staged in shared memory, backward accumulation in a
      * shared tile per leaf */

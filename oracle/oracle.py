@@ -226,7 +226,7 @@ class TrainOut(C.Structure):
 
 
 def train_step(cfg, den, den_grad, den_m, den_v, k0, k0_grad, k0_m, k0_v, mask, net, net_m, net_v, rays_o, rays_d, viewdirs,
-               target, cap_keep=0):
+               target, cap_keep=0, den_perlr=None):
     """Runs orc_train_step. `cfg` is a dict of TrainCfg fields. net/net_m/net_v: float32[22019], updated in place.
     Returns a dict of numpy outputs."""
     c = TrainCfg()
@@ -258,8 +258,9 @@ def train_step(cfg, den, den_grad, den_m, den_v, k0, k0_grad, k0_m, k0_v, mask, 
         for k, a in keep.items():
             setattr(o, k, a.ctypes.data)
         res.update(keep)
-    lib.orc_train_step(C.byref(c), den.h, den_grad.h, den_m.h, den_v.h, k0.h, k0_grad.h, k0_m.h, k0_v.h, _p(m), _p(net),
-                       _p(net_m), _p(net_v), _p(ro), _p(rd), _p(vd), _p(tg), n, C.byref(o))
+    lib.orc_train_step_perlr(C.byref(c), den.h, den_grad.h, den_m.h, den_v.h, k0.h, k0_grad.h, k0_m.h, k0_v.h,
+                             den_perlr.h if den_perlr is not None else None, _p(m), _p(net), _p(net_m), _p(net_v), _p(ro), _p(rd), _p(vd),
+                             _p(tg), n, C.byref(o))
     res["loss"] = np.array(list(o.loss), np.float32)
     for k in ("M0", "M0_in", "M1", "M2", "M2_trim", "M3", "V_mask", "V_den", "V_den_grad", "V_k0"):
         res[k] = int(getattr(o, k))

@@ -449,11 +449,16 @@ inline float wld2idx(float p, float mn, float mx, float rm1) { return ((p - mn) 
 inline float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 }  // namespace
 
-extern "C" void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid* den_grad, orc_grid* den_m, orc_grid* den_v,
-                               orc_grid* k0, orc_grid* k0_grad, orc_grid* k0_m, orc_grid* k0_v, const uint8_t* mask, float* net,
-                               float* net_m, float* net_v, const float* rays_o, const float* rays_d, const float* viewdirs,
-                               const float* target, int n_rays, orc_train_out* out) {
+// One iteration of run.py:541-588.  k0->C == 12: fine stage, view-dependent colour through the rgbnet (dvgo.py:347-360).
+// k0->C == 3: coarse stage — no rgbnet, rgb = sigmoid(k0) (dvgo.py:344-346, configs/default.py:94 rgbnet_dim = 0), `net` unused;
+// den_perlr: the per-voxel lr grid of stepmode 2 (masked_adam.py:43-46, 58-59), may be null otherwise.
+static void train_step_impl(const orc_train_cfg* cfg, orc_grid* den, orc_grid* den_grad, orc_grid* den_m, orc_grid* den_v,
+                            orc_grid* k0, orc_grid* k0_grad, orc_grid* k0_m, orc_grid* k0_v, const orc_grid* den_perlr, const uint8_t* mask, float* net,
+                            float* net_m, float* net_v, const float* rays_o, const float* rays_d, const float* viewdirs,
+                            const float* target, int n_rays, orc_train_out* out) {
     const int threads = std::max(1, cfg->threads);
+    const bool direct = k0->C == 3;
+    const int KC = k0->C;
     const float* mn = cfg->xyz_min; const float* mx = cfg->xyz_max;
     const int R[3] = {cfg->reso[0], cfg->reso[1], cfg->reso[2]};
     // MaskGrid buffers (grid.py:229-231) in float32 like torch: scale = (shape-1)/xyz_len; shift = -xyz_min*scale
@@ -541,17 +546,21 @@ extern "C" void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid
             }
     }
     {
-        std::vector<float> k0v((size_t)M3 * K0);
+        std::vector<float> k0v((size_t)M3 * KC);
         orc_sample_forward(k0, kx.data(), ky.data(), kz.data(), M3, k0v.data(), k_leaf.data(), k_offs.data(), threads);
         parallel_for(M3, threads, [&](int64_t b, int64_t e_) {
             for (int64_t s = b; s < e_; ++s) {
-                for (int c = 0; c < K0; ++c) feat[s * DIN + c] = k0v[s * K0 + c];
-                view_embed(viewdirs + (size_t)k_ray[s] * 3, &feat[s * DIN + K0]);
+                for (int c = 0; c < KC; ++c) feat[s * DIN + c] = k0v[s * KC + c];
+                if (!direct) view_embed(viewdirs + (size_t)k_ray[s] * 3, &feat[s * DIN + K0]);
             }
         });
     }
     const float *w0 = net + OFF_W0, *b0 = net + OFF_B0, *w1 = net + OFF_W1, *b1 = net + OFF_B1, *w2 = net + OFF_W2, *b2 = net + OFF_B2;
     // rgbnet (dvgo.py:99-107): Linear(39,128) ReLU Linear(128,128) ReLU Linear(128,3); fp32 in, double accumulate
+    if (direct) {   // dvgo.py:344-346: rgb = torch.sigmoid(k0)
+        for (int64_t s = 0; s < M3; ++s)
+            for (int j = 0; j < 3; ++j) rgb[s * 3 + j] = sigmoidf(feat[s * DIN + j]);
+    } else
     parallel_for(M3, threads, [&](int64_t b, int64_t e_) {
         for (int64_t s = b; s < e_; ++s) {
             for (int j = 0; j < W; ++j) {
@@ -617,7 +626,7 @@ extern "C" void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid
         g_last[r] = gsum * cfg->bg + ge;
     }
     // d rgb, d weight for kept samples; sigmoid backward; rgbnet backward
-    std::vector<float> g_logit((size_t)M3 * 3), g_w(M3), g_feat((size_t)M3 * K0);
+    std::vector<float> g_logit((size_t)M3 * 3), g_w(M3), g_feat((size_t)M3 * KC);
     for (int64_t s = 0; s < M3; ++s) {
         const int r = k_ray[s];
         const float w = ray_smp[r][k_idx[s]].weight;
@@ -632,6 +641,10 @@ extern "C" void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid
     }
     std::vector<std::vector<double>> gnet_t(threads, std::vector<double>(NET_N, 0.0));
     tid_ctr = 0;
+    if (direct) {   // the logit IS the interpolated k0 value
+        for (int64_t s = 0; s < M3; ++s)
+            for (int j = 0; j < 3; ++j) g_feat[s * 3 + j] = g_logit[s * 3 + j];
+    } else
     parallel_for(M3, threads, [&](int64_t b, int64_t e_) {
         std::vector<double>& gn = gnet_t[tid_ctr++];
         std::vector<float> gh1(W), gh0(W);
@@ -708,9 +721,9 @@ extern "C" void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid
 
     // ---- update (run.py:585-588): MaskedAdam on rgbnet (mode 0), VDBAdam step on density / k0
     if (cfg->do_update) {
-        orc_dense_adam(net, gnet.data(), net_m, net_v, nullptr, NET_N, 0, cfg->step, cfg->beta0, cfg->beta1, cfg->lr_net, cfg->eps);
+        if (!direct) orc_dense_adam(net, gnet.data(), net_m, net_v, nullptr, NET_N, 0, cfg->step, cfg->beta0, cfg->beta1, cfg->lr_net, cfg->eps);
         orc_adam_step(den, den_grad, den_m, den_v, cfg->den_mode, orc_adam_stepsize(cfg->lr_density, cfg->beta0, cfg->beta1, cfg->step),
-                      cfg->eps, cfg->beta0, cfg->beta1, nullptr);
+                      cfg->eps, cfg->beta0, cfg->beta1, cfg->den_mode == 2 ? den_perlr : nullptr);
         orc_adam_step(k0, k0_grad, k0_m, k0_v, cfg->k0_mode, orc_adam_stepsize(cfg->lr_k0, cfg->beta0, cfg->beta1, cfg->step), cfg->eps,
                       cfg->beta0, cfg->beta1, nullptr);
     }
@@ -736,7 +749,7 @@ extern "C" void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid
         if (out->keep_step) out->keep_step[s] = sm.step;
         if (out->keep_weight) out->keep_weight[s] = sm.weight;
         if (out->keep_rgb) for (int c = 0; c < 3; ++c) out->keep_rgb[s * 3 + c] = rgb[s * 3 + c];
-        if (out->keep_feat) for (int c = 0; c < K0; ++c) out->keep_feat[s * K0 + c] = feat[s * DIN + c];
+        if (out->keep_feat) for (int c = 0; c < K0; ++c) out->keep_feat[s * K0 + c] = c < KC ? feat[s * DIN + c] : 0.f;
         if (out->keep_leaf) for (int q = 0; q < 8; ++q) out->keep_leaf[s * 8 + q] = k_leaf[s * 8 + q];
         if (out->keep_off) for (int q = 0; q < 8; ++q) out->keep_off[s * 8 + q] = k_offs[s * 8 + q];
     }
@@ -745,6 +758,19 @@ extern "C" void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid
     for (int t = 0; t < threads; ++t) { vm.insert(vmask_t[t].begin(), vmask_t[t].end()); vd.insert(vden_t[t].begin(), vden_t[t].end()); }
     for (int64_t s = 0; s < M3; ++s) for (int q = 0; q < 8; ++q) if (k_leaf[s * 8 + q] >= 0) vk.insert((int64_t)k_leaf[s * 8 + q] * 512 + k_offs[s * 8 + q]);
     out->V_mask = (int64_t)vm.size(); out->V_den = (int64_t)vd.size(); out->V_den_grad = (int64_t)vdeng_t[0].size(); out->V_k0 = (int64_t)vk.size();
+}
+
+extern "C" void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid* den_grad, orc_grid* den_m, orc_grid* den_v,
+                               orc_grid* k0, orc_grid* k0_grad, orc_grid* k0_m, orc_grid* k0_v, const uint8_t* mask, float* net,
+                               float* net_m, float* net_v, const float* rays_o, const float* rays_d, const float* viewdirs,
+                               const float* target, int n_rays, orc_train_out* out) {
+    train_step_impl(cfg, den, den_grad, den_m, den_v, k0, k0_grad, k0_m, k0_v, nullptr, mask, net, net_m, net_v, rays_o, rays_d, viewdirs, target, n_rays, out);
+}
+extern "C" void orc_train_step_perlr(const orc_train_cfg* cfg, orc_grid* den, orc_grid* den_grad, orc_grid* den_m, orc_grid* den_v,
+                                     orc_grid* k0, orc_grid* k0_grad, orc_grid* k0_m, orc_grid* k0_v, const orc_grid* den_perlr, const uint8_t* mask,
+                                     float* net, float* net_m, float* net_v, const float* rays_o, const float* rays_d, const float* viewdirs,
+                                     const float* target, int n_rays, orc_train_out* out) {
+    train_step_impl(cfg, den, den_grad, den_m, den_v, k0, k0_grad, k0_m, k0_v, den_perlr, mask, net, net_m, net_v, rays_o, rays_d, viewdirs, target, n_rays, out);
 }
 
 // ------------------------------------------------------------------------------------------------

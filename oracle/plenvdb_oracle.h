@@ -106,6 +106,13 @@ void orc_train_step(const orc_train_cfg* cfg, orc_grid* den, orc_grid* den_grad,
                     float* net, float* net_m, float* net_v, const float* rays_o, const float* rays_d,
                     const float* viewdirs, const float* target, int n_rays, orc_train_out* out);
 
+/* The same with the per-voxel lr grid of stepmode 2 (masked_adam.py:43-46).  k0 with 3 channels selects the coarse stage: no
+ * rgbnet, rgb = sigmoid(k0) (dvgo.py:344-346); `net*` are not touched then. */
+void orc_train_step_perlr(const orc_train_cfg* cfg, orc_grid* den, orc_grid* den_grad, orc_grid* den_m, orc_grid* den_v,
+                          orc_grid* k0, orc_grid* k0_grad, orc_grid* k0_m, orc_grid* k0_v, const orc_grid* den_perlr, const uint8_t* mask /*[reso]*/,
+                          float* net, float* net_m, float* net_v, const float* rays_o, const float* rays_d,
+                          const float* viewdirs, const float* target, int n_rays, orc_train_out* out);
+
 /* R1: vdb_compression.py:19-59.  Returns N (active voxels); den [N+1], col [(N+1)*cdim] rounded through fp16;
  * idx_dense [reso] 1-based float ids (0 = inactive).  Pass NULL outputs to size. */
 int64_t orc_merge(const orc_grid* den, const orc_grid* k0, const uint8_t* mask, float* dendata, float* coldata,

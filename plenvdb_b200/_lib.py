@@ -72,6 +72,7 @@ class pvdb_train_bufs(C.Structure):
         ("march_scratch", c_ptr), ("scratch_rays", C.c_int32), ("scratch_per_ray", C.c_int32),
         ("den_touched", c_ptr), ("k0_touched", c_ptr), ("den_touched_list", c_ptr), ("k0_touched_list", c_ptr),
         ("counters", c_ptr), ("loss", c_ptr),
+        ("den_perlr", c_ptr),
         ("ll_cnt", c_ptr), ("ll_off", c_ptr), ("ll_cur", c_ptr), ("ll_list", c_ptr), ("ll_items", c_ptr), ("k_dx", c_ptr),
         ("step_scalars", c_ptr),
     ]

@@ -372,6 +372,7 @@ int pvdb_rgbnet_prep_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cud
 int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
 
 int pvdb_rgbnet_forward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
+    if (pvdb_direct_colour(cfg)) return pvdb_direct_forward(b, st);
     if (cfg->use_tensor_cores) return pvdb_rgbnet_forward_tc(cfg, b, viewdirs, st);   // after pvdb_rgbnet_prepare
     static bool attr_set = false;
     if (!attr_set) {
@@ -406,11 +407,13 @@ int pvdb_rgbnet_backward_fp32(const pvdb_train_cfg* cfg, const pvdb_train_bufs* 
 
 // Per-step preparation that does not depend on the samples (tensor-core path: weight images); a no-op for fp32.
 int pvdb_rgbnet_prepare(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st) {
+    if (pvdb_direct_colour(cfg)) return PVDB_OK;
     if (cfg->use_tensor_cores) return pvdb_rgbnet_prep_tc(cfg, b, st);
     return PVDB_OK;
 }
 
 int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
+    if (pvdb_direct_colour(cfg)) return pvdb_direct_backward(b, st);
     if (cfg->use_tensor_cores) return pvdb_rgbnet_backward_tc(cfg, b, viewdirs, st);   // overwrites net_grad (partials + reduce)
     PVDB_CUDA(cudaMemsetAsync(b->net_grad, 0, PVDB_NET_N * sizeof(float), st));
     return pvdb_rgbnet_backward_fp32(cfg, b, viewdirs, st);

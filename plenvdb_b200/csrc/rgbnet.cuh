@@ -26,3 +26,8 @@ int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, co
 int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
 struct PvdbDpNetPush;   // dp_exchange.cuh; nullptr outside a data-parallel step
 int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st, const PvdbDpNetPush* dp_push);
+
+// Coarse stage (k0_dim == 3, no rgbnet): rgb = sigmoid(k0) (coarse.cu)
+static inline bool pvdb_direct_colour(const pvdb_train_cfg* cfg) { return cfg->k0_dim == 3 && cfg->net_width == 0; }
+int pvdb_direct_forward(const pvdb_train_bufs* b, cudaStream_t st);
+int pvdb_direct_backward(const pvdb_train_bufs* b, cudaStream_t st);

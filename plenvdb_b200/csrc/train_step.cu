@@ -989,12 +989,16 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                            const float* viewdirs, const float* target, int n_rays, int phases, void* stream,
                            const pvdb_dp_peers* peers, uint32_t dp_step) {
     PVDB_CHECK_ARG(cfg && b && b->tree, "null cfg/bufs");
-    PVDB_CHECK_ARG(cfg->k0_dim == 12 && cfg->net_width == 128, "the fused step is specialised for k0_dim=12, rgbnet_width=128");
+    const bool direct = pvdb_direct_colour(cfg);      // coarse stage: 3 colour channels, no rgbnet (coarse.cu)
+    PVDB_CHECK_ARG((cfg->k0_dim == 12 && cfg->net_width == 128) || direct,
+                   "the fused step is specialised for k0_dim=12 with rgbnet_width=128 (fine stage) or k0_dim=3 without rgbnet (coarse stage)");
+    PVDB_CHECK_ARG(!direct || !peers, "the data-parallel step covers the fine stage only");
     PVDB_CHECK_ARG(n_rays > 0, "n_rays must be positive");
     const bool do_fwd = phases & PVDB_PHASE_FORWARD, do_bwd = phases & PVDB_PHASE_BACKWARD, do_upd = phases & PVDB_PHASE_UPDATE;
     PVDB_CHECK_ARG(!do_bwd || (do_fwd && target), "backward needs the forward phase and target colours");
-    PVDB_CHECK_ARG(!do_upd || (cfg->den_mode == 1 && cfg->k0_mode == 1),
-                   "the fused update implements stepmode 1 (skip zero grad); use pvdb_adam_step for modes 0/2");
+    PVDB_CHECK_ARG(!do_upd || direct || (cfg->den_mode == 1 && cfg->k0_mode == 1),
+                   "the fine-stage update implements stepmode 1 (skip zero grad); stepmodes 0 / 2 are the coarse stage's (k0_dim=3)");
+    PVDB_CHECK_ARG(!do_upd || !direct || cfg->den_mode != 2 || b->den_perlr, "stepmode 2 needs the per-voxel lr plane (den_perlr)");
     cudaStream_t st = (cudaStream_t)stream;
     pvdb_reset_launch_count();
     pvdb_prof_begin(st);
@@ -1115,7 +1119,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
         stamp(st, 1);
-        if (cfg->use_tensor_cores && pvdb_leaf_local_enabled(b)) {      // alternative k0 path: leaf buckets + staged gather (leaf_local.cu)
+        if (cfg->use_tensor_cores && !direct && pvdb_leaf_local_enabled(b)) {      // alternative k0 path: leaf buckets + staged gather (leaf_local.cu)
             int rcl = pvdb_leaf_local_forward(b, st);
             if (rcl) return rcl;
         }
@@ -1160,7 +1164,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         } else {
             int rc = pvdb_rgbnet_backward(cfg, b, viewdirs, st);
             if (rc) return rc;
-            pvdb_prof_mark(cfg->use_tensor_cores ? "rgbnet_bwd_wgrad" : "rgbnet_bwd", st);
+            pvdb_prof_mark(cfg->use_tensor_cores && !direct ? "rgbnet_bwd_wgrad" : "rgbnet_bwd", st);
         }
         k_ray_bwd<<<warp_grid, 256, 0, sb>>>(b->off_alpha, b->off_keep, b->s_alpha, b->s_T, b->s_weight, b->s_density,
                                                              b->k_gw, b->alphainv_last, b->grad_last, b->s_gden, n_rays,
@@ -1173,7 +1177,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                                   b->cap_alpha));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("density_scatter", st);
-        if (sd && cfg->use_tensor_cores && (peers || do_upd)) {
+        if (sd && cfg->use_tensor_cores && !direct && (peers || do_upd)) {
             // The grid gradients are final once the activation-gradient kernel (main) and the density scatter (side) are done.
             // Everything that only needs them runs on the side stream UNDER the weight-gradient kernel: the NVLink tile
             // exchange of a data-parallel step, and the sparse Adam of the touched leaves.  After the weight-gradient kernel
@@ -1240,6 +1244,26 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                 if (rc) return rc;
             }
         }
+    }
+    if (do_upd && direct) {
+        // Coarse stage (masked_adam.py:56-68 with configs/default.py:48, 64): full-grid Adam in the configured stepmodes — 0 updates every
+        // voxel whatever its gradient, 2 scales the step with the per-voxel lr —, then zero_grad of both planes (run.py:549-550 does it
+        // at the start of the next iteration) and the touched-leaf bookkeeping back to empty.
+        const pvdb_tree* t = b->tree;
+        int rc = pvdb_adam_step(t, b->den, b->den_grad, b->den_m, b->den_v, 1, cfg->den_mode, cfg->den_stepsz, cfg->eps, cfg->beta0, cfg->beta1,
+                                cfg->den_mode == 2 ? b->den_perlr : nullptr, st);
+        if (rc) return rc;
+        rc = pvdb_adam_step(t, b->k0, b->k0_grad, b->k0_m, b->k0_v, 3, cfg->k0_mode, cfg->k0_stepsz, cfg->eps, cfg->beta0, cfg->beta1, nullptr, st);
+        if (rc) return rc;
+        rc = pvdb_zero_grad(t, b->den_grad, 1, st);
+        if (rc) return rc;
+        rc = pvdb_zero_grad(t, b->k0_grad, 3, st);
+        if (rc) return rc;
+        const size_t nl = (size_t)(t->n_leaf > 0 ? t->n_leaf : 1) * sizeof(int32_t);
+        PVDB_CUDA(cudaMemsetAsync(b->den_touched, 0, nl, st));
+        PVDB_CUDA(cudaMemsetAsync(b->k0_touched, 0, nl, st));
+        pvdb_prof_mark("update_dense", st);
+        return PVDB_OK;
     }
     if (do_upd && !update_done) {
         if (!do_bwd && !(phases & PVDB_PHASE_LISTS_READY)) {   // gradients (and flags) came from elsewhere, e.g. a data-parallel all-reduce: rebuild the lists

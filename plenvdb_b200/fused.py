@@ -60,14 +60,21 @@ class FusedTrainer:
         self.topo = topo
         self._bound = (density.topo_version, k0.topo_version)
         self.n_rays = int(n_rays)
-        self.use_tc = bool(use_tensor_cores)
+        self.k0_dim = int(k0.ndim)
+        self.direct = self.k0_dim == 3       # coarse stage: 3 colour channels, no rgbnet (dvgo.py:344-346)
+        assert self.k0_dim in (3, 12), "k0 must have 12 channels (fine stage) or 3 (coarse stage)"
+        self.use_tc = bool(use_tensor_cores) and not self.direct
         self.step_count = 0
         self.launches_total = 0      # kernels of this library launched through this trainer
         f32 = dict(dtype=torch.float32, device=self.dev)
         i32 = dict(dtype=torch.int32, device=self.dev)
         # optimiser state (DensityOpt / ColorOpt / MaskedAdam equivalents)
         self.den_m, self.den_v = topo.new_plane(1), topo.new_plane(1)
-        self.k0_m, self.k0_v = topo.new_plane(12), topo.new_plane(12)
+        self.k0_m, self.k0_v = topo.new_plane(self.k0_dim), topo.new_plane(self.k0_dim)
+        self.den_perlr = None                # per-voxel lr plane of stepmode 2 (set_pervoxel_lr)
+        if net is None:
+            assert self.direct, "the fine stage needs the packed rgbnet parameters"
+            net = np.zeros(NET_N, np.float32)
         self.net = torch.as_tensor(np.asarray(net, np.float32)).to(self.dev).contiguous()
         assert self.net.numel() == NET_N
         self.net_grad, self.net_m, self.net_v = (torch.zeros(NET_N, **f32) for _ in range(3))
@@ -91,13 +98,17 @@ class FusedTrainer:
             counters=z(16, **i32), loss=z(4, **f32),
         )
         # activations kept for the fp32 rgbnet backward (the tcgen05 forward still pairs with it)
-        self.t["k_h0"] = z(ck, 128, **f32)
-        self.t["k_h1"] = z(ck, 128, **f32)
+        if self.direct:   # no rgbnet: no activations to keep
+            self.t["k_h0"] = self.t["k_h1"] = z(1, **f32)
+        else:
+            self.t["k_h0"] = z(ck, 128, **f32)
+            self.t["k_h1"] = z(ck, 128, **f32)
+        if self.use_tc or self.direct:
+            self.t["k_corner"] = z(ck, 8, **i32)     # record ids of the eight corners, saved by the march
         if self.use_tc:   # tensor-core backward: input rows and masked activation gradients for the weight-gradient GEMM
             self.t["k_x"] = z(ck, 40, **f32)
             self.t["k_dh0"] = z(ck, 128, **f32)
             self.t["k_mask"] = z(ck, 8, **i32)
-            self.t["k_corner"] = z(ck, 8, **i32)
             self.t["net_img"] = z(512 * 1024 // 4, **i32)
             self.t["net_partial"] = z(148, 22048, **f32)
         if self.use_tc:   # leaf-local alternative of the k0 gather / scatter (csrc/leaf_local.cu): used only when switched on
@@ -152,7 +163,7 @@ class FusedTrainer:
         for k in ("near", "far", "stepdist", "act_shift", "interval", "fast_color_thres", "bg", "weight_main",
                   "weight_entropy_last", "weight_rgbper", "eps", "beta0", "beta1", "den_mode", "k0_mode"):
             setattr(c, k, P[k])
-        c.k0_dim, c.net_width = 12, 128
+        c.k0_dim, c.net_width = (3, 0) if self.direct else (12, 128)
         c.use_tensor_cores = int(self.use_tc)
         c.n_rays_global = self.n_rays_global
         c.parity_counts = int(self.parity_counts)
@@ -169,6 +180,7 @@ class FusedTrainer:
             setattr(b, k, p(t))
         b.scratch_rays, b.scratch_per_ray = self.n_rays, self.scratch_per_ray
         b.step_scalars = None
+        b.den_perlr = self.den_perlr.data_ptr() if self.den_perlr is not None else None
         self._bufs = b
         self._graphs = {}           # captured graphs hold the old pointers
 
@@ -215,6 +227,15 @@ class FusedTrainer:
         g["graph"].replay()
         self.launches_total += g["launches"]
 
+    def set_pervoxel_lr(self, count):
+        """VDBAdam.set_pervoxel_lr (masked_adam.py:43-46): `count` is the dense view-count grid [reso]; the density step of
+        stepmode 2 is scaled by count / count.max() per voxel."""
+        c = torch.as_tensor(np.asarray(count.cpu() if torch.is_tensor(count) else count, np.float32)).to(self.dev)
+        per = (c / c.max()).reshape(-1).contiguous()
+        self.den_perlr = self.topo.new_plane(1)
+        self.density.copyFromDense_torch(per.reshape(self.density.reso), plane=self.den_perlr)
+        self._build_structs()
+
     def decay_lr(self, factor):
         """run.py:592-598: multiply every lr by `factor` (float32 for the grids, like the C++ members)."""
         self.lr_density = float(np.float32(self.lr_density) * np.float32(factor))
@@ -236,8 +257,9 @@ class FusedTrainer:
         self.topo = topo
         self.den_m = topo.new_plane(1) if den_m is None else den_m
         self.den_v = topo.new_plane(1) if den_v is None else den_v
-        self.k0_m = topo.new_plane(12) if k0_m is None else k0_m
-        self.k0_v = topo.new_plane(12) if k0_v is None else k0_v
+        self.k0_m = topo.new_plane(self.k0_dim) if k0_m is None else k0_m
+        self.k0_v = topo.new_plane(self.k0_dim) if k0_v is None else k0_v
+        self.den_perlr = None      # congruent with the old tree: set_pervoxel_lr again
         i32 = dict(dtype=torch.int32, device=self.dev)
         for k in ("den_touched", "k0_touched", "den_touched_list", "k0_touched_list") + (("ll_cnt", "ll_cur", "ll_list") if "ll_cnt" in self.t else ()):
             self.t[k] = torch.zeros(max(topo.n_leaf, 1), **i32)

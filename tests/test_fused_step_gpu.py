@@ -469,3 +469,65 @@ def test_leaf_local_path_matches_the_default_path(variant, small):
     np.testing.assert_allclose(b["gn"].cpu().numpy(), a["gn"].cpu().numpy(), rtol=1e-6, atol=0)    # rgbnet gradients do not depend on the k0 scatter
     err = (a["k0"] - b["k0"]).abs()
     assert float((err > 1e-4).float().mean()) < 1e-4      # Adam turns a cancelled gradient into +-lr: counted, not zero
+
+
+def test_coarse_stage_step_matches_the_oracle():
+    """The coarse stage of run.py (configs/default.py:41-66, 94): ColorVDB with 3 channels, no rgbnet, rgb = sigmoid(k0)
+    (dvgo.py:72-79, 344-346), fast_color_thres 1e-7, VDBAdam with the per-voxel lr for the density (stepmode 2) and stepmode 0 for
+    k0 (masked_adam.py:43-46, 56-68) — through the same fused step (coarse.cu + the full-grid Adam), three iterations against the
+    oracle: counts and lists bit for bit, colours 1e-5, parameters after every step."""
+    from oracle import oracle as orc
+    from plenvdb_b200 import synth
+    from plenvdb_b200.fused import FusedTrainer
+    from plenvdb_b200.plenvdb import ColorVDB, DensityVDB
+    scene = synth.make_scene(64, "dense")
+    scene = dict(scene, fast_color_thres=1e-7, den_mode=2, k0_mode=0)
+    R = scene["reso"]
+    k0_dense = np.ascontiguousarray(scene["k0"][..., :3])
+    den = DensityVDB(list(R), 1)
+    k0 = ColorVDB(list(R), 3)
+    k0._set_topology(den.topo)
+    den.copyFromDense(scene["density"].reshape(-1))
+    k0.copyFromDense(k0_dense.reshape(-1))
+    n = 1024
+    tr = FusedTrainer(scene, den, k0, scene["mask"], None, n, cap_alpha_per_ray=256, cap_keep_per_ray=256)
+    rng = np.random.default_rng(9)
+    count = rng.integers(1, 40, R).astype(np.float32)                    # view counts (dvgo.py:212-243 produces them)
+    tr.set_pervoxel_lr(count)
+    oden, ok0 = orc.Grid(R, 1), orc.Grid(R, 3)
+    oden.copy_from_dense(scene["density"])
+    ok0.copy_from_dense(k0_dense)
+    operlr = orc.Grid(R, 1)
+    operlr.copy_from_dense((count / count.max()).astype(np.float32))
+    aux = [orc.Grid(R, c) for c in (1, 1, 1, 3, 3, 3)]
+    dummy = np.zeros(22019, np.float32)
+    for step in range(1, 4):
+        rays = synth.ray_batch(n, H=160, W=160, K=synth.intrinsics(160, 160), seed=100 + step)
+        o = orc.train_step(_oracle_cfg(scene, step, 1), oden, aux[0], aux[1], aux[2], ok0, aux[3], aux[4], aux[5], scene["mask"], dummy, dummy.copy(),
+                           dummy.copy(), *rays, cap_keep=256 * n, den_perlr=operlr)
+        cu = [_cu(a) for a in rays]
+        tr.forward_backward(*cu)
+        torch.cuda.synchronize()
+        c = tr.counters()
+        assert c["overflow"] == 0 and c["M_keep"] == o["M3"] > 3000 and c["M_alpha"] == o["M2_trim"]
+        t = {k: tr.t[k].cpu().numpy() for k in ("cnt_keep", "cnt_alpha", "k_ray", "s_step", "k_sample", "rgb_marched", "loss", "k_feat", "k_corner")}
+        M3 = o["M3"]
+        assert np.array_equal(t["cnt_keep"], o["cnt_keep"]) and np.array_equal(t["cnt_alpha"], o["cnt_alpha"])
+        assert np.array_equal(t["k_ray"][:M3], o["keep_ray"]) and np.array_equal(t["s_step"][t["k_sample"][:M3]], o["keep_step"])
+        assert np.array_equal(t["k_corner"][:M3], np.where(o["keep_leaf"] >= 0, o["keep_leaf"] * 512 + o["keep_off"], -1))
+        if step == 1:
+            assert np.array_equal(t["k_feat"][:M3, :3], o["keep_feat"][:, :3])                       # same arithmetic, same order: bit-exact
+        np.testing.assert_allclose(t["rgb_marched"], o["rgb_marched"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(t["loss"], o["loss"], rtol=1e-4)
+        gk, wk = k0.grad.cpu().numpy().reshape(-1), aux[3].get_values().reshape(-1)
+        np.testing.assert_allclose(gk, wk, rtol=1e-5, atol=1e-5 * np.abs(wk).max())
+        gd, wd = den.grad.cpu().numpy().reshape(-1), aux[0].get_values().reshape(-1)
+        np.testing.assert_allclose(gd, wd, rtol=1e-5, atol=2e-5 * np.abs(wd).max())
+        tr.update()
+        torch.cuda.synchronize()
+        for got, want in ((den.grid, oden), (k0.grid, ok0)):
+            got, want = got.cpu().numpy().reshape(-1), want.get_values().reshape(-1)
+            err = np.abs(got - want)
+            off = err > 1e-4 * np.abs(want) + 2e-4
+            assert off.mean() < 2e-4 and err.max() <= 2.0 * step * 0.1 + 1e-3, (step, int(off.sum()), float(err.max()))
+        assert float(den.grad.abs().max()) == 0.0 and float(k0.grad.abs().max()) == 0.0 and int(tr.t["k0_touched"].sum()) == 0
