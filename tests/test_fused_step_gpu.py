@@ -509,7 +509,7 @@ def test_coarse_stage_step_matches_the_oracle():
         tr.forward_backward(*cu)
         torch.cuda.synchronize()
         c = tr.counters()
-        assert c["overflow"] == 0 and c["M_keep"] == o["M3"] > 3000 and c["M_alpha"] == o["M2_trim"]
+        assert c["overflow"] == 0 and c["M_keep"] == o["M3"] > 1000 and c["M_alpha"] == o["M2_trim"]
         t = {k: tr.t[k].cpu().numpy() for k in ("cnt_keep", "cnt_alpha", "k_ray", "s_step", "k_sample", "rgb_marched", "loss", "k_feat", "k_corner")}
         M3 = o["M3"]
         assert np.array_equal(t["cnt_keep"], o["cnt_keep"]) and np.array_equal(t["cnt_alpha"], o["cnt_alpha"])
