@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr int CNT_M_ALPHA = 0, CNT_M_KEEP = 1, CNT_N_TOUCHED_DEN = 2, CNT_OVERFLOW = 3, CNT_N_TOUCHED_K0 = 4, CNT_RAY_TICKET = 5, CNT_CTA_DONE = 6;
+constexpr int CNT_M_ALPHA = 0, CNT_M_KEEP = 1, CNT_N_TOUCHED_DEN = 2, CNT_OVERFLOW = 3, CNT_N_TOUCHED_K0 = 4, CNT_RAY_TICKET = 5, CNT_CTA_DONE = 6, CNT_MARCH_DONE = 9;
 
 struct MarchParams {
     pvdb_tree tree;
@@ -337,25 +337,46 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
 // ticket == nullptr: warp w marches ray w.  Otherwise a resident grid of warps draws rays from an atomic ticket counter
 // (rays differ 10x in length; 8192 of them are 1.4 waves of static warps, so the tail of a static grid idles a third of
 // the machine).  The counter is reset by k_scan_counts, which always follows the count pass.
+// Option (off, measured slower — see where it is set): the exclusive scans that turn the per-ray counts into segment offsets
+// (scan_counts_cta below) run in the LAST CTA of the count pass to finish instead of in k_scan_counts.
+struct ScanTail {
+    int32_t *oa, *ok; float* loss; int64_t cap_alpha, cap_keep;
+    int enabled;
+};
+__device__ void scan_counts_cta(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck, int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
+                                int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha, int64_t cap_keep);
+
 template <int MODE, bool PARITY, int VAR>
 __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
-                                                  const float* __restrict__ rays_d, int n_rays, int32_t* __restrict__ ticket) {
+                                                  const float* __restrict__ rays_d, int n_rays, int32_t* __restrict__ ticket, ScanTail S) {
     pvdb_pdl_wait();
     const int lane = threadIdx.x & 31;
     if (ticket == nullptr) {
         const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-        if (r >= n_rays) return;
-        march_ray<MODE, PARITY, VAR>(P, O, rays_o, rays_d, r, lane);
-        return;
+        if (r < n_rays) march_ray<MODE, PARITY, VAR>(P, O, rays_o, rays_d, r, lane);
+    } else {
+        // first ray of every resident warp: its own index (no atomic — thousands of warps drawing their first ticket at once
+        // was 12 % of the kernel's stall samples); further rays are drawn from the counter, which numbers the rays after those
+        const int n_warps = (gridDim.x * blockDim.x) >> 5;
+        int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        while (r < n_rays) {
+            march_ray<MODE, PARITY, VAR>(P, O, rays_o, rays_d, r, lane);
+            if (lane == 0) r = n_warps + atomicAdd(ticket, 1);
+            r = __shfl_sync(0xffffffffu, r, 0);
+        }
     }
-    // first ray of every resident warp: its own index (no atomic — thousands of warps drawing their first ticket at once
-    // was 12 % of the kernel's stall samples); further rays are drawn from the counter, which numbers the rays after those
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    while (r < n_rays) {
-        march_ray<MODE, PARITY, VAR>(P, O, rays_o, rays_d, r, lane);
-        if (lane == 0) r = n_warps + atomicAdd(ticket, 1);
-        r = __shfl_sync(0xffffffffu, r, 0);
+    if (MODE == 0 && S.enabled) {
+        __shared__ bool s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();                       // this CTA's counts before its arrival (threadFenceReduction pattern)
+            s_last = atomicAdd(O.counters + CNT_MARCH_DONE, 1) == (int)gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            scan_counts_cta(O.cnt_alpha, O.cnt_keep, S.oa, S.ok, n_rays, O.counters, S.loss, S.cap_alpha, S.cap_keep);
+        }
     }
 }
 
@@ -430,28 +451,27 @@ __global__ void __launch_bounds__(256) k_hit_mask(MarchParams P, const float* __
 // consecutive rays (two 16-byte loads per array), scans them in registers, then warp shuffle scan + a 32-entry block scan;
 // batches of 8192 rays are chained through a running carry.  Also clears the per-step accumulators of the kernels that
 // follow (loss sums, touched-leaf counts, tickets), which saves two memsets in the stream.
-__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck,
-                                                      int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
-                                                      int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha,
-                                                      int64_t cap_keep) {
-    pvdb_pdl_wait();
+__device__ void scan_counts_cta(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck, int32_t* __restrict__ oa,
+                                int32_t* __restrict__ ok, int n, int32_t* __restrict__ counters, float* __restrict__ loss,
+                                int64_t cap_alpha, int64_t cap_keep) {
     __shared__ int2 wtot[32];
     __shared__ int2 carry_s;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (threadIdx.x == 0) carry_s = make_int2(0, 0);
     if (threadIdx.x < 4) loss[threadIdx.x] = 0.f;
     __syncthreads();
-    for (int base = 0; base < n; base += 8192) {
+    const int per_round = blockDim.x * 8;
+    for (int base = 0; base < n; base += per_round) {
         const int i0 = base + threadIdx.x * 8;
         int a[8], k[8];
         if (i0 + 8 <= n) {
-            const int4 a0 = *reinterpret_cast<const int4*>(ca + i0), a1 = *reinterpret_cast<const int4*>(ca + i0 + 4);
-            const int4 k0 = *reinterpret_cast<const int4*>(ck + i0), k1 = *reinterpret_cast<const int4*>(ck + i0 + 4);
+            const int4 a0 = __ldcg(reinterpret_cast<const int4*>(ca + i0)), a1 = __ldcg(reinterpret_cast<const int4*>(ca + i0 + 4));
+            const int4 k0 = __ldcg(reinterpret_cast<const int4*>(ck + i0)), k1 = __ldcg(reinterpret_cast<const int4*>(ck + i0 + 4));
             a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
             k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { a[j] = i0 + j < n ? ca[i0 + j] : 0; k[j] = i0 + j < n ? ck[i0 + j] : 0; }
+            for (int j = 0; j < 8; ++j) { a[j] = i0 + j < n ? __ldcg(ca + i0 + j) : 0; k[j] = i0 + j < n ? __ldcg(ck + i0 + j) : 0; }
         }
         int2 tot = make_int2(0, 0);
 #pragma unroll
@@ -466,14 +486,14 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
         __syncthreads();
         const int2 carry = carry_s;
         if (wid == 0) {
-            const int2 own = wtot[lane];
+            const int2 own = lane < nw ? wtot[lane] : make_int2(0, 0);
             int2 w = own;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int ux = __shfl_up_sync(0xffffffffu, w.x, o), uy = __shfl_up_sync(0xffffffffu, w.y, o);
                 if (lane >= o) { w.x += ux; w.y += uy; }
             }
-            wtot[lane] = make_int2(w.x - own.x, w.y - own.y);   // exclusive prefix of each warp
+            if (lane < nw) wtot[lane] = make_int2(w.x - own.x, w.y - own.y);   // exclusive prefix of each warp
             if (lane == 31) carry_s = make_int2(carry.x + w.x, carry.y + w.y);
         }
         __syncthreads();
@@ -497,7 +517,15 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
         counters[CNT_M_ALPHA] = w.x; counters[CNT_M_KEEP] = w.y;
         counters[CNT_OVERFLOW] = (w.x > cap_alpha || w.y > cap_keep) ? 1 : 0;
         counters[CNT_N_TOUCHED_DEN] = 0; counters[CNT_N_TOUCHED_K0] = 0; counters[CNT_RAY_TICKET] = 0; counters[CNT_CTA_DONE] = 0;
+        counters[CNT_MARCH_DONE] = 0;
     }
+}
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck,
+                                                      int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
+                                                      int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha,
+                                                      int64_t cap_keep) {
+    pvdb_pdl_wait();
+    scan_counts_cta(ca, ck, oa, ok, n, counters, loss, cap_alpha, cap_keep);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1071,6 +1099,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     if (dp_fused) O.dp_flags = pvdb_dp_flags_ptr(peers, dp_step);
     stamp(st, 0);
 
+    bool scan_fused = false;
     if (do_fwd) {
         PVDB_CHECK_ARG(rays_o && rays_d && viewdirs, "null rays");
         if (sd) {
@@ -1081,9 +1110,18 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             PVDB_CUDA(cudaEventRecord(sd->join2, sd->s));
         }
         const int var = (P.run_skip ? 1 : 0) | (O.dp_flags ? 2 : 0);
+        // PVDB_SCAN_IN_MARCH=1: the offset scans in the last CTA of the count pass instead of a kernel of their own.  Measured
+        // slower (0.2037 vs 0.2008 ms per step, two runs each on one box): the 256-thread tail needs four dependent rounds where
+        // k_scan_counts does one with 1024 threads, and that kernel's launch is already hidden by the programmatic dependent launch.
+        static int scan_in_march = -1;
+        if (scan_in_march < 0) { const char* e = getenv("PVDB_SCAN_IN_MARCH"); scan_in_march = e ? (atoi(e) != 0) : 0; }
+        ScanTail S;
+        S.oa = b->off_alpha; S.ok = b->off_keep; S.loss = b->loss; S.cap_alpha = b->cap_alpha; S.cap_keep = b->cap_keep;
+        S.enabled = (scan_in_march && !pvdb_prof_active()) ? 1 : 0;       // per-kernel profiling keeps the scan visible as a kernel
+        scan_fused = S.enabled != 0;
         if (cfg->parity_counts) {
-            if (var & 1) k_march<0, true, 1><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
-            else k_march<0, true, 0><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+            if (var & 1) k_march<0, true, 1><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr, S);
+            else k_march<0, true, 0><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr, S);
             PVDB_CHECK_ARG(!(var & 2), "parity_counts is a single-GPU diagnostic (not available in the data-parallel step)");
         } else {
             static int resident = 0;   // CTAs of the count kernel that fit the device at once
@@ -1094,17 +1132,19 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             }
             const dim3 grid(min(resident, warp_grid));
             int32_t* ticket = b->counters + CNT_RAY_TICKET;
-            if (var == 0) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 0>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket));
-            else if (var == 1) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 1>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket));
-            else if (var == 2) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 2>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket));
-            else PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 3>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket));
+            if (var == 0) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 0>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket, S));
+            else if (var == 1) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 1>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket, S));
+            else if (var == 2) PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 2>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket, S));
+            else PVDB_CUDA(pvdb_launch_pdl(k_march<0, false, 3>, grid, dim3(256), 0, st, P, O, rays_o, rays_d, n_rays, ticket, S));
         }
         PVDB_LAUNCH_CHECK();
         stamp(st, 8);
         pvdb_prof_mark("march_count", st);
-        PVDB_CUDA(pvdb_launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays,
-                                  b->counters, b->loss, b->cap_alpha, b->cap_keep));
-        PVDB_LAUNCH_CHECK();
+        if (!scan_fused) {
+            PVDB_CUDA(pvdb_launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays,
+                                      b->counters, b->loss, b->cap_alpha, b->cap_keep));
+            PVDB_LAUNCH_CHECK();
+        }
         stamp(st, 9);
         pvdb_prof_mark("scan", st);
         PVDB_CHECK_ARG(!O.scratch || n_rays <= b->scratch_rays, "march_scratch holds fewer rays than this batch");
@@ -1112,9 +1152,9 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             if (O.dp_flags) PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch<2>, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
             else PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch<0>, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
         } else if (O.dp_flags) {
-            k_march<1, false, 2><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+            k_march<1, false, 2><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr, ScanTail{});
         } else {
-            k_march<1, false, 0><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr);
+            k_march<1, false, 0><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr, ScanTail{});
         }
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("march_emit", st);
