@@ -232,6 +232,8 @@ typedef struct pvdb_train_bufs {
 #define PVDB_PHASE_FORWARD 1    /* sample, interpolate, rgbnet, composite (+ losses when target != NULL) */
 #define PVDB_PHASE_BACKWARD 2   /* gradients into den_grad / k0_grad / net_grad (accumulating, like autograd) */
 #define PVDB_PHASE_UPDATE 4     /* sparse Adam on touched leaves + rgbnet Adam; clears the gradients it consumed */
+#define PVDB_PHASE_ACCUMULATE 16 /* with FORWARD: gradients of an earlier BACKWARD have not been consumed by an UPDATE yet (gradient accumulation
+                                  * over several batches): keep their leaves on the touched lists */
 #define PVDB_PHASE_LISTS_READY 8 /* with UPDATE alone: den/k0_touched_list + counters[2],[4] are already valid (pvdb_dp_exchange) */
 int pvdb_train_step(const pvdb_train_cfg* cfg, const pvdb_train_bufs* bufs,
                     const float* rays_o, const float* rays_d, const float* viewdirs, const float* target,

@@ -414,7 +414,6 @@ int pvdb_rgbnet_prepare(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cud
 
 int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
     if (pvdb_direct_colour(cfg)) return pvdb_direct_backward(b, st);
-    if (cfg->use_tensor_cores) return pvdb_rgbnet_backward_tc(cfg, b, viewdirs, st);   // overwrites net_grad (partials + reduce)
-    PVDB_CUDA(cudaMemsetAsync(b->net_grad, 0, PVDB_NET_N * sizeof(float), st));
-    return pvdb_rgbnet_backward_fp32(cfg, b, viewdirs, st);
+    if (cfg->use_tensor_cores) return pvdb_rgbnet_backward_tc(cfg, b, viewdirs, st);   // partials + reduce, added to net_grad
+    return pvdb_rgbnet_backward_fp32(cfg, b, viewdirs, st);                             // atomics into net_grad (accumulating)
 }

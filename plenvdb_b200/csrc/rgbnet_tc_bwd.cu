@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
         float t = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
-        net_grad[e] = t;
+        net_grad[e] += t;      // accumulating, like the grid gradients (the rgbnet Adam clears what it consumed)
         if (push.world > 1) {
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -725,7 +725,7 @@ int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs
     return PVDB_OK;
 }
 
-// B2: weight gradients -> net_grad (overwritten)
+// B2: weight gradients -> net_grad (accumulated)
 int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st, const PvdbDpNetPush* dp_push) {
     if (int rc = bwd_attrs()) return rc;
     BwdWgradArgs W;

@@ -341,10 +341,10 @@ __device__ __forceinline__ void march_ray(const MarchParams& P, const MarchOut& 
 // (scan_counts_cta below) run in the LAST CTA of the count pass to finish instead of in k_scan_counts.
 struct ScanTail {
     int32_t *oa, *ok; float* loss; int64_t cap_alpha, cap_keep;
-    int enabled;
+    int enabled, keep_touched;
 };
 __device__ void scan_counts_cta(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck, int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
-                                int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha, int64_t cap_keep);
+                                int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha, int64_t cap_keep, int keep_touched);
 
 template <int MODE, bool PARITY, int VAR>
 __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, con
         __syncthreads();
         if (s_last) {
             __threadfence();
-            scan_counts_cta(O.cnt_alpha, O.cnt_keep, S.oa, S.ok, n_rays, O.counters, S.loss, S.cap_alpha, S.cap_keep);
+            scan_counts_cta(O.cnt_alpha, O.cnt_keep, S.oa, S.ok, n_rays, O.counters, S.loss, S.cap_alpha, S.cap_keep, S.keep_touched);
         }
     }
 }
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256) k_hit_mask(MarchParams P, const float* __
 // follow (loss sums, touched-leaf counts, tickets), which saves two memsets in the stream.
 __device__ void scan_counts_cta(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck, int32_t* __restrict__ oa,
                                 int32_t* __restrict__ ok, int n, int32_t* __restrict__ counters, float* __restrict__ loss,
-                                int64_t cap_alpha, int64_t cap_keep) {
+                                int64_t cap_alpha, int64_t cap_keep, int keep_touched) {
     __shared__ int2 wtot[32];
     __shared__ int2 carry_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -516,16 +516,19 @@ __device__ void scan_counts_cta(const int32_t* __restrict__ ca, const int32_t* _
         oa[n] = w.x; ok[n] = w.y;
         counters[CNT_M_ALPHA] = w.x; counters[CNT_M_KEEP] = w.y;
         counters[CNT_OVERFLOW] = (w.x > cap_alpha || w.y > cap_keep) ? 1 : 0;
-        counters[CNT_N_TOUCHED_DEN] = 0; counters[CNT_N_TOUCHED_K0] = 0; counters[CNT_RAY_TICKET] = 0; counters[CNT_CTA_DONE] = 0;
+        // keep_touched: gradients of an earlier backward are still waiting for their update (gradient accumulation): their leaves
+        // stay on the touched lists, which only the update empties
+        if (!keep_touched) { counters[CNT_N_TOUCHED_DEN] = 0; counters[CNT_N_TOUCHED_K0] = 0; }
+        counters[CNT_RAY_TICKET] = 0; counters[CNT_CTA_DONE] = 0;
         counters[CNT_MARCH_DONE] = 0;
     }
 }
 __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ ca, const int32_t* __restrict__ ck,
                                                       int32_t* __restrict__ oa, int32_t* __restrict__ ok, int n,
                                                       int32_t* __restrict__ counters, float* __restrict__ loss, int64_t cap_alpha,
-                                                      int64_t cap_keep) {
+                                                      int64_t cap_keep, int keep_touched) {
     pvdb_pdl_wait();
-    scan_counts_cta(ca, ck, oa, ok, n, counters, loss, cap_alpha, cap_keep);
+    scan_counts_cta(ca, ck, oa, ok, n, counters, loss, cap_alpha, cap_keep, keep_touched);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1117,6 +1120,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         if (scan_in_march < 0) { const char* e = getenv("PVDB_SCAN_IN_MARCH"); scan_in_march = e ? (atoi(e) != 0) : 0; }
         ScanTail S;
         S.oa = b->off_alpha; S.ok = b->off_keep; S.loss = b->loss; S.cap_alpha = b->cap_alpha; S.cap_keep = b->cap_keep;
+        S.keep_touched = (phases & PVDB_PHASE_ACCUMULATE) ? 1 : 0;
         S.enabled = (scan_in_march && !pvdb_prof_active()) ? 1 : 0;       // per-kernel profiling keeps the scan visible as a kernel
         scan_fused = S.enabled != 0;
         if (cfg->parity_counts) {
@@ -1142,7 +1146,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         pvdb_prof_mark("march_count", st);
         if (!scan_fused) {
             PVDB_CUDA(pvdb_launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, b->cnt_alpha, b->cnt_keep, b->off_alpha, b->off_keep, n_rays,
-                                      b->counters, b->loss, b->cap_alpha, b->cap_keep));
+                                      b->counters, b->loss, b->cap_alpha, b->cap_keep, (int)((phases & PVDB_PHASE_ACCUMULATE) ? 1 : 0)));
             PVDB_LAUNCH_CHECK();
         }
         stamp(st, 9);

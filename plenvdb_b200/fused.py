@@ -16,7 +16,7 @@ from .plenvdb import ColorVDB, DensityVDB
 from .synth import mask_scale_shift  # noqa: F401  (numpy-only helper; re-exported for callers of this module)
 from .tree import Topology
 
-PHASE_FORWARD, PHASE_BACKWARD, PHASE_UPDATE, PHASE_LISTS_READY = 1, 2, 4, 8
+PHASE_FORWARD, PHASE_BACKWARD, PHASE_UPDATE, PHASE_LISTS_READY, PHASE_ACCUMULATE = 1, 2, 4, 8, 16
 NET_N = 22019
 
 
@@ -278,9 +278,15 @@ class FusedTrainer:
         if phases & PHASE_UPDATE:
             self.step_count += 1
             self._set_step_scalars()
+        if (phases & PHASE_BACKWARD) and getattr(self, "_grads_pending", False):
+            phases |= PHASE_ACCUMULATE        # a backward without update came before: its leaves stay on the touched lists
         _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(rays_o), _lib.ptr(rays_d),
                   _lib.ptr(viewdirs), _lib.ptr(target), n, int(phases), _lib.current_stream())
         self.launches_total += int(_lib.lib.pvdb_last_launch_count())
+        if phases & PHASE_UPDATE:
+            self._grads_pending = False
+        elif phases & PHASE_BACKWARD:
+            self._grads_pending = True
 
     def step(self, rays_o, rays_d, viewdirs, target):
         """One full iteration: forward + backward + sparse Adam (grids) + Adam (rgbnet).  With use_graph=True the batch is
@@ -415,6 +421,7 @@ class FusedTrainer:
         _lib.call("pvdb_train_step", C.byref(self.cfg), C.byref(self._bufs), _lib.ptr(dummy), _lib.ptr(dummy), _lib.ptr(dummy),
                   None, self.n_rays, PHASE_UPDATE | (PHASE_LISTS_READY if lists_ready else 0), _lib.current_stream())
         self.launches_total += int(_lib.lib.pvdb_last_launch_count())
+        self._grads_pending = False
 
     def forward(self, rays_o, rays_d, viewdirs):
         """Render rays through the training model (run.py:171-189); returns rgb_marched [n,3]."""

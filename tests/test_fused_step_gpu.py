@@ -531,3 +531,28 @@ def test_coarse_stage_step_matches_the_oracle():
             off = err > 1e-4 * np.abs(want) + 2e-4
             assert off.mean() < 2e-4 and err.max() <= 2.0 * step * 0.1 + 1e-3, (step, int(off.sum()), float(err.max()))
         assert float(den.grad.abs().max()) == 0.0 and float(k0.grad.abs().max()) == 0.0 and int(tr.t["k0_touched"].sum()) == 0
+
+
+def test_two_backward_passes_before_one_update_accumulate(small):
+    """Gradient accumulation: forward_backward on two half batches, then one update, equals one full-batch
+    iteration — the leaves touched by the first pass must still be on the touched lists when the update runs."""
+    scene, net, rays = small
+    a = [_cu(x[:1024]) for x in rays]
+    b = [_cu(x[1024:]) for x in rays]
+    full = [_cu(x) for x in rays]
+    tr1, den1, k01 = _trainer(scene, net, 2048)
+    tr1.step(*full)
+    tr2, den2, k02 = _trainer(scene, net, 1024, n_rays_global=2048)
+    tr2.forward_backward(*a)
+    n_a = tr2.counters()["n_touched_den"]
+    tr2.forward_backward(*b)
+    torch.cuda.synchronize()
+    assert tr2.counters()["n_touched_den"] >= n_a > 0
+    lst = tr2.t["den_touched_list"][: tr2.counters()["n_touched_den"]].cpu().numpy()
+    assert len(set(lst.tolist())) == len(lst) == int(tr2.t["den_touched"].sum())       # every flagged leaf exactly once
+    tr2.update()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(den2.grid.cpu().numpy(), den1.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(k02.grid.cpu().numpy(), k01.grid.cpu().numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(tr2.net.cpu().numpy(), tr1.net.cpu().numpy(), rtol=1e-3, atol=2e-5)
+    assert float(den2.grad.abs().max()) == 0.0 and int(tr2.t["den_touched"].sum()) == 0
