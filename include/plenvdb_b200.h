@@ -227,6 +227,10 @@ typedef struct pvdb_train_bufs {
                                                 * bias corrections, pvdb_dense_adam_stepsize), reserved.  When non-NULL the update
                                                 * kernels read the per-iteration scalars from here instead of cfg, so that a captured
                                                 * CUDA graph of the step can be replayed for every iteration */
+    float *ray_pe;                             /* optional [n_rays][28] scratch (tensor-core path): view-direction embedding of every ray
+                                                * (dvgo.py:354-357: viewdirs, sin, cos, one zero of padding), filled once per step
+                                                * underneath the march and read by the rgbnet forward for the ~10 kept samples of a
+                                                * ray; NULL: the forward evaluates the 24 sinf / cosf per sample */
 } pvdb_train_bufs;
 
 #define PVDB_PHASE_FORWARD 1    /* sample, interpolate, rgbnet, composite (+ losses when target != NULL) */

@@ -74,7 +74,7 @@ class pvdb_train_bufs(C.Structure):
         ("counters", c_ptr), ("loss", c_ptr),
         ("den_perlr", c_ptr),
         ("ll_cnt", c_ptr), ("ll_off", c_ptr), ("ll_cur", c_ptr), ("ll_list", c_ptr), ("ll_items", c_ptr), ("k_dx", c_ptr),
-        ("step_scalars", c_ptr),
+        ("step_scalars", c_ptr), ("ray_pe", c_ptr),
     ]
 
 

@@ -368,7 +368,7 @@ constexpr size_t BWD_SMEM = (size_t)(W * W + W * KX + 3 * W + TS * 4 + TS * LDX 
 }  // namespace
 
 int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
-int pvdb_rgbnet_prep_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st);
+int pvdb_rgbnet_prep_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, int n_rays, cudaStream_t st);
 int pvdb_rgbnet_backward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
 
 int pvdb_rgbnet_forward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st) {
@@ -406,9 +406,9 @@ int pvdb_rgbnet_backward_fp32(const pvdb_train_cfg* cfg, const pvdb_train_bufs* 
 }
 
 // Per-step preparation that does not depend on the samples (tensor-core path: weight images); a no-op for fp32.
-int pvdb_rgbnet_prepare(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st) {
+int pvdb_rgbnet_prepare(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, int n_rays, cudaStream_t st) {
     if (pvdb_direct_colour(cfg)) return PVDB_OK;
-    if (cfg->use_tensor_cores) return pvdb_rgbnet_prep_tc(cfg, b, st);
+    if (cfg->use_tensor_cores) return pvdb_rgbnet_prep_tc(cfg, b, viewdirs, n_rays, st);
     return PVDB_OK;
 }
 

@@ -15,7 +15,8 @@
 #define PVDB_NET_N (PVDB_NET_OFF_B2 + 3)   // 22019
 
 // Sample-independent per-step preparation (weight images of the tensor-core kernels); must precede the forward.
-int pvdb_rgbnet_prepare(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st);
+// viewdirs / n_rays: the batch whose forward follows (per-ray view embedding table, when b->ray_pe is there).
+int pvdb_rgbnet_prepare(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, int n_rays, cudaStream_t st);
 // Forward over the kept-sample list: k_feat, k_h0, k_h1 (fp32 path), k_rgb.  Enqueues on `st`.
 int pvdb_rgbnet_forward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
 // Backward: consumes g_logit (in k_rgb), produces net_grad (zeroed first) and scatters the k0 gradient.

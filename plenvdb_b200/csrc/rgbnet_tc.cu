@@ -13,6 +13,7 @@
 //     (~2^-11) would not.
 // One thread issues the MMAs; completion is signalled through tcgen05.commit -> mbarrier.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ray_math.cuh"
 #include "rgbnet.cuh"
@@ -38,18 +39,19 @@ constexpr int SM_W0LO = SM_W0HI + WD * K0P * 4;
 constexpr int SM_W1HI = SM_W0LO + WD * K0P * 4;             // [128][128]
 constexpr int SM_W1LO = SM_W1HI + WD * WD * 4;
 constexpr int SM_W2F = SM_W1LO + WD * WD * 4;               // [3][128] fp32 (layer 2 runs on the CUDA cores)
-constexpr int SM_B0 = SM_W2F + 3 * WD * 4;
-constexpr int SM_B1 = SM_B0 + WD * 4;
-constexpr int SM_B2 = SM_B1 + WD * 4;                       // [4]
+// The biases ride on the tensor core: b0 is column 39 of the W0 image (the K padding; the staged input row carries a 1
+// there), b1 is one extra k-step of layer 1 whose A operand is a constant tile of ones (columns 0, 1) and whose B operand
+// holds hi(b1) in k = 0 and lo(b1) in k = 1 — one MMA per tile instead of an LDS + FADD per activation value.
+constexpr int SM_ONES = SM_W2F + 3 * WD * 4;                // A [128][8]
+constexpr int SM_B1T = SM_ONES + WD * 8 * 4;                // B [128][8]
+constexpr int SM_B2 = SM_B1T + WD * 8 * 4;                  // [4]
 constexpr int IMG_BYTES = SM_B2 + 16;
-constexpr int SM_BAR = IMG_BYTES;   // mbarriers: W, L0, L1, FULL[2], EMPTY[2], X_RDY, A_RDY[4]; tmem base at +96
-constexpr int BAR_W = 0, BAR_L0 = 8, BAR_L1 = 16, BAR_FULL = 24, BAR_EMPTY = 40, BAR_XRDY = 56, BAR_ARDY = 64, TMEM_SLOT = 96;
-constexpr int XLD = 44;   // staging row stride in floats: 16-byte row reads/writes by 8 consecutive threads hit distinct banks
+constexpr int SM_BAR = IMG_BYTES;   // mbarriers: W, L0, L1, X_RDY, A_RDY[4]; tmem base at +96
+constexpr int BAR_W = 0, BAR_L0 = 8, BAR_L1 = 16, BAR_XRDY = 56, BAR_ARDY = 64, TMEM_SLOT = 96;
 constexpr int SM_RED = SM_BAR + 112;                        // [3][128] partial outputs of the second lane-warp group
-constexpr int SM_XBUF = SM_RED + 3 * 128 * 4;               // two staging buffers [128][44] floats
-constexpr int XBUF_BYTES = 128 * XLD * 4;
-constexpr int SM_TOTAL = SM_XBUF + 2 * XBUF_BYTES;
-static_assert(IMG_BYTES % 16 == 0 && SM_XBUF % 16 == 0 && SM_TOTAL <= 227 * 1024, "smem map");
+constexpr int SM_STAGE = SM_RED + 3 * 128 * 4;              // activation store staging, one region per lane warp (stage_store32)
+constexpr int SM_TOTAL = SM_STAGE + 8 * STAGE_WARP_BYTES;
+static_assert(IMG_BYTES % 16 == 0 && SM_STAGE % 16 == 0 && SM_TOTAL <= 227 * 1024, "smem map");
 
 // Issue the 3xTF32 MMAs of k-steps [ks0, ks1) of one layer: D[128 x N] (+)= A[128 x K] * W[N x K]^T.  Single thread.
 __device__ __forceinline__ void issue_ksteps(uint32_t tmem, uint32_t d_col, uint32_t smem_base, int off_hi, int off_lo, int K, int N,
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(256) k_prep_fwd_image(TcWeights Wt, unsigned c
     if (net_packed) prep_bwd_image(net_packed, img + PVDB_BWD_IMG_OFFSET, gtid, gsz);
     for (int e = gtid; e < WD * K0P; e += gsz) {
         const int n = e / K0P, k = e % K0P;
-        const float v = k < PVDB_NET_DIN ? __ldg(Wt.w0 + (size_t)n * Wt.w0_sn + (size_t)k * Wt.w0_sk) : 0.f;
+        const float v = k < PVDB_NET_DIN ? __ldg(Wt.w0 + (size_t)n * Wt.w0_sn + (size_t)k * Wt.w0_sk) : __ldg(Wt.b0 + n);
         uint32_t hi, lo;
         split_tf32(v, hi, lo);
         const int o = canon_off(n, k, K0P);
@@ -119,24 +121,54 @@ __global__ void __launch_bounds__(256) k_prep_fwd_image(TcWeights Wt, unsigned c
     }
     float* w2f = reinterpret_cast<float*>(img + SM_W2F);
     for (int e = gtid; e < 3 * WD; e += gsz) w2f[e] = __ldg(Wt.w2 + (size_t)(e / WD) * Wt.w2_sn + (size_t)(e % WD) * Wt.w2_sk);
-    for (int e = gtid; e < WD; e += gsz) {
-        reinterpret_cast<float*>(img + SM_B0)[e] = __ldg(Wt.b0 + e);
-        reinterpret_cast<float*>(img + SM_B1)[e] = __ldg(Wt.b1 + e);
+    for (int e = gtid; e < WD * 8; e += gsz) {
+        const int n = e >> 3, k = e & 7;
+        uint32_t hi, lo;
+        split_tf32(__ldg(Wt.b1 + n), hi, lo);
+        const int o = canon_off(n, k, 8);
+        *reinterpret_cast<float*>(img + SM_ONES + o) = k < 2 ? 1.0f : 0.f;
+        *reinterpret_cast<uint32_t*>(img + SM_B1T + o) = k == 0 ? hi : k == 1 ? lo : 0u;
     }
     if (gtid < 4) reinterpret_cast<float*>(img + SM_B2)[gtid] = gtid < 3 ? __ldg(Wt.b2 + gtid) : 0.f;
 }
 
+// x[12..39] of every ray of the batch: [vd(3) | sin(vd_a 2^k) a-major (12) | cos (12) | 0], the same expressions as
+// view_embed_tc.  One thread per ray; runs with the image prep on the side stream, underneath the march.
+__global__ void __launch_bounds__(128) k_ray_pe(const float* __restrict__ viewdirs, int n_rays, float* __restrict__ pe) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const float d[3] = {__ldg(viewdirs + (size_t)r * 3), __ldg(viewdirs + (size_t)r * 3 + 1), __ldg(viewdirs + (size_t)r * 3 + 2)};
+    float o[28];
+    o[0] = d[0]; o[1] = d[1]; o[2] = d[2]; o[27] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float x = __fmul_rn(d[a], (float)(1 << k));
+            o[3 + a * 4 + k] = sinf(x);
+            o[15 + a * 4 + k] = cosf(x);
+        }
+    float4* dst = reinterpret_cast<float4*>(pe + (size_t)r * 28);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) dst[q] = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+}
+
 // Common body, warp specialised (13 warps):
 //   warps 0-7   "lane warps": thread = (TMEM lane = sample, column half).  Warp w and w+4 share the 32 lanes of quarter
-//               w%4 (the TMEM access rule) and split every 128-column row in two.  They run the epilogues (bias, ReLU, tf32
-//               split back into TMEM as the next A operand, activation stores) and the 128 -> 3 output layer on the CUDA cores;
-//   warps 8-11  "producers": gather the input rows of the tiles ahead (k0 trilinear / feature list + view PE, the memory-
-//               and SFU-latency bound part) into two shared staging buffers (full/empty mbarriers);
+//               w%4 (the TMEM access rule) and split every 128-column row in two.  They run the epilogues (ReLU, tf32 split
+//               back into TMEM as the next A operand, activation stores through the per-warp staging regions) and the
+//               128 -> 3 output layer on the CUDA cores;
+//   warps 8-11  "producers": thread = sample; warp 8+q owns TMEM quarter q.  They gather the input row of the next tile
+//               (k0 trilinear / feature list + view PE: the memory-latency bound part) into registers while the current
+//               tile computes, and write it straight into TMEM as the layer-0 A operand once layer 1 of the current tile
+//               has left those columns;
 //   warp 12     "issuer": one thread feeds the tensor core.  It never touches TMEM data itself, so the lane warps are never
 //               held up behind a queue of MMAs: they signal "chunk c of A is in TMEM" through mbarriers and move on.
 // Per tile: epilogue 0 drains D0 in four 32-column chunks and the issuer starts layer 1's k-steps of each chunk (into D1)
 // as soon as it lands; while the lane warps run epilogue 1 from D1, the next tile's layer 0 already runs into D0.
-// FeatFn(s, x[40]) fills the input row of sample s; ActFn sees each post-ReLU chunk; OutFn(s, raw[3]) consumes the result.
+// The biases are inside the MMAs (see the smem map).
+// FeatFn(s, valid, x[40]) fills the input row of sample s; ActFn(s, valid, layer, c, h[32], stage) sees each post-ReLU chunk;
+// OutFn(s, raw[3]) consumes the result.
 constexpr int FWD_THREADS = 416;
 constexpr int N_LANE_THREADS = 256;
 
@@ -149,8 +181,6 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + SM_BAR;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + TMEM_SLOT);
-    const float* sb0 = reinterpret_cast<const float*>(smem + SM_B0);
-    const float* sb1 = reinterpret_cast<const float*>(smem + SM_B1);
     const float* sb2 = reinterpret_cast<const float*>(smem + SM_B2);
     const float* sw2 = reinterpret_cast<const float*>(smem + SM_W2F);
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -158,8 +188,7 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
         mbar_init(bars + BAR_W, 1);
         mbar_init(bars + BAR_L0, 1);
         mbar_init(bars + BAR_L1, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(bars + BAR_FULL + 8 * b, 128); mbar_init(bars + BAR_EMPTY + 8 * b, N_LANE_THREADS); }
-        mbar_init(bars + BAR_XRDY, N_LANE_THREADS);
+        mbar_init(bars + BAR_XRDY, 128);
         for (int c = 0; c < 4; ++c) mbar_init(bars + BAR_ARDY + 8 * c, 128);
         fence_async_smem();
         mbar_expect_tx(bars + BAR_W, IMG_BYTES);
@@ -191,7 +220,9 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
                 for (int c = 0; c < 4; ++c) {
                     mbar_wait(bars + BAR_ARDY + 8 * c, i & 1);
                     tc_fence_after();
-                    issue_ksteps(tmem, COL_D1, sbase, SM_W1HI, SM_W1LO, WD, WD, c * 4, c * 4 + 4, c == 0);
+                    if (c == 0)      // D1 = 1 * hi(b1) + 1 * lo(b1): the layer's k-steps accumulate on top of the bias
+                        umma_tf32_ss(tmem + COL_D1, make_desc(sbase + SM_ONES, 8), make_desc(sbase + SM_B1T, 8), make_idesc(WD), 0u);
+                    issue_ksteps(tmem, COL_D1, sbase, SM_W1HI, SM_W1LO, WD, WD, c * 4, c * 4 + 4, false);
                 }
                 umma_commit(bars + BAR_L1);
                 if (tile + gridDim.x < n_tiles) {
@@ -204,59 +235,46 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
         }
     } else if (warp >= 8) {
         // ---------------- producers
-        const int p = tid - N_LANE_THREADS;
+        const int lane_s = (warp & 3) * 32 + (tid & 31);         // sample within the tile = TMEM lane (warp 8+q: quarter q)
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         int i = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
-            const int b = i & 1;
-            if (i >= 2) mbar_wait(bars + BAR_EMPTY + 8 * b, ((i >> 1) - 1) & 1);
-            const int64_t s = tile * TM + p;
+            const int64_t s = tile * TM + lane_s;
             float x[K0P];
 #pragma unroll
             for (int q = 0; q < K0P; ++q) x[q] = 0.f;
+#ifdef PVDB_TC_TIMING
+            if (tid == N_LANE_THREADS && i < 8) g_tc_t[blockIdx.x][i][12] = clock64();
+#endif
             feat(s, s < M, x);
-            float4* row = reinterpret_cast<float4*>(smem + SM_XBUF + b * XBUF_BYTES) + p * (XLD / 4);
-#pragma unroll
-            for (int q = 0; q < K0P / 4; ++q) row[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
-            mbar_arrive(bars + BAR_FULL + 8 * b);
+#ifdef PVDB_TC_TIMING
+            if (tid == N_LANE_THREADS && i < 8) g_tc_t[blockIdx.x][i][13] = clock64();
+#endif
+            x[K0P - 1] = 1.0f;      // multiplies the b0 column of the W0 image
+            // columns 0-39 of A still feed layer 1 of the previous tile until its MMAs have completed
+            if (i > 0) { mbar_wait(bars + BAR_L1, (i - 1) & 1); tc_fence_after(); }
+            store_a_row(lane_addr, 0, x, K0P);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bars + BAR_XRDY);
         }
     } else if ((int64_t)blockIdx.x < n_tiles) {
         // ---------------- lane warps
         const int grp = warp >> 2;                               // column half
         const int lane_s = (warp & 3) * 32 + (tid & 31);         // sample within the tile = TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32-lane quarter
+        unsigned char* stage = smem + SM_STAGE + warp * STAGE_WARP_BYTES;
         uint32_t par0 = 0, par1 = 0;
-        int i = 0;
-        // take this thread's part of tile `it`'s staged row (group 0: columns 0-23, group 1: 24-39), hand the buffer back,
-        // write it as the layer-0 A operand and tell the issuer
-        auto start_tile = [&](int it) {
-            const int b = it & 1;
-            mbar_wait(bars + BAR_FULL + 8 * b, (it >> 1) & 1);
-            const float4* row = reinterpret_cast<const float4*>(smem + SM_XBUF + b * XBUF_BYTES) + lane_s * (XLD / 4);
-            float x[24];
-            if (grp == 0) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) { const float4 v = row[q]; x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w; }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { const float4 v = row[6 + q]; x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w; }
-            }
-            mbar_arrive(bars + BAR_EMPTY + 8 * b);
-            if (grp == 0) store_a_row(lane_addr, 0, x, 24); else store_a_row(lane_addr, 24, x, 16);
-            tmem_st_wait();
-            tc_fence_before();     // also orders this thread's earlier D0 reads before the issuer's next layer-0 MMAs
-            mbar_arrive(bars + BAR_XRDY);
-        };
-        start_tile(0);
-        mbar_wait(bars + BAR_W, 0);      // biases / W2 of the image are read below
+        mbar_wait(bars + BAR_W, 0);      // W2 / b2 of the image are read below
         const int cb = grp * 64;         // this thread's 64 columns of every 128-column row
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i, ++tile_no) {
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
             const int64_t s = tile * TM + lane_s;
             const bool valid = s < M;
             TC_T(2);
             mbar_wait(bars + BAR_L0, par0); par0 ^= 1;
             tc_fence_after();
             TC_T(3);
-            // ---- epilogue 0: D0 -> bias + ReLU -> A; layer 1 follows chunk by chunk on the tensor core
+            // ---- epilogue 0: D0 -> ReLU -> A; layer 1 follows chunk by chunk on the tensor core
             {
                 uint32_t r[2][32];
                 tmem_ld32(lane_addr + COL_D0 + cb, r[0]);
@@ -267,22 +285,20 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
                     const int c = cb + j * 32;
                     float h[32];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]) + sb0[c + q], 0.f);
+                    for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]), 0.f);
                     store_a_row(lane_addr, c, h, 32);
                     tmem_st_wait();
                     tc_fence_before();   // (first chunk: also orders the previous tile's D1 reads before the new layer-1 MMAs)
                     mbar_arrive(bars + BAR_ARDY + 8 * (c >> 5));
-                    act(s, valid, 0, c, h);
+                    act(s, valid, 0, c, h, stage);
                 }
             }
             TC_T(4);
             mbar_wait(bars + BAR_L1, par1); par1 ^= 1;
             tc_fence_after();
             TC_T(5);
-            // ---- the next tile's layer 0 runs under this tile's second epilogue
-            if (tile + gridDim.x < n_tiles) start_tile(i + 1);
             TC_T(6);
-            // ---- epilogue 1: D1 -> bias + ReLU -> 128 -> 3 output layer on the CUDA cores
+            // ---- epilogue 1: D1 -> ReLU -> 128 -> 3 output layer on the CUDA cores (the next tile's layer 0 runs underneath)
             float o0 = 0.f, o1 = 0.f, o2 = 0.f;
             {
                 uint32_t r[2][32];
@@ -294,8 +310,8 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
                     const int c = cb + j * 32;
                     float h[32];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]) + sb1[c + q], 0.f);
-                    act(s, valid, 1, c, h);
+                    for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]), 0.f);
+                    act(s, valid, 1, c, h, stage);
 #pragma unroll
                     for (int q = 0; q < 32; q += 4) {
                         const float4 a = *reinterpret_cast<const float4*>(sw2 + c + q);
@@ -316,6 +332,7 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
             }
             TC_T(7);
         }
+        if ((tid & 31) == 0) bulk_wait0();      // this warp's activation blocks are in global memory before the kernel ends
     }
     tc_fence_before();
     __syncthreads();
@@ -345,6 +362,7 @@ struct TrainFwdArgs {
     const int32_t* counters; int64_t cap_keep;
     const unsigned char* img;
     int feat_ready;   // k_feat already holds the interpolated features (leaf_local.cu): read them instead of gathering
+    const float* ray_pe;   // [n_rays][28]: x[12..39] of every ray (view direction, sin, cos, padding), k_ray_pe; null: computed per sample
 };
 
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
@@ -396,7 +414,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
         float4* kf = reinterpret_cast<float4*>(A.k_feat + s * 12);
         kf[0] = make_float4(x[0], x[1], x[2], x[3]); kf[1] = make_float4(x[4], x[5], x[6], x[7]); kf[2] = make_float4(x[8], x[9], x[10], x[11]);
         }
-        view_embed_tc(A.viewdirs + (size_t)A.k_ray[s] * 3, x + 12);
+        if (A.ray_pe) {      // the embedding depends on the ray only (dvgo.py:354-357): ~10 kept samples share one table row
+            const float4* pe = reinterpret_cast<const float4*>(A.ray_pe + (size_t)A.k_ray[s] * 28);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const float4 a = __ldg(pe + q);
+                x[12 + q * 4] = a.x; x[13 + q * 4] = a.y; x[14 + q * 4] = a.z; x[15 + q * 4] = a.w;
+            }
+        } else {
+            view_embed_tc(A.viewdirs + (size_t)A.k_ray[s] * 3, x + 12);
+        }
         if (A.k_x) {   // input row for the weight-gradient pass, chunk-major (act_off);
                        // row 39 (the K padding) carries the constant 1 that turns the bias gradient into a GEMM column
             float* kx = A.k_x + act_off(s, 0, 40);
@@ -409,20 +436,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
 #pragma unroll
         for (int j = 0; j < 3; ++j) A.k_rgb[s * 3 + j] = 1.0f / (1.0f + expf(-raw[j]));
     };
-    auto act = [&](int64_t s, bool valid, int layer, int c, const float* h) {
+    auto act = [&](int64_t s, bool valid, int layer, int c, const float* h, unsigned char* stage) {
         if (A.k_mask) {   // ReLU sign bits for the backward: bit i of word (layer*4 + c/32) = h[c+i] > 0
+            // h >= 0 here, so h > 0 <=> its bit pattern is >= 1 <=> bit 31 of (bits + 0x7fffffff): two integer ops per value
             uint32_t m = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m |= (valid && h[i] > 0.f ? 1u : 0u) << i;
-            A.k_mask[(s >> 7) * (8 * 128) + (layer * 4 + (c >> 5)) * 128 + (s & 127)] = m;   // [tile][8][128]
+            for (int i = 31; i >= 0; --i) m = __funnelshift_l(__float_as_uint(h[i]) + 0x7fffffffu, m, 1);
+            A.k_mask[(s >> 7) * (8 * 128) + (layer * 4 + (c >> 5)) * 128 + (s & 127)] = valid ? m : 0u;   // [tile][8][128]
         }
         float* dst = layer == 0 ? A.k_h0 : A.k_h1;
-        if (!dst) return;
-        // chunk-major (act_off): a warp's store covers two full 64-byte runs, and the weight-gradient pass streams each
-        // 16-sample chunk as one contiguous block
-        float* g = dst + act_off(s, c, WD);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) g[i * 16] = valid ? h[i] : 0.f;   // zero rows past M: the weight-gradient pass reads whole tiles
+        if (dst) stage_store32(stage, dst, s - (threadIdx.x & 31), c, WD, h, valid);      // chunk-major (act_off)
     };
     mlp_tiles(smem, A.img, A.counters + CNT_M_KEEP, A.cap_keep, feat, out, act);
 }
@@ -455,7 +478,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs 
 #pragma unroll
         for (int j = 0; j < 3; ++j) A.s_rgb[s * 3 + j] = w / (1 + expf(-raw[j]));   // final_render (:115-117)
     };
-    auto act = [&](int64_t, bool, int, int, const float*) {};
+    auto act = [&](int64_t, bool, int, int, const float*, unsigned char*) {};
     mlp_tiles(smem, A.img, A.counters, A.cap, feat, out, act);
 }
 
@@ -470,7 +493,7 @@ extern "C" int pvdb_debug_tc_timing(long long* out) {
 
 // Weight images of the forward and of the activation-gradient kernel (independent of the march: the fused step runs it on
 // a side stream underneath the count pass).
-int pvdb_rgbnet_prep_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st) {
+int pvdb_rgbnet_prep_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, int n_rays, cudaStream_t st) {
     PVDB_CHECK_ARG(b->net_img, "net_img scratch missing (tensor-core rgbnet)");
     const float* net = b->net;   // PyTorch layout: W[n][k] row-major
     TcWeights W;
@@ -480,6 +503,10 @@ int pvdb_rgbnet_prep_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cud
     W.b0 = net + PVDB_NET_OFF_B0; W.b1 = net + PVDB_NET_OFF_B1; W.b2 = net + PVDB_NET_OFF_B2;
     k_prep_fwd_image<<<PVDB_SMS, 256, 0, st>>>(W, static_cast<unsigned char*>(b->net_img), b->net);
     PVDB_LAUNCH_CHECK();
+    if (b->ray_pe && viewdirs && n_rays > 0) {
+        k_ray_pe<<<(n_rays + 127) / 128, 128, 0, st>>>(viewdirs, n_rays, b->ray_pe);
+        PVDB_LAUNCH_CHECK();
+    }
     return PVDB_OK;
 }
 
@@ -497,6 +524,7 @@ int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     A.k_corner = b->k_corner;
     A.img = static_cast<const unsigned char*>(b->net_img);
     A.feat_ready = pvdb_leaf_local_enabled(b) ? 1 : 0;
+    A.ray_pe = b->ray_pe;
     PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_fwd_tc, dim3(PVDB_SMS), dim3(FWD_THREADS), SM_TOTAL, st, A));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;

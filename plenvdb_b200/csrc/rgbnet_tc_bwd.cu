@@ -259,41 +259,52 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
 // K-major instead: the activations live in HBM chunk-major [chunk of 16 samples][feature][16 samples] (act_off), i.e. a
 // chunk of one tensor is a row-major [features][64 bytes] block — exactly the K-major SWIZZLE_64B UMMA layout (8-row x
 // 64-byte atoms) up to the XOR of the 16-byte column with row bits, which TMA applies on the way in.
-// One elected thread issues five TMA tensor loads + one bulk copy per chunk; nothing else touches the load path.
-// Measured on B200 (scratch/tf32_probe.cu): kind::tf32 TRUNCATES the low 13 mantissa bits, so the raw fp32 tile is its own
-// "hi" operand and only lo = x - trunc(x) has to be computed (elementwise, layout-agnostic).
+// One elected thread issues four TMA tensor loads + five bulk copies per chunk; nothing else touches the load path.
+// Measured on B200 (scratch/tf32_probe.cu): kind::tf32 TRUNCATES the low 13 mantissa bits, so a raw fp32 tile in shared memory
+// is its own "hi" operand and only lo = x - trunc(x) has to be computed (elementwise, layout-agnostic).
 //
-// Warp-specialised streaming pipeline, 3 stages of 16 samples:
-//   warps 0-7   converters: wait full[st]; lo tiles; warps 4-7 also dW2 / db2 partial sums on the CUDA cores; arrive conv[st]
+// The kernel is bound by shared-memory bandwidth (round 2, scratch/wg_timing.py: 1.8 k cycles per 16-sample chunk with ~180 KB
+// of shared-memory traffic per chunk at 128 B/clk; four more converter warps made it slower), and 84 KB of the 180 were the
+// tensor core reading its operands — every operand three times for 3xTF32.  So the A operands (dH1^T, dH0^T: 128 features x
+// 16 samples) do not live in shared memory at all: a converter thread owns one feature row = one TMEM lane, computes (dH1) or
+// reads (dH0) its 16 samples and writes hi / lo straight into TMEM (A-from-TMEM form of tcgen05.mma, two alternating sets of
+// 64 columns).  Shared-memory traffic per chunk: ~110 KB.
+//
+// Warp-specialised streaming pipeline, 6 stages of 16 samples:
+//   warps 0-3   converters A1: dH1 = [h1 > 0] (g . W2) for feature row j, from the 16 x 3 logit gradients, W2 and the mask words
+//               (dH1 never exists in HBM) -> TMEM; their share of the lo tiles of the B operands
+//   warps 4-7   converters A0: dH0 row j from the landed tile -> TMEM; dW2 / db2 partial sums on the CUDA cores; lo tiles
 //   warp 8      loader: wait free[st]; expect_tx + TMA loads onto full[st]   (cp.async fallback: all 32 lanes copy)
 //   warp 9      issuer: wait conv[st]; 12 MMAs (2 k-steps x 3 passes x 2 GEMMs); tcgen05.commit -> free[st]
-// Accumulators stay in TMEM for the CTA's lifetime and are flushed once with red.global.add.
+// Accumulators stay in TMEM for the CTA's lifetime; the per-CTA partial sums leave through a shared-memory tile and bulk stores.
 constexpr int KC = 16;                                   // samples per chunk = 2 k-steps of 8
 constexpr int N1 = 144, N0 = 48;                         // padded N (128 + bias row, 39 + bias row)
 constexpr int ROWB = KC * 4;                             // 64-byte rows
-constexpr int S_A1 = 0;                                  // dH1^T [128][KC] raw (= hi)
-constexpr int S_B1 = S_A1 + WD * ROWB;                   // [H0^T ; 1 ; 0..] [144][KC]
-constexpr int S_A0 = S_B1 + N1 * ROWB;                   // dH0^T [128][KC]
+constexpr int S_B1 = 0;                                  // [H0^T ; 1 ; 0..] [144][KC] raw (= hi)
+constexpr int S_A0 = S_B1 + N1 * ROWB;                   // dH0^T [128][KC] landing tile (read by the A0 converters)
 constexpr int S_B0 = S_A0 + WD * ROWB;                   // [X^T(39) ; 1 ; 0..] [48][KC]  (k_x row 39 holds the ones)
 constexpr int S_H1 = S_B0 + N0 * ROWB;                   // H1^T [128][KC] raw, CUDA-core dW2
 constexpr int S_G = S_H1 + WD * ROWB;                    // logit gradients [KC][3] (192 B), then at +256 the h1 ReLU mask words [4][KC]
 constexpr int S_M = S_G + 256;
 constexpr int STAGE = S_G + 512;                         // one raw stage (what TMA fills)
-constexpr int NSTAGE = 4;
-// lo tiles (same order / offsets as the first four raw tiles) only live between the converters and the MMAs of one chunk:
-// two sets, alternating by chunk parity, instead of one per stage -> a fourth stage of loads in flight fits
-constexpr int LO_A1 = 0, LO_B1 = LO_A1 + WD * ROWB, LO_A0 = LO_B1 + N1 * ROWB, LO_B0 = LO_A0 + WD * ROWB;
+constexpr int NSTAGE = 6;
+// lo tiles of the B operands only live between the converters and the MMAs of one chunk: two sets, alternating by chunk parity
+constexpr int LO_B1 = 0, LO_B0 = LO_B1 + N1 * ROWB;
 constexpr int LOSET = LO_B0 + N0 * ROWB;
 constexpr int S_LOSETS = NSTAGE * STAGE;
-constexpr int B2_BAR = S_LOSETS + 2 * LOSET;             // full[4], conv[4], free[4] mbarriers + tmem slot
-constexpr int BAR_FULL2 = 0, BAR_CONV2 = 32, BAR_FREE2 = 64, TMEM_SLOT2 = 96;
-constexpr int S_W2 = B2_BAR + 128;                       // W2 [3][128] fp32 (dH1 is recomputed here, not read from HBM)
+constexpr int B2_BAR = S_LOSETS + 2 * LOSET;             // full[6], conv[6], free[6] mbarriers + tmem slot
+constexpr int BAR_FULL2 = 0, BAR_CONV2 = 64, BAR_FREE2 = 128, TMEM_SLOT2 = 192;
+constexpr int S_W2 = B2_BAR + 256;                       // W2 [3][128] fp32
 constexpr int B2_TOTAL = S_W2 + 3 * WD * 4;
-constexpr uint32_t ACC1 = 0, ACC0 = 144;                 // TMEM columns of the two accumulators (256 allocated)
+// TMEM: the two accumulators, then two sets of A operand columns (chunk parity): dH1 hi, dH1 lo, dH0 hi, dH0 lo, 16 columns each
+constexpr uint32_t ACC1 = 0, ACC0 = 144, ASET = 192, ASET_COLS = 64, A1HI = 0, A1LO = 16, A0HI = 32, A0LO = 48;
 constexpr uint32_t TX_BYTES = 3 * WD * ROWB + 40 * ROWB + KC * 3 * 4 + 4 * KC * 4;   // bytes landing per stage
-static_assert(S_B1 % 512 == 0 && S_A0 % 512 == 0 && S_B0 % 512 == 0 && S_H1 % 512 == 0 && LO_B1 % 512 == 0 &&
-              LO_A0 % 512 == 0 && LO_B0 % 512 == 0 && STAGE % 512 == 0 && LOSET % 512 == 0, "SW64 tiles must start on the 512-byte swizzle period");
+constexpr int N_LO_ITEMS = (WD + 40) * 4;                // 16-byte items of the B tiles that get a lo twin: B1 rows 0..127, B0 rows 0..39
+constexpr int DR_LD = 132;                               // drain staging row stride (floats): 16-byte aligned, float4 stores 4-way = optimal
+static_assert(S_A0 % 512 == 0 && S_B0 % 512 == 0 && S_H1 % 512 == 0 && LO_B0 % 512 == 0 && STAGE % 512 == 0 && LOSET % 512 == 0,
+              "SW64 tiles must start on the 512-byte swizzle period");
 static_assert(B2_TOTAL <= 227 * 1024, "wgrad smem");
+static_assert((128 * DR_LD + 128 * PVDB_NET_DIN) * 4 <= NSTAGE * STAGE, "the drain staging reuses the stage ring");
 
 // byte offset of (row f, 16-byte column k4) inside a K-major SWIZZLE_64B tile with 64-byte rows
 __device__ __forceinline__ uint32_t sw64_off(int f, int k4) { return (uint32_t)(f * ROWB + ((k4 ^ ((f >> 1) & 3)) << 4)); }
@@ -312,6 +323,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
                  "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
+}
+// 16 values of one feature row -> hi / lo columns [col, col + 16) of this thread's TMEM lane
+__device__ __forceinline__ void store_a_cols16(uint32_t lane_addr, uint32_t col_hi, uint32_t col_lo, const float* v) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_tf32(v[c + i], hi[i], lo[i]);
+        tmem_st8(lane_addr + col_hi + c, hi);
+        tmem_st8(lane_addr + col_lo + c, lo);
+    }
 }
 
 struct BwdWgradArgs {
@@ -337,7 +359,6 @@ constexpr int B2_THREADS = 320;
 constexpr int B2_CONV = 256;
 __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradArgs A, const __grid_constant__ WgradMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    pvdb_pdl_wait();
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long t_start = clock64();
     long long t_wait = 0, t_mma = 0, t_lo = 0;
@@ -345,33 +366,41 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
     const uint32_t bars = sbase + B2_BAR;
     const uint32_t bar_full = bars + BAR_FULL2, bar_conv = bars + BAR_CONV2, bar_free = bars + BAR_FREE2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B2_BAR + TMEM_SLOT2);
-    const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
-    const int64_t n_chunks = (M + KC - 1) / KC;
-    // contiguous chunk range of this CTA (sequential HBM addresses per array)
-    const int64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
-    const int64_t ch_lo = min(n_chunks, (int64_t)blockIdx.x * per), ch_hi = min(n_chunks, ch_lo + per);
-    const int n_it = (int)(ch_hi - ch_lo);
-    // constant parts of every stage: zero everything once, then the bias "ones" row of B1 (k = all samples; rows of A are
-    // zero for samples past M, so the padding contributes nothing)
-    for (int e = tid; e < B2_BAR / 16; e += B2_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    if (tid < NSTAGE * KC) {
-        const int st = tid / KC, k = tid % KC;
-        *reinterpret_cast<float*>(smem + st * STAGE + S_B1 + 128 * ROWB + k * 4) = 1.0f;
+    // Constant parts of the operand tiles (nothing here depends on the kernel before: it runs ahead of the PDL wait).  Every
+    // other byte of a stage / lo set is rewritten per chunk (TMA fills whole tiles, the producers zero rows past M):
+    //   B1 rows 128..143: the bias "ones" row (k = all samples; rows of A are zero past M, so padding adds nothing), then zeros
+    //   B0 rows 40..47: zeros (row 39 of k_x holds the ones); the same rows of the lo sets: zeros (lo(1) = 0)
+    for (int e = tid; e < NSTAGE * 24 * KC; e += B2_THREADS) {
+        const int st = e / (24 * KC), r = (e / KC) % 24, k = e % KC;
+        unsigned char* base = smem + st * STAGE;
+        if (r < 16) *reinterpret_cast<float*>(base + S_B1 + (128 + r) * ROWB + k * 4) = r == 0 ? 1.0f : 0.f;
+        else *reinterpret_cast<float*>(base + S_B0 + (40 + r - 16) * ROWB + k * 4) = 0.f;
     }
-    for (int e = tid; e < 3 * WD; e += B2_THREADS) reinterpret_cast<float*>(smem + S_W2)[e] = __ldg(A.w2 + e);
+    for (int e = tid; e < 2 * 24 * KC; e += B2_THREADS) {
+        const int ls = e / (24 * KC), r = (e / KC) % 24, k = e % KC;
+        unsigned char* base = smem + S_LOSETS + ls * LOSET;
+        if (r < 16) *reinterpret_cast<float*>(base + LO_B1 + (128 + r) * ROWB + k * 4) = 0.f;
+        else *reinterpret_cast<float*>(base + LO_B0 + (40 + r - 16) * ROWB + k * 4) = 0.f;
+    }
     if (tid == 0)
         for (int st = 0; st < NSTAGE; ++st) {
             mbar_init(bar_full + 8 * st, A.use_tma ? 1 : 32);
             mbar_init(bar_conv + 8 * st, B2_CONV);
             mbar_init(bar_free + 8 * st, 1);
         }
-    if (warp == 0) tmem_alloc(sbase + B2_BAR + TMEM_SLOT2, 256);
+    if (warp == 0) tmem_alloc(sbase + B2_BAR + TMEM_SLOT2, 512);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pvdb_pdl_wait();
+    const int64_t M = min((int64_t)A.counters[CNT_M_KEEP], A.cap_keep);
+    const int64_t n_chunks = (M + KC - 1) / KC;
+    // contiguous chunk range of this CTA (sequential HBM addresses per array)
+    const int64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const int64_t ch_lo = min(n_chunks, (int64_t)blockIdx.x * per), ch_hi = min(n_chunks, ch_lo + per);
+    const int n_it = (int)(ch_hi - ch_lo);
     float w2acc[3] = {0.f, 0.f, 0.f};
     float gs[3] = {0.f, 0.f, 0.f};
     if (tid == 0) { WG_T(0, t_start); WG_T(1, clock64()); WG_T(2, (long long)n_it); }
@@ -385,20 +414,19 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
                 { const long long t0 = clock64(); mbar_wait(bar_conv + 8 * st, (it / NSTAGE) & 1); t_wait += clock64() - t0; }
                 tc_fence_after();
                 const uint32_t base = sbase + st * STAGE, lob = sbase + S_LOSETS + (it & 1) * LOSET;
+                const uint32_t aset = tmem + ASET + (uint32_t)(it & 1) * ASET_COLS;
                 const uint32_t acc = it > 0 ? 1u : 0u;
-                const uint64_t a1h = make_desc_sw64(base + S_A1), a1l = make_desc_sw64(lob + LO_A1);
                 const uint64_t b1h = make_desc_sw64(base + S_B1), b1l = make_desc_sw64(lob + LO_B1);
-                const uint64_t a0h = make_desc_sw64(base + S_A0), a0l = make_desc_sw64(lob + LO_A0);
                 const uint64_t b0h = make_desc_sw64(base + S_B0), b0l = make_desc_sw64(lob + LO_B0);
 #pragma unroll
                 for (int ks = 0; ks < KC / 8; ++ks) {
                     const uint64_t adv = (uint64_t)(ks * 32) >> 4;   // 8 tf32 = 32 bytes along the swizzled row
-                    umma_tf32_ss(tmem + ACC1, a1h + adv, b1h + adv, id1, ks == 0 ? acc : 1u);
-                    umma_tf32_ss(tmem + ACC1, a1l + adv, b1h + adv, id1, 1u);
-                    umma_tf32_ss(tmem + ACC1, a1h + adv, b1l + adv, id1, 1u);
-                    umma_tf32_ss(tmem + ACC0, a0h + adv, b0h + adv, id0, ks == 0 ? acc : 1u);
-                    umma_tf32_ss(tmem + ACC0, a0l + adv, b0h + adv, id0, 1u);
-                    umma_tf32_ss(tmem + ACC0, a0h + adv, b0l + adv, id0, 1u);
+                    umma_tf32_ts(tmem + ACC1, aset + A1HI + ks * 8, b1h + adv, id1, ks == 0 ? acc : 1u);
+                    umma_tf32_ts(tmem + ACC1, aset + A1LO + ks * 8, b1h + adv, id1, 1u);
+                    umma_tf32_ts(tmem + ACC1, aset + A1HI + ks * 8, b1l + adv, id1, 1u);
+                    umma_tf32_ts(tmem + ACC0, aset + A0HI + ks * 8, b0h + adv, id0, ks == 0 ? acc : 1u);
+                    umma_tf32_ts(tmem + ACC0, aset + A0LO + ks * 8, b0h + adv, id0, 1u);
+                    umma_tf32_ts(tmem + ACC0, aset + A0HI + ks * 8, b0l + adv, id0, 1u);
                 }
                 umma_commit(bar_free + 8 * st);
             }
@@ -452,8 +480,11 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
         }
         if (t == 0) { WG_T(5, t_wait); WG_T(6, clock64()); }
     } else {
-        // ---------------- converters: lo = x - trunc(x) for the four MMA operand tiles; dW2 / db2 on the CUDA cores
-        const int f2 = tid - 128;                                  // warps 4-7: the dW2 feature of this thread
+        // ---------------- converters
+        const int role = warp >> 2;                                  // 0: dH1 rows (computed), 1: dH0 rows (landed) + dW2
+        const int j = (warp & 3) * 32 + (tid & 31);                  // feature row = TMEM lane (warp w: quarter w % 4)
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const float w2j0 = __ldg(A.w2 + j), w2j1 = __ldg(A.w2 + WD + j), w2j2 = __ldg(A.w2 + 2 * WD + j);
         for (int it = 0; it < n_it; ++it) {
             const int st = it % NSTAGE;
             { const long long t0 = clock64(); mbar_wait(bar_full + 8 * st, (it / NSTAGE) & 1); t_wait += clock64() - t0; }
@@ -473,57 +504,57 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
                                                : reinterpret_cast<const char*>(A.k_x + ch * (40 * KC)) + (tid - 192) * 128;
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
             }
-            // this lo set was last read by the MMAs of chunk it-2
-            if (it >= 2) { const long long t0 = clock64(); mbar_wait(bar_free + 8 * ((it - 2) % NSTAGE), ((it - 2) / NSTAGE) & 1); t_lo += clock64() - t0; }
-            // 1696 16-byte items: A1 512 (COMPUTED: dH1 = [h1 > 0] (g . W2), from the 16 x 3 logit gradients, W2 and the mask
-            // words — a fifth of the HBM reads of this kernel and half of the activation-gradient kernel's writes go away),
-            // B1 512 (rows 0..127), A0 512, B0 160 (rows 0..39).  All loads first (the two converter warps of a scheduler cannot
-            // hide shared-memory latency by themselves), then lo = x - trunc(x), then the stores.  The raw tiles are the hi
-            // operands as they are: async-copied data tracked by the mbarrier needs no proxy fence.
-            float4 v[7];
-            {
-                const float* sW2 = reinterpret_cast<const float*>(smem + S_W2);
-                const uint32_t* sM = reinterpret_cast<const uint32_t*>(sb + S_M);
+            // this lo set and this set of A columns were last read by the MMAs of chunk it-2
+            if (it >= 2) { const long long t0 = clock64(); mbar_wait(bar_free + 8 * ((it - 2) % NSTAGE), ((it - 2) / NSTAGE) & 1); t_lo += clock64() - t0; tc_fence_after(); }
+            const uint32_t aset = ASET + (uint32_t)(it & 1) * ASET_COLS;
+            // All shared-memory loads first (a scheduler's two converter warps cannot hide the latency by themselves), then the
+            // arithmetic, then the stores.  The raw B tiles are the hi operands as they are: async-copied data tracked by the
+            // mbarrier needs no proxy fence.
+            float4 vl[3];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int e = tid + q * B2_CONV, f = e >> 2, k4 = (e & 3) ^ ((f >> 1) & 3);   // physical column -> sample group
-                    const float w0 = sW2[f], w1 = sW2[WD + f], w2 = sW2[2 * WD + f];
-                    const float4 ga = *reinterpret_cast<const float4*>(sb + S_G + k4 * 48), gb = *reinterpret_cast<const float4*>(sb + S_G + k4 * 48 + 16),
-                                 gc = *reinterpret_cast<const float4*>(sb + S_G + k4 * 48 + 32);
-                    const uint4 mw = *reinterpret_cast<const uint4*>(sM + (f >> 5) * KC + k4 * 4);
-                    const int bit = f & 31;
-                    v[q].x = (mw.x >> bit) & 1u ? fmaf(ga.z, w2, fmaf(ga.y, w1, ga.x * w0)) : 0.f;
-                    v[q].y = (mw.y >> bit) & 1u ? fmaf(gb.y, w2, fmaf(gb.x, w1, ga.w * w0)) : 0.f;
-                    v[q].z = (mw.z >> bit) & 1u ? fmaf(gc.x, w2, fmaf(gb.w, w1, gb.z * w0)) : 0.f;
-                    v[q].w = (mw.w >> bit) & 1u ? fmaf(gc.w, w2, fmaf(gc.z, w1, gc.y * w0)) : 0.f;
-                    *reinterpret_cast<float4*>(sb + S_A1 + e * 16) = v[q];
+            for (int q = 0; q < 3; ++q) {      // items 0..511: B1 rows 0..127; 512..671: B0 rows 0..39 (item = 16 bytes, physical position)
+                const int u = tid + q * B2_CONV;
+                if (u < N_LO_ITEMS) vl[q] = *reinterpret_cast<const float4*>(sb + (u < 512 ? S_B1 + u * 16 : S_B0 + (u - 512) * 16));
+            }
+            float4 g4[12];      // the [16][3] logit-gradient tile (broadcast reads)
+#pragma unroll
+            for (int q = 0; q < 12; ++q) g4[q] = *reinterpret_cast<const float4*>(sb + S_G + q * 16);
+            const float* g = reinterpret_cast<const float*>(g4);
+            float a[16];
+            float4 h[4];
+            if (role == 0) {
+                // dH1[s][j] = [h1[s][j] > 0] (g[s] . W2[:, j]) for the 16 samples of the chunk
+                const uint32_t* sM = reinterpret_cast<const uint32_t*>(sb + S_M) + (j >> 5) * KC;
+                uint4 mw[4];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) mw[k4] = *reinterpret_cast<const uint4*>(sM + k4 * 4);
+                const uint32_t* m = reinterpret_cast<const uint32_t*>(mw);
+                const int bit = j & 31;
+#pragma unroll
+                for (int s = 0; s < 16; ++s) a[s] = (m[s] >> bit) & 1u ? fmaf(g[3 * s + 2], w2j2, fmaf(g[3 * s + 1], w2j1, g[3 * s] * w2j0)) : 0.f;
+            } else {
+                // dH0 row j of the landed tile, and the H1 row for dW2
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 v = *reinterpret_cast<const float4*>(sb + S_A0 + sw64_off(j, k4));
+                    a[4 * k4] = v.x; a[4 * k4 + 1] = v.y; a[4 * k4 + 2] = v.z; a[4 * k4 + 3] = v.w;
+                    h[k4] = *reinterpret_cast<const float4*>(sb + S_H1 + sw64_off(j, k4));
                 }
             }
+            store_a_cols16(lane_addr, aset + (role == 0 ? A1HI : A0HI), aset + (role == 0 ? A1LO : A0LO), a);
 #pragma unroll
-            for (int q = 2; q < 7; ++q) {
-                const int e = tid + q * B2_CONV;
-                if (e < 1696) v[q] = *reinterpret_cast<const float4*>(sb + e * 16 + (e >= 1024 ? 1024 : 0));
-            }
-            float4 h[4], g4[12];
-            if (tid >= 128) {   // H1 row of feature f2 (h[k4] = samples 4*k4 .. 4*k4+3) and the whole G tile (broadcast reads)
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) h[k4] = *reinterpret_cast<const float4*>(sb + S_H1 + sw64_off(f2, k4));
-#pragma unroll
-                for (int q = 0; q < 12; ++q) g4[q] = *reinterpret_cast<const float4*>(sb + S_G + q * 16);
-            }
-#pragma unroll
-            for (int q = 0; q < 7; ++q) {
-                const int e = tid + q * B2_CONV;
-                if (e < 1696) {
+            for (int q = 0; q < 3; ++q) {
+                const int u = tid + q * B2_CONV;
+                if (u < N_LO_ITEMS) {
                     float4 l;
-                    l.x = v[q].x - __uint_as_float(__float_as_uint(v[q].x) & 0xffffe000u);
-                    l.y = v[q].y - __uint_as_float(__float_as_uint(v[q].y) & 0xffffe000u);
-                    l.z = v[q].z - __uint_as_float(__float_as_uint(v[q].z) & 0xffffe000u);
-                    l.w = v[q].w - __uint_as_float(__float_as_uint(v[q].w) & 0xffffe000u);
-                    *reinterpret_cast<float4*>(lo + e * 16 + (e >= 1024 ? 1024 : 0)) = l;
+                    l.x = vl[q].x - __uint_as_float(__float_as_uint(vl[q].x) & 0xffffe000u);
+                    l.y = vl[q].y - __uint_as_float(__float_as_uint(vl[q].y) & 0xffffe000u);
+                    l.z = vl[q].z - __uint_as_float(__float_as_uint(vl[q].z) & 0xffffe000u);
+                    l.w = vl[q].w - __uint_as_float(__float_as_uint(vl[q].w) & 0xffffe000u);
+                    *reinterpret_cast<float4*>(lo + (u < 512 ? LO_B1 + u * 16 : LO_B0 + (u - 512) * 16)) = l;
                 }
             }
-            if (tid >= 128) {
+            if (role == 1) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     // samples 4*k4 .. 4*k4+3 occupy floats 12*k4 .. 12*k4+11 of the [16][3] gradient tile = g4[3*k4 .. 3*k4+2]
@@ -537,82 +568,86 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
                 if (tid == 128) {   // db2: sum of the logit gradients of the valid samples
                     const int64_t s0 = (ch_lo + it) * KC;
 #pragma unroll
-                    for (int q = 0; q < 12; ++q) {
-                        const float gq[4] = {g4[q].x, g4[q].y, g4[q].z, g4[q].w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int e = q * 4 + u;          // float e of the tile = (sample e / 3, channel e % 3)
-                            if (s0 + e / 3 < M) gs[e % 3] += gq[u];
-                        }
-                    }
+                    for (int e = 0; e < 48; ++e)          // float e of the tile = (sample e / 3, channel e % 3)
+                        if (s0 + e / 3 < M) gs[e % 3] += g[e];
                 }
             }
+            tmem_st_wait();
+            tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar_conv + 8 * st);
         }
         if (tid == 0) { WG_T(7, t_wait); WG_T(8, clock64()); WG_T(12, t_lo); }
     }
-    // ---- drain and flush: each CTA stores its partial sums (plain stores, net_grad layout); k_wgrad_reduce adds the
-    // gridDim.x partials.  148 CTAs x 22 k red.global.add on the same addresses cost ~16 us; this costs ~1 + 3.
+    // ---- drain and flush: each CTA stores its partial sums (net_grad layout); k_wgrad_reduce adds the gridDim.x partials.
+    // 148 CTAs x 22 k red.global.add on the same addresses cost ~16 us; plain stores straight out of the TMEM lanes (one
+    // 512-byte row per thread, half-used sectors, 39 scalar stores at a 156-byte stride) cost 11 k cycles; now the rows pass
+    // through the (idle) stage ring and leave as one bulk store per row (dW1) / one contiguous block (dW0): 5 k.
     __syncthreads();
     if (tid == 0) WG_T(9, clock64());
     float* P = A.partial + (size_t)blockIdx.x * PART_LD;
     if (n_it == 0) {
         for (int e = tid; e < PART_LD; e += B2_THREADS) P[e] = 0.f;
-    } else {
-        if (tid < B2_CONV) {
-            // all MMAs are complete once the last commit of every stage in use has fired
-            for (int st = 0; st < NSTAGE && st < n_it; ++st) {
-                const int last_it = ((n_it - 1 - st) / NSTAGE) * NSTAGE + st;
-                mbar_wait(bar_free + 8 * st, (last_it / NSTAGE) & 1);
-            }
-            tc_fence_after();
-            if (tid >= 128) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) P[PVDB_NET_OFF_W2 + c * WD + (tid - 128)] = w2acc[c];
-            }
-            if (tid == 128) { P[PVDB_NET_OFF_B2] = gs[0]; P[PVDB_NET_OFF_B2 + 1] = gs[1]; P[PVDB_NET_OFF_B2 + 2] = gs[2]; }
+    } else if (tid < B2_CONV) {
+        // all MMAs are complete once the last commit of every stage in use has fired (then nothing reads the ring any more)
+        for (int st = 0; st < NSTAGE && st < n_it; ++st) {
+            const int last_it = ((n_it - 1 - st) / NSTAGE) * NSTAGE + st;
+            mbar_wait(bar_free + 8 * st, (last_it / NSTAGE) & 1);
         }
-        if (tid < TM) {
-            const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-            const int j = tid;   // accumulator row
-            // dW1[j][0..128) and db1[j] (column 128)
+        tc_fence_after();
+        if (tid >= 128) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) P[PVDB_NET_OFF_W2 + c * WD + (tid - 128)] = w2acc[c];
+        }
+        if (tid == 128) { P[PVDB_NET_OFF_B2] = gs[0]; P[PVDB_NET_OFF_B2 + 1] = gs[1]; P[PVDB_NET_OFF_B2 + 2] = gs[2]; }
+        float* dr1 = reinterpret_cast<float*>(smem);                                   // [128][DR_LD]: dW1 rows
+        float* dr0 = reinterpret_cast<float*>(smem) + 128 * DR_LD;                     // [128 * 39]: dW0, already in the net_grad layout
+        asm volatile("bar.sync 2, %0;" ::"n"(B2_CONV) : "memory");                      // every converter is past its last chunk
+        {
+            // warps w and w+4 share TMEM quarter w%4: thread (row j, half) drains 64 of the 128 dW1 columns; half 0 also db1 and
+            // dW0[j][0..31], half 1 dW0[j][32..38] and db0
+            const int j = (warp & 3) * 32 + (tid & 31), half = warp >> 2;
+            const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < WD; c += 32) {
+            for (int c = half * 64; c < half * 64 + 64; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(lane_addr + ACC1 + c, r);
                 tmem_ld_wait();
-                float4* dst = reinterpret_cast<float4*>(P + PVDB_NET_OFF_W1 + j * WD + c);   // OFF_W1 = 5120: 16-byte aligned rows
+                float4* dst = reinterpret_cast<float4*>(dr1 + j * DR_LD + c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
             }
-            {
-                uint32_t r[8];
-                tmem_ld8(lane_addr + ACC1 + 128, r);
-                tmem_ld_wait();
-                P[PVDB_NET_OFF_B1 + j] = __uint_as_float(r[0]);
-            }
-            // dW0[j][0..39) and db0[j] (column 39)
-            {
-                uint32_t r[32];
+            if (half == 0) {
+                uint32_t r[32], q[8];
                 tmem_ld32(lane_addr + ACC0, r);
+                tmem_ld8(lane_addr + ACC1 + 128, q);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) P[PVDB_NET_OFF_W0 + j * PVDB_NET_DIN + i] = __uint_as_float(r[i]);
+                for (int i = 0; i < 32; ++i) dr0[j * PVDB_NET_DIN + i] = __uint_as_float(r[i]);
+                P[PVDB_NET_OFF_B1 + j] = __uint_as_float(q[0]);
+            } else {
                 uint32_t q[8];
                 tmem_ld8(lane_addr + ACC0 + 32, q);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 7; ++i) P[PVDB_NET_OFF_W0 + j * PVDB_NET_DIN + 32 + i] = __uint_as_float(q[i]);
+                for (int i = 0; i < 7; ++i) dr0[j * PVDB_NET_DIN + 32 + i] = __uint_as_float(q[i]);
                 P[PVDB_NET_OFF_B0 + j] = __uint_as_float(q[7]);
             }
+            fence_async_smem();
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(B2_CONV) : "memory");
+        if (tid < 128) {
+            bulk_s2g(P + PVDB_NET_OFF_W1 + tid * WD, smem_u32(dr1 + tid * DR_LD), WD * 4);
+            if (tid == 0) bulk_s2g(P + PVDB_NET_OFF_W0, smem_u32(dr0), 128 * PVDB_NET_DIN * 4);
+            bulk_commit();
+            bulk_wait0();
         }
     }
     tc_fence_before();
     __syncthreads();
     if (tid == 0) WG_T(10, clock64());
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // net_grad[e] = sum over the CTAs' partials.  32 elements x 8 partial groups per CTA: every thread has all of its ~19 loads

@@ -50,6 +50,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// 1-D bulk async copy shared -> global (TMA engine), tracked by the issuing thread's bulk groups.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }             // writes done
+
 // D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, issued by one thread
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -99,6 +107,39 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ size_t act_off(int64_t s, int f, int nf) {
     return (size_t)(s >> 7) * (size_t)(nf * 128) + (size_t)((s >> 4) & 7) * (size_t)(nf * 16) + (size_t)f * 16 + (size_t)(s & 15);
 }
+
+// Activation stores of the tcgen05 kernels.  One lane (= sample) writing its 32 values of a column group with 32 scalar
+// st.global makes the warp push 128 KB per tile through the SM's store path while it is blocked on it: the stores of the
+// forward alone are 104 MB per step = the L2 slices' whole-chip ingest rate (~6300 B/clk, /opt/skills/guides/B300_MICROARCH.md)
+// for 16 k cycles, and the lane warps sat through all of it (3.3 k of a 9.4 k-cycle tile, measured by leaving the stores out).
+// Staged instead: each lane warp owns a [2 chunks][32 features][16 samples] region of shared memory (chunk stride padded by
+// 16 floats: the two half-warps hit disjoint banks), writes its values there and lane 0 hands the two 2 KB blocks — already in
+// the chunk-major global layout (act_off) — to the TMA engine, which drains them while the warp goes on.
+constexpr int STAGE_CHUNK = 32 * 16 + 16;                 // floats between the two 16-sample chunks of a warp's region
+constexpr int STAGE_WARP_BYTES = 2 * STAGE_CHUNK * 4;     // 4224
+// h[32]: this lane's values for features c .. c+31 of sample s (lane = s & 31); g: tensor base (nf features per sample)
+__device__ __forceinline__ void stage_store32(unsigned char* stage_warp, float* g, int64_t s, int c, int nf, const float* h, bool valid) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) bulk_wait_read0();      // the previous blocks of this warp have left shared memory
+    __syncwarp();
+    float* p = reinterpret_cast<float*>(stage_warp) + (lane >> 4) * STAGE_CHUNK + (lane & 15);
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[i * 16] = h[i];
+    } else {      // rows past M (one partial tile per launch): zeros, the weight-gradient pass reads whole tiles
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[i * 16] = 0.f;
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t src = smem_u32(stage_warp);
+        bulk_s2g(g + act_off(s, c, nf), src, 32 * 16 * 4);
+        bulk_s2g(g + act_off(s + 16, c, nf), src + STAGE_CHUNK * 4, 32 * 16 * 4);
+        bulk_commit();
+    }
+}
+
 
 // ---- operand helpers ----------------------------------------------------------------------------------------
 // 3xTF32 split: hi keeps the 10 explicit tf32 mantissa bits, lo = x - hi is exact in fp32.

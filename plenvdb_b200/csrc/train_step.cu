@@ -1108,7 +1108,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         if (sd) {
             PVDB_CUDA(cudaEventRecord(sd->fork2, st));
             PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));
-            int rc = pvdb_rgbnet_prepare(cfg, b, sd->s);
+            int rc = pvdb_rgbnet_prepare(cfg, b, viewdirs, n_rays, sd->s);
             if (rc) return rc;
             PVDB_CUDA(cudaEventRecord(sd->join2, sd->s));
         }
@@ -1172,7 +1172,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         if (sd) {
             PVDB_CUDA(cudaStreamWaitEvent(st, sd->join2, 0));
         } else {
-            rc = pvdb_rgbnet_prepare(cfg, b, st);
+            rc = pvdb_rgbnet_prepare(cfg, b, viewdirs, n_rays, st);
             if (rc) return rc;
         }
         rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);

@@ -111,6 +111,7 @@ class FusedTrainer:
             self.t["k_mask"] = z(ck, 8, **i32)
             self.t["net_img"] = z(512 * 1024 // 4, **i32)
             self.t["net_partial"] = z(148, 22048, **f32)
+            self.t["ray_pe"] = z(n, 28, **f32)       # view-direction embedding per ray (the forward reads it per kept sample)
         if self.use_tc:   # leaf-local alternative of the k0 gather / scatter (csrc/leaf_local.cu): used only when switched on
             nl = max(topo.n_leaf, 1)
             self.t["ll_cnt"], self.t["ll_off"], self.t["ll_cur"], self.t["ll_list"] = z(nl, **i32), z(nl + 1, **i32), z(nl, **i32), z(nl, **i32)

@@ -26,3 +26,10 @@ for tile in range(5):
     print("tile", tile, "n=%d" % ok.sum(), " ".join("%s=%d" % (n, v) for n, v in zip(names[3:], d)), "total=%d" % d.sum(),
           "start=%d" % (row[ok][:, 2] - buf[ok, 0, 0]).mean())
 print("kernel span cycles (max end - min entry):", buf[:, :, 7].max() - buf[:, 0, 0].min())
+
+for tile in range(5):
+    row = buf[:, tile, :]
+    ok = row[:, 7] > 0
+    if not ok.any(): continue
+    r = row[ok]
+    print("tile", tile, "producer: feat start=%d dur=%d" % ((r[:, 12] - buf[ok, 0, 0]).mean(), (r[:, 13] - r[:, 12]).mean()))
