@@ -46,8 +46,8 @@ constexpr int SM_ONES = SM_W2F + 3 * WD * 4;                // A [128][8]
 constexpr int SM_B1T = SM_ONES + WD * 8 * 4;                // B [128][8]
 constexpr int SM_B2 = SM_B1T + WD * 8 * 4;                  // [4]
 constexpr int IMG_BYTES = SM_B2 + 16;
-constexpr int SM_BAR = IMG_BYTES;   // mbarriers: W, L0, L1, X_RDY, A_RDY[4]; tmem base at +96
-constexpr int BAR_W = 0, BAR_L0 = 8, BAR_L1 = 16, BAR_XRDY = 56, BAR_ARDY = 64, TMEM_SLOT = 96;
+constexpr int SM_BAR = IMG_BYTES;   // mbarriers: W, L0, L1, D0_FREE, X_RDY, A_RDY[4]; tmem base at +96
+constexpr int BAR_W = 0, BAR_L0 = 8, BAR_L1 = 16, BAR_D0FREE = 24, BAR_XRDY = 56, BAR_ARDY = 64, TMEM_SLOT = 96;
 constexpr int SM_RED = SM_BAR + 112;                        // [3][128] partial outputs of the second lane-warp group
 constexpr int SM_STAGE = SM_RED + 3 * 128 * 4;              // activation store staging, one region per lane warp (stage_store32)
 constexpr int SM_TOTAL = SM_STAGE + 8 * STAGE_WARP_BYTES;
@@ -189,6 +189,7 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
         mbar_init(bars + BAR_L0, 1);
         mbar_init(bars + BAR_L1, 1);
         mbar_init(bars + BAR_XRDY, 128);
+        mbar_init(bars + BAR_D0FREE, N_LANE_THREADS);
         for (int c = 0; c < 4; ++c) mbar_init(bars + BAR_ARDY + 8 * c, 128);
         fence_async_smem();
         mbar_expect_tx(bars + BAR_W, IMG_BYTES);
@@ -217,16 +218,18 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
             issue_ksteps(tmem, COL_D0, sbase, SM_W0HI, SM_W0LO, K0P, WD, 0, K0P / 8, true);
             umma_commit(bars + BAR_L0);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
-                for (int c = 0; c < 4; ++c) {
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = (cc >> 1) | ((cc & 1) << 1);      // 0, 2, 1, 3: the order the two column halves deliver their chunks
                     mbar_wait(bars + BAR_ARDY + 8 * c, i & 1);
                     tc_fence_after();
-                    if (c == 0)      // D1 = 1 * hi(b1) + 1 * lo(b1): the layer's k-steps accumulate on top of the bias
+                    if (cc == 0)     // D1 = 1 * hi(b1) + 1 * lo(b1): the layer's k-steps accumulate on top of the bias
                         umma_tf32_ss(tmem + COL_D1, make_desc(sbase + SM_ONES, 8), make_desc(sbase + SM_B1T, 8), make_idesc(WD), 0u);
                     issue_ksteps(tmem, COL_D1, sbase, SM_W1HI, SM_W1LO, WD, WD, c * 4, c * 4 + 4, false);
                 }
                 umma_commit(bars + BAR_L1);
                 if (tile + gridDim.x < n_tiles) {
                     mbar_wait(bars + BAR_XRDY, (i + 1) & 1);
+                    mbar_wait(bars + BAR_D0FREE, i & 1);      // the lane warps read D0 a second time for the activation stores
                     tc_fence_after();
                     issue_ksteps(tmem, COL_D0, sbase, SM_W0HI, SM_W0LO, K0P, WD, 0, K0P / 8, true);
                     umma_commit(bars + BAR_L0);
@@ -270,48 +273,36 @@ __device__ void mlp_tiles(unsigned char* smem, const unsigned char* __restrict__
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
             const int64_t s = tile * TM + lane_s;
             const bool valid = s < M;
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
             TC_T(2);
-            mbar_wait(bars + BAR_L0, par0); par0 ^= 1;
-            tc_fence_after();
-            TC_T(3);
-            // ---- epilogue 0: D0 -> ReLU -> A; layer 1 follows chunk by chunk on the tensor core
-            {
-                uint32_t r[2][32];
-                tmem_ld32(lane_addr + COL_D0 + cb, r[0]);
-                tmem_ld32(lane_addr + COL_D0 + cb + 32, r[1]);
+            // Six phases, ONE copy of the code: the epilogues are ~350 instructions per phase and every launch starts with a cold
+            // instruction cache — unrolled, the first tile of a launch took 23.5 k cycles against 8.5 k for the later ones, a
+            // pure-ALU block 3.0 k against 0.5 k (scratch/tc_timing.py).
+            //   0, 1  D0 chunk -> ReLU -> A: only what layer 1 waits for, so its MMAs start 0.4 k cycles into the tile
+            //   2, 3  D0 chunk again -> ReLU -> mask + staged store of h0, underneath those MMAs; then D0 is handed back
+            //   4, 5  D1 chunk -> ReLU -> mask + staged store of h1 -> 128 -> 3 output layer on the CUDA cores (the next
+            //         tile's layer 0 runs underneath)
+#pragma unroll 1
+            for (int ph = 0; ph < 6; ++ph) {
+                const int c = cb + (ph & 1) * 32;
+                if (ph == 0) { mbar_wait(bars + BAR_L0, par0); par0 ^= 1; tc_fence_after(); TC_T(3); }
+                if (ph == 4) { TC_T(4); mbar_wait(bars + BAR_L1, par1); par1 ^= 1; tc_fence_after(); TC_T(5); TC_T(6); }
+                uint32_t r[32];
+                tmem_ld32(lane_addr + (ph < 4 ? COL_D0 : COL_D1) + c, r);
                 tmem_ld_wait();
+                float h[32];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = cb + j * 32;
-                    float h[32];
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]), 0.f);
+                for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[q]), 0.f);
+                if (ph < 2) {
                     store_a_row(lane_addr, c, h, 32);
                     tmem_st_wait();
                     tc_fence_before();   // (first chunk: also orders the previous tile's D1 reads before the new layer-1 MMAs)
                     mbar_arrive(bars + BAR_ARDY + 8 * (c >> 5));
-                    act(s, valid, 0, c, h, stage);
+                } else {
+                    act(s, valid, ph >> 2, c, h, stage);
+                    if (ph == 3) { tc_fence_before(); mbar_arrive(bars + BAR_D0FREE); }
                 }
-            }
-            TC_T(4);
-            mbar_wait(bars + BAR_L1, par1); par1 ^= 1;
-            tc_fence_after();
-            TC_T(5);
-            TC_T(6);
-            // ---- epilogue 1: D1 -> ReLU -> 128 -> 3 output layer on the CUDA cores (the next tile's layer 0 runs underneath)
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-            {
-                uint32_t r[2][32];
-                tmem_ld32(lane_addr + COL_D1 + cb, r[0]);
-                tmem_ld32(lane_addr + COL_D1 + cb + 32, r[1]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = cb + j * 32;
-                    float h[32];
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) h[q] = fmaxf(__uint_as_float(r[j][q]), 0.f);
-                    act(s, valid, 1, c, h, stage);
+                if (ph >= 4) {
 #pragma unroll
                     for (int q = 0; q < 32; q += 4) {
                         const float4 a = *reinterpret_cast<const float4*>(sw2 + c + q);
@@ -362,6 +353,9 @@ struct TrainFwdArgs {
     const int32_t* counters; int64_t cap_keep;
     const unsigned char* img;
     int feat_ready;   // k_feat already holds the interpolated features (leaf_local.cu): read them instead of gathering
+#ifdef PVDB_TC_TIMING
+    int exp;
+#endif
     const float* ray_pe;   // [n_rays][28]: x[12..39] of every ray (view direction, sin, cos, padding), k_ray_pe; null: computed per sample
 };
 
@@ -447,6 +441,22 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
         float* dst = layer == 0 ? A.k_h0 : A.k_h1;
         if (dst) stage_store32(stage, dst, s - (threadIdx.x & 31), c, WD, h, valid);      // chunk-major (act_off)
     };
+#ifdef PVDB_TC_TIMING
+    if (A.exp) {      // experiment: touch the first tile's store targets ahead of the stores (1: L2 prefetch, 2: loads)
+        const size_t o = (size_t)blockIdx.x * 128 * WD + (size_t)threadIdx.x * 32;
+        if (threadIdx.x < 512 && A.exp == 1) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.k_h0 + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.k_h1 + o));
+        } else if (A.exp >= 3) {      // 3: stagger the CTAs in four phases of ~2000 cycles; 4: eight phases of ~1200
+            const long long t0 = clock64();
+            const long long d = A.exp == 3 ? (blockIdx.x & 3) * 2000 : (blockIdx.x & 7) * 1200;
+            while (clock64() - t0 < d) { }
+        } else if (threadIdx.x < 32 && A.exp == 2) {
+            float v = __ldcg(A.k_h0 + o) + __ldcg(A.k_h1 + o);
+            if (v == 1234.5f) A.k_rgb[0] = v;
+        }
+    }
+#endif
     mlp_tiles(smem, A.img, A.counters + CNT_M_KEEP, A.cap_keep, feat, out, act);
 }
 
@@ -525,6 +535,9 @@ int pvdb_rgbnet_forward_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     A.img = static_cast<const unsigned char*>(b->net_img);
     A.feat_ready = pvdb_leaf_local_enabled(b) ? 1 : 0;
     A.ray_pe = b->ray_pe;
+#ifdef PVDB_TC_TIMING
+    A.exp = getenv("PVDB_EXP") ? atoi(getenv("PVDB_EXP")) : 0;
+#endif
     PVDB_CUDA(pvdb_launch_pdl(k_rgbnet_fwd_tc, dim3(PVDB_SMS), dim3(FWD_THREADS), SM_TOTAL, st, A));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;

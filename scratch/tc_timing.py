@@ -33,3 +33,10 @@ for tile in range(5):
     if not ok.any(): continue
     r = row[ok]
     print("tile", tile, "producer: feat start=%d dur=%d" % ((r[:, 12] - buf[ok, 0, 0]).mean(), (r[:, 13] - r[:, 12]).mean()))
+
+for tile in range(5):
+    row = buf[:, tile, :]
+    ok = row[:, 7] > 0
+    if not ok.any(): continue
+    r = row[ok]
+    print("tile", tile, "ep1 detail: ld+relu=%d act(j=0)=%d fma(j=0)=%d rest=%d" % tuple((r[:, b] - r[:, a]).mean() for a, b in ((6, 8), (8, 9), (9, 10), (10, 7))))
