@@ -52,7 +52,9 @@ __device__ __forceinline__ void store_a_row32(uint32_t tmem_lane, int c0, const 
 //           until the NEXT tile's step 1 has been issued, so the scatter atomics run under that tile's MMAs
 constexpr int B1_BAR = B1_IMG;                          // W, D0, D1, A1_RDY[4], A0_RDY[4]; tmem slot at +88
 constexpr int B1B_W = 0, B1B_D0 = 8, B1B_D1 = 16, B1B_A1 = 24, B1B_A0 = 56, B1_TMEM_SLOT = 88;
-constexpr int B1_TOTAL = B1_BAR + 96;
+constexpr int B1_STAGE = B1_BAR + 96;                   // dH0 store staging, one region per lane warp (stage_store32)
+constexpr int B1_TOTAL = B1_STAGE + 8 * STAGE_WARP_BYTES;
+static_assert(B1_STAGE % 16 == 0 && B1_TOTAL <= 227 * 1024, "activation-gradient smem");
 constexpr uint32_t COL_D0 = 256, COL_D1 = 384;
 constexpr int B1_THREADS = 288, B1_LANES = 256;
 static_assert(B1_IMG % 16 == 0, "bulk copy granularity");
@@ -115,16 +117,18 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
             mbar_wait(bars + B1B_W, 0);
             int i = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
-                for (int c = 0; c < 4; ++c) {
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = (cc >> 1) | ((cc & 1) << 1);      // 0, 2, 1, 3: the order the two column halves deliver their chunks
                     mbar_wait(bars + B1B_A1 + 8 * c, i & 1);
                     tc_fence_after();
-                    issue_b1(tmem, COL_D0, sbase + B1_W1HI, sbase + B1_W1LO, WD, c * 4, c * 4 + 4, c == 0);
+                    issue_b1(tmem, COL_D0, sbase + B1_W1HI, sbase + B1_W1LO, WD, c * 4, c * 4 + 4, cc == 0);
                 }
                 umma_commit(bars + B1B_D0);
-                for (int c = 0; c < 4; ++c) {
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = (cc >> 1) | ((cc & 1) << 1);
                     mbar_wait(bars + B1B_A0 + 8 * c, i & 1);
                     tc_fence_after();
-                    issue_b1(tmem, COL_D1, sbase + B1_W0HI, sbase + B1_W0LO, 16, c * 4, c * 4 + 4, c == 0);
+                    issue_b1(tmem, COL_D1, sbase + B1_W0HI, sbase + B1_W0LO, 16, c * 4, c * 4 + 4, cc == 0);
                 }
                 umma_commit(bars + B1B_D1);
             }
@@ -162,10 +166,14 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
                 const uint32_t mw = jj == 0 ? in.m1a : in.m1b;
                 float d[32];
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int j = c + q;
-                    const float v = fmaf(in.g2, sW2[2 * WD + j], fmaf(in.g1, sW2[WD + j], in.g0 * sW2[j]));
-                    d[q] = (mw >> q) & 1u ? v : 0.f;
+                for (int q = 0; q < 32; q += 4) {
+                    const float4 wa = *reinterpret_cast<const float4*>(sW2 + c + q);
+                    const float4 wb = *reinterpret_cast<const float4*>(sW2 + WD + c + q);
+                    const float4 wc = *reinterpret_cast<const float4*>(sW2 + 2 * WD + c + q);
+                    d[q] = (mw >> q) & 1u ? fmaf(in.g2, wc.x, fmaf(in.g1, wb.x, in.g0 * wa.x)) : 0.f;
+                    d[q + 1] = (mw >> (q + 1)) & 1u ? fmaf(in.g2, wc.y, fmaf(in.g1, wb.y, in.g0 * wa.y)) : 0.f;
+                    d[q + 2] = (mw >> (q + 2)) & 1u ? fmaf(in.g2, wc.z, fmaf(in.g1, wb.z, in.g0 * wa.z)) : 0.f;
+                    d[q + 3] = (mw >> (q + 3)) & 1u ? fmaf(in.g2, wc.w, fmaf(in.g1, wb.w, in.g0 * wa.w)) : 0.f;
                 }
                 store_a_row32(lane_addr, c, d);
                 tmem_st_wait();
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
                 // dH1 is not stored: the weight-gradient pass recomputes it from g, W2 and the mask bits
             }
         };
+        unsigned char* stage = smem + B1_STAGE + warp * STAGE_WARP_BYTES;
         uint32_t par0 = 0, par1 = 0;
         In cur = fetch(blockIdx.x);
         mbar_wait(bars + B1B_W, 0);
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
                 tmem_ld32(lane_addr + COL_D0 + cb + 32, r[1]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
+                for (int jj = 0; jj < 2; ++jj) {      // what dX waits for first: both chunks of the A operand
                     const int c = cb + jj * 32;
                     const uint32_t mw = jj == 0 ? cur.m0a : cur.m0b;
                     float d[32];
@@ -201,9 +210,15 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(bars + B1B_A0 + 8 * (c >> 5));
-                    float* o = A.k_dh0 + act_off(s, c, WD);
+                }
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) o[q * 16] = d[q];
+                for (int jj = 0; jj < 2; ++jj) {      // then dH0 for the weight-gradient pass, underneath the dX MMAs (rows past M: masks are 0)
+                    const int c = cb + jj * 32;
+                    const uint32_t mw = jj == 0 ? cur.m0a : cur.m0b;
+                    float d[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) d[q] = (mw >> q) & 1u ? __uint_as_float(r[jj][q]) : 0.f;
+                    stage_store32(stage, A.k_dh0, s - (tid & 31), c, WD, d, true);
                 }
             }
             // every lane has drained D0 before any lane lets the issuer start the next tile's dH0 MMAs
@@ -244,6 +259,7 @@ __global__ void __launch_bounds__(B1_THREADS, 1) k_rgbnet_bwd_act_tc(BwdActArgs 
             }
             cur = nxt;
         }
+        if ((tid & 31) == 0) bulk_wait0();      // this warp's dH0 blocks are in global memory before the kernel ends
     }
     tc_fence_before();
     __syncthreads();
