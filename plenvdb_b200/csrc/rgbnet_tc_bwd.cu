@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "ray_math.cuh"
 #include "rgbnet.cuh"
 #include "tc_ptx.cuh"
 #include "dp_exchange.cuh"
@@ -670,7 +671,8 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
 // in flight at once (one latency), 128-byte coalesced across the 32 elements.
 // DP (push.world > 1): the sums also go straight into every rank's netx[parity][this rank] over NVLink and the last CTA
 // signals C — the rgbnet-gradient exchange of the data-parallel step has no kernel of its own (dp_exchange.cu).
-__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad, PvdbDpNetPush push) {
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad, PvdbDpNetPush push,
+                                                      PvdbNetAdam adam) {
     __shared__ float red[8][32];
     __shared__ bool last;
     pvdb_pdl_wait();
@@ -691,7 +693,14 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
         float t = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
-        net_grad[e] += t;      // accumulating, like the grid gradients (the rgbnet Adam clears what it consumed)
+        if (adam.on) {         // single GPU, update phase: the rgbnet Adam right here (what k_update_fused's trailing CTAs do otherwise)
+            const float g = net_grad[e] + t;
+            pvdb_dense_adam_update(adam.net[e], adam.m[e], adam.v[e], g, 1.f, false, adam.scalars ? __ldg(adam.scalars + 2) : adam.stepsize, adam.b0, adam.b1,
+                                   adam.eps);
+            net_grad[e] = 0.f;
+        } else {
+            net_grad[e] += t;      // accumulating, like the grid gradients (the rgbnet Adam clears what it consumed)
+        }
         if (push.world > 1) {
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -777,7 +786,8 @@ int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs
 }
 
 // B2: weight gradients -> net_grad (accumulated)
-int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st, const PvdbDpNetPush* dp_push) {
+int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st, const PvdbDpNetPush* dp_push,
+                                  const PvdbNetAdam* adam) {
     if (int rc = bwd_attrs()) return rc;
     BwdWgradArgs W;
     W.k_h0 = b->k_h0; W.k_dh0 = b->k_dh0; W.k_x = b->k_x; W.k_h1 = b->k_h1; W.k_glogit = b->k_rgb;
@@ -807,7 +817,10 @@ int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bu
     PVDB_LAUNCH_CHECK();
     PvdbDpNetPush push = {};
     if (dp_push) push = *dp_push;
-    PVDB_CUDA(pvdb_launch_pdl(k_wgrad_reduce, dim3((PVDB_NET_N + 31) / 32), dim3(256), 0, st, (const float*)b->net_partial, (int)PVDB_SMS, b->net_grad, push));
+    PvdbNetAdam ad = {};
+    if (adam) ad = *adam;
+    PVDB_CHECK_ARG(!(ad.on && push.world > 1), "the fused rgbnet Adam is the single-GPU path (data parallel: the Adam CTAs sum the ranks' pushes)");
+    PVDB_CUDA(pvdb_launch_pdl(k_wgrad_reduce, dim3((PVDB_NET_N + 31) / 32), dim3(256), 0, st, (const float*)b->net_partial, (int)PVDB_SMS, b->net_grad, push, ad));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

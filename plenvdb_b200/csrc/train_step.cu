@@ -549,30 +549,34 @@ struct CompositeParams {
     int64_t cap_keep;
     int do_backward;
 };
+// Eight lanes per ray (a fine-stage ray keeps ~10 samples: with a warp per ray two thirds of the lanes idled through ~430
+// instructions of per-ray scalar work, 3.5 M warp instructions per step).
+constexpr int CG = 8;
 __global__ void __launch_bounds__(256) k_composite(CompositeParams C, int n_rays) {
     pvdb_pdl_wait();
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) / CG;
+    const int lane = threadIdx.x & 31, sub = threadIdx.x & (CG - 1);
+    const bool live = r < n_rays;      // whole groups; every lane of the warp takes part in the shuffles below
     float l_mse = 0, l_ent = 0, l_per = 0;
-    if (r < n_rays) {
-        const int64_t b = C.off_keep[r], e = min((int64_t)C.off_keep[r + 1], C.cap_keep);
+    {
+        const int b = live ? C.off_keep[r] : 0, e = live ? (int)min((int64_t)C.off_keep[r + 1], C.cap_keep) : 0;
         float acc[3] = {0, 0, 0};
-        for (int64_t s = b + lane; s < e; s += 32) {
+        for (int s = b + sub; s < e; s += CG) {
             const float w = C.s_weight[C.k_sample[s]];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) acc[c] += w * C.k_rgb[s * 3 + c];
+            for (int c = 0; c < 3; ++c) acc[c] += w * C.k_rgb[(size_t)s * 3 + c];
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int o = 16; o; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-        const float ail = C.alphainv_last[r];
+            for (int o = CG / 2; o; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        const float ail = live ? C.alphainv_last[r] : 0.5f;
         float tg[3], gm[3], gsum = 0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            tg[c] = C.target ? __ldg(C.target + r * 3 + c) : 0.f;
+            tg[c] = C.target && live ? __ldg(C.target + r * 3 + c) : 0.f;
             const float m = acc[c] + ail * C.bg;
-            if (lane == 0) C.rgb_marched[r * 3 + c] = m;
+            if (sub == 0 && live) C.rgb_marched[r * 3 + c] = m;
             const float df = m - tg[c];
             l_mse += df * df;
             gm[c] = C.w_main * 2.0f * df * C.inv_N * (1.0f / 3.0f);
@@ -584,27 +588,33 @@ __global__ void __launch_bounds__(256) k_composite(CompositeParams C, int n_rays
         if (C.do_backward) {
             float ge = 0.f;
             if (C.w_ent > 0.f && ail >= 1e-6f && ail <= 1.0f - 1e-6f) ge = C.w_ent * (-(logf(ail) - logf(1.0f - ail))) * C.inv_N;
-            if (lane == 0) C.grad_last[r] = gsum * C.bg + ge;
+            if (sub == 0 && live) C.grad_last[r] = gsum * C.bg + ge;
         }
-        for (int64_t s = b + lane; C.target && s < e; s += 32) {
+        for (int s = b + sub; C.target && s < e; s += CG) {
             const float w = C.s_weight[C.k_sample[s]];
             float gw = 0, per = 0;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float col = C.k_rgb[s * 3 + c];
+                const float col = C.k_rgb[(size_t)s * 3 + c];
                 const float dc = col - tg[c];
                 per += dc * dc;
                 if (C.do_backward) {
                     const float grgb = w * gm[c] + C.w_per * 2.0f * dc * w * C.inv_N;
-                    C.k_rgb[s * 3 + c] = grgb * col * (1.0f - col);
+                    C.k_rgb[(size_t)s * 3 + c] = grgb * col * (1.0f - col);
                     gw += col * gm[c];
                 }
             }
             l_per += per * w;
             if (C.do_backward) C.k_gw[s] = gw;
         }
+        // warp sums: the per-ray terms count once per group (lane sub 0 of a live group), the per-sample term on every lane
+        if (sub != 0 || !live) { l_mse = 0.f; l_ent = 0.f; }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) l_per += __shfl_xor_sync(0xffffffffu, l_per, o);
+        for (int o = 16; o; o >>= 1) {
+            l_mse += __shfl_xor_sync(0xffffffffu, l_mse, o);
+            l_ent += __shfl_xor_sync(0xffffffffu, l_ent, o);
+            l_per += __shfl_xor_sync(0xffffffffu, l_per, o);
+        }
     }
     // block reduction of the three loss sums -> one atomic per CTA
     __shared__ float red[3][8];
@@ -1192,7 +1202,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         C.alphainv_last = b->alphainv_last; C.target = target; C.rgb_marched = b->rgb_marched; C.grad_last = b->grad_last;
         C.loss = b->loss; C.cta_done = b->counters + CNT_CTA_DONE; C.bg = cfg->bg; C.w_main = cfg->weight_main; C.w_ent = cfg->weight_entropy_last;
         C.w_per = cfg->weight_rgbper; C.inv_N = 1.0f / (float)n_glob; C.cap_keep = b->cap_keep; C.do_backward = do_bwd ? 1 : 0;
-        PVDB_CUDA(pvdb_launch_pdl(k_composite, dim3(warp_grid), dim3(256), 0, st, C, n_rays));
+        PVDB_CUDA(pvdb_launch_pdl(k_composite, dim3(pvdb_grid_for((int64_t)n_rays * CG, 256)), dim3(256), 0, st, C, n_rays));
         PVDB_LAUNCH_CHECK();
         pvdb_prof_mark("composite", st);
         stamp(st, 3);
@@ -1239,7 +1249,14 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             // weight-gradient CTA from starting at all.
             PvdbDpNetPush push;
             if (dp_fused) push = pvdb_dp_net_push_args(peers, dp_step);
-            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, dp_fused ? &push : nullptr);
+            // one GPU: the kernel that sums the weight-gradient partials applies the rgbnet Adam to what it has summed
+            const bool adam_in_reduce = do_upd && !peers;
+            PvdbNetAdam nad = {};
+            if (adam_in_reduce) {
+                nad.on = 1; nad.net = b->net; nad.m = b->net_m; nad.v = b->net_v; nad.stepsize = U.net_stepsize; nad.b0 = cfg->beta0; nad.b1 = cfg->beta1;
+                nad.eps = cfg->eps; nad.scalars = b->step_scalars;
+            }
+            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, dp_fused ? &push : nullptr, adam_in_reduce ? &nad : nullptr);
             if (rc) return rc;
             stamp(st, 5);
             PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));
@@ -1265,10 +1282,12 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
                 if (rc) return rc;
             }
             if (do_upd) {
-                if (dp_fused) U.dp = pvdb_dp_net_wait_args(peers, dp_step);
-                rc = launch_update(st, 2);
-                U.dp = PvdbDpNetWait{};
-                if (rc) return rc;
+                if (!adam_in_reduce) {
+                    if (dp_fused) U.dp = pvdb_dp_net_wait_args(peers, dp_step);
+                    rc = launch_update(st, 2);
+                    U.dp = PvdbDpNetWait{};
+                    if (rc) return rc;
+                }
                 update_done = true;
                 stamp(st, 6);
             }
