@@ -84,6 +84,8 @@ __device__ __forceinline__ void store_a_row(uint32_t tmem_lane, int c0, const fl
 
 // Optional phase timing (build with PVDB_EXTRA_NVCC_FLAGS=-DPVDB_TC_TIMING): clock64 stamps of thread 0, first 8 tiles per CTA.
 #ifdef PVDB_TC_TIMING
+__device__ unsigned long long g_tc_gt[PVDB_SMS][2];      // %globaltimer at CTA entry / exit of k_rgbnet_fwd_tc
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ long long g_tc_t[PVDB_SMS][8][16];
 #define TC_T(i) do { if (tid == 0 && tile_no < 8) g_tc_t[blockIdx.x][tile_no][i] = clock64(); } while (0)
 #else
@@ -361,6 +363,9 @@ struct TrainFwdArgs {
 
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
+#ifdef PVDB_TC_TIMING
+    if (threadIdx.x == 0) g_tc_gt[blockIdx.x][0] = gtimer();
+#endif
     auto feat = [&](int64_t s, bool valid, float* x) {
         if (!valid) {   // lanes past M in the last tile: zero input row in HBM (the weight-gradient pass reads whole tiles)
             if (A.k_x) {
@@ -458,6 +463,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_rgbnet_fwd_tc(TrainFwdArgs A
     }
 #endif
     mlp_tiles(smem, A.img, A.counters + CNT_M_KEEP, A.cap_keep, feat, out, act);
+#ifdef PVDB_TC_TIMING
+    if (threadIdx.x == 0) g_tc_gt[blockIdx.x][1] = gtimer();
+#endif
 }
 
 // ---- merged renderer MLP (renderer.cu:83-119): features from the gathered list, PE from the pixel's view direction
@@ -479,8 +487,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs 
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const float v = __fmul_rn(R.vd[a], (float)(1 << k));
-                x[12 + 3 + k + 4 * a] = sinf(v);
-                x[12 + 15 + k + 4 * a] = cosf(v);
+                sincosf(v, &x[12 + 3 + k + 4 * a], &x[12 + 15 + k + 4 * a]);      // one range reduction for both
             }
     };
     auto out = [&](int64_t s, const float* raw) {
@@ -495,6 +502,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_render_mlp_tc(RenderMlpArgs 
 }  // namespace
 
 #ifdef PVDB_TC_TIMING
+extern "C" int pvdb_debug_tc_gt(unsigned long long* out) {
+    PVDB_CUDA(cudaMemcpyFromSymbol(out, g_tc_gt, sizeof(unsigned long long) * PVDB_SMS * 2));
+    return PVDB_OK;
+}
 extern "C" int pvdb_debug_tc_timing(long long* out) {
     PVDB_CUDA(cudaMemcpyFromSymbol(out, g_tc_t, sizeof(long long) * PVDB_SMS * 8 * 16));
     return PVDB_OK;

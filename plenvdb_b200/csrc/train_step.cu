@@ -1184,6 +1184,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         } else {
             rc = pvdb_rgbnet_prepare(cfg, b, viewdirs, n_rays, st);
             if (rc) return rc;
+            pvdb_prof_mark("rgbnet_prep", st);      // per-kernel profiling runs without the side stream: keep the prep kernels out of the forward's time
         }
         rc = pvdb_rgbnet_forward(cfg, b, viewdirs, st);
         if (rc) return rc;

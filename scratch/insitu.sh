@@ -1,7 +1,7 @@
 #!/bin/bash
 # in-situ DRAM traffic per kernel of one training step (no cache flush between kernels, application replay)
 out=$1; shift
-ncu --cache-control none --clock-control none --replay-mode application --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:"k_march|k_scan_counts|k_emit|k_rgbnet|k_composite|k_ray_bwd|k_density|k_update|k_wgrad|k_prep" -s 40 -c 14 --csv --log-file $out python scratch/one_step.py 4 > /dev/null 2>&1
+ncu --cache-control none --clock-control none --replay-mode application --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:"k_march|k_scan_counts|k_emit|k_rgbnet|k_composite|k_ray_bwd|k_density|k_update|k_wgrad|k_prep" -s 39 -c 13 --csv --log-file $out python scratch/one_step.py 4 > /dev/null 2>&1
 python - $out <<'PY'
 import csv,collections,sys
 rows=[l for l in open(sys.argv[1]) if not l.startswith('==')]
