@@ -311,8 +311,7 @@ constexpr int LOSET = LO_B0 + N0 * ROWB;
 constexpr int S_LOSETS = NSTAGE * STAGE;
 constexpr int B2_BAR = S_LOSETS + 2 * LOSET;             // full[6], conv[6], free[6] mbarriers + tmem slot
 constexpr int BAR_FULL2 = 0, BAR_CONV2 = 64, BAR_FREE2 = 128, TMEM_SLOT2 = 192;
-constexpr int S_W2 = B2_BAR + 256;                       // W2 [3][128] fp32
-constexpr int B2_TOTAL = S_W2 + 3 * WD * 4;
+constexpr int B2_TOTAL = B2_BAR + 256;
 // TMEM: the two accumulators, then two sets of A operand columns (chunk parity): dH1 hi, dH1 lo, dH0 hi, dH0 lo, 16 columns each
 constexpr uint32_t ACC1 = 0, ACC0 = 144, ASET = 192, ASET_COLS = 64, A1HI = 0, A1LO = 16, A0HI = 32, A0LO = 48;
 constexpr uint32_t TX_BYTES = 3 * WD * ROWB + 40 * ROWB + KC * 3 * 4 + 4 * KC * 4;   // bytes landing per stage
@@ -378,7 +377,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long t_start = clock64();
-    long long t_wait = 0, t_mma = 0, t_lo = 0;
+    long long t_wait = 0, t_lo = 0;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + B2_BAR;
     const uint32_t bar_full = bars + BAR_FULL2, bar_conv = bars + BAR_CONV2, bar_free = bars + BAR_FREE2;
@@ -447,7 +446,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
                 }
                 umma_commit(bar_free + 8 * st);
             }
-            WG_T(3, t_wait); WG_T(4, clock64()); WG_T(11, t_mma);
+            WG_T(3, t_wait); WG_T(4, clock64());
         }
     } else if (warp == 8) {
         // ---------------- loader

@@ -17,7 +17,7 @@ print("init", (buf[:, 1] - t0).mean())
 print("issuer: wait %d  end %d" % (buf[:, 3].mean(), (buf[:, 4] - t0).mean()))
 print("loader: wait %d  end %d" % (buf[:, 5].mean(), (buf[:, 6] - t0).mean()))
 print("conv:   wait %d  end %d" % (buf[:, 7].mean(), (buf[:, 8] - t0).mean()))
-print("mma exec (issue->commit) %d   conv lo-set wait %d" % (buf[:, 11].mean(), buf[:, 12].mean()))
+print("conv lo-set / A-set wait %d" % buf[:, 12].mean())
 print("drain start %d  flush end %d" % ((buf[:, 9] - t0).mean(), (buf[:, 10] - t0).mean()))
 print("span", buf[:, 10].max() - t0.min())
 print("net_grad abs sum", float(tr.net_grad.abs().sum()))

@@ -71,3 +71,32 @@ def test_tc_forward_with_large_weights(setup):
     assert np.abs(ga - gb).max() <= 3e-5 * np.abs(ga).max()
     ka, kb = a.k0.grad.cpu().numpy(), b.k0.grad.cpu().numpy()
     assert np.abs(ka - kb).max() <= 3e-5 * np.abs(ka).max()
+
+
+def test_per_ray_embedding_table_gives_the_same_bits_as_the_per_sample_evaluation(setup):
+    """pvdb_train_bufs.ray_pe is optional: with it the forward reads the view-direction embedding of a kept sample from the row
+    k_ray_pe wrote for its ray, without it the producers evaluate the 24 sinf / cosf per sample (dvgo.py:354-357) — same
+    expressions, so the rgbnet inputs, activations, colours and every gradient must be the same bits."""
+    scene, net, rays = setup
+    from plenvdb_b200.fused import FusedTrainer, build_scene_grids
+    out = []
+    for with_table in (True, False):
+        den, k0 = build_scene_grids(scene)
+        tr = FusedTrainer(scene, den, k0, scene["mask"], net, rays[0].shape[0], use_tensor_cores=True)
+        if not with_table:
+            tr._bufs.ray_pe = None
+        tr.forward_backward(*[_cu(a) for a in rays])
+        torch.cuda.synchronize()
+        M = tr.counters()["M_keep"]
+        out.append({k: tr.t[k].cpu().numpy().copy() for k in ("k_x", "k_h0", "k_h1", "k_mask", "rgb_marched", "loss")})
+        out[-1]["net_grad"] = tr.net_grad.cpu().numpy().copy()
+        out[-1]["M"] = M
+    a, b = out
+    assert a["M"] == b["M"] > 1000
+    rows = (a["M"] + 127) // 128 * 128
+    for k in ("k_x", "k_h0", "k_h1", "k_mask"):
+        x, y = a[k].reshape(-1)[: rows * a[k].shape[-1]], b[k].reshape(-1)[: rows * b[k].shape[-1]]
+        assert np.array_equal(x, y), k
+    assert np.array_equal(a["rgb_marched"], b["rgb_marched"])
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)      # the loss terms are float atomics over the CTAs: order, not values
+    assert np.array_equal(a["net_grad"], b["net_grad"])      # the weight-gradient sums are deterministic (partials in CTA order)
