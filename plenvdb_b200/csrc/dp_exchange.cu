@@ -196,59 +196,76 @@ __global__ void __launch_bounds__(32) k_dp_wait(pvdb_dp_peers P, uint32_t epoch,
 // Reduce-scatter + all-gather: this rank sums the union leaves it owns (slot % world == rank) over all ranks' planes, in rank
 // order, and stores the sums into every rank's planes.  128 threads: with eight float4 in flight per thread (~100 registers) a
 // 256-thread CTA would not fit next to the persistent weight-gradient CTA it is meant to run under.
+// ITEMS tile elements per thread x at most 8 / ITEMS ranks = eight float4 in flight whatever the world size: one CTA fits on
+// an SM next to the weight-gradient CTA, so the working CTAs should be ONE wave — at N = 2 with one element per thread they
+// were 481 CTAs = 3.3 waves of ~9 us each (peer loads, peer stores, system fence: pure latency), the whole side chain 25 us late.
+template <int ITEMS>
 __global__ void __launch_bounds__(128) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, const int32_t* __restrict__ list, const int32_t* __restrict__ counters,
-                                               int cnt_den) {
+                                               int cnt_den, unsigned long long* __restrict__ dbg) {
+    constexpr int WMAX = 8 / ITEMS;
     pvdb_pdl_wait();
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[25] = globaltimer();
     // this kernel is enqueued behind the kernels that scatter into this rank's planes: they are final (signal B, first CTA)
     if (blockIdx.x == 0 && threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_B, epoch);
     const int n = counters[cnt_den];
+    constexpr int T4 = PVDB_LEAF_VOX * 13 / 4;       // 128 float4 of density + 1536 of k0 per leaf
+    const int mine = n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
+    const int64_t total = (int64_t)mine * T4;
+    const int64_t per = (int64_t)blockDim.x * ITEMS;      // tile elements of one CTA per grid pass
     // The grid is sized for the large case (S512: ~0.5 GB of tiles, five CTAs per SM once the weight-gradient kernel has left);
     // at F160 (74 union leaves, 2 MB) only the first ~120 CTAs have a tile element: the rest leave at once, without waiting for
     // the peers, and only take part in the last-CTA count.
-    {
-        const int mine0 = n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
-        if ((int64_t)blockIdx.x * blockDim.x >= (int64_t)mine0 * (PVDB_LEAF_VOX * 13 / 4) && blockIdx.x != 0) {
-            if (threadIdx.x == 0) {
-                uint32_t* done0 = view(P.base[P.rank], P.n_leaf).done + 1;
-                if (atomicAdd(done0, 1u) == gridDim.x - 1) {      // cannot be the last one unless every working CTA is done: they count after their fences
-                    *done0 = 0;
-                    __threadfence_system();
-                    for (int r = 0; r < P.world; ++r) signal_peer(P, r, SIG_D, epoch);
-                }
+    if ((int64_t)blockIdx.x * per >= total && blockIdx.x != 0) {
+        if (threadIdx.x == 0) {
+            uint32_t* done0 = view(P.base[P.rank], P.n_leaf).done + 1;
+            if (atomicAdd(done0, 1u) == gridDim.x - 1) {      // cannot be the last one unless every working CTA is done: they count after their fences
+                *done0 = 0;
+                __threadfence_system();
+                for (int r = 0; r < P.world; ++r) signal_peer(P, r, SIG_D, epoch);
             }
-            return;
         }
+        return;
     }
     if (threadIdx.x < P.world) wait_peer(P, threadIdx.x, SIG_B, epoch);
     __syncthreads();
-    float4* pd[8];
-    float4* pk[8];
-    for (int r = 0; r < 8; ++r) {
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[26] = globaltimer();
+    float4* pd[WMAX];
+    float4* pk[WMAX];
+#pragma unroll
+    for (int r = 0; r < WMAX; ++r) {
         const Blk b = view(P.base[r < P.world ? r : 0], P.n_leaf);
         pd[r] = reinterpret_cast<float4*>(b.den_grad);
         pk[r] = reinterpret_cast<float4*>(b.k0_grad);
     }
-    constexpr int T4 = PVDB_LEAF_VOX * 13 / 4;       // 128 float4 of density + 1536 of k0 per leaf
-    const int mine = n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
-    const int64_t total = (int64_t)mine * T4;
     // plain loads: the acquire + barrier above orders them after the peers' scatter kernels, and nothing on this GPU has read
     // these peer addresses since the previous step's exchange (another launch)
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(idx / T4), i = (int)(idx - (int64_t)j * T4);
-        const int leaf = list[P.rank + j * P.world];
-        const bool is_den = i < 128;
-        const int64_t off = is_den ? (int64_t)leaf * 128 + i : (int64_t)leaf * 1536 + (i - 128);
-        float4 v[8];
-        #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (r < P.world) v[r] = (is_den ? pd[r] : pk[r])[off];
-        float4 s = v[0];
-        #pragma unroll
-        for (int r = 1; r < 8; ++r)
-            if (r < P.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
-        #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (r < P.world) (is_den ? pd[r] : pk[r])[off] = s;
+    for (int64_t base = (int64_t)blockIdx.x * per; base < total; base += (int64_t)gridDim.x * per) {
+        float4 v[ITEMS][WMAX];
+        int64_t off[ITEMS];
+        bool den[ITEMS], live[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int64_t idx = base + (int64_t)k * blockDim.x + threadIdx.x;
+            live[k] = idx < total;
+            const int j = live[k] ? (int)(idx / T4) : 0, i = live[k] ? (int)(idx - (int64_t)j * T4) : 0;
+            const int leaf = list[P.rank + j * P.world];
+            den[k] = i < 128;
+            off[k] = den[k] ? (int64_t)leaf * 128 + i : (int64_t)leaf * 1536 + (i - 128);
+#pragma unroll
+            for (int r = 0; r < WMAX; ++r)
+                if (r < P.world && live[k]) v[k][r] = (den[k] ? pd[r] : pk[r])[off[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (!live[k]) continue;
+            float4 s = v[k][0];
+#pragma unroll
+            for (int r = 1; r < WMAX; ++r)
+                if (r < P.world) { s.x += v[k][r].x; s.y += v[k][r].y; s.z += v[k][r].z; s.w += v[k][r].w; }
+#pragma unroll
+            for (int r = 0; r < WMAX; ++r)
+                if (r < P.world) (den[k] ? pd[r] : pk[r])[off[k]] = s;
+        }
     }
     // last CTA out tells every peer that this rank's sums are in place (threadFenceReduction pattern with system-wide fences:
     // the stores it publishes are peer stores; the final st.release.sys is cumulative over what the counter made visible)
@@ -261,6 +278,8 @@ __global__ void __launch_bounds__(128) k_dp_rs(pvdb_dp_peers P, uint32_t epoch, 
         if (last) { *done = 0; __threadfence_system(); }
     }
     __syncthreads();
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[27] = globaltimer();
+    if (dbg && last && threadIdx.x == 0) dbg[28] = globaltimer();
     if (last && threadIdx.x < P.world) signal_peer(P, threadIdx.x, SIG_D, epoch);
 }
 
@@ -362,7 +381,7 @@ static void prefer_max_smem(K kernel) { cudaFuncSetAttribute(kernel, cudaFuncAtt
 static void dp_kernel_attrs() {
     static bool done = false;
     if (done) return;
-    prefer_max_smem(k_dp_union); prefer_max_smem(k_dp_rs); prefer_max_smem(k_dp_wait);
+    prefer_max_smem(k_dp_union); prefer_max_smem(k_dp_rs<1>); prefer_max_smem(k_dp_rs<2>); prefer_max_smem(k_dp_rs<4>); prefer_max_smem(k_dp_wait);
     done = true;
 }
 
@@ -382,8 +401,9 @@ static int exchange_tiles(const pvdb_dp_peers* P, const pvdb_train_bufs* b, uint
     if (!do_move) return PVDB_OK;
     // One CTA fits on each SM next to the persistent weight-gradient CTA, five once it has left; CTAs without a tile element
     // leave at once: 74 union leaves = 2 MB at F160 (latency bound, one wave of working CTAs), ~0.5 GB at S512
-    PVDB_CUDA(pvdb_launch_pdl(k_dp_rs, dim3(PVDB_SMS * 5), dim3(128), 0, st, *P, epoch, (const int32_t*)b->den_touched_list,
-                              (const int32_t*)b->counters, CNT_DEN));
+    auto rs = P->world <= 2 ? k_dp_rs<4> : P->world <= 4 ? k_dp_rs<2> : k_dp_rs<1>;
+    PVDB_CUDA(pvdb_launch_pdl(rs, dim3(PVDB_SMS * 5), dim3(128), 0, st, *P, epoch, (const int32_t*)b->den_touched_list,
+                              (const int32_t*)b->counters, CNT_DEN, pvdb_debug_stamps_ptr()));
     PVDB_LAUNCH_CHECK();
     pvdb_prof_mark("dp_rs", st);
     if (wait_sums) {

@@ -27,11 +27,13 @@ int pvdb_rgbnet_backward(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, co
 int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, const float* viewdirs, cudaStream_t st);
 struct PvdbDpNetPush;   // dp_exchange.cuh; nullptr outside a data-parallel step
 // The dense Adam of the 22019 rgbnet parameters (adam_upd_kernel.cu:9-23) applied by the kernel that sums the per-CTA
-// weight-gradient partials, to the element it has just summed: the single-GPU step ends one kernel earlier.  on = 0: the sums
+// weight-gradient partials, to the element it has just summed (data parallel: after the ranks' sums have arrived): the step ends
+// one kernel earlier.  on = 0: the sums
 // are only accumulated into net_grad.
 struct PvdbNetAdam { int on; float *net, *m, *v; float stepsize, b0, b1, eps; const float* scalars; };
+struct PvdbDpNetWait;   // data-parallel step with the Adam in the reduction: the CTAs wait for every rank's pushed sums first
 int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st, const PvdbDpNetPush* dp_push,
-                                  const PvdbNetAdam* adam = nullptr);
+                                  const PvdbNetAdam* adam = nullptr, const PvdbDpNetWait* dp_wait = nullptr);
 
 // Coarse stage (k0_dim == 3, no rgbnet): rgb = sigmoid(k0) (coarse.cu)
 static inline bool pvdb_direct_colour(const pvdb_train_cfg* cfg) { return cfg->k0_dim == 3 && cfg->net_width == 0; }

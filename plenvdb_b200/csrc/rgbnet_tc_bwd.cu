@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) k_rgbnet_bwd_wgrad_tc(BwdWgradA
 // DP (push.world > 1): the sums also go straight into every rank's netx[parity][this rank] over NVLink and the last CTA
 // signals C — the rgbnet-gradient exchange of the data-parallel step has no kernel of its own (dp_exchange.cu).
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int n_part, float* __restrict__ net_grad, PvdbDpNetPush push,
-                                                      PvdbNetAdam adam) {
+                                                      PvdbNetAdam adam, PvdbDpNetWait wait) {
     __shared__ float red[8][32];
     __shared__ bool last;
     pvdb_pdl_wait();
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
         float t = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
-        if (adam.on) {         // single GPU, update phase: the rgbnet Adam right here (what k_update_fused's trailing CTAs do otherwise)
+        if (adam.on && push.world <= 1) {   // single GPU, update phase: the rgbnet Adam right here (what k_update_fused's trailing CTAs do otherwise)
             const float g = net_grad[e] + t;
             pvdb_dense_adam_update(adam.net[e], adam.m[e], adam.v[e], g, 1.f, false, adam.scalars ? __ldg(adam.scalars + 2) : adam.stepsize, adam.b0, adam.b1,
                                    adam.eps);
@@ -715,6 +715,20 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
         }
         __syncthreads();
         if (last && threadIdx.x < push.world) st_release_sys(push.signal[threadIdx.x], push.epoch);
+        if (adam.on) {
+            // Data-parallel update: every rank's sums are in this rank's slots once the C words of all ranks (the own one included)
+            // have reached the epoch; then the rank-ordered sum and the Adam of this CTA's 32 elements.  Every CTA pushes before it
+            // waits and all CTAs of the grid are resident, so the wait cannot starve a peer.
+            if (threadIdx.x < wait.world) wait_epoch(wait.signal + threadIdx.x, wait.epoch, wait.err, 1);
+            __syncthreads();
+            if (g == 0 && e < PVDB_NET_N) {
+                float gs = __ldcg(wait.src + e);
+                for (int r = 1; r < wait.world; ++r) gs += __ldcg(wait.src + (size_t)r * PVDB_DP_NET_PAD + e);
+                pvdb_dense_adam_update(adam.net[e], adam.m[e], adam.v[e], gs, 1.f, false, adam.scalars ? __ldg(adam.scalars + 2) : adam.stepsize, adam.b0,
+                                       adam.b1, adam.eps);
+                net_grad[e] = 0.f;
+            }
+        }
     }
 }
 
@@ -786,7 +800,7 @@ int pvdb_rgbnet_backward_act_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs
 
 // B2: weight gradients -> net_grad (accumulated)
 int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, cudaStream_t st, const PvdbDpNetPush* dp_push,
-                                  const PvdbNetAdam* adam) {
+                                  const PvdbNetAdam* adam, const PvdbDpNetWait* dp_wait) {
     if (int rc = bwd_attrs()) return rc;
     BwdWgradArgs W;
     W.k_h0 = b->k_h0; W.k_dh0 = b->k_dh0; W.k_x = b->k_x; W.k_h1 = b->k_h1; W.k_glogit = b->k_rgb;
@@ -818,8 +832,10 @@ int pvdb_rgbnet_backward_wgrad_tc(const pvdb_train_cfg* cfg, const pvdb_train_bu
     if (dp_push) push = *dp_push;
     PvdbNetAdam ad = {};
     if (adam) ad = *adam;
-    PVDB_CHECK_ARG(!(ad.on && push.world > 1), "the fused rgbnet Adam is the single-GPU path (data parallel: the Adam CTAs sum the ranks' pushes)");
-    PVDB_CUDA(pvdb_launch_pdl(k_wgrad_reduce, dim3((PVDB_NET_N + 31) / 32), dim3(256), 0, st, (const float*)b->net_partial, (int)PVDB_SMS, b->net_grad, push, ad));
+    PvdbDpNetWait wt = {};
+    if (dp_wait) wt = *dp_wait;
+    PVDB_CHECK_ARG(!(ad.on && push.world > 1) || wt.world == push.world, "data-parallel rgbnet Adam in the reduction needs the wait arguments");
+    PVDB_CUDA(pvdb_launch_pdl(k_wgrad_reduce, dim3((PVDB_NET_N + 31) / 32), dim3(256), 0, st, (const float*)b->net_partial, (int)PVDB_SMS, b->net_grad, push, ad, wt));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
 }

@@ -158,6 +158,7 @@ struct MarchOut {
     // data-parallel step only: this rank's touched-leaf flags in its symmetric block (dp_exchange.cu).  The sample lists
     // determine the touched leaves before any gradient exists, so the cross-GPU union runs under the rgbnet forward.
     uint8_t* dp_flags;       // one byte per leaf; plain stores of 1 (idempotent: no atomics, benign races)
+    int dp_words;            // > 0: k_emit_scratch collects the leaves of its CTA in a shared bitmap of this many words first
 };
 
 // Flag the leaves of the eight corners of one alpha-list sample (every such sample feeds the density gradient, the kept ones
@@ -385,41 +386,71 @@ __global__ void __launch_bounds__(256, 4) k_march(MarchParams P, MarchOut O, con
 template <int VAR>
 __global__ void __launch_bounds__(256) k_emit_scratch(MarchParams P, MarchOut O, const float* __restrict__ rays_o,
                                                       const float* __restrict__ rays_d, int n_rays) {
+    // Data-parallel step: the touched-leaf flags of the CTA's eight rays are collected in a shared bitmap and stored once per
+    // leaf and CTA — ~10^4 byte stores per step instead of ~10^5 into the same few 32-byte sectors (the flags of the 74 touched
+    // leaves of the bench batch lie in three), which cost the emit kernel 7 us.
+    extern __shared__ uint32_t s_leafbits[];
     pvdb_pdl_wait();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (r >= n_rays) return;
-    const int na = O.cnt_alpha[r];
-    if (na > O.scr_cap) { march_ray<1, false, VAR & 2>(P, O, rays_o, rays_d, r, lane); return; }
-    const int64_t oa = O.off_alpha[r], ok = O.off_keep[r];
-    int dp_last_leaf = -1;
-    for (int i = lane; i < na; i += 32) {
-        const uint4* e = O.scratch + ((int64_t)r * O.scr_cap + i) * 5;
-        const uint4 e0 = e[0], e1 = e[1], e2 = e[2];
-        const int64_t ia = oa + i;
-        const float x = __uint_as_float(e0.y), y = __uint_as_float(e0.z), z = __uint_as_float(e0.w);
-        if (ia < O.cap_alpha) {
-            O.s_ray[ia] = r; O.s_step[ia] = (int32_t)e0.x;
-            O.s_xyz[ia * 3] = x; O.s_xyz[ia * 3 + 1] = y; O.s_xyz[ia * 3 + 2] = z;
-            O.s_density[ia] = __uint_as_float(e1.x); O.s_alpha[ia] = __uint_as_float(e1.y);
-            O.s_T[ia] = __uint_as_float(e1.z); O.s_weight[ia] = __uint_as_float(e1.w);
-        }
-        const int ki = (int32_t)e2.x;
-        if (VAR & 2) {
-            const uint4 c0 = e[3], c1 = e[4];
-            const int rec[8] = {(int)c0.x, (int)c0.y, (int)c0.z, (int)c0.w, (int)c1.x, (int)c1.y, (int)c1.z, (int)c1.w};
-            dp_flag_corners(O.dp_flags, rec, dp_last_leaf);
-        }
-        if (ki >= 0) {
-            const int64_t ik = ok + ki;
-            if (ik < O.cap_keep && ia < O.cap_alpha) {
-                O.k_sample[ik] = (int32_t)ia; O.k_ray[ik] = r;
-                O.k_xyz[ik * 3] = x; O.k_xyz[ik * 3 + 1] = y; O.k_xyz[ik * 3 + 2] = z;
-                if (O.k_corner) {
-                    uint4* kc = reinterpret_cast<uint4*>(O.k_corner + ik * 8);
-                    kc[0] = e[3];
-                    kc[1] = e[4];
+    const bool bitmap = (VAR & 2) && O.dp_words > 0;
+    if (bitmap) {
+        for (int w = threadIdx.x; w < O.dp_words; w += blockDim.x) s_leafbits[w] = 0u;
+        __syncthreads();
+    }
+    const int na = r < n_rays ? O.cnt_alpha[r] : 0;
+    if (r < n_rays && na > O.scr_cap) {
+        march_ray<1, false, VAR & 2>(P, O, rays_o, rays_d, r, lane);      // flags its leaves in global memory itself
+    } else if (r < n_rays) {
+        const int64_t oa = O.off_alpha[r], ok = O.off_keep[r];
+        int dp_last_leaf = -1;
+        for (int i = lane; i < na; i += 32) {
+            const uint4* e = O.scratch + ((int64_t)r * O.scr_cap + i) * 5;
+            const uint4 e0 = e[0], e1 = e[1], e2 = e[2];
+            const int64_t ia = oa + i;
+            const float x = __uint_as_float(e0.y), y = __uint_as_float(e0.z), z = __uint_as_float(e0.w);
+            if (ia < O.cap_alpha) {
+                O.s_ray[ia] = r; O.s_step[ia] = (int32_t)e0.x;
+                O.s_xyz[ia * 3] = x; O.s_xyz[ia * 3 + 1] = y; O.s_xyz[ia * 3 + 2] = z;
+                O.s_density[ia] = __uint_as_float(e1.x); O.s_alpha[ia] = __uint_as_float(e1.y);
+                O.s_T[ia] = __uint_as_float(e1.z); O.s_weight[ia] = __uint_as_float(e1.w);
+            }
+            const int ki = (int32_t)e2.x;
+            if (VAR & 2) {
+                const uint4 c0 = e[3], c1 = e[4];
+                const int rec[8] = {(int)c0.x, (int)c0.y, (int)c0.z, (int)c0.w, (int)c1.x, (int)c1.y, (int)c1.z, (int)c1.w};
+                if (bitmap) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int leaf = rec[q] >> 9;
+                        if (rec[q] >= 0 && leaf != dp_last_leaf) { atomicOr(&s_leafbits[leaf >> 5], 1u << (leaf & 31)); dp_last_leaf = leaf; }
+                    }
+                } else {
+                    dp_flag_corners(O.dp_flags, rec, dp_last_leaf);
                 }
+            }
+            if (ki >= 0) {
+                const int64_t ik = ok + ki;
+                if (ik < O.cap_keep && ia < O.cap_alpha) {
+                    O.k_sample[ik] = (int32_t)ia; O.k_ray[ik] = r;
+                    O.k_xyz[ik * 3] = x; O.k_xyz[ik * 3 + 1] = y; O.k_xyz[ik * 3 + 2] = z;
+                    if (O.k_corner) {
+                        uint4* kc = reinterpret_cast<uint4*>(O.k_corner + ik * 8);
+                        kc[0] = e[3];
+                        kc[1] = e[4];
+                    }
+                }
+            }
+        }
+    }
+    if (bitmap) {
+        __syncthreads();
+        for (int w = threadIdx.x; w < O.dp_words; w += blockDim.x) {
+            uint32_t bits = s_leafbits[w];
+            while (bits) {
+                const int bpos = __ffs(bits) - 1;
+                bits &= bits - 1;
+                O.dp_flags[w * 32 + bpos] = 1;
             }
         }
     }
@@ -913,7 +944,7 @@ static int fill_march(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, March
     O.counters = b->counters;
     O.scratch = reinterpret_cast<uint4*>(b->march_scratch);
     O.scr_cap = b->march_scratch ? b->scratch_per_ray : 0;
-    O.dp_flags = nullptr;
+    O.dp_flags = nullptr; O.dp_words = 0;
     return 0;
 }
 
@@ -1109,7 +1140,11 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
     // (peer stores) and the rgbnet Adam (wait + rank-ordered sum).  Needs the side stream and the tensor-core backward;
     // otherwise the stand-alone exchange runs after the backward.
     const bool dp_fused = peers && sd && cfg->use_tensor_cores && do_fwd && do_bwd && do_upd;
-    if (dp_fused) O.dp_flags = pvdb_dp_flags_ptr(peers, dp_step);
+    if (dp_fused) {
+        O.dp_flags = pvdb_dp_flags_ptr(peers, dp_step);
+        const int words = (b->tree->n_leaf + 31) / 32;
+        O.dp_words = words * 4 <= 40 * 1024 ? words : 0;      // larger trees flag straight into global memory
+    }
     stamp(st, 0);
 
     bool scan_fused = false;
@@ -1163,7 +1198,7 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
         pvdb_prof_mark("scan", st);
         PVDB_CHECK_ARG(!O.scratch || n_rays <= b->scratch_rays, "march_scratch holds fewer rays than this batch");
         if (O.scratch) {
-            if (O.dp_flags) PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch<2>, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
+            if (O.dp_flags) PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch<2>, dim3(warp_grid), dim3(256), (size_t)O.dp_words * 4, st, P, O, rays_o, rays_d, n_rays));
             else PVDB_CUDA(pvdb_launch_pdl(k_emit_scratch<0>, dim3(warp_grid), dim3(256), 0, st, P, O, rays_o, rays_d, n_rays));
         } else if (O.dp_flags) {
             k_march<1, false, 2><<<warp_grid, 256, 0, st>>>(P, O, rays_o, rays_d, n_rays, nullptr, ScanTail{});
@@ -1250,14 +1285,18 @@ static int train_step_impl(const pvdb_train_cfg* cfg, const pvdb_train_bufs* b, 
             // weight-gradient CTA from starting at all.
             PvdbDpNetPush push;
             if (dp_fused) push = pvdb_dp_net_push_args(peers, dp_step);
-            // one GPU: the kernel that sums the weight-gradient partials applies the rgbnet Adam to what it has summed
-            const bool adam_in_reduce = do_upd && !peers;
+            // the kernel that sums the weight-gradient partials applies the rgbnet Adam to what it has summed (data parallel:
+            // to the rank-ordered sum of what the ranks pushed)
+            const bool adam_in_reduce = do_upd && (!peers || dp_fused);
             PvdbNetAdam nad = {};
             if (adam_in_reduce) {
                 nad.on = 1; nad.net = b->net; nad.m = b->net_m; nad.v = b->net_v; nad.stepsize = U.net_stepsize; nad.b0 = cfg->beta0; nad.b1 = cfg->beta1;
                 nad.eps = cfg->eps; nad.scalars = b->step_scalars;
             }
-            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, dp_fused ? &push : nullptr, adam_in_reduce ? &nad : nullptr);
+            PvdbDpNetWait nwait = {};
+            if (dp_fused && adam_in_reduce) nwait = pvdb_dp_net_wait_args(peers, dp_step);
+            rc = pvdb_rgbnet_backward_wgrad_tc(cfg, b, st, dp_fused ? &push : nullptr, adam_in_reduce ? &nad : nullptr,
+                                               dp_fused && adam_in_reduce ? &nwait : nullptr);
             if (rc) return rc;
             stamp(st, 5);
             PVDB_CUDA(cudaStreamWaitEvent(sd->s, sd->fork2, 0));

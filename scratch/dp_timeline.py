@@ -11,7 +11,7 @@ scene, net, den, k0, tr, (ro, rd, vd, tg) = bench.build_workload(n, dev, seed=77
 mode = sys.argv[1] if len(sys.argv) > 1 else "nvlink"
 dp = pdist.DataParallelTrainer.wrap(tr, world, exchange=mode) if (world > 1 and mode != "none") else None
 step = dp.step if dp else tr.step
-names = {0: "start", 8: "march", 9: "scan", 1: "emit", 2: "fwd", 3: "composite", 4: "bwd_act", 5: "wgrad+red", 6: "net adam", 7: "join", 10: "s:union>", 11: "s:union<", 12: "s:tiles>", 13: "s:tiles<", 14: "s:leafadam", 20: "u:in", 21: "u:pub", 22: "u:sig", 23: "u:waited", 24: "u:out"}
+names = {0: "start", 8: "march", 9: "scan", 1: "emit", 2: "fwd", 3: "composite", 4: "bwd_act", 5: "wgrad+red", 6: "net adam", 7: "join", 10: "s:union>", 11: "s:union<", 12: "s:tiles>", 13: "s:tiles<", 14: "s:leafadam", 20: "u:in", 21: "u:pub", 22: "u:sig", 23: "u:waited", 24: "u:out", 25: "rs:in", 26: "rs:Bwaited", 27: "rs:cta0done", 28: "rs:last"}
 acc = []
 for i in range(n):
     if world > 1:
