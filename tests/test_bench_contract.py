@@ -32,7 +32,7 @@ def test_reference_arm_prints_the_contract_line():
 
 def test_committed_gpu_lines_carry_the_full_contract():
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r01[g-z]_n1*.json")) + glob.glob(os.path.join(ROOT, "profiles", "bench_r02_final_n*.json")) +
-                   glob.glob(os.path.join(ROOT, "profiles", "bench_r02c_n1.json")))
+                   glob.glob(os.path.join(ROOT, "profiles", "bench_r02[cd]_n1.json")))
     assert files, "no bench line of the final state under profiles/"
     for f in files:
         d = _last_json_line(open(f).read())
