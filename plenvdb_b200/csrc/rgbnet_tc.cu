@@ -3,9 +3,10 @@
 // The only dense contraction of the hot path (dvgo.py:99-107, 354-360; renderer.cu:83-109).  One persistent CTA
 // per SM, 128-sample tiles:
 //   * accumulators live in TMEM (128 lanes = 128 samples, 128 fp32 columns);
-//   * the activations never touch shared memory: each of the 128 threads owns one sample = one TMEM lane, reads
-//     the accumulator row with tcgen05.ld, applies bias + ReLU, and writes the next layer's A operand straight
-//     back into TMEM with tcgen05.st (A-from-TMEM form of tcgen05.mma);
+//   * between two layers the activations never touch shared memory: a thread owns one sample = one TMEM lane, reads
+//     its half of the accumulator row with tcgen05.ld, applies the ReLU (the biases are inside the MMAs), and writes the
+//     next layer's A operand straight back into TMEM with tcgen05.st (A-from-TMEM form of tcgen05.mma); the copies the
+//     backward needs leave through per-warp staging regions and bulk async stores;
 //   * the weights stay resident in shared memory for the CTA's lifetime in the canonical K-major (no swizzle)
 //     UMMA layout, read through shared-memory matrix descriptors;
 //   * precision: 3xTF32 error-compensated products (x = hi + lo, D = Ahi*Bhi + Alo*Bhi + Ahi*Blo, fp32 accumulate)

@@ -46,9 +46,10 @@ __device__ __forceinline__ void store_a_row32(uint32_t tmem_lane, int c0, const 
 // Same warp-specialised structure as the forward (rgbnet_tc.cu): 8 lane warps (thread = sample lane x column half), one
 // issuer warp; the weight image (W1^T, W0[:, :12]^T as tf32 hi/lo in the canonical K-major layout + W2 as fp32) is built
 // once per step (prep_bwd_image, run by the forward's prep kernel) and pulled into shared memory with one bulk async copy per CTA.
-//   step 1  dH1 = (g . W2) * [h1 > 0] on the CUDA cores, 32 columns at a time: to HBM (chunk-major, for B2) and into
-//           TMEM as the A operand; the issuer starts the matching k-steps of dH0 = dH1 . W1 (into D0) chunk by chunk
-//   step 2  dH0 = D0 * [h0 > 0]: to HBM and back into TMEM as A; the issuer follows with dX = dH0 . W0[:, :12] (into D1)
+//   step 1  dH1 = (g . W2) * [h1 > 0] on the CUDA cores, 32 columns at a time, into TMEM as the A operand (B2 recomputes it:
+//           it is never stored); the issuer starts the matching k-steps of dH0 = dH1 . W1 (into D0) chunk by chunk
+//   step 2  dH0 = D0 * [h0 > 0]: both chunks back into TMEM as A first — the issuer follows with dX = dH0 . W0[:, :12]
+//           (into D1) —, then to HBM (chunk-major, for B2) through the per-warp staging regions
 //   step 3  dX -> k0 gradient scatter (colorvdb.cu:130-160) with the corner record ids the march saved; it is deferred
 //           until the NEXT tile's step 1 has been issued, so the scatter atomics run under that tile's MMAs
 constexpr int B1_BAR = B1_IMG;                          // W, D0, D1, A1_RDY[4], A0_RDY[4]; tmem slot at +88
