@@ -98,17 +98,20 @@ class FusedTrainer:
             counters=z(16, **i32), loss=z(4, **f32),
         )
         # activations kept for the fp32 rgbnet backward (the tcgen05 forward still pairs with it)
+        # the tcgen05 kernels write and read these tensors in whole 128-sample tiles: rows rounded up to a tile (cap_keep itself
+        # is 64 * n_rays, not a multiple of 128 for an odd batch)
+        ckp = (ck + 127) // 128 * 128
         if self.direct:   # no rgbnet: no activations to keep
             self.t["k_h0"] = self.t["k_h1"] = z(1, **f32)
         else:
-            self.t["k_h0"] = z(ck, 128, **f32)
-            self.t["k_h1"] = z(ck, 128, **f32)
+            self.t["k_h0"] = z(ckp, 128, **f32)
+            self.t["k_h1"] = z(ckp, 128, **f32)
         if self.use_tc or self.direct:
             self.t["k_corner"] = z(ck, 8, **i32)     # record ids of the eight corners, saved by the march
         if self.use_tc:   # tensor-core backward: input rows and masked activation gradients for the weight-gradient GEMM
-            self.t["k_x"] = z(ck, 40, **f32)
-            self.t["k_dh0"] = z(ck, 128, **f32)
-            self.t["k_mask"] = z(ck, 8, **i32)
+            self.t["k_x"] = z(ckp, 40, **f32)
+            self.t["k_dh0"] = z(ckp, 128, **f32)
+            self.t["k_mask"] = z(ckp, 8, **i32)
             self.t["net_img"] = z(512 * 1024 // 4, **i32)
             self.t["net_partial"] = z(148, 22048, **f32)
             self.t["ray_pe"] = z(n, 28, **f32)       # view-direction embedding per ray (the forward reads it per kept sample)

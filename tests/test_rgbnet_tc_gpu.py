@@ -100,3 +100,19 @@ def test_per_ray_embedding_table_gives_the_same_bits_as_the_per_sample_evaluatio
     assert np.array_equal(a["rgb_marched"], b["rgb_marched"])
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)      # the loss terms are float atomics over the CTAs: order, not values
     assert np.array_equal(a["net_grad"], b["net_grad"])      # the weight-gradient sums are deterministic (partials in CTA order)
+
+
+def test_odd_batch_whose_sample_capacity_is_not_a_whole_tile(setup):
+    """cap_keep = 64 * n_rays is not a multiple of the 128-sample tile for an odd batch: the tile-major activation tensors are
+    padded to whole tiles, and the step agrees with the fp32 path as for any other batch."""
+    scene, net, rays = setup
+    n = 1001
+    sub = [a[:n] for a in rays]
+    a, *_ = _run(scene, net, sub, False)
+    b, *_ = _run(scene, net, sub, True)
+    assert a.counters()["M_keep"] == b.counters()["M_keep"] > 500 and b.cap_keep % 128 != 0
+    np.testing.assert_allclose(b.t["rgb_marched"].cpu().numpy(), a.t["rgb_marched"].cpu().numpy(), rtol=1e-5, atol=2e-6)
+    ga, gb = a.net_grad.cpu().numpy(), b.net_grad.cpu().numpy()
+    assert np.abs(ga - gb).max() <= 2e-5 * np.abs(ga).max()
+    ka, kb = a.k0.grad.cpu().numpy(), b.k0.grad.cpu().numpy()
+    assert np.abs(ka - kb).max() <= 2e-5 * np.abs(ka).max()
