@@ -200,7 +200,8 @@ typedef struct pvdb_train_bufs {
     int32_t *k_sample /* index into the alpha list */, *k_ray;
     float *k_xyz /*[.][3]*/, *k_feat /*[.][12]*/, *k_rgb /*[.][3] rgb, then dL/dlogit*/, *k_gw /*[.] dL/dweight*/;
     float *k_h0, *k_h1;                        /* post-ReLU activations kept for the backward: [.][128] row-major (fp32 path) or
-                                                * chunk-major [tile][8 chunks][128 features][16 samples] (tensor-core path) */
+                                                * chunk-major [tile][8 chunks][128 features][16 samples] (tensor-core path; the tile-major
+                                                * tensors k_h0, k_h1, k_x, k_dh0, k_mask hold cap_keep ROUNDED UP to 128 rows: whole tiles are written) */
     float *k_x;                                /* chunk-major [tile][8][40][16] rgbnet inputs (12 k0 + 27 PE + a ones row), tensor-core path */
     float *k_dh0, *k_dh1;                      /* k_dh0: chunk-major [tile][8][128][16] masked activation gradient of layer 0 (tensor-core
                                                 * backward); k_dh1 is unused (the weight-gradient pass recomputes dH1), may be NULL */
